@@ -1,0 +1,74 @@
+// Device-resident Gauss-Newton loop: host-visible declarations (see gn_kernel.cu).
+#pragma once
+#include "odom_internal.hpp"
+
+namespace slam {
+
+constexpr int kGnThreads = 512;
+constexpr int kGnMaxCtas = 256;        // >= SM count of any target part (B200: 148)
+constexpr int kGnPartialStride = 64;   // floats per CTA per buffer: [0..31] phase A, [32..63] phase B
+constexpr int kGnMaxTrace = 64;        // step records kept per sequence
+
+// Per-sequence inputs of one launch; refreshed by ONE host->device copy per launch (the
+// image pointers change when the reference swaps lastNextImage/nextImage, and the prior
+// pose comes from the caller).
+struct GnSeqIn
+{
+    const float * vcurr[SLAM_MAX_LEVELS];
+    const float * ncurr[SLAM_MAX_LEVELS];
+    const float * vprev[SLAM_MAX_LEVELS];
+    const float * nprev[SLAM_MAX_LEVELS];
+    const float * lastDepth[SLAM_MAX_LEVELS];
+    const float * nextDepth[SLAM_MAX_LEVELS];
+    const unsigned char * lastImage[SLAM_MAX_LEVELS];
+    const unsigned char * nextImage[SLAM_MAX_LEVELS];
+    const unsigned char * lastNextImage[SLAM_MAX_LEVELS];
+    const short * dIdx[SLAM_MAX_LEVELS];
+    const short * dIdy[SLAM_MAX_LEVELS];
+    Corres * corres[SLAM_MAX_LEVELS];
+    float Rprev[9];
+    float tprev[3];
+};
+
+struct GnCtl
+{
+    unsigned barrier[kGnMaxCtas];   // one arrival counter per CTA group; zeroed by the per-launch copy
+};
+
+struct GnLaunch
+{
+    int levels, batch;
+    LevelGeom geom[SLAM_MAX_LEVELS];
+    int iterations[SLAM_MAX_LEVELS];
+    bool icp, rgb, rgb_only, so3, trace;
+    float icp_weight;
+    float dist_thresh, angle_thresh;
+    float sobel_scale, max_depth_delta;
+    float min_scale[SLAM_MAX_LEVELS];
+};
+
+struct GnDevice
+{
+    // device
+    GnCtl * ctl = nullptr;
+    GnSeqIn * seq_in = nullptr;
+    float * partials = nullptr;
+    GnResult * results = nullptr;
+    slam_step_record * trace = nullptr;
+    int * trace_count = nullptr;
+    // host
+    char * h_stage = nullptr;       // pinned image of [GnCtl | GnSeqIn x batch]
+    size_t stage_bytes = 0;
+    int batch = 0;
+    int num_sms = 0;
+    bool so3_swapped = false;
+};
+
+size_t gn_state_bytes(int batch);
+void gn_bind_state(GnDevice & d, char * base, int batch);
+int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnResult * h_results,
+               cudaStream_t stream);
+int gn_read_trace(GnDevice & d, int seq, slam_step_record * out, int max_records, int * n_records, cudaStream_t stream);
+void gn_release(GnDevice & d);
+
+}   // namespace slam

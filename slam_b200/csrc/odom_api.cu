@@ -1,0 +1,1116 @@
+// libslam_odom: handle, buffers and the C ABI of the tracker (include/slam_odom.h).
+//
+// Host side of the reference's RGBDOdometryef (src/odom/RGBDOdometryef.cpp) re-designed
+// for B200: one device arena per handle, dense buffers, one stream, fused preparation
+// kernels, and two ways of running the Gauss-Newton iterations:
+//   * device-resident (default): the whole SO3 + coarse-to-fine ICP/RGB loop, including
+//     the 3x3 / 6x6 solves and the pose update, runs inside ONE persistent kernel
+//     (gn_kernel.cu); the host only enqueues it and reads back 48 bytes of pose;
+//   * host-stepped (params.host_loop = 1): the reference's control flow, one reduction
+//     launch + one sync per step, kept for step-by-step parity against the oracle.
+#include <mutex>
+#include <cstring>
+#include <cmath>
+#include <cfloat>
+#include <limits>
+#include "odom_internal.hpp"
+#include "gn_kernel.cuh"
+
+namespace slam {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string & msg) { g_last_error = msg; }
+
+}   // namespace slam
+
+using namespace slam;
+
+struct StagingSlot
+{
+    unsigned short * depth = nullptr;
+    uchar4 * rgba = nullptr;
+    float4 * mv = nullptr;
+    float4 * mn = nullptr;
+    uchar4 * mrgba = nullptr;
+    float pose[16 * 1];
+    std::vector<float> poses;
+    const void * tag_depth = nullptr;   // host pointer this slot was prefetched from
+    cudaEvent_t ready = nullptr;
+    bool pending = false;
+    float depth_cutoff = 0, model_depth_cutoff = 0;
+};
+
+struct slam_odom
+{
+    slam_odom_params p;
+    int levels = 3;
+    int batch = 1;
+    LevelGeom geom[SLAM_MAX_LEVELS];
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t compute_done = nullptr;
+
+    char * arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<SeqBuffers> seq;
+
+    // device-resident loop
+    GnDevice gn;                      // device pointers of the persistent kernel's state
+    GnResult * h_results = nullptr;   // pinned [batch]
+    float * h_sums = nullptr;         // pinned scratch for the host-stepped loop [96]
+
+    std::vector<slam_odom_stats> stats;
+    std::vector<std::vector<slam_step_record>> trace;
+    bool trace_on = false;
+    bool have_depth_tmp = false;
+    bool pending_async = false;
+    bool last_icp = false, last_rgb = false, last_so3 = false;
+    long long launches = 0;
+
+    StagingSlot slot[2];
+    int next_slot = 0;
+    bool staging_ready = false;
+
+    // constants of the reference ctor (RGBDOdometryef.cpp:34-37,108-110)
+    float sobelScale = 1.0f / 8.0f;
+    float maxDepthDeltaRGB = 0.07f;
+    float maxDepthRGB = 6.0f;
+    float minGrad[SLAM_MAX_LEVELS] = {5, 3, 1, 1};
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct ArenaPlan
+{
+    size_t off = 0;
+    size_t take(size_t bytes)
+    {
+        const size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+int check_handle(slam_odom_t h)
+{
+    if(!h)
+    {
+        set_last_error("null handle");
+        return SLAM_ERR_ARG;
+    }
+    return SLAM_OK;
+}
+
+int set_device(slam_odom_t h)
+{
+    SLAM_CUDA_TRY(cudaSetDevice(h->p.device));
+    return SLAM_OK;
+}
+
+// Lay out (plan == true: only measure) every per-sequence buffer inside the arena.
+void layout_sequence(slam_odom * h, ArenaPlan & plan, SeqBuffers * sb)
+{
+    char * base = h->arena;
+    auto P = [&](size_t bytes) -> char * {
+        const size_t o = plan.take(bytes);
+        return base ? base + o : nullptr;
+    };
+    SeqBuffers tmp;
+    SeqBuffers & s = sb ? *sb : tmp;
+    for(int l = 0; l < h->levels; l++)
+    {
+        const size_t n = (size_t)h->geom[l].rows * h->geom[l].cols;
+        s.depth[l] = (unsigned short *)P(n * 2);
+        s.vcurr[l] = (float *)P(n * 12);
+        s.ncurr[l] = (float *)P(n * 12);
+        s.vprev[l] = (float *)P(n * 12);
+        s.nprev[l] = (float *)P(n * 12);
+        s.lastDepth[l] = (float *)P(n * 4);
+        s.nextDepth[l] = (float *)P(n * 4);
+        s.lastImage[l] = (unsigned char *)P(n);
+        s.nextImage[l] = (unsigned char *)P(n);
+        s.lastNextImage[l] = (unsigned char *)P(n);
+        s.dIdx[l] = (short *)P(n * 2);
+        s.dIdy[l] = (short *)P(n * 2);
+        s.corres[l] = (Corres *)P(n * sizeof(Corres));
+    }
+    const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
+    s.depth_tmp = (float *)P(n0 * 4);
+    if(h->levels > 3)
+    {
+        const size_t n2 = (size_t)h->geom[2].rows * h->geom[2].cols;
+        s.vcam = (float *)P(n2 * 12);
+        s.ncam = (float *)P(n2 * 12);
+    }
+    else
+        s.vcam = s.ncam = nullptr;
+    s.workspace = P(kWorkspaceBytes);
+    s.sums = (float *)P(128 * 4);
+}
+
+void default_iterations(const slam_odom * h, int pyramid, int fast_odom, int * it)
+{
+    bool user = false;
+    for(int l = 0; l < SLAM_MAX_LEVELS; l++) user = user || h->p.iterations[l] != 0;
+    for(int l = 0; l < SLAM_MAX_LEVELS; l++) it[l] = 0;
+    if(user)
+    {
+        for(int l = 0; l < h->levels; l++) it[l] = h->p.iterations[l];
+        return;
+    }
+    // RGBDOdometryef.cpp:382-384
+    it[0] = fast_odom ? 3 : 10;
+    if(h->levels > 1) it[1] = pyramid ? 5 : 0;
+    if(h->levels > 2) it[2] = pyramid ? 4 : 0;
+    if(h->levels > 3) it[3] = pyramid ? 4 : 0;
+}
+
+void unpack_se3(const float * s, float * A, float * b)   // reduce.cu:472-486
+{
+    int shift = 0;
+    for(int i = 0; i < 6; ++i)
+        for(int j = i; j < 7; ++j)
+        {
+            const float value = s[shift++];
+            if(j == 6)
+                b[i] = value;
+            else
+                A[j * 6 + i] = A[i * 6 + j] = value;
+        }
+}
+
+void unpack_so3(const float * s, float * A, float * b)   // reduce.cu:1122-1136
+{
+    int shift = 0;
+    for(int i = 0; i < 3; ++i)
+        for(int j = i; j < 4; ++j)
+        {
+            const float value = s[shift++];
+            if(j == 3)
+                b[i] = value;
+            else
+                A[j * 3 + i] = A[i * 3 + j] = value;
+        }
+}
+
+void k_matrix(const LevelGeom & g, double * K)
+{
+    for(int i = 0; i < 9; i++) K[i] = 0;
+    K[0] = g.fx;
+    K[4] = g.fy;
+    K[2] = g.cx;
+    K[5] = g.cy;
+    K[8] = 1;
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------ frame preparation
+namespace {
+
+int enqueue_init_icp_depth(slam_odom * h, int b, const uint16_t * d_depth, size_t pitch, float cutoff)
+{
+    SeqBuffers & s = h->seq[b];
+    const LevelGeom & g0 = h->geom[0];
+    const size_t row_bytes = (size_t)g0.cols * 2;
+    const unsigned short * src = d_depth;
+    if(pitch != 0 && pitch != row_bytes)
+    {
+        SLAM_CUDA_TRY(cudaMemcpy2DAsync(s.depth[0], row_bytes, d_depth, pitch, row_bytes, g0.rows, cudaMemcpyDeviceToDevice, h->stream));
+        src = s.depth[0];
+    }
+    for(int l = 0; l < h->levels; l++)
+    {
+        const LevelGeom & g = h->geom[l];
+        const unsigned short * in = (l == 0) ? src : s.depth[l];
+        unsigned short * next = (l + 1 < h->levels) ? s.depth[l + 1] : nullptr;
+        int rc = launch_depth_level(in, g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, cutoff, s.vcurr[l], s.ncurr[l], next, h->stream);
+        if(rc) return rc;
+        h->launches++;
+    }
+    if(src != s.depth[0] && h->trace_on)   // keep a copy for the depth tap
+        SLAM_CUDA_TRY(cudaMemcpyAsync(s.depth[0], src, row_bytes * g0.rows, cudaMemcpyDeviceToDevice, h->stream));
+    return SLAM_OK;
+}
+
+int enqueue_model_maps(slam_odom * h, int b, const float * v4, const float * n4, bool model, const float * pose16)
+{
+    SeqBuffers & s = h->seq[b];
+    const LevelGeom & g0 = h->geom[0];
+    Mat3 R = {};
+    float3 t = make_float3(0, 0, 0);
+    if(model)
+    {
+        R.r0 = make_float3(pose16[0], pose16[1], pose16[2]);
+        R.r1 = make_float3(pose16[4], pose16[5], pose16[6]);
+        R.r2 = make_float3(pose16[8], pose16[9], pose16[10]);
+        t = make_float3(pose16[3], pose16[7], pose16[11]);
+    }
+    float ** vdst = model ? s.vprev : s.vcurr;
+    float ** ndst = model ? s.nprev : s.ncurr;
+    int rc = launch_model_maps_simple((const float4 *)v4, (const float4 *)n4, g0.rows, g0.cols, h->levels, vdst, ndst, model ? 1 : 0, R, t, s.depth_tmp,
+                                      h->maxDepthRGB, h->levels > 3 ? s.vcam : nullptr, h->levels > 3 ? s.ncam : nullptr, h->stream);
+    if(rc) return rc;
+    h->launches++;
+    if(h->levels > 3)
+    {
+        rc = launch_resize_transform(s.vcam, s.ncam, h->geom[2].rows, h->geom[2].cols, vdst[3], ndst[3], model ? 1 : 0, R, t, nullptr, nullptr, h->stream);
+        if(rc) return rc;
+        h->launches++;
+    }
+    return SLAM_OK;
+}
+
+// populateRGBDData, RGBDOdometryef.cpp:208-235 (destDepths may be null for initFirstRGB)
+int enqueue_populate_rgbd(slam_odom * h, int b, const uint8_t * rgba, float ** destDepths, unsigned char ** destImages)
+{
+    SeqBuffers & s = h->seq[b];
+    const LevelGeom & g0 = h->geom[0];
+    int rc = launch_rgbd_level0(s.depth_tmp, destDepths ? destDepths[0] : nullptr, (const uchar4 *)rgba, destImages[0], g0.rows * g0.cols, h->stream);
+    if(rc) return rc;
+    h->launches++;
+    for(int l = 0; l + 1 < h->levels; l++)
+    {
+        const LevelGeom & g = h->geom[l];
+        rc = launch_rgbd_down(destDepths ? destDepths[l] : nullptr, destDepths ? destDepths[l + 1] : nullptr, destImages[l], destImages[l + 1], g.rows,
+                              g.cols, h->stream);
+        if(rc) return rc;
+        h->launches++;
+    }
+    return SLAM_OK;
+}
+
+int enqueue_derivatives(slam_odom * h, int b)
+{
+    SeqBuffers & s = h->seq[b];
+    int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
+    for(int l = 0; l < h->levels; l++)
+    {
+        rows[l] = h->geom[l].rows;
+        cols[l] = h->geom[l].cols;
+    }
+    int rc = launch_derivatives_simple(h->levels, s.nextImage, s.dIdx, s.dIdy, rows, cols, h->stream);
+    if(rc) return rc;
+    h->launches++;
+    return SLAM_OK;
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------ host-stepped loop
+namespace {
+
+int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3)
+{
+    SeqBuffers & s = h->seq[b];
+    slam_odom_stats & st = h->stats[b];
+    std::vector<slam_step_record> * tr = h->trace_on ? &h->trace[b] : nullptr;
+    if(tr) tr->clear();
+
+    const bool icp = !rgbOnly && icpWeight > 0;
+    const bool rgb = rgbOnly || icpWeight < 100;
+
+    float Rprev[9], tprev[3], Rcurr[9], tcurr[3];
+    memcpy(Rprev, rot, sizeof(Rprev));
+    memcpy(tprev, trans, sizeof(tprev));
+    memcpy(Rcurr, Rprev, sizeof(Rprev));
+    memcpy(tcurr, tprev, sizeof(tprev));
+
+    if(rgb)
+    {
+        int rc = enqueue_derivatives(h, b);
+        if(rc) return rc;
+    }
+
+    float * d_icp = s.sums;
+    float * d_rgb = s.sums + 32;
+    float * d_so3 = s.sums + 64;
+    int * d_res = reinterpret_cast<int *>(s.sums + 80);
+
+    double resultR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    st.so3_iterations = 0;
+    st.gn_iterations = 0;
+
+    if(so3)
+    {
+        if(h->levels < 3)
+        {
+            set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
+            return SLAM_ERR_UNSUPPORTED;
+        }
+        const int L = 2;   // RGBDOdometryef.cpp:296
+        const LevelGeom & g = h->geom[L];
+        float R_lr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        double K[9], Kinv[9];
+        k_matrix(g, K);
+        smath::mat3_inverse(K, Kinv);
+
+        float lastError = std::numeric_limits<float>::max() / 2;
+        float lastCount = std::numeric_limits<float>::max() / 2;
+        double lastResultR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+        for(int i = 0; i < 10; i++)
+        {
+            double KR[9], H[9];
+            smath::mat3_mul(K, resultR, KR);
+            smath::mat3_mul(KR, Kinv, H);
+            float Hf[9], Kinvf[9], KRf[9];
+            for(int k = 0; k < 9; k++)
+            {
+                Hf[k] = (float)H[k];
+                Kinvf[k] = (float)Kinv[k];
+                KRf[k] = (float)KR[k];
+            }
+            So3Args a;
+            a.lastImage = s.lastNextImage[L];
+            a.nextImage = s.nextImage[L];
+            a.imageBasis = mat3_from(Hf);
+            a.kinv = mat3_from(Kinvf);
+            a.krlr = mat3_from(KRf);
+            a.cols = g.cols;
+            a.rows = g.rows;
+            int rc = launch_so3_step(a, s.workspace, d_so3, h->stream);
+            if(rc) return rc;
+            h->launches++;
+            SLAM_CUDA_TRY(cudaMemcpyAsync(h->h_sums, d_so3, 11 * 4, cudaMemcpyDeviceToHost, h->stream));
+            SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            st.so3_iterations++;
+
+            float jtj[9], jtr[3];
+            unpack_so3(h->h_sums, jtj, jtr);
+            const float residual0 = h->h_sums[9], residual1 = h->h_sums[10];
+
+            st.lastSO3Error = sqrtf(residual0) / residual1;
+            st.lastSO3Count = residual1;
+
+            slam_step_record rec = {};
+            rec.kind = 0;
+            rec.level = L;
+            rec.iteration = i;
+            memcpy(rec.so3, h->h_sums, 11 * 4);
+
+            bool stop = false;
+            if(st.lastSO3Error < lastError && lastCount == st.lastSO3Count)
+                stop = true;   // converged
+            else if((double)st.lastSO3Error > (double)lastError + 0.001)   // diverging
+            {
+                st.lastSO3Error = lastError;
+                st.lastSO3Count = lastCount;
+                memcpy(resultR, lastResultR, sizeof(resultR));
+                stop = true;
+            }
+            if(!stop)
+            {
+                lastError = st.lastSO3Error;
+                lastCount = st.lastSO3Count;
+                memcpy(lastResultR, resultR, sizeof(resultR));
+
+                float delta[3];
+                smath::ldlt_solve<float, 3>(jtj, jtr, delta, FLT_EPSILON);
+                const double dd[3] = {delta[0], delta[1], delta[2]};
+                double rotUpdate[9];
+                smath::rodrigues(dd, rotUpdate);
+                float ru[9];
+                for(int k = 0; k < 9; k++) ru[k] = (float)rotUpdate[k];
+                smath::mat3_mul(ru, R_lr, R_lr);
+                for(int k = 0; k < 9; k++) resultR[k] = R_lr[k];
+                for(int k = 0; k < 3; k++) rec.x[k] = delta[k];
+            }
+            if(tr)
+            {
+                for(int k = 0; k < 9; k++) rec.Rcurr[k] = (float)resultR[k];
+                tr->push_back(rec);
+            }
+            if(stop) break;
+        }
+    }
+
+    int iterations[SLAM_MAX_LEVELS];
+    default_iterations(h, pyramid, fastOdom, iterations);
+
+    float Rprev_inv[9];
+    smath::mat3_inverse(Rprev, Rprev_inv);
+
+    double resultRt[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if(so3)
+        for(int x = 0; x < 3; x++)
+            for(int y = 0; y < 3; y++) resultRt[x * 4 + y] = resultR[x * 3 + y];
+
+    for(int i = h->levels - 1; i >= 0; i--)
+    {
+        const LevelGeom & g = h->geom[i];
+        double K[9], Kinv[9];
+        k_matrix(g, K);
+        smath::mat3_inverse(K, Kinv);
+
+        st.lastRGBError = std::numeric_limits<float>::max();
+
+        for(int j = 0; j < iterations[i]; j++)
+        {
+            double Rt[16];
+            smath::mat4_inverse(resultRt, Rt);
+            double R[9], KR[9], KRK_inv[9];
+            for(int x = 0; x < 3; x++)
+                for(int y = 0; y < 3; y++) R[x * 3 + y] = Rt[x * 4 + y];
+            smath::mat3_mul(K, R, KR);
+            smath::mat3_mul(KR, Kinv, KRK_inv);
+            float krk[9];
+            for(int k = 0; k < 9; k++) krk[k] = (float)KRK_inv[k];
+            const double tv[3] = {Rt[3], Rt[7], Rt[11]};
+            float kt[3];
+            for(int x = 0; x < 3; x++) kt[x] = (float)(K[x * 3 + 0] * tv[0] + K[x * 3 + 1] * tv[1] + K[x * 3 + 2] * tv[2]);
+
+            int sigma = 0;
+            int rgbSize = 0;
+
+            slam_step_record rec = {};
+            rec.kind = 1;
+            rec.level = i;
+            rec.iteration = j;
+
+            if(rgb)
+            {
+                ResidualArgs a;
+                a.minScale = (float)(pow((double)h->minGrad[i], 2.0) / pow((double)h->sobelScale, 2.0));
+                a.dIdx = s.dIdx[i];
+                a.dIdy = s.dIdy[i];
+                a.lastDepth = s.lastDepth[i];
+                a.nextDepth = s.nextDepth[i];
+                a.lastImage = s.lastImage[i];
+                a.nextImage = s.nextImage[i];
+                a.maxDepthDelta = h->maxDepthDeltaRGB;
+                a.kt = make_float3(kt[0], kt[1], kt[2]);
+                a.krkinv = mat3_from(krk);
+                a.cols = g.cols;
+                a.rows = g.rows;
+                int rc = launch_rgb_residual(a, s.corres[i], s.workspace, d_res, h->stream);
+                if(rc) return rc;
+                h->launches++;
+                SLAM_CUDA_TRY(cudaMemcpyAsync(h->h_sums, d_res, 8, cudaMemcpyDeviceToHost, h->stream));
+                SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+                rgbSize = reinterpret_cast<int *>(h->h_sums)[0];
+                sigma = reinterpret_cast<int *>(h->h_sums)[1];
+            }
+            rec.rgb_count = rgbSize;
+            rec.rgb_sigma = sigma;
+
+            float sigmaVal = std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize);   // sic, RGBDOdometryef.cpp:457
+            const float rgbError = std::sqrt(sigma) / (rgbSize == 0 ? 1 : rgbSize);
+
+            if(rgbOnly && rgbError > st.lastRGBError) break;
+
+            st.lastRGBError = rgbError;
+            st.lastRGBCount = rgbSize;
+
+            if(rgbOnly) sigmaVal = -1;
+
+            float A_icp[36] = {0}, b_icp[6] = {0}, A_rgbd[36] = {0}, b_rgbd[6] = {0};
+
+            if(icp)
+            {
+                IcpArgs a;
+                a.Rcurr = mat3_from(Rcurr);
+                a.tcurr = make_float3(tcurr[0], tcurr[1], tcurr[2]);
+                a.Rprev_inv = mat3_from(Rprev_inv);
+                a.tprev = make_float3(tprev[0], tprev[1], tprev[2]);
+                a.fx = g.fx; a.fy = g.fy; a.cx = g.cx; a.cy = g.cy;
+                a.distThres = h->p.dist_thresh;
+                a.angleThres = h->p.angle_thresh;
+                a.cols = g.cols;
+                a.rows = g.rows;
+                a.vcurr = s.vcurr[i]; a.ncurr = s.ncurr[i]; a.vprev = s.vprev[i]; a.nprev = s.nprev[i];
+                int rc = launch_icp_step(a, s.workspace, d_icp, h->stream);
+                if(rc) return rc;
+                h->launches++;
+            }
+            if(rgb)
+            {
+                RgbStepArgs a;
+                a.sigma = sigmaVal;
+                a.fx = g.fx; a.fy = g.fy;
+                a.sobelScale = h->sobelScale;
+                a.cols = g.cols; a.rows = g.rows;
+                a.dIdx = s.dIdx[i]; a.dIdy = s.dIdy[i];
+                a.lastDepth = s.lastDepth[i];
+                a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
+                a.cloud = nullptr;
+                int rc = launch_rgb_step(a, s.corres[i], s.workspace, d_rgb, h->stream);
+                if(rc) return rc;
+                h->launches++;
+            }
+            SLAM_CUDA_TRY(cudaMemcpyAsync(h->h_sums, s.sums, 64 * 4, cudaMemcpyDeviceToHost, h->stream));
+            SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            st.gn_iterations++;
+
+            if(icp)
+            {
+                unpack_se3(h->h_sums, A_icp, b_icp);
+                st.lastICPError = sqrtf(h->h_sums[27]) / h->h_sums[28];
+                st.lastICPCount = h->h_sums[28];
+                memcpy(rec.icp, h->h_sums, 29 * 4);
+            }
+            if(rgb)
+            {
+                unpack_se3(h->h_sums + 32, A_rgbd, b_rgbd);
+                memcpy(rec.rgb, h->h_sums + 32, 29 * 4);
+            }
+
+            double result[6];
+            if(icp && rgb)
+            {
+                const double w = icpWeight;
+                for(int k = 0; k < 36; k++) st.lastA[k] = (double)A_rgbd[k] + w * w * (double)A_icp[k];
+                for(int k = 0; k < 6; k++) st.lastb[k] = (double)b_rgbd[k] + w * (double)b_icp[k];
+            }
+            else if(icp)
+            {
+                for(int k = 0; k < 36; k++) st.lastA[k] = A_icp[k];
+                for(int k = 0; k < 6; k++) st.lastb[k] = b_icp[k];
+            }
+            else
+            {
+                for(int k = 0; k < 36; k++) st.lastA[k] = A_rgbd[k];
+                for(int k = 0; k < 6; k++) st.lastb[k] = b_rgbd[k];
+            }
+            smath::ldlt_solve<double, 6>(st.lastA, st.lastb, result, DBL_EPSILON);
+
+            smath::update_se3(resultRt, result);
+            smath::compose_current_pose(Rprev, tprev, resultRt, Rcurr, tcurr);
+
+            if(tr)
+            {
+                for(int k = 0; k < 6; k++) rec.x[k] = result[k];
+                memcpy(rec.Rcurr, Rcurr, sizeof(Rcurr));
+                memcpy(rec.tcurr, tcurr, sizeof(tcurr));
+                tr->push_back(rec);
+            }
+        }
+    }
+
+    if(rgb)
+    {
+        const float dx = tcurr[0] - tprev[0], dy = tcurr[1] - tprev[1], dz = tcurr[2] - tprev[2];
+        if(sqrtf(dx * dx + dy * dy + dz * dz) > 0.3)   // RGBDOdometryef.cpp:579-583
+        {
+            memcpy(Rcurr, Rprev, sizeof(Rprev));
+            memcpy(tcurr, tprev, sizeof(tprev));
+        }
+    }
+    if(so3)
+        for(int l = 0; l < h->levels; l++) std::swap(s.lastNextImage[l], s.nextImage[l]);
+
+    memcpy(trans, tcurr, sizeof(tcurr));
+    memcpy(rot, Rcurr, sizeof(Rcurr));
+    return SLAM_OK;
+}
+
+}   // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" const char * slam_odom_version(void) { return "slam_b200 0.1 (sm_100a)"; }
+extern "C" const char * slam_odom_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * out)
+{
+    SLAM_ARG_CHECK(params && out);
+    SLAM_ARG_CHECK(params->width > 0 && params->height > 0);
+    SLAM_ARG_CHECK(params->num_levels >= 0 && params->num_levels <= SLAM_MAX_LEVELS);
+    int ndev = 0;
+    SLAM_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if(ndev == 0)
+    {
+        set_last_error("no CUDA device: libslam_odom has no CPU fallback");
+        return SLAM_ERR_CUDA;
+    }
+    SLAM_ARG_CHECK(params->device >= 0 && params->device < ndev);
+    SLAM_CUDA_TRY(cudaSetDevice(params->device));
+
+    slam_odom * h = new slam_odom();
+    h->p = *params;
+    if(h->p.dist_thresh == 0) h->p.dist_thresh = 0.10f;
+    if(h->p.angle_thresh == 0) h->p.angle_thresh = sinf(20.f * 3.14159254f / 180.f);
+    h->levels = params->num_levels ? params->num_levels : 3;
+    h->batch = params->batch > 1 ? params->batch : 1;
+    for(int l = 0; l < h->levels; l++)
+    {
+        const int div = 1 << l;
+        h->geom[l].rows = params->height >> l;
+        h->geom[l].cols = params->width >> l;
+        h->geom[l].fx = params->fx / div;
+        h->geom[l].fy = params->fy / div;
+        h->geom[l].cx = params->cx / div;
+        h->geom[l].cy = params->cy / div;
+        if(h->geom[l].rows < 2 || h->geom[l].cols < 2)
+        {
+            delete h;
+            set_last_error("image too small for the requested pyramid");
+            return SLAM_ERR_ARG;
+        }
+    }
+    if(params->stream)
+        h->stream = (cudaStream_t)params->stream;
+    else
+    {
+        SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    SLAM_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+
+    ArenaPlan plan;
+    for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
+    const size_t gn_off = plan.take(gn_state_bytes(h->batch));
+    h->arena_bytes = plan.off;
+    SLAM_CUDA_TRY(cudaMalloc((void **)&h->arena, h->arena_bytes));
+    SLAM_CUDA_TRY(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+    h->seq.resize(h->batch);
+    ArenaPlan place;
+    for(int b = 0; b < h->batch; b++) layout_sequence(h, place, &h->seq[b]);
+    gn_bind_state(h->gn, h->arena + gn_off, h->batch);
+
+    SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_results, sizeof(GnResult) * h->batch));
+    SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_sums, 128 * 4));
+
+    h->stats.resize(h->batch);
+    h->trace.resize(h->batch);
+    for(auto & st : h->stats)
+    {
+        memset(&st, 0, sizeof(st));
+        // RGBDOdometryef.cpp:26-31
+        st.lastICPCount = st.lastRGBCount = st.lastSO3Count = (float)(params->width * params->height);
+    }
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_destroy(slam_odom_t h)
+{
+    if(!h) return SLAM_OK;
+    cudaSetDevice(h->p.device);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->copy_stream);
+    for(auto & sl : h->slot)
+    {
+        if(sl.depth) cudaFree(sl.depth);
+        if(sl.ready) cudaEventDestroy(sl.ready);
+    }
+    gn_release(h->gn);
+    if(h->arena) cudaFree(h->arena);
+    if(h->h_results) cudaFreeHost(h->h_results);
+    if(h->h_sums) cudaFreeHost(h->h_sums);
+    if(h->compute_done) cudaEventDestroy(h->compute_done);
+    if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if(h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_init_icp_depth(slam_odom_t h, const uint16_t * d_depth, size_t pitch_bytes, float depth_cutoff)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(d_depth);
+    if(int rc = set_device(h)) return rc;
+    const size_t row = pitch_bytes ? pitch_bytes : (size_t)h->geom[0].cols * 2;
+    for(int b = 0; b < h->batch; b++)
+        if(int rc = enqueue_init_icp_depth(h, b, (const uint16_t *)((const char *)d_depth + (size_t)b * row * h->geom[0].rows), pitch_bytes, depth_cutoff))
+            return rc;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_init_icp_maps(slam_odom_t h, const float * d_vertices4, const float * d_normals4, float /*depth_cutoff*/)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(d_vertices4 && d_normals4);
+    if(int rc = set_device(h)) return rc;
+    const size_t n4 = (size_t)h->geom[0].rows * h->geom[0].cols * 4;
+    for(int b = 0; b < h->batch; b++)
+        if(int rc = enqueue_model_maps(h, b, d_vertices4 + b * n4, d_normals4 + b * n4, false, nullptr)) return rc;
+    h->have_depth_tmp = true;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_init_icp_model(slam_odom_t h, const float * d_vertices4, const float * d_normals4, float /*depth_cutoff*/,
+                                        const float * model_pose16)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(d_vertices4 && d_normals4 && model_pose16);
+    if(int rc = set_device(h)) return rc;
+    const size_t n4 = (size_t)h->geom[0].rows * h->geom[0].cols * 4;
+    for(int b = 0; b < h->batch; b++)
+        if(int rc = enqueue_model_maps(h, b, d_vertices4 + b * n4, d_normals4 + b * n4, true, model_pose16 + 16 * b)) return rc;
+    h->have_depth_tmp = true;
+    return SLAM_OK;
+}
+
+static int init_rgb_common(slam_odom_t h, const uint8_t * d_rgba, int which)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(d_rgba);
+    if(int rc = set_device(h)) return rc;
+    if(which != 2 && !h->have_depth_tmp)
+    {
+        // RGBDOdometryef.cpp:239,245: populateRGBDData reads vmaps_tmp written by initICPModel / initICP(maps)
+        set_last_error("initRGB/initRGBModel called before initICPModel/initICP(maps)");
+        return SLAM_ERR_ORDER;
+    }
+    const size_t n4 = (size_t)h->geom[0].rows * h->geom[0].cols * 4;
+    for(int b = 0; b < h->batch; b++)
+    {
+        SeqBuffers & s = h->seq[b];
+        int rc;
+        if(which == 0)
+            rc = enqueue_populate_rgbd(h, b, d_rgba + b * n4, s.nextDepth, s.nextImage);
+        else if(which == 1)
+            rc = enqueue_populate_rgbd(h, b, d_rgba + b * n4, s.lastDepth, s.lastImage);
+        else
+            rc = enqueue_populate_rgbd(h, b, d_rgba + b * n4, nullptr, s.lastNextImage);
+        if(rc) return rc;
+    }
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_init_rgb(slam_odom_t h, const uint8_t * d_rgba) { return init_rgb_common(h, d_rgba, 0); }
+extern "C" int slam_odom_init_rgb_model(slam_odom_t h, const uint8_t * d_rgba) { return init_rgb_common(h, d_rgba, 1); }
+extern "C" int slam_odom_init_first_rgb(slam_odom_t h, const uint8_t * d_rgba) { return init_rgb_common(h, d_rgba, 2); }
+
+// Enqueue the device-resident loop for the whole batch.
+static int enqueue_device_loop(slam_odom_t h, const float * trans, const float * rot, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    const bool icp = !rgb_only && icp_weight > 0;
+    const bool rgb = rgb_only || icp_weight < 100;
+    if(so3 && h->levels < 3)
+    {
+        set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
+        return SLAM_ERR_UNSUPPORTED;
+    }
+    if(rgb)
+        for(int b = 0; b < h->batch; b++)
+            if(int rc = enqueue_derivatives(h, b)) return rc;
+
+    GnLaunch L = {};
+    L.levels = h->levels;
+    L.batch = h->batch;
+    for(int l = 0; l < h->levels; l++) L.geom[l] = h->geom[l];
+    default_iterations(h, pyramid, fast_odom, L.iterations);
+    L.icp = icp;
+    L.rgb = rgb;
+    L.rgb_only = rgb_only != 0;
+    L.so3 = so3 != 0;
+    L.icp_weight = icp_weight;
+    L.dist_thresh = h->p.dist_thresh;
+    L.angle_thresh = h->p.angle_thresh;
+    L.sobel_scale = h->sobelScale;
+    L.max_depth_delta = h->maxDepthDeltaRGB;
+    for(int l = 0; l < h->levels; l++) L.min_scale[l] = (float)(pow((double)h->minGrad[l], 2.0) / pow((double)h->sobelScale, 2.0));
+    L.trace = h->trace_on;
+    int rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream);
+    if(rc) return rc;
+    h->launches++;
+    h->pending_async = true;
+    h->last_icp = icp;
+    h->last_rgb = rgb;
+    h->last_so3 = so3 != 0;
+    return SLAM_OK;
+}
+
+static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
+{
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if(!h->pending_async) return SLAM_OK;
+    h->pending_async = false;
+    for(int b = 0; b < h->batch; b++)
+    {
+        const GnResult & r = h->h_results[b];
+        slam_odom_stats & st = h->stats[b];
+        if(h->last_icp)
+        {
+            st.lastICPError = r.lastICPError;
+            st.lastICPCount = r.lastICPCount;
+        }
+        if(h->last_rgb)
+        {
+            st.lastRGBError = r.lastRGBError;
+            st.lastRGBCount = r.lastRGBCount;
+        }
+        if(h->last_so3)
+        {
+            st.lastSO3Error = r.lastSO3Error;
+            st.lastSO3Count = r.lastSO3Count;
+        }
+        memcpy(st.lastA, r.lastA, sizeof(st.lastA));
+        memcpy(st.lastb, r.lastb, sizeof(st.lastb));
+        st.so3_iterations = r.so3_iterations;
+        st.gn_iterations = r.gn_iterations;
+        if(trans) memcpy(trans + 3 * b, r.tcurr, 12);
+        if(rot) memcpy(rot + 9 * b, r.Rcurr, 36);
+        if(h->gn.so3_swapped)
+            for(int l = 0; l < h->levels; l++) std::swap(h->seq[b].lastNextImage[l], h->seq[b].nextImage[l]);
+    }
+    h->gn.so3_swapped = false;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_get_incremental_transformation_async(slam_odom_t h, const float * trans, const float * rot, int rgb_only, float icp_weight,
+                                                              int pyramid, int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(trans && rot);
+    if(int rc = set_device(h)) return rc;
+    if(h->p.host_loop)
+    {
+        set_last_error("async form needs the device-resident loop (host_loop = 0)");
+        return SLAM_ERR_UNSUPPORTED;
+    }
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    return enqueue_device_loop(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+}
+
+extern "C" int slam_odom_wait(slam_odom_t h, float * trans, float * rot)
+{
+    if(int rc = check_handle(h)) return rc;
+    if(int rc = set_device(h)) return rc;
+    return finish_device_loop(h, trans, rot);
+}
+
+extern "C" int slam_odom_get_incremental_transformation(slam_odom_t h, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
+                                                        int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(trans && rot);
+    if(int rc = set_device(h)) return rc;
+    if(h->p.host_loop)
+    {
+        for(int b = 0; b < h->batch; b++)
+            if(int rc = host_loop_one(h, b, trans + 3 * b, rot + 9 * b, rgb_only != 0, icp_weight, pyramid != 0, fast_odom != 0, so3 != 0)) return rc;
+        return SLAM_OK;
+    }
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    if(int rc = enqueue_device_loop(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3)) return rc;
+    return finish_device_loop(h, trans, rot);
+}
+
+extern "C" int slam_odom_get_covariance(slam_odom_t h, double * out36)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(out36);
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    for(int b = 0; b < h->batch; b++) smath::lu_inverse<double, 6>(h->stats[b].lastA, out36 + 36 * b);   // RGBDOdometryef.cpp:597-600
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_get_stats(slam_odom_t h, slam_odom_stats * stats)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(stats);
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    for(int b = 0; b < h->batch; b++) stats[b] = h->stats[b];
+    return SLAM_OK;
+}
+
+extern "C" long long slam_odom_launch_count(slam_odom_t h) { return h ? h->launches : 0; }
+
+extern "C" int slam_odom_set_trace(slam_odom_t h, int enable)
+{
+    if(int rc = check_handle(h)) return rc;
+    h->trace_on = enable != 0;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_records, int * n_records)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && n_records);
+    if(!h->p.host_loop)
+    {
+        if(h->pending_async)
+            if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+        if(int rc = set_device(h)) return rc;
+        return gn_read_trace(h->gn, seq, out, max_records, n_records, h->stream);
+    }
+    const auto & tr = h->trace[seq];
+    *n_records = (int)tr.size();
+    for(int i = 0; i < (int)tr.size() && i < max_records; i++) out[i] = tr[i];
+    return SLAM_OK;
+}
+
+// ------------------------------------------------------------------ taps
+extern "C" size_t slam_odom_tap_bytes(slam_odom_t h, int tap, int level)
+{
+    if(!h || level < 0 || level >= h->levels) return 0;
+    const size_t n = (size_t)h->geom[level].rows * h->geom[level].cols;
+    switch(tap)
+    {
+        case SLAM_TAP_DEPTH_U16: return n * 2;
+        case SLAM_TAP_VMAP_CURR:
+        case SLAM_TAP_NMAP_CURR:
+        case SLAM_TAP_VMAP_PREV:
+        case SLAM_TAP_NMAP_PREV: return n * 12;
+        case SLAM_TAP_LAST_DEPTH:
+        case SLAM_TAP_NEXT_DEPTH: return n * 4;
+        case SLAM_TAP_LAST_IMAGE:
+        case SLAM_TAP_NEXT_IMAGE:
+        case SLAM_TAP_LASTNEXT_IMAGE: return n;
+        case SLAM_TAP_DIDX:
+        case SLAM_TAP_DIDY: return n * 2;
+        case SLAM_TAP_CLOUD: return n * 12;
+        case SLAM_TAP_CORRES: return n * 16;
+    }
+    return 0;
+}
+
+extern "C" int slam_odom_tap(slam_odom_t h, int tap, int level, int seq, void * host_dst, size_t bytes)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(host_dst && seq >= 0 && seq < h->batch && level >= 0 && level < h->levels);
+    const size_t need = slam_odom_tap_bytes(h, tap, level);
+    SLAM_ARG_CHECK(need != 0 && bytes >= need);
+    if(int rc = set_device(h)) return rc;
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    SeqBuffers & s = h->seq[seq];
+    const void * src = nullptr;
+    switch(tap)
+    {
+        case SLAM_TAP_DEPTH_U16: src = s.depth[level]; break;
+        case SLAM_TAP_VMAP_CURR: src = s.vcurr[level]; break;
+        case SLAM_TAP_NMAP_CURR: src = s.ncurr[level]; break;
+        case SLAM_TAP_VMAP_PREV: src = s.vprev[level]; break;
+        case SLAM_TAP_NMAP_PREV: src = s.nprev[level]; break;
+        case SLAM_TAP_LAST_DEPTH: src = s.lastDepth[level]; break;
+        case SLAM_TAP_NEXT_DEPTH: src = s.nextDepth[level]; break;
+        case SLAM_TAP_LAST_IMAGE: src = s.lastImage[level]; break;
+        case SLAM_TAP_NEXT_IMAGE: src = s.nextImage[level]; break;
+        case SLAM_TAP_LASTNEXT_IMAGE: src = s.lastNextImage[level]; break;
+        case SLAM_TAP_DIDX: src = s.dIdx[level]; break;
+        case SLAM_TAP_DIDY: src = s.dIdy[level]; break;
+        case SLAM_TAP_CORRES: src = s.corres[level]; break;
+        case SLAM_TAP_CLOUD:
+        {
+            // pointClouds[level] is not materialised by the tracker (rgbStep re-derives the
+            // point from lastDepth); build it on demand with the same operator.
+            const LevelGeom & g = h->geom[level];
+            float * tmp = nullptr;
+            SLAM_CUDA_TRY(cudaMalloc((void **)&tmp, need));
+            int rc = slam_op_project_to_point_cloud(s.lastDepth[level], g.rows, g.cols, tmp, h->p.fx, h->p.fy, h->p.cx, h->p.cy, level, h->stream);
+            if(rc == SLAM_OK)
+            {
+                cudaError_t e = cudaMemcpyAsync(host_dst, tmp, need, cudaMemcpyDeviceToHost, h->stream);
+                if(e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+                if(e != cudaSuccess)
+                {
+                    set_last_error(cudaGetErrorString(e));
+                    rc = SLAM_ERR_CUDA;
+                }
+            }
+            cudaFree(tmp);
+            return rc;
+        }
+        default: return SLAM_ERR_ARG;
+    }
+    SLAM_CUDA_TRY(cudaMemcpyAsync(host_dst, src, need, cudaMemcpyDeviceToHost, h->stream));
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return SLAM_OK;
+}
+
+// ------------------------------------------------------------------ per-frame front ends
+static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, const uchar4 * rgba, const float4 * mv, const float4 * mn, const uchar4 * mrgba,
+                                  const float * poses16, float depth_cutoff, float model_cutoff, float * trans, float * rot, int rgb_only,
+                                  float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    // apps/elastic_fusion_file.cpp:366-374: initICPModel -> initRGBModel -> initICP -> initRGB -> getIncrementalTransformation
+    if(int rc = slam_odom_init_icp_model(h, (const float *)mv, (const float *)mn, model_cutoff, poses16)) return rc;
+    if(int rc = slam_odom_init_rgb_model(h, (const uint8_t *)mrgba)) return rc;
+    if(int rc = slam_odom_init_icp_depth(h, depth, 0, depth_cutoff)) return rc;
+    if(int rc = slam_odom_init_rgb(h, (const uint8_t *)rgba)) return rc;
+    return slam_odom_get_incremental_transformation(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+}
+
+extern "C" int slam_odom_track_device(slam_odom_t h, const slam_frame_host * f, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
+                                      int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16 && trans && rot);
+    return track_from_device_ptrs(h, f->depth, (const uchar4 *)f->rgba, (const float4 *)f->model_vertices4, (const float4 *)f->model_normals4,
+                                  (const uchar4 *)f->model_rgba, f->model_pose16, f->depth_cutoff, f->model_depth_cutoff, trans, rot, rgb_only,
+                                  icp_weight, pyramid, fast_odom, so3);
+}
+
+static int ensure_staging(slam_odom_t h)
+{
+    if(h->staging_ready) return SLAM_OK;
+    const size_t n = (size_t)h->geom[0].rows * h->geom[0].cols * h->batch;
+    for(auto & sl : h->slot)
+    {
+        // one allocation per slot: depth | rgba | mv | mn | mrgba
+        const size_t bytes = align_up(n * 2, 256) + align_up(n * 4, 256) * 2 + align_up(n * 16, 256) * 2;
+        char * base = nullptr;
+        SLAM_CUDA_TRY(cudaMalloc((void **)&base, bytes));
+        sl.depth = (unsigned short *)base;
+        base += align_up(n * 2, 256);
+        sl.rgba = (uchar4 *)base;
+        base += align_up(n * 4, 256);
+        sl.mrgba = (uchar4 *)base;
+        base += align_up(n * 4, 256);
+        sl.mv = (float4 *)base;
+        base += align_up(n * 16, 256);
+        sl.mn = (float4 *)base;
+        sl.poses.resize(16 * h->batch);
+        SLAM_CUDA_TRY(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
+    }
+    h->staging_ready = true;
+    return SLAM_OK;
+}
+
+static int stage_frame(slam_odom_t h, StagingSlot & sl, const slam_frame_host * f, cudaStream_t cs)
+{
+    const size_t n = (size_t)h->geom[0].rows * h->geom[0].cols * h->batch;
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.mv, f->model_vertices4, n * 16, cudaMemcpyHostToDevice, cs));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.mn, f->model_normals4, n * 16, cudaMemcpyHostToDevice, cs));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.mrgba, f->model_rgba, n * 4, cudaMemcpyHostToDevice, cs));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.depth, f->depth, n * 2, cudaMemcpyHostToDevice, cs));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.rgba, f->rgba, n * 4, cudaMemcpyHostToDevice, cs));
+    memcpy(sl.poses.data(), f->model_pose16, sizeof(float) * 16 * h->batch);
+    sl.depth_cutoff = f->depth_cutoff;
+    sl.model_depth_cutoff = f->model_depth_cutoff;
+    sl.tag_depth = f->depth;
+    SLAM_CUDA_TRY(cudaEventRecord(sl.ready, cs));
+    sl.pending = true;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_prefetch_host(slam_odom_t h, const slam_frame_host * f)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16);
+    if(int rc = set_device(h)) return rc;
+    if(int rc = ensure_staging(h)) return rc;
+    StagingSlot & sl = h->slot[h->next_slot];
+    // the slot was last consumed by kernels enqueued on the compute stream two frames ago;
+    // they are complete because track_host synchronises per frame.
+    return stage_frame(h, sl, f, h->copy_stream);
+}
+
+extern "C" int slam_odom_track_host(slam_odom_t h, const slam_frame_host * f, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
+                                    int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16 && trans && rot);
+    if(int rc = set_device(h)) return rc;
+    if(int rc = ensure_staging(h)) return rc;
+    StagingSlot & sl = h->slot[h->next_slot];
+    if(!(sl.pending && sl.tag_depth == f->depth))
+        if(int rc = stage_frame(h, sl, f, h->copy_stream)) return rc;
+    SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl.ready, 0));
+    sl.pending = false;
+    h->next_slot ^= 1;
+    return track_from_device_ptrs(h, sl.depth, sl.rgba, sl.mv, sl.mn, sl.mrgba, sl.poses.data(), sl.depth_cutoff, sl.model_depth_cutoff, trans, rot,
+                                  rgb_only, icp_weight, pyramid, fast_odom, so3);
+}

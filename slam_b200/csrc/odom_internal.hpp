@@ -1,0 +1,74 @@
+// Internal declarations shared by the translation units of libslam_odom.
+#pragma once
+#include <vector>
+#include <string>
+#include "common.cuh"
+#include "small_math.hpp"
+
+namespace slam {
+
+struct LevelGeom
+{
+    int rows, cols;
+    float fx, fy, cx, cy;   // CameraModel::operator()(level), sensors/Camera.h:14-18
+};
+
+// Device buffers of ONE sequence (all dense row-major; planar maps are [3][rows][cols]).
+struct SeqBuffers
+{
+    unsigned short * depth[SLAM_MAX_LEVELS];      // depth_tmp[i]          RGBDOdometryef.h:80
+    float * vcurr[SLAM_MAX_LEVELS];               // vmaps_curr_
+    float * ncurr[SLAM_MAX_LEVELS];               // nmaps_curr_
+    float * vprev[SLAM_MAX_LEVELS];               // vmaps_g_prev_
+    float * nprev[SLAM_MAX_LEVELS];               // nmaps_g_prev_
+    float * lastDepth[SLAM_MAX_LEVELS];
+    float * nextDepth[SLAM_MAX_LEVELS];
+    unsigned char * lastImage[SLAM_MAX_LEVELS];
+    unsigned char * nextImage[SLAM_MAX_LEVELS];       // swapped with lastNextImage after an so3 call
+    unsigned char * lastNextImage[SLAM_MAX_LEVELS];
+    short * dIdx[SLAM_MAX_LEVELS];
+    short * dIdy[SLAM_MAX_LEVELS];
+    Corres * corres[SLAM_MAX_LEVELS];             // corresImg
+    float * depth_tmp;                            // z of vmaps_tmp after the maxDepthRGB cut
+    float * vcam;                                 // camera-frame level-2 maps (only when levels == 4)
+    float * ncam;
+    void * workspace;                             // reduction scratch
+    float * sums;                                 // device: icp[32] rgb[32] so3[16] res(int)[2..]
+};
+
+// ---- device-resident Gauss-Newton state (one per sequence), see gn_kernel.cu ----
+struct GnResult
+{
+    float Rcurr[9];
+    float tcurr[3];
+    float lastICPError, lastICPCount;
+    float lastRGBError, lastRGBCount;
+    float lastSO3Error, lastSO3Count;
+    double lastA[36];
+    double lastb[6];
+    int so3_iterations;
+    int gn_iterations;
+};
+
+// launchers implemented in prep_kernels.cu / reduce_kernels.cu
+struct ModelMapsArgs;
+struct DerivArgs;
+int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,
+                       float * nmap, unsigned short * next_depth, cudaStream_t s);
+int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * rgba, unsigned char * image0, int n, cudaStream_t s);
+int launch_rgbd_down(const float * dsrc, float * ddst, const unsigned char * isrc, unsigned char * idst, int srows, int scols, cudaStream_t s);
+int launch_resize_transform(const float * vsrc, const float * nsrc, int srows, int scols, float * vdst, float * ndst, int transform, const Mat3 & R,
+                            const float3 & t, float * vcam, float * ncam, cudaStream_t s);
+int launch_icp_step(const IcpArgs & a, void * workspace, float * out29, cudaStream_t s);
+int launch_rgb_residual(const ResidualArgs & a, Corres * corres, void * workspace, int * out2, cudaStream_t s);
+int launch_rgb_step(const RgbStepArgs & a, const Corres * corres, void * workspace, float * out29, cudaStream_t s);
+int launch_so3_step(const So3Args & a, void * workspace, float * out11, cudaStream_t s);
+
+// helpers exported by prep_kernels.cu that need the full argument structs
+int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
+                             int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
+                             cudaStream_t s);
+int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
+                              cudaStream_t s);
+
+}   // namespace slam

@@ -1,0 +1,772 @@
+// Image / map preparation kernels of the tracker for sm_100a.
+//
+// Behavioural contract = the twelve prep kernels of the reference's src/odom/utils.cu
+// (cited per kernel), including their border and NaN quirks (SURVEY.md appendix A,
+// items 19-24).  The kernels here are organised differently from the reference:
+// fused per pyramid level (depth -> vertex+normal map + next depth level in one
+// launch; float4 model maps -> planar global-frame maps of all three levels in one
+// launch; depth+intensity pyramids side by side), dense row-major buffers instead of
+// pitched ones, and no per-call cudaMalloc/cudaMemcpy/cudaDeviceSynchronize.
+// The un-fused operator entry points (slam_op_*) are kept for operator-level parity.
+#include "odom_internal.hpp"
+
+namespace slam {
+
+// ------------------------------------------------------------------ per-pixel pieces
+// utils.cu:57-94  pyrDownGaussKernel (u16 depth, bilateral-gated 5x5, sigma_color = 30)
+__device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned short * src, int srows, int scols, int x, int y)
+{
+    const int D = 5;
+    const float sigma_color = 30;
+    const int center = src[(2 * y) * scols + 2 * x];
+
+    const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
+    const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
+    const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
+    const int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
+
+    float sum = 0;
+    float wall = 0;
+    const float weights[] = {0.375f, 0.25f, 0.0625f};
+
+    for(int yi = y_mi; yi < y_ma; ++yi)
+        for(int xi = x_mi; xi < x_ma; ++xi)
+        {
+            const int val = src[(2 * y + yi) * scols + 2 * x + xi];
+            if(abs(val - center) < 3 * sigma_color)
+            {
+                sum += val * weights[abs(xi)] * weights[abs(yi)];
+                wall += weights[abs(xi)] * weights[abs(yi)];
+            }
+        }
+    return static_cast<unsigned short>(static_cast<int>(sum / wall));
+}
+
+// utils.cu:109-133 computeVmapKernel.  Returns false (vertex invalid) or the vertex.
+__device__ __forceinline__ bool vertex_from_depth(unsigned short d, int u, int v, float fx_inv, float fy_inv, float cx, float cy,
+                                                  float depthCutoff, float3 & p)
+{
+    const float z = d / 1000.f;
+    if(z != 0 && z < depthCutoff)
+    {
+        // explicit _rn multiplies: same roundings as the reference's stores, and they keep
+        // the compiler from fusing them into the normal's subtractions below
+        p.x = __fmul_rn(__fmul_rn(z, (u - cx)), fx_inv);
+        p.y = __fmul_rn(__fmul_rn(z, (v - cy)), fy_inv);
+        p.z = z;
+        return true;
+    }
+    return false;
+}
+
+// 5x5 {1,4,6,4,1}^2 pyramid tap loop shared by the float-depth and u8-intensity versions
+// (utils.cu:332-363 and 470-500): window [max(0,2x-2), min(2x+3, cols-1)), weight index
+// (ty-cy-1)*5+(tx-cx-1), integer `count`.
+__device__ __forceinline__ float gauss5_weight(int idx)
+{
+    const float k[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+    return k[idx];
+}
+
+__device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int srows, int scols, int x, int y)
+{
+    const int D = 5;
+    const int tx = min(2 * x - D / 2 + D, scols - 1);
+    const int ty = min(2 * y - D / 2 + D, srows - 1);
+    int cy = max(0, 2 * y - D / 2);
+    float sum = 0;
+    int count = 0;
+    for(; cy < ty; ++cy)
+        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
+        {
+            const float s = src[cy * scols + cx];
+            if(!isnan(s))
+            {
+                const float w = gauss5_weight((ty - cy - 1) * 5 + (tx - cx - 1));
+                sum += s * w;
+                count += w;
+            }
+        }
+    return (float)(sum / (float)count);
+}
+
+__device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned char * src, int srows, int scols, int x, int y)
+{
+    const int D = 5;
+    const int tx = min(2 * x - D / 2 + D, scols - 1);
+    const int ty = min(2 * y - D / 2 + D, srows - 1);
+    int cy = max(0, 2 * y - D / 2);
+    float sum = 0;
+    int count = 0;
+    for(; cy < ty; ++cy)
+        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
+        {
+            const unsigned char s = src[cy * scols + cx];
+            if(s > 0)
+            {
+                const float w = gauss5_weight((ty - cy - 1) * 5 + (tx - cx - 1));
+                sum += s * w;
+                count += w;
+            }
+        }
+    return (unsigned char)(sum / (float)count);
+}
+
+// utils.cu:550-563 bgr2IntensityKernel (c0,c1,c2 = first three bytes of the RGBA8 texel)
+__device__ __forceinline__ unsigned char intensity_pixel(uchar4 src)
+{
+    const int value = (float)src.x * 0.114f + (float)src.y * 0.299f + (float)src.z * 0.587f;
+    return (unsigned char)value;
+}
+
+// utils.cu:526-537 verticesToDepthKernel
+__device__ __forceinline__ float depth_from_vertex_z(float z, float cutOff) { return z > cutOff || z <= 0 ? SLAM_QNAN : z; }
+
+// ------------------------------------------------------------------ fused depth level
+// One launch per pyramid level l of the CURRENT frame:
+//   blocks [0, nb_map)  : depth_l -> vmap_l, nmap_l  (createVMap + createNMap, utils.cu:109-188)
+//   blocks [nb_map, ..) : depth_l -> depth_{l+1}     (pyrDown, utils.cu:57-94), if dst != nullptr
+__global__ void __launch_bounds__(256) k_depth_level(const unsigned short * __restrict__ depth, int rows, int cols, float fx_inv, float fy_inv,
+                                                     float cx, float cy, float depthCutoff, float * __restrict__ vmap, float * __restrict__ nmap,
+                                                     unsigned short * __restrict__ next_depth, int nb_map_x, int nb_map)
+{
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if((int)blockIdx.x < nb_map)
+    {
+        const int bx = blockIdx.x % nb_map_x, by = blockIdx.x / nb_map_x;
+        const int u = bx * 32 + tx, v = by * 8 + ty;
+        if(u >= cols || v >= rows) return;
+        const int plane = rows * cols;
+        const int o = v * cols + u;
+
+        float3 v00;
+        const bool ok00 = vertex_from_depth(depth[o], u, v, fx_inv, fy_inv, cx, cy, depthCutoff, v00);
+        if(ok00)
+        {
+            vmap[o] = v00.x;
+            vmap[o + plane] = v00.y;
+            vmap[o + 2 * plane] = v00.z;
+        }
+        else
+            vmap[o] = SLAM_QNAN;   // y,z planes keep stale data, as in the reference
+
+        if(u == cols - 1 || v == rows - 1)
+        {
+            nmap[o] = SLAM_QNAN;
+            return;
+        }
+        float3 v01, v10;
+        const bool ok01 = vertex_from_depth(depth[o + 1], u + 1, v, fx_inv, fy_inv, cx, cy, depthCutoff, v01);
+        const bool ok10 = vertex_from_depth(depth[o + cols], u, v + 1, fx_inv, fy_inv, cx, cy, depthCutoff, v10);
+        if(ok00 && ok01 && ok10)
+        {
+            const float3 r = unit3(cross3(v01 - v00, v10 - v00));
+            nmap[o] = r.x;
+            nmap[o + plane] = r.y;
+            nmap[o + 2 * plane] = r.z;
+        }
+        else
+            nmap[o] = SLAM_QNAN;
+    }
+    else
+    {
+        const int drows = rows / 2, dcols = cols / 2;
+        const int nbx = div_up(dcols, 32);
+        const int b = blockIdx.x - nb_map;
+        const int x = (b % nbx) * 32 + tx, y = (b / nbx) * 8 + ty;
+        if(x >= dcols || y >= drows) return;
+        next_depth[y * dcols + x] = pyr_down_u16_pixel(depth, rows, cols, x, y);
+    }
+}
+
+// ------------------------------------------------------------------ fused model maps
+// initICPModel / initICP(maps): RGBA32F vertex+normal (camera frame) -> planar maps of all
+// levels, optionally moved to the global frame.  One thread owns a 4x4 block of level-0
+// pixels = 2x2 of level 1 = 1 of level 2 (copyMaps utils.cu:270-310, resizeMap :365-416,
+// tranformMaps :206-248, verticesToDepth :526-537 for the RGB path's depth source).
+struct ModelMapsArgs
+{
+    const float4 * vsrc;
+    const float4 * nsrc;
+    int rows, cols;        // level 0
+    int levels;            // 1..3 handled here
+    float * vdst[3];
+    float * ndst[3];
+    int transform;         // 0: keep camera frame (initICP maps overload), 1: apply R,t
+    Mat3 R;
+    float3 t;
+    float * depth_tmp;     // [rows][cols] z of the vertex map with the maxDepthRGB cut, or nullptr
+    float depth_cut;
+    float * vcam2;         // optional camera-frame copies of level 2 (source of a 4th level), or nullptr
+    float * ncam2;
+};
+
+__device__ __forceinline__ void store_map_pixel(float * vdst, float * ndst, int plane, int o, float3 v, float3 n, bool transform, const Mat3 & R,
+                                                const float3 & t)
+{
+    // tranformMapsKernel semantics: NaN in x => only the x plane is (re)written
+    if(transform)
+    {
+        if(!isnan(v.x))
+        {
+            const float3 d = R * v + t;
+            vdst[o] = d.x;
+            vdst[o + plane] = d.y;
+            vdst[o + 2 * plane] = d.z;
+        }
+        else
+            vdst[o] = SLAM_QNAN;
+        if(!isnan(n.x))
+        {
+            const float3 d = R * n;
+            ndst[o] = d.x;
+            ndst[o + plane] = d.y;
+            ndst[o + 2 * plane] = d.z;
+        }
+        else
+            ndst[o] = SLAM_QNAN;
+    }
+    else
+    {
+        vdst[o] = v.x;
+        ndst[o] = n.x;
+        if(!isnan(v.x))
+        {
+            vdst[o + plane] = v.y;
+            vdst[o + 2 * plane] = v.z;
+        }
+        if(!isnan(n.x))
+        {
+            ndst[o + plane] = n.y;
+            ndst[o + 2 * plane] = n.z;
+        }
+    }
+}
+
+// 2x2 average with the reference's NaN rule (any NaN x => result x NaN, y/z untouched).
+template <bool normalize>
+__device__ __forceinline__ float3 resize4(const float3 & a00, const float3 & a01, const float3 & a10, const float3 & a11)
+{
+    float3 n;
+    if(isnan(a00.x) || isnan(a01.x) || isnan(a10.x) || isnan(a11.x))
+    {
+        n.x = SLAM_QNAN;
+        n.y = n.z = 0.f;
+        return n;
+    }
+    n.x = (a00.x + a01.x + a10.x + a11.x) / 4;
+    n.y = (a00.y + a01.y + a10.y + a11.y) / 4;
+    n.z = (a00.z + a01.z + a10.z + a11.z) / 4;
+    if(normalize) n = unit3(n);
+    return n;
+}
+
+__global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a)
+{
+    // thread -> 4x4 block; consecutive threads walk along x
+    const int bcols = div_up(a.cols, 4), brows = div_up(a.rows, 4);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b >= bcols * brows) return;
+    const int bx = b % bcols, by = b / bcols;
+
+    float3 v0[4][4], n0[4][4];
+    const int plane0 = a.rows * a.cols;
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+#pragma unroll
+        for(int i = 0; i < 4; i++)
+        {
+            const int x = bx * 4 + i, y = by * 4 + j;
+            float3 v = make_float3(SLAM_QNAN, SLAM_QNAN, SLAM_QNAN), n = v;
+            if(x < a.cols && y < a.rows)
+            {
+                const float4 vs = __ldg(a.vsrc + y * a.cols + x);
+                const float4 ns = __ldg(a.nsrc + y * a.cols + x);
+                if(!(vs.z == 0))   // copyMapsKernel: validity of BOTH maps keyed on the vertex z
+                {
+                    v = make_float3(vs.x, vs.y, vs.z);
+                    n = make_float3(ns.x, ns.y, ns.z);
+                }
+                if(a.depth_tmp) a.depth_tmp[y * a.cols + x] = depth_from_vertex_z(vs.z, a.depth_cut);
+                // level-0 copyMaps writes all three planes, NaN included
+                if(a.transform)
+                    store_map_pixel(a.vdst[0], a.ndst[0], plane0, y * a.cols + x, v, n, true, a.R, a.t);
+                else
+                {
+                    const int o = y * a.cols + x;
+                    a.vdst[0][o] = v.x; a.vdst[0][o + plane0] = v.y; a.vdst[0][o + 2 * plane0] = v.z;
+                    a.ndst[0][o] = n.x; a.ndst[0][o + plane0] = n.y; a.ndst[0][o + 2 * plane0] = n.z;
+                }
+            }
+            v0[j][i] = v;
+            n0[j][i] = n;
+        }
+    if(a.levels < 2) return;
+
+    const int rows1 = a.rows / 2, cols1 = a.cols / 2, plane1 = rows1 * cols1;
+    float3 v1[2][2], n1[2][2];
+#pragma unroll
+    for(int j = 0; j < 2; j++)
+#pragma unroll
+        for(int i = 0; i < 2; i++)
+        {
+            v1[j][i] = resize4<false>(v0[2 * j][2 * i], v0[2 * j][2 * i + 1], v0[2 * j + 1][2 * i], v0[2 * j + 1][2 * i + 1]);
+            n1[j][i] = resize4<true>(n0[2 * j][2 * i], n0[2 * j][2 * i + 1], n0[2 * j + 1][2 * i], n0[2 * j + 1][2 * i + 1]);
+            const int x = bx * 2 + i, y = by * 2 + j;
+            if(x < cols1 && y < rows1) store_map_pixel(a.vdst[1], a.ndst[1], plane1, y * cols1 + x, v1[j][i], n1[j][i], a.transform, a.R, a.t);
+        }
+    if(a.levels < 3) return;
+
+    const int rows2 = rows1 / 2, cols2 = cols1 / 2, plane2 = rows2 * cols2;
+    if(bx < cols2 && by < rows2)
+    {
+        const float3 v2 = resize4<false>(v1[0][0], v1[0][1], v1[1][0], v1[1][1]);
+        const float3 n2 = resize4<true>(n1[0][0], n1[0][1], n1[1][0], n1[1][1]);
+        store_map_pixel(a.vdst[2], a.ndst[2], plane2, by * cols2 + bx, v2, n2, a.transform, a.R, a.t);
+        if(a.vcam2) store_map_pixel(a.vcam2, a.ncam2, plane2, by * cols2 + bx, v2, n2, false, a.R, a.t);
+    }
+}
+
+// Levels beyond the third (the reference's NUM_PYRS is 3; BASELINE config 3 asks for 4):
+// resize a camera-frame level and write it transformed, same per-level operators.
+__global__ void __launch_bounds__(256) k_resize_transform(const float * vsrc, const float * nsrc, int srows, int scols, float * vdst, float * ndst,
+                                                          int transform, const Mat3 R, const float3 t, float * vcam, float * ncam)
+{
+    const int drows = srows / 2, dcols = scols / 2;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if(o >= drows * dcols) return;
+    const int y = o / dcols, x = o - y * dcols;
+    const int splane = srows * scols, dplane = drows * dcols;
+    const int s = (2 * y) * scols + 2 * x;
+    float3 v[4], n[4];
+    const int offs[4] = {s, s + 1, s + scols, s + scols + 1};
+#pragma unroll
+    for(int k = 0; k < 4; k++)
+    {
+        v[k] = make_float3(vsrc[offs[k]], vsrc[offs[k] + splane], vsrc[offs[k] + 2 * splane]);
+        n[k] = make_float3(nsrc[offs[k]], nsrc[offs[k] + splane], nsrc[offs[k] + 2 * splane]);
+    }
+    const float3 vr = resize4<false>(v[0], v[1], v[2], v[3]);
+    const float3 nr = resize4<true>(n[0], n[1], n[2], n[3]);
+    store_map_pixel(vdst, ndst, dplane, o, vr, nr, transform, R, t);
+    if(vcam) store_map_pixel(vcam, ncam, dplane, o, vr, nr, false, R, t);
+}
+
+// ------------------------------------------------------------------ RGB-D pyramids
+// populateRGBDData (RGBDOdometryef.cpp:208-235) in three dependent launches instead of
+// six kernels + four cudaMalloc/cudaFree:
+//   k_rgbd_level0 : depth_tmp -> depth[0] (copy), rgba -> image[0]
+//   k_rgbd_down   : depth[l] -> depth[l+1] and image[l] -> image[l+1]   (l = 0, 1)
+__global__ void __launch_bounds__(256) k_rgbd_level0(const float * __restrict__ depth_tmp, float * __restrict__ depth0, const uchar4 * __restrict__ rgba,
+                                                     unsigned char * __restrict__ image0, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(depth0) depth0[i] = depth_tmp[i];
+    image0[i] = intensity_pixel(__ldg(rgba + i));
+}
+
+__global__ void __launch_bounds__(256) k_rgbd_down(const float * __restrict__ dsrc, float * __restrict__ ddst, const unsigned char * __restrict__ isrc,
+                                                   unsigned char * __restrict__ idst, int srows, int scols)
+{
+    const int drows = srows / 2, dcols = scols / 2;
+    const int nbx = div_up(dcols, 32);
+    const int x = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
+    const int y = (blockIdx.x / nbx) * 8 + (threadIdx.x >> 5);
+    if(x >= dcols || y >= drows) return;
+    if(ddst) ddst[y * dcols + x] = pyr_down_gauss_f_pixel(dsrc, srows, scols, x, y);
+    if(idst) idst[y * dcols + x] = pyr_down_gauss_u8_pixel(isrc, srows, scols, x, y);
+}
+
+// ------------------------------------------------------------------ image derivatives
+// applyKernel, utils.cu:582-606: running kernelIndex from 8 downwards over the CLIPPED
+// window (border taps misalign, on purpose), float -> short truncation.  All levels in
+// one launch: level l owns blocks [first[l], first[l+1]).
+struct DerivArgs
+{
+    const unsigned char * src[SLAM_MAX_LEVELS];
+    short * dx[SLAM_MAX_LEVELS];
+    short * dy[SLAM_MAX_LEVELS];
+    int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
+    int first[SLAM_MAX_LEVELS + 1];
+    int levels;
+};
+
+__device__ __forceinline__ void derivative_pixel(const unsigned char * src, int rows, int cols, int x, int y, short & dx, short & dy)
+{
+    const float gx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+    const float gy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+    float dxVal = 0;
+    float dyVal = 0;
+    int kernelIndex = 8;
+    for(int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
+        for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
+        {
+            const float s = (float)src[j * cols + i];
+            dxVal += s * gx[kernelIndex];
+            dyVal += s * gy[kernelIndex];
+            --kernelIndex;
+        }
+    dx = (short)dxVal;
+    dy = (short)dyVal;
+}
+
+__global__ void __launch_bounds__(256) k_derivatives(const DerivArgs a)
+{
+    int l = 0;
+    while(l + 1 < a.levels && (int)blockIdx.x >= a.first[l + 1]) l++;
+    const int rows = a.rows[l], cols = a.cols[l];
+    const int nbx = div_up(cols, 32);
+    const int b = blockIdx.x - a.first[l];
+    const int x = (b % nbx) * 32 + (threadIdx.x & 31);
+    const int y = (b / nbx) * 8 + (threadIdx.x >> 5);
+    if(x >= cols || y >= rows) return;
+    short dx, dy;
+    derivative_pixel(a.src[l], rows, cols, x, y, dx, dy);
+    a.dx[l][y * cols + x] = dx;
+    a.dy[l][y * cols + x] = dy;
+}
+
+// ------------------------------------------------------------------ un-fused operator kernels
+__global__ void __launch_bounds__(256) k_pyr_down_u16(const unsigned short * src, int srows, int scols, unsigned short * dst)
+{
+    const int drows = srows / 2, dcols = scols / 2;
+    const int nbx = div_up(dcols, 32);
+    const int x = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
+    const int y = (blockIdx.x / nbx) * 8 + (threadIdx.x >> 5);
+    if(x >= dcols || y >= drows) return;
+    dst[y * dcols + x] = pyr_down_u16_pixel(src, srows, scols, x, y);
+}
+
+__global__ void __launch_bounds__(256) k_create_vmap(const unsigned short * depth, int rows, int cols, float fx_inv, float fy_inv, float cx, float cy,
+                                                     float depthCutoff, float * vmap)
+{
+    const int nbx = div_up(cols, 32);
+    const int u = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
+    const int v = (blockIdx.x / nbx) * 8 + (threadIdx.x >> 5);
+    if(u >= cols || v >= rows) return;
+    const int plane = rows * cols, o = v * cols + u;
+    float3 p;
+    if(vertex_from_depth(depth[o], u, v, fx_inv, fy_inv, cx, cy, depthCutoff, p))
+    {
+        vmap[o] = p.x;
+        vmap[o + plane] = p.y;
+        vmap[o + 2 * plane] = p.z;
+    }
+    else
+        vmap[o] = SLAM_QNAN;
+}
+
+// utils.cu:151-188 computeNmapKernel (reads an existing vertex map)
+__global__ void __launch_bounds__(256) k_create_nmap(const float * vmap, int rows, int cols, float * nmap)
+{
+    const int nbx = div_up(cols, 32);
+    const int u = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
+    const int v = (blockIdx.x / nbx) * 8 + (threadIdx.x >> 5);
+    if(u >= cols || v >= rows) return;
+    const int plane = rows * cols, o = v * cols + u;
+    if(u == cols - 1 || v == rows - 1)
+    {
+        nmap[o] = SLAM_QNAN;
+        return;
+    }
+    float3 v00, v01, v10;
+    v00.x = vmap[o];
+    v01.x = vmap[o + 1];
+    v10.x = vmap[o + cols];
+    if(!isnan(v00.x) && !isnan(v01.x) && !isnan(v10.x))
+    {
+        v00.y = vmap[o + plane];
+        v01.y = vmap[o + 1 + plane];
+        v10.y = vmap[o + cols + plane];
+        v00.z = vmap[o + 2 * plane];
+        v01.z = vmap[o + 1 + 2 * plane];
+        v10.z = vmap[o + cols + 2 * plane];
+        const float3 r = unit3(cross3(v01 - v00, v10 - v00));
+        nmap[o] = r.x;
+        nmap[o + plane] = r.y;
+        nmap[o + 2 * plane] = r.z;
+    }
+    else
+        nmap[o] = SLAM_QNAN;
+}
+
+__global__ void __launch_bounds__(256) k_transform_maps(const float * vsrc, const float * nsrc, int rows, int cols, const Mat3 R, const float3 t,
+                                                        float * vdst, float * ndst)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = rows * cols;
+    if(o >= plane) return;
+    float3 v = make_float3(vsrc[o], 0.f, 0.f), n = make_float3(nsrc[o], 0.f, 0.f);
+    if(!isnan(v.x))
+    {
+        v.y = vsrc[o + plane];
+        v.z = vsrc[o + 2 * plane];
+    }
+    if(!isnan(n.x))
+    {
+        n.y = nsrc[o + plane];
+        n.z = nsrc[o + 2 * plane];
+    }
+    store_map_pixel(vdst, ndst, plane, o, v, n, true, R, t);
+}
+
+template <bool normalize>
+__global__ void __launch_bounds__(256) k_resize_map(const float * src, int srows, int scols, float * dst)
+{
+    const int drows = srows / 2, dcols = scols / 2;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if(o >= drows * dcols) return;
+    const int y = o / dcols, x = o - y * dcols;
+    const int splane = srows * scols, dplane = drows * dcols;
+    const int s = (2 * y) * scols + 2 * x;
+    float3 a00, a01, a10, a11;
+    a00.x = src[s]; a01.x = src[s + 1]; a10.x = src[s + scols]; a11.x = src[s + scols + 1];
+    if(isnan(a00.x) || isnan(a01.x) || isnan(a10.x) || isnan(a11.x))
+    {
+        dst[o] = SLAM_QNAN;
+        return;
+    }
+    a00.y = src[s + splane]; a01.y = src[s + 1 + splane]; a10.y = src[s + scols + splane]; a11.y = src[s + scols + 1 + splane];
+    a00.z = src[s + 2 * splane]; a01.z = src[s + 1 + 2 * splane]; a10.z = src[s + scols + 2 * splane]; a11.z = src[s + scols + 1 + 2 * splane];
+    const float3 n = resize4<normalize>(a00, a01, a10, a11);
+    dst[o] = n.x;
+    dst[o + dplane] = n.y;
+    dst[o + 2 * dplane] = n.z;
+}
+
+__global__ void __launch_bounds__(256) k_vertices_to_depth(const float4 * vsrc, int n, float * dst, float cutOff)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    dst[i] = depth_from_vertex_z(__ldg(vsrc + i).z, cutOff);
+}
+
+// utils.cu:640-658 projectPointsKernel
+__global__ void __launch_bounds__(256) k_project_points(const float * depth, int rows, int cols, float * cloud3, float invFx, float invFy, float cx,
+                                                        float cy)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if(o >= rows * cols) return;
+    const int y = o / cols, x = o - y * cols;
+    const float3 p = cloud_point(depth, cols, x, y, invFx, invFy, cx, cy);
+    cloud3[3 * o + 0] = p.x;
+    cloud3[3 * o + 1] = p.y;
+    cloud3[3 * o + 2] = p.z;
+}
+
+// ------------------------------------------------------------------ host launchers
+static inline int tiles_32x8(int rows, int cols) { return div_up(cols, 32) * div_up(rows, 8); }
+
+int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,
+                       float * nmap, unsigned short * next_depth, cudaStream_t s)
+{
+    const int nb_map_x = div_up(cols, 32);
+    const int nb_map = tiles_32x8(rows, cols);
+    const int nb_down = next_depth ? tiles_32x8(rows / 2, cols / 2) : 0;
+    k_depth_level<<<nb_map + nb_down, 256, 0, s>>>(depth, rows, cols, 1.f / fx, 1.f / fy, cx, cy, depthCutoff, vmap, nmap, next_depth, nb_map_x, nb_map);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_model_maps(const ModelMapsArgs & a, cudaStream_t s)
+{
+    const int nblk = div_up(a.cols, 4) * div_up(a.rows, 4);
+    k_model_maps<<<div_up(nblk, 128), 128, 0, s>>>(a);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_resize_transform(const float * vsrc, const float * nsrc, int srows, int scols, float * vdst, float * ndst, int transform, const Mat3 & R,
+                            const float3 & t, float * vcam, float * ncam, cudaStream_t s)
+{
+    k_resize_transform<<<div_up((srows / 2) * (scols / 2), 256), 256, 0, s>>>(vsrc, nsrc, srows, scols, vdst, ndst, transform, R, t, vcam, ncam);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * rgba, unsigned char * image0, int n, cudaStream_t s)
+{
+    k_rgbd_level0<<<div_up(n, 256), 256, 0, s>>>(depth_tmp, depth0, rgba, image0, n);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_rgbd_down(const float * dsrc, float * ddst, const unsigned char * isrc, unsigned char * idst, int srows, int scols, cudaStream_t s)
+{
+    k_rgbd_down<<<tiles_32x8(srows / 2, scols / 2), 256, 0, s>>>(dsrc, ddst, isrc, idst, srows, scols);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_derivatives(DerivArgs & a, cudaStream_t s)
+{
+    int total = 0;
+    for(int l = 0; l < a.levels; l++)
+    {
+        a.first[l] = total;
+        total += tiles_32x8(a.rows[l], a.cols[l]);
+    }
+    a.first[a.levels] = total;
+    k_derivatives<<<total, 256, 0, s>>>(a);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
+                             int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
+                             cudaStream_t s)
+{
+    ModelMapsArgs a = {};
+    a.vsrc = vsrc;
+    a.nsrc = nsrc;
+    a.rows = rows;
+    a.cols = cols;
+    a.levels = levels < 3 ? levels : 3;
+    for(int l = 0; l < a.levels; l++)
+    {
+        a.vdst[l] = vdst[l];
+        a.ndst[l] = ndst[l];
+    }
+    a.transform = transform;
+    a.R = R;
+    a.t = t;
+    a.depth_tmp = depth_tmp;
+    a.depth_cut = depth_cut;
+    a.vcam2 = vcam2;
+    a.ncam2 = ncam2;
+    return launch_model_maps(a, s);
+}
+
+int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
+                              cudaStream_t s)
+{
+    DerivArgs a = {};
+    a.levels = levels;
+    for(int l = 0; l < levels; l++)
+    {
+        a.src[l] = src[l];
+        a.dx[l] = dx[l];
+        a.dy[l] = dy[l];
+        a.rows[l] = rows[l];
+        a.cols[l] = cols[l];
+    }
+    return launch_derivatives(a, s);
+}
+
+}   // namespace slam
+
+// ------------------------------------------------------------------ C ABI (operators)
+using namespace slam;
+
+extern "C" int slam_op_pyr_down(const uint16_t * src, int src_rows, int src_cols, uint16_t * dst, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src_rows > 1 && src_cols > 1);
+    k_pyr_down_u16<<<tiles_32x8(src_rows / 2, src_cols / 2), 256, 0, (cudaStream_t)stream>>>(src, src_rows, src_cols, dst);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_create_vmap(float fx, float fy, float cx, float cy, const uint16_t * depth, int rows, int cols, float * vmap,
+                                   float depth_cutoff, void * stream)
+{
+    SLAM_ARG_CHECK(depth && vmap && rows > 0 && cols > 0);
+    k_create_vmap<<<tiles_32x8(rows, cols), 256, 0, (cudaStream_t)stream>>>(depth, rows, cols, 1.f / fx, 1.f / fy, cx, cy, depth_cutoff, vmap);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_create_nmap(const float * vmap, int rows, int cols, float * nmap, void * stream)
+{
+    SLAM_ARG_CHECK(vmap && nmap && rows > 0 && cols > 0);
+    k_create_nmap<<<tiles_32x8(rows, cols), 256, 0, (cudaStream_t)stream>>>(vmap, rows, cols, nmap);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_transform_maps(const float * vmap_src, const float * nmap_src, int rows, int cols, const float * R9, const float * t3,
+                                      float * vmap_dst, float * nmap_dst, void * stream)
+{
+    SLAM_ARG_CHECK(vmap_src && nmap_src && R9 && t3 && vmap_dst && nmap_dst && rows > 0 && cols > 0);
+    k_transform_maps<<<div_up(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(vmap_src, nmap_src, rows, cols, mat3_from(R9),
+                                                                                 make_float3(t3[0], t3[1], t3[2]), vmap_dst, nmap_dst);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_copy_maps(const float * vertices4, const float * normals4, int rows, int cols, float * vmap_dst, float * nmap_dst,
+                                 void * stream)
+{
+    SLAM_ARG_CHECK(vertices4 && normals4 && vmap_dst && nmap_dst && rows > 0 && cols > 0);
+    ModelMapsArgs a = {};
+    a.vsrc = reinterpret_cast<const float4 *>(vertices4);
+    a.nsrc = reinterpret_cast<const float4 *>(normals4);
+    a.rows = rows; a.cols = cols; a.levels = 1;
+    a.vdst[0] = vmap_dst; a.ndst[0] = nmap_dst;
+    a.transform = 0;
+    a.depth_tmp = nullptr;
+    return launch_model_maps(a, (cudaStream_t)stream);
+}
+
+extern "C" int slam_op_resize_vmap(const float * src, int src_rows, int src_cols, float * dst, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src_rows > 1 && src_cols > 1);
+    k_resize_map<false><<<div_up((src_rows / 2) * (src_cols / 2), 256), 256, 0, (cudaStream_t)stream>>>(src, src_rows, src_cols, dst);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_resize_nmap(const float * src, int src_rows, int src_cols, float * dst, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src_rows > 1 && src_cols > 1);
+    k_resize_map<true><<<div_up((src_rows / 2) * (src_cols / 2), 256), 256, 0, (cudaStream_t)stream>>>(src, src_rows, src_cols, dst);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_image_bgr_to_intensity(const uint8_t * rgba, int rows, int cols, uint8_t * dst, void * stream)
+{
+    SLAM_ARG_CHECK(rgba && dst && rows > 0 && cols > 0);
+    return launch_rgbd_level0(nullptr, nullptr, reinterpret_cast<const uchar4 *>(rgba), dst, rows * cols, (cudaStream_t)stream);
+}
+
+extern "C" int slam_op_vertices_to_depth(const float * vertices4, int rows, int cols, float * dst, float cutoff, void * stream)
+{
+    SLAM_ARG_CHECK(vertices4 && dst && rows > 0 && cols > 0);
+    k_vertices_to_depth<<<div_up(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(vertices4), rows * cols, dst, cutoff);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_project_to_point_cloud(const float * depth, int rows, int cols, float * cloud3, float fx, float fy, float cx, float cy,
+                                              int level, void * stream)
+{
+    SLAM_ARG_CHECK(depth && cloud3 && rows > 0 && cols > 0 && level >= 0 && level < 16);
+    const int div = 1 << level;   // CameraModel::operator()(level), sensors/Camera.h:14-18
+    const float lfx = fx / div, lfy = fy / div, lcx = cx / div, lcy = cy / div;
+    k_project_points<<<div_up(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(depth, rows, cols, cloud3, 1.0f / lfx, 1.0f / lfy, lcx, lcy);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_op_pyr_down_gauss_f(const float * src, int src_rows, int src_cols, float * dst, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src_rows > 1 && src_cols > 1);
+    return launch_rgbd_down(src, dst, nullptr, nullptr, src_rows, src_cols, (cudaStream_t)stream);
+}
+
+extern "C" int slam_op_pyr_down_uchar_gauss(const uint8_t * src, int src_rows, int src_cols, uint8_t * dst, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src_rows > 1 && src_cols > 1);
+    return launch_rgbd_down(nullptr, nullptr, src, dst, src_rows, src_cols, (cudaStream_t)stream);
+}
+
+extern "C" int slam_op_compute_derivative_images(const uint8_t * src, int rows, int cols, int16_t * dx, int16_t * dy, void * stream)
+{
+    SLAM_ARG_CHECK(src && dx && dy && rows > 0 && cols > 0);
+    DerivArgs a = {};
+    a.levels = 1;
+    a.src[0] = src; a.dx[0] = dx; a.dy[0] = dy;
+    a.rows[0] = rows; a.cols[0] = cols;
+    return launch_derivatives(a, (cudaStream_t)stream);
+}
