@@ -167,6 +167,11 @@ typedef struct slam_step_record
     int rgb_count, rgb_sigma;   /* computeRgbResidual outputs */
     double x[6];                /* solved increment */
     float Rcurr[9], tcurr[3];   /* pose after the step */
+    /* inputs of the step, exactly as handed to the kernels (for teacher-forced replays in the tests) */
+    float Rcurr_in[9], tcurr_in[3];   /* icpStep: Rcurr, tcurr */
+    float krkinv_in[9], kt_in[3];     /* computeRgbResidual: krkinv, kt */
+    float sigma_in;                   /* rgbStep: sigma */
+    float so3_in[27];                 /* kind 0: so3Step imageBasis, kinv, krlr; kind 1: [0..8] = icpStep Rprev_inv */
 } slam_step_record;
 int slam_odom_set_trace(slam_odom_t h, int enable);
 int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_records, int * n_records);

@@ -240,6 +240,7 @@ struct RefOdom
                 {
                     rec.kind = 0; rec.level = pyramidLevel; rec.iteration = i;
                     outDataSO3.download((JtJJtrSO3 *)rec.so3);
+                    memcpy(rec.so3_in, Hf, 36); memcpy(rec.so3_in + 9, Kinvf, 36); memcpy(rec.so3_in + 18, KRf, 36);
                 }
                 bool stop = false;
                 if(lastSO3Error < lastError && lastCount == lastSO3Count)
@@ -321,6 +322,9 @@ struct RefOdom
                 slam_step_record rec;
                 memset(&rec, 0, sizeof(rec));
                 rec.kind = 1; rec.level = i; rec.iteration = j;
+                memcpy(rec.Rcurr_in, Rcurr, 36); memcpy(rec.tcurr_in, tcurr, 12);
+                memcpy(rec.so3_in, Rprev_inv, 36);
+                memcpy(rec.krkinv_in, krk, 36); rec.kt_in[0] = kt.x; rec.kt_in[1] = kt.y; rec.kt_in[2] = kt.z;
 
                 if(rgb)
                     computeRgbResidual(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0), nextdIdx[i], nextdIdy[i], lastDepth[i], nextDepth[i],
@@ -335,6 +339,7 @@ struct RefOdom
                 lastRGBError = rgbError;
                 lastRGBCount = rgbSize;
                 if(rgbOnly) sigmaVal = -1;
+                rec.sigma_in = sigmaVal;
 
                 float A_icp[36] = {0}, b_icp[6] = {0};
                 mat33 device_Rcurr = to_mat33(Rcurr);
@@ -432,7 +437,7 @@ extern "C" {
 void * ref_odom_create(int width, int height, float cx, float cy, float fx, float fy, float distThresh, float angleThresh)
 {
     if(distThresh == 0) distThresh = 0.10f;
-    if(angleThresh == 0) angleThresh = sin(20.f * 3.14159254f / 180.f);
+    if(angleThresh == 0) angleThresh = sinf(20.f * 3.14159254f / 180.f);
     return new RefOdom(width, height, cx, cy, fx, fy, distThresh, angleThresh);
 }
 void ref_odom_destroy(void * h) { delete (RefOdom *)h; }

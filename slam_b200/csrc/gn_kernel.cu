@@ -182,6 +182,12 @@ __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record 
         rec->level = 2;
         rec->iteration = it;
         for(int k = 0; k < 11; k++) rec->so3[k] = s[k];
+        for(int k = 0; k < 9; k++)
+        {
+            rec->so3_in[k] = sh.so3H[k];
+            rec->so3_in[9 + k] = sh.so3Kinv[k];
+            rec->so3_in[18 + k] = sh.so3KR[k];
+        }
     }
 
     bool stop = false;
@@ -250,6 +256,7 @@ __device__ __noinline__ void gn_sigma(GnShared & sh, const bool rgb_only, slam_s
     sh.sigmaVal = sigmaVal;
     if(rec)
     {
+        rec->sigma_in = sigmaVal;
         rec->rgb_count = rgbSize;
         rec->rgb_sigma = sigma;
     }
@@ -466,6 +473,17 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         rec->kind = 1;
                         rec->level = lvl;
                         rec->iteration = j;
+                        for(int k = 0; k < 9; k++)
+                        {
+                            rec->Rcurr_in[k] = sh.Rcurr[k];
+                            rec->krkinv_in[k] = sh.krk[k];
+                            rec->so3_in[k] = sh.Rprev_inv[k];
+                        }
+                        for(int k = 0; k < 3; k++)
+                        {
+                            rec->tcurr_in[k] = sh.tcurr[k];
+                            rec->kt_in[k] = sh.kt[k];
+                        }
                     }
                 }
                 __syncthreads();

@@ -391,6 +391,9 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
             rec.level = L;
             rec.iteration = i;
             memcpy(rec.so3, h->h_sums, 11 * 4);
+            memcpy(rec.so3_in, Hf, 36);
+            memcpy(rec.so3_in + 9, Kinvf, 36);
+            memcpy(rec.so3_in + 18, KRf, 36);
 
             bool stop = false;
             if(st.lastSO3Error < lastError && lastCount == st.lastSO3Count)
@@ -470,6 +473,11 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
             rec.kind = 1;
             rec.level = i;
             rec.iteration = j;
+            memcpy(rec.Rcurr_in, Rcurr, 36);
+            memcpy(rec.tcurr_in, tcurr, 12);
+            memcpy(rec.krkinv_in, krk, 36);
+            memcpy(rec.so3_in, Rprev_inv, 36);
+            memcpy(rec.kt_in, kt, 12);
 
             if(rgb)
             {
@@ -506,6 +514,7 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
             st.lastRGBCount = rgbSize;
 
             if(rgbOnly) sigmaVal = -1;
+            rec.sigma_in = sigmaVal;
 
             float A_icp[36] = {0}, b_icp[6] = {0}, A_rgbd[36] = {0}, b_rgbd[6] = {0};
 

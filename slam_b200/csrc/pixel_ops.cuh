@@ -22,10 +22,19 @@ struct Mat3
 
 __device__ __forceinline__ float3 operator-(const float3 & a, const float3 & b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator+(const float3 & a, const float3 & b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float dot3(const float3 & a, const float3 & b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// dot / cross are written with explicit roundings: exactly the instruction sequence nvcc
+// (-fmad=true) emits for the reference's `a.x*b.x + a.y*b.y + a.z*b.z` and
+// `a.y*b.z - a.z*b.y` (cuda/operators.cuh:67-75), read off the reference's sm_100a SASS
+// (computeNmapKernel, resizeMapKernel, icpKernel): the middle product is rounded, the outer
+// two are fused.  Pinning them keeps fused kernels bit-identical to the reference whatever
+// contraction choices the compiler would make in a different inlining context.
+__device__ __forceinline__ float dot3(const float3 & a, const float3 & b)
+{
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
 __device__ __forceinline__ float3 cross3(const float3 & a, const float3 & b)
 {
-    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return make_float3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
 }
 __device__ __forceinline__ float norm3(const float3 & a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ float3 unit3(const float3 & a)   // cuda/operators.cuh:82-86 (rsqrtf)
@@ -34,6 +43,26 @@ __device__ __forceinline__ float3 unit3(const float3 & a)   // cuda/operators.cu
     return make_float3(a.x * rn, a.y * rn, a.z * rn);
 }
 __device__ __forceinline__ float3 operator*(const Mat3 & m, const float3 & a) { return make_float3(dot3(m.r0, a), dot3(m.r1, a), dot3(m.r2, a)); }
+
+// `a / b` exactly as nvcc --prec-div=false lowers it on sm_100a (div.approx.ftz.f32, seen in the
+// reference's SASS as MUFU.RCP + FMUL with both operands pre-scaled by 1/4 when |b| > 2^126),
+// split in two so that the final multiply can be fused with a following add where ptxas does so
+// in the reference (icpKernel: x*fx/z + cx  ->  FFMA(rcp, x*fx, cx)).
+struct ApproxDivisor
+{
+    float rcp;
+    bool big;
+};
+__device__ __forceinline__ ApproxDivisor approx_divisor(float b)
+{
+    ApproxDivisor d;
+    d.big = fabsf(b) > 8.50705917302346158658e+37f;
+    const float bs = d.big ? __fmul_rn(b, 0.25f) : b;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(d.rcp) : "f"(bs));
+    return d;
+}
+__device__ __forceinline__ float approx_div(float a, const ApproxDivisor & d) { return __fmul_rn(d.rcp, d.big ? __fmul_rn(a, 0.25f) : a); }
+__device__ __forceinline__ float approx_div_add(float a, const ApproxDivisor & d, float c) { return __fmaf_rn(d.rcp, d.big ? __fmul_rn(a, 0.25f) : a, c); }
 
 __host__ __device__ inline Mat3 mat3_from(const float * p)
 {
@@ -72,8 +101,10 @@ __device__ __forceinline__ bool icp_pixel(const IcpArgs & a, const float3 vcurr,
     const float3 vcurr_g = a.Rcurr * vcurr + a.tcurr;
     const float3 vcurr_cp = a.Rprev_inv * (vcurr_g - a.tprev);
 
-    const int ux = __float2int_rn(vcurr_cp.x * a.fx / vcurr_cp.z + a.cx);
-    const int uy = __float2int_rn(vcurr_cp.y * a.fy / vcurr_cp.z + a.cy);
+    // vcurr_cp.x * fx / vcurr_cp.z + cx  (reduce.cu:295-296): one reciprocal shared by both components
+    const ApproxDivisor dz = approx_divisor(vcurr_cp.z);
+    const int ux = __float2int_rn(approx_div_add(__fmul_rn(vcurr_cp.x, a.fx), dz, a.cx));
+    const int uy = __float2int_rn(approx_div_add(__fmul_rn(vcurr_cp.y, a.fy), dz, a.cy));
 
     if(ux < 0 || uy < 0 || ux >= a.cols || uy >= a.rows || vcurr_cp.z < 0) return false;
 
@@ -174,9 +205,16 @@ __device__ __forceinline__ bool rgb_candidate(const ResidualArgs & a, int j0, in
 __device__ __forceinline__ bool rgb_associate(const ResidualArgs & a, int x, int y, Corres & c)
 {
     const float d1 = a.nextDepth[y * a.cols + x];
-    const float transformed_d1 = (float)(d1 * (a.krkinv.r2.x * x + a.krkinv.r2.y * y + a.krkinv.r2.z) + a.kt.z);
-    const int u0 = __float2int_rn((d1 * (a.krkinv.r0.x * x + a.krkinv.r0.y * y + a.krkinv.r0.z) + a.kt.x) / transformed_d1);
-    const int v0 = __float2int_rn((d1 * (a.krkinv.r1.x * x + a.krkinv.r1.y * y + a.krkinv.r1.z) + a.kt.y) / transformed_d1);
+    // d1 * (k.x * x + k.y * y + k.z) + kt, the reference's roundings (residualKernel SASS): k.y*y rounded, k.x*x fused,
+    // + k.z added, then one FFMA with d1; the two quotients share one approximate reciprocal.
+    const float xf = (float)x, yf = (float)y;
+    const float s2 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r2.x, __fmul_rn(yf, a.krkinv.r2.y)), a.krkinv.r2.z);
+    const float s0 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r0.x, __fmul_rn(yf, a.krkinv.r0.y)), a.krkinv.r0.z);
+    const float s1 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r1.x, __fmul_rn(yf, a.krkinv.r1.y)), a.krkinv.r1.z);
+    const float transformed_d1 = __fmaf_rn(d1, s2, a.kt.z);
+    const ApproxDivisor dz = approx_divisor(transformed_d1);
+    const int u0 = __float2int_rn(approx_div(__fmaf_rn(d1, s0, a.kt.x), dz));
+    const int v0 = __float2int_rn(approx_div(__fmaf_rn(d1, s1, a.kt.y), dz));
 
     if(u0 >= 0 && v0 >= 0 && u0 < a.cols && v0 < a.rows)
     {
@@ -188,7 +226,7 @@ __device__ __forceinline__ bool rgb_associate(const ResidualArgs & a, int x, int
             c.zy = (short)v0;
             c.ox = (short)x;
             c.oy = (short)y;
-            c.diff = static_cast<float>(a.nextImage[y * a.cols + x]) - static_cast<float>(l);
+            c.diff = __fsub_rn(static_cast<float>(a.nextImage[y * a.cols + x]), static_cast<float>(l));
             c.valid = 1;
             return true;
         }
@@ -286,9 +324,15 @@ __device__ __forceinline__ bool so3_pixel(const So3Args & a, int x, int y, float
     row[0] = row[1] = row[2] = row[3] = 0.f;
 
     const float3 unwarped = make_float3((float)x, (float)y, 1.0f);
-    const float3 warped = a.imageBasis * unwarped;
-    const int wx = __float2int_rn(warped.x / warped.z);
-    const int wy = __float2int_rn(warped.y / warped.z);
+    // imageBasis * (x, y, 1) with the roundings of the reference's so3Kernel SASS.  The z = 1 term folds to
+    // an add; rows 1 and 2 round the y product and fuse the x product, row 0 is the other way round.
+    float3 warped;
+    warped.x = __fadd_rn(__fmaf_rn(unwarped.y, a.imageBasis.r0.y, __fmul_rn(unwarped.x, a.imageBasis.r0.x)), a.imageBasis.r0.z);
+    warped.y = __fadd_rn(__fmaf_rn(unwarped.x, a.imageBasis.r1.x, __fmul_rn(unwarped.y, a.imageBasis.r1.y)), a.imageBasis.r1.z);
+    warped.z = __fadd_rn(__fmaf_rn(unwarped.x, a.imageBasis.r2.x, __fmul_rn(unwarped.y, a.imageBasis.r2.y)), a.imageBasis.r2.z);
+    const ApproxDivisor dz = approx_divisor(warped.z);
+    const int wx = __float2int_rn(approx_div(warped.x, dz));
+    const int wy = __float2int_rn(approx_div(warped.y, dz));
 
     const bool found = wx >= 1 && wx < a.cols - 1 && wy >= 1 && wy < a.rows - 1 && x >= 1 && x < a.cols - 1 && y >= 1 && y < a.rows - 1;
     if(!found) return false;

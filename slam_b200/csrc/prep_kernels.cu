@@ -46,7 +46,10 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
 __device__ __forceinline__ bool vertex_from_depth(unsigned short d, int u, int v, float fx_inv, float fy_inv, float cx, float cy,
                                                   float depthCutoff, float3 & p)
 {
-    const float z = d / 1000.f;
+    // `depth / 1000.f` is a multiply by the rounded constant 0.001f in the reference's SASS
+    // (computeVmapKernel: FMUL.FTZ R, R, 0.0010000000474974513); written as such, with an explicit
+    // rounding, so it can never be fused into the subtractions of the normal computation below
+    const float z = __fmul_rn((float)d, 0.001f);
     if(z != 0 && z < depthCutoff)
     {
         // explicit _rn multiplies: same roundings as the reference's stores, and they keep
@@ -83,7 +86,7 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
             if(!isnan(s))
             {
                 const float w = gauss5_weight((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum += s * w;
+                sum = __fmaf_rn(s, w, sum);
                 count += w;
             }
         }
@@ -115,7 +118,8 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
 // utils.cu:550-563 bgr2IntensityKernel (c0,c1,c2 = first three bytes of the RGBA8 texel)
 __device__ __forceinline__ unsigned char intensity_pixel(uchar4 src)
 {
-    const int value = (float)src.x * 0.114f + (float)src.y * 0.299f + (float)src.z * 0.587f;
+    // (float)c0*0.114f + (float)c1*0.299f + (float)c2*0.587f with the reference's roundings (middle product rounded)
+    const int value = __fmaf_rn((float)src.z, 0.587f, __fmaf_rn((float)src.x, 0.114f, __fmul_rn((float)src.y, 0.299f)));
     return (unsigned char)value;
 }
 
@@ -403,8 +407,8 @@ __device__ __forceinline__ void derivative_pixel(const unsigned char * src, int 
         for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
         {
             const float s = (float)src[j * cols + i];
-            dxVal += s * gx[kernelIndex];
-            dyVal += s * gy[kernelIndex];
+            dxVal = __fmaf_rn(s, gx[kernelIndex], dxVal);
+            dyVal = __fmaf_rn(s, gy[kernelIndex], dyVal);
             --kernelIndex;
         }
     dx = (short)dxVal;

@@ -167,12 +167,12 @@ static void albedo(const double p[3], const double n[3], uint8_t rgb[3])
     /* three gratings + checker, per channel phase shifts; lambert-ish fixed shading per facet */
     double g1 = sin(2.0 * M_PI * (p[0] * 1.7 + p[1] * 0.6 + p[2] * 0.3));
     double g2 = sin(2.0 * M_PI * (p[0] * 0.4 - p[1] * 1.9 + p[2] * 1.1) + 1.3);
-    double g3 = sin(2.0 * M_PI * (-p[0] * 0.9 + p[1] * 0.5 + p[2] * 2.3) + 2.1);
+    double g3 = sin(2.0 * M_PI * (-p[0] * 9.0 + p[1] * 7.0 + p[2] * 11.0) + 2.1);
     int cx = (int)floor(p[0] / 0.25 + 1e-9), cy = (int)floor(p[1] / 0.25 + 1e-9), cz = (int)floor(p[2] / 0.25 + 1e-9);
     double chk = ((cx + cy + cz) & 1) ? 1.0 : -1.0;
     const double L[3] = {0.3, 0.8, 0.52};
     double sh = 0.75 + 0.25 * fabs(n[0] * L[0] + n[1] * L[1] + n[2] * L[2]);
-    double base[3] = {128 + 38 * g1 + 30 * g2 + 22 * chk, 128 + 30 * g2 + 38 * g3 - 22 * chk, 128 + 38 * g3 + 30 * g1 + 22 * chk};
+    double base[3] = {128 + 30 * g1 + 22 * g2 + 20 * g3 + 36 * chk, 128 + 22 * g2 + 30 * g3 + 20 * g1 + 36 * chk, 128 + 30 * g3 + 22 * g1 + 20 * g2 + 36 * chk};
     for(int c = 0; c < 3; c++)
     {
         double v = base[c] * sh;

