@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- RGB-D camera-tracking throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference arm (host cores)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...  # N > 1, one rank per GPU
+
+Workload (BASELINE.json configs[1]): ICP+RGB+SO3 frame-to-model odometry over a synthetic ICL-NUIM-shaped
+640x480 sequence (3-level pyramid, 10/5/4 iterations, icpWeight 10, so3 on).  A *step* is one tracked frame:
+initICPModel -> initRGBModel -> initICP(depth) -> initRGB -> getIncrementalTransformation, i.e. everything
+RGBDOdometryef does per frame (apps/elastic_fusion_file.cpp:366-374).  Inputs are open-loop (the model
+prediction of frame k is ray-cast at the ground-truth pose of frame k-1, outside the timed region), so every
+rank can replay its own sequence without a renderer in the loop.
+
+  value  frames/s, whole job, inputs already resident in HBM (device pointers through the C ABI)
+  e2e    frames/s through the host-buffer entry point of the C ABI (slam_odom_track_host): every step's depth,
+         RGB and model maps are copied from pinned host memory (H2D, prefetched one frame ahead on a copy
+         stream) and the pose is read back (D2H) inside the timed region
+  roofline     persistent Gauss-Newton kernel: algorithmic bytes (48 + 30 + 32 B per
+               pixel-iteration, 2 B per SO3 pixel-iteration) / its CUDA-event duration, vs the measured HBM peak
+  cpu_baseline the CPU port (oracle/odom_oracle.c, OpenMP, all host cores) on a bounded sample of the same frames
+  ref_cuda     (extra) the reference's own kernels + launch/sync pattern (oracle/_ref) on the same GPU and frames:
+               the denominator of the north-star's ">= 20x the reference's own CUDA path"
+
+Multi-GPU: independent sequences, one per rank (weak scaling), no collective on the data path; the only
+collectives are the barrier around the timed region and a max-reduce of the elapsed time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 640, 480
+LEVELS = 3
+ITERS = (10, 5, 4)
+N_FRAMES_DISTINCT = 96          # distinct frames cycled through: 96 x 12.9 MB = 1.24 GB of inputs >> 126 MB of L2
+DEPTH_CUTOFF, MODEL_CUTOFF = 3.0, 20.0
+BYTES_PER_FRAME_IN = W * H * (2 + 4 + 16 + 16 + 4)      # depth u16 + rgba + vertices + normals + model rgba
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def algorithmic_bytes_per_frame(so3_iters: float) -> float:
+    """SURVEY.md 8(d) / BASELINE.md 3: ICP 48 + RGB residual 30 + RGB step 32 B per pixel-iteration; SO3 2 B/px-iteration."""
+    px_iter = sum((W >> l) * (H >> l) * ITERS[l] for l in range(LEVELS))
+    return px_iter * 110.0 + so3_iters * (W >> 2) * (H >> 2) * 2.0
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_frames(seed: int, n: int):
+    """n open-loop frame pairs of one synthetic sequence (numpy, host)."""
+    from slam_b200.synth import Scene
+    scene = Scene(seed=0x51A7)
+    poses = scene.trajectory(1000, seed=0x51A7 + seed)
+    frames = []
+    stride = max(1, 900 // n)
+    for i in range(n):
+        k = 1 + i * stride
+        depth, rgba = scene.render_frame(poses[k])
+        mv, mn, mrgba = scene.render_model(poses[k - 1])
+        frames.append(dict(depth=depth, rgba=rgba, mv=mv, mn=mn, mrgba=mrgba, model_pose=poses[k - 1].copy(), gt_pose=poses[k].copy()))
+    first_rgba = scene.render_frame(poses[0])[1]
+    return frames, first_rgba
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.samples:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:   # region shorter than the sampling period: take whatever we have
+            for t, line in self.samples[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_port_fps(frames, first_rgba, n_frames: int):
+    """The CPU port on all host cores over n_frames of the workload; returns (frames/s, cores)."""
+    from oracle.cpu_oracle import CpuOdometry, load
+    lib = load()
+    cores = lib.oracle_num_threads()
+    odo = CpuOdometry(W, H, 319.5, 239.5, 481.20, -480.0)
+    odo.initFirstRGB(first_rgba)
+
+    def one(fr):
+        odo.initICPModel(fr["mv"], fr["mn"], MODEL_CUTOFF, fr["model_pose"])
+        odo.initRGBModel(fr["mrgba"])
+        odo.initICP(fr["depth"], DEPTH_CUTOFF)
+        odo.initRGB(fr["rgba"])
+        p = fr["model_pose"]
+        return odo.getIncrementalTransformation(p[:3, 3].copy(), p[:3, :3].copy(), False, 10.0, True, False, True)
+
+    one(frames[0])   # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        one(frames[i % len(frames)])
+    dt = time.perf_counter() - t0
+    odo.close()
+    return n_frames / dt, cores
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference has no CPU tracking path; its reduction math restated for the host
+    (oracle/odom_oracle.c, kind "port") runs on all host cores.  Rank 0 only; other ranks exit."""
+    if rank != 0:
+        return
+    frames, first_rgba = make_frames(0, 8)
+    # a step = one frame (~0.15 s on 8 cores): K steps + W warm-up stay within minutes for the driver's K
+    cpu_port_fps(frames, first_rgba, min(3, max(1, args.warmup)))   # warm-up
+    steps = max(1, args.steps)
+    fps, cores = cpu_port_fps(frames, first_rgba, steps)
+    line = {
+        "impl": "reference", "metric": "ICP+RGB tracking frames/sec @640x480", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} frames of the workload (full per-frame path: pyramids, maps, SO3 + 19 ICP+RGB iterations), oracle/odom_oracle.c, OpenMP"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference publishes no CPU path for RGBDOdometryef; this is its reduction math restated in C on the host cores (context only)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: ICP+RGB+SO3 frame-to-model odometry, synthetic ICL-NUIM-shaped 640x480 sequence, 3-level pyramid, 10/5/4 iterations, "
+                        "icpWeight 10, open-loop inputs", "frames_distinct": N_FRAMES_DISTINCT, "sequences": n_gpus,
+            "l2_policy": f"inputs larger than L2: {N_FRAMES_DISTINCT} distinct frames x {BYTES_PER_FRAME_IN / 1e6:.1f} MB cycled", "parallelism": f"1 sequence per GPU x {n_gpus}"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from slam_b200 import RGBDOdometry
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    t_gen = time.perf_counter()
+    frames, first_rgba = make_frames(rank, N_FRAMES_DISTINCT)
+    log(f"[rank {rank}] generated {len(frames)} synthetic frames in {time.perf_counter() - t_gen:.1f}s")
+
+    # ---- device-resident copies of all inputs
+    def up(a):
+        a = a.view(np.int16) if a.dtype == np.uint16 else a
+        return torch.from_numpy(a).to(dev)
+
+    dframes = [{k: (up(v) if k not in ("model_pose", "gt_pose") else v) for k, v in fr.items()} for fr in frames]
+    dfirst = up(first_rgba)
+    # ---- pinned host copies for the end-to-end arm
+    def pin(a):
+        a = a.view(np.int16) if a.dtype == np.uint16 else a
+        return torch.from_numpy(a).pin_memory()
+
+    hframes = [{k: (pin(v) if k not in ("model_pose", "gt_pose") else v) for k, v in fr.items()} for fr in frames]
+    torch.cuda.synchronize()
+
+    odo = RGBDOdometry(W, H, 319.5, 239.5, 481.20, -480.0, device=local_rank)
+    odo.initFirstRGB(dfirst)
+    dev_frames = [odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], d["model_pose"], DEPTH_CUTOFF, MODEL_CUTOFF) for d in dframes]
+    host_frames = [odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], d["model_pose"], DEPTH_CUTOFF, MODEL_CUTOFF) for d in hframes]
+    priors = [(fr["model_pose"][:3, 3].copy(), fr["model_pose"][:3, :3].copy()) for fr in frames]
+    nf = len(frames)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.ExternalStream(odo.stream, device=dev)
+
+    # ================= value: inputs resident in HBM =================
+    for i in range(args.warmup):
+        odo.track_device(dev_frames[i % nf], *priors[i % nf])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    odo.set_profiling(True)
+    odo.get_profile(reset=True)
+    launches0 = odo.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(stream)
+    so3_iters = 0
+    last = None
+    for i in range(args.steps):
+        j = (args.warmup + i) % nf
+        last = odo.track_device(dev_frames[j], *priors[j])
+    e1.record(stream)
+    barrier()
+    w1 = time.perf_counter()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(w0, w1)
+    gn_ms, gn_launches = odo.get_profile(reset=True)
+    odo.set_profiling(False)
+    launches = odo.launch_count() - launches0
+    so3_iters = odo.stats().so3_iterations
+    elapsed_ms = max_over_ranks(dev_ms)
+    value = world * args.steps / (elapsed_ms / 1e3)
+    # sanity: the last tracked pose must be close to the ground truth of that frame (no work skipped)
+    jlast = (args.warmup + args.steps - 1) % nf
+    err_mm = float(np.linalg.norm(last[0] - frames[jlast]["gt_pose"][:3, 3]) * 1e3)
+    prior_mm = float(np.linalg.norm(priors[jlast][0] - frames[jlast]["gt_pose"][:3, 3]) * 1e3)
+
+    # ================= e2e: host buffers through the C ABI =================
+    for i in range(args.warmup):
+        odo.track_host(host_frames[i % nf], *priors[i % nf])
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    j = args.warmup % nf
+    odo.prefetch_host(host_frames[j])
+    for i in range(args.steps):
+        j = (args.warmup + i) % nf
+        jn = (args.warmup + i + 1) % nf
+        if i + 1 < args.steps:
+            odo.prefetch_host(host_frames[jn])       # next frame's H2D overlaps this frame's solve
+        odo.track_host(host_frames[j], *priors[j])   # returns the pose (D2H) of this frame
+    e3.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3        # host wall clock of this rank: what the caller of the API sees
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), wall_ms))
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+
+    # ================= roofline of the dominant kernel =================
+    peak, peak_src = measured_peak()
+    alg_bytes = algorithmic_bytes_per_frame(so3_iters)
+    gn_us = gn_ms / max(1, gn_launches) * 1e3
+    achieved = alg_bytes / (gn_us * 1e-6) / 1e9 if gn_launches else None
+    traffic = None
+    tp = ROOT / "profiles" / "gn_kernel_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = None
+    if rank == 0:
+        # ---- context baselines (N = 1 only): CPU port and the reference's own CUDA path
+        cpu = None
+        ref_cuda = None
+        if world == 1 and not args.no_baselines:
+            try:
+                n_cpu = 60
+                fps_cpu, cores = cpu_port_fps(frames[:8], first_rgba, n_cpu)
+                cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "sample": f"{n_cpu} frames of the same workload (full per-frame path), oracle/odom_oracle.c with OpenMP on all host cores"}
+            except Exception as e:   # pragma: no cover
+                cpu = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
+            try:
+                from oracle import ref_cuda as rc
+                if rc.available():
+                    ref = rc.RefOdometry(W, H, 319.5, 239.5, 481.20, -480.0)
+                    ref.initFirstRGB(dfirst)
+
+                    def ref_frame(d):
+                        ref.initICPModel(d["mv"], d["mn"], MODEL_CUTOFF, d["model_pose"])
+                        ref.initRGBModel(d["mrgba"])
+                        ref.initICP(d["depth"], DEPTH_CUTOFF)
+                        ref.initRGB(d["rgba"])
+                        p = d["model_pose"]
+                        return ref.getIncrementalTransformation(p[:3, 3].copy(), p[:3, :3].copy(), False, 10.0, True, False, True)
+
+                    for i in range(10):
+                        ref_frame(dframes[i % nf])
+                    torch.cuda.synchronize()
+                    nref = 100
+                    t0 = time.perf_counter()
+                    for i in range(nref):
+                        ref_frame(dframes[(10 + i) % nf])
+                    torch.cuda.synchronize()
+                    ref_cuda = {"value": nref / (time.perf_counter() - t0), "unit": "frames/s",
+                                "kind": "reference kernels (src/odom/*.cu compiled for sm_100a) with the reference's launch/sync/malloc pattern, same GPU, same frames",
+                                "sample": f"{nref} frames, device-resident inputs"}
+                    ref.close()
+            except Exception as e:   # pragma: no cover
+                ref_cuda = {"value": None, "note": f"failed: {e}"}
+
+        line = {
+            "metric": "ICP+RGB tracking frames/sec @640x480", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "icp_iterations_per_s": value * sum(ITERS),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": BYTES_PER_FRAME_IN + 64, "d2h_bytes_per_step": 48,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_gn_persistent", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": peak_src, "us_per_launch": gn_us, "launches": int(gn_launches),
+                         "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": (gn_ms / dev_ms) if dev_ms else None,
+                         "note": "one launch = all SO3 + 19 ICP/RGB iterations of a frame; the 45 MB working set stays in the 126 MB L2, so DRAM traffic is far "
+                                 "below the algorithmic bytes and the kernel is latency-bound (grid barriers + fp64 solves), not bandwidth-bound"},
+            "cpu_baseline": cpu,
+            "ref_cuda": ref_cuda,
+            "clocks": clocks,
+            "check": {"last_frame_error_mm": err_mm, "prior_error_mm": prior_mm},
+        }
+    odo.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / ref_cuda context measurements")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 200   # bounded sample: ~0.15 s per frame on 8 cores
+        run_reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        log(f"--gpus {args.gpus} without torchrun: running a single rank (launch with torch.distributed.run for N > 1)")
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

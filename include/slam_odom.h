@@ -172,12 +172,24 @@ typedef struct slam_step_record
     float krkinv_in[9], kt_in[3];     /* computeRgbResidual: krkinv, kt */
     float sigma_in;                   /* rgbStep: sigma */
     float so3_in[27];                 /* kind 0: so3Step imageBasis, kinv, krlr; kind 1: [0..8] = icpStep Rprev_inv */
+    /* device-resident loop only: SM-clock timestamps (cycles since the kernel started, CTA 0) at
+     * [0] step begin, [1] parameters ready, [2] phase A mapped, [3] phase A published + barrier passed,
+     * [4] sigma known, [5] phase B mapped, [6] phase B published + barrier + fold done, [7] solve done */
+    unsigned int t_cycles[8];
 } slam_step_record;
+/* enable: 0 = off, 1 = step records only, 2 = records + the full DataTerm image of every RGB residual
+ * pass (what the reference writes; needed by SLAM_TAP_CORRES) */
 int slam_odom_set_trace(slam_odom_t h, int enable);
 int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_records, int * n_records);
 
-/* Kernel-launch counter (for bench.py's gpu_launches) and per-kernel CUDA-event timing. */
+/* Kernel-launch counter (for bench.py's gpu_launches). */
 long long slam_odom_launch_count(slam_odom_t h);
+/* CUDA-event timing of the persistent Gauss-Newton kernel on the handle's stream: enable, run,
+ * then read the accumulated device time and launch count (reset = 1 clears the totals). */
+int slam_odom_set_profiling(slam_odom_t h, int enable);
+int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_kernel_launches, int reset);
+/* The stream the handle runs on (cudaStream_t), e.g. to record the caller's own events on it. */
+void * slam_odom_stream(slam_odom_t h);
 
 /* ---- operator-level API: the free host wrappers of src/odom/utils.cuh:62-175 ----------
  * Raw dense device pointers; `stream` is a cudaStream_t (NULL = default stream).  Each call

@@ -304,7 +304,7 @@ struct RefOdom
             for(int j = 0; j < iterations[i]; j++)
             {
                 double Rt[16], R[9], KR[9], KRK_inv[9];
-                smath::mat4_inverse(resultRt, Rt);
+                smath::mat4_affine_inverse(resultRt, Rt);
                 for(int x = 0; x < 3; x++)
                     for(int y = 0; y < 3; y++) R[x * 3 + y] = Rt[x * 4 + y];
                 smath::mat3_mul(K, R, KR);

@@ -36,11 +36,12 @@ struct GnShared
     // solver state (thread 0)
     double resultRt[16];
     double resultR[9], lastResultR[9];
+    double K[9], Kinv[9];   // intrinsics of the running level (and of level 2 during SO3)
     float R_lr[9];
     float lastError, lastCount;
     GnResult res;
     // reduction scratch
-    float red[16 * kGnPartialStride];
+    alignas(16) float red[32 * kGnPartialStride];
     float total[kGnPartialStride];
 };
 
@@ -82,31 +83,51 @@ __device__ __forceinline__ void cta_publish(T (&acc)[NV], GnShared & sh, T * dst
     __syncthreads();
 }
 
-// Fold the G partial rows (64 columns each) of this group in rank order into sh.total.
-// Columns 29 and 30 hold the integer count / sigma of the RGB residual.
+// Fold the G partial rows (64 columns each) of this group into sh.total, in a fixed order (so
+// every CTA of the group gets bit-identical sums).  All of a thread's loads are issued before the
+// first use: one L2 round trip for the whole fold.  Columns 29 and 30 hold the integer count /
+// sigma of the RGB residual (bit patterns).
 __device__ __forceinline__ void fold_partials(GnShared & sh, const float * rows, int G)
 {
-    const int v = threadIdx.x & (kGnPartialStride - 1);
-    const int c = threadIdx.x / kGnPartialStride;
-    const int nc = blockDim.x / kGnPartialStride;
-    const bool is_int = (v == 29 || v == 30);
-    float fs = 0.f;
-    int is = 0;
-    for(int r = c; r < G; r += nc)
+    constexpr int kVecPerRow = kGnPartialStride / 4;                       // 16 float4 per row
+    constexpr int kMaxPasses = (kGnMaxCtas * kVecPerRow) / kGnThreads;     // 8
+    const int nvec = G * kVecPerRow;
+    const int c4 = threadIdx.x % kVecPerRow;    // which float4 column
+    const int r0 = threadIdx.x / kVecPerRow;    // first row of this thread; stride 32 rows
+    float4 v[kMaxPasses];
+#pragma unroll
+    for(int m = 0; m < kMaxPasses; m++)
     {
-        const float x = __ldcg(rows + r * kGnPartialStride + v);
-        if(is_int)
-            is += __float_as_int(x);
-        else
-            fs += x;
+        const int q = threadIdx.x + m * kGnThreads;
+        v[m] = (q < nvec) ? __ldcg(reinterpret_cast<const float4 *>(rows) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    sh.red[c * kGnPartialStride + v] = is_int ? __int_as_float(is) : fs;
+    float4 acc = v[0];
+    const bool has_int = (c4 == 7);   // columns 28..31 -> .y = count, .z = sigma
+#pragma unroll
+    for(int m = 1; m < kMaxPasses; m++)
+    {
+        acc.x += v[m].x;
+        acc.w += v[m].w;
+        if(has_int)
+        {
+            acc.y = __int_as_float(__float_as_int(acc.y) + __float_as_int(v[m].y));
+            acc.z = __int_as_float(__float_as_int(acc.z) + __float_as_int(v[m].z));
+        }
+        else
+        {
+            acc.y += v[m].y;
+            acc.z += v[m].z;
+        }
+    }
+    reinterpret_cast<float4 *>(sh.red)[r0 * kVecPerRow + c4] = acc;
     __syncthreads();
     if(threadIdx.x < kGnPartialStride)
     {
+        const bool is_int = (threadIdx.x == 29 || threadIdx.x == 30);
         float ft = 0.f;
         int it = 0;
-        for(int k = 0; k < nc; k++)
+#pragma unroll 8
+        for(int k = 0; k < kGnThreads / kVecPerRow; k++)
         {
             const float x = sh.red[k * kGnPartialStride + threadIdx.x];
             if(is_int)
@@ -141,12 +162,28 @@ __device__ __forceinline__ void k_matrix_d(const LevelGeom & g, double * K)
 
 // ---- thread-0 scalar sections (kept out of line: they are fp64-heavy and must not
 //      inflate the register allocation of the pixel loops) ---------------------------
-__device__ __noinline__ void so3_prepare(GnShared & sh, const LevelGeom g)
+__device__ __noinline__ void level_begin(GnShared & sh, const LevelGeom g)
 {
-    double K[9], Kinv[9], KR[9], H[9];
+    double K[9], Kinv[9];
     k_matrix_d(g, K);
     smath::mat3_inverse(K, Kinv);
-    smath::mat3_mul(K, sh.resultR, KR);
+    for(int k = 0; k < 9; k++)
+    {
+        sh.K[k] = K[k];
+        sh.Kinv[k] = Kinv[k];
+    }
+}
+
+__device__ __noinline__ void so3_prepare(GnShared & sh)
+{
+    double K[9], Kinv[9], R[9], KR[9], H[9];
+    for(int k = 0; k < 9; k++)
+    {
+        K[k] = sh.K[k];
+        Kinv[k] = sh.Kinv[k];
+        R[k] = sh.resultR[k];
+    }
+    smath::mat3_mul(K, R, KR);
     smath::mat3_mul(KR, Kinv, H);
     for(int k = 0; k < 9; k++)
     {
@@ -223,12 +260,16 @@ __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record 
 }
 
 // RGBDOdometryef.cpp:422-432
-__device__ __noinline__ void gn_prepare(GnShared & sh, const LevelGeom g)
+__device__ __noinline__ void gn_prepare(GnShared & sh)
 {
-    double K[9], Kinv[9], Rt[16], R[9], KR[9], KRK[9];
-    k_matrix_d(g, K);
-    smath::mat3_inverse(K, Kinv);
-    smath::mat4_inverse(sh.resultRt, Rt);
+    double K[9], Kinv[9], M[16], Rt[16], R[9], KR[9], KRK[9];
+    for(int k = 0; k < 9; k++)
+    {
+        K[k] = sh.K[k];
+        Kinv[k] = sh.Kinv[k];
+    }
+    for(int k = 0; k < 16; k++) M[k] = sh.resultRt[k];
+    smath::mat4_affine_inverse(M, Rt);
     for(int x = 0; x < 3; x++)
         for(int y = 0; y < 3; y++) R[x * 3 + y] = Rt[x * 4 + y];
     smath::mat3_mul(K, R, KR);
@@ -382,6 +423,8 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
     // partial rows of this group: [parity][rank][64]
     float * gpart = partials + (size_t)group * 2 * G * kGnPartialStride;
 
+    const long long t_start = clock64();
+#define GN_STAMP(rec, idx) do { if(rec) (rec)->t_cycles[idx] = (unsigned)(clock64() - t_start); } while(0)
     const int gtid = rank * blockDim.x + threadIdx.x;
     const int gthreads = G * blockDim.x;
     const bool leader = (rank == 0 && threadIdx.x == 0);
@@ -400,9 +443,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
         {
             const LevelGeom g = L.geom[2];
             const int N = g.rows * g.cols;
+            if(threadIdx.x == 0) level_begin(sh, g);
             for(int it = 0; it < 10; it++)
             {
-                if(threadIdx.x == 0) so3_prepare(sh, g);
+                if(threadIdx.x == 0) so3_prepare(sh);
                 __syncthreads();
                 So3Args a;
                 a.lastImage = in.lastNextImage[2];
@@ -458,14 +502,43 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
             const int plane = g.rows * g.cols;
             const bool vec = (plane & 3) == 0;
             const int nitems = (plane + 3) >> 2;
-            if(threadIdx.x == 0) sh.res.lastRGBError = FLT_MAX;
+            if(threadIdx.x == 0)
+            {
+                sh.res.lastRGBError = FLT_MAX;
+                level_begin(sh, g);
+            }
+            // Pose-independent half of the RGB association (border, 4x4 non-zero window, gradient magnitude,
+            // finite depth; reduce.cu:780-807), evaluated once per level instead of once per iteration: bit m
+            // of `cand` = this thread's m-th pixel (k = gtid + m * gthreads) is a candidate.
+            const int nslots = (plane + gthreads - 1) / gthreads;
+            const bool use_flags = L.rgb && nslots <= 32;
+            unsigned cand = 0;
+            if(use_flags)
+            {
+                ResidualArgs a;
+                a.minScale = L.min_scale[lvl];
+                a.dIdx = in.dIdx[lvl]; a.dIdy = in.dIdy[lvl];
+                a.nextDepth = in.nextDepth[lvl];
+                a.nextImage = in.nextImage[lvl];
+                a.cols = g.cols; a.rows = g.rows;
+                for(int m = 0; m < nslots; m++)
+                {
+                    const int k = gtid + m * gthreads;
+                    if(k < plane)
+                    {
+                        const int i = k / g.cols;
+                        if(rgb_candidate(a, k - i * g.cols, i)) cand |= 1u << m;
+                    }
+                }
+            }
 
             for(int j = 0; j < L.iterations[lvl]; j++)
             {
                 slam_step_record * rec = nullptr;
+                const long long t_iter = clock64();
                 if(threadIdx.x == 0)
                 {
-                    gn_prepare(sh, g);
+                    gn_prepare(sh);
                     if(tr && ntr < kGnMaxTrace)
                     {
                         rec = &tr[ntr];
@@ -473,6 +546,8 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         rec->kind = 1;
                         rec->level = lvl;
                         rec->iteration = j;
+                        rec->t_cycles[0] = (unsigned)(t_iter - t_start);
+                        GN_STAMP(rec, 1);
                         for(int k = 0; k < 9; k++)
                         {
                             rec->Rcurr_in[k] = sh.Rcurr[k];
@@ -491,6 +566,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                 float * rowsA = gpart + (step & 1) * G * kGnPartialStride;
                 float * myrow = rowsA + rank * kGnPartialStride;
 
+                unsigned valid_mask = 0;   // bit m: this thread's m-th pixel has an RGB correspondence this iteration
                 // ---------------- phase A: ICP products + RGB association
                 {
                     float acc[29];
@@ -542,22 +618,31 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         a.krkinv = mat3_from(sh.krk);
                         a.cols = g.cols; a.rows = g.rows;
                         Corres * cimg = in.corres[lvl];
-                        for(int k = gtid; k < plane; k += gthreads)
+                        valid_mask = 0;
+                        for(int m = 0; m < nslots; m++)
                         {
+                            const int k = gtid + m * gthreads;
+                            if(k >= plane) break;
                             const int i = k / g.cols;
                             const int j0 = k - i * g.cols;
                             Corres c;
                             c.zx = c.zy = c.ox = c.oy = 0;
                             c.diff = 0.f;
                             c.valid = 0;
-                            if(rgb_candidate(a, j0, i) && rgb_associate(a, j0, i, c))
+                            const bool is_cand = use_flags ? ((cand >> m) & 1u) != 0 : rgb_candidate(a, j0, i);
+                            const bool ok = is_cand && rgb_associate(a, j0, i, c);
+                            if(ok)
                             {
                                 cnt[0] += 1;
                                 cnt[1] += (int)(c.diff * c.diff);
+                                if(m < 32) valid_mask |= 1u << m;
                             }
-                            reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
+                            // the reference writes a DataTerm for every pixel; only the valid ones are ever read again,
+                            // so the others are written only when a test wants to tap the whole image
+                            if(ok || L.full_corres || !use_flags) reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
                         }
                     }
+                    GN_STAMP(rec, 2);
                     cta_publish<float, 29>(acc, sh, myrow);
                     if(L.rgb) cta_publish<int, 2>(cnt, sh, reinterpret_cast<int *>(myrow + 29));
                 }
@@ -565,6 +650,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                 if(L.rgb)
                 {
                     group_barrier(bar, target, G);
+                    GN_STAMP(rec, 3);
                     // count / sigma of the whole image -> sigmaVal (every CTA, identically)
                     if(threadIdx.x < 32)
                     {
@@ -584,6 +670,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         }
                     }
                     __syncthreads();
+                    GN_STAMP(rec, 4);
                     if(sh.stop)
                     {
                         step++;
@@ -604,8 +691,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                     a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
                     a.cloud = nullptr;
                     const Corres * cimg = in.corres[lvl];
-                    for(int k = gtid; k < plane; k += gthreads)
+                    for(int m = 0; m < nslots; m++)
                     {
+                        const int k = gtid + m * gthreads;
+                        if(k >= plane) break;
+                        if(use_flags && !((valid_mask >> m) & 1u)) continue;
                         const int4 raw = *(reinterpret_cast<const int4 *>(cimg) + k);   // written by this very thread in phase A
                         const Corres c = *reinterpret_cast<const Corres *>(&raw);
                         if(c.valid & 0xff)
@@ -615,13 +705,16 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                             accumulate_se3(acc, row, true);
                         }
                     }
+                    GN_STAMP(rec, 5);
                     cta_publish<float, 29>(acc, sh, myrow + 32);
                 }
                 group_barrier(bar, target, G);
                 fold_partials(sh, rowsA, G);
                 step++;
+                GN_STAMP(rec, 6);
 
                 if(threadIdx.x == 0) gn_update(sh, L.icp, L.rgb, L.icp_weight, rec);
+                GN_STAMP(rec, 7);
                 if(rec) ntr++;
                 __syncthreads();
             }
@@ -664,8 +757,27 @@ void gn_bind_state(GnDevice & d, char * base, int batch)
     d.stage_bytes = (sizeof(GnCtl) + 255) / 256 * 256 + sizeof(GnSeqIn) * batch;
 }
 
+// Fold finished event pairs into kernel_ms / kernel_launches (synchronises on them).
+int gn_fold_profile(GnDevice & d)
+{
+    for(size_t i = 0; i + 1 < d.ev.size(); i += 2)
+    {
+        SLAM_CUDA_TRY(cudaEventSynchronize(d.ev[i + 1]));
+        float ms = 0.f;
+        SLAM_CUDA_TRY(cudaEventElapsedTime(&ms, d.ev[i], d.ev[i + 1]));
+        d.kernel_ms += ms;
+        d.kernel_launches++;
+        cudaEventDestroy(d.ev[i]);
+        cudaEventDestroy(d.ev[i + 1]);
+    }
+    d.ev.clear();
+    return SLAM_OK;
+}
+
 void gn_release(GnDevice & d)
 {
+    for(auto e : d.ev) cudaEventDestroy(e);
+    d.ev.clear();
     if(d.h_stage) cudaFreeHost(d.h_stage);
     d.h_stage = nullptr;
 }
@@ -728,7 +840,22 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     slam_step_record * trace = d.trace;
     int * trace_count = d.trace_count;
     void * args[] = {&Lc, &ctl, &seq_in, &partials, &results, &trace, &trace_count, &G, &groups};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if(d.profiling)
+    {
+        if(d.ev.size() >= 4096)
+            if(int rc = gn_fold_profile(d)) return rc;
+        SLAM_CUDA_TRY(cudaEventCreate(&e0));
+        SLAM_CUDA_TRY(cudaEventCreate(&e1));
+        SLAM_CUDA_TRY(cudaEventRecord(e0, stream));
+    }
     SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_gn_persistent, dim3(G * groups), dim3(kGnThreads), args, 0, stream));
+    if(d.profiling)
+    {
+        SLAM_CUDA_TRY(cudaEventRecord(e1, stream));
+        d.ev.push_back(e0);
+        d.ev.push_back(e1);
+    }
     SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * L.batch, cudaMemcpyDeviceToHost, stream));
     d.so3_swapped = L.so3;
     return SLAM_OK;

@@ -1,5 +1,6 @@
 // Device-resident Gauss-Newton loop: host-visible declarations (see gn_kernel.cu).
 #pragma once
+#include <vector>
 #include "odom_internal.hpp"
 
 namespace slam {
@@ -40,7 +41,7 @@ struct GnLaunch
     int levels, batch;
     LevelGeom geom[SLAM_MAX_LEVELS];
     int iterations[SLAM_MAX_LEVELS];
-    bool icp, rgb, rgb_only, so3, trace;
+    bool icp, rgb, rgb_only, so3, trace, full_corres;
     float icp_weight;
     float dist_thresh, angle_thresh;
     float sobel_scale, max_depth_delta;
@@ -62,7 +63,14 @@ struct GnDevice
     int batch = 0;
     int num_sms = 0;
     bool so3_swapped = false;
+    // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // start/stop pairs of launches not yet folded into the totals
+    double kernel_ms = 0.0;
+    long long kernel_launches = 0;
 };
+
+int gn_fold_profile(GnDevice & d);
 
 size_t gn_state_bytes(int batch);
 void gn_bind_state(GnDevice & d, char * base, int batch);

@@ -63,6 +63,7 @@ struct slam_odom
     std::vector<slam_odom_stats> stats;
     std::vector<std::vector<slam_step_record>> trace;
     bool trace_on = false;
+    int trace_level = 0;
     bool have_depth_tmp = false;
     bool pending_async = false;
     bool last_icp = false, last_rgb = false, last_so3 = false;
@@ -454,7 +455,7 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
         for(int j = 0; j < iterations[i]; j++)
         {
             double Rt[16];
-            smath::mat4_inverse(resultRt, Rt);
+            smath::mat4_affine_inverse(resultRt, Rt);
             double R[9], KR[9], KRK_inv[9];
             for(int x = 0; x < 3; x++)
                 for(int y = 0; y < 3; y++) R[x * 3 + y] = Rt[x * 4 + y];
@@ -816,6 +817,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     L.max_depth_delta = h->maxDepthDeltaRGB;
     for(int l = 0; l < h->levels; l++) L.min_scale[l] = (float)(pow((double)h->minGrad[l], 2.0) / pow((double)h->sobelScale, 2.0));
     L.trace = h->trace_on;
+    L.full_corres = h->trace_level >= 2;
     int rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream);
     if(rc) return rc;
     h->launches++;
@@ -926,10 +928,35 @@ extern "C" int slam_odom_get_stats(slam_odom_t h, slam_odom_stats * stats)
 
 extern "C" long long slam_odom_launch_count(slam_odom_t h) { return h ? h->launches : 0; }
 
+extern "C" int slam_odom_set_profiling(slam_odom_t h, int enable)
+{
+    if(int rc = check_handle(h)) return rc;
+    h->gn.profiling = enable != 0;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_kernel_launches, int reset)
+{
+    if(int rc = check_handle(h)) return rc;
+    if(int rc = set_device(h)) return rc;
+    if(int rc = gn_fold_profile(h->gn)) return rc;
+    if(gn_kernel_ms) *gn_kernel_ms = h->gn.kernel_ms;
+    if(gn_kernel_launches) *gn_kernel_launches = h->gn.kernel_launches;
+    if(reset)
+    {
+        h->gn.kernel_ms = 0.0;
+        h->gn.kernel_launches = 0;
+    }
+    return SLAM_OK;
+}
+
+extern "C" void * slam_odom_stream(slam_odom_t h) { return h ? (void *)h->stream : nullptr; }
+
 extern "C" int slam_odom_set_trace(slam_odom_t h, int enable)
 {
     if(int rc = check_handle(h)) return rc;
     h->trace_on = enable != 0;
+    h->trace_level = enable;
     return SLAM_OK;
 }
 
@@ -1095,16 +1122,36 @@ static int stage_frame(slam_odom_t h, StagingSlot & sl, const slam_frame_host * 
     return SLAM_OK;
 }
 
+static StagingSlot * find_staged(slam_odom_t h, const void * tag)
+{
+    for(auto & sl : h->slot)
+        if(sl.pending && sl.tag_depth == tag) return &sl;
+    return nullptr;
+}
+
+static StagingSlot * free_slot(slam_odom_t h)
+{
+    for(auto & sl : h->slot)
+        if(!sl.pending) return &sl;
+    return nullptr;
+}
+
 extern "C" int slam_odom_prefetch_host(slam_odom_t h, const slam_frame_host * f)
 {
     if(int rc = check_handle(h)) return rc;
     SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16);
     if(int rc = set_device(h)) return rc;
     if(int rc = ensure_staging(h)) return rc;
-    StagingSlot & sl = h->slot[h->next_slot];
-    // the slot was last consumed by kernels enqueued on the compute stream two frames ago;
-    // they are complete because track_host synchronises per frame.
-    return stage_frame(h, sl, f, h->copy_stream);
+    if(find_staged(h, f->depth)) return SLAM_OK;
+    StagingSlot * sl = free_slot(h);
+    if(!sl)
+    {
+        set_last_error("prefetch: both staging slots hold frames that were not tracked yet");
+        return SLAM_ERR_ORDER;
+    }
+    // a free slot was last read by kernels of a frame whose track_host already returned (it synchronises),
+    // so the copy stream may overwrite it now
+    return stage_frame(h, *sl, f, h->copy_stream);
 }
 
 extern "C" int slam_odom_track_host(slam_odom_t h, const slam_frame_host * f, float * trans, float * rot, int rgb_only, float icp_weight, int pyramid,
@@ -1114,12 +1161,20 @@ extern "C" int slam_odom_track_host(slam_odom_t h, const slam_frame_host * f, fl
     SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16 && trans && rot);
     if(int rc = set_device(h)) return rc;
     if(int rc = ensure_staging(h)) return rc;
-    StagingSlot & sl = h->slot[h->next_slot];
-    if(!(sl.pending && sl.tag_depth == f->depth))
-        if(int rc = stage_frame(h, sl, f, h->copy_stream)) return rc;
-    SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl.ready, 0));
-    sl.pending = false;
-    h->next_slot ^= 1;
-    return track_from_device_ptrs(h, sl.depth, sl.rgba, sl.mv, sl.mn, sl.mrgba, sl.poses.data(), sl.depth_cutoff, sl.model_depth_cutoff, trans, rot,
-                                  rgb_only, icp_weight, pyramid, fast_odom, so3);
+    StagingSlot * sl = find_staged(h, f->depth);
+    if(!sl)
+    {
+        sl = free_slot(h);
+        if(!sl)
+        {
+            sl = &h->slot[0];   // drop a stale prefetch
+            SLAM_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        }
+        if(int rc = stage_frame(h, *sl, f, h->copy_stream)) return rc;
+    }
+    SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl->ready, 0));
+    const int rc = track_from_device_ptrs(h, sl->depth, sl->rgba, sl->mv, sl->mn, sl->mrgba, sl->poses.data(), sl->depth_cutoff, sl->model_depth_cutoff, trans,
+                                          rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    sl->pending = false;
+    return rc;
 }

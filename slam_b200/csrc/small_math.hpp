@@ -146,7 +146,7 @@ SM_HD void mat4_inverse(const T * m, T * out)
 // treat pivots below max|D|*eps as zero (pseudo-inverse), so a rank-deficient system
 // (e.g. no correspondences => A = 0) yields 0 rather than NaN.
 template <typename T, int N>
-SM_HD void ldlt_solve(const T * A, const T * b, T * x, T eps)
+SM_HD void ldlt_solve_pivoted(const T * A, const T * b, T * x, T eps)
 {
     T m[N * N];
     int perm[N];
@@ -228,6 +228,114 @@ SM_HD void ldlt_solve(const T * A, const T * b, T * x, T eps)
     for(int i = N - 1; i >= 0; i--)
         for(int j = i + 1; j < N; j++) y[i] = sub(y[i], mul(m[j * N + i], y[j]));
     for(int i = 0; i < N; i++) x[perm[i]] = y[i];
+}
+
+// LDL^T without pivoting, written so that every index is a compile-time constant after
+// unrolling (the whole factorisation lives in registers on the GPU; one reciprocal per
+// pivot).  Returns false -- leaving x untouched -- when a pivot is not safely positive
+// (d_k <= 1e-9 * largest diagonal entry): the caller then takes the pivoted route above.
+// For the well-conditioned SPD normal equations of a tracked frame this path is always taken.
+template <typename T, int N>
+SM_HD bool ldlt_solve_nopivot(const T * A, const T * b, T * x)
+{
+    T L[N][N];
+    T d[N], inv_d[N], y[N];
+    T dmax = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < N; i++) dmax = A[i * N + i] > dmax ? A[i * N + i] : dmax;
+    const T floor_d = mul(dmax, T(1e-9));
+    bool ok = dmax > T(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int j = 0; j < N; j++)
+    {
+        T dj = A[j * N + j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k = 0; k < j; k++) dj = sub(dj, mul(mul(L[j][k], L[j][k]), d[k]));
+        d[j] = dj;
+        ok = ok && (dj > floor_d);
+        inv_d[j] = dvd(T(1), dj);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int i = j + 1; i < N; i++)
+        {
+            T v = A[i * N + j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for(int k = 0; k < j; k++) v = sub(v, mul(mul(L[i][k], L[j][k]), d[k]));
+            L[i][j] = mul(v, inv_d[j]);
+        }
+    }
+    if(!ok) return false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < N; i++)
+    {
+        T v = b[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k = 0; k < i; k++) v = sub(v, mul(L[i][k], y[k]));
+        y[i] = v;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < N; i++) y[i] = mul(y[i], inv_d[i]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = N - 1; i >= 0; i--)
+    {
+        T v = y[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for(int k = i + 1; k < N; k++) v = sub(v, mul(L[k][i], y[k]));
+        y[i] = v;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for(int i = 0; i < N; i++) x[i] = y[i];
+    return true;
+}
+
+// The solver behind every `A.ldlt().solve(b)` of the path: register-resident fast route for
+// positive definite systems, pivoted / pseudo-inverse route for degenerate ones.
+template <typename T, int N>
+SM_HD void ldlt_solve(const T * A, const T * b, T * x, T eps)
+{
+    if(!ldlt_solve_nopivot<T, N>(A, b, x)) ldlt_solve_pivoted<T, N>(A, b, x, eps);
+}
+
+// Inverse of an affine 4x4 [M t; 0 0 0 1] (every resultRt is one: products of such matrices keep
+// the last row exactly): [M^-1, -M^-1 t; 0 0 0 1].  Stands in for resultRt.inverse(),
+// RGBDOdometryef.cpp:422.
+template <typename T>
+SM_HD void mat4_affine_inverse(const T * m, T * out)
+{
+    T M[9], Mi[9];
+    for(int i = 0; i < 3; i++)
+        for(int j = 0; j < 3; j++) M[i * 3 + j] = m[i * 4 + j];
+    mat3_inverse(M, Mi);
+    T r[16];
+    for(int i = 0; i < 3; i++)
+    {
+        for(int j = 0; j < 3; j++) r[i * 4 + j] = Mi[i * 3 + j];
+        r[i * 4 + 3] = -dot3(Mi[i * 3 + 0], m[3], Mi[i * 3 + 1], m[7], Mi[i * 3 + 2], m[11]);
+    }
+    r[12] = r[13] = r[14] = 0;
+    r[15] = 1;
+    for(int i = 0; i < 16; i++) out[i] = r[i];
 }
 
 // Axis-angle -> rotation (double), odom/utils.h:16-52; identity below DBL_EPSILON.

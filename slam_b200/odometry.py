@@ -60,7 +60,7 @@ class StepRecord(C.Structure):
         ("rgb_count", C.c_int), ("rgb_sigma", C.c_int),
         ("x", C.c_double * 6), ("Rcurr", C.c_float * 9), ("tcurr", C.c_float * 3),
         ("Rcurr_in", C.c_float * 9), ("tcurr_in", C.c_float * 3), ("krkinv_in", C.c_float * 9), ("kt_in", C.c_float * 3),
-        ("sigma_in", C.c_float), ("so3_in", C.c_float * 27),
+        ("sigma_in", C.c_float), ("so3_in", C.c_float * 27), ("t_cycles", C.c_uint * 8),
     ]
 
     def as_dict(self):
@@ -69,7 +69,7 @@ class StepRecord(C.Structure):
                     rgb_sigma=self.rgb_sigma, x=np.array(self.x[:]), Rcurr=np.array(self.Rcurr[:], np.float32).reshape(3, 3),
                     tcurr=np.array(self.tcurr[:], np.float32), Rcurr_in=np.array(self.Rcurr_in[:], np.float32), tcurr_in=np.array(self.tcurr_in[:], np.float32),
                     krkinv_in=np.array(self.krkinv_in[:], np.float32), kt_in=np.array(self.kt_in[:], np.float32), sigma_in=float(self.sigma_in),
-                    so3_in=np.array(self.so3_in[:], np.float32))
+                    so3_in=np.array(self.so3_in[:], np.float32), t_cycles=np.array(self.t_cycles[:], np.int64))
 
 
 class FrameHost(C.Structure):
@@ -120,6 +120,10 @@ def load_library():
     lib.slam_odom_get_trace.argtypes = [vp, i, C.POINTER(StepRecord), i, C.POINTER(i)]
     lib.slam_odom_launch_count.argtypes = [vp]
     lib.slam_odom_launch_count.restype = C.c_longlong
+    lib.slam_odom_set_profiling.argtypes = [vp, i]
+    lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
+    lib.slam_odom_stream.argtypes = [vp]
+    lib.slam_odom_stream.restype = vp
     lib.slam_op_workspace_bytes.restype = C.c_size_t
     # operator-level API
     lib.slam_op_pyr_down.argtypes = [vp, i, i, vp, vp]
@@ -284,13 +288,27 @@ class RGBDOdometry:
         _check(self.lib, self.lib.slam_odom_prefetch_host(self._h, C.byref(frame)))
 
     def set_trace(self, on=True):
-        _check(self.lib, self.lib.slam_odom_set_trace(self._h, int(on)))
+        """True / 2: step records + full correspondence images (tests); 1: step records only (timelines); 0: off."""
+        _check(self.lib, self.lib.slam_odom_set_trace(self._h, 2 if on is True else int(on)))
 
     def get_trace(self, seq=0):
         arr = (StepRecord * 64)()
         n = C.c_int(0)
         _check(self.lib, self.lib.slam_odom_get_trace(self._h, seq, arr, 64, C.byref(n)))
         return [arr[k].as_dict() for k in range(min(n.value, 64))]
+
+    def set_profiling(self, on=True):
+        _check(self.lib, self.lib.slam_odom_set_profiling(self._h, int(on)))
+
+    def get_profile(self, reset=False):
+        """-> (device milliseconds spent in the persistent Gauss-Newton kernel, number of its launches)."""
+        ms, n = C.c_double(0), C.c_longlong(0)
+        _check(self.lib, self.lib.slam_odom_get_profile(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.slam_odom_stream(self._h) or 0)
 
     def launch_count(self) -> int:
         return int(self.lib.slam_odom_launch_count(self._h))
