@@ -77,6 +77,14 @@ def build_synth(force: bool = False) -> Path:
     return out
 
 
+def build_hostmath(force: bool = False) -> Path:
+    out = ROOT / "slam_b200" / "libslam_hostmath.so"
+    src = CSRC / "hostmath_capi.cpp"
+    if force or _stale(out, [src, CSRC / "small_math.hpp"]):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
+    return out
+
+
 def build_oracle(force: bool = False) -> Path:
     out = ROOT / "oracle" / "liboracle.so"
     src = ROOT / "oracle" / "odom_oracle.c"
@@ -126,6 +134,7 @@ def build_reference(force: bool = False) -> Path | None:
 def build_all(force: bool = False) -> None:
     build_product(force)
     build_synth(force)
+    build_hostmath(force)
     build_oracle(force)
     build_reference(force)
 

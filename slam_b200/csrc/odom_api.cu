@@ -7,7 +7,7 @@
 //     the 3x3 / 6x6 solves and the pose update, runs inside ONE persistent kernel
 //     (gn_kernel.cu); the host only enqueues it and reads back 48 bytes of pose;
 //   * host-stepped (params.host_loop = 1): the reference's control flow, one reduction
-//     launch + one sync per step, kept for step-by-step parity against the oracle.
+//     launch + one sync per step, kept for step-by-step parity checks against the reference replay.
 #include <mutex>
 #include <cstring>
 #include <cmath>
