@@ -101,7 +101,7 @@ def build_reference(force: bool = False) -> Path | None:
         return out if out.exists() else None
     shim = ROOT / "oracle" / "ref_shim.cuh"
     harness = ROOT / "oracle" / "ref_harness.cu"
-    deps = [shim, harness, CSRC / "small_math.hpp", refsrc / "odom" / "reduce.cu", refsrc / "odom" / "utils.cu"]
+    deps = [shim, harness, CSRC / "small_math.hpp", ROOT / "include" / "slam_odom.h", refsrc / "odom" / "reduce.cu", refsrc / "odom" / "utils.cu"]
     if not force and not _stale(out, deps):
         return out
     out.parent.mkdir(parents=True, exist_ok=True)

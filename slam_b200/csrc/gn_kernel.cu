@@ -9,13 +9,20 @@
 //   * the CTAs of the grid are split into groups of G CTAs; a group owns one sequence
 //     (batch == 1: one group of all 148 CTAs; batch > 1: independent groups, so
 //     independent sequences progress concurrently with no inter-group traffic);
-//   * a step is "map" (every thread accumulates its pixels' 29/11 products in registers)
-//     + "publish" (warp shuffle -> shared memory -> one 64-float partial row per CTA in
-//     global memory) + a group barrier (release/acquire counter) + "fold" (every CTA
-//     re-reads the G partial rows in rank order, so all CTAs hold bit-identical sums);
-//   * thread 0 of EVERY CTA then solves the normal equations redundantly in fp64
-//     (small_math.hpp) and leaves the next iteration's parameters in shared memory;
-//     no host round trip, no second launch, no broadcast step;
+//   * every thread owns a fixed set of pixels per level ("slots": k = gtid + m * gthreads),
+//     so per-pixel state that does not depend on the pose (RGB candidate flag, depth,
+//     intensity, gradients) is loaded ONCE per level into registers, and the photometric
+//     correspondences found in phase A stay in registers for phase B;
+//   * loads are issued for all of a thread's slots before any is consumed (the working set
+//     lives in the 126 MB L2, so what matters is round trips, not bytes);
+//   * a step is "map" (accumulate the 29/11 products in registers) + "publish" (transposed
+//     warp reduction -> shared memory -> one 64-float partial row per CTA in global memory)
+//     + a group barrier (release/acquire counter) + "fold" (every CTA re-reads the G partial
+//     rows in a fixed order, so all CTAs hold bit-identical sums);
+//   * warp 0 of EVERY CTA then solves the normal equations redundantly in fp64
+//     (small_math.hpp): the 6x6 LDL^T on one lane, everything around it (combining the
+//     systems, resultRt update, K R K^-1, K t, current pose) spread over the lanes in
+//     shared-memory stages.  No host round trip, no second launch, no broadcast step;
 //   * partial rows are double-buffered by step parity, which makes one barrier per
 //     reduction sufficient.
 // Per-pixel arithmetic is pixel_ops.cuh, shared with the single-launch operator kernels.
@@ -25,18 +32,23 @@
 
 namespace slam {
 
+constexpr int kSlotChunk = 5;   // slots processed together (640x480 on 148 CTAs: 5 slots per thread at level 0)
+constexpr int kIcpChunk = 3;    // ICP gathers in flight per thread (register budget)
+
 struct GnShared
 {
-    // parameters of the running iteration (thread 0 writes, everyone reads after a sync)
+    // parameters of the running iteration (warp 0 writes, everyone reads after a sync)
     float Rcurr[9], tcurr[3], Rprev[9], tprev[3], Rprev_inv[9];
     float krk[9], kt[3];
     float so3H[9], so3Kinv[9], so3KR[9];
     float sigmaVal;
     int stop;
-    // solver state (thread 0)
+    // solver state (warp 0)
     double resultRt[16];
     double resultR[9], lastResultR[9];
     double K[9], Kinv[9];   // intrinsics of the running level (and of level 2 during SO3)
+    double A[36], b[6], x[6], Rinc[9], newRt[12], Mi[9], KR[9], tinv[3];
+    float tinvf[3];
     float R_lr[9];
     float lastError, lastCount;
     GnResult res;
@@ -61,24 +73,42 @@ __device__ __forceinline__ void group_barrier(unsigned * ctr, unsigned & target,
     __syncthreads();
 }
 
-// Block sum of NV per-thread values -> dst[0..NV) (global partial row of this CTA).
-template <typename T, int NV>
-__device__ __forceinline__ void cta_publish(T (&acc)[NV], GnShared & sh, T * dst)
+// Block sum of up to 32 per-thread floats (v[NV..31] must be 0) -> dst[0..31] (global partial row
+// of this CTA).  Transposed warp reduction, then 32 threads add the per-warp rows.
+__device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, float * dst)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    T * red = reinterpret_cast<T *>(sh.red);
-#pragma unroll
-    for(int k = 0; k < NV; k++)
+    const float s = warp_reduce_scatter32(v);
+    sh.red[wid * 32 + lane] = s;
+    __syncthreads();
+    if(threadIdx.x < 32)
     {
-        const T s = warp_sum(acc[k]);
-        if(lane == 0) red[wid * NV + k] = s;
+        float total = 0.f;
+#pragma unroll 16
+        for(int w = 0; w < nw; w++) total += sh.red[w * 32 + threadIdx.x];
+        dst[threadIdx.x] = total;
     }
     __syncthreads();
-    if(threadIdx.x < NV)
+}
+
+// Same for two per-thread ints (count, sigma) -> dst[0..1].
+__device__ __forceinline__ void cta_publish_int2(int c0, int c1, GnShared & sh, int * dst)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    c0 = warp_sum(c0);
+    c1 = warp_sum(c1);
+    int * red = reinterpret_cast<int *>(sh.red);
+    if(lane == 0)
     {
-        T total = 0;
-        for(int w = 0; w < nw; w++) total += red[w * NV + threadIdx.x];
-        dst[threadIdx.x] = total;
+        red[wid * 2] = c0;
+        red[wid * 2 + 1] = c1;
+    }
+    __syncthreads();
+    if(threadIdx.x < 2)
+    {
+        int t = 0;
+        for(int w = 0; w < nw; w++) t += red[w * 2 + threadIdx.x];
+        dst[threadIdx.x] = t;
     }
     __syncthreads();
 }
@@ -140,17 +170,31 @@ __device__ __forceinline__ void fold_partials(GnShared & sh, const float * rows,
     __syncthreads();
 }
 
-__device__ __forceinline__ void load4(const float * base, int p, int n, bool vec, float (&out)[4])
+// count / sigma of the whole image right after the phase-A barrier (warp 0 only): all loads in flight at once.
+__device__ __forceinline__ void fold_count_sigma(GnShared & sh, const float * rows, int G)
 {
-    if(vec)
-    {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(base + p));
-        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-    }
-    else
-    {
+    constexpr int kMax = kGnMaxCtas / 32;
+    int c0 = 0, c1 = 0;
+    float a[kMax], b[kMax];
 #pragma unroll
-        for(int k = 0; k < 4; k++) out[k] = (p + k < n) ? __ldg(base + p + k) : SLAM_QNAN;
+    for(int j = 0; j < kMax; j++)
+    {
+        const int r = (int)threadIdx.x + 32 * j;
+        a[j] = (r < G) ? __ldcg(rows + r * kGnPartialStride + 29) : 0.f;
+        b[j] = (r < G) ? __ldcg(rows + r * kGnPartialStride + 30) : 0.f;
+    }
+#pragma unroll
+    for(int j = 0; j < kMax; j++)
+    {
+        c0 += __float_as_int(a[j]);
+        c1 += __float_as_int(b[j]);
+    }
+    c0 = warp_sum(c0);
+    c1 = warp_sum(c1);
+    if(threadIdx.x == 0)
+    {
+        sh.total[29] = __int_as_float(c0);
+        sh.total[30] = __int_as_float(c1);
     }
 }
 
@@ -160,9 +204,13 @@ __device__ __forceinline__ void k_matrix_d(const LevelGeom & g, double * K)
     K[0] = g.fx; K[4] = g.fy; K[2] = g.cx; K[5] = g.cy; K[8] = 1;
 }
 
-// ---- thread-0 scalar sections (kept out of line: they are fp64-heavy and must not
-//      inflate the register allocation of the pixel loops) ---------------------------
-__device__ __noinline__ void level_begin(GnShared & sh, const LevelGeom g)
+// =====================================================================================
+// fp64 bookkeeping on warp 0.  Every stage reads its inputs from shared memory, writes its
+// outputs to shared memory and ends with __syncwarp(); each lane evaluates exactly the
+// expression small_math.hpp evaluates for that entry, so the host-stepped loop (which runs
+// the serial routines) and this code agree bit for bit.
+// =====================================================================================
+__device__ __noinline__ void level_begin(GnShared & sh, const LevelGeom g)   // lane 0
 {
     double K[9], Kinv[9];
     k_matrix_d(g, K);
@@ -174,7 +222,161 @@ __device__ __noinline__ void level_begin(GnShared & sh, const LevelGeom g)
     }
 }
 
-__device__ __noinline__ void so3_prepare(GnShared & sh)
+// cofactor index table of smath::mat3_inverse: r[k] = det2(m[a], m[b], m[c], m[d]) / det
+__constant__ int kCof[9][4] = {{4, 8, 5, 7}, {2, 7, 1, 8}, {1, 5, 2, 4}, {5, 6, 3, 8}, {0, 8, 2, 6}, {2, 3, 0, 5}, {3, 7, 4, 6}, {1, 6, 0, 7}, {0, 4, 1, 3}};
+
+// From sh.resultRt: krk = float(K R K^-1), kt = float(K t) with [R|t] = resultRt^-1 (RGBDOdometryef.cpp:422-432),
+// and the current pose Rcurr/tcurr = [Rprev|tprev] * float(resultRt)^-1 (:563-575).  Warp 0, all lanes.
+__device__ __forceinline__ void warp_prepare(GnShared & sh, const bool with_pose)
+{
+    const int lane = threadIdx.x & 31;
+    const double * M = sh.resultRt;   // row-major 4x4, affine
+    // ---- stage 1: Mi = (3x3 part)^-1 (lanes 0..8); float isometry inverse pieces (lanes 12..23)
+    if(lane < 9)
+    {
+        auto m = [&](int i) { return M[(i / 3) * 4 + (i % 3)]; };
+        const double c00 = smath::det2(m(4), m(8), m(5), m(7));
+        const double c01 = smath::det2(m(5), m(6), m(3), m(8));
+        const double c02 = smath::det2(m(3), m(7), m(4), m(6));
+        const double det = smath::dot3(m(0), c00, m(1), c01, m(2), c02);
+        const double id = smath::dvd(1.0, det);
+        const double cof = smath::det2(m(kCof[lane][0]), m(kCof[lane][1]), m(kCof[lane][2]), m(kCof[lane][3]));
+        sh.Mi[lane] = smath::mul(cof, id);
+    }
+    else if(with_pose && lane >= 12 && lane < 15)
+    {
+        // tinv[i] = -(Rinv[i][:] . to), Rinv = Ro^T, Ro/to = float(resultRt)
+        const int i = lane - 12;
+        sh.tinvf[i] = -smath::dot3((float)M[0 * 4 + i], (float)M[3], (float)M[1 * 4 + i], (float)M[7], (float)M[2 * 4 + i], (float)M[11]);
+    }
+    else if(with_pose && lane >= 15 && lane < 24)
+    {
+        // Rcurr = Rprev * Rinv
+        const int i = (lane - 15) / 3, j = (lane - 15) % 3;
+        sh.Rcurr[i * 3 + j] = smath::dot3(sh.Rprev[i * 3 + 0], (float)M[j * 4 + 0], sh.Rprev[i * 3 + 1], (float)M[j * 4 + 1], sh.Rprev[i * 3 + 2], (float)M[j * 4 + 2]);
+    }
+    __syncwarp();
+    // ---- stage 2: KR = K * Mi (lanes 0..8), tinv = -Mi * t (lanes 9..11), tcurr (lanes 12..14)
+    if(lane < 9)
+    {
+        const int i = lane / 3, j = lane % 3;
+        sh.KR[lane] = smath::dot3(sh.K[i * 3 + 0], sh.Mi[0 * 3 + j], sh.K[i * 3 + 1], sh.Mi[1 * 3 + j], sh.K[i * 3 + 2], sh.Mi[2 * 3 + j]);
+    }
+    else if(lane < 12)
+    {
+        const int i = lane - 9;
+        sh.tinv[i] = -smath::dot3(sh.Mi[i * 3 + 0], M[3], sh.Mi[i * 3 + 1], M[7], sh.Mi[i * 3 + 2], M[11]);
+    }
+    else if(with_pose && lane < 15)
+    {
+        const int i = lane - 12;
+        sh.tcurr[i] = smath::add(smath::dot3(sh.Rprev[i * 3 + 0], sh.tinvf[0], sh.Rprev[i * 3 + 1], sh.tinvf[1], sh.Rprev[i * 3 + 2], sh.tinvf[2]), sh.tprev[i]);
+    }
+    __syncwarp();
+    // ---- stage 3: KRK = KR * Kinv (lanes 0..8), kt = K * tinv (lanes 9..11)
+    if(lane < 9)
+    {
+        const int i = lane / 3, j = lane % 3;
+        sh.krk[lane] = (float)smath::dot3(sh.KR[i * 3 + 0], sh.Kinv[0 * 3 + j], sh.KR[i * 3 + 1], sh.Kinv[1 * 3 + j], sh.KR[i * 3 + 2], sh.Kinv[2 * 3 + j]);
+    }
+    else if(lane < 12)
+    {
+        const int i = lane - 9;
+        sh.kt[i] = (float)smath::dot3(sh.K[i * 3 + 0], sh.tinv[0], sh.K[i * 3 + 1], sh.tinv[1], sh.K[i * 3 + 2], sh.tinv[2]);
+    }
+    __syncwarp();
+}
+
+// The serial core of one step: x = A^-1 b and the incremental rotation.  Lane 0.
+__device__ __noinline__ void solve_core(GnShared & sh)
+{
+    double A[36], b[6], x[6], R[9];
+    for(int k = 0; k < 36; k++) A[k] = sh.A[k];
+    for(int k = 0; k < 6; k++) b[k] = sh.b[k];
+    smath::ldlt_solve<double, 6>(A, b, x, DBL_EPSILON);
+    smath::rodrigues(x + 3, R);
+    for(int k = 0; k < 6; k++) sh.x[k] = x[k];
+    for(int k = 0; k < 9; k++) sh.Rinc[k] = R[k];
+}
+
+// RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems, solve, update resultRt, then the next
+// iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
+__device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec)
+{
+    const int lane = threadIdx.x & 31;
+    // ---- stage 0: lastA / lastb (upper triangle + mirror), stats
+    if(lane < 27)
+    {
+        // lane -> (i, j) of the row-major upper triangle of the 6x7 augmented system (reduce.cu:475-486)
+        int i = 0, rem = lane;
+        while(rem >= 7 - i)
+        {
+            rem -= 7 - i;
+            i++;
+        }
+        const int j = i + rem;
+        const float vi = sh.total[lane];
+        const float vr = sh.total[32 + lane];
+        double v;
+        if(icp && rgb)
+        {
+            const double w = icpWeight;
+            v = (j == 6) ? smath::add((double)vr, smath::mul(w, (double)vi)) : smath::add((double)vr, smath::mul(smath::mul(w, w), (double)vi));
+        }
+        else
+            v = icp ? (double)vi : (double)vr;
+        if(j == 6)
+            sh.b[i] = v;
+        else
+        {
+            sh.A[i * 6 + j] = v;
+            sh.A[j * 6 + i] = v;
+        }
+    }
+    else if(lane == 27 && icp)
+    {
+        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
+        sh.res.lastICPCount = sh.total[28];
+    }
+    __syncwarp();
+    // ---- stage 1: the serial core
+    if(lane == 0) solve_core(sh);
+    __syncwarp();
+    // ---- stage 2: resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), rows 0..2
+    if(lane < 12)
+    {
+        const int i = lane / 4, j = lane % 4;
+        double s = smath::mul(sh.Rinc[i * 3 + 0], sh.resultRt[0 * 4 + j]);   // add(0, x) == x
+        s = smath::add(s, smath::mul(sh.Rinc[i * 3 + 1], sh.resultRt[1 * 4 + j]));
+        s = smath::add(s, smath::mul(sh.Rinc[i * 3 + 2], sh.resultRt[2 * 4 + j]));
+        s = smath::add(s, smath::mul(sh.x[i], sh.resultRt[3 * 4 + j]));
+        sh.newRt[lane] = s;
+    }
+    __syncwarp();
+    if(lane < 12) sh.resultRt[lane] = sh.newRt[lane];
+    if(lane >= 12 && lane < 18) sh.res.lastb[lane - 12] = sh.b[lane - 12];
+    for(int k = lane; k < 36; k += 32) sh.res.lastA[k] = sh.A[k];
+    __syncwarp();
+    // ---- stages 3..5: parameters of the next iteration
+    warp_prepare(sh, true);
+    if(lane == 0)
+    {
+        sh.res.gn_iterations++;
+        if(rec)
+        {
+            for(int k = 0; k < 29; k++)
+            {
+                rec->icp[k] = icp ? sh.total[k] : 0.f;
+                rec->rgb[k] = rgb ? sh.total[32 + k] : 0.f;
+            }
+            for(int k = 0; k < 6; k++) rec->x[k] = sh.x[k];
+            for(int k = 0; k < 9; k++) rec->Rcurr[k] = sh.Rcurr[k];
+            for(int k = 0; k < 3; k++) rec->tcurr[k] = sh.tcurr[k];
+        }
+    }
+}
+
+__device__ __noinline__ void so3_prepare(GnShared & sh)   // lane 0
 {
     double K[9], Kinv[9], R[9], KR[9], H[9];
     for(int k = 0; k < 9; k++)
@@ -193,7 +395,7 @@ __device__ __noinline__ void so3_prepare(GnShared & sh)
     }
 }
 
-// RGBDOdometryef.cpp:346-378
+// RGBDOdometryef.cpp:346-378 (lane 0)
 __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record * rec)
 {
     const float * s = sh.total;
@@ -247,10 +449,18 @@ __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record 
         const double dd[3] = {delta[0], delta[1], delta[2]};
         double rotUpdate[9];
         smath::rodrigues(dd, rotUpdate);
-        float ru[9];
-        for(int k = 0; k < 9; k++) ru[k] = (float)rotUpdate[k];
-        smath::mat3_mul(ru, sh.R_lr, sh.R_lr);
-        for(int k = 0; k < 9; k++) sh.resultR[k] = sh.R_lr[k];
+        float ru[9], rl[9];
+        for(int k = 0; k < 9; k++)
+        {
+            ru[k] = (float)rotUpdate[k];
+            rl[k] = sh.R_lr[k];
+        }
+        smath::mat3_mul(ru, rl, rl);
+        for(int k = 0; k < 9; k++)
+        {
+            sh.R_lr[k] = rl[k];
+            sh.resultR[k] = rl[k];
+        }
         if(rec)
             for(int k = 0; k < 3; k++) rec->x[k] = delta[k];
     }
@@ -259,26 +469,7 @@ __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record 
     sh.stop = stop ? 1 : 0;
 }
 
-// RGBDOdometryef.cpp:422-432
-__device__ __noinline__ void gn_prepare(GnShared & sh)
-{
-    double K[9], Kinv[9], M[16], Rt[16], R[9], KR[9], KRK[9];
-    for(int k = 0; k < 9; k++)
-    {
-        K[k] = sh.K[k];
-        Kinv[k] = sh.Kinv[k];
-    }
-    for(int k = 0; k < 16; k++) M[k] = sh.resultRt[k];
-    smath::mat4_affine_inverse(M, Rt);
-    for(int x = 0; x < 3; x++)
-        for(int y = 0; y < 3; y++) R[x * 3 + y] = Rt[x * 4 + y];
-    smath::mat3_mul(K, R, KR);
-    smath::mat3_mul(KR, Kinv, KRK);
-    for(int k = 0; k < 9; k++) sh.krk[k] = (float)KRK[k];
-    for(int x = 0; x < 3; x++) sh.kt[x] = (float)smath::dot3(K[x * 3 + 0], Rt[3], K[x * 3 + 1], Rt[7], K[x * 3 + 2], Rt[11]);
-}
-
-// RGBDOdometryef.cpp:457-471; count/sigma are in sh.total[29], [30] (integer bit patterns)
+// RGBDOdometryef.cpp:457-471; count/sigma are in sh.total[29], [30] (integer bit patterns).  Lane 0.
 __device__ __noinline__ void gn_sigma(GnShared & sh, const bool rgb_only, slam_step_record * rec)
 {
     const int rgbSize = __float_as_int(sh.total[29]);
@@ -303,74 +494,7 @@ __device__ __noinline__ void gn_sigma(GnShared & sh, const bool rgb_only, slam_s
     }
 }
 
-// RGBDOdometryef.cpp:509-575: combine, solve, update pose.  icp sums = total[0..28],
-// rgb sums = total[32..60].
-__device__ __noinline__ void gn_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec)
-{
-    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
-    for(int k = 0; k < 36; k++) A_icp[k] = A_rgb[k] = 0.f;
-    for(int k = 0; k < 6; k++) b_icp[k] = b_rgb[k] = 0.f;
-    int shift = 0;
-    for(int i = 0; i < 6; ++i)
-        for(int j = i; j < 7; ++j)
-        {
-            const float vi = sh.total[shift];
-            const float vr = sh.total[32 + shift];
-            shift++;
-            if(j == 6)
-            {
-                b_icp[i] = vi;
-                b_rgb[i] = vr;
-            }
-            else
-            {
-                A_icp[j * 6 + i] = A_icp[i * 6 + j] = vi;
-                A_rgb[j * 6 + i] = A_rgb[i * 6 + j] = vr;
-            }
-        }
-    if(icp)
-    {
-        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
-        sh.res.lastICPCount = sh.total[28];
-    }
-    double * A = sh.res.lastA;
-    double * b = sh.res.lastb;
-    if(icp && rgb)
-    {
-        const double w = icpWeight;
-        const double ww = smath::mul(w, w);
-        for(int k = 0; k < 36; k++) A[k] = smath::add((double)A_rgb[k], smath::mul(ww, (double)A_icp[k]));
-        for(int k = 0; k < 6; k++) b[k] = smath::add((double)b_rgb[k], smath::mul(w, (double)b_icp[k]));
-    }
-    else if(icp)
-    {
-        for(int k = 0; k < 36; k++) A[k] = A_icp[k];
-        for(int k = 0; k < 6; k++) b[k] = b_icp[k];
-    }
-    else
-    {
-        for(int k = 0; k < 36; k++) A[k] = A_rgb[k];
-        for(int k = 0; k < 6; k++) b[k] = b_rgb[k];
-    }
-    double x[6];
-    smath::ldlt_solve<double, 6>(A, b, x, DBL_EPSILON);
-    smath::update_se3(sh.resultRt, x);
-    smath::compose_current_pose(sh.Rprev, sh.tprev, sh.resultRt, sh.Rcurr, sh.tcurr);
-    sh.res.gn_iterations++;
-    if(rec)
-    {
-        for(int k = 0; k < 29; k++)
-        {
-            rec->icp[k] = icp ? sh.total[k] : 0.f;
-            rec->rgb[k] = rgb ? sh.total[32 + k] : 0.f;
-        }
-        for(int k = 0; k < 6; k++) rec->x[k] = x[k];
-        for(int k = 0; k < 9; k++) rec->Rcurr[k] = sh.Rcurr[k];
-        for(int k = 0; k < 3; k++) rec->tcurr[k] = sh.tcurr[k];
-    }
-}
-
-__device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)
+__device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)   // lane 0
 {
     for(int k = 0; k < 9; k++) sh.Rprev[k] = sh.Rcurr[k] = in.Rprev[k];
     for(int k = 0; k < 3; k++) sh.tprev[k] = sh.tcurr[k] = in.tprev[k];
@@ -386,7 +510,7 @@ __device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)
     sh.stop = 0;
 }
 
-__device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, GnResult * out)
+__device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, GnResult * out)   // lane 0
 {
     if(rgb)
     {
@@ -428,6 +552,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
     const int gtid = rank * blockDim.x + threadIdx.x;
     const int gthreads = G * blockDim.x;
     const bool leader = (rank == 0 && threadIdx.x == 0);
+    const bool warp0 = threadIdx.x < 32;
 
     for(int seq = group; seq < L.batch; seq += groups)
     {
@@ -457,19 +582,24 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                 a.cols = g.cols;
                 a.rows = g.rows;
 
-                float acc[11];
+                float acc[32];
 #pragma unroll
-                for(int k = 0; k < 11; k++) acc[k] = 0.f;
+                for(int k = 0; k < 32; k++) acc[k] = 0.f;
                 for(int k = gtid; k < N; k += gthreads)
                 {
                     const int y = k / g.cols;
                     const int x = k - y * g.cols;
                     float row[4];
                     const bool found = so3_pixel(a, x, y, row);
-                    accumulate_so3(acc, row, found);
+                    float a11[11];
+#pragma unroll
+                    for(int q = 0; q < 11; q++) a11[q] = acc[q];
+                    accumulate_so3(a11, row, found);
+#pragma unroll
+                    for(int q = 0; q < 11; q++) acc[q] = a11[q];
                 }
                 float * myrow = gpart + ((step & 1) * G + rank) * kGnPartialStride;
-                cta_publish<float, 11>(acc, sh, myrow);
+                cta_publish32(acc, sh, myrow);
                 group_barrier(bar, target, G);
                 fold_partials(sh, gpart + (step & 1) * G * kGnPartialStride, G);
                 step++;
@@ -500,20 +630,31 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
         {
             const LevelGeom g = L.geom[lvl];
             const int plane = g.rows * g.cols;
-            const bool vec = (plane & 3) == 0;
-            const int nitems = (plane + 3) >> 2;
-            if(threadIdx.x == 0)
-            {
-                sh.res.lastRGBError = FLT_MAX;
-                level_begin(sh, g);
-            }
-            // Pose-independent half of the RGB association (border, 4x4 non-zero window, gradient magnitude,
-            // finite depth; reduce.cu:780-807), evaluated once per level instead of once per iteration: bit m
-            // of `cand` = this thread's m-th pixel (k = gtid + m * gthreads) is a candidate.
             const int nslots = (plane + gthreads - 1) / gthreads;
-            const bool use_flags = L.rgb && nslots <= 32;
-            unsigned cand = 0;
-            if(use_flags)
+            // all of this thread's pixels fit one register-resident chunk (always true for one 640x480 sequence on a full GPU)
+            const bool single = nslots <= kSlotChunk;
+            if(warp0)
+            {
+                if(threadIdx.x == 0)
+                {
+                    sh.res.lastRGBError = FLT_MAX;
+                    level_begin(sh, g);
+                }
+                __syncwarp();
+                warp_prepare(sh, false);   // krk / kt of the first iteration of this level (Rcurr/tcurr carry over)
+            }
+
+            // ---- per-level, pose-independent pixel state (registers): RGB candidate test (reduce.cu:780-807) and its operands
+            unsigned cand = 0;              // bit c: slot c is an RGB candidate
+            float c_d1[kSlotChunk];         // nextDepth
+            float c_img[kSlotChunk];        // nextImage as float
+            short c_gx[kSlotChunk], c_gy[kSlotChunk];
+#pragma unroll
+            for(int c = 0; c < kSlotChunk; c++)
+            {
+                c_d1[c] = 0.f; c_img[c] = 0.f; c_gx[c] = 0; c_gy[c] = 0;
+            }
+            if(L.rgb && single)
             {
                 ResidualArgs a;
                 a.minScale = L.min_scale[lvl];
@@ -521,57 +662,71 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                 a.nextDepth = in.nextDepth[lvl];
                 a.nextImage = in.nextImage[lvl];
                 a.cols = g.cols; a.rows = g.rows;
-                for(int m = 0; m < nslots; m++)
+#pragma unroll
+                for(int c = 0; c < kSlotChunk; c++)
                 {
-                    const int k = gtid + m * gthreads;
-                    if(k < plane)
+                    const int k = gtid + c * gthreads;
+                    if(c < nslots && k < plane)
                     {
                         const int i = k / g.cols;
-                        if(rgb_candidate(a, k - i * g.cols, i)) cand |= 1u << m;
+                        const int j0 = k - i * g.cols;
+                        if(rgb_candidate(a, j0, i))
+                        {
+                            cand |= 1u << c;
+                            c_d1[c] = a.nextDepth[k];
+                            c_img[c] = static_cast<float>(a.nextImage[k]);
+                            c_gx[c] = a.dIdx[k];
+                            c_gy[c] = a.dIdy[k];
+                        }
                     }
                 }
             }
+            __syncthreads();
 
             for(int j = 0; j < L.iterations[lvl]; j++)
             {
                 slam_step_record * rec = nullptr;
-                const long long t_iter = clock64();
-                if(threadIdx.x == 0)
+                if(threadIdx.x == 0 && tr && ntr < kGnMaxTrace)
                 {
-                    gn_prepare(sh);
-                    if(tr && ntr < kGnMaxTrace)
+                    rec = &tr[ntr];
+                    memset(rec, 0, sizeof(*rec));
+                    rec->kind = 1;
+                    rec->level = lvl;
+                    rec->iteration = j;
+                    for(int k = 0; k < 9; k++)
                     {
-                        rec = &tr[ntr];
-                        memset(rec, 0, sizeof(*rec));
-                        rec->kind = 1;
-                        rec->level = lvl;
-                        rec->iteration = j;
-                        rec->t_cycles[0] = (unsigned)(t_iter - t_start);
-                        GN_STAMP(rec, 1);
-                        for(int k = 0; k < 9; k++)
-                        {
-                            rec->Rcurr_in[k] = sh.Rcurr[k];
-                            rec->krkinv_in[k] = sh.krk[k];
-                            rec->so3_in[k] = sh.Rprev_inv[k];
-                        }
-                        for(int k = 0; k < 3; k++)
-                        {
-                            rec->tcurr_in[k] = sh.tcurr[k];
-                            rec->kt_in[k] = sh.kt[k];
-                        }
+                        rec->Rcurr_in[k] = sh.Rcurr[k];
+                        rec->krkinv_in[k] = sh.krk[k];
+                        rec->so3_in[k] = sh.Rprev_inv[k];
                     }
+                    for(int k = 0; k < 3; k++)
+                    {
+                        rec->tcurr_in[k] = sh.tcurr[k];
+                        rec->kt_in[k] = sh.kt[k];
+                    }
+                    GN_STAMP(rec, 0);
+                    GN_STAMP(rec, 1);
                 }
-                __syncthreads();
 
                 float * rowsA = gpart + (step & 1) * G * kGnPartialStride;
                 float * myrow = rowsA + rank * kGnPartialStride;
 
-                unsigned valid_mask = 0;   // bit m: this thread's m-th pixel has an RGB correspondence this iteration
+                // phase A -> B state of this thread's slots (registers, single-chunk case)
+                unsigned valid_mask = 0;
+                int r_zxy[kSlotChunk];      // (zy << 16) | zx : pixel in the last image
+                float r_diff[kSlotChunk];   // next - last intensity
+                float r_d0[kSlotChunk];     // lastDepth at that pixel
+#pragma unroll
+                for(int c = 0; c < kSlotChunk; c++)
+                {
+                    r_zxy[c] = 0; r_diff[c] = 0.f; r_d0[c] = 0.f;
+                }
+
                 // ---------------- phase A: ICP products + RGB association
                 {
-                    float acc[29];
+                    float acc[32];
 #pragma unroll
-                    for(int k = 0; k < 29; k++) acc[k] = 0.f;
+                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
                     if(L.icp)
                     {
                         IcpArgs a;
@@ -585,27 +740,56 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         a.cols = g.cols;
                         a.rows = g.rows;
                         a.vcurr = in.vcurr[lvl]; a.ncurr = in.ncurr[lvl]; a.vprev = in.vprev[lvl]; a.nprev = in.nprev[lvl];
-                        for(int item = gtid; item < nitems; item += gthreads)
+                        for(int m0 = 0; m0 < nslots; m0 += kIcpChunk)
                         {
-                            const int p = item << 2;
-                            float vx[4], vy[4], vz[4], nx[4], ny[4], nz[4];
-                            load4(a.vcurr, p, plane, vec, vx);
-                            load4(a.vcurr + plane, p, plane, vec, vy);
-                            load4(a.vcurr + 2 * plane, p, plane, vec, vz);
-                            load4(a.ncurr, p, plane, vec, nx);
-                            load4(a.ncurr + plane, p, plane, vec, ny);
-                            load4(a.ncurr + 2 * plane, p, plane, vec, nz);
+                            float3 vg[kIcpChunk], nc[kIcpChunk], vp[kIcpChunk], np[kIcpChunk];
+                            int o[kIcpChunk];
+                            bool ok[kIcpChunk];
+                            // 1) current vertex + normal of every slot of the chunk (coalesced across the warp)
 #pragma unroll
-                            for(int k = 0; k < 4; k++)
-                                if(p + k < plane)
+                            for(int c = 0; c < kIcpChunk; c++)
+                            {
+                                const int k = gtid + (m0 + c) * gthreads;
+                                ok[c] = (m0 + c < nslots) && (k < plane);
+                                const int kk = ok[c] ? k : 0;
+                                vg[c] = make_float3(__ldg(a.vcurr + kk), __ldg(a.vcurr + plane + kk), __ldg(a.vcurr + 2 * plane + kk));
+                                nc[c] = make_float3(__ldg(a.ncurr + kk), __ldg(a.ncurr + plane + kk), __ldg(a.ncurr + 2 * plane + kk));
+                            }
+                            // 2) project all, 3) issue all gathers
+#pragma unroll
+                            for(int c = 0; c < kIcpChunk; c++)
+                            {
+                                float3 g3;
+                                const bool inb = icp_project(a, vg[c], g3, o[c]);
+                                vg[c] = g3;
+                                ok[c] = ok[c] && inb;
+                                if(!ok[c]) o[c] = 0;
+                            }
+#pragma unroll
+                            for(int c = 0; c < kIcpChunk; c++)
+                            {
+                                vp[c] = make_float3(__ldg(a.vprev + o[c]), __ldg(a.vprev + plane + o[c]), __ldg(a.vprev + 2 * plane + o[c]));
+                                np[c] = make_float3(__ldg(a.nprev + o[c]), __ldg(a.nprev + plane + o[c]), __ldg(a.nprev + 2 * plane + o[c]));
+                            }
+                            // 4) gates, rows, products
+#pragma unroll
+                            for(int c = 0; c < kIcpChunk; c++)
+                            {
+                                float row[7];
+                                const bool found = icp_finish(a, vg[c], nc[c], vp[c], np[c], row) && ok[c];
+                                if(found)
                                 {
-                                    float row[7];
-                                    const bool found = icp_pixel(a, make_float3(vx[k], vy[k], vz[k]), make_float3(nx[k], ny[k], nz[k]), row);
-                                    accumulate_se3(acc, row, found);
+                                    float a29[29];
+#pragma unroll
+                                    for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                    accumulate_se3(a29, row, true);
+#pragma unroll
+                                    for(int q = 0; q < 29; q++) acc[q] = a29[q];
                                 }
+                            }
                         }
                     }
-                    int cnt[2] = {0, 0};
+                    int cnt0 = 0, cnt1 = 0;
                     if(L.rgb)
                     {
                         ResidualArgs a;
@@ -618,33 +802,95 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         a.krkinv = mat3_from(sh.krk);
                         a.cols = g.cols; a.rows = g.rows;
                         Corres * cimg = in.corres[lvl];
-                        valid_mask = 0;
-                        for(int m = 0; m < nslots; m++)
+                        if(single)
                         {
-                            const int k = gtid + m * gthreads;
-                            if(k >= plane) break;
-                            const int i = k / g.cols;
-                            const int j0 = k - i * g.cols;
-                            Corres c;
-                            c.zx = c.zy = c.ox = c.oy = 0;
-                            c.diff = 0.f;
-                            c.valid = 0;
-                            const bool is_cand = use_flags ? ((cand >> m) & 1u) != 0 : rgb_candidate(a, j0, i);
-                            const bool ok = is_cand && rgb_associate(a, j0, i, c);
-                            if(ok)
+                            int o0[kSlotChunk];
+                            float td1[kSlotChunk];
+                            unsigned inb = 0;
+                            // 1) warp every candidate, 2) issue the gathers, 3) gates
+#pragma unroll
+                            for(int c = 0; c < kSlotChunk; c++)
                             {
-                                cnt[0] += 1;
-                                cnt[1] += (int)(c.diff * c.diff);
-                                if(m < 32) valid_mask |= 1u << m;
+                                o0[c] = 0;
+                                td1[c] = 0.f;
+                                if((cand >> c) & 1u)
+                                {
+                                    const int k = gtid + c * gthreads;
+                                    const int i = k / g.cols;
+                                    int u0, v0;
+                                    if(rgb_project(a, k - i * g.cols, i, c_d1[c], u0, v0, td1[c]))
+                                    {
+                                        inb |= 1u << c;
+                                        o0[c] = v0 * g.cols + u0;
+                                        r_zxy[c] = (v0 << 16) | u0;
+                                    }
+                                }
                             }
-                            // the reference writes a DataTerm for every pixel; only the valid ones are ever read again,
-                            // so the others are written only when a test wants to tap the whole image
-                            if(ok || L.full_corres || !use_flags) reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
+                            unsigned char lst[kSlotChunk];
+#pragma unroll
+                            for(int c = 0; c < kSlotChunk; c++)
+                            {
+                                r_d0[c] = __ldg(a.lastDepth + o0[c]);
+                                lst[c] = __ldg(a.lastImage + o0[c]);
+                            }
+#pragma unroll
+                            for(int c = 0; c < kSlotChunk; c++)
+                            {
+                                if(((inb >> c) & 1u) && rgb_accept(a, td1[c], r_d0[c], lst[c]))
+                                {
+                                    valid_mask |= 1u << c;
+                                    r_diff[c] = __fsub_rn(c_img[c], static_cast<float>(lst[c]));
+                                    cnt0 += 1;
+                                    cnt1 += (int)(r_diff[c] * r_diff[c]);
+                                }
+                            }
+                            if(L.full_corres)   // the reference writes a DataTerm for every pixel (reduce.cu:838): only when a test taps it
+                            {
+#pragma unroll
+                                for(int c = 0; c < kSlotChunk; c++)
+                                {
+                                    const int k = gtid + c * gthreads;
+                                    if(c < nslots && k < plane)
+                                    {
+                                        Corres cc;
+                                        const bool v = (valid_mask >> c) & 1u;
+                                        const int i = k / g.cols;
+                                        cc.zx = v ? (short)(r_zxy[c] & 0xffff) : 0;
+                                        cc.zy = v ? (short)(r_zxy[c] >> 16) : 0;
+                                        cc.ox = v ? (short)(k - i * g.cols) : 0;
+                                        cc.oy = v ? (short)i : 0;
+                                        cc.diff = v ? r_diff[c] : 0.f;
+                                        cc.valid = v ? 1 : 0;
+                                        reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&cc);
+                                    }
+                                }
+                            }
+                        }
+                        else
+                        {
+                            // general case (several sequences share the GPU, or a large image): correspondences go through memory
+                            for(int m = 0; m < nslots; m++)
+                            {
+                                const int k = gtid + m * gthreads;
+                                if(k >= plane) break;
+                                const int i = k / g.cols;
+                                const int j0 = k - i * g.cols;
+                                Corres c;
+                                c.zx = c.zy = c.ox = c.oy = 0;
+                                c.diff = 0.f;
+                                c.valid = 0;
+                                if(rgb_candidate(a, j0, i) && rgb_associate(a, j0, i, c))
+                                {
+                                    cnt0 += 1;
+                                    cnt1 += (int)(c.diff * c.diff);
+                                }
+                                reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
+                            }
                         }
                     }
                     GN_STAMP(rec, 2);
-                    cta_publish<float, 29>(acc, sh, myrow);
-                    if(L.rgb) cta_publish<int, 2>(cnt, sh, reinterpret_cast<int *>(myrow + 29));
+                    cta_publish32(acc, sh, myrow);
+                    if(L.rgb) cta_publish_int2(cnt0, cnt1, sh, reinterpret_cast<int *>(myrow + 29));
                 }
 
                 if(L.rgb)
@@ -652,22 +898,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                     group_barrier(bar, target, G);
                     GN_STAMP(rec, 3);
                     // count / sigma of the whole image -> sigmaVal (every CTA, identically)
-                    if(threadIdx.x < 32)
+                    if(warp0)
                     {
-                        int c0 = 0, c1 = 0;
-                        for(int r = threadIdx.x; r < G; r += 32)
-                        {
-                            c0 += __float_as_int(__ldcg(rowsA + r * kGnPartialStride + 29));
-                            c1 += __float_as_int(__ldcg(rowsA + r * kGnPartialStride + 30));
-                        }
-                        c0 = warp_sum(c0);
-                        c1 = warp_sum(c1);
-                        if(threadIdx.x == 0)
-                        {
-                            sh.total[29] = __int_as_float(c0);
-                            sh.total[30] = __int_as_float(c1);
-                            gn_sigma(sh, L.rgb_only, rec);
-                        }
+                        fold_count_sigma(sh, rowsA, G);
+                        if(threadIdx.x == 0) gn_sigma(sh, L.rgb_only, rec);
                     }
                     __syncthreads();
                     GN_STAMP(rec, 4);
@@ -678,9 +912,9 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                     }
 
                     // ---------------- phase B: RGB Jacobian products
-                    float acc[29];
+                    float acc[32];
 #pragma unroll
-                    for(int k = 0; k < 29; k++) acc[k] = 0.f;
+                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
                     RgbStepArgs a;
                     a.sigma = sh.sigmaVal;
                     a.fx = g.fx; a.fy = g.fy;
@@ -690,30 +924,53 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                     a.lastDepth = in.lastDepth[lvl];
                     a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
                     a.cloud = nullptr;
-                    const Corres * cimg = in.corres[lvl];
-                    for(int m = 0; m < nslots; m++)
+                    if(single)
                     {
-                        const int k = gtid + m * gthreads;
-                        if(k >= plane) break;
-                        if(use_flags && !((valid_mask >> m) & 1u)) continue;
-                        const int4 raw = *(reinterpret_cast<const int4 *>(cimg) + k);   // written by this very thread in phase A
-                        const Corres c = *reinterpret_cast<const Corres *>(&raw);
-                        if(c.valid & 0xff)
+#pragma unroll
+                        for(int c = 0; c < kSlotChunk; c++)
+                            if((valid_mask >> c) & 1u)
+                            {
+                                float row[7];
+                                rgb_row_regs(a, r_zxy[c] & 0xffff, r_zxy[c] >> 16, r_d0[c], c_gx[c], c_gy[c], r_diff[c], row);
+                                float a29[29];
+#pragma unroll
+                                for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                accumulate_se3(a29, row, true);
+#pragma unroll
+                                for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                            }
+                    }
+                    else
+                    {
+                        const Corres * cimg = in.corres[lvl];
+                        for(int m = 0; m < nslots; m++)
                         {
-                            float row[7];
-                            rgb_row(a, c, row);
-                            accumulate_se3(acc, row, true);
+                            const int k = gtid + m * gthreads;
+                            if(k >= plane) break;
+                            const int4 raw = *(reinterpret_cast<const int4 *>(cimg) + k);   // written by this very thread in phase A
+                            const Corres c = *reinterpret_cast<const Corres *>(&raw);
+                            if(c.valid & 0xff)
+                            {
+                                float row[7];
+                                rgb_row(a, c, row);
+                                float a29[29];
+#pragma unroll
+                                for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                accumulate_se3(a29, row, true);
+#pragma unroll
+                                for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                            }
                         }
                     }
                     GN_STAMP(rec, 5);
-                    cta_publish<float, 29>(acc, sh, myrow + 32);
+                    cta_publish32(acc, sh, myrow + 32);
                 }
                 group_barrier(bar, target, G);
                 fold_partials(sh, rowsA, G);
                 step++;
                 GN_STAMP(rec, 6);
 
-                if(threadIdx.x == 0) gn_update(sh, L.icp, L.rgb, L.icp_weight, rec);
+                if(warp0) warp_update(sh, L.icp, L.rgb, L.icp_weight, rec);
                 GN_STAMP(rec, 7);
                 if(rec) ntr++;
                 __syncthreads();

@@ -91,14 +91,13 @@ struct IcpArgs
     const float * nprev;
 };
 
-// vcurr / ncurr: this pixel's current-frame vertex and normal (already loaded).
-// Returns found_coresp and fills row[7] = [n, s x n, n.(s-d)] (zeros when not found).
-__device__ __forceinline__ bool icp_pixel(const IcpArgs & a, const float3 vcurr, const float3 ncurr, float (&row)[7])
+// The association is split in two so that a kernel can issue the gathers of several pixels before
+// consuming any of them (memory-level parallelism): icp_project() needs only the current vertex,
+// icp_finish() the gathered model vertex / normal.
+//   icp_project: reduce.cu:285-299 -> global-frame vertex, linear index of the model pixel, in-bounds flag
+__device__ __forceinline__ bool icp_project(const IcpArgs & a, const float3 vcurr, float3 & vcurr_g, int & o)
 {
-#pragma unroll
-    for(int k = 0; k < 7; k++) row[k] = 0.f;
-
-    const float3 vcurr_g = a.Rcurr * vcurr + a.tcurr;
+    vcurr_g = a.Rcurr * vcurr + a.tcurr;
     const float3 vcurr_cp = a.Rprev_inv * (vcurr_g - a.tprev);
 
     // vcurr_cp.x * fx / vcurr_cp.z + cx  (reduce.cu:295-296): one reciprocal shared by both components
@@ -106,19 +105,16 @@ __device__ __forceinline__ bool icp_pixel(const IcpArgs & a, const float3 vcurr,
     const int ux = __float2int_rn(approx_div_add(__fmul_rn(vcurr_cp.x, a.fx), dz, a.cx));
     const int uy = __float2int_rn(approx_div_add(__fmul_rn(vcurr_cp.y, a.fy), dz, a.cy));
 
-    if(ux < 0 || uy < 0 || ux >= a.cols || uy >= a.rows || vcurr_cp.z < 0) return false;
+    o = uy * a.cols + ux;
+    return !(ux < 0 || uy < 0 || ux >= a.cols || uy >= a.rows || vcurr_cp.z < 0);
+}
 
-    const int plane = a.rows * a.cols;
-    const int o = uy * a.cols + ux;
-
-    float3 vprev_g, nprev_g;
-    vprev_g.x = __ldg(a.vprev + o);
-    vprev_g.y = __ldg(a.vprev + o + plane);
-    vprev_g.z = __ldg(a.vprev + o + 2 * plane);
-    nprev_g.x = __ldg(a.nprev + o);
-    nprev_g.y = __ldg(a.nprev + o + plane);
-    nprev_g.z = __ldg(a.nprev + o + 2 * plane);
-
+//   icp_finish: reduce.cu:301-348 -> found_coresp and the row [n, s x n, n.(s-d)] (zeros when not found)
+__device__ __forceinline__ bool icp_finish(const IcpArgs & a, const float3 vcurr_g, const float3 ncurr, const float3 vprev_g, const float3 nprev_g,
+                                           float (&row)[7])
+{
+#pragma unroll
+    for(int k = 0; k < 7; k++) row[k] = 0.f;
     const float3 ncurr_g = a.Rcurr * ncurr;
 
     const float dist = norm3(vprev_g - vcurr_g);
@@ -140,6 +136,26 @@ __device__ __forceinline__ bool icp_pixel(const IcpArgs & a, const float3 vcurr,
         row[6] = dot3(n_cp, s_cp - d_cp);
     }
     return found;
+}
+
+// vcurr / ncurr: this pixel's current-frame vertex and normal (already loaded).
+// Returns found_coresp and fills row[7] (zeros when not found).
+__device__ __forceinline__ bool icp_pixel(const IcpArgs & a, const float3 vcurr, const float3 ncurr, float (&row)[7])
+{
+#pragma unroll
+    for(int k = 0; k < 7; k++) row[k] = 0.f;
+    float3 vcurr_g;
+    int o;
+    if(!icp_project(a, vcurr, vcurr_g, o)) return false;
+    const int plane = a.rows * a.cols;
+    float3 vprev_g, nprev_g;
+    vprev_g.x = __ldg(a.vprev + o);
+    vprev_g.y = __ldg(a.vprev + o + plane);
+    vprev_g.z = __ldg(a.vprev + o + 2 * plane);
+    nprev_g.x = __ldg(a.nprev + o);
+    nprev_g.y = __ldg(a.nprev + o + plane);
+    nprev_g.z = __ldg(a.nprev + o + 2 * plane);
+    return icp_finish(a, vcurr_g, ncurr, vprev_g, nprev_g, row);
 }
 
 // acc[0..26] += upper triangle of row^T row (7x7, row-major, without gg), acc[27] += gg
@@ -200,27 +216,39 @@ __device__ __forceinline__ bool rgb_candidate(const ResidualArgs & a, int j0, in
     return !isnan(a.nextDepth[i * a.cols + j0]);
 }
 
-// Pose-dependent part (reduce.cu:809-831).  Returns validity; fills c (zero = pixel in the
-// last image, one = this pixel, diff = next - last intensity).
-__device__ __forceinline__ bool rgb_associate(const ResidualArgs & a, int x, int y, Corres & c)
+// Pose-dependent part (reduce.cu:809-831), again split around the gather:
+//   rgb_project: warp pixel (x, y) with depth d1 into the last image -> (u0, v0), warped depth, in-bounds flag
+__device__ __forceinline__ bool rgb_project(const ResidualArgs & a, int x, int y, float d1, int & u0, int & v0, float & transformed_d1)
 {
-    const float d1 = a.nextDepth[y * a.cols + x];
     // d1 * (k.x * x + k.y * y + k.z) + kt, the reference's roundings (residualKernel SASS): k.y*y rounded, k.x*x fused,
     // + k.z added, then one FFMA with d1; the two quotients share one approximate reciprocal.
     const float xf = (float)x, yf = (float)y;
     const float s2 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r2.x, __fmul_rn(yf, a.krkinv.r2.y)), a.krkinv.r2.z);
     const float s0 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r0.x, __fmul_rn(yf, a.krkinv.r0.y)), a.krkinv.r0.z);
     const float s1 = __fadd_rn(__fmaf_rn(xf, a.krkinv.r1.x, __fmul_rn(yf, a.krkinv.r1.y)), a.krkinv.r1.z);
-    const float transformed_d1 = __fmaf_rn(d1, s2, a.kt.z);
+    transformed_d1 = __fmaf_rn(d1, s2, a.kt.z);
     const ApproxDivisor dz = approx_divisor(transformed_d1);
-    const int u0 = __float2int_rn(approx_div(__fmaf_rn(d1, s0, a.kt.x), dz));
-    const int v0 = __float2int_rn(approx_div(__fmaf_rn(d1, s1, a.kt.y), dz));
+    u0 = __float2int_rn(approx_div(__fmaf_rn(d1, s0, a.kt.x), dz));
+    v0 = __float2int_rn(approx_div(__fmaf_rn(d1, s1, a.kt.y), dz));
+    return u0 >= 0 && v0 >= 0 && u0 < a.cols && v0 < a.rows;
+}
+//   rgb_accept: the gathered last depth / intensity pass the gates
+__device__ __forceinline__ bool rgb_accept(const ResidualArgs & a, float transformed_d1, float d0, unsigned char l)
+{
+    return d0 > 0 && fabsf(transformed_d1 - d0) <= a.maxDepthDelta && l != 0;
+}
 
-    if(u0 >= 0 && v0 >= 0 && u0 < a.cols && v0 < a.rows)
+// Returns validity; fills c (zero = pixel in the last image, one = this pixel, diff = next - last intensity).
+__device__ __forceinline__ bool rgb_associate(const ResidualArgs & a, int x, int y, Corres & c)
+{
+    const float d1 = a.nextDepth[y * a.cols + x];
+    int u0, v0;
+    float transformed_d1;
+    if(rgb_project(a, x, y, d1, u0, v0, transformed_d1))
     {
         const float d0 = __ldg(a.lastDepth + v0 * a.cols + u0);
         const unsigned char l = __ldg(a.lastImage + v0 * a.cols + u0);
-        if(d0 > 0 && fabsf(transformed_d1 - d0) <= a.maxDepthDelta && l != 0)
+        if(rgb_accept(a, transformed_d1, d0, l))
         {
             c.zx = (short)u0;
             c.zy = (short)v0;
@@ -287,6 +315,32 @@ __device__ __forceinline__ void rgb_row(const RgbStepArgs & a, const Corres & c,
     const float v1 = dI_dy_val * a.fy * invz;
     const float v2 = -(v0 * cloudPoint.x + v1 * cloudPoint.y) * invz;
 
+    row[0] = v0;
+    row[1] = v1;
+    row[2] = v2;
+    row[3] = -cloudPoint.z * v1 + cloudPoint.y * v2;
+    row[4] = cloudPoint.z * v0 - cloudPoint.x * v2;
+    row[5] = -cloudPoint.y * v0 + cloudPoint.x * v1;
+}
+
+// Same row from values the caller already holds in registers: z = lastDepth at (zx, zy) (the reference's
+// cloud point is (x - cx) * z * invFx, ..., utils.cu:655), the two gradients at the pixel itself, diff.
+__device__ __forceinline__ void rgb_row_regs(const RgbStepArgs & a, int zx, int zy, float z, short gx, short gy, float diff, float (&row)[7])
+{
+    float w = a.sigma + fabsf(diff);
+    w = w > SLAM_FLT_EPSILON ? 1.0f / w : 1.0f;
+    if(a.sigma == -1) w = 1;
+    row[6] = -w * diff;
+    float3 cloudPoint;
+    cloudPoint.x = __fmul_rn(__fmul_rn((zx - a.cx), z), a.invFx);
+    cloudPoint.y = __fmul_rn(__fmul_rn((zy - a.cy), z), a.invFy);
+    cloudPoint.z = z;
+    const float invz = 1.0 / cloudPoint.z;
+    const float dI_dx_val = w * a.sobelScale * gx;
+    const float dI_dy_val = w * a.sobelScale * gy;
+    const float v0 = dI_dx_val * a.fx * invz;
+    const float v1 = dI_dy_val * a.fy * invz;
+    const float v2 = -(v0 * cloudPoint.x + v1 * cloudPoint.y) * invz;
     row[0] = v0;
     row[1] = v1;
     row[2] = v2;
@@ -388,6 +442,31 @@ __device__ __forceinline__ T warp_sum(T v)
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Transposed ("reduce-scatter") warp reduction: 32 values per lane in, lane L ends with the warp-wide
+// sum of value L in v[0].  31 shuffles instead of 32 x 5, fixed summation pattern (deterministic).
+template <int W>
+__device__ __forceinline__ void warp_rs_step(float (&v)[32], const int lane)
+{
+    const bool upper = (lane & W) != 0;
+#pragma unroll
+    for(int i = 0; i < W; i++)
+    {
+        const float send = upper ? v[i] : v[i + W];
+        const float keep = upper ? v[i + W] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+    }
+}
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32])
+{
+    const int lane = threadIdx.x & 31;
+    warp_rs_step<16>(v, lane);
+    warp_rs_step<8>(v, lane);
+    warp_rs_step<4>(v, lane);
+    warp_rs_step<2>(v, lane);
+    warp_rs_step<1>(v, lane);
+    return v[0];
 }
 
 // Block-wide sum of NV values per thread. blockDim.x must be a multiple of 32 and <= 1024.
