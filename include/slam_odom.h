@@ -176,6 +176,9 @@ typedef struct slam_step_record
      * [0] step begin, [1] parameters ready, [2] phase A mapped, [3] phase A published + barrier passed,
      * [4] sigma known, [5] phase B mapped, [6] phase B published + barrier + fold done, [7] solve done */
     unsigned int t_cycles[8];
+    /* sub-stages of the solve: [0] systems combined, [1] elimination done, [2] rotation increment, [3] resultRt updated,
+     * [4] next parameters ready (cycles since the kernel started) */
+    unsigned int t_solve[8];
 } slam_step_record;
 /* enable: 0 = off, 1 = step records only, 2 = records + the full DataTerm image of every RGB residual
  * pass (what the reference writes; needed by SLAM_TAP_CORRES) */

@@ -379,7 +379,7 @@ struct RefOdom
                     for(int k = 0; k < 36; k++) lastA[k] = A_rgbd[k];
                     for(int k = 0; k < 6; k++) lastb[k] = b_rgbd[k];
                 }
-                smath::ldlt_solve<double, 6>(lastA, lastb, result, DBL_EPSILON);
+                smath::spd_solve6(lastA, lastb, result);
                 smath::update_se3(resultRt, result);
                 smath::compose_current_pose(Rprev, tprev, resultRt, Rcurr, tcurr);
 

@@ -48,6 +48,8 @@ struct GnShared
     double resultR[9], lastResultR[9];
     double K[9], Kinv[9];   // intrinsics of the running level (and of level 2 during SO3)
     double A[36], b[6], x[6], Rinc[9], newRt[12], Mi[9], KR[9], tinv[3];
+    double aug[2][42];      // ping-pong buffers of the 6x7 Gauss-Jordan elimination
+    int solve_ok;
     float tinvf[3];
     float R_lr[9];
     float lastError, lastCount;
@@ -75,7 +77,11 @@ __device__ __forceinline__ void group_barrier(unsigned * ctr, unsigned & target,
 
 // Block sum of up to 32 per-thread floats (v[NV..31] must be 0) -> dst[0..31] (global partial row
 // of this CTA).  Transposed warp reduction, then 32 threads add the per-warp rows.
-__device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, float * dst)
+// The caller must reach a __syncthreads() (e.g. group_barrier) before sh.red is reused.
+// With count_cols, slots 29 / 30 / 31 carry exact small integers as floats (RGB correspondence count, low
+// 12 bits and high bits of the squared-residual sum); they are recombined into the two int32 columns
+// 29 (count) and 30 (sigma) of the partial row.
+__device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, float * dst, const bool count_cols = false)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float s = warp_reduce_scatter32(v);
@@ -86,9 +92,14 @@ __device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, flo
         float total = 0.f;
 #pragma unroll 16
         for(int w = 0; w < nw; w++) total += sh.red[w * 32 + threadIdx.x];
+        if(count_cols)
+        {
+            const float hi = __shfl_sync(0xffffffffu, total, 31);
+            if(threadIdx.x == 29) total = __int_as_float((int)total);
+            if(threadIdx.x == 30) total = __int_as_float((int)total + ((int)hi << 12));
+        }
         dst[threadIdx.x] = total;
     }
-    __syncthreads();
 }
 
 // Same for two per-thread ints (count, sigma) -> dst[0..1].
@@ -287,23 +298,76 @@ __device__ __forceinline__ void warp_prepare(GnShared & sh, const bool with_pose
     __syncwarp();
 }
 
-// The serial core of one step: x = A^-1 b and the incremental rotation.  Lane 0.
-__device__ __noinline__ void solve_core(GnShared & sh)
+// smath::gauss_jordan_solve<double, 6> with the 42 entries of [A | b] spread over the lanes of warp 0
+// (same per-entry arithmetic, bit-identical result).  sh.aug[0] holds the system on entry; x lands in sh.x.
+__device__ __forceinline__ void warp_gauss_jordan(GnShared & sh)
 {
-    double A[36], b[6], x[6], R[9];
+    const int lane = threadIdx.x & 31;
+    double dmax = 0;
+#pragma unroll
+    for(int i = 0; i < 6; i++)
+    {
+        const double d = sh.aug[0][i * 7 + i];
+        dmax = d > dmax ? d : dmax;
+    }
+    const double floor_d = smath::mul(dmax, 1e-9);
+    bool ok = dmax > 0.0;
+#pragma unroll
+    for(int k = 0; k < 6; k++)
+    {
+        const double * src = sh.aug[k & 1];
+        double * dst = sh.aug[(k & 1) ^ 1];
+        const double p = src[k * 7 + k];
+        ok = ok && (p > floor_d);
+        const double inv = smath::dvd(1.0, p);
+#pragma unroll
+        for(int pass = 0; pass < 2; pass++)
+        {
+            const int e = lane + 32 * pass;
+            if(e < 42)
+            {
+                const int i = e / 7, j = e - i * 7;
+                double v = src[e];
+                if(j > k)
+                {
+                    const double rkj = smath::mul(src[k * 7 + j], inv);
+                    v = (i == k) ? rkj : smath::sub(v, smath::mul(src[i * 7 + k], rkj));
+                }
+                dst[e] = v;
+            }
+        }
+        __syncwarp();
+    }
+    // six steps: the result is back in aug[0]
+    if(lane < 6) sh.x[lane] = sh.aug[0][lane * 7 + 6];
+    if(lane == 0) sh.solve_ok = ok ? 1 : 0;
+    __syncwarp();
+}
+
+// Degenerate system (a pivot not safely positive): the pivoted / pseudo-inverse LDL^T of small_math.hpp.  Lane 0.
+__device__ __noinline__ void solve_fallback(GnShared & sh)
+{
+    double A[36], b[6], x[6];
     for(int k = 0; k < 36; k++) A[k] = sh.A[k];
     for(int k = 0; k < 6; k++) b[k] = sh.b[k];
-    smath::ldlt_solve<double, 6>(A, b, x, DBL_EPSILON);
-    smath::rodrigues(x + 3, R);
+    smath::ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON);
     for(int k = 0; k < 6; k++) sh.x[k] = x[k];
+}
+
+// Incremental rotation of the step (odom/utils.h:16-52).  Lane 0.
+__device__ __noinline__ void rodrigues_core(GnShared & sh)
+{
+    double r[3] = {sh.x[3], sh.x[4], sh.x[5]}, R[9];
+    smath::rodrigues(r, R);
     for(int k = 0; k < 9; k++) sh.Rinc[k] = R[k];
 }
 
 // RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems, solve, update resultRt, then the next
 // iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
-__device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec)
+__device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec, const long long t_start)
 {
     const int lane = threadIdx.x & 31;
+#define GN_SSTAMP(idx) do { if(rec) rec->t_solve[idx] = (unsigned)(clock64() - t_start); } while(0)
     // ---- stage 0: lastA / lastb (upper triangle + mirror), stats
     if(lane < 27)
     {
@@ -326,11 +390,16 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
         else
             v = icp ? (double)vi : (double)vr;
         if(j == 6)
+        {
             sh.b[i] = v;
+            sh.aug[0][i * 7 + 6] = v;
+        }
         else
         {
             sh.A[i * 6 + j] = v;
             sh.A[j * 6 + i] = v;
+            sh.aug[0][i * 7 + j] = v;
+            sh.aug[0][j * 7 + i] = v;
         }
     }
     else if(lane == 27 && icp)
@@ -339,9 +408,17 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
         sh.res.lastICPCount = sh.total[28];
     }
     __syncwarp();
-    // ---- stage 1: the serial core
-    if(lane == 0) solve_core(sh);
+    GN_SSTAMP(0);
+    // ---- stage 1: x = A^-1 b (parallel elimination), then the incremental rotation
+    warp_gauss_jordan(sh);
+    GN_SSTAMP(1);
+    if(lane == 0)
+    {
+        if(!sh.solve_ok) solve_fallback(sh);
+        rodrigues_core(sh);
+    }
     __syncwarp();
+    GN_SSTAMP(2);
     // ---- stage 2: resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), rows 0..2
     if(lane < 12)
     {
@@ -357,8 +434,10 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
     if(lane >= 12 && lane < 18) sh.res.lastb[lane - 12] = sh.b[lane - 12];
     for(int k = lane; k < 36; k += 32) sh.res.lastA[k] = sh.A[k];
     __syncwarp();
+    GN_SSTAMP(3);
     // ---- stages 3..5: parameters of the next iteration
     warp_prepare(sh, true);
+    GN_SSTAMP(4);
     if(lane == 0)
     {
         sh.res.gn_iterations++;
@@ -889,8 +968,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                         }
                     }
                     GN_STAMP(rec, 2);
-                    cta_publish32(acc, sh, myrow);
-                    if(L.rgb) cta_publish_int2(cnt0, cnt1, sh, reinterpret_cast<int *>(myrow + 29));
+                    // per-thread counts are tiny: carried through the float reduction exactly (block sums < 2^24)
+                    acc[29] = (float)cnt0;
+                    acc[30] = (float)(cnt1 & 0xfff);
+                    acc[31] = (float)(cnt1 >> 12);
+                    cta_publish32(acc, sh, myrow, L.rgb);
                 }
 
                 if(L.rgb)
@@ -970,7 +1052,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                 step++;
                 GN_STAMP(rec, 6);
 
-                if(warp0) warp_update(sh, L.icp, L.rgb, L.icp_weight, rec);
+                if(warp0) warp_update(sh, L.icp, L.rgb, L.icp_weight, rec, t_start);
                 GN_STAMP(rec, 7);
                 if(rec) ntr++;
                 __syncthreads();

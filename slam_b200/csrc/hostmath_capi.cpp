@@ -7,7 +7,7 @@ void hm_mat3_inverse_f(const float * m, float * out) { smath::mat3_inverse(m, ou
 void hm_mat3_inverse_d(const double * m, double * out) { smath::mat3_inverse(m, out); }
 void hm_mat4_inverse_d(const double * m, double * out) { smath::mat4_inverse(m, out); }
 void hm_mat4_affine_inverse_d(const double * m, double * out) { smath::mat4_affine_inverse(m, out); }
-void hm_ldlt6_d(const double * A, const double * b, double * x) { smath::ldlt_solve<double, 6>(A, b, x, DBL_EPSILON); }
+void hm_ldlt6_d(const double * A, const double * b, double * x) { smath::spd_solve6(A, b, x); }
 void hm_ldlt6_pivoted_d(const double * A, const double * b, double * x) { smath::ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON); }
 void hm_ldlt3_f(const float * A, const float * b, float * x) { smath::ldlt_solve<float, 3>(A, b, x, FLT_EPSILON); }
 void hm_rodrigues(const double * r, double * R) { smath::rodrigues(r, R); }

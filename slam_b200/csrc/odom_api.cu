@@ -585,7 +585,7 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
                 for(int k = 0; k < 36; k++) st.lastA[k] = A_rgbd[k];
                 for(int k = 0; k < 6; k++) st.lastb[k] = b_rgbd[k];
             }
-            smath::ldlt_solve<double, 6>(st.lastA, st.lastb, result, DBL_EPSILON);
+            smath::spd_solve6(st.lastA, st.lastb, result);
 
             smath::update_se3(resultRt, result);
             smath::compose_current_pose(Rprev, tprev, resultRt, Rcurr, tcurr);

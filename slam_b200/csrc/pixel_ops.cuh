@@ -290,6 +290,12 @@ __device__ __forceinline__ float3 cloud_point(const float * depth, int cols, int
     return p;
 }
 
+// `float invz = 1.0 / cloudPoint.z` (reduce.cu:541) is an fp64 division rounded to float in the reference.
+// The correctly rounded fp32 reciprocal is the same number except when the fp64 quotient falls within
+// 2^-29 (relative) of a float rounding boundary, and it only scales a Jacobian row (sums: 1e-4 contract),
+// so the IEEE fp32 reciprocal is used: ~10x shorter dependency chain than the fp64 divide.
+__device__ __forceinline__ float rgb_invz(float z) { return __frcp_rn(z); }
+
 __device__ __forceinline__ void rgb_row(const RgbStepArgs & a, const Corres & c, float (&row)[7])
 {
 #define SLAM_FLT_EPSILON ((float)1.19209290E-07F)
@@ -308,7 +314,7 @@ __device__ __forceinline__ void rgb_row(const RgbStepArgs & a, const Corres & c,
     else
         cloudPoint = cloud_point(a.lastDepth, a.cols, c.zx, c.zy, a.invFx, a.invFy, a.cx, a.cy);
 
-    const float invz = 1.0 / cloudPoint.z;   // fp64 reciprocal on purpose, reduce.cu:541
+    const float invz = rgb_invz(cloudPoint.z);
     const float dI_dx_val = w * a.sobelScale * __ldg(a.dIdx + c.oy * a.cols + c.ox);
     const float dI_dy_val = w * a.sobelScale * __ldg(a.dIdy + c.oy * a.cols + c.ox);
     const float v0 = dI_dx_val * a.fx * invz;
@@ -335,7 +341,7 @@ __device__ __forceinline__ void rgb_row_regs(const RgbStepArgs & a, int zx, int 
     cloudPoint.x = __fmul_rn(__fmul_rn((zx - a.cx), z), a.invFx);
     cloudPoint.y = __fmul_rn(__fmul_rn((zy - a.cy), z), a.invFy);
     cloudPoint.z = z;
-    const float invz = 1.0 / cloudPoint.z;
+    const float invz = rgb_invz(cloudPoint.z);
     const float dI_dx_val = w * a.sobelScale * gx;
     const float dI_dy_val = w * a.sobelScale * gy;
     const float v0 = dI_dx_val * a.fx * invz;

@@ -309,7 +309,56 @@ SM_HD bool ldlt_solve_nopivot(const T * A, const T * b, T * x)
     return true;
 }
 
-// The solver behind every `A.ldlt().solve(b)` of the path: register-resident fast route for
+// Gauss-Jordan elimination of the augmented system [A | b] without pivoting.  Every entry's update
+// at step k reads only the previous step's values, so the 42 entries of a 6x7 system can be updated
+// by 42 independent workers: the device-resident loop spreads them over the lanes of a warp
+// (gn_kernel.cu: warp_gauss_jordan) and gets bit-identical results to this serial version.
+// Returns false when a pivot is not safely positive (caller falls back to the pivoted LDL^T).
+template <typename T, int N>
+SM_HD bool gauss_jordan_solve(const T * A, const T * b, T * x)
+{
+    constexpr int W = N + 1;
+    T cur[N * W], nxt[N * W];
+    T dmax = 0;
+    for(int i = 0; i < N; i++)
+    {
+        for(int j = 0; j < N; j++) cur[i * W + j] = A[i * N + j];
+        cur[i * W + N] = b[i];
+        dmax = A[i * N + i] > dmax ? A[i * N + i] : dmax;
+    }
+    const T floor_d = mul(dmax, T(1e-9));
+    bool ok = dmax > T(0);
+    for(int k = 0; k < N; k++)
+    {
+        const T p = cur[k * W + k];
+        ok = ok && (p > floor_d);
+        const T inv = dvd(T(1), p);
+        for(int i = 0; i < N; i++)
+            for(int j = 0; j < W; j++)
+            {
+                T v = cur[i * W + j];
+                if(j > k)
+                {
+                    const T rkj = mul(cur[k * W + j], inv);
+                    v = (i == k) ? rkj : sub(v, mul(cur[i * W + k], rkj));
+                }
+                nxt[i * W + j] = v;
+            }
+        for(int e = 0; e < N * W; e++) cur[e] = nxt[e];
+    }
+    if(!ok) return false;
+    for(int i = 0; i < N; i++) x[i] = cur[i * W + N];
+    return true;
+}
+
+// The 6x6 solve of every ICP / RGB step (`lastA.ldlt().solve(lastb)`, RGBDOdometryef.cpp:544-556): the
+// parallelisable elimination for positive definite systems, the pivoted / pseudo-inverse LDL^T otherwise.
+SM_HD void spd_solve6(const double * A, const double * b, double * x)
+{
+    if(!gauss_jordan_solve<double, 6>(A, b, x)) ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON);
+}
+
+// The solver behind the remaining `A.ldlt().solve(b)` calls (3x3 float SO3 system): register-resident fast route for
 // positive definite systems, pivoted / pseudo-inverse route for degenerate ones.
 template <typename T, int N>
 SM_HD void ldlt_solve(const T * A, const T * b, T * x, T eps)

@@ -60,7 +60,7 @@ class StepRecord(C.Structure):
         ("rgb_count", C.c_int), ("rgb_sigma", C.c_int),
         ("x", C.c_double * 6), ("Rcurr", C.c_float * 9), ("tcurr", C.c_float * 3),
         ("Rcurr_in", C.c_float * 9), ("tcurr_in", C.c_float * 3), ("krkinv_in", C.c_float * 9), ("kt_in", C.c_float * 3),
-        ("sigma_in", C.c_float), ("so3_in", C.c_float * 27), ("t_cycles", C.c_uint * 8),
+        ("sigma_in", C.c_float), ("so3_in", C.c_float * 27), ("t_cycles", C.c_uint * 8), ("t_solve", C.c_uint * 8),
     ]
 
     def as_dict(self):
@@ -69,7 +69,7 @@ class StepRecord(C.Structure):
                     rgb_sigma=self.rgb_sigma, x=np.array(self.x[:]), Rcurr=np.array(self.Rcurr[:], np.float32).reshape(3, 3),
                     tcurr=np.array(self.tcurr[:], np.float32), Rcurr_in=np.array(self.Rcurr_in[:], np.float32), tcurr_in=np.array(self.tcurr_in[:], np.float32),
                     krkinv_in=np.array(self.krkinv_in[:], np.float32), kt_in=np.array(self.kt_in[:], np.float32), sigma_in=float(self.sigma_in),
-                    so3_in=np.array(self.so3_in[:], np.float32), t_cycles=np.array(self.t_cycles[:], np.int64))
+                    so3_in=np.array(self.so3_in[:], np.float32), t_cycles=np.array(self.t_cycles[:], np.int64), t_solve=np.array(self.t_solve[:], np.int64))
 
 
 class FrameHost(C.Structure):

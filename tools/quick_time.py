@@ -37,7 +37,10 @@ def bench(name, odo, n=200, **kw):
             extra = f"  gn kernel {ms / nl * 1e3:8.1f} us/launch"
     print(f"{name:40s} {dt*1e6:9.1f} us/frame  {1/dt:9.1f} fps{extra}", flush=True)
 
+import os
+ONLY_DEV = os.environ.get("QT_DEVICE_ONLY")
 for kw, tag in ((dict(so3=True), "icp+rgb+so3"), (dict(so3=False, icpWeight=100.0), "icp only")):
     bench("device loop " + tag, RGBDOdometry(*args), **kw)
+    if ONLY_DEV: continue
     bench("host loop   " + tag, RGBDOdometry(*args, host_loop=True), **kw)
     bench("reference   " + tag, RefOdometry(*args), n=50, **kw)

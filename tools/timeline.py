@@ -29,4 +29,6 @@ for s in tr:
     d = np.diff(t)
     gap = t[0] - prev_end if prev_end is not None else 0
     prev_end = t[7]
-    print(f"{s['kind']:4d} {s['level']:3d} {s['iteration']:2d} | gap {gap:6d} " + " ".join(f"{int(x):6d}" for x in d) + f"  total {t[7]-t[0]:7d}")
+    ts = s["t_solve"]
+    sub = [ts[0] - t[6]] + list(np.diff(ts[:5])) + [t[7] - ts[4]]
+    print(f"{s['kind']:4d} {s['level']:3d} {s['iteration']:2d} | gap {gap:6d} " + " ".join(f"{int(x):6d}" for x in d) + f"  total {t[7]-t[0]:7d} | solve: comb {sub[0]} elim {sub[1]} rodr {sub[2]} upd {sub[3]} prep {sub[4]} rec {sub[5]}")
