@@ -50,6 +50,7 @@ struct GnShared
     double A[36], b[6], x[6], Rinc[9], newRt[12], Mi[9], KR[9], tinv[3];
     double aug[2][42];      // ping-pong buffers of the 6x7 Gauss-Jordan elimination
     int solve_ok;
+    int rgb_sigma_last, rgb_count_last;   // operands of lastRGBError (computed once, at the end)
     float tinvf[3];
     float R_lr[9];
     float lastError, lastCount;
@@ -549,21 +550,30 @@ __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record 
 }
 
 // RGBDOdometryef.cpp:457-471; count/sigma are in sh.total[29], [30] (integer bit patterns).  Lane 0.
-__device__ __noinline__ void gn_sigma(GnShared & sh, const bool rgb_only, slam_step_record * rec)
+// sigmaVal = sqrt(rgbSize) (or 1, or -1): the fp32 square root of an integer below 2^24 equals the reference's
+// float(sqrt(double)) exactly.  rgbError is only a statistic unless rgbOnly (where it decides the early exit), so
+// outside that mode its fp64 arithmetic is deferred to the end of the sequence.
+__device__ __forceinline__ void gn_sigma(GnShared & sh, const bool rgb_only, slam_step_record * rec)
 {
     const int rgbSize = __float_as_int(sh.total[29]);
     const int sigma = __float_as_int(sh.total[30]);
     // sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize): the quotient is 0 only for sigma == 0 with rgbSize != 0
     const int sel = (rgbSize != 0 && sigma == 0) ? 1 : rgbSize;
-    float sigmaVal = (float)sqrt((double)sel);
-    const float rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
-    sh.stop = (rgb_only && rgbError > sh.res.lastRGBError) ? 1 : 0;
+    float sigmaVal = __fsqrt_rn((float)sel);
+    sh.stop = 0;
+    if(rgb_only)
+    {
+        const float rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
+        sh.stop = (rgbError > sh.res.lastRGBError) ? 1 : 0;
+        if(!sh.stop) sh.res.lastRGBError = rgbError;
+        sigmaVal = -1;
+    }
     if(!sh.stop)
     {
-        sh.res.lastRGBError = rgbError;
+        sh.rgb_sigma_last = sigma;
+        sh.rgb_count_last = rgbSize;
         sh.res.lastRGBCount = (float)rgbSize;
     }
-    if(rgb_only) sigmaVal = -1;
     sh.sigmaVal = sigmaVal;
     if(rec)
     {
@@ -587,9 +597,11 @@ __device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)   // l
     sh.lastCount = FLT_MAX / 2;
     memset(&sh.res, 0, sizeof(sh.res));
     sh.stop = 0;
+    sh.rgb_sigma_last = 0;
+    sh.rgb_count_last = -1;
 }
 
-__device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, GnResult * out)   // lane 0
+__device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, const bool rgb_only, GnResult * out)   // lane 0
 {
     if(rgb)
     {
@@ -601,6 +613,8 @@ __device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, GnResult * o
             for(int k = 0; k < 3; k++) sh.tcurr[k] = sh.tprev[k];
         }
     }
+    if(rgb && !rgb_only && sh.rgb_count_last >= 0)   // RGBDOdometryef.cpp:458
+        sh.res.lastRGBError = (float)(sqrt((double)sh.rgb_sigma_last) / (double)(sh.rgb_count_last == 0 ? 1 : sh.rgb_count_last));
     if(out)
     {
         for(int k = 0; k < 9; k++) sh.res.Rcurr[k] = sh.Rcurr[k];
@@ -1059,7 +1073,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
             }
         }
 
-        if(threadIdx.x == 0) seq_end(sh, L.rgb, leader ? &results[seq] : nullptr);
+        if(threadIdx.x == 0) seq_end(sh, L.rgb, L.rgb_only, leader ? &results[seq] : nullptr);
         if(leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();
     }

@@ -29,6 +29,29 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
     float wall = 0;
     const float weights[] = {0.375f, 0.25f, 0.0625f};
 
+    if(x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3)
+    {
+        // interior: the full 5x5 window; all 25 loads are issued before the first use.  Every product and partial sum
+        // is exact in fp32 (16-bit values x multiples of 1/256), so only the final quotient rounds, as in the reference.
+        const unsigned short * p = src + (2 * y - 2) * scols + (2 * x - 2);
+        int val[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++) val[r][c] = p[r * scols + c];
+        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(abs(val[r][c] - center) < 3 * sigma_color)
+                {
+                    sum += val[r][c] * w5[c] * w5[r];
+                    wall += w5[c] * w5[r];
+                }
+        return static_cast<unsigned short>(static_cast<int>(sum / wall));
+    }
+
     for(int yi = y_mi; yi < y_ma; ++yi)
         for(int xi = x_mi; xi < x_ma; ++xi)
         {
@@ -79,6 +102,29 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
     int cy = max(0, 2 * y - D / 2);
     float sum = 0;
     int count = 0;
+    if(x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)
+    {
+        // interior: full window, weight index (4-r)*5 + (4-c) = the symmetric {1,4,6,4,1}^2 table; loads first,
+        // then the reference's accumulation order (rows outer, columns inner), one FMA per finite tap.
+        const float * p = src + (2 * y - 2) * scols + (2 * x - 2);
+        float v[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++) v[r][c] = p[r * scols + c];
+        const float w5[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(!isnan(v[r][c]))
+                {
+                    const float w = w5[r] * w5[c];
+                    sum = __fmaf_rn(v[r][c], w, sum);
+                    count += (int)w;
+                }
+        return (float)(sum / (float)count);
+    }
     for(; cy < ty; ++cy)
         for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
         {
@@ -101,6 +147,28 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
     int cy = max(0, 2 * y - D / 2);
     float sum = 0;
     int count = 0;
+    if(x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)
+    {
+        // interior: full window; integer arithmetic is exact here (<= 255 * 256), only the quotient rounds
+        const unsigned char * p = src + (2 * y - 2) * scols + (2 * x - 2);
+        int v[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++) v[r][c] = p[r * scols + c];
+        const int w5[5] = {1, 4, 6, 4, 1};
+        int isum = 0;
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(v[r][c] > 0)
+                {
+                    isum += v[r][c] * w5[r] * w5[c];
+                    count += w5[r] * w5[c];
+                }
+        return (unsigned char)((float)isum / (float)count);
+    }
     for(; cy < ty; ++cy)
         for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
         {
@@ -402,6 +470,27 @@ __device__ __forceinline__ void derivative_pixel(const unsigned char * src, int 
     const float gy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
     float dxVal = 0;
     float dyVal = 0;
+    if(x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1)
+    {
+        // interior: the nine taps are loaded first, then accumulated in the reference's order (kernelIndex 8 -> 0)
+        const unsigned char * p = src + (y - 1) * cols + (x - 1);
+        float v[9];
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) v[r * 3 + c] = (float)p[r * cols + c];
+        const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+        const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+#pragma unroll
+        for(int t = 0; t < 9; t++)
+        {
+            dxVal = __fmaf_rn(v[t], fgx[8 - t], dxVal);
+            dyVal = __fmaf_rn(v[t], fgy[8 - t], dyVal);
+        }
+        dx = (short)dxVal;
+        dy = (short)dyVal;
+        return;
+    }
     int kernelIndex = 8;
     for(int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
         for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
