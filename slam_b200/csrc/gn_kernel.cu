@@ -32,7 +32,6 @@
 
 namespace slam {
 
-constexpr int kSlotChunk = 5;   // slots processed together (640x480 on 148 CTAs: 5 slots per thread at level 0)
 constexpr int kIcpChunk = 3;    // ICP gathers in flight per thread (register budget)
 
 struct GnShared
@@ -625,8 +624,8 @@ __device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, const bool r
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kGnThreads, 1)
-k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * partials, GnResult * results, slam_step_record * trace, int * trace_count,
-                const int G, const int groups)
+k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, float * partials, GnResult * results, slam_step_record * trace,
+                int * trace_count, const int G, const int groups)
 {
     __shared__ GnShared sh;
 
@@ -635,7 +634,9 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
     if(group >= groups) return;
 
     unsigned * bar = &ctl->barrier[group];
-    unsigned target = 0;
+    // the counter is never reset: every launch starts from the value the previous launch ended with, published in
+    // ctl->base by the group leader (stable for the whole launch: it is rewritten only at the very end)
+    unsigned target = ctl->base[group];
     unsigned step = 0;
     // partial rows of this group: [parity][rank][64]
     float * gpart = partials + (size_t)group * 2 * G * kGnPartialStride;
@@ -649,7 +650,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
 
     for(int seq = group; seq < L.batch; seq += groups)
     {
-        const GnSeqIn & in = seqs[seq];
+        const GnSeqIn & in = (L.batch == 1) ? seq0 : seqs[seq];
         slam_step_record * tr = (L.trace && leader) ? trace + (size_t)seq * kGnMaxTrace : nullptr;
         int ntr = 0;
 
@@ -763,13 +764,23 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
                     {
                         const int i = k / g.cols;
                         const int j0 = k - i * g.cols;
-                        if(rgb_candidate(a, j0, i))
+                        short gx, gy;
+                        bool is_cand;
+                        if(L.derive_gradients)
+                            is_cand = rgb_candidate_derive(a, j0, i, gx, gy);
+                        else
+                        {
+                            is_cand = rgb_candidate(a, j0, i);
+                            gx = is_cand ? a.dIdx[k] : (short)0;
+                            gy = is_cand ? a.dIdy[k] : (short)0;
+                        }
+                        if(is_cand)
                         {
                             cand |= 1u << c;
                             c_d1[c] = a.nextDepth[k];
                             c_img[c] = static_cast<float>(a.nextImage[k]);
-                            c_gx[c] = a.dIdx[k];
-                            c_gy[c] = a.dIdy[k];
+                            c_gx[c] = gx;
+                            c_gy[c] = gy;
                         }
                     }
                 }
@@ -1077,6 +1088,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, float * par
         if(leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();
     }
+    if(leader) ctl->base[group] = target;   // every CTA of the group ends with the same target
 }
 
 // ------------------------------------------------------------------ host side
@@ -1098,7 +1110,7 @@ void gn_bind_state(GnDevice & d, char * base, int batch)
     char * p = base;
     d.ctl = (GnCtl *)p;
     p += (sizeof(GnCtl) + 255) / 256 * 256;
-    d.seq_in = (GnSeqIn *)p;   // must directly follow ctl (one staging copy covers both)
+    d.seq_in = (GnSeqIn *)p;
     p += (sizeof(GnSeqIn) * batch + 255) / 256 * 256;
     d.partials = (float *)p;
     p += (size_t)kGnMaxCtas * 2 * kGnPartialStride * 4;
@@ -1107,7 +1119,7 @@ void gn_bind_state(GnDevice & d, char * base, int batch)
     d.trace = (slam_step_record *)p;
     p += (sizeof(slam_step_record) * kGnMaxTrace * batch + 255) / 256 * 256;
     d.trace_count = (int *)p;
-    d.stage_bytes = (sizeof(GnCtl) + 255) / 256 * 256 + sizeof(GnSeqIn) * batch;
+    d.stage_bytes = sizeof(GnSeqIn) * batch;
 }
 
 // Fold finished event pairs into kernel_ms / kernel_launches (synchronises on them).
@@ -1153,8 +1165,8 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         }
         if(d.num_sms > kGnMaxCtas) d.num_sms = kGnMaxCtas;
     }
-    memset(d.h_stage, 0, d.stage_bytes);
-    GnSeqIn * in = reinterpret_cast<GnSeqIn *>(d.h_stage + (sizeof(GnCtl) + 255) / 256 * 256);
+    GnSeqIn * in = reinterpret_cast<GnSeqIn *>(d.h_stage);
+    memset(in, 0, sizeof(GnSeqIn) * L.batch);
     for(int b = 0; b < L.batch; b++)
     {
         const SeqBuffers & s = seqs[b];
@@ -1171,20 +1183,12 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         memcpy(in[b].Rprev, rot + 9 * b, 36);
         memcpy(in[b].tprev, trans + 3 * b, 12);
     }
-    SLAM_CUDA_TRY(cudaMemcpyAsync(d.ctl, d.h_stage, d.stage_bytes, cudaMemcpyHostToDevice, stream));
+    // one sequence: its pointer / pose block travels as a kernel parameter; several: one H2D copy of the array
+    if(L.batch > 1) SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, d.h_stage, sizeof(GnSeqIn) * L.batch, cudaMemcpyHostToDevice, stream));
 
     // group geometry: every sequence gets its own group of G CTAs while they fit
-    int G, groups;
-    if(L.batch >= d.num_sms)
-    {
-        G = 1;
-        groups = d.num_sms;
-    }
-    else
-    {
-        G = d.num_sms / L.batch;
-        groups = L.batch;
-    }
+    int G = gn_group_size(d.num_sms, L.batch);
+    int groups = L.batch >= d.num_sms ? d.num_sms : L.batch;
     GnLaunch Lc = L;
     GnCtl * ctl = d.ctl;
     const GnSeqIn * seq_in = d.seq_in;
@@ -1192,7 +1196,8 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     GnResult * results = d.results;
     slam_step_record * trace = d.trace;
     int * trace_count = d.trace_count;
-    void * args[] = {&Lc, &ctl, &seq_in, &partials, &results, &trace, &trace_count, &G, &groups};
+    GnSeqIn seq0 = in[0];
+    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &partials, &results, &trace, &trace_count, &G, &groups};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(d.profiling)
     {

@@ -9,6 +9,10 @@ constexpr int kGnThreads = 512;
 constexpr int kGnMaxCtas = 256;        // >= SM count of any target part (B200: 148)
 constexpr int kGnPartialStride = 64;   // floats per CTA per buffer: [0..31] phase A, [32..63] phase B
 constexpr int kGnMaxTrace = 64;        // step records kept per sequence
+constexpr int kSlotChunk = 5;          // pixels per thread and level that stay register-resident (640x480 on 148 CTAs: 5)
+
+// CTAs per sequence group for a batch on a device with num_sms SMs (must match gn_enqueue).
+inline int gn_group_size(int num_sms, int batch) { return batch >= num_sms ? 1 : num_sms / batch; }
 
 // Per-sequence inputs of one launch; refreshed by ONE host->device copy per launch (the
 // image pointers change when the reference swaps lastNextImage/nextImage, and the prior
@@ -33,7 +37,8 @@ struct GnSeqIn
 
 struct GnCtl
 {
-    unsigned barrier[kGnMaxCtas];   // one arrival counter per CTA group; zeroed by the per-launch copy
+    unsigned barrier[kGnMaxCtas];   // one arrival counter per CTA group, monotonically increasing across launches
+    unsigned base[kGnMaxCtas];      // counter value at the end of the previous launch (written by the group leader)
 };
 
 struct GnLaunch
@@ -42,6 +47,7 @@ struct GnLaunch
     LevelGeom geom[SLAM_MAX_LEVELS];
     int iterations[SLAM_MAX_LEVELS];
     bool icp, rgb, rgb_only, so3, trace, full_corres;
+    bool derive_gradients;   // no derivative images were made: single-chunk groups derive them from nextImage in registers
     float icp_weight;
     float dist_thresh, angle_thresh;
     float sobel_scale, max_depth_delta;

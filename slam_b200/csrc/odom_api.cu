@@ -49,7 +49,10 @@ struct slam_odom
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second branch of the per-frame preparation (depth pyramid / maps)
     cudaEvent_t compute_done = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    int num_sms = 0;
 
     char * arena = nullptr;
     size_t arena_bytes = 0;
@@ -668,7 +671,12 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
         h->own_stream = true;
     }
     SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
     SLAM_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+    SLAM_CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    SLAM_CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+    SLAM_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, params->device));
+    if(h->num_sms > kGnMaxCtas) h->num_sms = kGnMaxCtas;
 
     ArenaPlan plan;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
@@ -703,6 +711,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     cudaSetDevice(h->p.device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
+    if(h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     for(auto & sl : h->slot)
     {
         if(sl.depth) cudaFree(sl.depth);
@@ -714,6 +723,9 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->h_sums) cudaFreeHost(h->h_sums);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if(h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if(h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if(h->join_ev) cudaEventDestroy(h->join_ev);
     if(h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return SLAM_OK;
@@ -797,11 +809,18 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
         return SLAM_ERR_UNSUPPORTED;
     }
-    if(rgb)
+    // Derivative images are only materialised when something reads them from memory: a test tap / trace, or groups
+    // whose per-thread pixel sets do not fit the register-resident chunk.  Otherwise the persistent kernel derives
+    // the two gradients of its own pixels from nextImage (same arithmetic, bit-identical).
+    const int G = gn_group_size(h->num_sms, h->batch);
+    const int nslots0 = (h->geom[0].rows * h->geom[0].cols + G * kGnThreads - 1) / (G * kGnThreads);
+    const bool derive = rgb && !h->trace_on && nslots0 <= kSlotChunk;
+    if(rgb && !derive)
         for(int b = 0; b < h->batch; b++)
             if(int rc = enqueue_derivatives(h, b)) return rc;
 
     GnLaunch L = {};
+    L.derive_gradients = derive;
     L.levels = h->levels;
     L.batch = h->batch;
     for(int l = 0; l < h->levels; l++) L.geom[l] = h->geom[l];
@@ -1062,6 +1081,43 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
                                   float icp_weight, int pyramid, int fast_odom, int so3)
 {
     // apps/elastic_fusion_file.cpp:366-374: initICPModel -> initRGBModel -> initICP -> initRGB -> getIncrementalTransformation
+    if(!h->trace_on && !h->p.host_loop)
+    {
+        // All five inputs are known up front: the current-frame depth branch (pyramid, vertex / normal maps) runs on a
+        // second stream next to the model / RGB branch, and the "last" and "next" RGB-D pyramids are built together.
+        if(int rc = set_device(h)) return rc;
+        if(h->pending_async)
+            if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+        SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+        SLAM_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->fork_ev, 0));
+        cudaStream_t main_stream = h->stream;
+        const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
+        h->stream = h->aux_stream;   // enqueue_init_icp_depth launches on h->stream
+        int rc = SLAM_OK;
+        for(int b = 0; b < h->batch && rc == SLAM_OK; b++) rc = enqueue_init_icp_depth(h, b, depth + b * n0, 0, depth_cutoff);
+        h->stream = main_stream;
+        if(rc) return rc;
+        SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
+        for(int b = 0; b < h->batch; b++)
+        {
+            SeqBuffers & s = h->seq[b];
+            if(int rc2 = enqueue_model_maps(h, b, (const float *)(mv + b * n0), (const float *)(mn + b * n0), true, poses16 + 16 * b)) return rc2;
+            if(int rc2 = launch_rgbd_level0_dual(s.depth_tmp, s.lastDepth[0], s.nextDepth[0], mrgba + b * n0, s.lastImage[0], rgba + b * n0, s.nextImage[0], (int)n0,
+                                                 h->stream))
+                return rc2;
+            h->launches++;
+            for(int l = 0; l + 1 < h->levels; l++)
+            {
+                if(int rc2 = launch_rgbd_down_dual(s.lastDepth[l], s.lastDepth[l + 1], s.nextDepth[l + 1], s.lastImage[l], s.lastImage[l + 1], s.nextImage[l],
+                                                   s.nextImage[l + 1], h->geom[l].rows, h->geom[l].cols, h->stream))
+                    return rc2;
+                h->launches++;
+            }
+        }
+        h->have_depth_tmp = true;
+        SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        return slam_odom_get_incremental_transformation(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    }
     if(int rc = slam_odom_init_icp_model(h, (const float *)mv, (const float *)mn, model_cutoff, poses16)) return rc;
     if(int rc = slam_odom_init_rgb_model(h, (const uint8_t *)mrgba)) return rc;
     if(int rc = slam_odom_init_icp_depth(h, depth, 0, depth_cutoff)) return rc;

@@ -56,6 +56,10 @@ struct DerivArgs;
 int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,
                        float * nmap, unsigned short * next_depth, cudaStream_t s);
 int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * rgba, unsigned char * image0, int n, cudaStream_t s);
+int launch_rgbd_level0_dual(const float * depth_tmp, float * lastDepth0, float * nextDepth0, const uchar4 * model_rgba, unsigned char * lastImage0,
+                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s);
+int launch_rgbd_down_dual(const float * dsrc, float * ddstLast, float * ddstNext, const unsigned char * isrcLast, unsigned char * idstLast,
+                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s);
 int launch_rgbd_down(const float * dsrc, float * ddst, const unsigned char * isrc, unsigned char * idst, int srows, int scols, cudaStream_t s);
 int launch_resize_transform(const float * vsrc, const float * nsrc, int srows, int scols, float * vdst, float * ndst, int transform, const Mat3 & R,
                             const float3 & t, float * vcam, float * ncam, cudaStream_t s);

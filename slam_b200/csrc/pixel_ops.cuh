@@ -262,6 +262,66 @@ __device__ __forceinline__ bool rgb_associate(const ResidualArgs & a, int x, int
     return false;
 }
 
+// applyKernel, utils.cu:582-606: 3x3 derivative with a running kernelIndex from 8 downwards over the CLIPPED window
+// (border taps misalign, on purpose), float -> short truncation.
+__device__ __forceinline__ void derivative_pixel(const unsigned char * src, int rows, int cols, int x, int y, short & dx, short & dy)
+{
+    const float gx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+    const float gy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+    float dxVal = 0;
+    float dyVal = 0;
+    if(x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1)
+    {
+        // interior: the nine taps are loaded first, then accumulated in the reference's order (kernelIndex 8 -> 0)
+        const unsigned char * p = src + (y - 1) * cols + (x - 1);
+        float v[9];
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) v[r * 3 + c] = (float)p[r * cols + c];
+        const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+        const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+#pragma unroll
+        for(int t = 0; t < 9; t++)
+        {
+            dxVal = __fmaf_rn(v[t], fgx[8 - t], dxVal);
+            dyVal = __fmaf_rn(v[t], fgy[8 - t], dyVal);
+        }
+        dx = (short)dxVal;
+        dy = (short)dyVal;
+        return;
+    }
+    int kernelIndex = 8;
+    for(int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
+        for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
+        {
+            const float s = (float)src[j * cols + i];
+            dxVal = __fmaf_rn(s, gx[kernelIndex], dxVal);
+            dyVal = __fmaf_rn(s, gy[kernelIndex], dyVal);
+            --kernelIndex;
+        }
+    dx = (short)dxVal;
+    dy = (short)dyVal;
+}
+
+
+// rgb_candidate with the derivatives computed on the spot from nextImage instead of read from dIdx/dIdy
+// (bit-identical values; lets the persistent kernel run without the derivative images).
+__device__ __forceinline__ bool rgb_candidate_derive(const ResidualArgs & a, int j0, int i, short & gx, short & gy)
+{
+    gx = gy = 0;
+    if(!(j0 < a.cols - 5 && i < a.rows - 1)) return false;
+    bool valid = true;
+    for(int u = max(i - 2, 0); u < min(i + 2, a.rows); u++)
+        for(int v = max(j0 - 2, 0); v < min(j0 + 2, a.cols); v++) valid = valid && (a.nextImage[u * a.cols + v] > 0);
+    if(!valid) return false;
+    derivative_pixel(a.nextImage, a.rows, a.cols, j0, i, gx, gy);
+    const int valx = gx, valy = gy;
+    const float mTwo = (valx * valx) + (valy * valy);
+    if(!(mTwo >= a.minScale)) return false;
+    return !isnan(a.nextDepth[i * a.cols + j0]);
+}
+
 // ------------------------------------------------------------------------------------
 // RGB step: photometric Jacobian row.   reduce.cu:512-558
 // ------------------------------------------------------------------------------------

@@ -450,6 +450,38 @@ __global__ void __launch_bounds__(256) k_rgbd_down(const float * __restrict__ ds
     if(idst) idst[y * dcols + x] = pyr_down_gauss_u8_pixel(isrc, srows, scols, x, y);
 }
 
+// Frame-level variants used by the one-call-per-frame front end (slam_odom_track_*): the "last" (model) and "next"
+// (current frame) pyramids of populateRGBDData are built side by side; in frame-to-model tracking both depth pyramids
+// derive from the same model vertices (RGBDOdometryef.cpp:239,245), so each depth value is computed once and stored twice.
+__global__ void __launch_bounds__(256) k_rgbd_level0_dual(const float * __restrict__ depth_tmp, float * __restrict__ lastDepth0, float * __restrict__ nextDepth0,
+                                                          const uchar4 * __restrict__ model_rgba, unsigned char * __restrict__ lastImage0,
+                                                          const uchar4 * __restrict__ rgba, unsigned char * __restrict__ nextImage0, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const float d = depth_tmp[i];
+    lastDepth0[i] = d;
+    nextDepth0[i] = d;
+    lastImage0[i] = intensity_pixel(__ldg(model_rgba + i));
+    nextImage0[i] = intensity_pixel(__ldg(rgba + i));
+}
+
+__global__ void __launch_bounds__(256) k_rgbd_down_dual(const float * __restrict__ dsrc, float * __restrict__ ddstLast, float * __restrict__ ddstNext,
+                                                        const unsigned char * __restrict__ isrcLast, unsigned char * __restrict__ idstLast,
+                                                        const unsigned char * __restrict__ isrcNext, unsigned char * __restrict__ idstNext, int srows, int scols)
+{
+    const int drows = srows / 2, dcols = scols / 2;
+    const int nbx = div_up(dcols, 32);
+    const int x = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
+    const int y = (blockIdx.x / nbx) * 8 + (threadIdx.x >> 5);
+    if(x >= dcols || y >= drows) return;
+    const float d = pyr_down_gauss_f_pixel(dsrc, srows, scols, x, y);
+    ddstLast[y * dcols + x] = d;
+    ddstNext[y * dcols + x] = d;
+    idstLast[y * dcols + x] = pyr_down_gauss_u8_pixel(isrcLast, srows, scols, x, y);
+    idstNext[y * dcols + x] = pyr_down_gauss_u8_pixel(isrcNext, srows, scols, x, y);
+}
+
 // ------------------------------------------------------------------ image derivatives
 // applyKernel, utils.cu:582-606: running kernelIndex from 8 downwards over the CLIPPED
 // window (border taps misalign, on purpose), float -> short truncation.  All levels in
@@ -463,46 +495,6 @@ struct DerivArgs
     int first[SLAM_MAX_LEVELS + 1];
     int levels;
 };
-
-__device__ __forceinline__ void derivative_pixel(const unsigned char * src, int rows, int cols, int x, int y, short & dx, short & dy)
-{
-    const float gx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-    const float gy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-    float dxVal = 0;
-    float dyVal = 0;
-    if(x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1)
-    {
-        // interior: the nine taps are loaded first, then accumulated in the reference's order (kernelIndex 8 -> 0)
-        const unsigned char * p = src + (y - 1) * cols + (x - 1);
-        float v[9];
-#pragma unroll
-        for(int r = 0; r < 3; r++)
-#pragma unroll
-            for(int c = 0; c < 3; c++) v[r * 3 + c] = (float)p[r * cols + c];
-        const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-        const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-#pragma unroll
-        for(int t = 0; t < 9; t++)
-        {
-            dxVal = __fmaf_rn(v[t], fgx[8 - t], dxVal);
-            dyVal = __fmaf_rn(v[t], fgy[8 - t], dyVal);
-        }
-        dx = (short)dxVal;
-        dy = (short)dyVal;
-        return;
-    }
-    int kernelIndex = 8;
-    for(int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
-        for(int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++)
-        {
-            const float s = (float)src[j * cols + i];
-            dxVal = __fmaf_rn(s, gx[kernelIndex], dxVal);
-            dyVal = __fmaf_rn(s, gy[kernelIndex], dyVal);
-            --kernelIndex;
-        }
-    dx = (short)dxVal;
-    dy = (short)dyVal;
-}
 
 __global__ void __launch_bounds__(256) k_derivatives(const DerivArgs a)
 {
@@ -681,6 +673,22 @@ int launch_resize_transform(const float * vsrc, const float * nsrc, int srows, i
 int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * rgba, unsigned char * image0, int n, cudaStream_t s)
 {
     k_rgbd_level0<<<div_up(n, 256), 256, 0, s>>>(depth_tmp, depth0, rgba, image0, n);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_rgbd_level0_dual(const float * depth_tmp, float * lastDepth0, float * nextDepth0, const uchar4 * model_rgba, unsigned char * lastImage0,
+                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s)
+{
+    k_rgbd_level0_dual<<<div_up(n, 256), 256, 0, s>>>(depth_tmp, lastDepth0, nextDepth0, model_rgba, lastImage0, rgba, nextImage0, n);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_rgbd_down_dual(const float * dsrc, float * ddstLast, float * ddstNext, const unsigned char * isrcLast, unsigned char * idstLast,
+                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s)
+{
+    k_rgbd_down_dual<<<tiles_32x8(srows / 2, scols / 2), 256, 0, s>>>(dsrc, ddstLast, ddstNext, isrcLast, idstLast, isrcNext, idstNext, srows, scols);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }

@@ -362,6 +362,46 @@ def test_closed_loop_sequence_ate_matches_reference(setup):
     ref.close()
 
 
+def test_frame_call_equals_separate_calls(setup):
+    """slam_odom_track_device / _track_host (one call per frame: forked depth branch, fused last/next pyramids, gradients
+    derived inside the persistent kernel) must give exactly what the five separate reference-shaped calls give."""
+    from slam_b200 import Tap
+    i = setup["intr"]
+    t = setup["torch"]
+    fr0, d0 = device_frame(setup, 349)
+    results = []
+    taps = []
+    for which in ("separate", "track_device", "track_host"):
+        o = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+        o.initFirstRGB(d0["rgba"])
+        out = None
+        for k in (350, 351):   # two frames: the second exercises the image swap after the SO3 call
+            fr, d = device_frame(setup, k)
+            pose = d["model_pose"]
+            if which == "separate":
+                out = run_frame(o, d, so3=True)
+            elif which == "track_device":
+                frame = o.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], pose, 3.0, 20.0)
+                out = o.track_device(frame, pose[:3, 3].copy(), pose[:3, :3].copy())
+            else:
+                host = {k2: (t.from_numpy(v.view(np.int16) if v.dtype == np.uint16 else v).pin_memory()) for k2, v in fr.items() if k2 not in ("model_pose", "gt_pose")}
+                frame = o.make_frame(host["depth"], host["rgba"], host["mv"], host["mn"], host["mrgba"], pose, 3.0, 20.0)
+                out = o.track_host(frame, pose[:3, 3].copy(), pose[:3, :3].copy())
+        results.append(out)
+        taps.append({(tap, l): o.tap(tap, l) for tap in (Tap.VMAP_CURR, Tap.NMAP_PREV, Tap.LAST_DEPTH, Tap.NEXT_DEPTH, Tap.LAST_IMAGE, Tap.NEXT_IMAGE) for l in range(3)})
+        o.close()
+    for r in results[1:]:
+        assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]), "frame-level call differs from the separate calls"
+    for tp in taps[1:]:
+        for key, a in tp.items():
+            b = taps[0][key]
+            assert np.array_equal(np.isnan(a), np.isnan(b)) if a.dtype == np.float32 else True
+            ok = ~np.isnan(b) if a.dtype == np.float32 else np.ones(a.shape, bool)
+            if key[0] in (Tap.VMAP_CURR, Tap.NMAP_PREV):
+                ok = np.broadcast_to(~np.isnan(b[0]), b.shape)   # validity lives in the x plane
+            assert np.array_equal(a[ok], b[ok]), f"tap {key} differs"
+
+
 def test_batch_equals_single_sequences(setup):
     i = setup["intr"]
     t = setup["torch"]
