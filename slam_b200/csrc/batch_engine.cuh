@@ -1,0 +1,30 @@
+// Batched streaming engine: declarations (see batch_engine.cu).
+#pragma once
+#include "gn_kernel.cuh"
+
+namespace slam {
+
+constexpr int kBatchEngineMin = 4;   // batches of at least this many sequences use the streaming engine
+
+struct BatchDevice
+{
+    char * states = nullptr;        // [batch][state_stride]: persistent prefix of GnShared per sequence
+    size_t state_stride = 0;
+    float * sums = nullptr;         // [batch][64]: folded sums of the last phase A (0..31) / phase B (32..63)
+    GnSeqIn * seq_in = nullptr;     // [batch] (shared with the persistent kernel's array)
+    GnResult * results = nullptr;   // [batch]
+    unsigned char * cand0 = nullptr;    // candidate masks, vmask: per sequence, per level
+    size_t aux_stride = 0;              // bytes between consecutive sequences' aux blocks
+    size_t cand_off[SLAM_MAX_LEVELS], vmask_off[SLAM_MAX_LEVELS];
+    char * ws_float = nullptr;      // [batch][kWorkspaceBytes]
+    char * ws_int = nullptr;        // [batch][kWorkspaceBytes]
+    int batch = 0;
+    long long launches = 0;
+};
+
+size_t batch_state_bytes(int batch, const LevelGeom * geom, int levels);
+void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom * geom, int levels, GnSeqIn * seq_in, GnResult * results);
+int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
+                  cudaStream_t stream);
+
+}   // namespace slam

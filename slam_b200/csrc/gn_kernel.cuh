@@ -80,6 +80,7 @@ int gn_fold_profile(GnDevice & d);
 
 size_t gn_state_bytes(int batch);
 void gn_bind_state(GnDevice & d, char * base, int batch);
+int gn_stage_inputs(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnSeqIn ** out);
 int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnResult * h_results,
                cudaStream_t stream);
 int gn_read_trace(GnDevice & d, int seq, slam_step_record * out, int max_records, int * n_records, cudaStream_t stream);

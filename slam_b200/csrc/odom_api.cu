@@ -15,6 +15,7 @@
 #include <limits>
 #include "odom_internal.hpp"
 #include "gn_kernel.cuh"
+#include "batch_engine.cuh"
 
 namespace slam {
 
@@ -60,6 +61,7 @@ struct slam_odom
 
     // device-resident loop
     GnDevice gn;                      // device pointers of the persistent kernel's state
+    BatchDevice be;                   // batched streaming engine (batch >= kBatchEngineMin)
     GnResult * h_results = nullptr;   // pinned [batch]
     float * h_sums = nullptr;         // pinned scratch for the host-stepped loop [96]
 
@@ -681,6 +683,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     ArenaPlan plan;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
     const size_t gn_off = plan.take(gn_state_bytes(h->batch));
+    const size_t be_off = h->batch >= kBatchEngineMin ? plan.take(batch_state_bytes(h->batch, h->geom, h->levels)) : 0;
     h->arena_bytes = plan.off;
     SLAM_CUDA_TRY(cudaMalloc((void **)&h->arena, h->arena_bytes));
     SLAM_CUDA_TRY(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -688,6 +691,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     ArenaPlan place;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, place, &h->seq[b]);
     gn_bind_state(h->gn, h->arena + gn_off, h->batch);
+    if(h->batch >= kBatchEngineMin) batch_bind_state(h->be, h->arena + be_off, h->batch, h->geom, h->levels, h->gn.seq_in, h->gn.results);
 
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_results, sizeof(GnResult) * h->batch));
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_sums, 128 * 4));
@@ -812,9 +816,10 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     // Derivative images are only materialised when something reads them from memory: a test tap / trace, or groups
     // whose per-thread pixel sets do not fit the register-resident chunk.  Otherwise the persistent kernel derives
     // the two gradients of its own pixels from nextImage (same arithmetic, bit-identical).
+    const bool streaming = h->batch >= kBatchEngineMin && h->trace_level < 2;   // many sequences: lock-step streaming launches
     const int G = gn_group_size(h->num_sms, h->batch);
     const int nslots0 = (h->geom[0].rows * h->geom[0].cols + G * kGnThreads - 1) / (G * kGnThreads);
-    const bool derive = rgb && !h->trace_on && nslots0 <= kSlotChunk;
+    const bool derive = rgb && !h->trace_on && !streaming && nslots0 <= kSlotChunk;
     if(rgb && !derive)
         for(int b = 0; b < h->batch; b++)
             if(int rc = enqueue_derivatives(h, b)) return rc;
@@ -837,9 +842,23 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     for(int l = 0; l < h->levels; l++) L.min_scale[l] = (float)(pow((double)h->minGrad[l], 2.0) / pow((double)h->sobelScale, 2.0));
     L.trace = h->trace_on;
     L.full_corres = h->trace_level >= 2;
-    int rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream);
+    int rc;
+    if(streaming)
+    {
+        GnSeqIn * in = nullptr;
+        rc = gn_stage_inputs(h->gn, L, h->seq.data(), trans, rot, &in);
+        if(rc) return rc;
+        const long long before = h->be.launches;
+        rc = batch_enqueue(h->be, L, in, h->h_results, h->gn.trace, h->gn.trace_count, h->stream);
+        h->launches += h->be.launches - before;
+        h->gn.so3_swapped = L.so3;
+    }
+    else
+    {
+        rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream);
+        h->launches++;
+    }
     if(rc) return rc;
-    h->launches++;
     h->pending_async = true;
     h->last_icp = icp;
     h->last_rgb = rgb;
