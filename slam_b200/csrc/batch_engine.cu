@@ -24,6 +24,23 @@ __device__ __forceinline__ const GnShared & bstate(const char * states, size_t s
     return *reinterpret_cast<const GnShared *>(states + (size_t)seq * stride);
 }
 
+template <int PX>
+__device__ __forceinline__ void vec_load(const float * p, float (&v)[PX])
+{
+    if(PX == 4)
+    {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = q.x; v[1] = q.y; v[2 % PX] = q.z; v[3 % PX] = q.w;
+    }
+    else if(PX == 2)
+    {
+        const float2 q = __ldg(reinterpret_cast<const float2 *>(p));
+        v[0] = q.x; v[1 % PX] = q.y;
+    }
+    else
+        v[0] = __ldg(p);
+}
+
 // copy the persistent prefix of GnShared between global and shared memory (one warp)
 __device__ __forceinline__ void state_load(GnShared & sh, const char * g)
 {
@@ -40,6 +57,112 @@ __device__ __forceinline__ void state_store(const GnShared & sh, char * g)
     unsigned * dst = reinterpret_cast<unsigned *>(g);
     const unsigned * src = reinterpret_cast<const unsigned *>(&sh);
     for(int i = threadIdx.x; i < n; i += 32) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ per-sequence reduction + bookkeeping tails
+constexpr int kRowWords = 40;   // one partial row per block: 32 floats + 2 ints (+ pad)
+
+// Block sum of 32 floats (+ optionally 2 ints) per thread, published as this block's partial row of its sequence;
+// the block that draws the sequence's last ticket folds all rows in block order into sh.total[dst..dst+31] (ints as
+// bit patterns in columns 29, 30 when with_ints) and returns true (block-uniform).  Deterministic for a given grid.
+__device__ __forceinline__ bool seq_reduce(float (&acc)[32], int c0, int c1, const bool with_ints, GnShared & sh, char * ws_seq, const int dst)
+{
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float s = warp_reduce_scatter32(acc);
+    sh.red[wid * 32 + lane] = s;
+    int * redi = reinterpret_cast<int *>(sh.red + 32 * 32);
+    if(with_ints)
+    {
+        c0 = warp_sum(c0);
+        c1 = warp_sum(c1);
+        if(lane == 0)
+        {
+            redi[wid * 2] = c0;
+            redi[wid * 2 + 1] = c1;
+        }
+    }
+    __syncthreads();
+    float * rows = reinterpret_cast<float *>(ws_seq);
+    if(threadIdx.x < 32)
+    {
+        float total = 0.f;
+        for(int w = 0; w < nw; w++) total += sh.red[w * 32 + threadIdx.x];
+        rows[blockIdx.x * kRowWords + threadIdx.x] = total;
+    }
+    else if(threadIdx.x < 34 && with_ints)
+    {
+        int t = 0;
+        for(int w = 0; w < nw; w++) t += redi[w * 2 + (threadIdx.x - 32)];
+        reinterpret_cast<int *>(rows)[blockIdx.x * kRowWords + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned * ticket = workspace_ticket(ws_seq);
+    if(threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if(!s_last) return false;
+    __threadfence();
+    const int nb = gridDim.x;
+    if(threadIdx.x < 32)
+    {
+        float total = 0.f;
+        int r = 0;
+        for(; r + 8 <= nb; r += 8)
+        {
+            float v[8];
+#pragma unroll
+            for(int q = 0; q < 8; q++) v[q] = __ldcg(rows + (r + q) * kRowWords + threadIdx.x);
+#pragma unroll
+            for(int q = 0; q < 8; q++) total += v[q];
+        }
+        for(; r < nb; r++) total += __ldcg(rows + r * kRowWords + threadIdx.x);
+        if(!(with_ints && threadIdx.x >= 29 && threadIdx.x <= 30)) sh.total[dst + threadIdx.x] = total;
+    }
+    else if(threadIdx.x < 34 && with_ints)
+    {
+        int t = 0;
+        for(int r = 0; r < nb; r++) t += __ldcg(reinterpret_cast<const int *>(rows) + r * kRowWords + threadIdx.x);
+        sh.total[dst + 29 + (threadIdx.x - 32)] = __int_as_float(t);
+    }
+    if(threadIdx.x == 0) *ticket = 0u;   // ready for the next launch
+    __syncthreads();
+    return true;
+}
+
+// One warp (warp 0 of the block that finished a sequence's reduction, sums in sh.total): RGBDOdometryef.cpp:457-575.
+__device__ __forceinline__ void seq_update(GnShared & sh, const GnLaunch & L, char * state, int seq, int lvl, int j, slam_step_record * trace)
+{
+    state_load(sh, state);
+    slam_step_record * rec = (trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
+    if(rec && threadIdx.x == 0)
+    {
+        memset(rec, 0, sizeof(*rec));
+        rec->kind = 1;
+        rec->level = lvl;
+        rec->iteration = j;
+        for(int k = 0; k < 9; k++)
+        {
+            rec->Rcurr_in[k] = sh.Rcurr[k];
+            rec->krkinv_in[k] = sh.krk[k];
+            rec->so3_in[k] = sh.Rprev_inv[k];
+        }
+        for(int k = 0; k < 3; k++)
+        {
+            rec->tcurr_in[k] = sh.tcurr[k];
+            rec->kt_in[k] = sh.kt[k];
+        }
+    }
+    __syncwarp();
+    if(L.rgb)
+    {
+        if(threadIdx.x == 0) gn_sigma(sh, L.rgb_only, rec);   // never a stop here: phase B returned early in that case
+        __syncwarp();
+    }
+    warp_update(sh, L.icp, L.rgb, L.icp_weight, threadIdx.x == 0 ? rec : nullptr, clock64());
+    if(rec && threadIdx.x == 0) sh.ntr++;
+    __syncwarp();
+    state_store(sh, state);
 }
 
 // ------------------------------------------------------------------ one warp per sequence
@@ -63,28 +186,6 @@ __global__ void __launch_bounds__(32) kb_begin(const GnLaunch L, const GnSeqIn *
     state_store(sh, states + (size_t)seq * stride);
 }
 
-__global__ void __launch_bounds__(32) kb_so3_update(const GnLaunch L, char * states, size_t stride, const float * sums, int it, slam_step_record * trace)
-{
-    __shared__ GnShared sh;
-    const int seq = blockIdx.x;
-    state_load(sh, states + (size_t)seq * stride);
-    if(sh.so3_done) return;
-    if(threadIdx.x < 11) sh.total[threadIdx.x] = sums[seq * 64 + threadIdx.x];
-    __syncwarp();
-    if(threadIdx.x == 0)
-    {
-        slam_step_record * rec = (trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
-        if(rec) memset(rec, 0, sizeof(*rec));
-        so3_update(sh, it, rec);
-        if(rec) sh.ntr++;
-        if(sh.stop || it == 9)
-            sh.so3_done = 1;
-        else
-            so3_prepare(sh);
-    }
-    state_store(sh, states + (size_t)seq * stride);
-}
-
 __global__ void __launch_bounds__(32) kb_level_begin(const GnLaunch L, char * states, size_t stride, int lvl, int first)
 {
     __shared__ GnShared sh;
@@ -104,51 +205,6 @@ __global__ void __launch_bounds__(32) kb_level_begin(const GnLaunch L, char * st
     state_store(sh, states + (size_t)seq * stride);
 }
 
-__global__ void __launch_bounds__(32) kb_update(const GnLaunch L, char * states, size_t stride, const float * sums, int lvl, int j, slam_step_record * trace)
-{
-    __shared__ GnShared sh;
-    const int seq = blockIdx.x;
-    state_load(sh, states + (size_t)seq * stride);
-    if(sh.stop_level == lvl) return;
-    for(int i = threadIdx.x; i < 64; i += 32) sh.total[i] = sums[seq * 64 + i];
-    slam_step_record * rec = (trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
-    if(rec && threadIdx.x == 0)
-    {
-        memset(rec, 0, sizeof(*rec));
-        rec->kind = 1;
-        rec->level = lvl;
-        rec->iteration = j;
-        for(int k = 0; k < 9; k++)
-        {
-            rec->Rcurr_in[k] = sh.Rcurr[k];
-            rec->krkinv_in[k] = sh.krk[k];
-            rec->so3_in[k] = sh.Rprev_inv[k];
-        }
-        for(int k = 0; k < 3; k++)
-        {
-            rec->tcurr_in[k] = sh.tcurr[k];
-            rec->kt_in[k] = sh.kt[k];
-        }
-    }
-    __syncwarp();
-    if(L.rgb)
-    {
-        if(threadIdx.x == 0)
-        {
-            gn_sigma(sh, L.rgb_only, rec);
-            if(sh.stop) sh.stop_level = lvl;   // rgbOnly && rgbError > lastRGBError, RGBDOdometryef.cpp:460-463
-        }
-        __syncwarp();
-    }
-    if(sh.stop_level != lvl)
-    {
-        warp_update(sh, L.icp, L.rgb, L.icp_weight, threadIdx.x == 0 ? rec : nullptr, clock64());
-        if(rec && threadIdx.x == 0) sh.ntr++;
-        __syncwarp();
-    }
-    state_store(sh, states + (size_t)seq * stride);
-}
-
 __global__ void __launch_bounds__(32) kb_end(const GnLaunch L, char * states, size_t stride, GnResult * results, int * trace_count)
 {
     __shared__ GnShared sh;
@@ -162,8 +218,11 @@ __global__ void __launch_bounds__(32) kb_end(const GnLaunch L, char * states, si
 }
 
 // ------------------------------------------------------------------ streaming map-reduce launches
-__global__ void __launch_bounds__(kBThreads) kb_so3_map(const GnLaunch L, const GnSeqIn * seqs, const char * states, size_t stride, char * ws, float * sums)
+// SO3 pre-alignment iteration (reduce.cu:953-1054 + RGBDOdometryef.cpp:300-372): map over level 2, the sequence's last
+// block updates the rotation estimate.
+__global__ void __launch_bounds__(kBThreads) kb_so3(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, int it, slam_step_record * trace)
 {
+    __shared__ GnShared sh;
     const int seq = blockIdx.y;
     const GnShared & st = bstate(states, stride, seq);
     if(st.so3_done) return;
@@ -177,9 +236,9 @@ __global__ void __launch_bounds__(kBThreads) kb_so3_map(const GnLaunch L, const 
     a.krlr = mat3_from(st.so3KR);
     a.cols = g.cols;
     a.rows = g.rows;
-    float acc[11];
+    float acc[32];
 #pragma unroll
-    for(int k = 0; k < 11; k++) acc[k] = 0.f;
+    for(int k = 0; k < 32; k++) acc[k] = 0.f;
     const int N = g.rows * g.cols;
     for(int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x)
     {
@@ -187,9 +246,29 @@ __global__ void __launch_bounds__(kBThreads) kb_so3_map(const GnLaunch L, const 
         const int x = k - y * g.cols;
         float row[4];
         const bool found = so3_pixel(a, x, y, row);
-        accumulate_so3(acc, row, found);
+        float a11[11];
+#pragma unroll
+        for(int q = 0; q < 11; q++) a11[q] = acc[q];
+        accumulate_so3(a11, row, found);
+#pragma unroll
+        for(int q = 0; q < 11; q++) acc[q] = a11[q];
     }
-    grid_finish<float, 11>(acc, ws + (size_t)seq * kWorkspaceBytes, sums + seq * 64);
+    if(!seq_reduce(acc, 0, 0, false, sh, ws + (size_t)seq * kWorkspaceBytes, 0)) return;
+    if(threadIdx.x >= 32) return;
+    char * state = states + (size_t)seq * stride;
+    state_load(sh, state);
+    if(threadIdx.x == 0)
+    {
+        slam_step_record * rec = (trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
+        if(rec) memset(rec, 0, sizeof(*rec));
+        so3_update(sh, it, rec);
+        if(rec) sh.ntr++;
+        if(sh.stop || it == 9)
+            sh.so3_done = 1;
+        else
+            so3_prepare(sh);
+    }
+    state_store(sh, state);
 }
 
 // Pose-independent half of the RGB association, once per level and frame (reduce.cu:780-807).
@@ -213,22 +292,48 @@ __global__ void __launch_bounds__(kBThreads) kb_candidates(const GnLaunch L, con
     }
 }
 
-__global__ void __launch_bounds__(kBThreads) kb_phase_a(const GnLaunch L, const GnSeqIn * seqs, const char * states, size_t stride, char * ws_float, char * ws_int,
-                                                        float * sums, unsigned char * cand0, size_t aux_stride, size_t cand_off, size_t vmask_off, int lvl)
+// Compact correspondence of the streaming engine (the 16 bytes of a Corres slot): everything phase B needs, so that
+// phase B is a dense stream with no gathers.
+struct __align__(16) BCorres
 {
+    int zxy;       // zx | zy << 16: the pixel of the last image
+    float d0;      // lastDepth there (z of the reference's cloud point)
+    float diff;    // next - last intensity
+    int gxy;       // dIdx | dIdy << 16 at the pixel itself
+};
+
+constexpr int kCountsOffset = 1024 * kRowWords * 4;   // per-warp correspondence counts inside a sequence's workspace (after the partial rows)
+
+// Pixel ownership of the streaming launches: warp w of a sequence's grid owns the contiguous pixels [w * chunk, (w + 1) * chunk),
+// walked 32 * PX at a time.  Its valid correspondences are compacted, in (trip, c, lane) order, into the same range of the
+// sequence's correspondence buffer; phase B (same grid) streams them back.
+__device__ __forceinline__ int warp_chunk(int plane, int px)
+{
+    const int warps = gridDim.x * (kBThreads / 32);
+    const int per = (plane + warps - 1) / warps;
+    return (per + 32 * px - 1) / (32 * px) * (32 * px);
+}
+
+// Phase A of a Gauss-Newton iteration: ICP products (reduce.cu:257-416) and RGB association (reduce.cu:739-867) of
+// PX consecutive pixels per thread and trip.  All coalesced loads of a trip are issued first, then all gathers.
+template <int PX>
+__global__ void __launch_bounds__(kBThreads, PX == 4 ? 1 : 2)
+kb_phase_a(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, float * sums, unsigned char * cand0, size_t aux_stride, size_t cand_off,
+           int lvl)
+{
+    __shared__ GnShared sh;
     const int seq = blockIdx.y;
     const GnShared & st = bstate(states, stride, seq);
     if(st.stop_level == lvl) return;
     const GnSeqIn & in = seqs[seq];
     const LevelGeom g = L.geom[lvl];
-    const int plane = g.rows * g.cols;
-    const bool vec = (plane & 3) == 0;
-    const int nitems = (plane + 3) >> 2;
+    const int plane = g.rows * g.cols;   // a multiple of PX (checked by the host)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    float acc[29];
+    float acc[32];
 #pragma unroll
-    for(int k = 0; k < 29; k++) acc[k] = 0.f;
-    int cnt[2] = {0, 0};
+    for(int k = 0; k < 32; k++) acc[k] = 0.f;
+    int cnt0 = 0, cnt1 = 0;
 
     IcpArgs ia;
     ia.Rcurr = mat3_from(st.Rcurr);
@@ -251,114 +356,155 @@ __global__ void __launch_bounds__(kBThreads) kb_phase_a(const GnLaunch L, const 
     ra.krkinv = mat3_from(st.krk);
     ra.cols = g.cols; ra.rows = g.rows;
     const unsigned char * cand = cand0 + (size_t)seq * aux_stride + cand_off;
-    unsigned char * vmask = cand0 + (size_t)seq * aux_stride + vmask_off;
-    Corres * cimg = in.corres[lvl];
+    BCorres * cimg = reinterpret_cast<BCorres *>(in.corres[lvl]);
 
-    for(int item = blockIdx.x * blockDim.x + threadIdx.x; item < nitems; item += gridDim.x * blockDim.x)
+    const int chunk = warp_chunk(plane, PX);
+    const int gw = blockIdx.x * (kBThreads / 32) + wid;
+    const int w0 = min(gw * chunk, plane);
+    const int w1 = min(w0 + chunk, plane);
+    int wcount = 0;   // correspondences this warp has written (warp-uniform)
+
+    for(int base = w0; base < w1; base += 32 * PX)
     {
-        const int p = item << 2;
-        if(L.icp)
+        const int p = base + lane * PX;
+        const bool inside = p < w1;
+        // ---- stage 1: coalesced loads
+        float vx[PX], vy[PX], vz[PX], nx[PX], ny[PX], nz[PX], d1[PX];
+        unsigned cm = 0, im = 0;
+        if(inside)
         {
-            float3 vg[4], nc[4], vp[4], np[4];
-            int o[4];
-            bool ok[4];
-            if(vec)
+            if(L.icp)
             {
-                const float4 a0 = __ldg(reinterpret_cast<const float4 *>(ia.vcurr + p));
-                const float4 a1 = __ldg(reinterpret_cast<const float4 *>(ia.vcurr + plane + p));
-                const float4 a2 = __ldg(reinterpret_cast<const float4 *>(ia.vcurr + 2 * plane + p));
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(ia.ncurr + p));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(ia.ncurr + plane + p));
-                const float4 b2 = __ldg(reinterpret_cast<const float4 *>(ia.ncurr + 2 * plane + p));
-                vg[0] = make_float3(a0.x, a1.x, a2.x); vg[1] = make_float3(a0.y, a1.y, a2.y); vg[2] = make_float3(a0.z, a1.z, a2.z); vg[3] = make_float3(a0.w, a1.w, a2.w);
-                nc[0] = make_float3(b0.x, b1.x, b2.x); nc[1] = make_float3(b0.y, b1.y, b2.y); nc[2] = make_float3(b0.z, b1.z, b2.z); nc[3] = make_float3(b0.w, b1.w, b2.w);
-#pragma unroll
-                for(int c = 0; c < 4; c++) ok[c] = true;
+                vec_load<PX>(ia.vcurr + p, vx);
+                vec_load<PX>(ia.vcurr + plane + p, vy);
+                vec_load<PX>(ia.vcurr + 2 * plane + p, vz);
+                vec_load<PX>(ia.ncurr + p, nx);
+                vec_load<PX>(ia.ncurr + plane + p, ny);
+                vec_load<PX>(ia.ncurr + 2 * plane + p, nz);
             }
-            else
+            if(L.rgb)
             {
-#pragma unroll
-                for(int c = 0; c < 4; c++)
-                {
-                    ok[c] = p + c < plane;
-                    const int kk = ok[c] ? p + c : 0;
-                    vg[c] = make_float3(__ldg(ia.vcurr + kk), __ldg(ia.vcurr + plane + kk), __ldg(ia.vcurr + 2 * plane + kk));
-                    nc[c] = make_float3(__ldg(ia.ncurr + kk), __ldg(ia.ncurr + plane + kk), __ldg(ia.ncurr + 2 * plane + kk));
-                }
+                if(PX == 4) { cm = __ldg(reinterpret_cast<const unsigned *>(cand + p)); im = __ldg(reinterpret_cast<const unsigned *>(ra.nextImage + p)); }
+                else if(PX == 2) { cm = __ldg(reinterpret_cast<const unsigned short *>(cand + p)); im = __ldg(reinterpret_cast<const unsigned short *>(ra.nextImage + p)); }
+                else { cm = __ldg(cand + p); im = __ldg(ra.nextImage + p); }
+                vec_load<PX>(ra.nextDepth + p, d1);
             }
+        }
+        // ---- stage 2: projections, then every gather of the trip
+        float3 vg[PX], vp[PX], np[PX];
+        int o[PX];
+        bool ok[PX];
+        float td1[PX], d0[PX];
+        int zxy[PX];
+        unsigned char li[PX];
+        bool rok[PX];
 #pragma unroll
-            for(int c = 0; c < 4; c++)
+        for(int c = 0; c < PX; c++)
+        {
+            ok[c] = false;
+            o[c] = 0;
+            if(L.icp && inside) ok[c] = icp_project(ia, make_float3(vx[c], vy[c], vz[c]), vg[c], o[c]);
+            if(!ok[c]) o[c] = 0;
+            rok[c] = false;
+            zxy[c] = 0;
+            if(L.rgb && ((cm >> (8 * c)) & 0xff))
             {
-                float3 g3;
-                const bool inb = icp_project(ia, vg[c], g3, o[c]);
-                vg[c] = g3;
-                ok[c] = ok[c] && inb;
-                if(!ok[c]) o[c] = 0;
+                const int k = p + c;
+                const int y = k / g.cols;
+                const int x = k - y * g.cols;
+                int u0, v0;
+                rok[c] = rgb_project(ra, x, y, d1[c], u0, v0, td1[c]);
+                if(rok[c]) zxy[c] = u0 | (v0 << 16);
             }
+        }
 #pragma unroll
-            for(int c = 0; c < 4; c++)
+        for(int c = 0; c < PX; c++)
+        {
+            if(L.icp)
             {
                 vp[c] = make_float3(__ldg(ia.vprev + o[c]), __ldg(ia.vprev + plane + o[c]), __ldg(ia.vprev + 2 * plane + o[c]));
                 np[c] = make_float3(__ldg(ia.nprev + o[c]), __ldg(ia.nprev + plane + o[c]), __ldg(ia.nprev + 2 * plane + o[c]));
             }
+            if(L.rgb)
+            {
+                const int r = (zxy[c] >> 16) * g.cols + (zxy[c] & 0xffff);
+                d0[c] = __ldg(ra.lastDepth + r);
+                li[c] = __ldg(ra.lastImage + r);
+            }
+        }
+        // ---- stage 3: products
+        if(L.icp)
+        {
 #pragma unroll
-            for(int c = 0; c < 4; c++)
+            for(int c = 0; c < PX; c++)
             {
                 float row[7];
-                const bool found = icp_finish(ia, vg[c], nc[c], vp[c], np[c], row) && ok[c];
-                if(found) accumulate_se3(acc, row, true);
+                const bool found = ok[c] && icp_finish(ia, vg[c], make_float3(nx[c], ny[c], nz[c]), vp[c], np[c], row);
+                if(found)
+                {
+                    float a29[29];
+#pragma unroll
+                    for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                    accumulate_se3(a29, row, true);
+#pragma unroll
+                    for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                }
             }
         }
         if(L.rgb)
         {
-            // candidate flags of the four pixels, then the warp + gathers of the candidates
-            unsigned cm = 0;
-            if(vec)
-                cm = __ldg(reinterpret_cast<const unsigned *>(cand + p));
-            else
-                for(int c = 0; c < 4; c++)
-                    if(p + c < plane) cm |= (unsigned)cand[p + c] << (8 * c);
-            unsigned vm = 0;
-            if(cm)
-            {
 #pragma unroll
-                for(int c = 0; c < 4; c++)
-                    if((cm >> (8 * c)) & 0xff)
-                    {
-                        const int k = p + c;
-                        const int i = k / g.cols;
-                        Corres cc;
-                        cc.zx = cc.zy = cc.ox = cc.oy = 0;
-                        cc.diff = 0.f;
-                        cc.valid = 0;
-                        if(rgb_associate(ra, k - i * g.cols, i, cc))
-                        {
-                            cnt[0] += 1;
-                            cnt[1] += (int)(cc.diff * cc.diff);
-                            vm |= 1u << (8 * c);
-                            reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&cc);
-                        }
-                    }
+            for(int c = 0; c < PX; c++)
+            {
+                const bool valid = rok[c] && rgb_accept(ra, td1[c], d0[c], li[c]);
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                if(valid)
+                {
+                    BCorres cc;
+                    cc.zxy = zxy[c];
+                    cc.d0 = d0[c];
+                    cc.diff = __fsub_rn(static_cast<float>((im >> (8 * c)) & 0xff), static_cast<float>(li[c]));
+                    const int k = p + c;
+                    cc.gxy = (int)(unsigned short)__ldg(ra.dIdx + k) | ((int)__ldg(ra.dIdy + k) << 16);
+                    cnt0 += 1;
+                    cnt1 += (int)(cc.diff * cc.diff);
+                    reinterpret_cast<int4 *>(cimg)[w0 + wcount + __popc(m & ((1u << lane) - 1u))] = *reinterpret_cast<const int4 *>(&cc);
+                }
+                wcount += __popc(m);
             }
-            if(vec)
-                *reinterpret_cast<unsigned *>(vmask + p) = vm;
-            else
-                for(int c = 0; c < 4; c++)
-                    if(p + c < plane) vmask[p + c] = (vm >> (8 * c)) & 0xff;
         }
     }
-    grid_finish<float, 29>(acc, ws_float + (size_t)seq * kWorkspaceBytes, sums + seq * 64);
-    if(L.rgb) grid_finish<int, 2>(cnt, ws_int + (size_t)seq * kWorkspaceBytes, reinterpret_cast<int *>(sums + seq * 64 + 29));
+    char * ws_seq = ws + (size_t)seq * kWorkspaceBytes;
+    if(L.rgb && lane == 0) reinterpret_cast<int *>(ws_seq + kCountsOffset)[gw] = wcount;
+    if(!seq_reduce(acc, cnt0, cnt1, L.rgb, sh, ws_seq, 0)) return;
+    if(threadIdx.x >= 32) return;
+    // phase B (or, without RGB, kb_update) picks up the ICP sums, count and sigma here: the fp64 solve is kept out of
+    // this kernel because its register footprint would cap the occupancy of the streaming part
+    sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kBThreads) kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, const char * states, size_t stride, char * ws_float, float * sums,
-                                                        const unsigned char * cand0, size_t aux_stride, size_t vmask_off, int lvl)
+// ICP-only runs: the update as its own one-warp-per-sequence launch.
+__global__ void __launch_bounds__(32) kb_update(const GnLaunch L, char * states, size_t stride, const float * sums, int lvl, int j, slam_step_record * trace)
 {
+    __shared__ GnShared sh;
+    const int seq = blockIdx.x;
+    if(bstate(states, stride, seq).stop_level == lvl) return;
+    sh.total[threadIdx.x] = sums[seq * 64 + threadIdx.x];
+    __syncwarp();
+    seq_update(sh, L, states + (size_t)seq * stride, seq, lvl, j, trace);
+}
+
+// Phase B: RGB Jacobian products (reduce.cu:494-624) from the compacted correspondences of phase A (same grid), then the update.
+template <int PX>
+__global__ void __launch_bounds__(kBThreads, 2)
+kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, const float * sums, int lvl, int j, slam_step_record * trace)
+{
+    __shared__ GnShared sh;
     const int seq = blockIdx.y;
     const GnShared & st = bstate(states, stride, seq);
     if(st.stop_level == lvl) return;
     // sigmaVal and the rgbOnly early exit are re-derived from the folded count / sigma by every block, identically
-    // (RGBDOdometryef.cpp:457-471); kb_update does the bookkeeping once per sequence afterwards.
+    // (RGBDOdometryef.cpp:457-471)
     const int rgbSize = __float_as_int(__ldcg(sums + seq * 64 + 29));
     const int sigma = __float_as_int(__ldcg(sums + seq * 64 + 30));
     const int sel = (rgbSize != 0 && sigma == 0) ? 1 : rgbSize;
@@ -366,50 +512,66 @@ __global__ void __launch_bounds__(kBThreads) kb_phase_b(const GnLaunch L, const 
     if(L.rgb_only)
     {
         const float rgbError = (float)(sqrt((double)sigma) / (double)(rgbSize == 0 ? 1 : rgbSize));
-        if(rgbError > st.res.lastRGBError) return;
+        if(rgbError > st.res.lastRGBError)
+        {
+            // RGBDOdometryef.cpp:460-463: the level's remaining iterations are skipped (blocks that read the flag
+            // early return one line above, the others here: same outcome)
+            if(blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<GnShared *>(states + (size_t)seq * stride)->stop_level = lvl;
+            return;
+        }
         sigmaVal = -1;
     }
     const GnSeqIn & in = seqs[seq];
     const LevelGeom g = L.geom[lvl];
     const int plane = g.rows * g.cols;
-    const bool vec = (plane & 3) == 0;
-    const int nitems = (plane + 3) >> 2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     RgbStepArgs a;
     a.sigma = sigmaVal;
     a.fx = g.fx; a.fy = g.fy;
     a.sobelScale = L.sobel_scale;
     a.cols = g.cols; a.rows = g.rows;
-    a.dIdx = in.dIdx[lvl]; a.dIdy = in.dIdy[lvl];
-    a.lastDepth = in.lastDepth[lvl];
+    a.dIdx = nullptr; a.dIdy = nullptr;
+    a.lastDepth = nullptr;
     a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
     a.cloud = nullptr;
-    const unsigned char * vmask = cand0 + (size_t)seq * aux_stride + vmask_off;
-    const Corres * cimg = in.corres[lvl];
-    float acc[29];
+    char * ws_seq = ws + (size_t)seq * kWorkspaceBytes;
+    const int chunk = warp_chunk(plane, PX);
+    const int gw = blockIdx.x * (kBThreads / 32) + wid;
+    const int w0 = min(gw * chunk, plane);
+    const int n = __ldcg(reinterpret_cast<const int *>(ws_seq + kCountsOffset) + gw);
+    const int4 * list = reinterpret_cast<const int4 *>(in.corres[lvl]) + w0;
+    float acc[32];
 #pragma unroll
-    for(int k = 0; k < 29; k++) acc[k] = 0.f;
-    for(int item = blockIdx.x * blockDim.x + threadIdx.x; item < nitems; item += gridDim.x * blockDim.x)
+    for(int k = 0; k < 32; k++) acc[k] = 0.f;
+    for(int i0 = 0; i0 < n; i0 += 128)
     {
-        const int p = item << 2;
-        unsigned vm = 0;
-        if(vec)
-            vm = __ldcg(reinterpret_cast<const unsigned *>(vmask + p));
-        else
-            for(int c = 0; c < 4; c++)
-                if(p + c < plane) vm |= (unsigned)__ldcg(vmask + p + c) << (8 * c);
-        if(!vm) continue;
+        int4 raw[4];
 #pragma unroll
-        for(int c = 0; c < 4; c++)
-            if((vm >> (8 * c)) & 0xff)
+        for(int q = 0; q < 4; q++)
+        {
+            const int i = i0 + q * 32 + lane;
+            raw[q] = i < n ? __ldcg(list + i) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for(int q = 0; q < 4; q++)
+            if(i0 + q * 32 + lane < n)
             {
-                const int4 raw = __ldcg(reinterpret_cast<const int4 *>(cimg) + p + c);
-                const Corres cc = *reinterpret_cast<const Corres *>(&raw);
+                const BCorres cc = *reinterpret_cast<const BCorres *>(&raw[q]);
                 float row[7];
-                rgb_row(a, cc, row);
-                accumulate_se3(acc, row, true);
+                rgb_row_regs(a, cc.zxy & 0xffff, cc.zxy >> 16, cc.d0, (short)(cc.gxy & 0xffff), (short)(cc.gxy >> 16), cc.diff, row);
+                float a29[29];
+#pragma unroll
+                for(int k = 0; k < 29; k++) a29[k] = acc[k];
+                accumulate_se3(a29, row, true);
+#pragma unroll
+                for(int k = 0; k < 29; k++) acc[k] = a29[k];
             }
     }
-    grid_finish<float, 29>(acc, ws_float + (size_t)seq * kWorkspaceBytes, sums + seq * 64 + 32);
+    if(!seq_reduce(acc, 0, 0, false, sh, ws_seq, 32)) return;
+    if(threadIdx.x >= 32) return;
+    sh.total[threadIdx.x] = __ldcg(sums + seq * 64 + threadIdx.x);
+    __syncwarp();
+    seq_update(sh, L, states + (size_t)seq * stride, seq, lvl, j, trace);
 }
 
 // ------------------------------------------------------------------ host side
@@ -419,7 +581,7 @@ size_t batch_state_bytes(int batch, const LevelGeom * geom, int levels)
 {
     size_t aux = 0;
     for(int l = 0; l < levels; l++) aux += 2 * up256((size_t)geom[l].rows * geom[l].cols);
-    return up256(up256(offsetof(GnShared, red)) * batch) + up256((size_t)batch * 64 * 4) + aux * batch + 2 * kWorkspaceBytes * (size_t)batch + 4096;
+    return up256(up256(offsetof(GnShared, red)) * batch) + up256((size_t)batch * 64 * 4) + aux * batch + kWorkspaceBytes * (size_t)batch + 4096;
 }
 
 void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom * geom, int levels, GnSeqIn * seq_in, GnResult * results)
@@ -445,17 +607,30 @@ void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom *
     d.aux_stride = off;
     d.cand0 = (unsigned char *)p;
     p += off * batch;
-    d.ws_float = p;
-    p += kWorkspaceBytes * (size_t)batch;
-    d.ws_int = p;
+    d.ws = p;
 }
 
-static int blocks_for(int nitems)
+static int blocks_per_seq(int nitems, int batch, int num_sms)
 {
-    int g = (nitems + kBThreads - 1) / kBThreads;
-    if(g < 1) g = 1;
-    if(g > kMaxReduceBlocks) g = kMaxReduceBlocks;
-    return g;
+    // ~16 blocks per SM over the whole batch (tail under 1/16 of a wave), at least one trip of 256 items per block
+    int want = (num_sms * 16 + batch - 1) / batch;
+    const int cap = (nitems + kBThreads - 1) / kBThreads;
+    if(want > cap) want = cap;
+    if(want < 1) want = 1;
+    if(want > 1024) want = 1024;
+    return want;
+}
+
+static int px_variant()
+{
+    static int v = -1;
+    if(v < 0)
+    {
+        const char * e = getenv("SLAM_BATCH_PX");
+        v = e ? atoi(e) : 4;
+        if(v != 1 && v != 2 && v != 4) v = 4;
+    }
+    return v;
 }
 
 int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
@@ -468,12 +643,11 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
     d.launches++;
     if(L.so3)
     {
-        const int nb = blocks_for(L.geom[2].rows * L.geom[2].cols);
+        const int nb = blocks_per_seq(L.geom[2].rows * L.geom[2].cols, B, d.num_sms);
         for(int it = 0; it < 10; it++)
         {
-            kb_so3_map<<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws_float, d.sums);
-            kb_so3_update<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.sums, it, trace);
-            d.launches += 2;
+            kb_so3<<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, it, trace);
+            d.launches++;
         }
     }
     bool first = true;
@@ -486,22 +660,30 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         if(L.iterations[lvl] <= 0) continue;
         if(L.rgb)
         {
-            kb_candidates<<<dim3(blocks_for(plane), B), kBThreads, 0, s>>>(L, d.seq_in, d.cand0, d.aux_stride, d.cand_off[lvl], lvl);
+            kb_candidates<<<dim3(blocks_per_seq(plane, B, d.num_sms), B), kBThreads, 0, s>>>(L, d.seq_in, d.cand0, d.aux_stride, d.cand_off[lvl], lvl);
             d.launches++;
         }
-        const int nb = blocks_for((plane + 3) / 4);
+        int px = px_variant();
+        while(plane % px) px >>= 1;
+        const int nb = blocks_per_seq(plane / px, B, d.num_sms);
         for(int j = 0; j < L.iterations[lvl]; j++)
         {
-            kb_phase_a<<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws_float, d.ws_int, d.sums, d.cand0, d.aux_stride, d.cand_off[lvl],
-                                                         d.vmask_off[lvl], lvl);
+#define SLAM_PHASE_A(PXV) \
+    kb_phase_a<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride, d.cand_off[lvl], lvl)
+#define SLAM_PHASE_B(PXV) \
+    kb_phase_b<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, lvl, j, trace)
+            if(px == 4) SLAM_PHASE_A(4); else if(px == 2) SLAM_PHASE_A(2); else SLAM_PHASE_A(1);
             d.launches++;
             if(L.rgb)
             {
-                kb_phase_b<<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws_float, d.sums, d.cand0, d.aux_stride, d.vmask_off[lvl], lvl);
+                if(px == 4) SLAM_PHASE_B(4); else if(px == 2) SLAM_PHASE_B(2); else SLAM_PHASE_B(1);
                 d.launches++;
             }
-            kb_update<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.sums, lvl, j, trace);
-            d.launches++;
+            else
+            {
+                kb_update<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.sums, lvl, j, trace);
+                d.launches++;
+            }
         }
     }
     kb_end<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.results, trace_count);

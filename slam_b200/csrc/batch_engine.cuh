@@ -16,8 +16,8 @@ struct BatchDevice
     unsigned char * cand0 = nullptr;    // candidate masks, vmask: per sequence, per level
     size_t aux_stride = 0;              // bytes between consecutive sequences' aux blocks
     size_t cand_off[SLAM_MAX_LEVELS], vmask_off[SLAM_MAX_LEVELS];
-    char * ws_float = nullptr;      // [batch][kWorkspaceBytes]
-    char * ws_int = nullptr;        // [batch][kWorkspaceBytes]
+    char * ws = nullptr;            // [batch][kWorkspaceBytes]: partial rows + ticket of each sequence's running reduction
+    int num_sms = 148;
     int batch = 0;
     long long launches = 0;
 };

@@ -58,6 +58,9 @@ struct slam_odom
     char * arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<SeqBuffers> seq;
+    size_t seq_stride = 0;            // bytes between the buffers of consecutive sequences in the arena
+    float * d_poses12 = nullptr;      // [batch][12] model poses (R row-major | t) of the batched preparation launches
+    float * h_poses12 = nullptr;      // pinned staging of the same
 
     // device-resident loop
     GnDevice gn;                      // device pointers of the persistent kernel's state
@@ -682,6 +685,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
 
     ArenaPlan plan;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
+    const size_t pose_off = plan.take(sizeof(float) * 12 * h->batch);
     const size_t gn_off = plan.take(gn_state_bytes(h->batch));
     const size_t be_off = h->batch >= kBatchEngineMin ? plan.take(batch_state_bytes(h->batch, h->geom, h->levels)) : 0;
     h->arena_bytes = plan.off;
@@ -690,8 +694,15 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     h->seq.resize(h->batch);
     ArenaPlan place;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, place, &h->seq[b]);
+    h->seq_stride = h->batch > 1 ? (size_t)((char *)h->seq[1].depth[0] - (char *)h->seq[0].depth[0]) : 0;
+    h->d_poses12 = (float *)(h->arena + pose_off);
+    SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_poses12, sizeof(float) * 12 * h->batch));
     gn_bind_state(h->gn, h->arena + gn_off, h->batch);
-    if(h->batch >= kBatchEngineMin) batch_bind_state(h->be, h->arena + be_off, h->batch, h->geom, h->levels, h->gn.seq_in, h->gn.results);
+    if(h->batch >= kBatchEngineMin)
+    {
+        batch_bind_state(h->be, h->arena + be_off, h->batch, h->geom, h->levels, h->gn.seq_in, h->gn.results);
+        h->be.num_sms = h->num_sms;
+    }
 
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_results, sizeof(GnResult) * h->batch));
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_sums, 128 * 4));
@@ -725,6 +736,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->arena) cudaFree(h->arena);
     if(h->h_results) cudaFreeHost(h->h_results);
     if(h->h_sums) cudaFreeHost(h->h_sums);
+    if(h->h_poses12) cudaFreeHost(h->h_poses12);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if(h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -821,8 +833,17 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     const int nslots0 = (h->geom[0].rows * h->geom[0].cols + G * kGnThreads - 1) / (G * kGnThreads);
     const bool derive = rgb && !h->trace_on && !streaming && nslots0 <= kSlotChunk;
     if(rgb && !derive)
-        for(int b = 0; b < h->batch; b++)
-            if(int rc = enqueue_derivatives(h, b)) return rc;
+    {
+        int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
+        for(int l = 0; l < h->levels; l++)
+        {
+            rows[l] = h->geom[l].rows;
+            cols[l] = h->geom[l].cols;
+        }
+        SeqBuffers & s0 = h->seq[0];
+        if(int rc = launch_derivatives_simple(h->levels, s0.nextImage, s0.dIdx, s0.dIdy, rows, cols, h->stream, h->batch, h->seq_stride)) return rc;
+        h->launches++;
+    }
 
     GnLaunch L = {};
     L.derive_gradients = derive;
@@ -1109,27 +1130,61 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
             if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
         SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
         SLAM_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->fork_ev, 0));
-        cudaStream_t main_stream = h->stream;
         const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
-        h->stream = h->aux_stream;   // enqueue_init_icp_depth launches on h->stream
+        // every launch covers all sequences of the batch (gridDim.y), see prep_kernels.cu: seq_shift
+        const int B = h->batch;
+        const size_t S = h->seq_stride;
+        SeqBuffers & s = h->seq[0];
         int rc = SLAM_OK;
-        for(int b = 0; b < h->batch && rc == SLAM_OK; b++) rc = enqueue_init_icp_depth(h, b, depth + b * n0, 0, depth_cutoff);
-        h->stream = main_stream;
+        for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
+        {
+            const LevelGeom & g = h->geom[l];
+            rc = launch_depth_level(l == 0 ? depth : s.depth[l], g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, depth_cutoff, s.vcurr[l], s.ncurr[l],
+                                    l + 1 < h->levels ? s.depth[l + 1] : nullptr, h->aux_stream, B, l == 0 ? n0 * 2 : S, S);
+            h->launches++;
+        }
         if(rc) return rc;
         SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
-        for(int b = 0; b < h->batch; b++)
+        for(int b = 0; b < B; b++)
         {
-            SeqBuffers & s = h->seq[b];
-            if(int rc2 = enqueue_model_maps(h, b, (const float *)(mv + b * n0), (const float *)(mn + b * n0), true, poses16 + 16 * b)) return rc2;
-            if(int rc2 = launch_rgbd_level0_dual(s.depth_tmp, s.lastDepth[0], s.nextDepth[0], mrgba + b * n0, s.lastImage[0], rgba + b * n0, s.nextImage[0], (int)n0,
-                                                 h->stream))
-                return rc2;
+            const float * q = poses16 + 16 * b;
+            float * o = h->h_poses12 + 12 * b;
+            for(int r = 0; r < 3; r++)
+            {
+                for(int c = 0; c < 3; c++) o[3 * r + c] = q[4 * r + c];
+                o[9 + r] = q[4 * r + 3];
+            }
+        }
+        SLAM_CUDA_TRY(cudaMemcpyAsync(h->d_poses12, h->h_poses12, sizeof(float) * 12 * B, cudaMemcpyHostToDevice, h->stream));
+        {
+            const Mat3 R0 = {};
+            rc = launch_model_maps_simple(mv, mn, h->geom[0].rows, h->geom[0].cols, h->levels, s.vprev, s.nprev, 1, R0, make_float3(0, 0, 0), s.depth_tmp,
+                                          h->maxDepthRGB, h->levels > 3 ? s.vcam : nullptr, h->levels > 3 ? s.ncam : nullptr, h->stream, B, n0 * 16, S,
+                                          h->d_poses12);
+            if(rc) return rc;
+            h->launches++;
+            if(h->levels > 3)
+                for(int b = 0; b < B; b++)
+                {
+                    const float * q = h->h_poses12 + 12 * b;
+                    Mat3 R;
+                    R.r0 = make_float3(q[0], q[1], q[2]);
+                    R.r1 = make_float3(q[3], q[4], q[5]);
+                    R.r2 = make_float3(q[6], q[7], q[8]);
+                    SeqBuffers & sb = h->seq[b];
+                    rc = launch_resize_transform(sb.vcam, sb.ncam, h->geom[2].rows, h->geom[2].cols, sb.vprev[3], sb.nprev[3], 1, R, make_float3(q[9], q[10], q[11]),
+                                                 nullptr, nullptr, h->stream);
+                    if(rc) return rc;
+                    h->launches++;
+                }
+            rc = launch_rgbd_level0_dual(s.depth_tmp, s.lastDepth[0], s.nextDepth[0], mrgba, s.lastImage[0], rgba, s.nextImage[0], (int)n0, h->stream, B, n0 * 4, S);
+            if(rc) return rc;
             h->launches++;
             for(int l = 0; l + 1 < h->levels; l++)
             {
-                if(int rc2 = launch_rgbd_down_dual(s.lastDepth[l], s.lastDepth[l + 1], s.nextDepth[l + 1], s.lastImage[l], s.lastImage[l + 1], s.nextImage[l],
-                                                   s.nextImage[l + 1], h->geom[l].rows, h->geom[l].cols, h->stream))
-                    return rc2;
+                rc = launch_rgbd_down_dual(s.lastDepth[l], s.lastDepth[l + 1], s.nextDepth[l + 1], s.lastImage[l], s.lastImage[l + 1], s.nextImage[l],
+                                           s.nextImage[l + 1], h->geom[l].rows, h->geom[l].cols, h->stream, B, S);
+                if(rc) return rc;
                 h->launches++;
             }
         }

@@ -54,12 +54,13 @@ struct GnResult
 struct ModelMapsArgs;
 struct DerivArgs;
 int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,
-                       float * nmap, unsigned short * next_depth, cudaStream_t s);
+                       float * nmap, unsigned short * next_depth, cudaStream_t s, int nseq = 1, size_t in_stride = 0, size_t out_stride = 0);
 int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * rgba, unsigned char * image0, int n, cudaStream_t s);
 int launch_rgbd_level0_dual(const float * depth_tmp, float * lastDepth0, float * nextDepth0, const uchar4 * model_rgba, unsigned char * lastImage0,
-                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s);
+                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s, int nseq = 1, size_t in_stride = 0, size_t arena_stride = 0);
 int launch_rgbd_down_dual(const float * dsrc, float * ddstLast, float * ddstNext, const unsigned char * isrcLast, unsigned char * idstLast,
-                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s);
+                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s, int nseq = 1,
+                          size_t arena_stride = 0);
 int launch_rgbd_down(const float * dsrc, float * ddst, const unsigned char * isrc, unsigned char * idst, int srows, int scols, cudaStream_t s);
 int launch_resize_transform(const float * vsrc, const float * nsrc, int srows, int scols, float * vdst, float * ndst, int transform, const Mat3 & R,
                             const float3 & t, float * vcam, float * ncam, cudaStream_t s);
@@ -71,8 +72,8 @@ int launch_so3_step(const So3Args & a, void * workspace, float * out11, cudaStre
 // helpers exported by prep_kernels.cu that need the full argument structs
 int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
                              int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
-                             cudaStream_t s);
+                             cudaStream_t s, int nseq = 1, size_t in_stride = 0, size_t out_stride = 0, const float * poses12 = nullptr);
 int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
-                              cudaStream_t s);
+                              cudaStream_t s, int nseq = 1, size_t arena_stride = 0);
 
 }   // namespace slam

@@ -194,14 +194,26 @@ __device__ __forceinline__ unsigned char intensity_pixel(uchar4 src)
 // utils.cu:526-537 verticesToDepthKernel
 __device__ __forceinline__ float depth_from_vertex_z(float z, float cutOff) { return z > cutOff || z <= 0 ? SLAM_QNAN : z; }
 
+// Batched launches: gridDim.y = number of sequences; every per-sequence buffer sits at a constant byte stride from
+// sequence 0's (odom_api.cu: layout_sequence), and so do the caller's dense input stacks.
+template <class T>
+__device__ __forceinline__ T * seq_shift(T * p, size_t stride_bytes)
+{
+    return p ? (T *)((const char *)p + (size_t)blockIdx.y * stride_bytes) : p;
+}
+
 // ------------------------------------------------------------------ fused depth level
 // One launch per pyramid level l of the CURRENT frame:
 //   blocks [0, nb_map)  : depth_l -> vmap_l, nmap_l  (createVMap + createNMap, utils.cu:109-188)
 //   blocks [nb_map, ..) : depth_l -> depth_{l+1}     (pyrDown, utils.cu:57-94), if dst != nullptr
 __global__ void __launch_bounds__(256) k_depth_level(const unsigned short * __restrict__ depth, int rows, int cols, float fx_inv, float fy_inv,
                                                      float cx, float cy, float depthCutoff, float * __restrict__ vmap, float * __restrict__ nmap,
-                                                     unsigned short * __restrict__ next_depth, int nb_map_x, int nb_map)
+                                                     unsigned short * __restrict__ next_depth, int nb_map_x, int nb_map, size_t in_stride, size_t out_stride)
 {
+    depth = seq_shift(depth, in_stride);
+    vmap = seq_shift(vmap, out_stride);
+    nmap = seq_shift(nmap, out_stride);
+    next_depth = seq_shift(next_depth, out_stride);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if((int)blockIdx.x < nb_map)
     {
@@ -271,6 +283,9 @@ struct ModelMapsArgs
     float depth_cut;
     float * vcam2;         // optional camera-frame copies of level 2 (source of a 4th level), or nullptr
     float * ncam2;
+    // batched launch (gridDim.y sequences): byte strides of the inputs / of the arena buffers, per-sequence [R | t] (12 floats each)
+    size_t in_stride, out_stride;
+    const float * poses12;
 };
 
 __device__ __forceinline__ void store_map_pixel(float * vdst, float * ndst, int plane, int o, float3 v, float3 n, bool transform, const Mat3 & R,
@@ -333,8 +348,30 @@ __device__ __forceinline__ float3 resize4(const float3 & a00, const float3 & a01
     return n;
 }
 
-__global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a)
+__global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a0)
 {
+    ModelMapsArgs a = a0;
+    if(gridDim.y > 1 || a.poses12)
+    {
+        a.vsrc = seq_shift(a.vsrc, a.in_stride);
+        a.nsrc = seq_shift(a.nsrc, a.in_stride);
+        for(int l = 0; l < 3; l++)
+        {
+            a.vdst[l] = seq_shift(a.vdst[l], a.out_stride);
+            a.ndst[l] = seq_shift(a.ndst[l], a.out_stride);
+        }
+        a.depth_tmp = seq_shift(a.depth_tmp, a.out_stride);
+        a.vcam2 = seq_shift(a.vcam2, a.out_stride);
+        a.ncam2 = seq_shift(a.ncam2, a.out_stride);
+        if(a.poses12)
+        {
+            const float * q = a.poses12 + 12 * blockIdx.y;
+            a.R.r0 = make_float3(__ldg(q + 0), __ldg(q + 1), __ldg(q + 2));
+            a.R.r1 = make_float3(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+            a.R.r2 = make_float3(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+            a.t = make_float3(__ldg(q + 9), __ldg(q + 10), __ldg(q + 11));
+        }
+    }
     // thread -> 4x4 block; consecutive threads walk along x
     const int bcols = div_up(a.cols, 4), brows = div_up(a.rows, 4);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,8 +492,16 @@ __global__ void __launch_bounds__(256) k_rgbd_down(const float * __restrict__ ds
 // derive from the same model vertices (RGBDOdometryef.cpp:239,245), so each depth value is computed once and stored twice.
 __global__ void __launch_bounds__(256) k_rgbd_level0_dual(const float * __restrict__ depth_tmp, float * __restrict__ lastDepth0, float * __restrict__ nextDepth0,
                                                           const uchar4 * __restrict__ model_rgba, unsigned char * __restrict__ lastImage0,
-                                                          const uchar4 * __restrict__ rgba, unsigned char * __restrict__ nextImage0, int n)
+                                                          const uchar4 * __restrict__ rgba, unsigned char * __restrict__ nextImage0, int n, size_t in_stride,
+                                                          size_t arena_stride)
 {
+    depth_tmp = seq_shift(depth_tmp, arena_stride);
+    lastDepth0 = seq_shift(lastDepth0, arena_stride);
+    nextDepth0 = seq_shift(nextDepth0, arena_stride);
+    lastImage0 = seq_shift(lastImage0, arena_stride);
+    nextImage0 = seq_shift(nextImage0, arena_stride);
+    model_rgba = seq_shift(model_rgba, in_stride);
+    rgba = seq_shift(rgba, in_stride);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     const float d = depth_tmp[i];
@@ -468,8 +513,16 @@ __global__ void __launch_bounds__(256) k_rgbd_level0_dual(const float * __restri
 
 __global__ void __launch_bounds__(256) k_rgbd_down_dual(const float * __restrict__ dsrc, float * __restrict__ ddstLast, float * __restrict__ ddstNext,
                                                         const unsigned char * __restrict__ isrcLast, unsigned char * __restrict__ idstLast,
-                                                        const unsigned char * __restrict__ isrcNext, unsigned char * __restrict__ idstNext, int srows, int scols)
+                                                        const unsigned char * __restrict__ isrcNext, unsigned char * __restrict__ idstNext, int srows, int scols,
+                                                        size_t arena_stride)
 {
+    dsrc = seq_shift(dsrc, arena_stride);
+    ddstLast = seq_shift(ddstLast, arena_stride);
+    ddstNext = seq_shift(ddstNext, arena_stride);
+    isrcLast = seq_shift(isrcLast, arena_stride);
+    idstLast = seq_shift(idstLast, arena_stride);
+    isrcNext = seq_shift(isrcNext, arena_stride);
+    idstNext = seq_shift(idstNext, arena_stride);
     const int drows = srows / 2, dcols = scols / 2;
     const int nbx = div_up(dcols, 32);
     const int x = (blockIdx.x % nbx) * 32 + (threadIdx.x & 31);
@@ -494,6 +547,7 @@ struct DerivArgs
     int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
     int first[SLAM_MAX_LEVELS + 1];
     int levels;
+    size_t arena_stride;   // batched launch: gridDim.y sequences
 };
 
 __global__ void __launch_bounds__(256) k_derivatives(const DerivArgs a)
@@ -507,9 +561,9 @@ __global__ void __launch_bounds__(256) k_derivatives(const DerivArgs a)
     const int y = (b / nbx) * 8 + (threadIdx.x >> 5);
     if(x >= cols || y >= rows) return;
     short dx, dy;
-    derivative_pixel(a.src[l], rows, cols, x, y, dx, dy);
-    a.dx[l][y * cols + x] = dx;
-    a.dy[l][y * cols + x] = dy;
+    derivative_pixel(seq_shift(a.src[l], a.arena_stride), rows, cols, x, y, dx, dy);
+    seq_shift(a.dx[l], a.arena_stride)[y * cols + x] = dx;
+    seq_shift(a.dy[l], a.arena_stride)[y * cols + x] = dy;
 }
 
 // ------------------------------------------------------------------ un-fused operator kernels
@@ -644,20 +698,21 @@ __global__ void __launch_bounds__(256) k_project_points(const float * depth, int
 static inline int tiles_32x8(int rows, int cols) { return div_up(cols, 32) * div_up(rows, 8); }
 
 int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,
-                       float * nmap, unsigned short * next_depth, cudaStream_t s)
+                       float * nmap, unsigned short * next_depth, cudaStream_t s, int nseq, size_t in_stride, size_t out_stride)
 {
     const int nb_map_x = div_up(cols, 32);
     const int nb_map = tiles_32x8(rows, cols);
     const int nb_down = next_depth ? tiles_32x8(rows / 2, cols / 2) : 0;
-    k_depth_level<<<nb_map + nb_down, 256, 0, s>>>(depth, rows, cols, 1.f / fx, 1.f / fy, cx, cy, depthCutoff, vmap, nmap, next_depth, nb_map_x, nb_map);
+    k_depth_level<<<dim3(nb_map + nb_down, nseq), 256, 0, s>>>(depth, rows, cols, 1.f / fx, 1.f / fy, cx, cy, depthCutoff, vmap, nmap, next_depth, nb_map_x, nb_map,
+                                                               in_stride, out_stride);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
 
-int launch_model_maps(const ModelMapsArgs & a, cudaStream_t s)
+int launch_model_maps(const ModelMapsArgs & a, cudaStream_t s, int nseq = 1)
 {
     const int nblk = div_up(a.cols, 4) * div_up(a.rows, 4);
-    k_model_maps<<<div_up(nblk, 128), 128, 0, s>>>(a);
+    k_model_maps<<<dim3(div_up(nblk, 128), nseq), 128, 0, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
@@ -678,17 +733,19 @@ int launch_rgbd_level0(const float * depth_tmp, float * depth0, const uchar4 * r
 }
 
 int launch_rgbd_level0_dual(const float * depth_tmp, float * lastDepth0, float * nextDepth0, const uchar4 * model_rgba, unsigned char * lastImage0,
-                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s)
+                            const uchar4 * rgba, unsigned char * nextImage0, int n, cudaStream_t s, int nseq, size_t in_stride, size_t arena_stride)
 {
-    k_rgbd_level0_dual<<<div_up(n, 256), 256, 0, s>>>(depth_tmp, lastDepth0, nextDepth0, model_rgba, lastImage0, rgba, nextImage0, n);
+    k_rgbd_level0_dual<<<dim3(div_up(n, 256), nseq), 256, 0, s>>>(depth_tmp, lastDepth0, nextDepth0, model_rgba, lastImage0, rgba, nextImage0, n, in_stride,
+                                                                  arena_stride);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
 
 int launch_rgbd_down_dual(const float * dsrc, float * ddstLast, float * ddstNext, const unsigned char * isrcLast, unsigned char * idstLast,
-                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s)
+                          const unsigned char * isrcNext, unsigned char * idstNext, int srows, int scols, cudaStream_t s, int nseq, size_t arena_stride)
 {
-    k_rgbd_down_dual<<<tiles_32x8(srows / 2, scols / 2), 256, 0, s>>>(dsrc, ddstLast, ddstNext, isrcLast, idstLast, isrcNext, idstNext, srows, scols);
+    k_rgbd_down_dual<<<dim3(tiles_32x8(srows / 2, scols / 2), nseq), 256, 0, s>>>(dsrc, ddstLast, ddstNext, isrcLast, idstLast, isrcNext, idstNext, srows, scols,
+                                                                                  arena_stride);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
@@ -700,7 +757,7 @@ int launch_rgbd_down(const float * dsrc, float * ddst, const unsigned char * isr
     return SLAM_OK;
 }
 
-int launch_derivatives(DerivArgs & a, cudaStream_t s)
+int launch_derivatives(DerivArgs & a, cudaStream_t s, int nseq = 1)
 {
     int total = 0;
     for(int l = 0; l < a.levels; l++)
@@ -709,14 +766,14 @@ int launch_derivatives(DerivArgs & a, cudaStream_t s)
         total += tiles_32x8(a.rows[l], a.cols[l]);
     }
     a.first[a.levels] = total;
-    k_derivatives<<<total, 256, 0, s>>>(a);
+    k_derivatives<<<dim3(total, nseq), 256, 0, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
 
 int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
                              int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
-                             cudaStream_t s)
+                             cudaStream_t s, int nseq, size_t in_stride, size_t out_stride, const float * poses12)
 {
     ModelMapsArgs a = {};
     a.vsrc = vsrc;
@@ -736,13 +793,17 @@ int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows,
     a.depth_cut = depth_cut;
     a.vcam2 = vcam2;
     a.ncam2 = ncam2;
-    return launch_model_maps(a, s);
+    a.in_stride = in_stride;
+    a.out_stride = out_stride;
+    a.poses12 = poses12;
+    return launch_model_maps(a, s, nseq);
 }
 
 int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
-                              cudaStream_t s)
+                              cudaStream_t s, int nseq, size_t arena_stride)
 {
     DerivArgs a = {};
+    a.arena_stride = arena_stride;
     a.levels = levels;
     for(int l = 0; l < levels; l++)
     {
@@ -752,7 +813,7 @@ int launch_derivatives_simple(int levels, const unsigned char * const * src, sho
         a.rows[l] = rows[l];
         a.cols[l] = cols[l];
     }
-    return launch_derivatives(a, s);
+    return launch_derivatives(a, s, nseq);
 }
 
 }   // namespace slam
