@@ -483,6 +483,244 @@ kb_phase_a(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
     sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
 }
 
+// ---- staged variant: the coalesced operands of a trip reach shared memory through cp.async, kStages - 1 trips ahead of
+// their use, so the only exposed latency of a trip is the gathers'.  One pipeline per warp (a trip = kTripPx contiguous
+// pixels of the warp's chunk, consumed as two half trips of 2 pixels per lane); no block-level synchronisation.
+constexpr int kTripPx = 128;
+constexpr int kStages = 3;
+struct WarpStage
+{
+    float f[7][kTripPx];            // vcurr x,y,z  ncurr x,y,z  nextDepth
+    unsigned char cand[kTripPx];
+    unsigned char img[kTripPx];
+};
+constexpr int kStagedSmem = (kBThreads / 32) * kStages * (int)sizeof(WarpStage);
+
+__device__ __forceinline__ void cp_async16(void * smem, const void * gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void * smem, const void * gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kBThreads, 2)
+kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, float * sums, unsigned char * cand0, size_t aux_stride,
+                  size_t cand_off, int lvl)
+{
+    __shared__ GnShared sh;
+    extern __shared__ __align__(16) char dyn_smem[];
+    const int seq = blockIdx.y;
+    const GnShared & st = bstate(states, stride, seq);
+    if(st.stop_level == lvl) return;
+    const GnSeqIn & in = seqs[seq];
+    const LevelGeom g = L.geom[lvl];
+    const int plane = g.rows * g.cols;   // a multiple of 4 (checked by the host)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpStage * stages = reinterpret_cast<WarpStage *>(dyn_smem) + wid * kStages;
+
+    float acc[32];
+#pragma unroll
+    for(int k = 0; k < 32; k++) acc[k] = 0.f;
+    int cnt0 = 0, cnt1 = 0;
+
+    IcpArgs ia;
+    ia.Rcurr = mat3_from(st.Rcurr);
+    ia.tcurr = make_float3(st.tcurr[0], st.tcurr[1], st.tcurr[2]);
+    ia.Rprev_inv = mat3_from(st.Rprev_inv);
+    ia.tprev = make_float3(st.tprev[0], st.tprev[1], st.tprev[2]);
+    ia.fx = g.fx; ia.fy = g.fy; ia.cx = g.cx; ia.cy = g.cy;
+    ia.distThres = L.dist_thresh;
+    ia.angleThres = L.angle_thresh;
+    ia.cols = g.cols; ia.rows = g.rows;
+    ia.vcurr = in.vcurr[lvl]; ia.ncurr = in.ncurr[lvl]; ia.vprev = in.vprev[lvl]; ia.nprev = in.nprev[lvl];
+
+    ResidualArgs ra;
+    ra.minScale = L.min_scale[lvl];
+    ra.dIdx = in.dIdx[lvl]; ra.dIdy = in.dIdy[lvl];
+    ra.lastDepth = in.lastDepth[lvl]; ra.nextDepth = in.nextDepth[lvl];
+    ra.lastImage = in.lastImage[lvl]; ra.nextImage = in.nextImage[lvl];
+    ra.maxDepthDelta = L.max_depth_delta;
+    ra.kt = make_float3(st.kt[0], st.kt[1], st.kt[2]);
+    ra.krkinv = mat3_from(st.krk);
+    ra.cols = g.cols; ra.rows = g.rows;
+    const unsigned char * cand = cand0 + (size_t)seq * aux_stride + cand_off;
+    BCorres * cimg = reinterpret_cast<BCorres *>(in.corres[lvl]);
+
+    const int chunk = warp_chunk(plane, 4);
+    const int gw = blockIdx.x * (kBThreads / 32) + wid;
+    const int w0 = min(gw * chunk, plane);
+    const int w1 = min(w0 + chunk, plane);
+    const int ntrips = (w1 - w0 + kTripPx - 1) / kTripPx;
+    int wcount = 0;   // correspondences this warp has written (warp-uniform)
+
+    auto issue = [&](int t) {
+        if(t < ntrips)
+        {
+            const int p = w0 + t * kTripPx + lane * 4;
+            if(p < w1)
+            {
+                WarpStage & S = stages[t % kStages];
+                if(L.icp)
+                {
+#pragma unroll
+                    for(int q = 0; q < 3; q++)
+                    {
+                        cp_async16(&S.f[q][lane * 4], ia.vcurr + q * plane + p);
+                        cp_async16(&S.f[3 + q][lane * 4], ia.ncurr + q * plane + p);
+                    }
+                }
+                if(L.rgb)
+                {
+                    cp_async16(&S.f[6][lane * 4], ra.nextDepth + p);
+                    cp_async4(&S.cand[lane * 4], cand + p);
+                    cp_async4(&S.img[lane * 4], ra.nextImage + p);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for(int t = 0; t < kStages - 1; t++) issue(t);
+
+    for(int t = 0; t < ntrips; t++)
+    {
+        issue(t + kStages - 1);
+        cp_async_wait<kStages - 1>();
+        __syncwarp();
+        const WarpStage & S = stages[t % kStages];
+#pragma unroll 1
+        for(int half = 0; half < 2; half++)
+        {
+            constexpr int PX = 2;
+            const int q0 = half * 64 + lane * 2;
+            const int p = w0 + t * kTripPx + q0;
+            const bool inside = p < w1;
+            const int py0 = p / g.cols, px0 = p - py0 * g.cols;   // one division per pair of pixels
+            float vx[PX], vy[PX], vz[PX], nx[PX], ny[PX], nz[PX], d1[PX];
+            unsigned cm = 0, im = 0;
+            if(inside)
+            {
+                if(L.icp)
+                {
+                    const float2 a0 = *reinterpret_cast<const float2 *>(&S.f[0][q0]), a1 = *reinterpret_cast<const float2 *>(&S.f[1][q0]),
+                                 a2 = *reinterpret_cast<const float2 *>(&S.f[2][q0]), b0 = *reinterpret_cast<const float2 *>(&S.f[3][q0]),
+                                 b1 = *reinterpret_cast<const float2 *>(&S.f[4][q0]), b2 = *reinterpret_cast<const float2 *>(&S.f[5][q0]);
+                    vx[0] = a0.x; vx[1] = a0.y; vy[0] = a1.x; vy[1] = a1.y; vz[0] = a2.x; vz[1] = a2.y;
+                    nx[0] = b0.x; nx[1] = b0.y; ny[0] = b1.x; ny[1] = b1.y; nz[0] = b2.x; nz[1] = b2.y;
+                }
+                if(L.rgb)
+                {
+                    cm = *reinterpret_cast<const unsigned short *>(&S.cand[q0]);
+                    im = *reinterpret_cast<const unsigned short *>(&S.img[q0]);
+                    const float2 dd = *reinterpret_cast<const float2 *>(&S.f[6][q0]);
+                    d1[0] = dd.x; d1[1] = dd.y;
+                }
+            }
+            float3 vg[PX], vp[PX], np[PX];
+            int o[PX];
+            bool ok[PX];
+            float td1[PX], d0[PX];
+            int zxy[PX];
+            unsigned char li[PX];
+            bool rok[PX];
+#pragma unroll
+            for(int c = 0; c < PX; c++)
+            {
+                ok[c] = false;
+                o[c] = 0;
+                if(L.icp && inside) ok[c] = icp_project(ia, make_float3(vx[c], vy[c], vz[c]), vg[c], o[c]);
+                if(!ok[c]) o[c] = 0;
+                rok[c] = false;
+                zxy[c] = 0;
+                if(L.rgb && ((cm >> (8 * c)) & 0xff))
+                {
+                    int x = px0 + c, y = py0;
+                    if(x >= g.cols)
+                    {
+                        x -= g.cols;
+                        y++;
+                    }
+                    int u0, v0;
+                    rok[c] = rgb_project(ra, x, y, d1[c], u0, v0, td1[c]);
+                    if(rok[c]) zxy[c] = u0 | (v0 << 16);
+                }
+            }
+#pragma unroll
+            for(int c = 0; c < PX; c++)
+            {
+                if(L.icp)
+                {
+                    vp[c] = make_float3(__ldg(ia.vprev + o[c]), __ldg(ia.vprev + plane + o[c]), __ldg(ia.vprev + 2 * plane + o[c]));
+                    np[c] = make_float3(__ldg(ia.nprev + o[c]), __ldg(ia.nprev + plane + o[c]), __ldg(ia.nprev + 2 * plane + o[c]));
+                }
+                if(L.rgb)
+                {
+                    const int r = (zxy[c] >> 16) * g.cols + (zxy[c] & 0xffff);
+                    d0[c] = __ldg(ra.lastDepth + r);
+                    li[c] = __ldg(ra.lastImage + r);
+                }
+            }
+            if(L.icp)
+            {
+#pragma unroll
+                for(int c = 0; c < PX; c++)
+                {
+                    float row[7];
+                    bool found = icp_finish(ia, vg[c], make_float3(nx[c], ny[c], nz[c]), vp[c], np[c], row);
+                    if(!ok[c])
+                    {
+                        found = false;
+#pragma unroll
+                        for(int q = 0; q < 7; q++) row[q] = 0.f;
+                    }
+                    if(__any_sync(0xffffffffu, found))   // warp-uniform: lanes that miss add zeros
+                    {
+                        float a29[29];
+#pragma unroll
+                        for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                        accumulate_se3(a29, row, found);
+#pragma unroll
+                        for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                    }
+                }
+            }
+            if(L.rgb)
+            {
+#pragma unroll
+                for(int c = 0; c < PX; c++)
+                {
+                    const bool valid = rok[c] && rgb_accept(ra, td1[c], d0[c], li[c]);
+                    const unsigned m = __ballot_sync(0xffffffffu, valid);
+                    if(valid)
+                    {
+                        BCorres cc;
+                        cc.zxy = zxy[c];
+                        cc.d0 = d0[c];
+                        cc.diff = __fsub_rn(static_cast<float>((im >> (8 * c)) & 0xff), static_cast<float>(li[c]));
+                        const int k = p + c;
+                        cc.gxy = (int)(unsigned short)__ldg(ra.dIdx + k) | ((int)__ldg(ra.dIdy + k) << 16);
+                        cnt0 += 1;
+                        cnt1 += (int)(cc.diff * cc.diff);
+                        reinterpret_cast<int4 *>(cimg)[w0 + wcount + __popc(m & ((1u << lane) - 1u))] = *reinterpret_cast<const int4 *>(&cc);
+                    }
+                    wcount += __popc(m);
+                }
+            }
+        }
+        __syncwarp();   // the stage is free for the issue of the next iteration
+    }
+    char * ws_seq = ws + (size_t)seq * kWorkspaceBytes;
+    if(L.rgb && lane == 0) reinterpret_cast<int *>(ws_seq + kCountsOffset)[gw] = wcount;
+    if(!seq_reduce(acc, cnt0, cnt1, L.rgb, sh, ws_seq, 0)) return;
+    if(threadIdx.x >= 32) return;
+    sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
+}
+
 // ICP-only runs: the update as its own one-warp-per-sequence launch.
 __global__ void __launch_bounds__(32) kb_update(const GnLaunch L, char * states, size_t stride, const float * sums, int lvl, int j, slam_step_record * trace)
 {
@@ -627,8 +865,8 @@ static int px_variant()
     if(v < 0)
     {
         const char * e = getenv("SLAM_BATCH_PX");
-        v = e ? atoi(e) : 4;
-        if(v != 1 && v != 2 && v != 4) v = 4;
+        v = e ? atoi(e) : 0;   // 0: cp.async-staged phase A (default); 1 / 2 / 4: register-only variants with that many pixels per thread
+        if(v != 0 && v != 1 && v != 2 && v != 4) v = 0;
     }
     return v;
 }
@@ -664,15 +902,29 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
             d.launches++;
         }
         int px = px_variant();
+        const bool staged = px == 0 && plane % 4 == 0;
+        if(px == 0) px = 4;
         while(plane % px) px >>= 1;
         const int nb = blocks_per_seq(plane / px, B, d.num_sms);
+        if(staged)
+        {
+            static bool attr_set = false;
+            if(!attr_set)
+            {
+                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem));
+                attr_set = true;
+            }
+        }
         for(int j = 0; j < L.iterations[lvl]; j++)
         {
 #define SLAM_PHASE_A(PXV) \
     kb_phase_a<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride, d.cand_off[lvl], lvl)
 #define SLAM_PHASE_B(PXV) \
     kb_phase_b<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, lvl, j, trace)
-            if(px == 4) SLAM_PHASE_A(4); else if(px == 2) SLAM_PHASE_A(2); else SLAM_PHASE_A(1);
+            if(staged)
+                kb_phase_a_staged<<<dim3(nb, B), kBThreads, kStagedSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride,
+                                                                               d.cand_off[lvl], lvl);
+            else if(px == 4) SLAM_PHASE_A(4); else if(px == 2) SLAM_PHASE_A(2); else SLAM_PHASE_A(1);
             d.launches++;
             if(L.rgb)
             {

@@ -113,28 +113,25 @@ __device__ __forceinline__ bool icp_project(const IcpArgs & a, const float3 vcur
 __device__ __forceinline__ bool icp_finish(const IcpArgs & a, const float3 vcurr_g, const float3 ncurr, const float3 vprev_g, const float3 nprev_g,
                                            float (&row)[7])
 {
-#pragma unroll
-    for(int k = 0; k < 7; k++) row[k] = 0.f;
     const float3 ncurr_g = a.Rcurr * ncurr;
 
     const float dist = norm3(vprev_g - vcurr_g);
     const float sine = norm3(cross3(ncurr_g, nprev_g));
 
     const bool found = (sine < a.angleThres && dist <= a.distThres && !isnan(ncurr.x) && !isnan(nprev_g.x));
-    if(found)
-    {
-        const float3 s_cp = a.Rprev_inv * (vcurr_g - a.tprev);
-        const float3 d_cp = a.Rprev_inv * (vprev_g - a.tprev);
-        const float3 n_cp = a.Rprev_inv * nprev_g;
-        const float3 sxn = cross3(s_cp, n_cp);
-        row[0] = n_cp.x;
-        row[1] = n_cp.y;
-        row[2] = n_cp.z;
-        row[3] = sxn.x;
-        row[4] = sxn.y;
-        row[5] = sxn.z;
-        row[6] = dot3(n_cp, s_cp - d_cp);
-    }
+    // branch-free: the row is computed regardless and zeroed by selects (a divergent branch here costs more than the ~45
+    // instructions it would skip in the lanes that miss)
+    const float3 s_cp = a.Rprev_inv * (vcurr_g - a.tprev);
+    const float3 d_cp = a.Rprev_inv * (vprev_g - a.tprev);
+    const float3 n_cp = a.Rprev_inv * nprev_g;
+    const float3 sxn = cross3(s_cp, n_cp);
+    row[0] = found ? n_cp.x : 0.f;
+    row[1] = found ? n_cp.y : 0.f;
+    row[2] = found ? n_cp.z : 0.f;
+    row[3] = found ? sxn.x : 0.f;
+    row[4] = found ? sxn.y : 0.f;
+    row[5] = found ? sxn.z : 0.f;
+    row[6] = found ? dot3(n_cp, s_cp - d_cp) : 0.f;
     return found;
 }
 
