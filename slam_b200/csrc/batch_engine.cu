@@ -488,6 +488,7 @@ kb_phase_a(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
 // pixels of the warp's chunk, consumed as two half trips of 2 pixels per lane); no block-level synchronisation.
 constexpr int kTripPx = 128;
 constexpr int kStages = 3;
+constexpr int kL2Ahead = 2;
 struct WarpStage
 {
     float f[7][kTripPx];            // vcurr x,y,z  ncurr x,y,z  nextDepth
@@ -503,6 +504,11 @@ __device__ __forceinline__ void cp_async16(void * smem, const void * gmem)
 __device__ __forceinline__ void cp_async4(void * smem, const void * gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+// TMA prefetch of a contiguous range into L2 (no destination): warms the lines the gathers of a later trip will hit
+__device__ __forceinline__ void prefetch_l2_bulk(const void * gmem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -558,6 +564,16 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
     const int ntrips = (w1 - w0 + kTripPx - 1) / kTripPx;
     int wcount = 0;   // correspondences this warp has written (warp-uniform)
 
+    // The projective gathers of a trip land near the same pixels of the model maps: TMA-prefetch those lines into L2
+    // kL2Ahead trips before they are needed, one plane per lane.
+    auto warm = [&](int t) {
+        if(t >= ntrips) return;
+        const int b0 = w0 + t * kTripPx;
+        const unsigned npx = (unsigned)min(kTripPx, w1 - b0);
+        if(L.icp && lane < 6) prefetch_l2_bulk((lane < 3 ? ia.vprev + lane * plane : ia.nprev + (lane - 3) * plane) + b0, npx * 4u);
+        if(L.rgb && lane == 6) prefetch_l2_bulk(ra.lastDepth + b0, npx * 4u);
+        if(L.rgb && lane == 7) prefetch_l2_bulk(ra.lastImage + b0, (npx + 15u) & ~15u);
+    };
     auto issue = [&](int t) {
         if(t < ntrips)
         {
@@ -584,11 +600,13 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
         }
         cp_async_commit();
     };
+    for(int t = 0; t < kL2Ahead; t++) warm(t);
 #pragma unroll
     for(int t = 0; t < kStages - 1; t++) issue(t);
 
     for(int t = 0; t < ntrips; t++)
     {
+        warm(t + kL2Ahead);
         issue(t + kStages - 1);
         cp_async_wait<kStages - 1>();
         __syncwarp();
