@@ -18,6 +18,8 @@ rank can replay its own sequence without a renderer in the loop.
          stream) and the pose is read back (D2H) inside the timed region
   roofline     persistent Gauss-Newton kernel: algorithmic bytes (48 + 30 + 32 B per
                pixel-iteration, 2 B per SO3 pixel-iteration) / its CUDA-event duration, vs the measured HBM peak
+  batched      (extra) BASELINE.json configs[3]: 64 independent sequences, 64 / N per GPU in one batched handle; frames/s and
+               the HBM roofline of its ICP/RGB reduction launches
   cpu_baseline the CPU port (oracle/odom_oracle.c, OpenMP, all host cores) on a bounded sample of the same frames
   ref_cuda     (extra) the reference's own kernels + launch/sync pattern (oracle/_ref) on the same GPU and frames:
                the denominator of the north-star's ">= 20x the reference's own CUDA path"
@@ -312,6 +314,14 @@ def run_ours(args, rank, local_rank, world):
         except Exception:
             traffic = None
 
+    # ================= batched extra: BASELINE.json configs[3] =================
+    batched = None
+    if not args.no_batched:
+        try:
+            batched = run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames, barrier, max_over_ranks, peak, peak_src)
+        except Exception as e:   # pragma: no cover
+            batched = {"value": None, "note": f"failed: {e}"}
+
     line = None
     if rank == 0:
         # ---- context baselines (N = 1 only): CPU port and the reference's own CUDA path
@@ -367,6 +377,7 @@ def run_ours(args, rank, local_rank, world):
                          "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": (gn_ms / dev_ms) if dev_ms else None,
                          "note": "one launch = all SO3 + 19 ICP/RGB iterations of a frame; the 45 MB working set stays in the 126 MB L2, so DRAM traffic is far "
                                  "below the algorithmic bytes and the kernel is latency-bound (grid barriers + fp64 solves), not bandwidth-bound"},
+            "batched": batched,
             "cpu_baseline": cpu,
             "ref_cuda": ref_cuda,
             "clocks": clocks,
@@ -380,6 +391,103 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
 
 
+def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames, barrier, max_over_ranks, peak, peak_src):
+    """BASELINE.json configs[3]: 64 independent 640x480 sequences, 64 / N per GPU, one handle with batch = 64 / N per rank
+    (the batched streaming engine: lock-step map-reduce launches over all sequences).  A step = one frame of every
+    sequence.  Reported: whole-job frames/s, and the HBM roofline of the ICP/RGB reduction launches (phase A + phase B),
+    timed by CUDA events on the handle's stream inside the library."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    dev = f"cuda:{local_rank}"
+    total = 64
+    B = max(1, total // world)
+    nf = len(dframes)
+    keys = ("depth", "rgba", "mv", "mn", "mrgba")
+    odo = RGBDOdometry(W, H, 319.5, 239.5, 481.20, -480.0, device=local_rank, batch=B)
+    odo.initFirstRGB(torch.stack([dfirst] * B))
+    sets = []
+    for off in (0, 37):    # two distinct batch frames (2 x 826 MB at B = 64) + a 2.6 GB arena: far beyond L2
+        d = {k: torch.stack([dframes[(off + 5 * b) % nf][k] for b in range(B)]) for k in keys}
+        P = np.stack([frames[(off + 5 * b) % nf]["model_pose"] for b in range(B)])
+        G = np.stack([frames[(off + 5 * b) % nf]["gt_pose"][:3, 3] for b in range(B)])
+        sets.append((d, P, odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, DEPTH_CUTOFF, MODEL_CUTOFF), G))
+    torch.cuda.synchronize()
+    steps = max(4, min(40, args.steps // 16))
+    warm = 3
+
+    def step(i):
+        d, P, fr, G = sets[i % 2]
+        return odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+
+    for i in range(warm):
+        step(i)
+    stream = torch.cuda.ExternalStream(odo.stream, device=dev)
+    odo.set_profiling(True)
+    odo.get_profile(reset=True)
+    l0 = odo.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    out = None
+    for i in range(steps):
+        out = step(warm + i)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    red_ms, _ = odo.get_profile(reset=True)
+    odo.set_profiling(False)
+    launches = odo.launch_count() - l0
+    G = sets[(warm + steps - 1) % 2][3]
+    err_mm = float(np.linalg.norm(out[0].reshape(B, 3) - G, axis=1).max() * 1e3)
+    value = world * B * steps / (ms / 1e3)
+    # ---- end to end: the same batch from pinned host memory (H2D of every input inside the timed region)
+    e2e = None
+    if B * BYTES_PER_FRAME_IN * 2 < 4e9:
+        hsets = []
+        for off in (0, 37):
+            d = {k: torch.stack([hframes[(off + 5 * b) % nf][k] for b in range(B)]).pin_memory() for k in keys}
+            P = np.stack([frames[(off + 5 * b) % nf]["model_pose"] for b in range(B)])
+            hsets.append((d, P, odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, DEPTH_CUTOFF, MODEL_CUTOFF)))
+        for i in range(2):
+            d, P, fr = hsets[i % 2]
+            odo.track_host(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(4, steps // 2)
+        odo.prefetch_host(hsets[0][2])
+        for i in range(n_e2e):
+            d, P, fr = hsets[i % 2]
+            if i + 1 < n_e2e:
+                odo.prefetch_host(hsets[(i + 1) % 2][2])
+            odo.track_host(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e = {"value": world * B * n_e2e / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": B * (BYTES_PER_FRAME_IN + 64), "d2h_bytes_per_step": B * 48,
+               "ms_per_step": e2e_ms / n_e2e, "note": "PCIe-bound: 12.9 MB of host inputs per tracked frame"}
+    odo.close()
+    px_iter = sum((W >> l) * (H >> l) * ITERS[l] for l in range(LEVELS))
+    alg = px_iter * 110.0 * B            # per step and GPU: 48 + 30 + 32 B per pixel-iteration (SURVEY.md 8d)
+    achieved = alg * steps / (red_ms * 1e-3) / 1e9 if red_ms > 0 else None
+    traffic = None
+    tp = ROOT / "profiles" / "batch_kernel_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_step")
+        except Exception:
+            traffic = None
+    return {
+        "workload": "configs[3]: 64 independent synthetic 640x480 sequences, ICP+RGB+SO3, 64 / N per GPU in one batched handle (streaming engine), no collective",
+        "sequences_total": B * world, "sequences_per_gpu": B, "value": value, "unit": "frames/s", "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+        "scaling": "strong (64 sequences in total)", "gpu_launches_per_step": launches / steps, "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "kb_phase_a_staged + kb_phase_b (every ICP/RGB reduction launch of a step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src, "ms_per_step": red_ms / steps,
+                     "algorithmic_bytes_per_step": alg, "share_of_step": red_ms / ms if ms else None,
+                     "note": "algorithmic bytes = what the reference's icpStep + computeRgbResidual + rgbStep move per pixel-iteration (110 B); the fused kernels "
+                             "move less (compacted correspondences, candidate masks), see DESIGN.md"},
+        "check": {"max_frame_error_mm": err_mm},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,6 +495,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / ref_cuda context measurements")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched extra (configs[3])")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

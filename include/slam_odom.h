@@ -187,8 +187,10 @@ int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_
 
 /* Kernel-launch counter (for bench.py's gpu_launches). */
 long long slam_odom_launch_count(slam_odom_t h);
-/* CUDA-event timing of the persistent Gauss-Newton kernel on the handle's stream: enable, run,
- * then read the accumulated device time and launch count (reset = 1 clears the totals). */
+/* CUDA-event timing of the Gauss-Newton reduction kernels on the handle's stream: enable, run, then read the
+ * accumulated device time and the number of timed brackets (reset = 1 clears the totals).  batch < 4: one bracket per
+ * frame around the persistent kernel; batch >= 4 (streaming engine): one bracket per pyramid level around that level's
+ * phase A / phase B launches. */
 int slam_odom_set_profiling(slam_odom_t h, int enable);
 int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_kernel_launches, int reset);
 /* The stream the handle runs on (cudaStream_t), e.g. to record the caller's own events on it. */

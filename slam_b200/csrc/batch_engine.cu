@@ -890,7 +890,7 @@ static int px_variant()
 }
 
 int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
-                  cudaStream_t s)
+                  cudaStream_t s, std::vector<cudaEvent_t> * prof_events)
 {
     const int B = L.batch;
     if(!L.trace) trace = nullptr, trace_count = nullptr;
@@ -933,6 +933,13 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
                 attr_set = true;
             }
         }
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if(prof_events)   // CUDA-event bracket of this level's reduction launches (phase A + phase B / update)
+        {
+            SLAM_CUDA_TRY(cudaEventCreate(&e0));
+            SLAM_CUDA_TRY(cudaEventCreate(&e1));
+            SLAM_CUDA_TRY(cudaEventRecord(e0, s));
+        }
         for(int j = 0; j < L.iterations[lvl]; j++)
         {
 #define SLAM_PHASE_A(PXV) \
@@ -954,6 +961,12 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
                 kb_update<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.sums, lvl, j, trace);
                 d.launches++;
             }
+        }
+        if(prof_events)
+        {
+            SLAM_CUDA_TRY(cudaEventRecord(e1, s));
+            prof_events->push_back(e0);
+            prof_events->push_back(e1);
         }
     }
     kb_end<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.results, trace_count);

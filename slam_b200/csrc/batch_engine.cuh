@@ -1,5 +1,6 @@
 // Batched streaming engine: declarations (see batch_engine.cu).
 #pragma once
+#include <vector>
 #include "gn_kernel.cuh"
 
 namespace slam {
@@ -25,6 +26,6 @@ struct BatchDevice
 size_t batch_state_bytes(int batch, const LevelGeom * geom, int levels);
 void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom * geom, int levels, GnSeqIn * seq_in, GnResult * results);
 int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
-                  cudaStream_t stream);
+                  cudaStream_t stream, std::vector<cudaEvent_t> * prof_events = nullptr);
 
 }   // namespace slam

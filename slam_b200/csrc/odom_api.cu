@@ -870,7 +870,9 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         rc = gn_stage_inputs(h->gn, L, h->seq.data(), trans, rot, &in);
         if(rc) return rc;
         const long long before = h->be.launches;
-        rc = batch_enqueue(h->be, L, in, h->h_results, h->gn.trace, h->gn.trace_count, h->stream);
+        if(h->gn.profiling && h->gn.ev.size() >= 4096)
+            if(int rc2 = gn_fold_profile(h->gn)) return rc2;
+        rc = batch_enqueue(h->be, L, in, h->h_results, h->gn.trace, h->gn.trace_count, h->stream, h->gn.profiling ? &h->gn.ev : nullptr);
         h->launches += h->be.launches - before;
         h->gn.so3_swapped = L.so3;
     }
