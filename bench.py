@@ -55,6 +55,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line (the JSON record): libraries that print there from native code (NCCL's version banner,
+# the reference kernels' "performance database" notes) are diverted to stderr by re-pointing fd 1 for the run.
+_REAL_STDOUT = None
+
+
+def divert_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def algorithmic_bytes_per_frame(so3_iters: float) -> float:
     """SURVEY.md 8(d) / BASELINE.md 3: ICP 48 + RGB residual 30 + RGB step 32 B per pixel-iteration; SO3 2 B/px-iteration."""
     px_iter = sum((W >> l) * (H >> l) * ITERS[l] for l in range(LEVELS))
@@ -184,7 +206,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference publishes no CPU path for RGBDOdometryef; this is its reduction math restated in C on the host cores (context only)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -388,7 +410,7 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames, barrier, max_over_ranks, peak, peak_src):
@@ -501,6 +523,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    divert_stdout()
     if args.impl == "reference":
         if args.steps > 200:
             args.steps = 200   # bounded sample: ~0.15 s per frame on 8 cores
