@@ -12,6 +12,8 @@
 // and per SO3 iteration kb_so3_map + kb_so3_update.  All per-sequence state lives in device memory; the host
 // enqueues a fixed launch sequence (sequences that finished a loop early skip their blocks) and reads back
 // the GnResult array once.  Same per-pixel arithmetic (pixel_ops.cuh) => same masks as the single-sequence path.
+#include <cstdio>
+#include <cstdlib>
 #include "batch_engine.cuh"
 #include "gn_scalar.cuh"
 
@@ -750,12 +752,15 @@ __global__ void __launch_bounds__(32) kb_update(const GnLaunch L, char * states,
     seq_update(sh, L, states + (size_t)seq * stride, seq, lvl, j, trace);
 }
 
-// Phase B: RGB Jacobian products (reduce.cu:494-624) from the compacted correspondences of phase A (same grid), then the update.
-template <int PX>
+// Phase B: RGB Jacobian products (reduce.cu:494-624) from the compacted correspondences of phase A, then the update.
+// The lists are short (a few hundred records per phase-A warp), so this launch is a single wave: each warp walks several
+// lists as one flat index space (prefix sums of their counts in shared memory).  a_blocks / a_px describe phase A's grid.
 __global__ void __launch_bounds__(kBThreads, 2)
-kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, const float * sums, int lvl, int j, slam_step_record * trace)
+kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, const float * sums, int lvl, int j, slam_step_record * trace,
+           int a_blocks, int a_px)
 {
     __shared__ GnShared sh;
+    __shared__ int s_pre[kBThreads / 32][33];
     const int seq = blockIdx.y;
     const GnShared & st = bstate(states, stride, seq);
     if(st.stop_level == lvl) return;
@@ -791,26 +796,57 @@ kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
     a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
     a.cloud = nullptr;
     char * ws_seq = ws + (size_t)seq * kWorkspaceBytes;
-    const int chunk = warp_chunk(plane, PX);
+    // phase A's ownership: list l covers pixels [l * chunk, ...), its records start at the same offset
+    const int a_warps = a_blocks * (kBThreads / 32);
+    const int per = (plane + a_warps - 1) / a_warps;
+    const int chunk = (per + 32 * a_px - 1) / (32 * a_px) * (32 * a_px);
+    const int b_warps = gridDim.x * (kBThreads / 32);
     const int gw = blockIdx.x * (kBThreads / 32) + wid;
-    const int w0 = min(gw * chunk, plane);
-    const int n = __ldcg(reinterpret_cast<const int *>(ws_seq + kCountsOffset) + gw);
-    const int4 * list = reinterpret_cast<const int4 *>(in.corres[lvl]) + w0;
+    // this warp's lists: gw, gw + b_warps, ... (at most 32, checked by the host); lane k holds the count of the k-th
+    const int my_list = gw + lane * b_warps;
+    const int cnt = my_list < a_warps ? __ldcg(reinterpret_cast<const int *>(ws_seq + kCountsOffset) + my_list) : 0;
+    int pre = cnt;   // inclusive prefix over the lanes
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1)
+    {
+        const int v = __shfl_up_sync(0xffffffffu, pre, d);
+        if(lane >= d) pre += v;
+    }
+    s_pre[wid][lane + 1] = pre;
+    if(lane == 0) s_pre[wid][0] = 0;
+    __syncwarp();
+    const int total = s_pre[wid][32];
+    const int4 * cimg = reinterpret_cast<const int4 *>(in.corres[lvl]);
     float acc[32];
 #pragma unroll
     for(int k = 0; k < 32; k++) acc[k] = 0.f;
-    for(int i0 = 0; i0 < n; i0 += 128)
+    for(int i0 = 0; i0 < total; i0 += 128)
     {
         int4 raw[4];
+        bool have[4];
 #pragma unroll
         for(int q = 0; q < 4; q++)
         {
             const int i = i0 + q * 32 + lane;
-            raw[q] = i < n ? __ldcg(list + i) : make_int4(0, 0, 0, 0);
+            have[q] = i < total;
+            raw[q] = make_int4(0, 0, 0, 0);
+            if(have[q])
+            {
+                // list k with s_pre[k] <= i < s_pre[k + 1]
+                int lo = 0, hi = 31;
+#pragma unroll
+                for(int it = 0; it < 5; it++)
+                {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if(s_pre[wid][mid] <= i) lo = mid; else hi = mid - 1;
+                }
+                const int l = gw + lo * b_warps;
+                raw[q] = __ldcg(cimg + min(l * chunk, plane) + (i - s_pre[wid][lo]));
+            }
         }
 #pragma unroll
         for(int q = 0; q < 4; q++)
-            if(i0 + q * 32 + lane < n)
+            if(have[q])
             {
                 const BCorres cc = *reinterpret_cast<const BCorres *>(&raw[q]);
                 float row[7];
@@ -889,12 +925,76 @@ static int px_variant()
     return v;
 }
 
-int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
-                  cudaStream_t s, std::vector<cudaEvent_t> * prof_events)
+// Development aid (SLAM_BATCH_DETAIL=1): CUDA-event pair around every launch, totals per kernel printed by batch_report().
+namespace {
+struct DetailProf
 {
-    const int B = L.batch;
-    if(!L.trace) trace = nullptr, trace_count = nullptr;
-    SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, h_seq_in_pinned, sizeof(GnSeqIn) * B, cudaMemcpyHostToDevice, s));
+    bool on = false, init = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+} g_detail;
+const char * kTagName[8] = {"begin/end/level", "so3", "candidates", "phase_a", "phase_b", "update", "", ""};
+void detail_fold()
+{
+    for(size_t i = 0; i + 1 < g_detail.ev.size(); i += 2)
+    {
+        cudaEventSynchronize(g_detail.ev[i + 1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_detail.ev[i], g_detail.ev[i + 1]);
+        g_detail.ms[g_detail.tag[i / 2]] += ms;
+        g_detail.n[g_detail.tag[i / 2]]++;
+        cudaEventDestroy(g_detail.ev[i]);
+        cudaEventDestroy(g_detail.ev[i + 1]);
+    }
+    g_detail.ev.clear();
+    g_detail.tag.clear();
+}
+struct DetailScope
+{
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DetailScope(cudaStream_t s_, int tag) : s(s_)
+    {
+        if(!g_detail.on) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+        g_detail.tag.push_back(tag);
+    }
+    ~DetailScope()
+    {
+        if(!g_detail.on) return;
+        cudaEventRecord(e1, s);
+        g_detail.ev.push_back(e0);
+        g_detail.ev.push_back(e1);
+    }
+};
+}   // namespace
+
+void batch_report()
+{
+    if(!g_detail.on) return;
+    detail_fold();
+    for(int t = 0; t < 6; t++)
+        if(g_detail.n[t]) fprintf(stderr, "[batch detail] %-16s %8lld launches %10.3f ms total %8.2f us/launch\n", kTagName[t], g_detail.n[t], g_detail.ms[t], 1e3 * g_detail.ms[t] / g_detail.n[t]);
+    for(int t = 0; t < 8; t++) g_detail.ms[t] = 0, g_detail.n[t] = 0;
+}
+
+// The launch sequence of one group of sequences [s0, s0 + B) on stream s (all per-sequence arrays are indexed from s0).
+static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, slam_step_record * trace, int * trace_count, cudaStream_t s)
+{
+    BatchDevice d = d0;
+    d.seq_in += s0;
+    d.states += (size_t)s0 * d.state_stride;
+    d.sums += (size_t)s0 * 64;
+    d.cand0 += (size_t)s0 * d.aux_stride;
+    d.ws += (size_t)s0 * kWorkspaceBytes;
+    d.results += s0;
+    if(trace) trace += (size_t)s0 * kGnMaxTrace;
+    if(trace_count) trace_count += s0;
+    d.launches = 0;
     kb_begin<<<B, 32, 0, s>>>(L, d.seq_in, d.states, d.state_stride);
     d.launches++;
     if(L.so3)
@@ -902,6 +1002,7 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         const int nb = blocks_per_seq(L.geom[2].rows * L.geom[2].cols, B, d.num_sms);
         for(int it = 0; it < 10; it++)
         {
+            DetailScope ds(s, 1);
             kb_so3<<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, it, trace);
             d.launches++;
         }
@@ -916,6 +1017,7 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         if(L.iterations[lvl] <= 0) continue;
         if(L.rgb)
         {
+            DetailScope ds(s, 2);
             kb_candidates<<<dim3(blocks_per_seq(plane, B, d.num_sms), B), kBThreads, 0, s>>>(L, d.seq_in, d.cand0, d.aux_stride, d.cand_off[lvl], lvl);
             d.launches++;
         }
@@ -924,6 +1026,11 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         if(px == 0) px = 4;
         while(plane % px) px >>= 1;
         const int nb = blocks_per_seq(plane / px, B, d.num_sms);
+        // phase B: one wave (2 blocks per SM), but every warp may walk at most 32 of phase A's per-warp lists
+        int nbB = (2 * d.num_sms) / B;
+        if(nbB < (nb + 31) / 32) nbB = (nb + 31) / 32;
+        if(nbB < 1) nbB = 1;
+        if(nbB > nb) nbB = nb;
         if(staged)
         {
             static bool attr_set = false;
@@ -933,47 +1040,106 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
                 attr_set = true;
             }
         }
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if(prof_events)   // CUDA-event bracket of this level's reduction launches (phase A + phase B / update)
-        {
-            SLAM_CUDA_TRY(cudaEventCreate(&e0));
-            SLAM_CUDA_TRY(cudaEventCreate(&e1));
-            SLAM_CUDA_TRY(cudaEventRecord(e0, s));
-        }
         for(int j = 0; j < L.iterations[lvl]; j++)
         {
 #define SLAM_PHASE_A(PXV) \
     kb_phase_a<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride, d.cand_off[lvl], lvl)
-#define SLAM_PHASE_B(PXV) \
-    kb_phase_b<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, lvl, j, trace)
+            {
+            DetailScope ds(s, 3);
             if(staged)
                 kb_phase_a_staged<<<dim3(nb, B), kBThreads, kStagedSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride,
                                                                                d.cand_off[lvl], lvl);
             else if(px == 4) SLAM_PHASE_A(4); else if(px == 2) SLAM_PHASE_A(2); else SLAM_PHASE_A(1);
+            }
             d.launches++;
             if(L.rgb)
             {
-                if(px == 4) SLAM_PHASE_B(4); else if(px == 2) SLAM_PHASE_B(2); else SLAM_PHASE_B(1);
+                DetailScope ds(s, 4);
+                kb_phase_b<<<dim3(nbB, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, lvl, j, trace, nb, px);
                 d.launches++;
             }
             else
             {
+                DetailScope ds(s, 5);
                 kb_update<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.sums, lvl, j, trace);
                 d.launches++;
             }
-        }
-        if(prof_events)
-        {
-            SLAM_CUDA_TRY(cudaEventRecord(e1, s));
-            prof_events->push_back(e0);
-            prof_events->push_back(e1);
         }
     }
     kb_end<<<B, 32, 0, s>>>(L, d.states, d.state_stride, d.results, trace_count);
     d.launches++;
     SLAM_CUDA_TRY(cudaGetLastError());
+    d0.launches += d.launches;
+    return SLAM_OK;
+}
+
+// Whole batch.  With 8 or more sequences the batch runs as two (SLAM_BATCH_GROUPS: 1..4) independent groups on their own
+// streams: while one group sits in a latency-bound stretch (phase B, the fp64 solves, the SO3 iterations of the small level)
+// the other group's streaming launches keep the memory system busy.  Results do not depend on the grouping.
+int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
+                  cudaStream_t s, std::vector<cudaEvent_t> * prof_events)
+{
+    const int B = L.batch;
+    if(!L.trace) trace = nullptr, trace_count = nullptr;
+    if(!g_detail.init)
+    {
+        g_detail.init = true;
+        const char * e = getenv("SLAM_BATCH_DETAIL");
+        g_detail.on = e && atoi(e) != 0;
+    }
+    if(g_detail.on && g_detail.ev.size() > 8192) detail_fold();
+    int groups = B >= 8 ? 2 : 1;
+    if(const char * e = getenv("SLAM_BATCH_GROUPS")) groups = atoi(e);
+    if(groups < 1) groups = 1;
+    if(groups > 4) groups = 4;
+    if(groups > B) groups = B;
+    if(g_detail.on) groups = 1;   // per-kernel timing wants the launches back to back
+    while((int)d.side.size() < groups - 1)
+    {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        SLAM_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        d.side.push_back(st);
+        d.side_done.push_back(ev);
+    }
+    if(!d.fork) SLAM_CUDA_TRY(cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, h_seq_in_pinned, sizeof(GnSeqIn) * B, cudaMemcpyHostToDevice, s));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if(prof_events)   // CUDA-event bracket of the whole engine section of this step
+    {
+        SLAM_CUDA_TRY(cudaEventCreate(&e0));
+        SLAM_CUDA_TRY(cudaEventCreate(&e1));
+        SLAM_CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    if(groups > 1) SLAM_CUDA_TRY(cudaEventRecord(d.fork, s));
+    for(int gidx = 0; gidx < groups; gidx++)
+    {
+        const int s0 = (int)((long long)B * gidx / groups), s1 = (int)((long long)B * (gidx + 1) / groups);
+        cudaStream_t st = gidx == 0 ? s : d.side[gidx - 1];
+        if(gidx > 0) SLAM_CUDA_TRY(cudaStreamWaitEvent(st, d.fork, 0));
+        if(int rc = enqueue_group(d, L, s0, s1 - s0, trace, trace_count, st)) return rc;
+        if(gidx > 0) SLAM_CUDA_TRY(cudaEventRecord(d.side_done[gidx - 1], st));
+    }
+    for(int gidx = 1; gidx < groups; gidx++) SLAM_CUDA_TRY(cudaStreamWaitEvent(s, d.side_done[gidx - 1], 0));
+    if(prof_events)
+    {
+        SLAM_CUDA_TRY(cudaEventRecord(e1, s));
+        prof_events->push_back(e0);
+        prof_events->push_back(e1);
+    }
     SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * B, cudaMemcpyDeviceToHost, s));
     return SLAM_OK;
+}
+
+void batch_release(BatchDevice & d)
+{
+    for(auto st : d.side) cudaStreamDestroy(st);
+    for(auto ev : d.side_done) cudaEventDestroy(ev);
+    if(d.fork) cudaEventDestroy(d.fork);
+    d.side.clear();
+    d.side_done.clear();
+    d.fork = nullptr;
 }
 
 }   // namespace slam

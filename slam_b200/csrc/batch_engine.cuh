@@ -19,6 +19,9 @@ struct BatchDevice
     size_t cand_off[SLAM_MAX_LEVELS], vmask_off[SLAM_MAX_LEVELS];
     char * ws = nullptr;            // [batch][kWorkspaceBytes]: partial rows + ticket of each sequence's running reduction
     int num_sms = 148;
+    std::vector<cudaStream_t> side;       // streams of the sequence groups beyond the first
+    std::vector<cudaEvent_t> side_done;
+    cudaEvent_t fork = nullptr;
     int batch = 0;
     long long launches = 0;
 };
@@ -27,5 +30,8 @@ size_t batch_state_bytes(int batch, const LevelGeom * geom, int levels);
 void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom * geom, int levels, GnSeqIn * seq_in, GnResult * results);
 int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
                   cudaStream_t stream, std::vector<cudaEvent_t> * prof_events = nullptr);
+
+void batch_release(BatchDevice & d);
+void batch_report();   // SLAM_BATCH_DETAIL=1: print per-kernel event totals to stderr
 
 }   // namespace slam

@@ -732,6 +732,12 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
         if(sl.depth) cudaFree(sl.depth);
         if(sl.ready) cudaEventDestroy(sl.ready);
     }
+    if(h->batch >= kBatchEngineMin)
+    {
+        batch_report();
+        for(auto st : h->be.side) cudaStreamSynchronize(st);
+        batch_release(h->be);
+    }
     gn_release(h->gn);
     if(h->arena) cudaFree(h->arena);
     if(h->h_results) cudaFreeHost(h->h_results);
