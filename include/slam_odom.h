@@ -185,6 +185,15 @@ typedef struct slam_step_record
 int slam_odom_set_trace(slam_odom_t h, int enable);
 int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_records, int * n_records);
 
+/* Relocalisation scoring (BASELINE.json configs[4]; the acceptance test of lc/Ferns.cpp:253-268 reads the same two numbers
+ * after a full track): score n candidate poses of the CURRENT frame (row-major rot9, trans3 each) against the model
+ * prediction prepared by init_icp_model + init_icp_depth/maps, at pyramid level `level`, in one launch.  prev_trans3 /
+ * prev_rot9 = the pose the model maps were predicted at.  Per hypothesis: residual[i] = sum of squared point-to-plane
+ * distances over the inliers of icpStep's association (JtJJtrSE3::residual, cuda/types.cuh:79-92), count[i] = inliers;
+ * the reference's lastICPError is sqrt(residual) / count.  Host output arrays; synchronises the handle's stream. */
+int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
+                          const float * rot9n, float * residual_n, float * count_n);
+
 /* Kernel-launch counter (for bench.py's gpu_launches). */
 long long slam_odom_launch_count(slam_odom_t h);
 /* CUDA-event timing of the Gauss-Newton reduction kernels on the handle's stream: enable, run, then read the

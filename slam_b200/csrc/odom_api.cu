@@ -59,6 +59,8 @@ struct slam_odom
     size_t arena_bytes = 0;
     std::vector<SeqBuffers> seq;
     size_t seq_stride = 0;            // bytes between the buffers of consecutive sequences in the arena
+    char * score_ws = nullptr;        // pose-hypothesis scoring: poses | partials | tickets | results (grown on demand)
+    size_t score_ws_bytes = 0;
     float * d_poses12 = nullptr;      // [batch][12] model poses (R row-major | t) of the batched preparation launches
     float * h_poses12 = nullptr;      // pinned staging of the same
 
@@ -743,6 +745,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->h_results) cudaFreeHost(h->h_results);
     if(h->h_sums) cudaFreeHost(h->h_sums);
     if(h->h_poses12) cudaFreeHost(h->h_poses12);
+    if(h->score_ws) cudaFree(h->score_ws);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if(h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -990,6 +993,64 @@ extern "C" int slam_odom_get_stats(slam_odom_t h, slam_odom_stats * stats)
     if(h->pending_async)
         if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
     for(int b = 0; b < h->batch; b++) stats[b] = h->stats[b];
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
+                                     const float * rot9n, float * residual_n, float * count_n)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && level >= 0 && level < h->levels && n > 0 && n <= 65535);
+    SLAM_ARG_CHECK(prev_trans3 && prev_rot9 && trans3n && rot9n && residual_n && count_n);
+    if(int rc = set_device(h)) return rc;
+    if(h->pending_async)
+        if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    const LevelGeom & g = h->geom[level];
+    const int plane = g.rows * g.cols;
+    const size_t pose_bytes = align_up((size_t)n * 12 * 4, 256);
+    const size_t need = pose_bytes + score_workspace_bytes(n, plane);
+    if(need > h->score_ws_bytes)
+    {
+        SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if(h->score_ws) cudaFree(h->score_ws);
+        h->score_ws = nullptr;
+        h->score_ws_bytes = 0;
+        SLAM_CUDA_TRY(cudaMalloc((void **)&h->score_ws, need));
+        h->score_ws_bytes = need;
+    }
+    // the layout of the workspace depends on n: tickets must start at zero
+    SLAM_CUDA_TRY(cudaMemsetAsync(h->score_ws, 0, need, h->stream));
+    std::vector<float> poses((size_t)n * 12);
+    for(int i = 0; i < n; i++)
+    {
+        memcpy(&poses[(size_t)i * 12], rot9n + (size_t)i * 9, 9 * sizeof(float));
+        memcpy(&poses[(size_t)i * 12 + 9], trans3n + (size_t)i * 3, 3 * sizeof(float));
+    }
+    SLAM_CUDA_TRY(cudaMemcpyAsync(h->score_ws, poses.data(), (size_t)n * 12 * 4, cudaMemcpyHostToDevice, h->stream));
+    SeqBuffers & s = h->seq[seq];
+    float Rprev_inv[9];
+    smath::mat3_inverse(prev_rot9, Rprev_inv);
+    IcpArgs a;
+    a.Rcurr = mat3_from(prev_rot9);
+    a.tcurr = make_float3(prev_trans3[0], prev_trans3[1], prev_trans3[2]);
+    a.Rprev_inv = mat3_from(Rprev_inv);
+    a.tprev = make_float3(prev_trans3[0], prev_trans3[1], prev_trans3[2]);
+    a.fx = g.fx; a.fy = g.fy; a.cx = g.cx; a.cy = g.cy;
+    a.distThres = h->p.dist_thresh;
+    a.angleThres = h->p.angle_thresh;
+    a.cols = g.cols; a.rows = g.rows;
+    a.vcurr = s.vcurr[level]; a.ncurr = s.ncurr[level]; a.vprev = s.vprev[level]; a.nprev = s.nprev[level];
+    float * out2 = nullptr;
+    if(int rc = launch_score_poses(a, reinterpret_cast<const float *>(h->score_ws), n, h->score_ws + pose_bytes, &out2, h->stream)) return rc;
+    h->launches++;
+    std::vector<float> out((size_t)n * 2);
+    SLAM_CUDA_TRY(cudaMemcpyAsync(out.data(), out2, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for(int i = 0; i < n; i++)
+    {
+        residual_n[i] = out[2 * i];
+        count_n[i] = out[2 * i + 1];
+    }
     return SLAM_OK;
 }
 

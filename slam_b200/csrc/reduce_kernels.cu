@@ -147,6 +147,83 @@ int launch_icp_step(const IcpArgs & a, void * workspace, float * out29, cudaStre
     return SLAM_OK;
 }
 
+// ---------------------------------------------------------------- pose-hypothesis scoring (BASELINE.json configs[4])
+// One launch scores n candidate poses of the current frame against the model prediction: for each hypothesis the ICP
+// association of every pixel (reduce.cu:257-345, same arithmetic as icpStep) and the two sums the reference's acceptance
+// test reads, residual = sum of squared point-to-plane distances (JtJJtrSE3::residual) and the inlier count.
+// grid = (pixel blocks, hypotheses); the maps are shared by all hypotheses and stay in L2.  Per-hypothesis last-ticket fold
+// in block order: deterministic.
+constexpr int kScoreStride = 2;
+__global__ void __launch_bounds__(kReduceThreads) k_score_poses(const IcpArgs a0, const float * __restrict__ poses12, float * partials, unsigned * tickets,
+                                                                float * out2)
+{
+    __shared__ float s_red[2][kReduceThreads / 32];
+    __shared__ int s_last;
+    const int hyp = blockIdx.y;
+    IcpArgs a = a0;
+    const float * q = poses12 + 12 * hyp;
+    a.Rcurr.r0 = make_float3(__ldg(q + 0), __ldg(q + 1), __ldg(q + 2));
+    a.Rcurr.r1 = make_float3(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+    a.Rcurr.r2 = make_float3(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+    a.tcurr = make_float3(__ldg(q + 9), __ldg(q + 10), __ldg(q + 11));
+    const int plane = a.rows * a.cols;
+    float res = 0.f, cnt = 0.f;
+    for(int k = blockIdx.x * blockDim.x + threadIdx.x; k < plane; k += gridDim.x * blockDim.x)
+    {
+        float row[7];
+        const bool found = icp_pixel(a, make_float3(__ldg(a.vcurr + k), __ldg(a.vcurr + plane + k), __ldg(a.vcurr + 2 * plane + k)),
+                                     make_float3(__ldg(a.ncurr + k), __ldg(a.ncurr + plane + k), __ldg(a.ncurr + 2 * plane + k)), row);
+        res += row[6] * row[6];
+        cnt += found ? 1.f : 0.f;
+    }
+    res = warp_sum(res);
+    cnt = warp_sum(cnt);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if(lane == 0)
+    {
+        s_red[0][wid] = res;
+        s_red[1][wid] = cnt;
+    }
+    __syncthreads();
+    float * rows = partials + (size_t)hyp * gridDim.x * kScoreStride;
+    if(threadIdx.x < 2)
+    {
+        float t = 0.f;
+        for(int w = 0; w < kReduceThreads / 32; w++) t += s_red[threadIdx.x][w];
+        rows[blockIdx.x * kScoreStride + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if(threadIdx.x == 0) s_last = (atomicAdd(tickets + hyp, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if(!s_last) return;
+    __threadfence();
+    if(threadIdx.x < 2)
+    {
+        float t = 0.f;
+        for(int b = 0; b < (int)gridDim.x; b++) t += __ldcg(rows + b * kScoreStride + threadIdx.x);
+        out2[hyp * 2 + threadIdx.x] = t;
+    }
+    if(threadIdx.x == 0) tickets[hyp] = 0u;
+}
+
+int score_blocks(int plane) { int g = div_up(plane, kReduceThreads * 4); return g < 1 ? 1 : (g > 64 ? 64 : g); }
+
+size_t score_workspace_bytes(int n, int plane) { return (size_t)n * score_blocks(plane) * kScoreStride * 4 + (size_t)n * 4 + (size_t)n * 8 + 256; }
+
+int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * workspace, float ** out2_dev, cudaStream_t s)
+{
+    const int plane = a.rows * a.cols;
+    const int nb = score_blocks(plane);
+    float * partials = reinterpret_cast<float *>(workspace);
+    unsigned * tickets = reinterpret_cast<unsigned *>(partials + (size_t)n * nb * kScoreStride);
+    float * out2 = reinterpret_cast<float *>(tickets + n);
+    k_score_poses<<<dim3(nb, n), kReduceThreads, 0, s>>>(a, poses12, partials, tickets, out2);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    *out2_dev = out2;
+    return SLAM_OK;
+}
+
 int launch_rgb_residual(const ResidualArgs & a, Corres * corres, void * workspace, int * out2, cudaStream_t s)
 {
     k_rgb_residual<<<reduce_grid(a.rows * a.cols), kReduceThreads, 0, s>>>(a, corres, workspace, out2);

@@ -120,6 +120,7 @@ def load_library():
     lib.slam_odom_get_trace.argtypes = [vp, i, C.POINTER(StepRecord), i, C.POINTER(i)]
     lib.slam_odom_launch_count.argtypes = [vp]
     lib.slam_odom_launch_count.restype = C.c_longlong
+    lib.slam_odom_score_poses.argtypes = [vp, i, i, i, fp, fp, fp, fp, fp, fp]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
     lib.slam_odom_stream.argtypes = [vp]
@@ -296,6 +297,20 @@ class RGBDOdometry:
         n = C.c_int(0)
         _check(self.lib, self.lib.slam_odom_get_trace(self._h, seq, arr, 64, C.byref(n)))
         return [arr[k].as_dict() for k in range(min(n.value, 64))]
+
+    def score_poses(self, level, prev_pose, trans_n, rot_n, seq=0):
+        """Score n candidate poses of the current frame against the prepared model prediction (slam_odom_score_poses):
+        -> (residual[n] = sum of squared point-to-plane distances, count[n] = inliers)."""
+        prev = np.ascontiguousarray(prev_pose, dtype=np.float32)
+        pt = np.ascontiguousarray(prev[:3, 3]).copy()
+        pr = np.ascontiguousarray(prev[:3, :3]).reshape(-1).copy()
+        t = np.ascontiguousarray(trans_n, dtype=np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(rot_n, dtype=np.float32).reshape(-1, 9)
+        assert len(t) == len(r)
+        res = np.zeros(len(t), np.float32)
+        cnt = np.zeros(len(t), np.float32)
+        _check(self.lib, self.lib.slam_odom_score_poses(self._h, int(seq), int(level), len(t), _fptr(pt), _fptr(pr), _fptr(t), _fptr(r), _fptr(res), _fptr(cnt)))
+        return res, cnt
 
     def set_profiling(self, on=True):
         _check(self.lib, self.lib.slam_odom_set_profiling(self._h, int(on)))

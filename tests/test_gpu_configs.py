@@ -1,0 +1,204 @@
+"""BASELINE.json configs[2]: 1280x720 RealSense-shaped depth, 4-level pyramid, ICP-only tracking with 10/5/4/4 iterations.
+
+The reference is compiled for three levels (NUM_PYRS, RGBDOdometryef.h:75), so parity is pinned in two steps:
+  * at 1280x720 with three levels the whole tracker is compared with the reference replay (prepared maps bit-exact, pose);
+  * the fourth level's buffers are compared with the reference's own per-level operators (pyrDown, createVMap,
+    createNMap, resizeVMap / resizeNMap, tranformMaps) applied once more, and the 4-level device-resident loop is compared
+    with the host-stepped loop (which launches the operator kernels the other tests pin) and with the ground truth.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.support import DEPTH_CUTOFF, MODEL_CUTOFF, frame_pair, make_scene, planar_map_mismatch, run_frame, to_device
+
+pytestmark = pytest.mark.gpu
+
+W, H = 1280, 720
+ITER4 = (10, 5, 4, 4)
+
+
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+@pytest.fixture(scope="module")
+def hd(built, ref_lib):
+    import torch
+    from oracle.ref_cuda import RefOdometry
+    from slam_b200 import RGBDOdometry
+    scene, intr = make_scene(W, H)
+    poses = scene.trajectory(1000)
+    fr = frame_pair(scene, poses, 200)
+    d = to_device(fr)
+    torch.cuda.synchronize()
+    return dict(torch=torch, scene=scene, intr=intr, poses=poses, fr=fr, d=d, Ref=RefOdometry, Odo=RGBDOdometry, ref=ref_lib)
+
+
+def test_720p_three_levels_match_reference(hd):
+    from slam_b200 import Tap
+    i = hd["intr"]
+    mine = hd["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    mine.set_trace(1)
+    ref = hd["Ref"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    kw = dict(so3=False, rgbOnly=False, icpWeight=100.0, pyramid=True, fastOdom=False)
+    tm, rm = run_frame(mine, hd["d"], **kw)
+    tr, rr = run_frame(ref, hd["d"], **kw)
+    for level in range(3):
+        for tap in (Tap.VMAP_CURR, Tap.NMAP_CURR, Tap.VMAP_PREV, Tap.NMAP_PREV):
+            nan_diff, val_diff = planar_map_mismatch(mine.tap(tap, level), ref.tap(tap, level))
+            assert nan_diff == 0 and val_diff == 0, f"tap {tap} level {level}: nan {nan_diff} values {val_diff}"
+    assert np.abs(tm - tr).max() < 1e-5 and np.abs(rm - rr).max() < 1e-5
+    sm, sr = mine.stats(), ref.stats()
+    assert abs(sm.lastICPCount - sr.lastICPCount) <= max(8, 2e-3 * sr.lastICPCount)
+    gt = hd["fr"]["gt_pose"]
+    assert np.linalg.norm(tm - gt[:3, 3]) < 0.002
+    mine.close()
+    ref.close()
+
+
+def reference_level3_maps(hd, taps2):
+    """Level-3 buffers from the level-2 taps with the reference's own operators."""
+    torch, ref = hd["torch"], hd["ref"]
+    dev = "cuda:0"
+    i = hd["intr"]
+    h2, w2 = H >> 2, W >> 2
+    h3, w3 = h2 // 2, w2 // 2
+    out = {}
+    d2 = torch.from_numpy(taps2["depth"].view(np.int16)).to(dev)
+    d3 = torch.zeros((h3, w3), dtype=torch.int16, device=dev)
+    ref.ref_op_pyr_down(d2.data_ptr(), h2, w2, d3.data_ptr())
+    fx, fy, cx, cy = (float(np.float32(i[k]) / np.float32(8.0)) for k in ("fx", "fy", "cx", "cy"))
+    v3 = torch.full((3, h3, w3), float("nan"), dtype=torch.float32, device=dev)
+    n3 = torch.full((3, h3, w3), float("nan"), dtype=torch.float32, device=dev)
+    ref.ref_op_create_vmap(fx, fy, cx, cy, d3.data_ptr(), h3, w3, v3.data_ptr(), DEPTH_CUTOFF, 1)
+    ref.ref_op_create_nmap(v3.data_ptr(), h3, w3, n3.data_ptr(), 1)
+    torch.cuda.synchronize()
+    out["depth"], out["vcurr"], out["ncurr"] = d3.cpu().numpy().view(np.uint16), v3.cpu().numpy(), n3.cpu().numpy()
+    # model maps: camera-frame pyramid from the RGBA32F inputs, then one more resize, then the transform
+    d = hd["d"]
+    v = torch.full((3, H, W), float("nan"), dtype=torch.float32, device=dev)
+    n = torch.full((3, H, W), float("nan"), dtype=torch.float32, device=dev)
+    ref.ref_op_copy_maps(d["mv"].data_ptr(), d["mn"].data_ptr(), H, W, v.data_ptr(), n.data_ptr())
+    for l in range(1, 4):
+        h, w = H >> l, W >> l
+        v2 = torch.full((3, h, w), float("nan"), dtype=torch.float32, device=dev)
+        n2 = torch.full((3, h, w), float("nan"), dtype=torch.float32, device=dev)
+        ref.ref_op_resize_map(v.data_ptr(), h * 2, w * 2, v2.data_ptr(), 0)
+        ref.ref_op_resize_map(n.data_ptr(), h * 2, w * 2, n2.data_ptr(), 1)
+        v, n = v2, n2
+    pose = hd["fr"]["model_pose"]
+    R = np.ascontiguousarray(pose[:3, :3], dtype=np.float32).reshape(-1)
+    t = np.ascontiguousarray(pose[:3, 3], dtype=np.float32)
+    vg, ng = v.clone(), n.clone()
+    ref.ref_op_transform_maps(v.data_ptr(), n.data_ptr(), h3, w3, fp(R), fp(t), vg.data_ptr(), ng.data_ptr())
+    torch.cuda.synchronize()
+    out["vprev"], out["nprev"] = vg.cpu().numpy(), ng.cpu().numpy()
+    return out
+
+
+def test_720p_four_levels(hd):
+    from slam_b200 import Tap
+    i = hd["intr"]
+    kw = dict(so3=False, rgbOnly=False, icpWeight=100.0, pyramid=True, fastOdom=False)
+    host = hd["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], num_levels=4, iterations=ITER4, host_loop=True)
+    host.set_trace(True)
+    th, rh = run_frame(host, hd["d"], **kw)
+    # ---- the fourth level's prepared buffers against the reference's operators
+    taps2 = dict(depth=host.tap(Tap.DEPTH_U16, 2))
+    want = reference_level3_maps(hd, taps2)
+    assert np.array_equal(host.tap(Tap.DEPTH_U16, 3), want["depth"])
+    for tap, key in ((Tap.VMAP_CURR, "vcurr"), (Tap.NMAP_CURR, "ncurr"), (Tap.VMAP_PREV, "vprev"), (Tap.NMAP_PREV, "nprev")):
+        nan_diff, val_diff = planar_map_mismatch(host.tap(tap, 3), want[key])
+        assert nan_diff == 0 and val_diff == 0, f"{key} level 3: nan {nan_diff} values {val_diff}"
+    trh = host.get_trace()
+    assert [r["level"] for r in trh] == [3] * 4 + [2] * 4 + [1] * 5 + [0] * 10
+    # ---- device-resident 4-level loop == host-stepped loop
+    devo = hd["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], num_levels=4, iterations=ITER4)
+    devo.set_trace(1)
+    td, rd = run_frame(devo, hd["d"], **kw)
+    trd = devo.get_trace()
+    assert len(trd) == len(trh)
+    assert trd[0]["icp"][28] == trh[0]["icp"][28]          # first step: same inlier mask
+    assert np.abs(td - th).max() < 1e-5 and np.abs(rd - rh).max() < 1e-5
+    gt = hd["fr"]["gt_pose"]
+    assert np.linalg.norm(td - gt[:3, 3]) < 0.002
+    # ---- and the one-call-per-frame entry point (fast path, no trace)
+    fast = hd["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], num_levels=4, iterations=ITER4)
+    d = hd["d"]
+    frame = fast.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], d["model_pose"], DEPTH_CUTOFF, MODEL_CUTOFF)
+    pose = d["model_pose"]
+    tf, rf = fast.track_device(frame, pose[:3, 3].copy(), pose[:3, :3].copy(), False, 100.0, True, False, False)
+    assert np.array_equal(tf, td) and np.array_equal(rf, rd)
+    for o in (host, devo, fast):
+        o.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: relocalisation scoring, 256 pose hypotheses per frame, each scored by the ICP residual
+# reduction; here on one GPU (the sharding + min-allreduce logic is covered on CPU by tests/test_synth_and_sharding.py).
+def perturbed_poses(pose, n, seed=7):
+    """n candidate poses around `pose`: hypothesis 0 is the pose itself, the others are displaced by 5 .. 60 mm / up to 3 deg."""
+    def rodrigues_np(w):
+        th = np.linalg.norm(w)
+        if th < 1e-12:
+            return np.eye(3)
+        k = w / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+    rng = np.random.default_rng(seed)
+    T = np.repeat(pose[:3, 3][None].astype(np.float32), n, 0)
+    R = np.repeat(pose[:3, :3][None].astype(np.float32), n, 0)
+    for k in range(1, n):
+        d = rng.normal(size=3)
+        T[k] += (d / np.linalg.norm(d) * rng.uniform(0.005, 0.06)).astype(np.float32)
+        w = rng.normal(size=3)
+        w = w / np.linalg.norm(w) * np.deg2rad(rng.uniform(0.0, 3.0))
+        R[k] = (rodrigues_np(w) @ pose[:3, :3]).astype(np.float32)
+    return T, R
+
+
+def test_pose_hypothesis_scores_match_reference_icp_step(built, ref_lib, icl_sequence):
+    import torch
+    from slam_b200 import RGBDOdometry, Tap
+    from slam_b200.relocalise import icp_error, score_sharded
+    from tests.support import ANGLE_THRESH
+    scene, intr, poses = icl_sequence
+    fr = frame_pair(scene, poses, 500)
+    d = to_device(fr)
+    torch.cuda.synchronize()
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    odo.set_trace(1)   # keeps the prepared maps readable through the taps
+    odo.initICPModel(d["mv"], d["mn"], MODEL_CUTOFF, d["model_pose"])
+    odo.initICP(d["depth"], DEPTH_CUTOFF)
+    model = fr["model_pose"].astype(np.float32)
+    N = 256
+    T, R = perturbed_poses(fr["gt_pose"].astype(np.float32), N)
+    for level in (2, 0):
+        res, cnt = odo.score_poses(level, model, T, R)
+        assert res.shape == (N,) and np.all(cnt > 0)
+        # ---- the reference's icpStep on the same maps, same poses (a sample of the hypotheses)
+        h, w = 480 >> level, 640 >> level
+        div = np.float32(1 << level)
+        fx, fy, cx, cy = (float(np.float32(intr[k]) / div) for k in ("fx", "fy", "cx", "cy"))
+        maps = [torch.from_numpy(odo.tap(t, level)).to("cuda:0") for t in (Tap.VMAP_CURR, Tap.NMAP_CURR, Tap.VMAP_PREV, Tap.NMAP_PREV)]
+        Rprev_inv = np.linalg.inv(model[:3, :3].astype(np.float64)).astype(np.float32)
+        tprev = model[:3, 3].copy()
+        for k in (0, 1, 17, 100, 255):
+            host = np.zeros(32, dtype=np.float32)
+            ref_lib.ref_op_icp_step(fp(np.ascontiguousarray(R[k].reshape(-1))), fp(np.ascontiguousarray(T[k])), maps[0].data_ptr(), maps[1].data_ptr(),
+                                    fp(np.ascontiguousarray(Rprev_inv.reshape(-1))), fp(tprev), fx, fy, cx, cy, maps[2].data_ptr(), maps[3].data_ptr(), 0.10,
+                                    float(np.float32(ANGLE_THRESH)), h, w, fp(host))
+            assert cnt[k] == host[28], f"level {level} hypothesis {k}: inliers {cnt[k]} vs {host[28]}"
+            assert abs(res[k] - host[27]) <= 1e-4 * abs(host[27]), f"level {level} hypothesis {k}: residual {res[k]} vs {host[27]}"
+        # ---- the unperturbed pose wins, and the error grows with the displacement
+        err = icp_error(res, cnt, min_inliers=0.2 * h * w)
+        best, e, _ = score_sharded(odo, level, model, T, R, min_inliers=0.2 * h * w)
+        assert best == int(np.argmin(err)) and abs(e - err.min()) < 1e-12
+        assert best == 0, f"level {level}: hypothesis {best} beats the true pose ({err[best]} vs {err[0]})"
+        # deterministic run to run
+        res2, cnt2 = odo.score_poses(level, model, T, R)
+        assert np.array_equal(res, res2) and np.array_equal(cnt, cnt2)
+    odo.close()

@@ -106,3 +106,73 @@ def test_reference_arm_prints_contract_line(built):
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_relocalise_key_packing_orders_like_error_then_index():
+    from slam_b200.relocalise import icp_error, pack_keys, shard_range, unpack_key
+    rng = np.random.default_rng(3)
+    err = rng.uniform(0, 1e-2, 1000).astype(np.float32)
+    err[10] = err[700]                      # a tie: the smaller index must win
+    err[5] = np.inf
+    keys = pack_keys(err, np.arange(1000))
+    order = np.argsort(keys, kind="stable")
+    want = np.lexsort((np.arange(1000), err))
+    assert np.array_equal(order, want)
+    e, i = unpack_key(keys.min())
+    assert i == int(want[0]) and e == float(err[want[0]])
+    assert unpack_key(pack_keys(np.array([np.inf], np.float32), np.array([123456]))[0]) == (float("inf"), 123456)
+    # error definition: sqrt(residual) / count, +inf below the inlier threshold or for empty sets
+    got = icp_error(np.array([4.0, 1.0, 0.0], np.float32), np.array([100.0, 5.0, 0.0], np.float32), min_inliers=10)
+    assert got[0] == np.float32(0.02) and np.isinf(got[1]) and np.isinf(got[2])
+    # shards tile the hypothesis range for any world size
+    for world in (1, 2, 3, 8):
+        cover = [shard_range(256, r, world) for r in range(world)]
+        assert cover[0][0] == 0 and cover[-1][1] == 256 and all(cover[k][1] == cover[k + 1][0] for k in range(world - 1))
+
+
+RELOC_WORKER = r'''
+import json, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+import numpy as np
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+from slam_b200.relocalise import score_sharded, icp_error
+
+class FakeScorer:
+    """Stands in for RGBDOdometry.score_poses on a machine without a GPU: residual / count are a deterministic function
+    of the pose, identical on every rank (as the real scores are: every rank holds the same frame)."""
+    def score_poses(self, level, prev_pose, trans_n, rot_n, seq=0):
+        d = np.linalg.norm(np.asarray(trans_n, np.float32) - np.float32([0.1, 0.2, 0.3]), axis=1)
+        count = np.where(d < 0.12, 5000.0, 3.0).astype(np.float32)      # far hypotheses lose their inliers
+        return (count * (1e-3 + d) ** 2).astype(np.float32), count
+
+rng = np.random.default_rng(11)
+T = (np.float32([0.1, 0.2, 0.3]) + rng.normal(scale=0.05, size=(257, 3))).astype(np.float32)
+T[200] = [0.1, 0.2, 0.3005]
+T[41] = [0.1, 0.2, 0.3005]      # same error as 200: the smaller index wins on every world size
+R = np.repeat(np.eye(3, dtype=np.float32)[None], 257, 0)
+best, err, local = score_sharded(FakeScorer(), 2, np.eye(4, dtype=np.float32), T, R, rank, world, min_inliers=10)
+res, cnt = FakeScorer().score_poses(2, None, T, R)
+full = icp_error(res, cnt, 10)
+if rank == 0:
+    print(json.dumps({"best": best, "err": err, "want": int(np.lexsort((np.arange(257), full))[0]), "want_err": float(full.min()), "local": len(local)}))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_relocalisation_min_allreduce_gloo(built, tmp_path):
+    import json
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "reloc_worker.py"
+    script.write_text(RELOC_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                          str(port), str(script), str(ROOT)], capture_output=True, text=True, timeout=280, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["best"] == res["want"] == 41 and res["err"] == res["want_err"]
+    assert res["local"] == 128      # rank 0 scored its half of the 257 hypotheses

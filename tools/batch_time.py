@@ -1,5 +1,5 @@
 """Throughput of the tracker for batches of independent sequences on one GPU (development aid)."""
-import sys, time
+import os, sys, time
 from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -32,7 +32,9 @@ for B in [int(x) for x in (sys.argv[1:] or ["1", "2", "4", "8", "16", "32", "64"
     odo.initFirstRGB(firstB)
     def step(i):
         d, P, fr = sets[i % 2]
-        return odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+        m = os.environ.get('SLAM_MODE', 'full')
+        kw = dict(icpWeight=100.0, so3=False) if m == 'icp' else dict(rgbOnly=True, so3=False) if m == 'rgb' else {}
+        return odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy(), **kw)
     for i in range(4):
         out = step(i)
     torch.cuda.synchronize()
