@@ -344,6 +344,13 @@ def run_ours(args, rank, local_rank, world):
         except Exception as e:   # pragma: no cover
             batched = {"value": None, "note": f"failed: {e}"}
 
+    extras = None
+    if not args.no_batched:
+        try:
+            extras = run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barrier, max_over_ranks)
+        except Exception as e:   # pragma: no cover
+            extras = {"note": f"failed: {e}"}
+
     line = None
     if rank == 0:
         # ---- context baselines (N = 1 only): CPU port and the reference's own CUDA path
@@ -400,6 +407,7 @@ def run_ours(args, rank, local_rank, world):
                          "note": "one launch = all SO3 + 19 ICP/RGB iterations of a frame; the 45 MB working set stays in the 126 MB L2, so DRAM traffic is far "
                                  "below the algorithmic bytes and the kernel is latency-bound (grid barriers + fp64 solves), not bandwidth-bound"},
             "batched": batched,
+            "other_configs": extras,
             "cpu_baseline": cpu,
             "ref_cuda": ref_cuda,
             "clocks": clocks,
@@ -508,6 +516,74 @@ def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames,
                              "move less (compacted correspondences, candidate masks), see DESIGN.md"},
         "check": {"max_frame_error_mm": err_mm},
     }
+
+
+def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barrier, max_over_ranks):
+    """Short measurements of the remaining BASELINE.json configurations (their parity tests are tests/test_gpu_configs.py).
+
+    configs[4]: 256 pose hypotheses per frame scored by the ICP residual reduction, 256 / N per GPU, best pose by one NCCL
+                min-allreduce of packed 64-bit keys (slam_b200/relocalise.py);
+    configs[2]: 1280x720, 4-level pyramid, ICP only, 10/5/4/4 iterations (rank 0, N = 1 only)."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    from slam_b200.relocalise import score_sharded
+    dev = f"cuda:{local_rank}"
+    out = {}
+    # ---- configs[4]
+    d = dframes[3]
+    fr = frames[3]
+    odo.initICPModel(d["mv"], d["mn"], MODEL_CUTOFF, d["model_pose"])
+    odo.initICP(d["depth"], DEPTH_CUTOFF)
+    rng = np.random.default_rng(5)
+    n_hyp = 256
+    T = (fr["gt_pose"][:3, 3][None] + rng.normal(scale=0.02, size=(n_hyp, 3))).astype(np.float32)
+    T[0] = fr["gt_pose"][:3, 3]
+    R = np.repeat(fr["gt_pose"][:3, :3][None].astype(np.float32), n_hyp, 0)
+    model = fr["model_pose"].astype(np.float32)
+    for level in (0, 2):
+        for _ in range(3):
+            best, err, _ = score_sharded(odo, level, model, T, R, rank, world, min_inliers=1000 >> (2 * level), device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            best, err, _ = score_sharded(odo, level, model, T, R, rank, world, min_inliers=1000 >> (2 * level), device=dev)
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
+        out[f"configs[4] level {level}"] = {"hypotheses": n_hyp, "per_gpu": n_hyp // world, "ms_per_frame": ms, "hypotheses_per_s": n_hyp / (ms * 1e-3),
+                                            "best_index": best, "best_error": err, "collective": "1 min-allreduce (int64)" if world > 1 else "none"}
+    # ---- configs[2]
+    if world == 1:
+        from slam_b200.synth import Scene
+        W2, H2 = 1280, 720
+        sc = W2 / 640.0
+        scene = Scene(width=W2, height=H2, fx=481.20 * sc, fy=-480.0 * sc, cx=(319.5 + 0.5) * sc - 0.5, cy=(239.5 + 0.5) * sc - 0.5, seed=0x51A7)
+        poses = scene.trajectory(1000, seed=0x51A7)
+        hd = RGBDOdometry(W2, H2, (319.5 + 0.5) * sc - 0.5, (239.5 + 0.5) * sc - 0.5, 481.20 * sc, -480.0 * sc, num_levels=4, iterations=(10, 5, 4, 4), device=local_rank)
+        fl = []
+        for i in range(8):
+            k = 50 + 100 * i
+            depth, rgba = scene.render_frame(poses[k])
+            mv, mn, mrgba = scene.render_model(poses[k - 1])
+            t = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).to(dev)
+            dd = dict(depth=t(depth), rgba=t(rgba), mv=t(mv), mn=t(mn), mrgba=t(mrgba))
+            P = poses[k - 1].astype(np.float32)
+            fl.append((dd, P, hd.make_frame(dd["depth"], dd["rgba"], dd["mv"], dd["mn"], dd["mrgba"], P, DEPTH_CUTOFF, MODEL_CUTOFF), poses[k][:3, 3]))
+        torch.cuda.synchronize()
+        run = lambda i: hd.track_device(fl[i % 8][2], fl[i % 8][1][:3, 3].copy(), fl[i % 8][1][:3, :3].copy(), False, 100.0, True, False, False)
+        for i in range(5):
+            run(i)
+        torch.cuda.synchronize()
+        n2 = 100
+        t0 = time.perf_counter()
+        for i in range(n2):
+            last = run(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["configs[2] 1280x720 4-level ICP-only"] = {"frames_per_s": n2 / dt, "ms_per_frame": dt / n2 * 1e3,
+                                                        "last_frame_error_mm": float(np.linalg.norm(last[0] - fl[(n2 - 1) % 8][3]) * 1e3)}
+        hd.close()
+    return out
 
 
 def main():
