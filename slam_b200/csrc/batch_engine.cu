@@ -494,6 +494,8 @@ constexpr int kL2Ahead = 2;
 struct WarpStage
 {
     float f[7][kTripPx];            // vcurr x,y,z  ncurr x,y,z  nextDepth
+    short gx[kTripPx], gy[kTripPx];   // dIdx, dIdy at the pixel itself (needed only for accepted correspondences, but a
+                                      // dependent global round trip after the acceptance test would cost more than 4 B/px)
     unsigned char cand[kTripPx];
     unsigned char img[kTripPx];
 };
@@ -502,6 +504,10 @@ constexpr int kStagedSmem = (kBThreads / 32) * kStages * (int)sizeof(WarpStage);
 __device__ __forceinline__ void cp_async16(void * smem, const void * gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void * smem, const void * gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async4(void * smem, const void * gmem)
 {
@@ -597,6 +603,8 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                     cp_async16(&S.f[6][lane * 4], ra.nextDepth + p);
                     cp_async4(&S.cand[lane * 4], cand + p);
                     cp_async4(&S.img[lane * 4], ra.nextImage + p);
+                    cp_async8(&S.gx[lane * 4], ra.dIdx + p);
+                    cp_async8(&S.gy[lane * 4], ra.dIdy + p);
                 }
             }
         }
@@ -723,7 +731,7 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                         cc.d0 = d0[c];
                         cc.diff = __fsub_rn(static_cast<float>((im >> (8 * c)) & 0xff), static_cast<float>(li[c]));
                         const int k = p + c;
-                        cc.gxy = (int)(unsigned short)__ldg(ra.dIdx + k) | ((int)__ldg(ra.dIdy + k) << 16);
+                        cc.gxy = (int)(unsigned short)S.gx[q0 + c] | ((int)S.gy[q0 + c] << 16);
                         cnt0 += 1;
                         cnt1 += (int)(cc.diff * cc.diff);
                         reinterpret_cast<int4 *>(cimg)[w0 + wcount + __popc(m & ((1u << lane) - 1u))] = *reinterpret_cast<const int4 *>(&cc);
