@@ -489,17 +489,7 @@ kb_phase_a(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
 // their use, so the only exposed latency of a trip is the gathers'.  One pipeline per warp (a trip = kTripPx contiguous
 // pixels of the warp's chunk, consumed as two half trips of 2 pixels per lane); no block-level synchronisation.
 constexpr int kTripPx = 128;
-constexpr int kStages = 3;
 constexpr int kL2Ahead = 2;
-struct WarpStage
-{
-    float f[7][kTripPx];            // vcurr x,y,z  ncurr x,y,z  nextDepth
-    short gx[kTripPx], gy[kTripPx];   // dIdx, dIdy at the pixel itself (needed only for accepted correspondences, but a
-                                      // dependent global round trip after the acceptance test would cost more than 4 B/px)
-    unsigned char cand[kTripPx];
-    unsigned char img[kTripPx];
-};
-constexpr int kStagedSmem = (kBThreads / 32) * kStages * (int)sizeof(WarpStage);
 
 __device__ __forceinline__ void cp_async16(void * smem, const void * gmem)
 {
@@ -522,12 +512,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kBThreads, 2)
+// Roles: <true, true> does both halves of phase A in one pass; <true, false> and <false, true> are the ICP and the RGB
+// association as separate launches with their own register budgets (80 / 64 registers, 3 / 4 blocks per SM instead of 128 / 2):
+// run on two streams they fill each other's stalls (both are bound by gather round trips, not by issue slots or bandwidth).
+template <bool kIcp, bool kRgb>
+struct RoleCfg
+{
+    static constexpr int kStagesR = (kIcp && kRgb) ? 3 : (kIcp ? 3 : 4);
+    static constexpr int kStageBytes = (kIcp ? 6 * kTripPx * 4 : 0) + (kRgb ? kTripPx * 4 + 2 * kTripPx * 2 + 2 * kTripPx : 0);
+    static constexpr int kMinBlocks = (kIcp && kRgb) ? 2 : (kIcp ? 3 : 4);
+    static constexpr int kSmem = (kBThreads / 32) * kStagesR * kStageBytes;
+};
+
+template <bool kIcp, bool kRgb>
+__global__ void __launch_bounds__(kBThreads, (RoleCfg<kIcp, kRgb>::kMinBlocks))
 kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, float * sums, unsigned char * cand0, size_t aux_stride,
                   size_t cand_off, int lvl)
 {
-    __shared__ GnShared sh;
+    using Cfg = RoleCfg<kIcp, kRgb>;
+    constexpr int kStages = Cfg::kStagesR;
     extern __shared__ __align__(16) char dyn_smem[];
+    static_assert(sizeof(GnShared) <= Cfg::kSmem, "the epilogue scratch aliases the staging buffers");
+    GnShared & sh = *reinterpret_cast<GnShared *>(dyn_smem);   // epilogue only, after every warp is done with its stages
     const int seq = blockIdx.y;
     const GnShared & st = bstate(states, stride, seq);
     if(st.stop_level == lvl) return;
@@ -535,7 +541,19 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
     const LevelGeom g = L.geom[lvl];
     const int plane = g.rows * g.cols;   // a multiple of 4 (checked by the host)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpStage * stages = reinterpret_cast<WarpStage *>(dyn_smem) + wid * kStages;
+    // stage layout of this role: [vcurr xyz | ncurr xyz] (ICP) [nextDepth | dIdx | dIdy | cand | nextImage] (RGB)
+    char * stage0 = dyn_smem + (size_t)wid * kStages * Cfg::kStageBytes;
+    struct StageView
+    {
+        char * base;
+        __device__ float * f(int k) const { return reinterpret_cast<float *>(base) + k * kTripPx; }                                  // k < 6: ICP planes
+        __device__ float * d1() const { return reinterpret_cast<float *>(base + (kIcp ? 6 * kTripPx * 4 : 0)); }
+        __device__ short * gx() const { return reinterpret_cast<short *>(base + (kIcp ? 6 * kTripPx * 4 : 0) + kTripPx * 4); }
+        __device__ short * gy() const { return gx() + kTripPx; }
+        __device__ unsigned char * cand() const { return reinterpret_cast<unsigned char *>(gy() + kTripPx); }
+        __device__ unsigned char * img() const { return cand() + kTripPx; }
+    };
+    auto stage_of = [&](int t) { return StageView{stage0 + (size_t)(t % kStages) * Cfg::kStageBytes}; };
 
     float acc[32];
 #pragma unroll
@@ -578,9 +596,9 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
         if(t >= ntrips) return;
         const int b0 = w0 + t * kTripPx;
         const unsigned npx = (unsigned)min(kTripPx, w1 - b0);
-        if(L.icp && lane < 6) prefetch_l2_bulk((lane < 3 ? ia.vprev + lane * plane : ia.nprev + (lane - 3) * plane) + b0, npx * 4u);
-        if(L.rgb && lane == 6) prefetch_l2_bulk(ra.lastDepth + b0, npx * 4u);
-        if(L.rgb && lane == 7) prefetch_l2_bulk(ra.lastImage + b0, (npx + 15u) & ~15u);
+        if(kIcp && lane < 6) prefetch_l2_bulk((lane < 3 ? ia.vprev + lane * plane : ia.nprev + (lane - 3) * plane) + b0, npx * 4u);
+        if(kRgb && lane == 6) prefetch_l2_bulk(ra.lastDepth + b0, npx * 4u);
+        if(kRgb && lane == 7) prefetch_l2_bulk(ra.lastImage + b0, (npx + 15u) & ~15u);
     };
     auto issue = [&](int t) {
         if(t < ntrips)
@@ -588,23 +606,23 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
             const int p = w0 + t * kTripPx + lane * 4;
             if(p < w1)
             {
-                WarpStage & S = stages[t % kStages];
-                if(L.icp)
+                const StageView S = stage_of(t);
+                if(kIcp)
                 {
 #pragma unroll
                     for(int q = 0; q < 3; q++)
                     {
-                        cp_async16(&S.f[q][lane * 4], ia.vcurr + q * plane + p);
-                        cp_async16(&S.f[3 + q][lane * 4], ia.ncurr + q * plane + p);
+                        cp_async16(S.f(q) + lane * 4, ia.vcurr + q * plane + p);
+                        cp_async16(S.f(3 + q) + lane * 4, ia.ncurr + q * plane + p);
                     }
                 }
-                if(L.rgb)
+                if(kRgb)
                 {
-                    cp_async16(&S.f[6][lane * 4], ra.nextDepth + p);
-                    cp_async4(&S.cand[lane * 4], cand + p);
-                    cp_async4(&S.img[lane * 4], ra.nextImage + p);
-                    cp_async8(&S.gx[lane * 4], ra.dIdx + p);
-                    cp_async8(&S.gy[lane * 4], ra.dIdy + p);
+                    cp_async16(S.d1() + lane * 4, ra.nextDepth + p);
+                    cp_async4(S.cand() + lane * 4, cand + p);
+                    cp_async4(S.img() + lane * 4, ra.nextImage + p);
+                    cp_async8(S.gx() + lane * 4, ra.dIdx + p);
+                    cp_async8(S.gy() + lane * 4, ra.dIdy + p);
                 }
             }
         }
@@ -620,7 +638,7 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
         issue(t + kStages - 1);
         cp_async_wait<kStages - 1>();
         __syncwarp();
-        const WarpStage & S = stages[t % kStages];
+        const StageView S = stage_of(t);
 #pragma unroll 1
         for(int half = 0; half < 2; half++)
         {
@@ -633,19 +651,19 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
             unsigned cm = 0, im = 0;
             if(inside)
             {
-                if(L.icp)
+                if(kIcp)
                 {
-                    const float2 a0 = *reinterpret_cast<const float2 *>(&S.f[0][q0]), a1 = *reinterpret_cast<const float2 *>(&S.f[1][q0]),
-                                 a2 = *reinterpret_cast<const float2 *>(&S.f[2][q0]), b0 = *reinterpret_cast<const float2 *>(&S.f[3][q0]),
-                                 b1 = *reinterpret_cast<const float2 *>(&S.f[4][q0]), b2 = *reinterpret_cast<const float2 *>(&S.f[5][q0]);
+                    const float2 a0 = *reinterpret_cast<const float2 *>(S.f(0) + q0), a1 = *reinterpret_cast<const float2 *>(S.f(1) + q0),
+                                 a2 = *reinterpret_cast<const float2 *>(S.f(2) + q0), b0 = *reinterpret_cast<const float2 *>(S.f(3) + q0),
+                                 b1 = *reinterpret_cast<const float2 *>(S.f(4) + q0), b2 = *reinterpret_cast<const float2 *>(S.f(5) + q0);
                     vx[0] = a0.x; vx[1] = a0.y; vy[0] = a1.x; vy[1] = a1.y; vz[0] = a2.x; vz[1] = a2.y;
                     nx[0] = b0.x; nx[1] = b0.y; ny[0] = b1.x; ny[1] = b1.y; nz[0] = b2.x; nz[1] = b2.y;
                 }
-                if(L.rgb)
+                if(kRgb)
                 {
-                    cm = *reinterpret_cast<const unsigned short *>(&S.cand[q0]);
-                    im = *reinterpret_cast<const unsigned short *>(&S.img[q0]);
-                    const float2 dd = *reinterpret_cast<const float2 *>(&S.f[6][q0]);
+                    cm = *reinterpret_cast<const unsigned short *>(S.cand() + q0);
+                    im = *reinterpret_cast<const unsigned short *>(S.img() + q0);
+                    const float2 dd = *reinterpret_cast<const float2 *>(S.d1() + q0);
                     d1[0] = dd.x; d1[1] = dd.y;
                 }
             }
@@ -661,11 +679,11 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
             {
                 ok[c] = false;
                 o[c] = 0;
-                if(L.icp && inside) ok[c] = icp_project(ia, make_float3(vx[c], vy[c], vz[c]), vg[c], o[c]);
+                if(kIcp && inside) ok[c] = icp_project(ia, make_float3(vx[c], vy[c], vz[c]), vg[c], o[c]);
                 if(!ok[c]) o[c] = 0;
                 rok[c] = false;
                 zxy[c] = 0;
-                if(L.rgb && ((cm >> (8 * c)) & 0xff))
+                if(kRgb && ((cm >> (8 * c)) & 0xff))
                 {
                     int x = px0 + c, y = py0;
                     if(x >= g.cols)
@@ -681,19 +699,19 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
 #pragma unroll
             for(int c = 0; c < PX; c++)
             {
-                if(L.icp)
+                if(kIcp)
                 {
                     vp[c] = make_float3(__ldg(ia.vprev + o[c]), __ldg(ia.vprev + plane + o[c]), __ldg(ia.vprev + 2 * plane + o[c]));
                     np[c] = make_float3(__ldg(ia.nprev + o[c]), __ldg(ia.nprev + plane + o[c]), __ldg(ia.nprev + 2 * plane + o[c]));
                 }
-                if(L.rgb)
+                if(kRgb)
                 {
                     const int r = (zxy[c] >> 16) * g.cols + (zxy[c] & 0xffff);
                     d0[c] = __ldg(ra.lastDepth + r);
                     li[c] = __ldg(ra.lastImage + r);
                 }
             }
-            if(L.icp)
+            if(kIcp)
             {
 #pragma unroll
                 for(int c = 0; c < PX; c++)
@@ -717,7 +735,7 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                     }
                 }
             }
-            if(L.rgb)
+            if(kRgb)
             {
 #pragma unroll
                 for(int c = 0; c < PX; c++)
@@ -731,7 +749,7 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                         cc.d0 = d0[c];
                         cc.diff = __fsub_rn(static_cast<float>((im >> (8 * c)) & 0xff), static_cast<float>(li[c]));
                         const int k = p + c;
-                        cc.gxy = (int)(unsigned short)S.gx[q0 + c] | ((int)S.gy[q0 + c] << 16);
+                        cc.gxy = (int)(unsigned short)S.gx()[q0 + c] | ((int)S.gy()[q0 + c] << 16);
                         cnt0 += 1;
                         cnt1 += (int)(cc.diff * cc.diff);
                         reinterpret_cast<int4 *>(cimg)[w0 + wcount + __popc(m & ((1u << lane) - 1u))] = *reinterpret_cast<const int4 *>(&cc);
@@ -743,10 +761,21 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
         __syncwarp();   // the stage is free for the issue of the next iteration
     }
     char * ws_seq = ws + (size_t)seq * kWorkspaceBytes;
-    if(L.rgb && lane == 0) reinterpret_cast<int *>(ws_seq + kCountsOffset)[gw] = wcount;
-    if(!seq_reduce(acc, cnt0, cnt1, L.rgb, sh, ws_seq, 0)) return;
+    if(kRgb && lane == 0) reinterpret_cast<int *>(ws_seq + kCountsOffset)[gw] = wcount;
+    __syncthreads();   // every warp is done with its staging buffers: the epilogue scratch may overwrite them
+    if(!seq_reduce(acc, cnt0, cnt1, kRgb, sh, ws_seq, 0)) return;
     if(threadIdx.x >= 32) return;
-    sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
+    // phase B (or, without RGB, kb_update) picks up the ICP sums, count and sigma here: the fp64 solve is kept out of
+    // this kernel because its register footprint would cap the occupancy of the streaming part.  Split roles write
+    // their own columns of the row.
+    if(kIcp && kRgb)
+        sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
+    else if(kIcp)
+    {
+        if(threadIdx.x < 29) sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
+    }
+    else if(threadIdx.x == 29 || threadIdx.x == 30)
+        sums[seq * 64 + threadIdx.x] = sh.total[threadIdx.x];
 }
 
 // ICP-only runs: the update as its own one-warp-per-sequence launch.
@@ -764,8 +793,8 @@ __global__ void __launch_bounds__(32) kb_update(const GnLaunch L, char * states,
 // The lists are short (a few hundred records per phase-A warp), so this launch is a single wave: each warp walks several
 // lists as one flat index space (prefix sums of their counts in shared memory).  a_blocks / a_px describe phase A's grid.
 __global__ void __launch_bounds__(kBThreads, 2)
-kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, const float * sums, int lvl, int j, slam_step_record * trace,
-           int a_blocks, int a_px)
+kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride, char * ws, const char * ws_counts, const float * sums, int lvl, int j,
+           slam_step_record * trace, int a_blocks, int a_px)
 {
     __shared__ GnShared sh;
     __shared__ int s_pre[kBThreads / 32][33];
@@ -812,7 +841,7 @@ kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
     const int gw = blockIdx.x * (kBThreads / 32) + wid;
     // this warp's lists: gw, gw + b_warps, ... (at most 32, checked by the host); lane k holds the count of the k-th
     const int my_list = gw + lane * b_warps;
-    const int cnt = my_list < a_warps ? __ldcg(reinterpret_cast<const int *>(ws_seq + kCountsOffset) + my_list) : 0;
+    const int cnt = my_list < a_warps ? __ldcg(reinterpret_cast<const int *>(ws_counts + (size_t)seq * kWorkspaceBytes + kCountsOffset) + my_list) : 0;
     int pre = cnt;   // inclusive prefix over the lanes
 #pragma unroll
     for(int d = 1; d < 32; d <<= 1)
@@ -881,7 +910,7 @@ size_t batch_state_bytes(int batch, const LevelGeom * geom, int levels)
 {
     size_t aux = 0;
     for(int l = 0; l < levels; l++) aux += 2 * up256((size_t)geom[l].rows * geom[l].cols);
-    return up256(up256(offsetof(GnShared, red)) * batch) + up256((size_t)batch * 64 * 4) + aux * batch + kWorkspaceBytes * (size_t)batch + 4096;
+    return up256(up256(offsetof(GnShared, red)) * batch) + up256((size_t)batch * 64 * 4) + aux * batch + 2 * kWorkspaceBytes * (size_t)batch + 4096;
 }
 
 void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom * geom, int levels, GnSeqIn * seq_in, GnResult * results)
@@ -908,6 +937,8 @@ void batch_bind_state(BatchDevice & d, char * base, int batch, const LevelGeom *
     d.cand0 = (unsigned char *)p;
     p += off * batch;
     d.ws = p;
+    p += kWorkspaceBytes * (size_t)batch;
+    d.ws2 = p;
 }
 
 static int blocks_per_seq(int nitems, int batch, int num_sms)
@@ -919,6 +950,17 @@ static int blocks_per_seq(int nitems, int batch, int num_sms)
     if(want < 1) want = 1;
     if(want > 1024) want = 1024;
     return want;
+}
+
+static bool split_roles()
+{
+    static int v = -1;
+    if(v < 0)
+    {
+        const char * e = getenv("SLAM_BATCH_SPLIT");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
 }
 
 static int px_variant()
@@ -991,7 +1033,8 @@ void batch_report()
 }
 
 // The launch sequence of one group of sequences [s0, s0 + B) on stream s (all per-sequence arrays are indexed from s0).
-static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, slam_step_record * trace, int * trace_count, cudaStream_t s)
+static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, slam_step_record * trace, int * trace_count, cudaStream_t s, cudaStream_t s_rgb,
+                         cudaEvent_t ev_rgb_done, cudaEvent_t ev_updated)
 {
     BatchDevice d = d0;
     d.seq_in += s0;
@@ -999,6 +1042,7 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
     d.sums += (size_t)s0 * 64;
     d.cand0 += (size_t)s0 * d.aux_stride;
     d.ws += (size_t)s0 * kWorkspaceBytes;
+    d.ws2 += (size_t)s0 * kWorkspaceBytes;
     d.results += s0;
     if(trace) trace += (size_t)s0 * kGnMaxTrace;
     if(trace_count) trace_count += s0;
@@ -1039,14 +1083,23 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
         if(nbB < (nb + 31) / 32) nbB = (nb + 31) / 32;
         if(nbB < 1) nbB = 1;
         if(nbB > nb) nbB = nb;
+        // split roles: the ICP and the RGB association of an ICP+RGB iteration as two launches on two streams
+        const bool split = staged && L.icp && L.rgb && s_rgb != nullptr && split_roles();
         if(staged)
         {
             static bool attr_set = false;
             if(!attr_set)
             {
-                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem));
+                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, true>::kSmem));
+                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, false>::kSmem));
+                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<false, true>::kSmem));
                 attr_set = true;
             }
+        }
+        if(split)
+        {
+            // the RGB stream joins here: the candidates of this level and the level-begin state are ready
+            SLAM_CUDA_TRY(cudaEventRecord(ev_updated, s));
         }
         for(int j = 0; j < L.iterations[lvl]; j++)
         {
@@ -1054,17 +1107,35 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
     kb_phase_a<PXV><<<dim3(nb, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride, d.cand_off[lvl], lvl)
             {
             DetailScope ds(s, 3);
-            if(staged)
-                kb_phase_a_staged<<<dim3(nb, B), kBThreads, kStagedSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0, d.aux_stride,
-                                                                               d.cand_off[lvl], lvl);
+            if(split)
+            {
+                SLAM_CUDA_TRY(cudaStreamWaitEvent(s_rgb, ev_updated, 0));
+                kb_phase_a_staged<false, true><<<dim3(nb, B), kBThreads, RoleCfg<false, true>::kSmem, s_rgb>>>(L, d.seq_in, d.states, d.state_stride, d.ws2, d.sums, d.cand0,
+                                                                                                          d.aux_stride, d.cand_off[lvl], lvl);
+                SLAM_CUDA_TRY(cudaEventRecord(ev_rgb_done, s_rgb));
+                kb_phase_a_staged<true, false><<<dim3(nb, B), kBThreads, RoleCfg<true, false>::kSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0,
+                                                                                                      d.aux_stride, d.cand_off[lvl], lvl);
+                SLAM_CUDA_TRY(cudaStreamWaitEvent(s, ev_rgb_done, 0));
+                d.launches++;
+            }
+            else if(staged && L.icp && L.rgb)
+                kb_phase_a_staged<true, true><<<dim3(nb, B), kBThreads, RoleCfg<true, true>::kSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0,
+                                                                                                    d.aux_stride, d.cand_off[lvl], lvl);
+            else if(staged && L.icp)
+                kb_phase_a_staged<true, false><<<dim3(nb, B), kBThreads, RoleCfg<true, false>::kSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0,
+                                                                                                      d.aux_stride, d.cand_off[lvl], lvl);
+            else if(staged)
+                kb_phase_a_staged<false, true><<<dim3(nb, B), kBThreads, RoleCfg<false, true>::kSmem, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, d.cand0,
+                                                                                                      d.aux_stride, d.cand_off[lvl], lvl);
             else if(px == 4) SLAM_PHASE_A(4); else if(px == 2) SLAM_PHASE_A(2); else SLAM_PHASE_A(1);
             }
             d.launches++;
             if(L.rgb)
             {
                 DetailScope ds(s, 4);
-                kb_phase_b<<<dim3(nbB, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, d.sums, lvl, j, trace, nb, px);
+                kb_phase_b<<<dim3(nbB, B), kBThreads, 0, s>>>(L, d.seq_in, d.states, d.state_stride, d.ws, split ? d.ws2 : d.ws, d.sums, lvl, j, trace, nb, px);
                 d.launches++;
+                if(split) SLAM_CUDA_TRY(cudaEventRecord(ev_updated, s));   // the next iteration's RGB association needs the new pose
             }
             else
             {
@@ -1111,6 +1182,17 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         d.side.push_back(st);
         d.side_done.push_back(ev);
     }
+    while((int)d.role.size() < groups)   // per group: the stream of the RGB association role + its two events
+    {
+        cudaStream_t st = nullptr;
+        cudaEvent_t e1 = nullptr, e2 = nullptr;
+        SLAM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        SLAM_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        SLAM_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        d.role.push_back(st);
+        d.role_done.push_back(e1);
+        d.role_go.push_back(e2);
+    }
     if(!d.fork) SLAM_CUDA_TRY(cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming));
     SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, h_seq_in_pinned, sizeof(GnSeqIn) * B, cudaMemcpyHostToDevice, s));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1126,7 +1208,7 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         const int s0 = (int)((long long)B * gidx / groups), s1 = (int)((long long)B * (gidx + 1) / groups);
         cudaStream_t st = gidx == 0 ? s : d.side[gidx - 1];
         if(gidx > 0) SLAM_CUDA_TRY(cudaStreamWaitEvent(st, d.fork, 0));
-        if(int rc = enqueue_group(d, L, s0, s1 - s0, trace, trace_count, st)) return rc;
+        if(int rc = enqueue_group(d, L, s0, s1 - s0, trace, trace_count, st, g_detail.on ? nullptr : d.role[gidx], d.role_done[gidx], d.role_go[gidx])) return rc;
         if(gidx > 0) SLAM_CUDA_TRY(cudaEventRecord(d.side_done[gidx - 1], st));
     }
     for(int gidx = 1; gidx < groups; gidx++) SLAM_CUDA_TRY(cudaStreamWaitEvent(s, d.side_done[gidx - 1], 0));
@@ -1144,6 +1226,12 @@ void batch_release(BatchDevice & d)
 {
     for(auto st : d.side) cudaStreamDestroy(st);
     for(auto ev : d.side_done) cudaEventDestroy(ev);
+    for(auto st : d.role) cudaStreamDestroy(st);
+    for(auto ev : d.role_done) cudaEventDestroy(ev);
+    for(auto ev : d.role_go) cudaEventDestroy(ev);
+    d.role.clear();
+    d.role_done.clear();
+    d.role_go.clear();
     if(d.fork) cudaEventDestroy(d.fork);
     d.side.clear();
     d.side_done.clear();

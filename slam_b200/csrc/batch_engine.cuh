@@ -18,7 +18,10 @@ struct BatchDevice
     size_t aux_stride = 0;              // bytes between consecutive sequences' aux blocks
     size_t cand_off[SLAM_MAX_LEVELS], vmask_off[SLAM_MAX_LEVELS];
     char * ws = nullptr;            // [batch][kWorkspaceBytes]: partial rows + ticket of each sequence's running reduction
+    char * ws2 = nullptr;           // [batch][kWorkspaceBytes]: the same for the RGB association when it runs as its own launch
     int num_sms = 148;
+    std::vector<cudaStream_t> role;       // per sequence group: stream of the RGB association role
+    std::vector<cudaEvent_t> role_done, role_go;
     std::vector<cudaStream_t> side;       // streams of the sequence groups beyond the first
     std::vector<cudaEvent_t> side_done;
     cudaEvent_t fork = nullptr;

@@ -738,6 +738,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     {
         batch_report();
         for(auto st : h->be.side) cudaStreamSynchronize(st);
+        for(auto st : h->be.role) cudaStreamSynchronize(st);
         batch_release(h->be);
     }
     gn_release(h->gn);
