@@ -513,14 +513,27 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Roles: <true, true> does both halves of phase A in one pass; <true, false> and <false, true> are the ICP and the RGB
-// association as separate launches with their own register budgets (80 / 64 registers, 3 / 4 blocks per SM instead of 128 / 2):
+// association as separate launches with their own register budgets (80 / 48 registers, 3 / 5 blocks per SM instead of 128 / 2;
+// stage counts and block targets tuned on a B200, overridable with -DSLAM_ICP_STAGES ... for experiments):
 // run on two streams they fill each other's stalls (both are bound by gather round trips, not by issue slots or bandwidth).
 template <bool kIcp, bool kRgb>
 struct RoleCfg
 {
-    static constexpr int kStagesR = (kIcp && kRgb) ? 3 : (kIcp ? 3 : 4);
+#ifndef SLAM_ICP_STAGES
+#define SLAM_ICP_STAGES 2
+#endif
+#ifndef SLAM_ICP_BLOCKS
+#define SLAM_ICP_BLOCKS 3
+#endif
+#ifndef SLAM_RGB_STAGES
+#define SLAM_RGB_STAGES 3
+#endif
+#ifndef SLAM_RGB_BLOCKS
+#define SLAM_RGB_BLOCKS 5
+#endif
+    static constexpr int kStagesR = (kIcp && kRgb) ? 3 : (kIcp ? SLAM_ICP_STAGES : SLAM_RGB_STAGES);
     static constexpr int kStageBytes = (kIcp ? 6 * kTripPx * 4 : 0) + (kRgb ? kTripPx * 4 + 2 * kTripPx * 2 + 2 * kTripPx : 0);
-    static constexpr int kMinBlocks = (kIcp && kRgb) ? 2 : (kIcp ? 3 : 4);
+    static constexpr int kMinBlocks = (kIcp && kRgb) ? 2 : (kIcp ? SLAM_ICP_BLOCKS : SLAM_RGB_BLOCKS);
     static constexpr int kSmem = (kBThreads / 32) * kStagesR * kStageBytes;
 };
 
