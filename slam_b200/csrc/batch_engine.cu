@@ -870,12 +870,13 @@ kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
     float acc[32];
 #pragma unroll
     for(int k = 0; k < 32; k++) acc[k] = 0.f;
-    for(int i0 = 0; i0 < total; i0 += 128)
+    constexpr int kInFlight = 8;   // records a lane has in flight per trip
+    for(int i0 = 0; i0 < total; i0 += 32 * kInFlight)
     {
-        int4 raw[4];
-        bool have[4];
+        int4 raw[kInFlight];
+        bool have[kInFlight];
 #pragma unroll
-        for(int q = 0; q < 4; q++)
+        for(int q = 0; q < kInFlight; q++)
         {
             const int i = i0 + q * 32 + lane;
             have[q] = i < total;
@@ -895,7 +896,7 @@ kb_phase_b(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t stride,
             }
         }
 #pragma unroll
-        for(int q = 0; q < 4; q++)
+        for(int q = 0; q < kInFlight; q++)
             if(have[q])
             {
                 const BCorres cc = *reinterpret_cast<const BCorres *>(&raw[q]);
