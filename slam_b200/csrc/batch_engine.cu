@@ -1081,7 +1081,7 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
         d.launches++;
         first = false;
         if(L.iterations[lvl] <= 0) continue;
-        if(L.rgb)
+        if(L.rgb && !d.cand_ready)
         {
             DetailScope ds(s, 2);
             kb_candidates<<<dim3(blocks_per_seq(plane, B, d.num_sms), B), kBThreads, 0, s>>>(L, d.seq_in, d.cand0, d.aux_stride, d.cand_off[lvl], lvl);

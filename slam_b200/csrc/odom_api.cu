@@ -842,6 +842,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     const int G = gn_group_size(h->num_sms, h->batch);
     const int nslots0 = (h->geom[0].rows * h->geom[0].cols + G * kGnThreads - 1) / (G * kGnThreads);
     const bool derive = rgb && !h->trace_on && !streaming && nslots0 <= kSlotChunk;
+    h->be.cand_ready = false;
     if(rgb && !derive)
     {
         int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
@@ -851,7 +852,25 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
             cols[l] = h->geom[l].cols;
         }
         SeqBuffers & s0 = h->seq[0];
-        if(int rc = launch_derivatives_simple(h->levels, s0.nextImage, s0.dIdx, s0.dIdy, rows, cols, h->stream, h->batch, h->seq_stride)) return rc;
+        bool quads = true;
+        for(int l = 0; l < h->levels; l++) quads = quads && cols[l] % 4 == 0;
+        if(streaming && quads)
+        {
+            // the batched engine also wants the pose-independent half of the RGB association: same pass over nextImage
+            unsigned char * cand[SLAM_MAX_LEVELS];
+            float min_scale[SLAM_MAX_LEVELS];
+            for(int l = 0; l < h->levels; l++)
+            {
+                cand[l] = h->be.cand0 + h->be.cand_off[l];
+                min_scale[l] = (float)(pow((double)h->minGrad[l], 2.0) / pow((double)h->sobelScale, 2.0));
+            }
+            if(int rc = launch_deriv_cand(h->levels, s0.nextImage, s0.nextDepth, s0.dIdx, s0.dIdy, cand, min_scale, rows, cols, h->stream, h->batch, h->seq_stride,
+                                          h->be.aux_stride))
+                return rc;
+            h->be.cand_ready = true;
+        }
+        else if(int rc = launch_derivatives_simple(h->levels, s0.nextImage, s0.dIdx, s0.dIdy, rows, cols, h->stream, h->batch, h->seq_stride))
+            return rc;
         h->launches++;
     }
 

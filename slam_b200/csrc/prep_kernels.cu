@@ -566,6 +566,136 @@ __global__ void __launch_bounds__(256) k_derivatives(const DerivArgs a)
     seq_shift(a.dy[l], a.arena_stride)[y * cols + x] = dy;
 }
 
+// Frame-level variant for the batched engine: derivative images AND the pose-independent half of the RGB association
+// (rgb_candidate, reduce.cu:780-807) of all levels and sequences in one launch.  One thread = 4 consecutive pixels; in the
+// interior the 4x4 / 3x3 windows come from twelve aligned 32-bit loads of nextImage instead of 25 byte loads per pixel.
+struct DerivCandArgs
+{
+    const unsigned char * src[SLAM_MAX_LEVELS];   // nextImage
+    const float * depth[SLAM_MAX_LEVELS];         // nextDepth
+    short * dx[SLAM_MAX_LEVELS];
+    short * dy[SLAM_MAX_LEVELS];
+    unsigned char * cand[SLAM_MAX_LEVELS];        // sequence 0; other sequences at cand_stride
+    float min_scale[SLAM_MAX_LEVELS];
+    int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
+    int first[SLAM_MAX_LEVELS + 1];
+    int levels;
+    size_t arena_stride, cand_stride;
+};
+
+template <int K>
+__device__ __forceinline__ unsigned byte12(unsigned w0, unsigned w1, unsigned w2)   // byte K of the 12-byte row segment
+{
+    return ((K < 4 ? w0 : (K < 8 ? w1 : w2)) >> (8 * (K & 3))) & 0xffu;
+}
+
+template <int C>
+__device__ __forceinline__ void deriv_from_words(const unsigned (&w)[4][3], short & dx, short & dy)
+{
+    // taps of pixel C: rows 1..3 of the window (y-1..y+1), columns 3+C .. 5+C, accumulated in the reference's order
+    const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+    const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+    float v[9];
+#pragma unroll
+    for(int r = 0; r < 3; r++)
+    {
+        v[r * 3 + 0] = (float)byte12<3 + C>(w[r + 1][0], w[r + 1][1], w[r + 1][2]);
+        v[r * 3 + 1] = (float)byte12<4 + C>(w[r + 1][0], w[r + 1][1], w[r + 1][2]);
+        v[r * 3 + 2] = (float)byte12<5 + C>(w[r + 1][0], w[r + 1][1], w[r + 1][2]);
+    }
+    float dxVal = 0.f, dyVal = 0.f;
+#pragma unroll
+    for(int t = 0; t < 9; t++)
+    {
+        dxVal = __fmaf_rn(v[t], fgx[8 - t], dxVal);
+        dyVal = __fmaf_rn(v[t], fgy[8 - t], dyVal);
+    }
+    dx = (short)dxVal;
+    dy = (short)dyVal;
+}
+
+__global__ void __launch_bounds__(256) k_deriv_cand(const DerivCandArgs a)
+{
+    int l = 0;
+    while(l + 1 < a.levels && (int)blockIdx.x >= a.first[l + 1]) l++;
+    const int rows = a.rows[l], cols = a.cols[l];
+    const int qcols = cols >> 2;                 // cols is a multiple of 4 (checked by the host)
+    const int nbx = div_up(qcols, 32);
+    const int b = blockIdx.x - a.first[l];
+    const int qx = (b % nbx) * 32 + (threadIdx.x & 31);
+    const int y = (b / nbx) * 8 + (threadIdx.x >> 5);
+    if(qx >= qcols || y >= rows) return;
+    const int x0 = qx * 4;
+    const unsigned char * src = seq_shift(a.src[l], a.arena_stride);
+    const float * depth = seq_shift(a.depth[l], a.arena_stride);
+    short * dxp = seq_shift(a.dx[l], a.arena_stride);
+    short * dyp = seq_shift(a.dy[l], a.arena_stride);
+    unsigned char * cand = a.cand[l] ? a.cand[l] + (size_t)blockIdx.y * a.cand_stride : nullptr;
+    const int o = y * cols + x0;
+    short dx[4], dy[4];
+    unsigned char cd[4] = {0, 0, 0, 0};
+    const float minScale = a.min_scale[l];
+    if(y >= 2 && y + 1 < rows && x0 >= 4 && x0 + 8 <= cols)
+    {
+        unsigned w[4][3];
+#pragma unroll
+        for(int r = 0; r < 4; r++)
+        {
+            const unsigned * p = reinterpret_cast<const unsigned *>(src + (y - 2 + r) * cols + x0 - 4);
+            w[r][0] = __ldg(p);
+            w[r][1] = __ldg(p + 1);
+            w[r][2] = __ldg(p + 2);
+        }
+        deriv_from_words<0>(w, dx[0], dy[0]);
+        deriv_from_words<1>(w, dx[1], dy[1]);
+        deriv_from_words<2>(w, dx[2], dy[2]);
+        deriv_from_words<3>(w, dx[3], dy[3]);
+        if(cand)
+        {
+            // zero bytes anywhere in rows y-2..y+1 (0xff per zero byte), then the 4-column window of each pixel
+            const unsigned z0 = __vcmpeq4(w[0][0], 0u) | __vcmpeq4(w[1][0], 0u) | __vcmpeq4(w[2][0], 0u) | __vcmpeq4(w[3][0], 0u);
+            const unsigned z1 = __vcmpeq4(w[0][1], 0u) | __vcmpeq4(w[1][1], 0u) | __vcmpeq4(w[2][1], 0u) | __vcmpeq4(w[3][1], 0u);
+            const unsigned z2 = __vcmpeq4(w[0][2], 0u) | __vcmpeq4(w[1][2], 0u) | __vcmpeq4(w[2][2], 0u) | __vcmpeq4(w[3][2], 0u);
+            const unsigned win[4] = {__funnelshift_r(z0, z1, 16), __funnelshift_r(z0, z1, 24), z1, __funnelshift_r(z1, z2, 8)};   // columns x-2 .. x+1
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(depth + o));
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for(int c = 0; c < 4; c++)
+            {
+                const int valx = dx[c], valy = dy[c];
+                const float mTwo = (valx * valx) + (valy * valy);
+                cd[c] = (x0 + c < cols - 5 && win[c] == 0u && mTwo >= minScale && !isnan(dd[c])) ? 1 : 0;
+            }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for(int c = 0; c < 4; c++)
+        {
+            const int x = x0 + c;
+            derivative_pixel(src, rows, cols, x, y, dx[c], dy[c]);
+            if(cand)
+            {
+                bool ok = x < cols - 5 && y < rows - 1;
+                if(ok)
+                    for(int u = max(y - 2, 0); u < min(y + 2, rows); u++)
+                        for(int v = max(x - 2, 0); v < min(x + 2, cols); v++) ok = ok && (src[u * cols + v] > 0);
+                if(ok)
+                {
+                    const int valx = dx[c], valy = dy[c];
+                    const float mTwo = (valx * valx) + (valy * valy);
+                    ok = mTwo >= minScale && !isnan(depth[o + c]);
+                }
+                cd[c] = ok ? 1 : 0;
+            }
+        }
+    }
+    *reinterpret_cast<short4 *>(dxp + o) = make_short4(dx[0], dx[1], dx[2], dx[3]);
+    *reinterpret_cast<short4 *>(dyp + o) = make_short4(dy[0], dy[1], dy[2], dy[3]);
+    if(cand) *reinterpret_cast<uchar4 *>(cand + o) = make_uchar4(cd[0], cd[1], cd[2], cd[3]);
+}
+
 // ------------------------------------------------------------------ un-fused operator kernels
 __global__ void __launch_bounds__(256) k_pyr_down_u16(const unsigned short * src, int srows, int scols, unsigned short * dst)
 {
@@ -767,6 +897,34 @@ int launch_derivatives(DerivArgs & a, cudaStream_t s, int nseq = 1)
     }
     a.first[a.levels] = total;
     k_derivatives<<<dim3(total, nseq), 256, 0, s>>>(a);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_deriv_cand(int levels, const unsigned char * const * src, const float * const * depth, short * const * dx, short * const * dy,
+                      unsigned char * const * cand, const float * min_scale, const int * rows, const int * cols, cudaStream_t s, int nseq, size_t arena_stride,
+                      size_t cand_stride)
+{
+    DerivCandArgs a = {};
+    a.levels = levels;
+    a.arena_stride = arena_stride;
+    a.cand_stride = cand_stride;
+    int total = 0;
+    for(int l = 0; l < levels; l++)
+    {
+        a.src[l] = src[l];
+        a.depth[l] = depth[l];
+        a.dx[l] = dx[l];
+        a.dy[l] = dy[l];
+        a.cand[l] = cand ? cand[l] : nullptr;
+        a.min_scale[l] = min_scale ? min_scale[l] : 0.f;
+        a.rows[l] = rows[l];
+        a.cols[l] = cols[l];
+        a.first[l] = total;
+        total += div_up(cols[l] / 4, 32) * div_up(rows[l], 8);
+    }
+    a.first[levels] = total;
+    k_deriv_cand<<<dim3(total, nseq), 256, 0, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
