@@ -528,3 +528,44 @@ def test_no_cpu_fallback_errors_are_loud(setup):
     with pytest.raises(OdometryError):
         setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], device=99)
     o.close()
+
+
+def test_streaming_batch_engine_ragged_size(built):
+    """126 x 94 (levels 126x94, 63x47, 31x23: pixel counts that are not multiples of 4, odd row lengths): the batched engine
+    falls back to its scalar-per-thread kernels and the per-level derivative / candidate launches; results == single sequences."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    from tests.support import make_scene
+    W, H = 126, 94
+    scene, intr = make_scene(W, H)
+    poses = scene.trajectory(1000)
+    ks = (120, 340, 560, 780)
+    frames = [frame_pair(scene, poses, k) for k in ks]
+    args = (intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    kw = dict(so3=False, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False)
+    singles, counts = [], []
+    for fr in frames:
+        o = RGBDOdometry(*args)
+        o.set_trace(1)
+        d = to_device(fr)
+        torch.cuda.synchronize()
+        singles.append(run_frame(o, d, **kw))
+        counts.append(o.get_trace(0)[0])
+        o.close()
+    B = len(frames)
+    ob = RGBDOdometry(*args, batch=B)
+    ob.set_trace(1)
+    stack = lambda key: torch.from_numpy(np.stack([(f[key].view(np.int16) if f[key].dtype == np.uint16 else f[key]) for f in frames])).to("cuda:0")
+    depth, rgba, mv, mn, mrgba = (stack(k) for k in ("depth", "rgba", "mv", "mn", "mrgba"))
+    P = np.stack([f["model_pose"] for f in frames])
+    torch.cuda.synchronize()
+    ob.initICPModel(mv, mn, 20.0, P)
+    ob.initRGBModel(mrgba)
+    ob.initICP(depth, 3.0)
+    ob.initRGB(rgba)
+    tb, rb = ob.getIncrementalTransformation(P[:, :3, 3].copy(), P[:, :3, :3].copy(), False, 10.0, True, False, False)
+    for b in range(B):
+        first = ob.get_trace(b)[0]
+        assert (first["rgb_count"], first["rgb_sigma"], first["icp"][28]) == (counts[b]["rgb_count"], counts[b]["rgb_sigma"], counts[b]["icp"][28]), f"sequence {b}"
+        assert np.abs(tb[b] - singles[b][0]).max() < 2e-4 and np.abs(rb[b] - singles[b][1]).max() < 2e-4, f"sequence {b}: {np.abs(tb[b] - singles[b][0]).max()}"
+    ob.close()
