@@ -185,6 +185,10 @@ typedef struct slam_step_record
 int slam_odom_set_trace(slam_odom_t h, int enable);
 int slam_odom_get_trace(slam_odom_t h, int seq, slam_step_record * out, int max_records, int * n_records);
 
+/* initICP on a RAW depth frame: the reference app's pre-filter (slam_op_depth_bilateral with max depth filter_max_depth_m,
+ * apps/elastic_fusion_file.cpp:342-346) followed by initICP(filtered, depth_cutoff) (:368), without leaving the device. */
+int slam_odom_init_icp_depth_raw(slam_odom_t h, const uint16_t * d_raw_depth, float filter_max_depth_m, float depth_cutoff);
+
 /* Relocalisation scoring (BASELINE.json configs[4]; the acceptance test of lc/Ferns.cpp:253-268 reads the same two numbers
  * after a full track): score n candidate poses of the CURRENT frame (row-major rot9, trans3 each) against the model
  * prediction prepared by init_icp_model + init_icp_depth/maps, at pyramid level `level`, in one launch.  prev_trans3 /
@@ -208,6 +212,10 @@ void * slam_odom_stream(slam_odom_t h);
 /* ---- operator-level API: the free host wrappers of src/odom/utils.cuh:62-175 ----------
  * Raw dense device pointers; `stream` is a cudaStream_t (NULL = default stream).  Each call
  * only enqueues work.  Planar maps are float [3][rows][cols]. */
+/* Depth pre-filter that produces DEPTH_FILTERED, the input of initICP: 13x13 bilateral, values < 300 mm or > max_depth_m -> 0
+ * (gl/shaders/depth_bilateral.frag:30-76, run by gl/ComputePack.cpp:41-73 from apps/elastic_fusion_file.cpp:342-346).
+ * n_images dense u16 images back to back; src != dst. */
+int slam_op_depth_bilateral(const uint16_t * src, int rows, int cols, float max_depth_m, uint16_t * dst, int n_images, void * stream);
 int slam_op_pyr_down(const uint16_t * src, int src_rows, int src_cols, uint16_t * dst, void * stream);                   /* pyrDown            utils.cuh:155 */
 int slam_op_create_vmap(float fx, float fy, float cx, float cy, const uint16_t * depth, int rows, int cols, float * vmap,
                         float depth_cutoff, void * stream);                                                               /* createVMap         :119 */

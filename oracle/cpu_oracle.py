@@ -31,6 +31,7 @@ def load():
     lib = C.CDLL(str(LIB_PATH))
     vp, i, f = C.c_void_p, C.c_int, C.c_float
     lib.oracle_num_threads.restype = i
+    lib.oracle_depth_bilateral.argtypes = [vp, i, i, f, vp]
     lib.oracle_create.restype = vp
     lib.oracle_create.argtypes = [i, i, f, f, f, f, f, f]
     lib.oracle_destroy.argtypes = [vp]
@@ -130,3 +131,12 @@ class CpuOdometry:
         dt = np.dtype(_TAP_DTYPE[tap])
         buf = np.frombuffer((C.c_uint8 * (n * dt.itemsize)).from_address(ptr), dtype=np.uint8).copy()
         return shape_tap(buf, tap, h, w)
+
+
+def depth_bilateral(depth_u16: np.ndarray, max_depth_m: float) -> np.ndarray:
+    """oracle/depth_filter_oracle.c: the reference's 13x13 bilateral depth pre-filter (gl/shaders/depth_bilateral.frag)."""
+    lib = load()
+    src = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+    dst = np.zeros_like(src)
+    lib.oracle_depth_bilateral(src.ctypes.data, src.shape[0], src.shape[1], float(max_depth_m), dst.ctypes.data)
+    return dst

@@ -87,9 +87,9 @@ def build_hostmath(force: bool = False) -> Path:
 
 def build_oracle(force: bool = False) -> Path:
     out = ROOT / "oracle" / "liboracle.so"
-    src = ROOT / "oracle" / "odom_oracle.c"
-    if force or _stale(out, [src]):
-        _run(["gcc", "-O3", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"])
+    srcs = [ROOT / "oracle" / "odom_oracle.c", ROOT / "oracle" / "depth_filter_oracle.c"]
+    if force or _stale(out, srcs):
+        _run(["gcc", "-O3", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"])
     return out
 
 

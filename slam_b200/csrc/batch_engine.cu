@@ -761,7 +761,6 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                         cc.zxy = zxy[c];
                         cc.d0 = d0[c];
                         cc.diff = __fsub_rn(static_cast<float>((im >> (8 * c)) & 0xff), static_cast<float>(li[c]));
-                        const int k = p + c;
                         cc.gxy = (int)(unsigned short)S.gx()[q0 + c] | ((int)S.gy()[q0 + c] << 16);
                         cnt0 += 1;
                         cnt1 += (int)(cc.diff * cc.diff);

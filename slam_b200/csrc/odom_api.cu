@@ -59,6 +59,7 @@ struct slam_odom
     size_t arena_bytes = 0;
     std::vector<SeqBuffers> seq;
     size_t seq_stride = 0;            // bytes between the buffers of consecutive sequences in the arena
+    unsigned short * filtered_depth = nullptr;   // [batch][H][W] output of the depth pre-filter (allocated on first use)
     char * score_ws = nullptr;        // pose-hypothesis scoring: poses | partials | tickets | results (grown on demand)
     size_t score_ws_bytes = 0;
     float * d_poses12 = nullptr;      // [batch][12] model poses (R row-major | t) of the batched preparation launches
@@ -747,6 +748,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->h_sums) cudaFreeHost(h->h_sums);
     if(h->h_poses12) cudaFreeHost(h->h_poses12);
     if(h->score_ws) cudaFree(h->score_ws);
+    if(h->filtered_depth) cudaFree(h->filtered_depth);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if(h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -1014,6 +1016,18 @@ extern "C" int slam_odom_get_stats(slam_odom_t h, slam_odom_stats * stats)
         if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
     for(int b = 0; b < h->batch; b++) stats[b] = h->stats[b];
     return SLAM_OK;
+}
+
+extern "C" int slam_odom_init_icp_depth_raw(slam_odom_t h, const uint16_t * d_raw_depth, float filter_max_depth_m, float depth_cutoff)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(d_raw_depth);
+    if(int rc = set_device(h)) return rc;
+    const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
+    if(!h->filtered_depth) SLAM_CUDA_TRY(cudaMalloc((void **)&h->filtered_depth, n0 * 2 * h->batch));
+    if(int rc = launch_depth_bilateral(d_raw_depth, h->geom[0].rows, h->geom[0].cols, filter_max_depth_m, h->filtered_depth, h->batch, h->stream)) return rc;
+    h->launches++;
+    return slam_odom_init_icp_depth(h, h->filtered_depth, 0, depth_cutoff);
 }
 
 extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,

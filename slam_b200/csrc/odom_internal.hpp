@@ -78,6 +78,7 @@ int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows,
 int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
                               cudaStream_t s, int nseq = 1, size_t arena_stride = 0);
 
+int launch_depth_bilateral(const unsigned short * src, int rows, int cols, float max_depth_m, unsigned short * dst, int n_images, cudaStream_t s);
 // derivative images + RGB candidate masks of all levels and sequences in one launch (cols % 4 == 0 at every level)
 int launch_deriv_cand(int levels, const unsigned char * const * src, const float * const * depth, short * const * dx, short * const * dy,
                       unsigned char * const * cand, const float * min_scale, const int * rows, const int * cols, cudaStream_t s, int nseq, size_t arena_stride,

@@ -696,6 +696,87 @@ __global__ void __launch_bounds__(256) k_deriv_cand(const DerivCandArgs a)
     if(cand) *reinterpret_cast<uchar4 *>(cand + o) = make_uchar4(cd[0], cd[1], cd[2], cd[3]);
 }
 
+// ------------------------------------------------------------------ depth pre-filter
+// The 13x13 bilateral filter that produces DEPTH_FILTERED, the input of initICP (gl/shaders/depth_bilateral.frag:30-76 run by
+// gl/ComputePack.cpp:41-73; caller apps/elastic_fusion_file.cpp:342-346).  Stencil kernel: a 32x8 output tile + 6-pixel halo
+// is staged in shared memory, the 169 spatial exponents come from a constant table (same fp32 values as computed in place),
+// every pixel walks its clipped window in the shader's order with the shader's operations (no FMA contraction: the sums
+// decide a round-to-integer).  Compute-bound: 169 exp per valid pixel; HBM traffic is 4 B/px.
+constexpr int kBilR = 6;
+constexpr int kBilTileX = 32, kBilTileY = 8;
+__constant__ float c_bil_space[13 * 13];
+
+__global__ void __launch_bounds__(256) k_depth_bilateral(const unsigned short * __restrict__ src, int rows, int cols, unsigned cut, unsigned short * __restrict__ dst,
+                                                         size_t image_stride)
+{
+    __shared__ unsigned short tile[kBilTileY + 2 * kBilR][kBilTileX + 2 * kBilR + 4];
+    src = reinterpret_cast<const unsigned short *>(reinterpret_cast<const char *>(src) + (size_t)blockIdx.z * image_stride);
+    dst = reinterpret_cast<unsigned short *>(reinterpret_cast<char *>(dst) + (size_t)blockIdx.z * image_stride);
+    const int bx = blockIdx.x * kBilTileX, by = blockIdx.y * kBilTileY;
+    for(int k = threadIdx.x; k < (kBilTileY + 2 * kBilR) * (kBilTileX + 2 * kBilR); k += blockDim.x)
+    {
+        const int ty = k / (kBilTileX + 2 * kBilR), tx = k - ty * (kBilTileX + 2 * kBilR);
+        const int gx = bx + tx - kBilR, gy = by + ty - kBilR;
+        tile[ty][tx] = (gx >= 0 && gy >= 0 && gx < cols && gy < rows) ? __ldg(src + gy * cols + gx) : (unsigned short)0;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = bx + lx, y = by + ly;
+    if(x >= cols || y >= rows) return;
+    const unsigned value = tile[ly + kBilR][lx + kBilR];
+    if(value > cut || value < 300u)
+    {
+        dst[y * cols + x] = 0;
+        return;
+    }
+    const float sigma_color2_inv_half = 0.000555556f;
+    const float fv = (float)value;
+    const int cy0 = max(y - kBilR, 0), cy1 = min(y + kBilR + 1, rows);
+    const int cx0 = max(x - kBilR, 0), cx1 = min(x + kBilR + 1, cols);
+    float sum1 = 0.f, sum2 = 0.f;
+    for(int cy = cy0; cy < cy1; ++cy)
+    {
+        const int trow = cy - by + kBilR, tcol0 = kBilR - bx;
+        const int srow = (cy - y + kBilR) * 13 + (kBilR - x);
+#pragma unroll 13
+        for(int cx = cx0; cx < cx1; ++cx)
+        {
+            const float ft = (float)tile[trow][cx + tcol0];
+            const float dc = __fsub_rn(fv, ft);
+            const float arg = __fadd_rn(c_bil_space[srow + cx], __fmul_rn(__fmul_rn(dc, dc), sigma_color2_inv_half));
+            const float weight = expf(-arg);
+            sum1 = __fadd_rn(sum1, __fmul_rn(ft, weight));
+            sum2 = __fadd_rn(sum2, weight);
+        }
+    }
+    dst[y * cols + x] = (unsigned short)(unsigned)roundf(__fdiv_rn(sum1, sum2));
+}
+
+int launch_depth_bilateral(const unsigned short * src, int rows, int cols, float max_depth_m, unsigned short * dst, int n_images, cudaStream_t s)
+{
+    static bool table_ready[64] = {};
+    int dev = 0;
+    SLAM_CUDA_TRY(cudaGetDevice(&dev));
+    if(dev < 64 && !table_ready[dev])
+    {
+        float tab[13 * 13];
+        for(int j = 0; j < 13; j++)
+            for(int i = 0; i < 13; i++)
+            {
+                // (float(x) - float(cx))^2 + (float(y) - float(cy))^2, times sigma_space2_inv_half: small integers, exact products
+                const float dx = (float)(kBilR - i), dy = (float)(kBilR - j);
+                const float space2 = dx * dx + dy * dy;
+                tab[j * 13 + i] = space2 * 0.024691358f;
+            }
+        SLAM_CUDA_TRY(cudaMemcpyToSymbol(c_bil_space, tab, sizeof(tab)));
+        table_ready[dev] = true;
+    }
+    const unsigned cut = (unsigned)(max_depth_m * 1000.0f);
+    k_depth_bilateral<<<dim3(div_up(cols, kBilTileX), div_up(rows, kBilTileY), n_images), 256, 0, s>>>(src, rows, cols, cut, dst, (size_t)rows * cols * 2);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
 // ------------------------------------------------------------------ un-fused operator kernels
 __global__ void __launch_bounds__(256) k_pyr_down_u16(const unsigned short * src, int srows, int scols, unsigned short * dst)
 {
@@ -978,6 +1059,12 @@ int launch_derivatives_simple(int levels, const unsigned char * const * src, sho
 
 // ------------------------------------------------------------------ C ABI (operators)
 using namespace slam;
+
+extern "C" int slam_op_depth_bilateral(const uint16_t * src, int rows, int cols, float max_depth_m, uint16_t * dst, int n_images, void * stream)
+{
+    SLAM_ARG_CHECK(src && dst && src != dst && rows > 0 && cols > 0 && n_images > 0 && n_images <= 65535);
+    return launch_depth_bilateral(src, rows, cols, max_depth_m, dst, n_images, (cudaStream_t)stream);
+}
 
 extern "C" int slam_op_pyr_down(const uint16_t * src, int src_rows, int src_cols, uint16_t * dst, void * stream)
 {

@@ -120,6 +120,8 @@ def load_library():
     lib.slam_odom_get_trace.argtypes = [vp, i, C.POINTER(StepRecord), i, C.POINTER(i)]
     lib.slam_odom_launch_count.argtypes = [vp]
     lib.slam_odom_launch_count.restype = C.c_longlong
+    lib.slam_odom_init_icp_depth_raw.argtypes = [vp, vp, f, f]
+    lib.slam_op_depth_bilateral.argtypes = [vp, i, i, f, vp, i, vp]
     lib.slam_odom_score_poses.argtypes = [vp, i, i, i, fp, fp, fp, fp, fp, fp]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
@@ -297,6 +299,10 @@ class RGBDOdometry:
         n = C.c_int(0)
         _check(self.lib, self.lib.slam_odom_get_trace(self._h, seq, arr, 64, C.byref(n)))
         return [arr[k].as_dict() for k in range(min(n.value, 64))]
+
+    def initICPRaw(self, rawDepth, filterMaxDepth, depthCutoff):
+        """The reference app's depth pre-filter (13x13 bilateral, apps/elastic_fusion_file.cpp:342-346) + initICP, on the device."""
+        _check(self.lib, self.lib.slam_odom_init_icp_depth_raw(self._h, _addr(rawDepth), float(filterMaxDepth), float(depthCutoff)))
 
     def score_poses(self, level, prev_pose, trans_n, rot_n, seq=0):
         """Score n candidate poses of the current frame against the prepared model prediction (slam_odom_score_poses):
