@@ -552,6 +552,36 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
         ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
         out[f"configs[4] level {level}"] = {"hypotheses": n_hyp, "per_gpu": n_hyp // world, "ms_per_frame": ms, "hypotheses_per_s": n_hyp / (ms * 1e-3),
                                             "best_index": best, "best_error": err, "collective": "1 min-allreduce (int64)" if world > 1 else "none"}
+    # ---- the depth pre-filter in front of initICP (13x13 bilateral, compute-bound: 169 exp per pixel)
+    if world == 1:
+        from slam_b200.odometry import load_library
+        lib = load_library()
+        raw = torch.stack([dframes[(7 * b) % len(dframes)]["depth"] for b in range(64)])
+        out_f = torch.zeros_like(raw)
+        for nimg in (1, 64):
+            for _ in range(3):
+                lib.slam_op_depth_bilateral(raw.data_ptr(), H, W, DEPTH_CUTOFF, out_f.data_ptr(), nimg, None)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 50 if nimg == 1 else 10
+            e0.record()
+            for _ in range(reps):
+                lib.slam_op_depth_bilateral(raw.data_ptr(), H, W, DEPTH_CUTOFF, out_f.data_ptr(), nimg, None)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            out[f"depth pre-filter 640x480 x{nimg}"] = {"us_per_launch": us, "frames_per_s": nimg / (us * 1e-6), "exp_per_s": nimg * W * H * 169 / (us * 1e-6)}
+        try:
+            from oracle.cpu_oracle import depth_bilateral
+            host = frames[0]["depth"]
+            depth_bilateral(host, DEPTH_CUTOFF)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                depth_bilateral(host, DEPTH_CUTOFF)
+            out["depth pre-filter 640x480 x1"]["cpu_port_us"] = (time.perf_counter() - t0) / 3 * 1e6
+        except Exception:
+            pass
+        del raw, out_f
     # ---- configs[2]
     if world == 1:
         from slam_b200.synth import Scene
