@@ -1258,12 +1258,22 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
                 o[9 + r] = q[4 * r + 3];
             }
         }
-        SLAM_CUDA_TRY(cudaMemcpyAsync(h->d_poses12, h->h_poses12, sizeof(float) * 12 * B, cudaMemcpyHostToDevice, h->stream));
+        // one sequence: the pose travels in the kernel parameters (no copy in front of the first launch of the chain)
+        if(B > 1) SLAM_CUDA_TRY(cudaMemcpyAsync(h->d_poses12, h->h_poses12, sizeof(float) * 12 * B, cudaMemcpyHostToDevice, h->stream));
         {
-            const Mat3 R0 = {};
-            rc = launch_model_maps_simple(mv, mn, h->geom[0].rows, h->geom[0].cols, h->levels, s.vprev, s.nprev, 1, R0, make_float3(0, 0, 0), s.depth_tmp,
+            Mat3 R0 = {};
+            float3 t0 = make_float3(0, 0, 0);
+            if(B == 1)
+            {
+                const float * q = h->h_poses12;
+                R0.r0 = make_float3(q[0], q[1], q[2]);
+                R0.r1 = make_float3(q[3], q[4], q[5]);
+                R0.r2 = make_float3(q[6], q[7], q[8]);
+                t0 = make_float3(q[9], q[10], q[11]);
+            }
+            rc = launch_model_maps_simple(mv, mn, h->geom[0].rows, h->geom[0].cols, h->levels, s.vprev, s.nprev, 1, R0, t0, s.depth_tmp,
                                           h->maxDepthRGB, h->levels > 3 ? s.vcam : nullptr, h->levels > 3 ? s.ncam : nullptr, h->stream, B, n0 * 16, S,
-                                          h->d_poses12);
+                                          B > 1 ? h->d_poses12 : nullptr);
             if(rc) return rc;
             h->launches++;
             if(h->levels > 3)
