@@ -965,6 +965,30 @@ static int blocks_per_seq(int nitems, int batch, int num_sms)
     return want;
 }
 
+static int ensure_kernel_attributes()
+{
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+        SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, true>::kSmem));
+        SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, false>::kSmem));
+        SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<false, true>::kSmem));
+        attr_set = true;
+    }
+    return SLAM_OK;
+}
+
+static bool use_graphs()
+{
+    static int v = -1;
+    if(v < 0)
+    {
+        const char * e = getenv("SLAM_BATCH_GRAPH");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 static bool split_roles()
 {
     static int v = -1;
@@ -1098,17 +1122,6 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
         if(nbB > nb) nbB = nb;
         // split roles: the ICP and the RGB association of an ICP+RGB iteration as two launches on two streams
         const bool split = staged && L.icp && L.rgb && s_rgb != nullptr && split_roles();
-        if(staged)
-        {
-            static bool attr_set = false;
-            if(!attr_set)
-            {
-                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, true>::kSmem));
-                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<true, false>::kSmem));
-                SLAM_CUDA_TRY(cudaFuncSetAttribute(kb_phase_a_staged<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RoleCfg<false, true>::kSmem));
-                attr_set = true;
-            }
-        }
         if(split)
         {
             // the RGB stream joins here: the candidates of this level and the level-begin state are ready
@@ -1165,7 +1178,7 @@ static int enqueue_group(BatchDevice & d0, const GnLaunch & L, int s0, int B, sl
     return SLAM_OK;
 }
 
-// Whole batch.  With 8 or more sequences the batch runs as two (SLAM_BATCH_GROUPS: 1..4) independent groups on their own
+// Whole batch.  With 24 or more sequences the batch runs as two (SLAM_BATCH_GROUPS: 1..4) independent groups on their own
 // streams: while one group sits in a latency-bound stretch (phase B, the fp64 solves, the SO3 iterations of the small level)
 // the other group's streaming launches keep the memory system busy.  Results do not depend on the grouping.
 int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_pinned, GnResult * h_results, slam_step_record * trace, int * trace_count,
@@ -1180,7 +1193,7 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         g_detail.on = e && atoi(e) != 0;
     }
     if(g_detail.on && g_detail.ev.size() > 8192) detail_fold();
-    int groups = B >= 8 ? 2 : 1;
+    int groups = B >= 24 ? 2 : 1;   // measured on a B200: two groups pay off from a few dozen sequences on
     if(const char * e = getenv("SLAM_BATCH_GROUPS")) groups = atoi(e);
     if(groups < 1) groups = 1;
     if(groups > 4) groups = 4;
@@ -1207,7 +1220,25 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         d.role_go.push_back(e2);
     }
     if(!d.fork) SLAM_CUDA_TRY(cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming));
-    SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, h_seq_in_pinned, sizeof(GnSeqIn) * B, cudaMemcpyHostToDevice, s));
+    if(int rc = ensure_kernel_attributes()) return rc;
+
+    // the launch sequence of a step: copy in, fork the groups, join, copy out
+    auto body = [&]() -> int {
+        SLAM_CUDA_TRY(cudaMemcpyAsync(d.seq_in, h_seq_in_pinned, sizeof(GnSeqIn) * B, cudaMemcpyHostToDevice, s));
+        if(groups > 1) SLAM_CUDA_TRY(cudaEventRecord(d.fork, s));
+        for(int gidx = 0; gidx < groups; gidx++)
+        {
+            const int s0 = (int)((long long)B * gidx / groups), s1 = (int)((long long)B * (gidx + 1) / groups);
+            cudaStream_t st = gidx == 0 ? s : d.side[gidx - 1];
+            if(gidx > 0) SLAM_CUDA_TRY(cudaStreamWaitEvent(st, d.fork, 0));
+            if(int rc = enqueue_group(d, L, s0, s1 - s0, trace, trace_count, st, g_detail.on ? nullptr : d.role[gidx], d.role_done[gidx], d.role_go[gidx])) return rc;
+            if(gidx > 0) SLAM_CUDA_TRY(cudaEventRecord(d.side_done[gidx - 1], st));
+        }
+        for(int gidx = 1; gidx < groups; gidx++) SLAM_CUDA_TRY(cudaStreamWaitEvent(s, d.side_done[gidx - 1], 0));
+        SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * B, cudaMemcpyDeviceToHost, s));
+        return SLAM_OK;
+    };
+
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(prof_events)   // CUDA-event bracket of the whole engine section of this step
     {
@@ -1215,28 +1246,61 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         SLAM_CUDA_TRY(cudaEventCreate(&e1));
         SLAM_CUDA_TRY(cudaEventRecord(e0, s));
     }
-    if(groups > 1) SLAM_CUDA_TRY(cudaEventRecord(d.fork, s));
-    for(int gidx = 0; gidx < groups; gidx++)
+    if(use_graphs() && !g_detail.on)
     {
-        const int s0 = (int)((long long)B * gidx / groups), s1 = (int)((long long)B * (gidx + 1) / groups);
-        cudaStream_t st = gidx == 0 ? s : d.side[gidx - 1];
-        if(gidx > 0) SLAM_CUDA_TRY(cudaStreamWaitEvent(st, d.fork, 0));
-        if(int rc = enqueue_group(d, L, s0, s1 - s0, trace, trace_count, st, g_detail.on ? nullptr : d.role[gidx], d.role_done[gidx], d.role_go[gidx])) return rc;
-        if(gidx > 0) SLAM_CUDA_TRY(cudaEventRecord(d.side_done[gidx - 1], st));
+        // Every argument of every launch of a step is a constant of (mode, geometry, handle): the sequence is captured once
+        // per such key as a CUDA graph and replayed, which removes ~75 stream launches and ~80 event operations per step
+        // from the host's critical path (what small batches are bound by).
+        std::vector<char> key(sizeof(GnLaunch) + 8 * sizeof(void *));
+        memset(key.data(), 0, key.size());
+        memcpy(key.data(), &L, sizeof(GnLaunch));
+        const void * extra[8] = {trace, trace_count, h_seq_in_pinned, h_results, (const void *)s, (const void *)(size_t)groups, (const void *)(size_t)(d.cand_ready ? 1 : 0),
+                                 (const void *)(size_t)B};
+        memcpy(key.data() + sizeof(GnLaunch), extra, sizeof(extra));
+        BatchDevice::GraphEntry * hit = nullptr;
+        for(auto & g : d.graphs)
+            if(g.key == key) hit = &g;
+        if(!hit)
+        {
+            if(d.graphs.size() >= 16)   // modes come and go in tests: drop the oldest
+            {
+                cudaGraphExecDestroy(d.graphs.front().exec);
+                d.graphs.erase(d.graphs.begin());
+            }
+            const long long before = d.launches;
+            SLAM_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = body();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if(rc) { if(graph) cudaGraphDestroy(graph); return rc; }
+            SLAM_CUDA_TRY(ce);
+            BatchDevice::GraphEntry entry;
+            entry.key = key;
+            entry.launches = d.launches - before;
+            d.launches = before;
+            SLAM_CUDA_TRY(cudaGraphInstantiate(&entry.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            d.graphs.push_back(entry);
+            hit = &d.graphs.back();
+        }
+        SLAM_CUDA_TRY(cudaGraphLaunch(hit->exec, s));
+        d.launches += hit->launches;
     }
-    for(int gidx = 1; gidx < groups; gidx++) SLAM_CUDA_TRY(cudaStreamWaitEvent(s, d.side_done[gidx - 1], 0));
+    else if(int rc = body())
+        return rc;
     if(prof_events)
     {
         SLAM_CUDA_TRY(cudaEventRecord(e1, s));
         prof_events->push_back(e0);
         prof_events->push_back(e1);
     }
-    SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * B, cudaMemcpyDeviceToHost, s));
     return SLAM_OK;
 }
 
 void batch_release(BatchDevice & d)
 {
+    for(auto & g : d.graphs) cudaGraphExecDestroy(g.exec);
+    d.graphs.clear();
     for(auto st : d.side) cudaStreamDestroy(st);
     for(auto ev : d.side_done) cudaEventDestroy(ev);
     for(auto st : d.role) cudaStreamDestroy(st);

@@ -20,6 +20,13 @@ struct BatchDevice
     char * ws = nullptr;            // [batch][kWorkspaceBytes]: partial rows + ticket of each sequence's running reduction
     char * ws2 = nullptr;           // [batch][kWorkspaceBytes]: the same for the RGB association when it runs as its own launch
     int num_sms = 148;
+    struct GraphEntry
+    {
+        std::vector<char> key;      // GnLaunch bytes + the pointers / counts the launch sequence depends on
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+    };
+    std::vector<GraphEntry> graphs;   // captured launch sequences of a step, one per key
     bool cand_ready = false;        // the candidate masks of this frame were written by the fused derivative launch
     std::vector<cudaStream_t> role;       // per sequence group: stream of the RGB association role
     std::vector<cudaEvent_t> role_done, role_go;
