@@ -99,13 +99,12 @@ def make_frames(seed: int, n: int):
     scene = Scene(seed=0x51A7)
     poses = scene.trajectory(1000, seed=0x51A7 + seed)
     frames = []
-    stride = max(1, 900 // n)
     for i in range(n):
-        k = 1 + i * stride
+        k = 100 + i          # consecutive frames: the SO3 pre-alignment compares each image with the one tracked just before
         depth, rgba = scene.render_frame(poses[k])
         mv, mn, mrgba = scene.render_model(poses[k - 1])
         frames.append(dict(depth=depth, rgba=rgba, mv=mv, mn=mn, mrgba=mrgba, model_pose=poses[k - 1].copy(), gt_pose=poses[k].copy()))
-    first_rgba = scene.render_frame(poses[0])[1]
+    first_rgba = scene.render_frame(poses[99])[1]
     return frames, first_rgba
 
 
@@ -314,9 +313,9 @@ def run_ours(args, rank, local_rank, world):
     for i in range(args.steps):
         j = (args.warmup + i) % nf
         jn = (args.warmup + i + 1) % nf
-        if i + 1 < args.steps:
-            odo.prefetch_host(host_frames[jn])       # next frame's H2D overlaps this frame's solve
-        odo.track_host(host_frames[j], *priors[j])   # returns the pose (D2H) of this frame
+        # this frame's kernels are enqueued, then the next frame's H2D copies are issued (they overlap this frame's solve),
+        # then the pose of this frame is read back (D2H)
+        odo.track_host(host_frames[j], *priors[j], next_frame=host_frames[jn] if i + 1 < args.steps else None)
     e3.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3        # host wall clock of this rank: what the caller of the API sees
@@ -436,7 +435,7 @@ def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames,
     odo = RGBDOdometry(W, H, 319.5, 239.5, 481.20, -480.0, device=local_rank, batch=B)
     odo.initFirstRGB(torch.stack([dfirst] * B))
     sets = []
-    for off in (0, 37):    # two distinct batch frames (2 x 826 MB at B = 64) + a 2.6 GB arena: far beyond L2
+    for off in (0, 1):     # two consecutive frames of every sequence (2 x 826 MB at B = 64) + a 2.6 GB arena: far beyond L2
         d = {k: torch.stack([dframes[(off + 5 * b) % nf][k] for b in range(B)]) for k in keys}
         P = np.stack([frames[(off + 5 * b) % nf]["model_pose"] for b in range(B)])
         G = np.stack([frames[(off + 5 * b) % nf]["gt_pose"][:3, 3] for b in range(B)])
@@ -474,7 +473,7 @@ def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames,
     e2e = None
     if B * BYTES_PER_FRAME_IN * 2 < 4e9:
         hsets = []
-        for off in (0, 37):
+        for off in (0, 1):
             d = {k: torch.stack([hframes[(off + 5 * b) % nf][k] for b in range(B)]).pin_memory() for k in keys}
             P = np.stack([frames[(off + 5 * b) % nf]["model_pose"] for b in range(B)])
             hsets.append((d, P, odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, DEPTH_CUTOFF, MODEL_CUTOFF)))
@@ -487,9 +486,7 @@ def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames,
         odo.prefetch_host(hsets[0][2])
         for i in range(n_e2e):
             d, P, fr = hsets[i % 2]
-            if i + 1 < n_e2e:
-                odo.prefetch_host(hsets[(i + 1) % 2][2])
-            odo.track_host(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+            odo.track_host(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy(), next_frame=hsets[(i + 1) % 2][2] if i + 1 < n_e2e else None)
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {"value": world * B * n_e2e / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": B * (BYTES_PER_FRAME_IN + 64), "d2h_bytes_per_step": B * 48,

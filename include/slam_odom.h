@@ -131,6 +131,10 @@ typedef struct slam_frame_host
 int slam_odom_prefetch_host(slam_odom_t h, const slam_frame_host * frame);
 int slam_odom_track_host(slam_odom_t h, const slam_frame_host * frame, float * trans, float * rot, int rgb_only,
                          float icp_weight, int pyramid, int fast_odom, int so3);
+/* Same, and the copies of the NEXT frame (may be NULL) are issued right after this frame's kernels, before waiting for them:
+ * the host time of staging overlaps the device time of tracking (a pipelined reader loop in one call). */
+int slam_odom_track_host_next(slam_odom_t h, const slam_frame_host * f, const slam_frame_host * next, float * trans, float * rot, int rgb_only,
+                              float icp_weight, int pyramid, int fast_odom, int so3);
 /* Same sequence with all inputs already in device memory (one call per frame). */
 int slam_odom_track_device(slam_odom_t h, const slam_frame_host * frame_dev, float * trans, float * rot, int rgb_only,
                            float icp_weight, int pyramid, int fast_odom, int so3);

@@ -1221,7 +1221,7 @@ extern "C" int slam_odom_tap(slam_odom_t h, int tap, int level, int seq, void * 
 // ------------------------------------------------------------------ per-frame front ends
 static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, const uchar4 * rgba, const float4 * mv, const float4 * mn, const uchar4 * mrgba,
                                   const float * poses16, float depth_cutoff, float model_cutoff, float * trans, float * rot, int rgb_only,
-                                  float icp_weight, int pyramid, int fast_odom, int so3)
+                                  float icp_weight, int pyramid, int fast_odom, int so3, bool defer_wait = false)
 {
     // apps/elastic_fusion_file.cpp:366-374: initICPModel -> initRGBModel -> initICP -> initRGB -> getIncrementalTransformation
     if(!h->trace_on && !h->p.host_loop)
@@ -1303,6 +1303,7 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         }
         h->have_depth_tmp = true;
         SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+        if(defer_wait) return slam_odom_get_incremental_transformation_async(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
         return slam_odom_get_incremental_transformation(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
     }
     if(int rc = slam_odom_init_icp_model(h, (const float *)mv, (const float *)mn, model_cutoff, poses16)) return rc;
@@ -1418,6 +1419,45 @@ extern "C" int slam_odom_track_host(slam_odom_t h, const slam_frame_host * f, fl
     SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl->ready, 0));
     const int rc = track_from_device_ptrs(h, sl->depth, sl->rgba, sl->mv, sl->mn, sl->mrgba, sl->poses.data(), sl->depth_cutoff, sl->model_depth_cutoff, trans,
                                           rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+    sl->pending = false;
+    return rc;
+}
+
+extern "C" int slam_odom_track_host_next(slam_odom_t h, const slam_frame_host * f, const slam_frame_host * next, float * trans, float * rot, int rgb_only,
+                                         float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16 && trans && rot);
+    if(int rc = set_device(h)) return rc;
+    if(int rc = ensure_staging(h)) return rc;
+    StagingSlot * sl = find_staged(h, f->depth);
+    if(!sl)
+    {
+        sl = free_slot(h);
+        if(!sl)
+        {
+            sl = &h->slot[0];   // drop a stale prefetch
+            SLAM_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        }
+        if(int rc = stage_frame(h, *sl, f, h->copy_stream)) return rc;
+    }
+    SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl->ready, 0));
+    // enqueue this frame's work, and only then spend host time on the next frame's copies: they overlap the kernels
+    int rc = track_from_device_ptrs(h, sl->depth, sl->rgba, sl->mv, sl->mn, sl->mrgba, sl->poses.data(), sl->depth_cutoff, sl->model_depth_cutoff, trans, rot,
+                                    rgb_only, icp_weight, pyramid, fast_odom, so3, true);
+    if(rc) return rc;
+    if(next && next->depth && !find_staged(h, next->depth))
+    {
+        StagingSlot * other = nullptr;
+        for(auto & cand : h->slot)
+            if(&cand != sl && !cand.pending) other = &cand;
+        if(other) rc = stage_frame(h, *other, next, h->copy_stream);   // the slot still in use by this frame's kernels is left alone
+    }
+    if(h->pending_async)
+    {
+        const int rc2 = finish_device_loop(h, trans, rot);
+        if(!rc) rc = rc2;
+    }
     sl->pending = false;
     return rc;
 }

@@ -113,6 +113,7 @@ def load_library():
     lib.slam_odom_prefetch_host.argtypes = [vp, C.POINTER(FrameHost)]
     lib.slam_odom_track_host.argtypes = [vp, C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
     lib.slam_odom_track_device.argtypes = [vp, C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
+    lib.slam_odom_track_host_next.argtypes = [vp, C.POINTER(FrameHost), C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
     lib.slam_odom_tap_bytes.argtypes = [vp, i, i]
     lib.slam_odom_tap_bytes.restype = C.c_size_t
     lib.slam_odom_tap.argtypes = [vp, i, i, i, vp, C.c_size_t]
@@ -284,8 +285,14 @@ class RGBDOdometry:
     def track_device(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True):
         return self._track(self.lib.slam_odom_track_device, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
 
-    def track_host(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True):
-        return self._track(self.lib.slam_odom_track_host, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
+    def track_host(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True, next_frame=None):
+        if next_frame is None:
+            return self._track(self.lib.slam_odom_track_host, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
+        t = np.ascontiguousarray(trans, dtype=np.float32).reshape(-1).copy()
+        r = np.ascontiguousarray(rot, dtype=np.float32).reshape(-1).copy()
+        _check(self.lib, self.lib.slam_odom_track_host_next(self._h, C.byref(frame), C.byref(next_frame), _fptr(t), _fptr(r), int(bool(rgbOnly)), float(icpWeight),
+                                                            int(bool(pyramid)), int(bool(fastOdom)), int(bool(so3))))
+        return t.reshape(np.shape(trans)), r.reshape(np.shape(rot))
 
     def prefetch_host(self, frame):
         _check(self.lib, self.lib.slam_odom_prefetch_host(self._h, C.byref(frame)))
