@@ -1273,7 +1273,7 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
             }
             rc = launch_model_maps_simple(mv, mn, h->geom[0].rows, h->geom[0].cols, h->levels, s.vprev, s.nprev, 1, R0, t0, s.depth_tmp,
                                           h->maxDepthRGB, h->levels > 3 ? s.vcam : nullptr, h->levels > 3 ? s.ncam : nullptr, h->stream, B, n0 * 16, S,
-                                          B > 1 ? h->d_poses12 : nullptr);
+                                          B > 1 ? h->d_poses12 : nullptr, s.lastDepth[0], s.nextDepth[0], mrgba, rgba, s.lastImage[0], s.nextImage[0], n0 * 4);
             if(rc) return rc;
             h->launches++;
             if(h->levels > 3)
@@ -1290,9 +1290,7 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
                     if(rc) return rc;
                     h->launches++;
                 }
-            rc = launch_rgbd_level0_dual(s.depth_tmp, s.lastDepth[0], s.nextDepth[0], mrgba, s.lastImage[0], rgba, s.nextImage[0], (int)n0, h->stream, B, n0 * 4, S);
-            if(rc) return rc;
-            h->launches++;
+            // level 0 of both RGB-D pyramids was written by the model-map launch
             for(int l = 0; l + 1 < h->levels; l++)
             {
                 rc = launch_rgbd_down_dual(s.lastDepth[l], s.lastDepth[l + 1], s.nextDepth[l + 1], s.lastImage[l], s.lastImage[l + 1], s.nextImage[l],

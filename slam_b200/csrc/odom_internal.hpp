@@ -74,7 +74,9 @@ int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * w
 // helpers exported by prep_kernels.cu that need the full argument structs
 int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
                              int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
-                             cudaStream_t s, int nseq = 1, size_t in_stride = 0, size_t out_stride = 0, const float * poses12 = nullptr);
+                             cudaStream_t s, int nseq = 1, size_t in_stride = 0, size_t out_stride = 0, const float * poses12 = nullptr, float * lastDepth0 = nullptr,
+                             float * nextDepth0 = nullptr, const uchar4 * model_rgba = nullptr, const uchar4 * rgba = nullptr, unsigned char * lastImage0 = nullptr,
+                             unsigned char * nextImage0 = nullptr, size_t rgba_stride = 0);
 int launch_derivatives_simple(int levels, const unsigned char * const * src, short * const * dx, short * const * dy, const int * rows, const int * cols,
                               cudaStream_t s, int nseq = 1, size_t arena_stride = 0);
 

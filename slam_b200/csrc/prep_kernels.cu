@@ -286,6 +286,15 @@ struct ModelMapsArgs
     // batched launch (gridDim.y sequences): byte strides of the inputs / of the arena buffers, per-sequence [R | t] (12 floats each)
     size_t in_stride, out_stride;
     const float * poses12;
+    // frame-level front end: level 0 of populateRGBDData for the model AND the current frame in the same pass
+    // (RGBDOdometryef.cpp:208-235: depth[0] = z of the vertices after the maxDepthRGB cut, image[0] = intensity of the RGBA8 texel)
+    float * lastDepth0;
+    float * nextDepth0;
+    const uchar4 * model_rgba;
+    const uchar4 * rgba;
+    unsigned char * lastImage0;
+    unsigned char * nextImage0;
+    size_t rgba_stride;
 };
 
 __device__ __forceinline__ void store_map_pixel(float * vdst, float * ndst, int plane, int o, float3 v, float3 n, bool transform, const Mat3 & R,
@@ -361,6 +370,12 @@ __global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a0)
             a.ndst[l] = seq_shift(a.ndst[l], a.out_stride);
         }
         a.depth_tmp = seq_shift(a.depth_tmp, a.out_stride);
+        a.lastDepth0 = seq_shift(a.lastDepth0, a.out_stride);
+        a.nextDepth0 = seq_shift(a.nextDepth0, a.out_stride);
+        a.lastImage0 = seq_shift(a.lastImage0, a.out_stride);
+        a.nextImage0 = seq_shift(a.nextImage0, a.out_stride);
+        a.model_rgba = seq_shift(a.model_rgba, a.rgba_stride);
+        a.rgba = seq_shift(a.rgba, a.rgba_stride);
         a.vcam2 = seq_shift(a.vcam2, a.out_stride);
         a.ncam2 = seq_shift(a.ncam2, a.out_stride);
         if(a.poses12)
@@ -396,7 +411,16 @@ __global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a0)
                     v = make_float3(vs.x, vs.y, vs.z);
                     n = make_float3(ns.x, ns.y, ns.z);
                 }
-                if(a.depth_tmp) a.depth_tmp[y * a.cols + x] = depth_from_vertex_z(vs.z, a.depth_cut);
+                const float dz = depth_from_vertex_z(vs.z, a.depth_cut);
+                if(a.depth_tmp) a.depth_tmp[y * a.cols + x] = dz;
+                if(a.lastDepth0)
+                {
+                    const int o0 = y * a.cols + x;
+                    a.lastDepth0[o0] = dz;
+                    a.nextDepth0[o0] = dz;
+                    a.lastImage0[o0] = intensity_pixel(__ldg(a.model_rgba + o0));
+                    a.nextImage0[o0] = intensity_pixel(__ldg(a.rgba + o0));
+                }
                 // level-0 copyMaps writes all three planes, NaN included
                 if(a.transform)
                     store_map_pixel(a.vdst[0], a.ndst[0], plane0, y * a.cols + x, v, n, true, a.R, a.t);
@@ -1012,7 +1036,8 @@ int launch_deriv_cand(int levels, const unsigned char * const * src, const float
 
 int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,
                              int transform, const Mat3 & R, const float3 & t, float * depth_tmp, float depth_cut, float * vcam2, float * ncam2,
-                             cudaStream_t s, int nseq, size_t in_stride, size_t out_stride, const float * poses12)
+                             cudaStream_t s, int nseq, size_t in_stride, size_t out_stride, const float * poses12, float * lastDepth0, float * nextDepth0,
+                             const uchar4 * model_rgba, const uchar4 * rgba, unsigned char * lastImage0, unsigned char * nextImage0, size_t rgba_stride)
 {
     ModelMapsArgs a = {};
     a.vsrc = vsrc;
@@ -1035,6 +1060,13 @@ int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows,
     a.in_stride = in_stride;
     a.out_stride = out_stride;
     a.poses12 = poses12;
+    a.lastDepth0 = lastDepth0;
+    a.nextDepth0 = nextDepth0;
+    a.model_rgba = model_rgba;
+    a.rgba = rgba;
+    a.lastImage0 = lastImage0;
+    a.nextImage0 = nextImage0;
+    a.rgba_stride = rgba_stride;
     return launch_model_maps(a, s, nseq);
 }
 
