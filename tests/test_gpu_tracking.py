@@ -626,4 +626,9 @@ def test_streaming_batch_engine_ragged_size(built):
         first = ob.get_trace(b)[0]
         assert (first["rgb_count"], first["rgb_sigma"], first["icp"][28]) == (counts[b]["rgb_count"], counts[b]["rgb_sigma"], counts[b]["icp"][28]), f"sequence {b}"
         assert np.abs(tb[b] - singles[b][0]).max() < 2e-4 and np.abs(rb[b] - singles[b][1]).max() < 2e-4, f"sequence {b}: {np.abs(tb[b] - singles[b][0]).max()}"
+    # the one-call-per-frame entry point (fused preparation launches, two pyramid levels per launch) at the same ragged size:
+    # same buffers, same engine => the same bits as the separate calls above
+    frame = ob.make_frame(depth, rgba, mv, mn, mrgba, P, 3.0, 20.0)
+    t2, r2 = ob.track_device(frame, P[:, :3, 3].copy(), P[:, :3, :3].copy(), False, 10.0, True, False, False)
+    assert np.array_equal(t2, tb) and np.array_equal(r2, rb)
     ob.close()
