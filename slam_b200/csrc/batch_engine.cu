@@ -1246,7 +1246,7 @@ int batch_enqueue(BatchDevice & d, const GnLaunch & L, const GnSeqIn * h_seq_in_
         SLAM_CUDA_TRY(cudaEventCreate(&e1));
         SLAM_CUDA_TRY(cudaEventRecord(e0, s));
     }
-    if(use_graphs() && !g_detail.on)
+    if(use_graphs() && !g_detail.on && s != nullptr)   // (the legacy default stream cannot be captured)
     {
         // Every argument of every launch of a step is a constant of (mode, geometry, handle): the sequence is captured once
         // per such key as a CUDA graph and replayed, which removes ~75 stream launches and ~80 event operations per step

@@ -632,3 +632,36 @@ def test_streaming_batch_engine_ragged_size(built):
     t2, r2 = ob.track_device(frame, P[:, :3, 3].copy(), P[:, :3, :3].copy(), False, 10.0, True, False, False)
     assert np.array_equal(t2, tb) and np.array_equal(r2, rb)
     ob.close()
+
+
+def test_host_buffer_entry_points_equal_device_entry_point(setup):
+    """slam_odom_track_host (+ prefetch) and slam_odom_track_host_next (the next frame's copies issued behind this frame's
+    kernels) from pinned host buffers == slam_odom_track_device on the same frames, bit for bit, over a short sequence."""
+    t = setup["torch"]
+    scene, poses = setup["scene"], setup["poses"]
+    i = setup["intr"]
+    ks = (400, 401, 402, 403)
+    frames = [frame_pair(scene, poses, k) for k in ks]
+    first = scene.render_frame(poses[ks[0] - 1])[1]
+    mk = lambda: setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    dev, host, nxt = mk(), mk(), mk()
+    pin = lambda a: t.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).pin_memory()
+    hfr = [{k: pin(v) for k, v in f.items() if k not in ("model_pose", "gt_pose")} for f in frames]
+    dfr = [to_device(f) for f in frames]
+    t.cuda.synchronize()
+    for o in (dev, host, nxt):
+        o.initFirstRGB(t.from_numpy(first).to("cuda:0"))
+    hframes = [host.make_frame(h["depth"], h["rgba"], h["mv"], h["mn"], h["mrgba"], f["model_pose"], 3.0, 20.0) for h, f in zip(hfr, frames)]
+    for n, f in enumerate(frames):
+        P = f["model_pose"]
+        prior = (P[:3, 3].copy(), P[:3, :3].copy())
+        d = dfr[n]
+        want = dev.track_device(dev.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, 3.0, 20.0), *prior)
+        if n + 1 < len(frames):
+            host.prefetch_host(hframes[n + 1]) if n % 2 == 0 else None     # with and without an explicit prefetch
+        got_h = host.track_host(hframes[n], *prior)
+        got_n = nxt.track_host(hframes[n], *prior, next_frame=hframes[n + 1] if n + 1 < len(frames) else None)
+        for got in (got_h, got_n):
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), f"frame {n}"
+    for o in (dev, host, nxt):
+        o.close()
