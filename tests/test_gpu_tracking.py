@@ -665,3 +665,49 @@ def test_host_buffer_entry_points_equal_device_entry_point(setup):
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), f"frame {n}"
     for o in (dev, host, nxt):
         o.close()
+
+
+def test_properties_identity_and_rigid_equivariance(setup):
+    """Size-independent properties of the whole tracker at the full 640x480 size:
+      * identity: a frame tracked against the model predicted at the frame's own pose stays where it is;
+      * rigid equivariance: moving the world by a rigid transform G (model pose -> G * model pose, same images) moves the
+        tracked pose by G: every kernel works on camera-frame maps + a pose, so only fp32 rounding of the global-frame
+        coordinates differs;
+      * the 6x6 system handed to the solver is symmetric with a non-negative diagonal (lastA)."""
+    t = setup["torch"]
+    scene, poses = setup["scene"], setup["poses"]
+    i = setup["intr"]
+    mk = lambda: setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    k = 640
+    # ---- identity
+    fr = frame_pair(scene, poses, k, model_k=k)
+    d = to_device(fr)
+    t.cuda.synchronize()
+    o = mk()
+    tt, rr = run_frame(o, d, so3=False)
+    # (1 mm: the depth image is quantised to millimetres and the model ray-cast is not, so the optimum is not exactly the prior)
+    assert np.abs(tt - fr["gt_pose"][:3, 3]).max() < 1e-3 and np.abs(rr - fr["gt_pose"][:3, :3]).max() < 1e-3
+    A = np.array(o.stats().lastA[:]).reshape(6, 6)
+    assert np.allclose(A, A.T, rtol=0, atol=0) and (np.diag(A) > 0).all()
+    assert np.linalg.eigvalsh(A).min() > 0, "JtJ must be positive definite on a well-textured frame"
+    o.close()
+    # ---- rigid equivariance
+    fr = frame_pair(scene, poses, k)
+    d = to_device(fr)
+    ang = 0.7
+    G = np.eye(4, dtype=np.float64)
+    G[:3, :3] = [[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]
+    G[:3, 3] = [0.4, -0.25, 1.1]
+    o1, o2 = mk(), mk()
+    t1, r1 = run_frame(o1, d, so3=False)
+    d2 = dict(d)
+    d2["model_pose"] = (G @ fr["model_pose"].astype(np.float64)).astype(np.float32)
+    t2, r2 = run_frame(o2, d2, so3=False)
+    T1 = np.eye(4)
+    T1[:3, :3], T1[:3, 3] = r1, t1
+    want = G @ T1
+    assert np.abs(t2 - want[:3, 3]).max() < 1e-4, f"translation off by {np.abs(t2 - want[:3, 3]).max()}"
+    assert np.abs(r2 - want[:3, :3]).max() < 1e-4
+    assert abs(o1.stats().lastICPCount - o2.stats().lastICPCount) <= 2e-3 * o1.stats().lastICPCount
+    o1.close()
+    o2.close()
