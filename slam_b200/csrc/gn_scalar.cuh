@@ -59,81 +59,149 @@ static __device__ __noinline__ void level_begin(GnShared & sh, const LevelGeom g
     }
 }
 
-// cofactor index table of smath::mat3_inverse: r[k] = det2(m[a], m[b], m[c], m[d]) / det
-static __constant__ int kCof[9][4] = {{4, 8, 5, 7}, {2, 7, 1, 8}, {1, 5, 2, 4}, {5, 6, 3, 8}, {0, 8, 2, 6}, {2, 3, 0, 5}, {3, 7, 4, 6}, {1, 6, 0, 7}, {0, 4, 1, 3}};
+// =====================================================================================
+// Register-resident bookkeeping.  ALL lanes of warp 0 evaluate the same expressions on the same values
+// (one instruction stream, no divergence, no shared-memory stage between the steps of the dependent chain):
+// a warp-wide fp64 instruction costs the same issue slots whether one lane or 32 are active, and the chain
+// solve -> Rodrigues -> resultRt -> inverse -> K R K^-1 is what bounds an iteration of a single sequence
+// (ncu: the other 15 warps wait at the block barrier for it).  Every entry is evaluated with exactly the
+// expression small_math.hpp uses for it, so the host-stepped loop and this code agree bit for bit.
+// =====================================================================================
 
-// From sh.resultRt: krk = float(K R K^-1), kt = float(K t) with [R|t] = resultRt^-1 (RGBDOdometryef.cpp:422-432),
-// and the current pose Rcurr/tcurr = [Rprev|tprev] * float(resultRt)^-1 (:563-575).  Warp 0, all lanes.
-__device__ __forceinline__ void warp_prepare(GnShared & sh, const bool with_pose)
+// From the affine rows M (3x4, row-major) of resultRt: krk = float(K R K^-1), kt = float(K t) with
+// [R|t] = resultRt^-1 (RGBDOdometryef.cpp:422-432) and, with_pose, the current pose
+// Rcurr/tcurr = [Rprev|tprev] * float(resultRt)^-1 (:563-575).  Warp 0, all lanes; lane 0 stores.
+__device__ __forceinline__ void prepare_from_rows(GnShared & sh, const double (&M)[12], const bool with_pose)
 {
     const int lane = threadIdx.x & 31;
-    const double * M = sh.resultRt;   // row-major 4x4, affine
-    // ---- stage 1: Mi = (3x3 part)^-1 (lanes 0..8); float isometry inverse pieces (lanes 12..23)
-    if(lane < 9)
+    double K[9], Kinv[9];
+#pragma unroll
+    for(int k = 0; k < 9; k++)
     {
-        auto m = [&](int i) { return M[(i / 3) * 4 + (i % 3)]; };
-        const double c00 = smath::det2(m(4), m(8), m(5), m(7));
-        const double c01 = smath::det2(m(5), m(6), m(3), m(8));
-        const double c02 = smath::det2(m(3), m(7), m(4), m(6));
-        const double det = smath::dot3(m(0), c00, m(1), c01, m(2), c02);
-        const double id = smath::dvd(1.0, det);
-        const double cof = smath::det2(m(kCof[lane][0]), m(kCof[lane][1]), m(kCof[lane][2]), m(kCof[lane][3]));
-        sh.Mi[lane] = smath::mul(cof, id);
+        K[k] = sh.K[k];
+        Kinv[k] = sh.Kinv[k];
     }
-    else if(with_pose && lane >= 12 && lane < 15)
+    const double R3[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+    double Mi[9], KR[9], KRK[9], tinv[3];
+    smath::mat3_inverse(R3, Mi);
+    smath::mat3_mul(K, Mi, KR);
+#pragma unroll
+    for(int i = 0; i < 3; i++) tinv[i] = -smath::dot3(Mi[i * 3 + 0], M[3], Mi[i * 3 + 1], M[7], Mi[i * 3 + 2], M[11]);
+    smath::mat3_mul(KR, Kinv, KRK);
+    float kt[3];
+#pragma unroll
+    for(int i = 0; i < 3; i++) kt[i] = (float)smath::dot3(K[i * 3 + 0], tinv[0], K[i * 3 + 1], tinv[1], K[i * 3 + 2], tinv[2]);
+    if(lane == 0)
     {
+#pragma unroll
+        for(int k = 0; k < 9; k++) sh.krk[k] = (float)KRK[k];
+#pragma unroll
+        for(int k = 0; k < 3; k++) sh.kt[k] = kt[k];
+    }
+    if(with_pose)
+    {
+        float Rp[9], tp[3], Mf[12], tinvf[3];
+#pragma unroll
+        for(int k = 0; k < 9; k++) Rp[k] = sh.Rprev[k];
+#pragma unroll
+        for(int k = 0; k < 3; k++) tp[k] = sh.tprev[k];
+#pragma unroll
+        for(int k = 0; k < 12; k++) Mf[k] = (float)M[k];
         // tinv[i] = -(Rinv[i][:] . to), Rinv = Ro^T, Ro/to = float(resultRt)
-        const int i = lane - 12;
-        sh.tinvf[i] = -smath::dot3((float)M[0 * 4 + i], (float)M[3], (float)M[1 * 4 + i], (float)M[7], (float)M[2 * 4 + i], (float)M[11]);
-    }
-    else if(with_pose && lane >= 15 && lane < 24)
-    {
-        // Rcurr = Rprev * Rinv
-        const int i = (lane - 15) / 3, j = (lane - 15) % 3;
-        sh.Rcurr[i * 3 + j] = smath::dot3(sh.Rprev[i * 3 + 0], (float)M[j * 4 + 0], sh.Rprev[i * 3 + 1], (float)M[j * 4 + 1], sh.Rprev[i * 3 + 2], (float)M[j * 4 + 2]);
-    }
-    __syncwarp();
-    // ---- stage 2: KR = K * Mi (lanes 0..8), tinv = -Mi * t (lanes 9..11), tcurr (lanes 12..14)
-    if(lane < 9)
-    {
-        const int i = lane / 3, j = lane % 3;
-        sh.KR[lane] = smath::dot3(sh.K[i * 3 + 0], sh.Mi[0 * 3 + j], sh.K[i * 3 + 1], sh.Mi[1 * 3 + j], sh.K[i * 3 + 2], sh.Mi[2 * 3 + j]);
-    }
-    else if(lane < 12)
-    {
-        const int i = lane - 9;
-        sh.tinv[i] = -smath::dot3(sh.Mi[i * 3 + 0], M[3], sh.Mi[i * 3 + 1], M[7], sh.Mi[i * 3 + 2], M[11]);
-    }
-    else if(with_pose && lane < 15)
-    {
-        const int i = lane - 12;
-        sh.tcurr[i] = smath::add(smath::dot3(sh.Rprev[i * 3 + 0], sh.tinvf[0], sh.Rprev[i * 3 + 1], sh.tinvf[1], sh.Rprev[i * 3 + 2], sh.tinvf[2]), sh.tprev[i]);
-    }
-    __syncwarp();
-    // ---- stage 3: KRK = KR * Kinv (lanes 0..8), kt = K * tinv (lanes 9..11)
-    if(lane < 9)
-    {
-        const int i = lane / 3, j = lane % 3;
-        sh.krk[lane] = (float)smath::dot3(sh.KR[i * 3 + 0], sh.Kinv[0 * 3 + j], sh.KR[i * 3 + 1], sh.Kinv[1 * 3 + j], sh.KR[i * 3 + 2], sh.Kinv[2 * 3 + j]);
-    }
-    else if(lane < 12)
-    {
-        const int i = lane - 9;
-        sh.kt[i] = (float)smath::dot3(sh.K[i * 3 + 0], sh.tinv[0], sh.K[i * 3 + 1], sh.tinv[1], sh.K[i * 3 + 2], sh.tinv[2]);
+#pragma unroll
+        for(int i = 0; i < 3; i++) tinvf[i] = -smath::dot3(Mf[0 * 4 + i], Mf[3], Mf[1 * 4 + i], Mf[7], Mf[2 * 4 + i], Mf[11]);
+        float Rc[9], tc[3];
+        // Rcurr = Rprev * Rinv, tcurr = Rprev * tinv + tprev
+#pragma unroll
+        for(int i = 0; i < 3; i++)
+        {
+#pragma unroll
+            for(int j = 0; j < 3; j++) Rc[i * 3 + j] = smath::dot3(Rp[i * 3 + 0], Mf[j * 4 + 0], Rp[i * 3 + 1], Mf[j * 4 + 1], Rp[i * 3 + 2], Mf[j * 4 + 2]);
+            tc[i] = smath::add(smath::dot3(Rp[i * 3 + 0], tinvf[0], Rp[i * 3 + 1], tinvf[1], Rp[i * 3 + 2], tinvf[2]), tp[i]);
+        }
+        if(lane == 0)
+        {
+#pragma unroll
+            for(int k = 0; k < 9; k++) sh.Rcurr[k] = Rc[k];
+#pragma unroll
+            for(int k = 0; k < 3; k++) sh.tcurr[k] = tc[k];
+        }
     }
     __syncwarp();
 }
 
-// smath::gauss_jordan_solve<double, 6> with the 42 entries of [A | b] spread over the lanes of warp 0
-// (same per-entry arithmetic, bit-identical result).  sh.aug[0] holds the system on entry; x lands in sh.x.
-__device__ __forceinline__ void warp_gauss_jordan(GnShared & sh)
+// The parameters of the first iteration of a level (Rcurr/tcurr carry over): resultRt comes from shared memory.
+__device__ __forceinline__ void warp_prepare(GnShared & sh, const bool with_pose)
+{
+    double M[12];
+#pragma unroll
+    for(int k = 0; k < 12; k++) M[k] = sh.resultRt[k];
+    prepare_from_rows(sh, M, with_pose);
+}
+
+// Degenerate system (a pivot not safely positive): the pivoted / pseudo-inverse LDL^T of small_math.hpp.  Lane 0.
+static __device__ __noinline__ void solve_fallback(GnShared & sh)
+{
+    double A[36], b[6], x[6];
+    for(int k = 0; k < 36; k++) A[k] = sh.res.lastA[k];
+    for(int k = 0; k < 6; k++) b[k] = sh.res.lastb[k];
+    smath::ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON);
+    for(int k = 0; k < 6; k++) sh.x[k] = x[k];
+}
+
+// RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems, solve, update resultRt, then the next
+// iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
+//
+// smath::gauss_jordan_solve<double, 6> with one COLUMN of [A | b] per lane (lane j < 7 holds column j, the other
+// lanes shadow column 6): step k broadcasts column k with shuffles, every lane forms 1 / pivot itself and updates
+// its own column -- the per-entry arithmetic of the serial routine, hence the same bits.
+__device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec, const long long t_start)
 {
     const int lane = threadIdx.x & 31;
+    const int j = lane < 7 ? lane : 6;
+#define GN_SSTAMP(idx) do { if(rec) rec->t_solve[idx] = (unsigned)(clock64() - t_start); } while(0)
+    // the affine rows of resultRt (needed after the solve: fetched now, off the dependent chain)
+    double Rt[12];
+#pragma unroll
+    for(int k = 0; k < 12; k++) Rt[k] = sh.resultRt[k];
+    // ---- column j of lastA | lastb: entry (i, j) is element (min, max) of the row-major upper triangle of the
+    //      6x7 augmented system (reduce.cu:475-486)
+    double c[6];
+    {
+        const double w = icpWeight;
+        const double ww = (j == 6) ? w : smath::mul(w, w);
+#pragma unroll
+        for(int i = 0; i < 6; i++)
+        {
+            const int a = i < j ? i : j, b = i < j ? j : i;
+            const int idx = 7 * a - (a * (a - 1)) / 2 + (b - a);
+            const float vi = sh.total[idx];
+            const float vr = sh.total[32 + idx];
+            c[i] = (icp && rgb) ? smath::add((double)vr, smath::mul(ww, (double)vi)) : (icp ? (double)vi : (double)vr);
+        }
+    }
+    if(lane < 6)
+    {
+#pragma unroll
+        for(int i = 0; i < 6; i++) sh.res.lastA[i * 6 + lane] = c[i];
+    }
+    else if(lane == 6)
+    {
+#pragma unroll
+        for(int i = 0; i < 6; i++) sh.res.lastb[i] = c[i];
+    }
+    else if(lane == 7 && icp)
+    {
+        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
+        sh.res.lastICPCount = sh.total[28];
+    }
+    GN_SSTAMP(0);
+    // ---- x = A^-1 b
     double dmax = 0;
 #pragma unroll
     for(int i = 0; i < 6; i++)
     {
-        const double d = sh.aug[0][i * 7 + i];
+        const double d = __shfl_sync(0xffffffffu, c[i], i);
         dmax = d > dmax ? d : dmax;
     }
     const double floor_d = smath::mul(dmax, 1e-9);
@@ -141,128 +209,68 @@ __device__ __forceinline__ void warp_gauss_jordan(GnShared & sh)
 #pragma unroll
     for(int k = 0; k < 6; k++)
     {
-        const double * src = sh.aug[k & 1];
-        double * dst = sh.aug[(k & 1) ^ 1];
-        const double p = src[k * 7 + k];
+        double colk[6];
+#pragma unroll
+        for(int i = 0; i < 6; i++) colk[i] = __shfl_sync(0xffffffffu, c[i], k);
+        const double p = colk[k];
         ok = ok && (p > floor_d);
         const double inv = smath::dvd(1.0, p);
+        const double rkj = smath::mul(c[k], inv);
+        const bool upd = j > k;
 #pragma unroll
-        for(int pass = 0; pass < 2; pass++)
+        for(int i = 0; i < 6; i++)
         {
-            const int e = lane + 32 * pass;
-            if(e < 42)
-            {
-                const int i = e / 7, j = e - i * 7;
-                double v = src[e];
-                if(j > k)
-                {
-                    const double rkj = smath::mul(src[k * 7 + j], inv);
-                    v = (i == k) ? rkj : smath::sub(v, smath::mul(src[i * 7 + k], rkj));
-                }
-                dst[e] = v;
-            }
-        }
-        __syncwarp();
-    }
-    // six steps: the result is back in aug[0]
-    if(lane < 6) sh.x[lane] = sh.aug[0][lane * 7 + 6];
-    if(lane == 0) sh.solve_ok = ok ? 1 : 0;
-    __syncwarp();
-}
-
-// Degenerate system (a pivot not safely positive): the pivoted / pseudo-inverse LDL^T of small_math.hpp.  Lane 0.
-static __device__ __noinline__ void solve_fallback(GnShared & sh)
-{
-    double A[36], b[6], x[6];
-    for(int k = 0; k < 36; k++) A[k] = sh.A[k];
-    for(int k = 0; k < 6; k++) b[k] = sh.b[k];
-    smath::ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON);
-    for(int k = 0; k < 6; k++) sh.x[k] = x[k];
-}
-
-// Incremental rotation of the step (odom/utils.h:16-52).  Lane 0.
-static __device__ __noinline__ void rodrigues_core(GnShared & sh)
-{
-    double r[3] = {sh.x[3], sh.x[4], sh.x[5]}, R[9];
-    smath::rodrigues(r, R);
-    for(int k = 0; k < 9; k++) sh.Rinc[k] = R[k];
-}
-
-// RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems, solve, update resultRt, then the next
-// iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
-__device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec, const long long t_start)
-{
-    const int lane = threadIdx.x & 31;
-#define GN_SSTAMP(idx) do { if(rec) rec->t_solve[idx] = (unsigned)(clock64() - t_start); } while(0)
-    // ---- stage 0: lastA / lastb (upper triangle + mirror), stats
-    if(lane < 27)
-    {
-        // lane -> (i, j) of the row-major upper triangle of the 6x7 augmented system (reduce.cu:475-486)
-        int i = 0, rem = lane;
-        while(rem >= 7 - i)
-        {
-            rem -= 7 - i;
-            i++;
-        }
-        const int j = i + rem;
-        const float vi = sh.total[lane];
-        const float vr = sh.total[32 + lane];
-        double v;
-        if(icp && rgb)
-        {
-            const double w = icpWeight;
-            v = (j == 6) ? smath::add((double)vr, smath::mul(w, (double)vi)) : smath::add((double)vr, smath::mul(smath::mul(w, w), (double)vi));
-        }
-        else
-            v = icp ? (double)vi : (double)vr;
-        if(j == 6)
-        {
-            sh.b[i] = v;
-            sh.aug[0][i * 7 + 6] = v;
-        }
-        else
-        {
-            sh.A[i * 6 + j] = v;
-            sh.A[j * 6 + i] = v;
-            sh.aug[0][i * 7 + j] = v;
-            sh.aug[0][j * 7 + i] = v;
+            const double v = (i == k) ? rkj : smath::sub(c[i], smath::mul(colk[i], rkj));
+            c[i] = upd ? v : c[i];
         }
     }
-    else if(lane == 27 && icp)
-    {
-        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
-        sh.res.lastICPCount = sh.total[28];
-    }
-    __syncwarp();
-    GN_SSTAMP(0);
-    // ---- stage 1: x = A^-1 b (parallel elimination), then the incremental rotation
-    warp_gauss_jordan(sh);
+    double x[6];
+#pragma unroll
+    for(int i = 0; i < 6; i++) x[i] = __shfl_sync(0xffffffffu, c[i], 6);
     GN_SSTAMP(1);
-    if(lane == 0)
+    if(!ok)   // uniform: every lane saw the same pivots
     {
-        if(!sh.solve_ok) solve_fallback(sh);
-        rodrigues_core(sh);
+        __syncwarp();
+        if(lane == 0) solve_fallback(sh);
+        __syncwarp();
+#pragma unroll
+        for(int i = 0; i < 6; i++) x[i] = sh.x[i];
     }
-    __syncwarp();
+    // ---- incremental rotation of the step (odom/utils.h:16-52)
+    double Rinc[9];
+    smath::rodrigues(x + 3, Rinc);
     GN_SSTAMP(2);
-    // ---- stage 2: resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), rows 0..2
+    // ---- resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), rows 0..2 (row 3 stays 0 0 0 1)
+    double M[12];
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+        for(int q = 0; q < 4; q++)
+        {
+            double s = smath::mul(Rinc[i * 3 + 0], Rt[0 * 4 + q]);   // add(0, x) == x
+            s = smath::add(s, smath::mul(Rinc[i * 3 + 1], Rt[1 * 4 + q]));
+            s = smath::add(s, smath::mul(Rinc[i * 3 + 2], Rt[2 * 4 + q]));
+            s = smath::add(s, smath::mul(x[i], q == 3 ? 1.0 : 0.0));
+            M[i * 4 + q] = s;
+        }
     if(lane < 12)
     {
-        const int i = lane / 4, j = lane % 4;
-        double s = smath::mul(sh.Rinc[i * 3 + 0], sh.resultRt[0 * 4 + j]);   // add(0, x) == x
-        s = smath::add(s, smath::mul(sh.Rinc[i * 3 + 1], sh.resultRt[1 * 4 + j]));
-        s = smath::add(s, smath::mul(sh.Rinc[i * 3 + 2], sh.resultRt[2 * 4 + j]));
-        s = smath::add(s, smath::mul(sh.x[i], sh.resultRt[3 * 4 + j]));
-        sh.newRt[lane] = s;
+        // lane-indexed store of a register array: selected with predicated moves, no local memory
+        double v = M[0];
+#pragma unroll
+        for(int k = 1; k < 12; k++) v = (lane == k) ? M[k] : v;
+        sh.resultRt[lane] = v;
     }
-    __syncwarp();
-    if(lane < 12) sh.resultRt[lane] = sh.newRt[lane];
-    if(lane >= 12 && lane < 18) sh.res.lastb[lane - 12] = sh.b[lane - 12];
-    for(int k = lane; k < 36; k += 32) sh.res.lastA[k] = sh.A[k];
-    __syncwarp();
+    else if(lane < 18)
+    {
+        double v = x[0];
+#pragma unroll
+        for(int k = 1; k < 6; k++) v = (lane - 12 == k) ? x[k] : v;
+        sh.x[lane - 12] = v;
+    }
     GN_SSTAMP(3);
-    // ---- stages 3..5: parameters of the next iteration
-    warp_prepare(sh, true);
+    // ---- parameters of the next iteration
+    prepare_from_rows(sh, M, true);
     GN_SSTAMP(4);
     if(lane == 0)
     {
