@@ -35,18 +35,46 @@ namespace slam {
 
 constexpr int kIcpChunk = 3;    // ICP gathers in flight per thread (register budget)
 
-__device__ __forceinline__ void group_barrier(unsigned * ctr, unsigned & target, unsigned G)
+// ctr points at the 64-bit barrier word of the group; the arrival counter is its high half.
+__device__ __forceinline__ void group_barrier(unsigned long long * ctr, unsigned & target, unsigned G)
 {
     __syncthreads();
     if(G > 1 && threadIdx.x == 0)
     {
+        unsigned * hi = reinterpret_cast<unsigned *>(ctr) + 1;
         target += G;
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(hi), "r"(1u) : "memory");
         unsigned v;
         do
         {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(hi) : "memory");
         } while((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// Barrier + all-reduce of one small unsigned per CTA in the same round trip: thread 0 adds `mine` to the low half of the
+// barrier word (relaxed) before it arrives on the high half (release), and polls the whole word: the value that shows the
+// last arrival also holds every CTA's contribution (a later contribution needs another barrier in between).  The low
+// half is a running sum modulo 2^32; `running` carries the previous total.  Returns the sum over the group in sh_out
+// (thread 0 writes it before the closing __syncthreads()).
+__device__ __forceinline__ void group_barrier_sum(unsigned long long * ctr, unsigned & target, unsigned G, unsigned mine, unsigned & running, int * sh_out)
+{
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        unsigned * lo = reinterpret_cast<unsigned *>(ctr);
+        target += G;
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(lo), "r"(mine) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(lo + 1), "r"(1u) : "memory");
+        unsigned long long v;
+        do
+        {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        } while((int)((unsigned)(v >> 32) - target) < 0);
+        const unsigned now = (unsigned)v;
+        *sh_out = (int)(now - running);
+        running = now;
     }
     __syncthreads();
 }
@@ -57,8 +85,10 @@ __device__ __forceinline__ void group_barrier(unsigned * ctr, unsigned & target,
 // With count_cols, slots 29 / 30 / 31 carry exact small integers as floats (RGB correspondence count, low
 // 12 bits and high bits of the squared-residual sum); they are recombined into the two int32 columns
 // 29 (count) and 30 (sigma) of the partial row.
-__device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, float * dst, const bool count_cols = false)
+// Returns (thread 0, with count_cols) the CTA's contribution to the mid-iteration all-reduce: count | (sigma != 0) << 24.
+__device__ __forceinline__ unsigned cta_publish32(float (&v)[32], GnShared & sh, float * dst, const bool count_cols = false)
 {
+    unsigned word = 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float s = warp_reduce_scatter32(v);
     sh.red[wid * 32 + lane] = s;
@@ -73,9 +103,13 @@ __device__ __forceinline__ void cta_publish32(float (&v)[32], GnShared & sh, flo
             const float hi = __shfl_sync(0xffffffffu, total, 31);
             if(threadIdx.x == 29) total = __int_as_float((int)total);
             if(threadIdx.x == 30) total = __int_as_float((int)total + ((int)hi << 12));
+            const unsigned cnt = (unsigned)__float_as_int(__shfl_sync(0xffffffffu, total, 29));
+            const unsigned sig = (unsigned)__float_as_int(__shfl_sync(0xffffffffu, total, 30));
+            word = cnt + (sig != 0u ? (1u << 24) : 0u);
         }
         dst[threadIdx.x] = total;
     }
+    return word;
 }
 
 // Same for two per-thread ints (count, sigma) -> dst[0..1].
@@ -185,6 +219,120 @@ __device__ __forceinline__ void fold_count_sigma(GnShared & sh, const float * ro
     }
 }
 
+// The buffers of one pyramid level of one sequence.  Read field by field from the kernel parameter (one sequence:
+// constant-bank loads, no local copy of the block) or from the per-sequence array in global memory.
+struct LevelPtrs
+{
+    const float * vcurr, * ncurr, * vprev, * nprev, * lastDepth, * nextDepth;
+    const unsigned char * lastImage, * nextImage, * lastNextImage;
+    const short * dIdx, * dIdy;
+    Corres * corres;
+};
+#define GN_LEVEL_FIELDS(S) \
+    p.vcurr = (S).vcurr[lvl]; p.ncurr = (S).ncurr[lvl]; p.vprev = (S).vprev[lvl]; p.nprev = (S).nprev[lvl]; \
+    p.lastDepth = (S).lastDepth[lvl]; p.nextDepth = (S).nextDepth[lvl]; p.lastImage = (S).lastImage[lvl]; \
+    p.nextImage = (S).nextImage[lvl]; p.lastNextImage = (S).lastNextImage[lvl]; p.dIdx = (S).dIdx[lvl]; \
+    p.dIdy = (S).dIdy[lvl]; p.corres = (S).corres[lvl];
+__device__ __forceinline__ LevelPtrs level_ptrs(const bool one, const GnSeqIn & seq0, const GnSeqIn * seqs, int seq, int lvl)
+{
+    LevelPtrs p;
+    if(one)
+    {
+        GN_LEVEL_FIELDS(seq0)
+    }
+    else
+    {
+        GN_LEVEL_FIELDS(seqs[seq])
+    }
+    return p;
+}
+
+// Pose-independent half of the photometric association (reduce.cu:780-807) for NS slots of a thread at once, with every
+// load of every slot issued before the first use (ONE round trip to L2 per batch instead of a chain of early-exit
+// branches per pixel): the clipped 4x4 all-nonzero window of nextImage, the gradient pair (from dIdx/dIdy, or derived
+// from the same window with the arithmetic of utils.cu:582-606 when no derivative images were made), nextDepth.
+template <int C0, int NS>
+__device__ __forceinline__ void candidate_batch(const ResidualArgs & a, const bool derive, const int gtid, const int gthreads, const int nslots, const int plane,
+                                                unsigned & cand, float (&c_d1)[kSlotChunk], float (&c_img)[kSlotChunk], short (&c_gx)[kSlotChunk],
+                                                short (&c_gy)[kSlotChunk])
+{
+    unsigned char w[NS][16];
+    float d1[NS];
+    short gxl[NS], gyl[NS];
+    int px[NS], py[NS];
+    bool live[NS];
+#pragma unroll
+    for(int s = 0; s < NS; s++)
+    {
+        const int c = C0 + s;
+        const int k = gtid + c * gthreads;
+        live[s] = (c < nslots) && (k < plane);
+        const int kk = live[s] ? k : 0;
+        py[s] = kk / a.cols;
+        px[s] = kk - py[s] * a.cols;
+#pragma unroll
+        for(int r = 0; r < 4; r++)
+#pragma unroll
+            for(int q = 0; q < 4; q++)
+            {
+                const int u = min(max(py[s] - 2 + r, 0), a.rows - 1), v = min(max(px[s] - 2 + q, 0), a.cols - 1);
+                w[s][r * 4 + q] = __ldg(a.nextImage + u * a.cols + v);
+            }
+        d1[s] = __ldg(a.nextDepth + kk);
+        gxl[s] = derive ? (short)0 : __ldg(a.dIdx + kk);
+        gyl[s] = derive ? (short)0 : __ldg(a.dIdy + kk);
+    }
+#pragma unroll
+    for(int s = 0; s < NS; s++)
+    {
+        const int c = C0 + s;
+        const int x = px[s], y = py[s];
+        bool ok = live[s] && (x < a.cols - 5 && y < a.rows - 1);
+        // window taps the reference's clipped loops never visit (rows / columns below 0) do not vote
+#pragma unroll
+        for(int r = 0; r < 4; r++)
+#pragma unroll
+            for(int q = 0; q < 4; q++)
+            {
+                const bool visited = (y - 2 + r >= 0) && (x - 2 + q >= 0);
+                ok = ok && (!visited || w[s][r * 4 + q] > 0);
+            }
+        short gx = gxl[s], gy = gyl[s];
+        if(derive)
+        {
+            if(x >= 1 && y >= 1 && x < a.cols - 1 && y < a.rows - 1)
+            {
+                // interior: the nine taps are window entries (r + 1, q + 1), accumulated in the reference's order
+                const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+                const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+                float dxVal = 0, dyVal = 0;
+#pragma unroll
+                for(int t = 0; t < 9; t++)
+                {
+                    const float v = (float)w[s][(t / 3 + 1) * 4 + (t % 3 + 1)];
+                    dxVal = __fmaf_rn(v, fgx[8 - t], dxVal);
+                    dyVal = __fmaf_rn(v, fgy[8 - t], dyVal);
+                }
+                gx = (short)dxVal;
+                gy = (short)dyVal;
+            }
+            else if(ok)
+                derivative_pixel(a.nextImage, a.rows, a.cols, x, y, gx, gy);   // image border: the clipped loop itself
+        }
+        const int valx = gx, valy = gy;
+        const float mTwo = (valx * valx) + (valy * valy);
+        ok = ok && (mTwo >= a.minScale) && !isnan(d1[s]);
+        if(ok)
+        {
+            cand |= 1u << c;
+            c_d1[c] = d1[s];
+            c_img[c] = static_cast<float>(w[s][2 * 4 + 2]);   // the pixel itself
+            c_gx[c] = gx;
+            c_gy[c] = gy;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kGnThreads, 1)
 k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, float * partials, GnResult * results, slam_step_record * trace,
@@ -196,7 +344,8 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     const int rank = blockIdx.x - group * G;
     if(group >= groups) return;
 
-    unsigned * bar = &ctl->barrier[group];
+    unsigned long long * bar = &ctl->barrier[group];
+    unsigned sum_running = ctl->sum_base[group];   // thread 0's copy is the one that is used
     // the counter is never reset: every launch starts from the value the previous launch ended with, published in
     // ctl->base by the group leader (stable for the whole launch: it is rewritten only at the very end)
     unsigned target = ctl->base[group];
@@ -213,11 +362,28 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 
     for(int seq = group; seq < L.batch; seq += groups)
     {
-        const GnSeqIn & in = (L.batch == 1) ? seq0 : seqs[seq];
         slam_step_record * tr = (L.trace && leader) ? trace + (size_t)seq * kGnMaxTrace : nullptr;
         int ntr = 0;
 
-        if(threadIdx.x == 0) seq_begin(sh, in);
+        if(threadIdx.x == 0)
+        {
+            float Rp[9], tp[3];
+            if(L.batch == 1)
+            {
+#pragma unroll
+                for(int k = 0; k < 9; k++) Rp[k] = seq0.Rprev[k];
+#pragma unroll
+                for(int k = 0; k < 3; k++) tp[k] = seq0.tprev[k];
+            }
+            else
+            {
+#pragma unroll
+                for(int k = 0; k < 9; k++) Rp[k] = seqs[seq].Rprev[k];
+#pragma unroll
+                for(int k = 0; k < 3; k++) tp[k] = seqs[seq].tprev[k];
+            }
+            seq_begin_pose(sh, Rp, tp);
+        }
         __syncthreads();
 
         // ------------------------------------------------ SO3 pre-alignment, level 2
@@ -225,14 +391,15 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         {
             const LevelGeom g = L.geom[2];
             const int N = g.rows * g.cols;
+            const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
             if(threadIdx.x == 0) level_begin(sh, g);
             for(int it = 0; it < 10; it++)
             {
                 if(threadIdx.x == 0) so3_prepare(sh);
                 __syncthreads();
                 So3Args a;
-                a.lastImage = in.lastNextImage[2];
-                a.nextImage = in.nextImage[2];
+                a.lastImage = P2.lastNextImage;
+                a.nextImage = P2.nextImage;
                 a.imageBasis = mat3_from(sh.so3H);
                 a.kinv = mat3_from(sh.so3Kinv);
                 a.krlr = mat3_from(sh.so3KR);
@@ -290,6 +457,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const int nslots = (plane + gthreads - 1) / gthreads;
             // all of this thread's pixels fit one register-resident chunk (always true for one 640x480 sequence on a full GPU)
             const bool single = nslots <= kSlotChunk;
+            const LevelPtrs P = level_ptrs(L.batch == 1, seq0, seqs, seq, lvl);
             if(warp0)
             {
                 if(threadIdx.x == 0)
@@ -315,38 +483,12 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             {
                 ResidualArgs a;
                 a.minScale = L.min_scale[lvl];
-                a.dIdx = in.dIdx[lvl]; a.dIdy = in.dIdy[lvl];
-                a.nextDepth = in.nextDepth[lvl];
-                a.nextImage = in.nextImage[lvl];
+                a.dIdx = P.dIdx; a.dIdy = P.dIdy;
+                a.nextDepth = P.nextDepth;
+                a.nextImage = P.nextImage;
                 a.cols = g.cols; a.rows = g.rows;
-#pragma unroll
-                for(int c = 0; c < kSlotChunk; c++)
-                {
-                    const int k = gtid + c * gthreads;
-                    if(c < nslots && k < plane)
-                    {
-                        const int i = k / g.cols;
-                        const int j0 = k - i * g.cols;
-                        short gx, gy;
-                        bool is_cand;
-                        if(L.derive_gradients)
-                            is_cand = rgb_candidate_derive(a, j0, i, gx, gy);
-                        else
-                        {
-                            is_cand = rgb_candidate(a, j0, i);
-                            gx = is_cand ? a.dIdx[k] : (short)0;
-                            gy = is_cand ? a.dIdy[k] : (short)0;
-                        }
-                        if(is_cand)
-                        {
-                            cand |= 1u << c;
-                            c_d1[c] = a.nextDepth[k];
-                            c_img[c] = static_cast<float>(a.nextImage[k]);
-                            c_gx[c] = gx;
-                            c_gy[c] = gy;
-                        }
-                    }
-                }
+                candidate_batch<0, 3>(a, L.derive_gradients, gtid, gthreads, nslots, plane, cand, c_d1, c_img, c_gx, c_gy);
+                if(nslots > 3) candidate_batch<3, kSlotChunk - 3>(a, L.derive_gradients, gtid, gthreads, nslots, plane, cand, c_d1, c_img, c_gx, c_gy);
             }
             __syncthreads();
 
@@ -389,6 +531,8 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     r_zxy[c] = 0; r_diff[c] = 0.f; r_d0[c] = 0.f;
                 }
 
+                unsigned mid_word = 0;
+                float sigma_now = 0.f;
                 // ---------------- phase A: ICP products + RGB association
                 {
                     float acc[32];
@@ -406,7 +550,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         a.angleThres = L.angle_thresh;
                         a.cols = g.cols;
                         a.rows = g.rows;
-                        a.vcurr = in.vcurr[lvl]; a.ncurr = in.ncurr[lvl]; a.vprev = in.vprev[lvl]; a.nprev = in.nprev[lvl];
+                        a.vcurr = P.vcurr; a.ncurr = P.ncurr; a.vprev = P.vprev; a.nprev = P.nprev;
                         for(int m0 = 0; m0 < nslots; m0 += kIcpChunk)
                         {
                             float3 vg[kIcpChunk], nc[kIcpChunk], vp[kIcpChunk], np[kIcpChunk];
@@ -461,14 +605,14 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     {
                         ResidualArgs a;
                         a.minScale = L.min_scale[lvl];
-                        a.dIdx = in.dIdx[lvl]; a.dIdy = in.dIdy[lvl];
-                        a.lastDepth = in.lastDepth[lvl]; a.nextDepth = in.nextDepth[lvl];
-                        a.lastImage = in.lastImage[lvl]; a.nextImage = in.nextImage[lvl];
+                        a.dIdx = P.dIdx; a.dIdy = P.dIdy;
+                        a.lastDepth = P.lastDepth; a.nextDepth = P.nextDepth;
+                        a.lastImage = P.lastImage; a.nextImage = P.nextImage;
                         a.maxDepthDelta = L.max_depth_delta;
                         a.kt = make_float3(sh.kt[0], sh.kt[1], sh.kt[2]);
                         a.krkinv = mat3_from(sh.krk);
                         a.cols = g.cols; a.rows = g.rows;
-                        Corres * cimg = in.corres[lvl];
+                        Corres * cimg = P.corres;
                         if(single)
                         {
                             int o0[kSlotChunk];
@@ -560,22 +704,37 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     acc[29] = (float)cnt0;
                     acc[30] = (float)(cnt1 & 0xfff);
                     acc[31] = (float)(cnt1 >> 12);
-                    cta_publish32(acc, sh, myrow, L.rgb);
+                    mid_word = cta_publish32(acc, sh, myrow, L.rgb);
                 }
 
                 if(L.rgb)
                 {
-                    group_barrier(bar, target, G);
-                    GN_STAMP(rec, 3);
-                    // count / sigma of the whole image -> sigmaVal (every CTA, identically)
-                    if(warp0)
+                    if(L.rgb_only)
                     {
-                        fold_count_sigma(sh, rowsA, G);
-                        if(threadIdx.x == 0) gn_sigma(sh, L.rgb_only, rec);
+                        group_barrier(bar, target, G);
+                        GN_STAMP(rec, 3);
+                        // count / sigma of the whole image -> rgbError decides the early exit (every CTA, identically)
+                        if(warp0)
+                        {
+                            fold_count_sigma(sh, rowsA, G);
+                            if(threadIdx.x == 0) gn_sigma(sh, true, rec);
+                        }
+                        __syncthreads();
                     }
-                    __syncthreads();
+                    else
+                    {
+                        // the barrier itself sums the correspondence counts: sigmaVal = sqrt(count) needs nothing else
+                        // (RGBDOdometryef.cpp:457-471; the squared-residual sum is a statistic, folded after phase B)
+                        group_barrier_sum(bar, target, G, mid_word, sum_running, &sh.mid_sum);
+                        GN_STAMP(rec, 3);
+                        const int word = sh.mid_sum;
+                        const int rgbSize = word & 0xffffff;
+                        const int sel = (rgbSize != 0 && (word >> 24) == 0) ? 1 : rgbSize;
+                        sigma_now = __fsqrt_rn((float)sel);
+                        if(rec) rec->sigma_in = sigma_now;
+                    }
                     GN_STAMP(rec, 4);
-                    if(sh.stop)
+                    if(L.rgb_only && sh.stop)
                     {
                         step++;
                         break;   // rgbOnly && rgbError > lastRGBError, RGBDOdometryef.cpp:460-463
@@ -586,12 +745,12 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 #pragma unroll
                     for(int k = 0; k < 32; k++) acc[k] = 0.f;
                     RgbStepArgs a;
-                    a.sigma = sh.sigmaVal;
+                    a.sigma = L.rgb_only ? sh.sigmaVal : sigma_now;
                     a.fx = g.fx; a.fy = g.fy;
                     a.sobelScale = L.sobel_scale;
                     a.cols = g.cols; a.rows = g.rows;
-                    a.dIdx = in.dIdx[lvl]; a.dIdy = in.dIdy[lvl];
-                    a.lastDepth = in.lastDepth[lvl];
+                    a.dIdx = P.dIdx; a.dIdy = P.dIdy;
+                    a.lastDepth = P.lastDepth;
                     a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
                     a.cloud = nullptr;
                     if(single)
@@ -612,7 +771,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     }
                     else
                     {
-                        const Corres * cimg = in.corres[lvl];
+                        const Corres * cimg = P.corres;
                         for(int m = 0; m < nslots; m++)
                         {
                             const int k = gtid + m * gthreads;
@@ -639,6 +798,19 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 fold_partials(sh, rowsA, G);
                 step++;
                 GN_STAMP(rec, 6);
+                if(L.rgb && !L.rgb_only && threadIdx.x == 32)
+                {
+                    // what gn_sigma records at the mid-iteration point, from the folded integer columns
+                    const int rgbSize = __float_as_int(sh.total[29]), sigma = __float_as_int(sh.total[30]);
+                    sh.rgb_sigma_last = sigma;
+                    sh.rgb_count_last = rgbSize;
+                    sh.res.lastRGBCount = (float)rgbSize;
+                }
+                if(rec && L.rgb && !L.rgb_only)
+                {
+                    rec->rgb_count = __float_as_int(sh.total[29]);
+                    rec->rgb_sigma = __float_as_int(sh.total[30]);
+                }
 
                 if(warp0) warp_update(sh, L.icp, L.rgb, L.icp_weight, rec, t_start);
                 GN_STAMP(rec, 7);
@@ -651,7 +823,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         if(leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();
     }
-    if(leader) ctl->base[group] = target;   // every CTA of the group ends with the same target
+    if(leader)
+    {
+        ctl->base[group] = target;   // every CTA of the group ends with the same target
+        ctl->sum_base[group] = sum_running;
+    }
 }
 
 // ------------------------------------------------------------------ host side

@@ -37,8 +37,11 @@ struct GnSeqIn
 
 struct GnCtl
 {
-    unsigned barrier[kGnMaxCtas];   // one arrival counter per CTA group, monotonically increasing across launches
-    unsigned base[kGnMaxCtas];      // counter value at the end of the previous launch (written by the group leader)
+    // one 64-bit word per CTA group, never reset: high half = arrival counter, low half = running sum of what the
+    // arriving CTAs contribute at the mid-iteration barrier (RGB correspondence count, see group_barrier_sum)
+    unsigned long long barrier[kGnMaxCtas];
+    unsigned base[kGnMaxCtas];      // arrival counter at the end of the previous launch (written by the group leader)
+    unsigned sum_base[kGnMaxCtas];  // running sum at the end of the previous launch
 };
 
 struct GnLaunch

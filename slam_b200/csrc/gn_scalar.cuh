@@ -26,6 +26,7 @@ struct GnShared
     int stop_level, so3_done;   // batched streaming engine only: level whose iterations were cut short (rgbOnly), SO3 loop finished
     int rgb_sigma_last, rgb_count_last;   // operands of lastRGBError (computed once, at the end)
     int ntr;                              // batched streaming engine only: step records written so far
+    int mid_sum;                          // persistent kernel only: result of the mid-iteration barrier sum
     float tinvf[3];
     float R_lr[9];
     float lastError, lastCount;
@@ -416,10 +417,13 @@ __device__ __forceinline__ void gn_sigma(GnShared & sh, const bool rgb_only, sla
     }
 }
 
-static __device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)   // lane 0
+// lane 0.  The prior pose arrives by value (registers): the persistent kernel reads it from its parameter block.
+__device__ __forceinline__ void seq_begin_pose(GnShared & sh, const float (&Rp)[9], const float (&tp)[3])
 {
-    for(int k = 0; k < 9; k++) sh.Rprev[k] = sh.Rcurr[k] = in.Rprev[k];
-    for(int k = 0; k < 3; k++) sh.tprev[k] = sh.tcurr[k] = in.tprev[k];
+#pragma unroll
+    for(int k = 0; k < 9; k++) sh.Rprev[k] = sh.Rcurr[k] = Rp[k];
+#pragma unroll
+    for(int k = 0; k < 3; k++) sh.tprev[k] = sh.tcurr[k] = tp[k];
     smath::mat3_inverse(sh.Rprev, sh.Rprev_inv);
     for(int k = 0; k < 9; k++)
     {
@@ -432,6 +436,14 @@ static __device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)
     sh.stop = 0;
     sh.rgb_sigma_last = 0;
     sh.rgb_count_last = -1;
+}
+
+static __device__ __noinline__ void seq_begin(GnShared & sh, const GnSeqIn & in)   // lane 0
+{
+    float Rp[9], tp[3];
+    for(int k = 0; k < 9; k++) Rp[k] = in.Rprev[k];
+    for(int k = 0; k < 3; k++) tp[k] = in.tprev[k];
+    seq_begin_pose(sh, Rp, tp);
 }
 
 static __device__ __noinline__ void seq_end(GnShared & sh, const bool rgb, const bool rgb_only, GnResult * out)   // lane 0

@@ -95,9 +95,10 @@ struct IcpArgs
 // consuming any of them (memory-level parallelism): icp_project() needs only the current vertex,
 // icp_finish() the gathered model vertex / normal.
 //   icp_project: reduce.cu:285-299 -> global-frame vertex, linear index of the model pixel, in-bounds flag
+__device__ __forceinline__ float3 icp_to_global(const IcpArgs & a, const float3 vcurr) { return a.Rcurr * vcurr + a.tcurr; }
 __device__ __forceinline__ bool icp_project(const IcpArgs & a, const float3 vcurr, float3 & vcurr_g, int & o)
 {
-    vcurr_g = a.Rcurr * vcurr + a.tcurr;
+    vcurr_g = icp_to_global(a, vcurr);
     const float3 vcurr_cp = a.Rprev_inv * (vcurr_g - a.tprev);
 
     // vcurr_cp.x * fx / vcurr_cp.z + cx  (reduce.cu:295-296): one reciprocal shared by both components
