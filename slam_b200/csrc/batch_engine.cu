@@ -161,6 +161,7 @@ __device__ __forceinline__ void seq_update(GnShared & sh, const GnLaunch & L, ch
         if(threadIdx.x == 0) gn_sigma(sh, L.rgb_only, rec);   // never a stop here: phase B returned early in that case
         __syncwarp();
     }
+    warp_stats(sh, L.icp, L.rgb, L.icp_weight);
     warp_update(sh, L.icp, L.rgb, L.icp_weight, threadIdx.x == 0 ? rec : nullptr, clock64());
     if(rec && threadIdx.x == 0) sh.ntr++;
     __syncwarp();
@@ -259,16 +260,17 @@ __global__ void __launch_bounds__(kBThreads) kb_so3(const GnLaunch L, const GnSe
     if(threadIdx.x >= 32) return;
     char * state = states + (size_t)seq * stride;
     state_load(sh, state);
-    if(threadIdx.x == 0)
+    __syncwarp();
     {
-        slam_step_record * rec = (trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
+        slam_step_record * rec = (threadIdx.x == 0 && trace && sh.ntr < kGnMaxTrace) ? trace + (size_t)seq * kGnMaxTrace + sh.ntr : nullptr;
         if(rec) memset(rec, 0, sizeof(*rec));
-        so3_update(sh, it, rec);
-        if(rec) sh.ntr++;
-        if(sh.stop || it == 9)
-            sh.so3_done = 1;
-        else
-            so3_prepare(sh);
+        warp_so3_update(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R
+        if(threadIdx.x == 0)
+        {
+            if(rec) sh.ntr++;
+            if(sh.stop || it == 9) sh.so3_done = 1;
+        }
+        __syncwarp();
     }
     state_store(sh, state);
 }

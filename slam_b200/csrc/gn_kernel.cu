@@ -392,11 +392,14 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const LevelGeom g = L.geom[2];
             const int N = g.rows * g.cols;
             const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
-            if(threadIdx.x == 0) level_begin(sh, g);
+            if(threadIdx.x == 0)
+            {
+                level_begin(sh, g);
+                so3_prepare(sh);
+            }
+            __syncthreads();
             for(int it = 0; it < 10; it++)
             {
-                if(threadIdx.x == 0) so3_prepare(sh);
-                __syncthreads();
                 So3Args a;
                 a.lastImage = P2.lastNextImage;
                 a.nextImage = P2.nextImage;
@@ -428,11 +431,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 fold_partials(sh, gpart + (step & 1) * G * kGnPartialStride, G);
                 step++;
 
-                if(threadIdx.x == 0)
+                if(warp0)
                 {
-                    slam_step_record * rec = (tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
+                    slam_step_record * rec = (threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
                     if(rec) memset(rec, 0, sizeof(*rec));
-                    so3_update(sh, it, rec);
+                    warp_so3_update(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R in shared memory
                     if(rec) ntr++;
                 }
                 __syncthreads();
@@ -812,7 +815,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     rec->rgb_sigma = __float_as_int(sh.total[30]);
                 }
 
-                if(warp0) warp_update(sh, L.icp, L.rgb, L.icp_weight, rec, t_start);
+                if(warp0)
+                    warp_update(sh, L.icp, L.rgb, L.icp_weight, rec, t_start);
+                else if(threadIdx.x < 64)
+                    warp_stats(sh, L.icp, L.rgb, L.icp_weight);   // lastA / lastb / ICP error: off the solving warp
                 GN_STAMP(rec, 7);
                 if(rec) ntr++;
                 __syncthreads();

@@ -141,17 +141,76 @@ __device__ __forceinline__ void warp_prepare(GnShared & sh, const bool with_pose
 }
 
 // Degenerate system (a pivot not safely positive): the pivoted / pseudo-inverse LDL^T of small_math.hpp.  Lane 0.
-static __device__ __noinline__ void solve_fallback(GnShared & sh)
+static __device__ __noinline__ void solve_fallback(GnShared & sh, const bool icp, const bool rgb, const float icpWeight)
 {
     double A[36], b[6], x[6];
-    for(int k = 0; k < 36; k++) A[k] = sh.res.lastA[k];
-    for(int k = 0; k < 6; k++) b[k] = sh.res.lastb[k];
+    int shift = 0;
+    for(int i = 0; i < 6; i++)
+        for(int j = i; j < 7; j++)
+        {
+            const float vi = sh.total[shift], vr = sh.total[32 + shift];
+            shift++;
+            double v;
+            if(icp && rgb)
+            {
+                const double w = icpWeight;
+                v = (j == 6) ? smath::add((double)vr, smath::mul(w, (double)vi)) : smath::add((double)vr, smath::mul(smath::mul(w, w), (double)vi));
+            }
+            else
+                v = icp ? (double)vi : (double)vr;
+            if(j == 6)
+                b[i] = v;
+            else
+                A[i * 6 + j] = A[j * 6 + i] = v;
+        }
     smath::ldlt_solve_pivoted<double, 6>(A, b, x, DBL_EPSILON);
     for(int k = 0; k < 6; k++) sh.x[k] = x[k];
 }
 
+// lastA / lastb / lastICPError / lastICPCount of the step (RGBDOdometryef.cpp:509-556) from the folded sums: same
+// expressions as the solver's own combination below, evaluated by ANOTHER warp while warp 0 solves (nothing on the
+// dependent chain reads them; the degenerate-pivot fallback does, after a block barrier in its caller's order --
+// see solve_fallback_sync).  One full warp.
+__device__ __forceinline__ void warp_stats(GnShared & sh, const bool icp, const bool rgb, const float icpWeight)
+{
+    const int lane = threadIdx.x & 31;
+    if(lane < 27)
+    {
+        int i = 0, rem = lane;
+        while(rem >= 7 - i)
+        {
+            rem -= 7 - i;
+            i++;
+        }
+        const int j = i + rem;
+        const float vi = sh.total[lane];
+        const float vr = sh.total[32 + lane];
+        double v;
+        if(icp && rgb)
+        {
+            const double w = icpWeight;
+            v = (j == 6) ? smath::add((double)vr, smath::mul(w, (double)vi)) : smath::add((double)vr, smath::mul(smath::mul(w, w), (double)vi));
+        }
+        else
+            v = icp ? (double)vi : (double)vr;
+        if(j == 6)
+            sh.res.lastb[i] = v;
+        else
+        {
+            sh.res.lastA[i * 6 + j] = v;
+            sh.res.lastA[j * 6 + i] = v;
+        }
+    }
+    else if(lane == 27 && icp)
+    {
+        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
+        sh.res.lastICPCount = sh.total[28];
+    }
+}
+
 // RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems, solve, update resultRt, then the next
-// iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
+// iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].  The caller runs warp_stats() as well
+// (on another warp, or before this call).
 //
 // smath::gauss_jordan_solve<double, 6> with one COLUMN of [A | b] per lane (lane j < 7 holds column j, the other
 // lanes shadow column 6): step k broadcasts column k with shuffles, every lane forms 1 / pivot itself and updates
@@ -180,21 +239,6 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
             const float vr = sh.total[32 + idx];
             c[i] = (icp && rgb) ? smath::add((double)vr, smath::mul(ww, (double)vi)) : (icp ? (double)vi : (double)vr);
         }
-    }
-    if(lane < 6)
-    {
-#pragma unroll
-        for(int i = 0; i < 6; i++) sh.res.lastA[i * 6 + lane] = c[i];
-    }
-    else if(lane == 6)
-    {
-#pragma unroll
-        for(int i = 0; i < 6; i++) sh.res.lastb[i] = c[i];
-    }
-    else if(lane == 7 && icp)
-    {
-        sh.res.lastICPError = __fdiv_rn(__fsqrt_rn(sh.total[27]), sh.total[28]);
-        sh.res.lastICPCount = sh.total[28];
     }
     GN_SSTAMP(0);
     // ---- x = A^-1 b
@@ -232,7 +276,7 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
     if(!ok)   // uniform: every lane saw the same pivots
     {
         __syncwarp();
-        if(lane == 0) solve_fallback(sh);
+        if(lane == 0) solve_fallback(sh, icp, rgb, icpWeight);
         __syncwarp();
 #pragma unroll
         for(int i = 0; i < 6; i++) x[i] = sh.x[i];
@@ -290,44 +334,75 @@ __device__ __forceinline__ void warp_update(GnShared & sh, const bool icp, const
     }
 }
 
-static __device__ __noinline__ void so3_prepare(GnShared & sh)   // lane 0
+// H = K R K^-1, K^-1, K R of the next SO3 iteration (RGBDOdometryef.cpp:313-323) from resultR, all in registers.
+__device__ __forceinline__ void so3_params(GnShared & sh, const double (&R)[9], const bool store)
 {
-    double K[9], Kinv[9], R[9], KR[9], H[9];
+    double K[9], Kinv[9], KR[9], H[9];
+#pragma unroll
     for(int k = 0; k < 9; k++)
     {
         K[k] = sh.K[k];
         Kinv[k] = sh.Kinv[k];
-        R[k] = sh.resultR[k];
     }
     smath::mat3_mul(K, R, KR);
     smath::mat3_mul(KR, Kinv, H);
-    for(int k = 0; k < 9; k++)
+    if(store)
     {
-        sh.so3H[k] = (float)H[k];
-        sh.so3Kinv[k] = (float)Kinv[k];
-        sh.so3KR[k] = (float)KR[k];
+#pragma unroll
+        for(int k = 0; k < 9; k++)
+        {
+            sh.so3H[k] = (float)H[k];
+            sh.so3Kinv[k] = (float)Kinv[k];
+            sh.so3KR[k] = (float)KR[k];
+        }
     }
 }
 
-// RGBDOdometryef.cpp:346-378 (lane 0)
-static __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_record * rec)
+static __device__ __noinline__ void so3_prepare(GnShared & sh)   // lane 0
 {
-    const float * s = sh.total;
+    double R[9];
+    for(int k = 0; k < 9; k++) R[k] = sh.resultR[k];
+    so3_params(sh, R, true);
+}
+
+static __device__ __noinline__ void so3_solve_fallback(GnShared & sh, const float * jtj, const float * jtr)   // lane 0
+{
+    float A[9], b[3], x[3];
+    for(int k = 0; k < 9; k++) A[k] = jtj[k];
+    for(int k = 0; k < 3; k++) b[k] = jtr[k];
+    smath::ldlt_solve_pivoted<float, 3>(A, b, x, FLT_EPSILON);
+    for(int k = 0; k < 3; k++) sh.x[k] = x[k];
+}
+
+// RGBDOdometryef.cpp:346-378 followed by the parameters of the next SO3 iteration (:313-323).  One full warp: every
+// lane evaluates the same expressions in registers (no local arrays, no shared-memory stages), lane 0 stores.
+__device__ __forceinline__ void warp_so3_update(GnShared & sh, int it, slam_step_record * rec)
+{
+    const int lane = threadIdx.x & 31;
+    float s[11];
+#pragma unroll
+    for(int k = 0; k < 11; k++) s[k] = sh.total[k];
     float jtj[9], jtr[3];
-    int shift = 0;
-    for(int i = 0; i < 3; ++i)
-        for(int j = i; j < 4; ++j)
-        {
-            const float value = s[shift++];
-            if(j == 3)
-                jtr[i] = value;
-            else
-                jtj[j * 3 + i] = jtj[i * 3 + j] = value;
-        }
-    const float residual0 = s[9], residual1 = s[10];
-    sh.res.lastSO3Error = __fdiv_rn(__fsqrt_rn(residual0), residual1);
-    sh.res.lastSO3Count = residual1;
-    sh.res.so3_iterations++;
+    {
+        int shift = 0;
+#pragma unroll
+        for(int i = 0; i < 3; ++i)
+#pragma unroll
+            for(int j = i; j < 4; ++j)
+            {
+                const float value = s[shift++];
+                if(j == 3)
+                    jtr[i] = value;
+                else
+                    jtj[j * 3 + i] = jtj[i * 3 + j] = value;
+            }
+    }
+    float so3Error = __fdiv_rn(__fsqrt_rn(s[9]), s[10]);
+    float so3Count = s[10];
+    const float lastError = sh.lastError, lastCount = sh.lastCount;
+    double R[9];
+#pragma unroll
+    for(int k = 0; k < 9; k++) R[k] = sh.resultR[k];
 
     if(rec)
     {
@@ -343,44 +418,76 @@ static __device__ __noinline__ void so3_update(GnShared & sh, int it, slam_step_
         }
     }
 
-    bool stop = false;
-    if(sh.res.lastSO3Error < sh.lastError && sh.lastCount == sh.res.lastSO3Count)
+    bool stop = false, restore = false;
+    if(so3Error < lastError && lastCount == so3Count)
         stop = true;
-    else if((double)sh.res.lastSO3Error > (double)sh.lastError + 0.001)
+    else if((double)so3Error > (double)lastError + 0.001)
     {
-        sh.res.lastSO3Error = sh.lastError;
-        sh.res.lastSO3Count = sh.lastCount;
-        for(int k = 0; k < 9; k++) sh.resultR[k] = sh.lastResultR[k];
+        so3Error = lastError;
+        so3Count = lastCount;
+        restore = true;
         stop = true;
     }
-    if(!stop)
+    __syncwarp();
+    if(restore)
     {
-        sh.lastError = sh.res.lastSO3Error;
-        sh.lastCount = sh.res.lastSO3Count;
-        for(int k = 0; k < 9; k++) sh.lastResultR[k] = sh.resultR[k];
+        if(lane < 9) sh.resultR[lane] = sh.lastResultR[lane];
+    }
+    if(!stop)   // uniform
+    {
         float delta[3];
-        smath::ldlt_solve<float, 3>(jtj, jtr, delta, FLT_EPSILON);
+        const bool ok = smath::ldlt_solve_nopivot<float, 3>(jtj, jtr, delta);
+        if(!ok)
+        {
+            if(lane == 0) so3_solve_fallback(sh, jtj, jtr);
+            __syncwarp();
+#pragma unroll
+            for(int k = 0; k < 3; k++) delta[k] = (float)sh.x[k];
+            __syncwarp();
+        }
         const double dd[3] = {delta[0], delta[1], delta[2]};
         double rotUpdate[9];
         smath::rodrigues(dd, rotUpdate);
-        float ru[9], rl[9];
+        float ru[9], rl[9], rn[9];
+#pragma unroll
         for(int k = 0; k < 9; k++)
         {
             ru[k] = (float)rotUpdate[k];
             rl[k] = sh.R_lr[k];
         }
-        smath::mat3_mul(ru, rl, rl);
-        for(int k = 0; k < 9; k++)
+        smath::mat3_mul(ru, rl, rn);
+        double Rn[9];
+#pragma unroll
+        for(int k = 0; k < 9; k++) Rn[k] = rn[k];
+        __syncwarp();
+        if(lane == 0)
         {
-            sh.R_lr[k] = rl[k];
-            sh.resultR[k] = rl[k];
+            sh.lastError = so3Error;
+            sh.lastCount = so3Count;
+#pragma unroll
+            for(int k = 0; k < 9; k++)
+            {
+                sh.lastResultR[k] = R[k];
+                sh.R_lr[k] = rn[k];
+                sh.resultR[k] = Rn[k];
+            }
+            if(rec)
+                for(int k = 0; k < 3; k++) rec->x[k] = delta[k];
         }
-        if(rec)
-            for(int k = 0; k < 3; k++) rec->x[k] = delta[k];
+        so3_params(sh, Rn, lane == 0);   // the next iteration's H, K^-1, K R
+#pragma unroll
+        for(int k = 0; k < 9; k++) R[k] = Rn[k];
     }
+    if(lane == 0)
+    {
+        sh.res.lastSO3Error = so3Error;
+        sh.res.lastSO3Count = so3Count;
+        sh.res.so3_iterations++;
+        sh.stop = stop ? 1 : 0;
+    }
+    __syncwarp();
     if(rec)
         for(int k = 0; k < 9; k++) rec->Rcurr[k] = (float)sh.resultR[k];
-    sh.stop = stop ? 1 : 0;
 }
 
 // RGBDOdometryef.cpp:457-471; count/sigma are in sh.total[29], [30] (integer bit patterns).  Lane 0.
