@@ -579,6 +579,37 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
         except Exception:
             pass
         del raw, out_f
+    # ---- the fern relocaliser around the ICP path (key-frame database in HBM)
+    if world == 1:
+        try:
+            from slam_b200.ferns import Ferns
+            fe = Ferns(500, int(DEPTH_CUTOFF * 1000), 115.0, 319.5, 239.5, 481.20, -480.0, W, H, seed=0x51A7, capacity=1100, device=local_rank)
+            nkf = 1024
+            for k in range(nkf):
+                dk = dframes[k % len(dframes)]
+                fe.addFrame(dk["mrgba"], dk["mv"], dk["mn"], frames[k % len(dframes)]["model_pose"], k, -1.0)   # threshold -1: every frame is kept
+            dq = dframes[5]
+            reps = 50
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fe.encode(dq["mrgba"], dq["mv"], dq["mn"])
+            enc_us = (time.perf_counter() - t0) / reps * 1e6
+            ms_search = []
+            for _ in range(reps):
+                fe.search(100000, use_time=True)
+                ms_search.append(fe.lastSearchMs())
+            cons = []
+            t0 = time.perf_counter()
+            for _ in range(20):
+                fe.findFrame(cons, frames[5]["model_pose"], dq["mv"], dq["mn"], dq["mrgba"], 100000, True)
+            ff_ms = (time.perf_counter() - t0) / 20 * 1e3
+            us = float(np.median(ms_search)) * 1e3
+            out["fern relocaliser, 1024 key frames"] = {"encode_us_incl_readback": enc_us, "search_kernel_us": us, "search_GBps": nkf * 512 / (us * 1e-6) / 1e9,
+                                                         "find_frame_ms": ff_ms, "accepted": int(fe.lastClosest >= 0), "icp_count": float(fe.lastMatch.icp_count)}
+            fe.close()
+        except Exception as e:   # the extra must never take the headline down
+            out["fern relocaliser, 1024 key frames"] = {"error": str(e)[:200]}
     # ---- configs[2]
     if world == 1:
         from slam_b200.synth import Scene

@@ -48,7 +48,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build_product(force: bool = False) -> Path:
     out = ROOT / "slam_b200" / "libslam_odom.so"
-    cus = [CSRC / n for n in ("odom_api.cu", "gn_kernel.cu", "batch_engine.cu", "reduce_kernels.cu", "prep_kernels.cu")]
+    cus = [CSRC / n for n in ("odom_api.cu", "gn_kernel.cu", "batch_engine.cu", "reduce_kernels.cu", "prep_kernels.cu", "ferns.cu")]
     deps = cus + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + [ROOT / "include" / "slam_odom.h"]
     if not force and not _stale(out, deps):
         return out

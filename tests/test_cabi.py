@@ -10,9 +10,9 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "slam_odom.h").read_text()
+    text = (ROOT / "include" / "slam_odom.h").read_text() + (ROOT / "include" / "slam_ferns.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(slam_(?:odom|op)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(slam_(?:odom|op|ferns)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_the_reference_interface():
@@ -24,7 +24,10 @@ def test_header_declares_the_reference_interface():
                    "slam_op_copy_maps", "slam_op_resize_vmap", "slam_op_resize_nmap", "slam_op_image_bgr_to_intensity", "slam_op_vertices_to_depth",
                    "slam_op_project_to_point_cloud", "slam_op_pyr_down_gauss_f", "slam_op_pyr_down_uchar_gauss", "slam_op_compute_derivative_images"):
         assert needed in syms, needed
-    assert len(syms) >= 40
+    for needed in ("slam_ferns_create", "slam_ferns_destroy", "slam_ferns_add_frame", "slam_ferns_find_frame", "slam_ferns_encode", "slam_ferns_search",
+                   "slam_ferns_photometric_check"):
+        assert needed in syms, needed
+    assert len(syms) >= 50
 
 
 def test_library_loads_and_exports_every_declared_symbol(built):
