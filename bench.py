@@ -610,6 +610,34 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
             fe.close()
         except Exception as e:   # the extra must never take the headline down
             out["fern relocaliser, 1024 key frames"] = {"error": str(e)[:200]}
+    # ---- the model-prediction producer (surfel splat + fill-in) that makes the tracker's model maps
+    if world == 1:
+        try:
+            from slam_b200.predict import ModelPredictor
+            from slam_b200.synth import Scene, surfels_from_frame
+            scene = Scene(seed=0x51A7)
+            poses = scene.trajectory(1000, seed=0x51A7)
+            mp = ModelPredictor(W, H, 319.5, 239.5, 481.20, -480.0, device=local_rank)
+            for nview in (1, 4):
+                model = np.concatenate([surfels_from_frame(scene, poses[40 * k], seed=k) for k in range(nview)])
+                d_model = torch.from_numpy(model).to(dev)
+                dq = dframes[5]
+                ts = []
+                for it in range(25):
+                    mp.predict(poses[5 + it % 3], d_model, len(model), MODEL_CUTOFF, 10.0, 1, 200, dq["depth"], dq["rgba"])
+                    ts.append(mp.lastMs())
+                a = np.array(ts[5:]) * 1e3
+                frags = mp.lastFragments()
+                splat_us, resolve_us = float(a[:, 0].mean()), float(a[:, 1].mean())
+                # resolve launch, per pixel: z-buffer 8 r + 8 w, winners 8 w, view ray 16 r, winner's surfel 48 r, FillIn textures 36 w, raw rgba 4 r
+                out[f"model prediction, {len(model)} surfels"] = {
+                    "splat_us": splat_us, "resolve_fill_us": resolve_us, "frames_per_s": 1e6 / (splat_us + resolve_us), "fragments": frags,
+                    "fragments_per_s": frags / (splat_us * 1e-6), "surfel_stream_GBps": len(model) * 48 / (splat_us * 1e-6) / 1e9,
+                    "resolve_GBps": W * H * 128 / (resolve_us * 1e-6) / 1e9, "covered": float((mp.winners()[1] >= 0).mean())}
+                del d_model
+            mp.close()
+        except Exception as e:   # the extra must never take the headline down
+            out["model prediction"] = {"error": str(e)[:200]}
     # ---- configs[2]
     if world == 1:
         from slam_b200.synth import Scene

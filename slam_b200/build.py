@@ -25,6 +25,11 @@ REF = Path(os.environ.get("SLAM_REFERENCE_DIR", "/root/reference"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 REF_NUMERIC_FLAGS = ["--ftz=true", "--prec-div=false", "--prec-sqrt=false"]
 NVCC_COMMON = ARCH + ["-std=c++17", "-O3", "-lineinfo"] + REF_NUMERIC_FLAGS + ["-Xcompiler", "-fPIC"]
+# predict.cu restates GLSL shaders, not the reference's CUDA: IEEE division / square root, no FMA contraction, no flush to
+# zero, so that the CPU restatement (oracle/predict_oracle.c) reproduces it bit for bit
+IEEE_NUMERIC_FLAGS = ["--ftz=false", "--prec-div=true", "--prec-sqrt=true", "--fmad=false"]
+NVCC_IEEE = ARCH + ["-std=c++17", "-O3", "-lineinfo"] + IEEE_NUMERIC_FLAGS + ["-Xcompiler", "-fPIC"]
+PER_FILE_FLAGS = {"predict.cu": NVCC_IEEE}
 
 
 def _nvcc() -> str:
@@ -48,8 +53,8 @@ def _stale(target: Path, sources) -> bool:
 
 def build_product(force: bool = False) -> Path:
     out = ROOT / "slam_b200" / "libslam_odom.so"
-    cus = [CSRC / n for n in ("odom_api.cu", "gn_kernel.cu", "batch_engine.cu", "reduce_kernels.cu", "prep_kernels.cu", "ferns.cu")]
-    deps = cus + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + [ROOT / "include" / "slam_odom.h"]
+    cus = [CSRC / n for n in ("odom_api.cu", "gn_kernel.cu", "batch_engine.cu", "reduce_kernels.cu", "prep_kernels.cu", "ferns.cu", "predict.cu")]
+    deps = cus + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp")) + [ROOT / "include" / n for n in ("slam_odom.h", "slam_ferns.h", "slam_predict.h")]
     if not force and not _stale(out, deps):
         return out
     objdir = ROOT / "build" / "product"
@@ -59,7 +64,7 @@ def build_product(force: bool = False) -> Path:
     for cu in cus:
         obj = objdir / (cu.stem + ".o")
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_COMMON + ["-I", ROOT / "include", "-c", cu, "-o", obj]
+        cmd = [_nvcc()] + PER_FILE_FLAGS.get(cu.name, NVCC_COMMON) + ["-I", ROOT / "include", "-c", cu, "-o", obj]
         print("+", " ".join(str(c) for c in cmd), flush=True)
         procs.append(subprocess.Popen([str(c) for c in cmd]))
     for p in procs:
@@ -87,7 +92,7 @@ def build_hostmath(force: bool = False) -> Path:
 
 def build_oracle(force: bool = False) -> Path:
     out = ROOT / "oracle" / "liboracle.so"
-    srcs = [ROOT / "oracle" / "odom_oracle.c", ROOT / "oracle" / "depth_filter_oracle.c"]
+    srcs = [ROOT / "oracle" / "odom_oracle.c", ROOT / "oracle" / "depth_filter_oracle.c", ROOT / "oracle" / "predict_oracle.c"]
     if force or _stale(out, srcs):
         _run(["gcc", "-O3", "-march=x86-64-v2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-o", out] + srcs + ["-lm"])
     return out

@@ -85,6 +85,33 @@ class Scene:
         return v, n, rgba
 
 
+def surfels_from_frame(scene: "Scene", pose, time=1, stride=1, conf=None, seed=0) -> np.ndarray:
+    """A surfel model (count x 12 float32: position+confidence, colour+times, normal+radius -- the reference's vertex buffer layout,
+    src/gl/Vertex.cpp) made from one rendered view, with the formulas the reference initialises surfels with
+    (src/model/shaders/data.vert:79-107: encodeColor, confidence; surfels.glsl:19-46: getRadius).  Test / bench data only."""
+    v, n, rgba = scene.render_model(pose)
+    ys, xs = np.mgrid[0:scene.height:stride, 0:scene.width:stride]
+    v, n, rgba = v[ys, xs].reshape(-1, 4), n[ys, xs].reshape(-1, 4), rgba[ys, xs].reshape(-1, 4)
+    ok = (v[:, 2] > 0) & (np.abs(n[:, 2]) > 1e-3)
+    v, n, rgba, xs, ys = v[ok], n[ok], rgba[ok], xs.reshape(-1)[ok], ys.reshape(-1)[ok]
+    pose = np.asarray(pose, dtype=np.float32)
+    R, t = pose[:3, :3], pose[:3, 3]
+    s = np.zeros((len(v), 12), np.float32)
+    s[:, 0:3] = v[:, :3] @ R.T + t
+    rad = np.hypot(xs - scene.cx, ys - scene.cy) / 400.0
+    s[:, 3] = np.exp(-(rad * rad) / 0.72) * 25.0 if conf is None else conf          # confidence(x, y, weighting)
+    rgb = rgba[:, :3].astype(np.int64)
+    s[:, 4] = ((rgb[:, 0] << 16) + (rgb[:, 1] << 8) + rgb[:, 2]).astype(np.float32)  # encodeColor
+    s[:, 6] = time                                                                  # initialisation time
+    s[:, 7] = time                                                                  # last update
+    s[:, 8:11] = n[:, :3] @ R.T
+    mean_focal = (abs(scene.fx) + abs(scene.fy)) / 2.0
+    radius = v[:, 2] / mean_focal * 1.41421356237 * stride
+    s[:, 11] = np.minimum(2.0 * radius, radius / np.abs(n[:, 2]))                   # getRadius
+    rng = np.random.default_rng(seed)
+    return s[rng.permutation(len(s))]          # draw order must not matter for anything but exact depth ties
+
+
 # ---- trajectory error metrics (definitions of the reference's benchmark scripts) --------------
 def ate_rmse(gt_xyz: np.ndarray, est_xyz: np.ndarray) -> float:
     """Absolute trajectory error: RMSE of translations after Horn alignment (benchmark/evaluate_ate.py:47-79,162)."""

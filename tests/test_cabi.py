@@ -10,9 +10,9 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "slam_odom.h").read_text() + (ROOT / "include" / "slam_ferns.h").read_text()
+    text = (ROOT / "include" / "slam_odom.h").read_text() + (ROOT / "include" / "slam_ferns.h").read_text() + (ROOT / "include" / "slam_predict.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(slam_(?:odom|op|ferns)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(slam_(?:odom|op|ferns|predict)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_the_reference_interface():
@@ -27,7 +27,10 @@ def test_header_declares_the_reference_interface():
     for needed in ("slam_ferns_create", "slam_ferns_destroy", "slam_ferns_add_frame", "slam_ferns_find_frame", "slam_ferns_encode", "slam_ferns_search",
                    "slam_ferns_photometric_check"):
         assert needed in syms, needed
-    assert len(syms) >= 50
+    for needed in ("slam_predict_create", "slam_predict_combined", "slam_predict_fill_vertex", "slam_predict_fill_normal", "slam_predict_fill_image",
+                   "slam_predict_frame"):
+        assert needed in syms, needed
+    assert len(syms) >= 60
 
 
 def test_library_loads_and_exports_every_declared_symbol(built):

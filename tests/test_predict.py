@@ -1,0 +1,339 @@
+"""Model-prediction producer: IndexMap::combinedPredict + the FillIn passes, the step that produces the
+tracker's model maps (src/model/IndexMap.cpp:243-341, splat.vert, combo_splat.frag; src/gl/FillIn.cpp:68-198, fill_*.frag).
+
+PARITY UNPINNED against the reference itself: there the path is GLSL on an OpenGL context (none here) and the reference
+holds no golden image of it.  What is pinned:
+  * the C restatement (oracle/predict_oracle.c, fp32, statement by statement, drawn in GL's order with a GL_LESS 24-bit
+    depth buffer) against an independent float64 evaluation of the shaders' formulas with an order-free arg-min: same
+    covered pixels (> 99.5 %), same depth to 1e-4 everywhere and to 1e-5 where the same surfel wins (> 90 %; overlapping surfels
+    of one surface lie a few 24-bit depth steps apart, which fp32 rounding reorders)                                  (CPU)
+  * the CUDA path through the C ABI against the C restatement: bit-exact on every output texture (the translation unit is
+    built with IEEE division / sqrt and without FMA contraction) -- full-size frames, culls by depth / confidence / time,
+    sprites larger than the viewport, surfels behind the camera, ragged sizes, empty model; fused call == separate calls;
+    repeated calls identical (the z-buffer re-arms itself)                                                           (GPU)
+  * the producer feeding the tracker: a surfel model built from one frame, predicted at the next pose, tracks the next
+    frame as well as the analytic model maps do                                                                      (GPU)
+"""
+import numpy as np
+import pytest
+
+from tests.support import DEPTH_CUTOFF, MODEL_CUTOFF, make_scene, scaled_intrinsics
+
+
+def surfels_from_frame(scene, intr, pose, **kw):
+    """Test data: a surfel model from one rendered frame (slam_b200.synth.surfels_from_frame; `intr` kept for the call sites)."""
+    from slam_b200.synth import surfels_from_frame as make
+    return make(scene, pose, **kw)
+
+
+def awkward_surfels(pose, rng):
+    """Surfels that exercise the culls and the rasterisation edge rules (positions given in the camera frame of `pose`)."""
+    rows = []
+
+    def add(p_cam, n_cam, rad, conf=20.0, colour=0x406080, t_init=3.0, t_last=5.0):
+        p = pose[:3, :3] @ np.asarray(p_cam, np.float64) + pose[:3, 3]
+        n = pose[:3, :3] @ (np.asarray(n_cam, np.float64) / np.linalg.norm(n_cam))
+        rows.append([*p, conf, colour, 0.0, t_init, t_last, *n, rad])
+
+    add([0.01, 0.005, 0.05], [0, 0, -1], 0.02)              # right in front of the lens: sprite taller than the viewport
+    add([0.1, 0.05, 0.6], [0.2, 0.1, -1], 0.3, colour=0xFFFFFF)   # big disc, partly hidden behind the first
+    add([0.0, 0.0, -1.0], [0, 0, -1], 0.1)                  # behind the camera                    (z < 0)
+    add([0.0, 0.0, 25.0], [0, 0, -1], 0.1)                  # beyond depthCutoff                   (z > maxDepth)
+    add([0.3, 0.2, 1.5], [0, 0, -1], 0.05, conf=2.0)        # unstable                             (conf < confThreshold)
+    add([0.3, -0.2, 1.5], [0, 0, -1], 0.05, t_last=1000.0)  # from the future                      (vColor.w > maxTime)
+    add([-0.3, 0.2, 1.5], [0, 0, -1], 0.05, t_last=-500.0)  # too old                              (time - vColor.w > timeDelta)
+    add([50.0, 0.0, 1.0], [0, 0, -1], 0.05)                 # centre outside the clip volume, sprite would reach in
+    add([0.2, 0.2, 1.0], [1, 0, 0], 0.05)                   # edge on: ray parallel to the disc for one pixel column at most
+    add([0.0, 0.3, 2.0], [0, 0, -1], 0.0)                   # zero radius (point size clamps to 1)
+    add([0.0, 0.3, 2.0], [0, 0, -1], 1e-3, colour=0)        # black surfel (fill_rgb replaces it)
+    for _ in range(40):                                     # exact depth ties: pairs of identical surfels, different colours
+        p = [rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4), rng.uniform(0.8, 2.5)]
+        add(p, [0, 0, -1], 0.02, colour=0x112233)
+        add(p, [0, 0, -1], 0.02, colour=0x332211)
+    return np.array(rows, np.float32)
+
+
+def predict_fp64(surfels, tinv, intr, max_depth, conf_thr, time, max_time, time_delta, max_point=2047.0):
+    """The shaders' formulas in float64, arg-min over (depth24, index) per pixel -- no draw order, no float32."""
+    W, H = intr["width"], intr["height"]
+    cx, cy, fx, fy = (float(np.float32(intr[k])) for k in ("cx", "cy", "fx", "fy"))
+    best = np.full((H, W), (0xFFFFFF << 32) | 0xFFFFFFFF, np.uint64)
+    zmap = np.zeros((H, W))
+    T = tinv.astype(np.float64)
+    for i, s in enumerate(surfels.astype(np.float64)):
+        home = T[:3, :3] @ s[0:3] + T[:3, 3]
+        if home[2] > max_depth or home[2] < 0 or s[3] < conf_thr or time - s[7] > time_delta or s[7] > max_time:
+            continue
+        n = T[:3, :3] @ s[8:11]
+        n = n / np.linalg.norm(n)
+        rad = s[11]
+        proj = lambda p: np.array([fx * p[0] / p[2] + cx, fy * p[1] / p[2] + cy])
+        with np.errstate(all="ignore"):
+            c = proj(home)
+            if not (abs((c[0] - W / 2) / (W / 2)) <= 1 and abs((c[1] - H / 2) / (H / 2)) <= 1):
+                continue
+            x1 = np.array([n[1] - n[2], -n[0], n[0]])
+            x1 = x1 / np.linalg.norm(x1) * rad * 1.41421356
+            y1 = np.cross(n, x1)
+            pts = np.array([proj(home + x1), proj(home + y1), proj(home - y1), proj(home - x1)])
+        size = np.nanmax([0.0, np.ptp(pts[:, 0]), np.ptp(pts[:, 1])])
+        size = min(max(size, 1.0), max_point)
+        x0, x1i = int(np.ceil(c[0] - size / 2 - 0.5)), int(np.ceil(c[0] + size / 2 - 0.5)) - 1
+        y0, y1i = int(np.ceil(c[1] - size / 2 - 0.5)), int(np.ceil(c[1] + size / 2 - 0.5)) - 1
+        x0, y0, x1i, y1i = max(x0, 0), max(y0, 0), min(x1i, W - 1), min(y1i, H - 1)
+        if x1i < x0 or y1i < y0:
+            continue
+        py, px = np.mgrid[y0:y1i + 1, x0:x1i + 1]
+        l = np.stack([(px + 0.5 - cx) / fx, (py + 0.5 - cy) / fy, np.ones_like(px, np.float64)], -1)
+        l /= np.linalg.norm(l, axis=-1, keepdims=True)
+        with np.errstate(all="ignore"):
+            cp = (home @ n / (l @ n))[..., None] * l
+            d = cp[..., 2] / (2 * max_depth) + 0.5
+        hit = (((cp - home) ** 2).sum(-1) <= rad * rad) & ~np.isnan(d)
+        d24 = np.rint(np.clip(np.where(hit, d, 1.0), 0, 1) * 16777215.0).astype(np.uint64)
+        key = (d24 << np.uint64(32)) | np.uint64(i)
+        sub = best[y0:y1i + 1, x0:x1i + 1]
+        take = hit & (d24 < 0xFFFFFF) & (key < sub)
+        sub[take] = key[take]
+        zmap[y0:y1i + 1, x0:x1i + 1][take] = cp[..., 2][take]
+    winner = np.where((best >> np.uint64(32)) < 0xFFFFFF, (best & np.uint64(0xFFFFFFFF)).astype(np.int64), -1)
+    return winner, zmap
+
+
+CALL = dict(depth_cutoff=MODEL_CUTOFF, conf_threshold=10.0, time=10, max_time=10, time_delta=200)
+
+
+def test_oracle_matches_fp64_formulas(built):
+    from oracle import predict_oracle as po
+    scene, intr = make_scene(64, 48)
+    poses = scene.trajectory(40)
+    surf = np.concatenate([surfels_from_frame(scene, intr, poses[0]), awkward_surfels(poses[3], np.random.default_rng(5))])
+    tinv = po.inverse4(poses[3])
+    assert np.allclose(tinv.astype(np.float64), np.linalg.inv(poses[3].astype(np.float64)), atol=2e-6)
+    got = po.combined_predict(surf, poses[3], intr, **CALL)
+    win, zmap = predict_fp64(surf, tinv, intr, MODEL_CUTOFF, 10.0, 10, 10, 200)
+    # neighbouring surfels of one surface overlap at depths a few 24-bit steps apart (one step = one fp32 ulp of gl_FragDepth), so
+    # fp32 rounding legitimately swaps some winners; the covered set and the depth they produce must agree
+    same = got["winner"] == win
+    assert same.mean() > 0.9, f"winner agreement {same.mean():.4f}"
+    both = (got["winner"] >= 0) & (win >= 0)
+    assert ((got["winner"] >= 0) == (win >= 0)).mean() > 0.995 and both.mean() > 0.9
+    assert np.abs(got["vertex"][..., 2][same & both] - zmap[same & both]).max() < 1e-5
+    assert np.abs(got["vertex"][..., 2][both] - zmap[both]).max() < 1e-4
+    # outputs are consistent with the winners: colour bytes, confidence, radius, time
+    hit = got["winner"] >= 0
+    w = got["winner"][hit]
+    rgb = surf[w, 4].astype(np.int64)
+    assert np.array_equal(got["image"][hit][:, 0], (rgb >> 16) & 0xFF) and np.array_equal(got["image"][hit][:, 2], rgb & 0xFF)
+    assert np.all(got["image"][hit][:, 3] == 255) and np.all(got["image"][~hit] == 0)
+    assert np.array_equal(got["vertex"][hit][:, 3], surf[w, 3]) and np.array_equal(got["normal"][hit][:, 3], surf[w, 11])
+    assert np.array_equal(got["time"][hit], surf[w, 6].astype(np.uint16))
+    # the culled surfels never win; of two identical surfels the one drawn first does
+    n0 = len(surf) - len(awkward_surfels(poses[3], np.random.default_rng(5)))
+    culled = n0 + np.array([2, 3, 4, 5, 6, 7])
+    assert not np.isin(got["winner"], culled).any()
+    ties_second = n0 + 11 + 2 * np.arange(40) + 1
+    assert not np.isin(got["winner"], ties_second).any()
+    assert np.isin(got["winner"], ties_second - 1).any()
+
+
+def test_oracle_fill_in_rules(built):
+    from oracle import predict_oracle as po
+    intr = scaled_intrinsics(32, 24)
+    rng = np.random.default_rng(3)
+    depth = rng.integers(500, 3000, (24, 32)).astype(np.uint16)
+    depth[5:8, 5:9] = 0
+    rgba = rng.integers(1, 255, (24, 32, 4)).astype(np.uint8)
+    v = np.zeros((24, 32, 4), np.float32)
+    v[::2, :, :] = [0.1, 0.2, 1.5, 30.0]
+    n = np.zeros((24, 32, 4), np.float32)
+    n[:, ::2, :] = [0.0, 0.6, -0.8, 0.01]
+    im = np.zeros((24, 32, 4), np.uint8)
+    im[:, 16:] = [9, 0, 0, 255]
+    out = po.fill_in(intr, depth, rgba, vertex=v, normal=n, image=im)
+    assert np.array_equal(out["vertex"][::2], v[::2]) and np.array_equal(out["normal"][:, ::2], n[:, ::2])
+    assert np.array_equal(out["image"][:, 16:], im[:, 16:]) and np.array_equal(out["image"][:, :16], rgba[:, :16])
+    y, x = 3, 7
+    z = np.float32(depth[y, x]) / np.float32(1000.0)
+    want = np.array([(x - intr["cx"]) * z / intr["fx"], (y - intr["cy"]) * z / intr["fy"], z, 1.0])
+    assert np.allclose(out["vertex"][y, x], want, rtol=1e-6)
+    # forward-difference normal of the raw depth, unit length, w = 1; a hole (all three depths 0) gives NaN like normalize(0) does
+    nn = out["normal"][3, 7]
+    assert abs(np.linalg.norm(nn[:3]) - 1) < 1e-6 and nn[3] == 1.0
+    assert np.isnan(out["normal"][6, 7, :3]).all()
+    # CLAMP_TO_EDGE at the last column / row: the x + 1 texel is the pixel itself, only the pixel coordinate moves
+    last = out["normal"][3, 31]
+    assert np.isfinite(last).all() or np.isnan(last[:3]).all()
+    # passthrough replaces everything
+    out2 = po.fill_in(intr, depth, rgba, vertex=v, image=im, passthrough=True)
+    assert np.array_equal(out2["image"], rgba) and np.all(out2["vertex"][..., 3] == 1.0)
+
+
+def test_header_and_library_export_the_interface(built):
+    import ctypes as C
+    import re
+    from slam_b200.odometry import library_path
+    from tests.support import ROOT
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "slam_predict.h").read_text(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(slam_predict_[a-z0-9_]+)\s*\(", text)))
+    for needed in ("slam_predict_create", "slam_predict_destroy", "slam_predict_combined", "slam_predict_fill_vertex", "slam_predict_fill_normal",
+                   "slam_predict_fill_image", "slam_predict_frame", "slam_predict_get_textures", "slam_predict_download"):
+        assert needed in syms
+    lib = C.CDLL(str(library_path()))
+    assert not [s for s in syms if not hasattr(lib, s)]
+    from slam_b200.predict import FillIn, IndexMap, ModelPredictor
+    for cls, names in ((IndexMap, ("combinedPredict", "imageTex", "vertexTex", "normalTex", "timeTex")),
+                       (FillIn, ("vertex", "normal", "image", "imageTexture", "vertexTexture", "normalTexture")), (ModelPredictor, ("predict",))):
+        for name in names:
+            assert hasattr(cls, name), name
+
+
+def test_no_gpu_means_loud_failure(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from slam_b200.predict import ModelPredictor, OdometryError
+    with pytest.raises(OdometryError):
+        ModelPredictor(640, 480, 319.5, 239.5, 481.2, -480.0)
+
+
+# ---- GPU parity ----------------------------------------------------------------------------------------------------------------
+def _bits(a):
+    """Bit pattern of a float32 array with every NaN mapped to one value (x86 and the GPU produce different default NaNs for 0 / 0)."""
+    if a.dtype != np.float32:
+        return a
+    b = np.ascontiguousarray(a).view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def _assert_textures_equal(mp, ref, names=("image", "vertex", "normal", "time"), prefix=""):
+    for name in names:
+        got = mp.download(prefix + name)
+        assert np.array_equal(_bits(got), _bits(ref[name])), f"{prefix}{name}: {(_bits(got) != _bits(ref[name])).sum()} differing words"
+
+
+def _upload(a):
+    import torch
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:
+        a = a.view(np.int16)
+    return torch.from_numpy(a.copy()).to("cuda:0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(640, 480), (61, 47)])
+def test_combined_predict_is_bit_exact(built, size):
+    from oracle import predict_oracle as po
+    from slam_b200.predict import ModelPredictor
+    scene, intr = make_scene(*size) if size == (640, 480) else make_scene(64, 48)
+    if size != (640, 480):
+        intr = dict(intr, width=size[0], height=size[1])
+    poses = scene.trajectory(60)
+    model = np.concatenate([surfels_from_frame(scene, dict(intr, width=scene.width, height=scene.height), poses[0]),
+                            surfels_from_frame(scene, dict(intr, width=scene.width, height=scene.height), poses[30], time=4, seed=1),
+                            awkward_surfels(poses[12], np.random.default_rng(7))])
+    mp = ModelPredictor(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    d_model = _upload(model)
+    for view, call in ((12, CALL), (31, dict(CALL, conf_threshold=15.0, time=5, max_time=4, time_delta=3)), (0, dict(CALL, depth_cutoff=2.0))):
+        mp.indexMap.combinedPredict(poses[view], d_model, len(model), call["depth_cutoff"], call["conf_threshold"], call["time"], call["max_time"],
+                                    call["time_delta"])
+        ref = po.combined_predict(model, poses[view], intr, **call, tinv=mp.tInv())
+        d24, win = mp.winners()
+        assert np.array_equal(win, ref["winner"]) and np.array_equal(d24, ref["depth24"])
+        _assert_textures_equal(mp, ref)
+        assert mp.lastFragments() == ref["fragments"]
+        # the product's own pose inverse against the independent one: same prediction up to rounding
+        ref2 = po.combined_predict(model, poses[view], intr, **call)
+        assert ((ref2["winner"] >= 0) == (win >= 0)).mean() > 0.995 and (ref2["winner"] == win).mean() > 0.7
+        both = (ref2["winner"] >= 0) & (win >= 0)
+        assert both.any() and np.quantile(np.abs(ref2["vertex"][..., 2] - ref["vertex"][..., 2])[both], 0.999) < 1e-4     # disc edges flip at occlusion boundaries
+    assert (win >= 0).mean() > 0.5
+    # repeated call: identical (the resolve launch re-arms the z-buffer); empty model: cleared textures
+    mp.indexMap.combinedPredict(poses[0], d_model, len(model), 2.0, 10.0, 10, 10, 200)
+    _assert_textures_equal(mp, ref)
+    mp.indexMap.combinedPredict(poses[0], d_model, 0, 2.0, 10.0, 10, 10, 200)
+    assert not mp.download("vertex").any() and not mp.download("image").any() and (mp.winners()[1] == -1).all()
+
+
+@pytest.mark.gpu
+def test_fill_in_and_fused_frame_are_bit_exact(built):
+    from oracle import predict_oracle as po
+    from slam_b200.predict import ModelPredictor
+    scene, intr = make_scene(640, 480)
+    poses = scene.trajectory(40)
+    model = surfels_from_frame(scene, intr, poses[0], stride=1)
+    model = model[: len(model) * 2 // 3]                       # leave holes for the fill passes
+    depth, rgba = scene.render_frame(poses[5])
+    depth = depth.copy()
+    depth[100:140, 200:260] = 0
+    mp = ModelPredictor(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    d_model, d_depth, d_rgba = _upload(model), _upload(depth), _upload(rgba)
+    # separate calls, the reference's sequence (apps/elastic_fusion_file.cpp:21-43)
+    mp.indexMap.combinedPredict(poses[5], d_model, len(model), MODEL_CUTOFF, 10.0, 10, 10, 200)
+    mp.fillIn.vertex(mp.indexMap.vertexTex(), d_depth, False)
+    mp.fillIn.normal(mp.indexMap.normalTex(), d_depth, False)
+    mp.fillIn.image(mp.indexMap.imageTex(), d_rgba, False)
+    ref = po.combined_predict(model, poses[5], intr, **CALL, tinv=mp.tInv())
+    fill = po.fill_in(intr, depth, rgba, vertex=ref["vertex"], normal=ref["normal"], image=ref["image"])
+    holes = ref["winner"] < 0
+    assert 0.02 < holes.mean() < 0.9
+    _assert_textures_equal(mp, ref)
+    sep = {k: mp.download("fill_" + k) for k in ("vertex", "normal", "image")}
+    for k in sep:
+        bad = _bits(sep[k]) != _bits(fill[k])
+        assert not bad.any(), f"{k}: {bad.sum()} differing words, first at {np.argwhere(bad)[0]}: {sep[k][bad][0]} vs {fill[k][bad][0]}"
+    both_holes = holes[:-1, :-1] & (depth[:-1, :-1] == 0) & (depth[1:, :-1] == 0) & (depth[:-1, 1:] == 0)
+    assert both_holes.any() and np.isnan(sep["normal"][:-1, :-1][both_holes][:, :3]).all()      # normalize(0): NaN, as GLSL's 0 * inf
+    # fused call: same FillIn textures, IndexMap textures too when asked for
+    mp.predict(poses[5], d_model, len(model), MODEL_CUTOFF, 10.0, 10, 200, d_depth, d_rgba, write_index_textures=True)
+    _assert_textures_equal(mp, ref)
+    _assert_textures_equal(mp, fill, names=("vertex", "normal", "image"), prefix="fill_")
+    # passthrough and caller-supplied `existing` textures
+    mp.fillIn.vertex(None, d_depth, True)
+    mp.fillIn.image(d_rgba, d_rgba, False)
+    pt = po.fill_in(intr, depth, rgba, vertex=ref["vertex"], passthrough=True)
+    assert np.array_equal(_bits(mp.download("fill_vertex")), _bits(pt["vertex"]))
+    assert np.array_equal(mp.download("fill_image"), rgba)
+
+
+@pytest.mark.gpu
+def test_prediction_feeds_the_tracker(built):
+    """Frame k's surfels predicted at the prior pose of frame k+1 track frame k+1 like the analytic model maps do."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    from slam_b200.predict import ModelPredictor
+    from tests.support import frame_pair, run_frame, to_device
+    scene, intr = make_scene(640, 480)
+    poses = scene.trajectory(1000)
+    # GL convention: pixel (x, y) is shaded along the ray through gl_FragCoord = (x + 0.5, y + 0.5).  The synthetic camera shoots its
+    # ray for pixel x through x itself, so a predictor given (cx, cy) is half a pixel off against these frames (a bias of the test data,
+    # ~1e-3 rad); given (cx + 0.5, cy + 0.5) it is the same camera and must track like the analytic maps.
+    mp_gl = ModelPredictor(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    mp_same = ModelPredictor(intr["width"], intr["height"], intr["cx"] + 0.5, intr["cy"] + 0.5, intr["fx"], intr["fy"])
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    rep = dict(t_gl=[], R_gl=[], t_same=[], R_same=[], t_analytic=[], R_analytic=[], covered=[])
+    frames = (1, 200, 640)
+    for k in frames:
+        model = surfels_from_frame(scene, intr, poses[k - 1])
+        d_model = _upload(model)
+        fr = frame_pair(scene, poses, k)
+        d = to_device(fr)
+        t_a, R_a = run_frame(odo, d, first_rgb=d["mrgba"])
+        rep["t_analytic"].append(float(np.abs(t_a - poses[k][:3, 3]).max()))
+        rep["R_analytic"].append(float(np.abs(R_a - poses[k][:3, :3]).max()))
+        for name, mp in (("gl", mp_gl), ("same", mp_same)):
+            mp.predict(poses[k - 1], d_model, len(model), MODEL_CUTOFF, 10.0, 1, 200, d["depth"], d["rgba"])
+            if name == "gl":
+                rep["covered"].append(float((mp.winners()[1] >= 0).mean()))
+            dp = dict(d, mv=mp.fillIn.vertexTexture, mn=mp.fillIn.normalTexture, mrgba=mp.fillIn.imageTexture)
+            torch.cuda.synchronize()
+            t_p, R_p = run_frame(odo, dp, first_rgb=mp.fillIn.imageTexture)
+            rep["t_" + name].append(float(np.abs(t_p - poses[k][:3, 3]).max()))
+            rep["R_" + name].append(float(np.abs(R_p - poses[k][:3, :3]).max()))
+    rep["prior"] = float(max(np.abs(poses[k][:3, 3] - poses[k - 1][:3, 3]).max() for k in frames))
+    rep["prior_rot"] = float(max(np.abs(poses[k][:3, :3] - poses[k - 1][:3, :3]).max() for k in frames))
+    print(rep)
+    assert min(rep["covered"]) > 0.5, rep       # the synthetic model maps end at 3.5 m
+    assert max(rep["t_gl"]) < 3e-3 and max(rep["t_gl"]) < 0.5 * rep["prior"] and max(rep["R_gl"]) < 4e-3 and max(rep["R_gl"]) < 0.5 * rep["prior_rot"], rep
+    assert max(rep["t_same"]) < max(2 * max(rep["t_analytic"]), 1.5e-3) and max(rep["R_same"]) < max(2 * max(rep["R_analytic"]), 1e-3), rep
