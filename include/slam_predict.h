@@ -87,7 +87,8 @@ int slam_predict_get_tinv(slam_predict_t h, float * tinv16);
 /* the resolved z-buffer of the last combined / frame call: per pixel the 24-bit depth (0xFFFFFF = empty) and the index of
  * the winning surfel (-1 = empty); host arrays of width x height, either may be NULL.  Valid until the next call. */
 int slam_predict_get_winners(slam_predict_t h, uint32_t * depth24, int32_t * surfel);
-/* CUDA-event times of the last call's launches (ms) and the number of fragments its splat launch evaluated. */
+/* CUDA-event times of the last call's launches (ms) and the number of fragments its splat launch evaluated (GL's sprite
+ * squares minus the parts outside the projected quad around each disc, which the fragment shader could only discard). */
 int slam_predict_last_ms(slam_predict_t h, float * splat_ms, float * resolve_ms);
 int slam_predict_last_fragments(slam_predict_t h, unsigned long long * fragments);
 

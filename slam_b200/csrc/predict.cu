@@ -83,7 +83,11 @@ __device__ __forceinline__ bool surfel_view(const float4 pos, const float4 col, 
 }
 
 // splat.vert:56 (gl_Position, rule R1) and :67-86 (gl_PointSize, rule R2).  Returns false when the point is clipped.
-__device__ __forceinline__ bool surfel_sprite(const SurfelView & s, const PredictCam & k, float & xw, float & yw, float & size)
+// `quad` receives the bounding box (xmin, xmax, ymin, ymax) of the four projected points; quad_ok tells whether all four lie in
+// front of the camera, in which case the projected disc is inside that box (the four points are the corners of the square
+// circumscribing the disc, and a perspective projection maps the convex hull of points in front of the camera onto the hull
+// of their projections).
+__device__ __forceinline__ bool surfel_sprite(const SurfelView & s, const PredictCam & k, float & xw, float & yw, float & size, float4 & quad, bool & quad_ok)
 {
     xw = (k.fx * s.px) / s.pz + k.cx;
     yw = (k.fy * s.py) / s.pz + k.cy;
@@ -95,27 +99,31 @@ __device__ __forceinline__ bool surfel_sprite(const SurfelView & s, const Predic
     const float al = sqrtf(dot3(ax, ay, az, ax, ay, az));
     const float x1x = ((ax / al) * s.rad) * 1.41421356f, x1y = ((ay / al) * s.rad) * 1.41421356f, x1z = ((az / al) * s.rad) * 1.41421356f;
     const float y1x = s.ny * x1z - s.nz * x1y, y1y = s.nz * x1x - s.nx * x1z, y1z = s.nx * x1y - s.ny * x1x;
-    float xmin, xmax, ymin, ymax;
+    float xmin, xmax, ymin, ymax, zmin;
     {
         const float qx = s.px + x1x, qy = s.py + x1y, qz = s.pz + x1z;
         xmin = xmax = (k.fx * qx) / qz + k.cx;
         ymin = ymax = (k.fy * qy) / qz + k.cy;
+        zmin = qz;
     }
     {
         const float qx = s.px + y1x, qy = s.py + y1y, qz = s.pz + y1z;
         const float u = (k.fx * qx) / qz + k.cx, v = (k.fy * qy) / qz + k.cy;
-        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v);
+        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v), zmin = fminf(zmin, qz);
     }
     {
         const float qx = s.px - y1x, qy = s.py - y1y, qz = s.pz - y1z;
         const float u = (k.fx * qx) / qz + k.cx, v = (k.fy * qy) / qz + k.cy;
-        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v);
+        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v), zmin = fminf(zmin, qz);
     }
     {
         const float qx = s.px - x1x, qy = s.py - x1y, qz = s.pz - x1z;
         const float u = (k.fx * qx) / qz + k.cx, v = (k.fy * qy) / qz + k.cy;
-        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v);
+        xmin = fminf(xmin, u), xmax = fmaxf(xmax, u), ymin = fminf(ymin, v), ymax = fmaxf(ymax, v), zmin = fminf(zmin, qz);
     }
+    quad = make_float4(xmin, xmax, ymin, ymax);
+    // all four finite and in front of the camera (a NaN anywhere fails the comparison chain)
+    quad_ok = zmin > 0.f && (xmax - xmin) < 1e6f && (ymax - ymin) < 1e6f;
     const float xd = fabsf(xmax - xmin), yd = fabsf(ymax - ymin);
     size = fmaxf(0.f, fmaxf(xd, yd));
     size = fminf(fmaxf(size, 1.f), k.max_point);
@@ -159,6 +167,7 @@ __global__ void __launch_bounds__(256) k_zclear(unsigned long long * __restrict_
 
 constexpr int kSplatWarps = 8;
 constexpr int kRecWords = 12;
+constexpr float kQuadPad = 0.01f;
 constexpr int kFragsPerTrip = 2;   // measured on B200: 1..4 within 5 % of each other (the loop is issue bound), 2 and 3 best
 
 // Pixel index of fragment `local` of a sprite record (row-major inside its bounding box).  The row comes from a float
@@ -196,13 +205,22 @@ __global__ void __launch_bounds__(kSplatWarps * 32) k_splat(const float4 * __res
             const float4 pos = __ldcs(surfels + 3 * (size_t)i), col = __ldcs(surfels + 3 * (size_t)i + 1), nr = __ldcs(surfels + 3 * (size_t)i + 2);
             SurfelView s;
             float xw, yw, size;
-            if(surfel_view(pos, col, nr, c, s) && surfel_sprite(s, k, xw, yw, size))
+            float4 quad;
+            bool quad_ok;
+            if(surfel_view(pos, col, nr, c, s) && surfel_sprite(s, k, xw, yw, size, quad, quad_ok))
             {
                 const float h = size * 0.5f;
                 // pixels with xw - h <= px + 0.5 < xw + h
                 int x0 = (int)ceilf((xw - h) - 0.5f), x1 = (int)ceilf((xw + h) - 0.5f) - 1;
                 int y0 = (int)ceilf((yw - h) - 0.5f), y1 = (int)ceilf((yw + h) - 0.5f) - 1;
                 x0 = max(x0, 0), y0 = max(y0, 0), x1 = min(x1, k.W - 1), y1 = min(y1, k.H - 1);
+                if(quad_ok)
+                {
+                    // Fragments of the sprite square outside the projected quad can only fail the disc test: skip them.  The box is
+                    // widened by kQuadPad pixels, two orders of magnitude above the fp32 rounding of the projections (~1e-4 px).
+                    x0 = max(x0, (int)ceilf((quad.x - kQuadPad) - 0.5f)), x1 = min(x1, (int)ceilf((quad.y + kQuadPad) - 0.5f) - 1);
+                    y0 = max(y0, (int)ceilf((quad.z - kQuadPad) - 0.5f)), y1 = min(y1, (int)ceilf((quad.w + kQuadPad) - 0.5f) - 1);
+                }
                 if(x1 >= x0 && y1 >= y0)
                 {
                     const int w = x1 - x0 + 1;

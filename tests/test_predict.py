@@ -242,7 +242,9 @@ def test_combined_predict_is_bit_exact(built, size):
         d24, win = mp.winners()
         assert np.array_equal(win, ref["winner"]) and np.array_equal(d24, ref["depth24"])
         _assert_textures_equal(mp, ref)
-        assert mp.lastFragments() == ref["fragments"]
+        # the splat launch skips the part of a sprite square that lies outside the projected quad around the disc (those fragments
+        # can only be discarded), so it evaluates fewer fragments than GL generates -- with identical results, as asserted above
+        assert 0.5 * ref["fragments"] < mp.lastFragments() <= ref["fragments"]
         # the product's own pose inverse against the independent one: same prediction up to rounding
         ref2 = po.combined_predict(model, poses[view], intr, **call)
         assert ((ref2["winner"] >= 0) == (win >= 0)).mean() > 0.995 and (ref2["winner"] == win).mean() > 0.7
@@ -315,7 +317,7 @@ def test_prediction_feeds_the_tracker(built):
     rep = dict(t_gl=[], R_gl=[], t_same=[], R_same=[], t_analytic=[], R_analytic=[], covered=[])
     frames = (1, 200, 640)
     for k in frames:
-        model = surfels_from_frame(scene, intr, poses[k - 1])
+        model = surfels_from_frame(scene, intr, poses[k - 1], conf=25.0)      # all stable: no corner holes for the fill-in to patch with the new frame
         d_model = _upload(model)
         fr = frame_pair(scene, poses, k)
         d = to_device(fr)
