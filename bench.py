@@ -636,6 +636,34 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
                     "resolve_GBps": W * H * 128 / (resolve_us * 1e-6) / 1e9, "covered": float((mp.winners()[1] >= 0).mean())}
                 del d_model
             mp.close()
+            # the reference's frame loop minus fusion: predict at the last estimated pose, then track from it (one stream, device pointers)
+            mp = ModelPredictor(W, H, 319.5 + 0.5, 239.5 + 0.5, 481.20, -480.0, device=local_rank, stream=odo.stream)
+            model = np.concatenate([surfels_from_frame(scene, poses[k], conf=25.0, seed=k) for k in (95, 110, 125, 140, 160)])
+            d_model = torch.from_numpy(model).to(dev)
+            up16 = lambda a: torch.from_numpy(a.view(np.int16).copy()).to(dev)
+            seq = [scene.render_frame(poses[k]) for k in range(101, 141)]
+            dseq = [(up16(d), torch.from_numpy(c).to(dev)) for d, c in seq]
+            tex = mp.fillIn
+
+            def loop(n, pose):
+                for i in range(n):
+                    dd, dc = dseq[i]
+                    mp.predict(pose, d_model, len(model), MODEL_CUTOFF, 10.0, i, 1000, dd, dc)
+                    fr = odo.make_frame(dd, dc, tex.vertexTexture, tex.normalTexture, tex.imageTexture, pose, DEPTH_CUTOFF, MODEL_CUTOFF)
+                    t, R = odo.track_device(fr, pose[:3, 3].copy(), pose[:3, :3].copy())
+                    pose = np.eye(4, dtype=np.float32)
+                    pose[:3, :3], pose[:3, 3] = R.reshape(3, 3), t
+                return pose
+            loop(5, poses[100].copy())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            last = loop(len(dseq), poses[100].copy())
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["closed loop: predict at the estimated pose + track, %d surfels" % len(model)] = {
+                "frames_per_s": len(dseq) / dt, "ms_per_frame": dt / len(dseq) * 1e3,
+                "final_error_mm": float(np.linalg.norm(last[:3, 3] - poses[140][:3, 3]) * 1e3)}
+            mp.close()
         except Exception as e:   # the extra must never take the headline down
             out["model prediction"] = {"error": str(e)[:200]}
     # ---- configs[2]

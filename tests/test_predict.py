@@ -339,3 +339,46 @@ def test_prediction_feeds_the_tracker(built):
     assert min(rep["covered"]) > 0.5, rep       # the synthetic model maps end at 3.5 m
     assert max(rep["t_gl"]) < 3e-3 and max(rep["t_gl"]) < 0.5 * rep["prior"] and max(rep["R_gl"]) < 4e-3 and max(rep["R_gl"]) < 0.5 * rep["prior_rot"], rep
     assert max(rep["t_same"]) < max(2 * max(rep["t_analytic"]), 1.5e-3) and max(rep["R_same"]) < max(2 * max(rep["R_analytic"]), 1e-3), rep
+
+
+@pytest.mark.gpu
+def test_closed_loop_predict_then_track(built):
+    """The reference's frame loop without the fusion step (apps/elastic_fusion_file.cpp:356-374 + predict(), :612): a fixed surfel model,
+    every frame predicted at the LAST ESTIMATED pose and tracked from it, 60 frames, predictor and tracker on one stream with the
+    FillIn textures handed over as device pointers.  The estimated trajectory must stay on the ground truth."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    from slam_b200.predict import ModelPredictor
+    from slam_b200.synth import ate_rmse
+    scene, intr = make_scene(640, 480)
+    poses = scene.trajectory(1000)
+    first, n_frames = 100, 60
+    # the map: surfels seen from five views along (and slightly beyond) the stretch that is tracked, all stable
+    model = np.concatenate([surfels_from_frame(scene, intr, poses[k], conf=25.0, seed=k) for k in (95, 110, 125, 140, 160)])
+    d_model = _upload(model)
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    # same camera as the synthetic frames (see test_prediction_feeds_the_tracker), same stream as the tracker
+    mp = ModelPredictor(intr["width"], intr["height"], intr["cx"] + 0.5, intr["cy"] + 0.5, intr["fx"], intr["fy"], stream=odo.stream)
+    pose = poses[first].copy()
+    est = [pose.copy()]
+    for k in range(first + 1, first + 1 + n_frames):
+        depth, rgba = scene.render_frame(poses[k])
+        d_depth, d_rgba = _upload(depth), _upload(rgba)
+        mp.predict(pose, d_model, len(model), MODEL_CUTOFF, 10.0, k, 1000, d_depth, d_rgba)
+        if k == first + 1:
+            odo.initFirstRGB(mp.fillIn.imageTexture)
+        odo.initICPModel(mp.fillIn.vertexTexture, mp.fillIn.normalTexture, MODEL_CUTOFF, pose)
+        odo.initRGBModel(mp.fillIn.imageTexture)
+        odo.initICP(d_depth, DEPTH_CUTOFF)
+        odo.initRGB(d_rgba)
+        t, R = odo.getIncrementalTransformation(pose[:3, 3].copy(), pose[:3, :3].copy(), False, 10.0, True, False, True)
+        pose = np.eye(4, dtype=np.float32)
+        pose[:3, :3], pose[:3, 3] = R, t
+        est.append(pose.copy())
+    est = np.array(est)
+    gt = poses[first:first + 1 + n_frames]
+    ate = ate_rmse(gt[:, :3, 3], est[:, :3, 3])
+    drift = np.abs(est[-1, :3, 3] - gt[-1, :3, 3]).max()
+    travelled = np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1).sum()
+    print(dict(ate_mm=ate * 1e3, final_drift_mm=drift * 1e3, travelled_m=travelled))
+    assert travelled > 0.3 and ate < 5e-3 and drift < 1e-2, (ate, drift, travelled)
