@@ -434,24 +434,9 @@ static int predict_check(slam_predict_t h)
     return SLAM_OK;
 }
 
-extern "C" int slam_predict_create(const slam_predict_params * params, slam_predict_t * out)
+// streams, events, buffers and the one-off tables of a new handle; on failure the caller destroys the partly built handle
+static int predict_setup(slam_predict * h, const slam_predict_params * params)
 {
-    SLAM_ARG_CHECK(params && out);
-    SLAM_ARG_CHECK(params->width > 0 && params->height > 0 && params->width <= 8192 && params->height <= 8192);
-    SLAM_ARG_CHECK(params->fx != 0.f && params->fy != 0.f);
-    int ndev = 0;
-    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-    {
-        set_last_error("no CUDA device: libslam_odom has no CPU fallback");
-        return SLAM_ERR_CUDA;
-    }
-    SLAM_ARG_CHECK(params->device >= 0 && params->device < ndev);
-    SLAM_CUDA_TRY(cudaSetDevice(params->device));
-    slam_predict * h = new slam_predict();
-    h->p = *params;
-    h->cam = PredictCam{params->cx, params->cy, params->fx, params->fy, (float)params->width, (float)params->height,
-                        params->max_point_size > 0.f ? params->max_point_size : 2047.f, params->width, params->height};
-    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, params->device);
     if(params->stream)
         h->stream = (cudaStream_t)params->stream;
     else
@@ -482,6 +467,32 @@ extern "C" int slam_predict_create(const slam_predict_params * params, slam_pred
     SLAM_CUDA_TRY(cudaMemsetAsync(h->winners, 0xFF, n * 8, h->stream));
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
     SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+extern "C" int slam_predict_create(const slam_predict_params * params, slam_predict_t * out)
+{
+    SLAM_ARG_CHECK(params && out);
+    SLAM_ARG_CHECK(params->width > 0 && params->height > 0 && params->width <= 8192 && params->height <= 8192);
+    SLAM_ARG_CHECK(params->fx != 0.f && params->fy != 0.f);
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    {
+        set_last_error("no CUDA device: libslam_odom has no CPU fallback");
+        return SLAM_ERR_CUDA;
+    }
+    SLAM_ARG_CHECK(params->device >= 0 && params->device < ndev);
+    SLAM_CUDA_TRY(cudaSetDevice(params->device));
+    slam_predict * h = new slam_predict();
+    h->p = *params;
+    h->cam = PredictCam{params->cx, params->cy, params->fx, params->fy, (float)params->width, (float)params->height,
+                        params->max_point_size > 0.f ? params->max_point_size : 2047.f, params->width, params->height};
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, params->device);
+    if(int rc = predict_setup(h, params))
+    {
+        slam_predict_destroy(h);
+        return rc;
+    }
     *out = h;
     return SLAM_OK;
 }
@@ -490,13 +501,13 @@ extern "C" int slam_predict_destroy(slam_predict_t h)
 {
     if(!h) return SLAM_OK;
     cudaSetDevice(h->p.device);
-    cudaStreamSynchronize(h->stream);
+    if(h->stream) cudaStreamSynchronize(h->stream);
     for(void * b : {(void *)h->rays, (void *)h->zbuf, (void *)h->winners, (void *)h->frag_counter, (void *)h->image, (void *)h->fill_image, (void *)h->vertex,
                     (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal, (void *)h->time})
         cudaFree(b);
     for(auto & e : h->ev)
         if(e) cudaEventDestroy(e);
-    if(h->own_stream) cudaStreamDestroy(h->stream);
+    if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SLAM_OK;
 }

@@ -151,6 +151,9 @@ def load_library():
     return lib
 
 
+_FP = C.POINTER(C.c_float)
+
+
 def _fptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
@@ -276,10 +279,13 @@ class RGBDOdometry:
         return fr
 
     def _track(self, fn, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
-        t = np.ascontiguousarray(trans, dtype=np.float32).reshape(-1).copy()
-        r = np.ascontiguousarray(rot, dtype=np.float32).reshape(-1).copy()
-        _check(self.lib, fn(self._h, C.byref(frame), _fptr(t), _fptr(r), int(bool(rgbOnly)), float(icpWeight), int(bool(pyramid)), int(bool(fastOdom)),
-                            int(bool(so3))))
+        # one conversion per argument: np.array(copy) + cached ctypes pointers keep the per-frame host cost of the mirror small
+        t = np.array(trans, dtype=np.float32).reshape(-1)
+        r = np.array(rot, dtype=np.float32).reshape(-1)
+        rc = fn(self._h, C.byref(frame), t.ctypes.data_as(_FP), r.ctypes.data_as(_FP), int(bool(rgbOnly)), float(icpWeight), int(bool(pyramid)),
+                int(bool(fastOdom)), int(bool(so3)))
+        if rc != 0:
+            _check(self.lib, rc)
         return t.reshape(np.shape(trans)), r.reshape(np.shape(rot))
 
     def track_device(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True):
