@@ -336,7 +336,7 @@ __device__ __forceinline__ void candidate_batch(const ResidualArgs & a, const bo
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kGnThreads, 1)
 k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, float * partials, GnResult * results, slam_step_record * trace,
-                int * trace_count, const int G, const int groups)
+                int * trace_count, const int G, const int groups, GnResult * host_results, unsigned * host_flags, const unsigned host_seqno)
 {
     __shared__ GnShared sh;
 
@@ -826,6 +826,18 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         }
 
         if(threadIdx.x == 0) seq_end(sh, L.rgb, L.rgb_only, leader ? &results[seq] : nullptr);
+        if(rank == 0 && host_results && warp0)   // `leader` is thread 0 of the group's first CTA: all of its warp 0 copies
+        {
+            // The result block also goes straight to mapped host memory, followed by a per-sequence flag the host polls: the caller
+            // has its pose ~1 us after the last solve instead of after kernel retirement + a D2H copy + a stream synchronisation.
+            __syncwarp();
+            const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
+            uint2 * dst = reinterpret_cast<uint2 *>(host_results + seq);
+            for(int k = threadIdx.x; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
+            __threadfence_system();
+            __syncwarp();
+            if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + seq) = host_seqno;
+        }
         if(leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();
     }
@@ -933,7 +945,7 @@ int gn_stage_inputs(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, c
 }
 
 int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnResult * h_results,
-               cudaStream_t stream)
+               cudaStream_t stream, unsigned * h_flags, unsigned seqno)
 {
     GnSeqIn * in = nullptr;
     if(int rc = gn_stage_inputs(d, L, seqs, trans, rot, &in)) return rc;
@@ -951,7 +963,9 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     slam_step_record * trace = d.trace;
     int * trace_count = d.trace_count;
     GnSeqIn seq0 = in[0];
-    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &partials, &results, &trace, &trace_count, &G, &groups};
+    // h_flags != nullptr: h_results / h_flags are mapped pinned memory the kernel writes itself (device view == host pointer under UVA)
+    GnResult * host_results = h_flags ? h_results : nullptr;
+    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &partials, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(d.profiling)
     {
@@ -968,7 +982,7 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         d.ev.push_back(e0);
         d.ev.push_back(e1);
     }
-    SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * L.batch, cudaMemcpyDeviceToHost, stream));
+    if(!h_flags) SLAM_CUDA_TRY(cudaMemcpyAsync(h_results, d.results, sizeof(GnResult) * L.batch, cudaMemcpyDeviceToHost, stream));
     d.so3_swapped = L.so3;
     return SLAM_OK;
 }

@@ -84,8 +84,10 @@ int gn_fold_profile(GnDevice & d);
 size_t gn_state_bytes(int batch);
 void gn_bind_state(GnDevice & d, char * base, int batch);
 int gn_stage_inputs(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnSeqIn ** out);
+// h_flags != nullptr: zero-copy completion -- the kernel writes h_results (mapped pinned memory) itself and then stores seqno into
+// h_flags[seq]; otherwise the results follow with a D2H copy on `stream`.
 int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnResult * h_results,
-               cudaStream_t stream);
+               cudaStream_t stream, unsigned * h_flags = nullptr, unsigned seqno = 0);
 int gn_read_trace(GnDevice & d, int seq, slam_step_record * out, int max_records, int * n_records, cudaStream_t stream);
 void gn_release(GnDevice & d);
 

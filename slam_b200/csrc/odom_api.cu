@@ -8,6 +8,8 @@
 //     (gn_kernel.cu); the host only enqueues it and reads back 48 bytes of pose;
 //   * host-stepped (params.host_loop = 1): the reference's control flow, one reduction
 //     launch + one sync per step, kept for step-by-step parity checks against the reference replay.
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <cstring>
 #include <cmath>
@@ -68,7 +70,11 @@ struct slam_odom
     // device-resident loop
     GnDevice gn;                      // device pointers of the persistent kernel's state
     BatchDevice be;                   // batched streaming engine (batch >= kBatchEngineMin)
-    GnResult * h_results = nullptr;   // pinned [batch]
+    GnResult * h_results = nullptr;   // pinned, mapped [batch]
+    unsigned * h_flags = nullptr;     // pinned, mapped [batch]: completion sequence numbers written by the persistent kernel
+    unsigned zc_seqno = 0;            // sequence number of the launch in flight
+    bool zero_copy = false;           // results + completion flag written by the kernel itself (single-launch loop only)
+    bool zc_pending = false;
     float * h_sums = nullptr;         // pinned scratch for the host-stepped loop [96]
 
     std::vector<slam_odom_stats> stats;
@@ -707,7 +713,18 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
         h->be.num_sms = h->num_sms;
     }
 
-    SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_results, sizeof(GnResult) * h->batch));
+    SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_results, sizeof(GnResult) * h->batch, cudaHostAllocMapped));
+    SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_flags, sizeof(unsigned) * h->batch, cudaHostAllocMapped));
+    memset(h->h_flags, 0, sizeof(unsigned) * h->batch);
+    {
+        // zero-copy completion needs the device view of the pinned block to be the host pointer (unified addressing)
+        void * dv = nullptr;
+        const char * off = getenv("SLAM_ODOM_ZERO_COPY");
+        h->zero_copy = !(off && off[0] == '0') && cudaHostGetDevicePointer(&dv, h->h_results, 0) == cudaSuccess && dv == (void *)h->h_results &&
+                       cudaHostGetDevicePointer(&dv, h->h_flags, 0) == cudaSuccess && dv == (void *)h->h_flags;
+        cudaGetLastError();
+        if(getenv("SLAM_ODOM_DEBUG")) fprintf(stderr, "slam_odom_create: zero-copy completion %s\n", h->zero_copy ? "on" : "off");
+    }
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_sums, 128 * 4));
 
     h->stats.resize(h->batch);
@@ -745,6 +762,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     gn_release(h->gn);
     if(h->arena) cudaFree(h->arena);
     if(h->h_results) cudaFreeHost(h->h_results);
+    if(h->h_flags) cudaFreeHost(h->h_flags);
     if(h->h_sums) cudaFreeHost(h->h_sums);
     if(h->h_poses12) cudaFreeHost(h->h_poses12);
     if(h->score_ws) cudaFree(h->score_ws);
@@ -909,7 +927,10 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     }
     else
     {
-        rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream);
+        const bool zc = h->zero_copy && !h->trace_on;
+        if(zc) h->zc_seqno++;
+        rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream, zc ? h->h_flags : nullptr, h->zc_seqno);
+        h->zc_pending = zc && rc == SLAM_OK;
         h->launches++;
     }
     if(rc) return rc;
@@ -920,9 +941,52 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     return SLAM_OK;
 }
 
+// Wait for the completion flags the persistent kernel writes into mapped host memory after its last solve.  The stream is polled
+// now and then so that a failed launch surfaces as an error instead of a hang.
+static int wait_zero_copy(slam_odom_t h)
+{
+    volatile unsigned * flags = h->h_flags;
+    for(unsigned spins = 1;; spins++)
+    {
+        bool all = true;
+        for(int b = 0; b < h->batch; b++) all = all && flags[b] == h->zc_seqno;
+        if(all) break;
+        if((spins & 0x3fff) == 0)
+        {
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            if(q == cudaSuccess)
+            {
+                for(int b = 0; b < h->batch; b++)
+                    if(flags[b] != h->zc_seqno)
+                    {
+                        set_last_error("persistent kernel finished without publishing its results");
+                        return SLAM_ERR_CUDA;
+                    }
+                break;
+            }
+            if(q != cudaErrorNotReady)
+            {
+                set_last_error(std::string("persistent kernel: ") + cudaGetErrorString(q));
+                return SLAM_ERR_CUDA;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return SLAM_OK;
+}
+
 static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
 {
-    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if(h->pending_async && h->zc_pending)
+    {
+        h->zc_pending = false;
+        if(int rc = wait_zero_copy(h)) return rc;
+    }
+    else
+        SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
     if(!h->pending_async) return SLAM_OK;
     h->pending_async = false;
     for(int b = 0; b < h->batch; b++)
@@ -1239,15 +1303,6 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         const size_t S = h->seq_stride;
         SeqBuffers & s = h->seq[0];
         int rc = SLAM_OK;
-        for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
-        {
-            const LevelGeom & g = h->geom[l];
-            rc = launch_depth_level(l == 0 ? depth : s.depth[l], g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, depth_cutoff, s.vcurr[l], s.ncurr[l],
-                                    l + 1 < h->levels ? s.depth[l + 1] : nullptr, h->aux_stream, B, l == 0 ? n0 * 2 : S, S);
-            h->launches++;
-        }
-        if(rc) return rc;
-        SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
         for(int b = 0; b < B; b++)
         {
             const float * q = poses16 + 16 * b;
@@ -1299,6 +1354,16 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
                 h->launches++;
             }
         }
+        // the depth branch is enqueued after the (longer) model / RGB branch so that the critical path starts first; it only waits for fork_ev
+        for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
+        {
+            const LevelGeom & g = h->geom[l];
+            rc = launch_depth_level(l == 0 ? depth : s.depth[l], g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, depth_cutoff, s.vcurr[l], s.ncurr[l],
+                                    l + 1 < h->levels ? s.depth[l + 1] : nullptr, h->aux_stream, B, l == 0 ? n0 * 2 : S, S);
+            h->launches++;
+        }
+        if(rc) return rc;
+        SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
         h->have_depth_tmp = true;
         SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         if(defer_wait) return slam_odom_get_incremental_transformation_async(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
