@@ -56,7 +56,15 @@ typedef struct slam_predict_textures
     const uint8_t * fill_image;   /* FillIn::imageTexture   RGBA8                      */
     const float * fill_vertex;    /* FillIn::vertexTexture  RGBA32F                    */
     const float * fill_normal;    /* FillIn::normalTexture  RGBA32F                    */
+    const uint8_t * old_image;    /* IndexMap::oldImageTex()   (INACTIVE prediction)   */
+    const float * old_vertex;     /* IndexMap::oldVertexTex()                          */
+    const float * old_normal;     /* IndexMap::oldNormalTex()                          */
+    const uint16_t * old_time;    /* IndexMap::oldTimeTex()                            */
 } slam_predict_textures;
+
+/* IndexMap::Prediction (model/IndexMap.h): which frame buffer combinedPredict renders into. */
+#define SLAM_PREDICT_ACTIVE 0
+#define SLAM_PREDICT_INACTIVE 1
 
 int slam_predict_create(const slam_predict_params * params, slam_predict_t * out);
 int slam_predict_destroy(slam_predict_t h);
@@ -65,6 +73,12 @@ int slam_predict_get_textures(slam_predict_t h, slam_predict_textures * out);
 /* IndexMap::combinedPredict (ACTIVE).  d_surfels: count x 12 floats, the model VBO; pose16: row-major 4x4 (host). */
 int slam_predict_combined(slam_predict_t h, const float * d_surfels, int count, const float * pose16, float depth_cutoff, float conf_threshold,
                           int time, int max_time, int time_delta);
+
+/* The same with the reference's last argument: SLAM_PREDICT_INACTIVE renders the old part of the map (apps/elastic_fusion_file.cpp:450-457
+ * calls it with time 0, maxTime tick - timeDelta) into the old* textures, which modelToModel.initICPModel / initRGBModel read
+ * (apps/elastic_fusion_file.cpp:460-463); the ACTIVE textures are left untouched. */
+int slam_predict_combined_type(slam_predict_t h, const float * d_surfels, int count, const float * pose16, float depth_cutoff, float conf_threshold,
+                               int time, int max_time, int time_delta, int prediction_type);
 
 /* FillIn::vertex / ::normal / ::image.  `existing` NULL => the handle's own IndexMap texture of that kind. */
 int slam_predict_fill_vertex(slam_predict_t h, const float * d_existing_vertex4, const uint16_t * d_raw_depth, int passthrough);
@@ -78,7 +92,8 @@ int slam_predict_frame(slam_predict_t h, const float * d_surfels, int count, con
                        int max_time, int time_delta, const uint16_t * d_raw_depth, const uint8_t * d_raw_rgba, int write_index_textures);
 
 /* Copy one texture to the host (synchronises the handle's stream).  texture: index of the field in slam_predict_textures
- * (0 image, 1 vertex, 2 normal, 3 time, 4 fill_image, 5 fill_vertex, 6 fill_normal); host_out: width x height texels. */
+ * (0 image, 1 vertex, 2 normal, 3 time, 4 fill_image, 5 fill_vertex, 6 fill_normal, 7 old_image, 8 old_vertex, 9 old_normal,
+ * 10 old_time); host_out: width x height texels. */
 int slam_predict_download(slam_predict_t h, int texture, void * host_out);
 
 /* ---- parity taps / timing aids --------------------------------------------------------------------------------- */

@@ -421,6 +421,10 @@ struct slam_predict
     uchar4 * image = nullptr, * fill_image = nullptr;
     float4 * vertex = nullptr, * normal = nullptr, * fill_vertex = nullptr, * fill_normal = nullptr;
     unsigned short * time = nullptr;
+    // IndexMap's oldFrameBuffer attachments (INACTIVE prediction)
+    uchar4 * old_image = nullptr;
+    float4 * old_vertex = nullptr, * old_normal = nullptr;
+    unsigned short * old_time = nullptr;
     bool timed = false;
 };
 
@@ -457,13 +461,19 @@ static int predict_setup(slam_predict * h, const slam_predict_params * params)
     SLAM_CUDA_TRY(cudaMalloc(&h->fill_vertex, n * 16));
     SLAM_CUDA_TRY(cudaMalloc(&h->fill_normal, n * 16));
     SLAM_CUDA_TRY(cudaMalloc(&h->time, n * 2));
+    SLAM_CUDA_TRY(cudaMalloc(&h->old_image, n * 4));
+    SLAM_CUDA_TRY(cudaMalloc(&h->old_vertex, n * 16));
+    SLAM_CUDA_TRY(cudaMalloc(&h->old_normal, n * 16));
+    SLAM_CUDA_TRY(cudaMalloc(&h->old_time, n * 2));
     const int nb = div_up((int)n, 256);
     k_ray_table<<<nb, 256, 0, h->stream>>>(h->cam, h->rays);
     k_zclear<<<nb, 256, 0, h->stream>>>(h->zbuf, (int)n);
     SLAM_CUDA_TRY(cudaMemsetAsync(h->frag_counter, 0, 8, h->stream));
-    for(void * b : {(void *)h->image, (void *)h->fill_image}) SLAM_CUDA_TRY(cudaMemsetAsync(b, 0, n * 4, h->stream));
-    for(void * b : {(void *)h->vertex, (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal}) SLAM_CUDA_TRY(cudaMemsetAsync(b, 0, n * 16, h->stream));
+    for(void * b : {(void *)h->image, (void *)h->fill_image, (void *)h->old_image}) SLAM_CUDA_TRY(cudaMemsetAsync(b, 0, n * 4, h->stream));
+    for(void * b : {(void *)h->vertex, (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal, (void *)h->old_vertex, (void *)h->old_normal})
+        SLAM_CUDA_TRY(cudaMemsetAsync(b, 0, n * 16, h->stream));
     SLAM_CUDA_TRY(cudaMemsetAsync(h->time, 0, n * 2, h->stream));
+    SLAM_CUDA_TRY(cudaMemsetAsync(h->old_time, 0, n * 2, h->stream));
     SLAM_CUDA_TRY(cudaMemsetAsync(h->winners, 0xFF, n * 8, h->stream));
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
     SLAM_CUDA_TRY(cudaGetLastError());
@@ -503,7 +513,8 @@ extern "C" int slam_predict_destroy(slam_predict_t h)
     cudaSetDevice(h->p.device);
     if(h->stream) cudaStreamSynchronize(h->stream);
     for(void * b : {(void *)h->rays, (void *)h->zbuf, (void *)h->winners, (void *)h->frag_counter, (void *)h->image, (void *)h->fill_image, (void *)h->vertex,
-                    (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal, (void *)h->time})
+                    (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal, (void *)h->time, (void *)h->old_image, (void *)h->old_vertex,
+                    (void *)h->old_normal, (void *)h->old_time})
         cudaFree(b);
     for(auto & e : h->ev)
         if(e) cudaEventDestroy(e);
@@ -523,6 +534,10 @@ extern "C" int slam_predict_get_textures(slam_predict_t h, slam_predict_textures
     out->fill_image = reinterpret_cast<const uint8_t *>(h->fill_image);
     out->fill_vertex = reinterpret_cast<const float *>(h->fill_vertex);
     out->fill_normal = reinterpret_cast<const float *>(h->fill_normal);
+    out->old_image = reinterpret_cast<const uint8_t *>(h->old_image);
+    out->old_vertex = reinterpret_cast<const float *>(h->old_vertex);
+    out->old_normal = reinterpret_cast<const float *>(h->old_normal);
+    out->old_time = h->old_time;
     return SLAM_OK;
 }
 
@@ -538,7 +553,7 @@ static void set_call(slam_predict * h, const float * pose16, float depth_cutoff,
     h->have_call = true;
 }
 
-static int run_predict(slam_predict * h, const float * d_surfels, int count, const uint16_t * d_raw_depth, const uint8_t * d_raw_rgba, int mode)
+static int run_predict(slam_predict * h, const float * d_surfels, int count, const uint16_t * d_raw_depth, const uint8_t * d_raw_rgba, int mode, bool inactive = false)
 {
     SLAM_CUDA_TRY(cudaSetDevice(h->p.device));
     const int n = h->cam.W * h->cam.H;
@@ -553,6 +568,7 @@ static int run_predict(slam_predict * h, const float * d_surfels, int count, con
     }
     SLAM_CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
     ResolveOut o{h->image, h->vertex, h->normal, h->time, h->fill_image, h->fill_vertex, h->fill_normal, h->winners};
+    if(inactive) o.image = h->old_image, o.vertex = h->old_vertex, o.normal = h->old_normal, o.time = h->old_time;
     k_resolve<<<div_up(n, 256), 256, 0, h->stream>>>(surfels, h->cam, h->call, h->zbuf, h->rays, d_raw_depth, reinterpret_cast<const uchar4 *>(d_raw_rgba), o, mode);
     SLAM_CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     SLAM_CUDA_TRY(cudaGetLastError());
@@ -567,6 +583,16 @@ extern "C" int slam_predict_combined(slam_predict_t h, const float * d_surfels, 
     SLAM_ARG_CHECK(pose16 && count >= 0 && (d_surfels || count == 0) && depth_cutoff > 0.f);
     set_call(h, pose16, depth_cutoff, conf_threshold, time, max_time, time_delta);
     return run_predict(h, d_surfels, count, nullptr, nullptr, 1);
+}
+
+extern "C" int slam_predict_combined_type(slam_predict_t h, const float * d_surfels, int count, const float * pose16, float depth_cutoff, float conf_threshold,
+                                          int time, int max_time, int time_delta, int prediction_type)
+{
+    if(int e = predict_check(h)) return e;
+    SLAM_ARG_CHECK(pose16 && count >= 0 && (d_surfels || count == 0) && depth_cutoff > 0.f);
+    SLAM_ARG_CHECK(prediction_type == SLAM_PREDICT_ACTIVE || prediction_type == SLAM_PREDICT_INACTIVE);   // the reference asserts
+    set_call(h, pose16, depth_cutoff, conf_threshold, time, max_time, time_delta);
+    return run_predict(h, d_surfels, count, nullptr, nullptr, 1, prediction_type == SLAM_PREDICT_INACTIVE);
 }
 
 extern "C" int slam_predict_frame(slam_predict_t h, const float * d_surfels, int count, const float * pose16, float depth_cutoff, float conf_threshold,
@@ -614,11 +640,11 @@ extern "C" int slam_predict_fill_image(slam_predict_t h, const uint8_t * d_exist
 extern "C" int slam_predict_download(slam_predict_t h, int texture, void * host_out)
 {
     if(int e = predict_check(h)) return e;
-    SLAM_ARG_CHECK(host_out && texture >= 0 && texture <= 6);
+    SLAM_ARG_CHECK(host_out && texture >= 0 && texture <= 10);
     SLAM_CUDA_TRY(cudaSetDevice(h->p.device));
     const size_t n = (size_t)h->cam.W * h->cam.H;
-    const void * src[7] = {h->image, h->vertex, h->normal, h->time, h->fill_image, h->fill_vertex, h->fill_normal};
-    const size_t texel[7] = {4, 16, 16, 2, 4, 16, 16};
+    const void * src[11] = {h->image, h->vertex, h->normal, h->time, h->fill_image, h->fill_vertex, h->fill_normal, h->old_image, h->old_vertex, h->old_normal, h->old_time};
+    const size_t texel[11] = {4, 16, 16, 2, 4, 16, 16, 4, 16, 16, 2};
     SLAM_CUDA_TRY(cudaMemcpyAsync(host_out, src[texture], n * texel[texture], cudaMemcpyDeviceToHost, h->stream));
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return SLAM_OK;

@@ -26,11 +26,13 @@ class PredictParams(C.Structure):
 
 class Textures(C.Structure):
     _fields_ = [("image", C.c_void_p), ("vertex", C.c_void_p), ("normal", C.c_void_p), ("time", C.c_void_p), ("fill_image", C.c_void_p),
-                ("fill_vertex", C.c_void_p), ("fill_normal", C.c_void_p)]
+                ("fill_vertex", C.c_void_p), ("fill_normal", C.c_void_p), ("old_image", C.c_void_p), ("old_vertex", C.c_void_p), ("old_normal", C.c_void_p),
+                ("old_time", C.c_void_p)]
 
 
 _TEX = {"image": (0, np.uint8, 4), "vertex": (1, np.float32, 4), "normal": (2, np.float32, 4), "time": (3, np.uint16, 1),
-        "fill_image": (4, np.uint8, 4), "fill_vertex": (5, np.float32, 4), "fill_normal": (6, np.float32, 4)}
+        "fill_image": (4, np.uint8, 4), "fill_vertex": (5, np.float32, 4), "fill_normal": (6, np.float32, 4), "old_image": (7, np.uint8, 4),
+        "old_vertex": (8, np.float32, 4), "old_normal": (9, np.float32, 4), "old_time": (10, np.uint16, 1)}
 
 _bound = False
 
@@ -44,6 +46,7 @@ def _bind(lib):
     lib.slam_predict_destroy.argtypes = [vp]
     lib.slam_predict_get_textures.argtypes = [vp, C.POINTER(Textures)]
     lib.slam_predict_combined.argtypes = [vp, vp, i, fp, f, f, i, i, i]
+    lib.slam_predict_combined_type.argtypes = [vp, vp, i, fp, f, f, i, i, i, i]
     lib.slam_predict_fill_vertex.argtypes = [vp, vp, vp, i]
     lib.slam_predict_fill_normal.argtypes = [vp, vp, vp, i]
     lib.slam_predict_fill_image.argtypes = [vp, vp, vp, i]
@@ -138,12 +141,10 @@ class IndexMap:
 
     def combinedPredict(self, pose, model, count, depthCutoff, confThreshold, time, maxTime, timeDelta, predictionType=0):
         """model = device pointer of the surfel buffer (count x 12 floats), the reference's (vbo, count) pair."""
-        if predictionType != IndexMap.ACTIVE:
-            raise OdometryError("only IndexMap::ACTIVE is implemented (the tracker's input); INACTIVE feeds the loop-closure path")
         o = self._o
         P = _pose(pose)
-        _check(o.lib, o.lib.slam_predict_combined(o._h, _addr(model), int(count), _fptr(P), float(depthCutoff), float(confThreshold), int(time), int(maxTime),
-                                                   int(timeDelta)))
+        _check(o.lib, o.lib.slam_predict_combined_type(o._h, _addr(model), int(count), _fptr(P), float(depthCutoff), float(confThreshold), int(time),
+                                                        int(maxTime), int(timeDelta), int(predictionType)))
 
     def imageTex(self):
         return self._o.textures.image
@@ -156,6 +157,18 @@ class IndexMap:
 
     def timeTex(self):
         return self._o.textures.time
+
+    def oldImageTex(self):
+        return self._o.textures.old_image
+
+    def oldVertexTex(self):
+        return self._o.textures.old_vertex
+
+    def oldNormalTex(self):
+        return self._o.textures.old_normal
+
+    def oldTimeTex(self):
+        return self._o.textures.old_time
 
 
 class FillIn:

@@ -251,6 +251,15 @@ def test_combined_predict_is_bit_exact(built, size):
         both = (ref2["winner"] >= 0) & (win >= 0)
         assert both.any() and np.quantile(np.abs(ref2["vertex"][..., 2] - ref["vertex"][..., 2])[both], 0.999) < 1e-4     # disc edges flip at occlusion boundaries
     assert (win >= 0).mean() > 0.5
+    # IndexMap::INACTIVE, as the loop-closure path calls it (time 0, maxTime = tick - timeDelta): only surfels last seen before maxTime, rendered
+    # into the old* textures; the ACTIVE textures keep the previous prediction
+    active = {k: mp.download(k) for k in ("image", "vertex", "normal", "time")}
+    mp.indexMap.combinedPredict(poses[0], d_model, len(model), MODEL_CUTOFF, 10.0, 0, 2, 200, mp.indexMap.INACTIVE)
+    old = po.combined_predict(model, poses[0], intr, MODEL_CUTOFF, 10.0, 0, 2, 200, tinv=mp.tInv())
+    assert 0.2 < (old["winner"] >= 0).mean() and set(np.unique(model[old["winner"][old["winner"] >= 0], 7])) == {1.0}
+    for k in ("image", "vertex", "normal", "time"):
+        assert np.array_equal(_bits(mp.download("old_" + k)), _bits(old[k])), "old_" + k
+        assert np.array_equal(_bits(mp.download(k)), _bits(active[k])), k
     # repeated call: identical (the resolve launch re-arms the z-buffer); empty model: cleared textures
     mp.indexMap.combinedPredict(poses[0], d_model, len(model), 2.0, 10.0, 10, 10, 200)
     _assert_textures_equal(mp, ref)
@@ -382,3 +391,47 @@ def test_closed_loop_predict_then_track(built):
     travelled = np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1).sum()
     print(dict(ate_mm=ate * 1e3, final_drift_mm=drift * 1e3, travelled_m=travelled))
     assert travelled > 0.3 and ate < 5e-3 and drift < 1e-2, (ate, drift, travelled)
+
+
+@pytest.mark.gpu
+def test_model_to_model_tracking_on_active_and_inactive_predictions(built):
+    """The local-loop-closure caller of the tracker (apps/elastic_fusion_file.cpp:448-479): the ACTIVE prediction (recent surfels) is tracked
+    against the INACTIVE one (old surfels).  The recent part of the map is a copy of the old part displaced by a small rigid drift d; with the old
+    part as the model at pose P and the recent part as the current frame the tracker must return d^-1 P."""
+    from slam_b200 import RGBDOdometry
+    from slam_b200.predict import ModelPredictor
+    scene, intr = make_scene(640, 480)
+    poses = scene.trajectory(1000)
+    P = poses[300].astype(np.float64)
+    old = surfels_from_frame(scene, intr, poses[300], time=1, conf=25.0)
+    ang = np.deg2rad(0.3)
+    d = np.eye(4)
+    d[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    d[:3, 3] = [0.008, -0.004, 0.006]
+    new = old.copy()
+    new[:, 0:3] = old[:, 0:3].astype(np.float64) @ d[:3, :3].T + d[:3, 3]
+    new[:, 8:11] = old[:, 8:11].astype(np.float64) @ d[:3, :3].T
+    new[:, 6] = new[:, 7] = 300
+    model = np.concatenate([old, new]).astype(np.float32)
+    d_model = _upload(model)
+    tick, time_delta = 300, 200
+    mp = ModelPredictor(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    im = mp.indexMap
+    im.combinedPredict(P, d_model, len(model), MODEL_CUTOFF, 10.0, tick, tick, time_delta, im.ACTIVE)
+    _, win_active = mp.winners()
+    im.combinedPredict(P, d_model, len(model), MODEL_CUTOFF, 10.0, 0, tick - time_delta, time_delta, im.INACTIVE)
+    _, win_old = mp.winners()
+    assert (win_active[win_active >= 0] >= len(old)).all() and (win_old[win_old >= 0] < len(old)).all()
+    assert (win_active >= 0).mean() > 0.8 and (win_old >= 0).mean() > 0.8
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    # WARNING initICP* must be called before initRGB*   (apps/elastic_fusion_file.cpp:459-466)
+    odo.initICPModel(im.oldVertexTex(), im.oldNormalTex(), MODEL_CUTOFF, P.astype(np.float32))
+    odo.initRGBModel(im.oldImageTex())
+    odo.initICP(im.vertexTex(), MODEL_CUTOFF, im.normalTex())
+    odo.initRGB(im.imageTex())
+    t, R = odo.getIncrementalTransformation(P[:3, 3].astype(np.float32), P[:3, :3].astype(np.float32), False, 10.0, True, False, False)
+    want = np.linalg.inv(d) @ P
+    err_t, err_R = np.abs(t - want[:3, 3]).max(), np.abs(R - want[:3, :3]).max()
+    moved = np.abs(want[:3, 3] - P[:3, 3]).max()
+    print(dict(err_t_mm=err_t * 1e3, err_R=err_R, moved_mm=moved * 1e3))
+    assert moved > 5e-3 and err_t < 1.5e-3 and err_R < 1e-3, (err_t, err_R, moved)
