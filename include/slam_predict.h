@@ -43,7 +43,8 @@ typedef struct slam_predict_params
     float cx, cy, fx, fy;       /* CameraModel */
     float max_point_size;       /* upper end of GL_POINT_SIZE_RANGE; 0 => 2047 */
     int device;
-    void * stream;              /* cudaStream_t; NULL => the library creates one */
+    void * stream;              /* cudaStream_t; NULL => the library creates one.  A supplied stream stays the caller's: it must
+                                   outlive the handle's last launch; slam_predict_destroy neither synchronises nor destroys it */
 } slam_predict_params;
 
 /* Device pointers of the handle's textures (dense row-major, width x height texels). */

@@ -511,7 +511,9 @@ extern "C" int slam_predict_destroy(slam_predict_t h)
 {
     if(!h) return SLAM_OK;
     cudaSetDevice(h->p.device);
-    if(h->stream) cudaStreamSynchronize(h->stream);
+    // a caller-supplied stream may already be gone (its owner was destroyed first): only our own stream is synchronised here,
+    // cudaFree below waits for outstanding work on the buffers either way
+    if(h->own_stream && h->stream) cudaStreamSynchronize(h->stream);
     for(void * b : {(void *)h->rays, (void *)h->zbuf, (void *)h->winners, (void *)h->frag_counter, (void *)h->image, (void *)h->fill_image, (void *)h->vertex,
                     (void *)h->normal, (void *)h->fill_vertex, (void *)h->fill_normal, (void *)h->time, (void *)h->old_image, (void *)h->old_vertex,
                     (void *)h->old_normal, (void *)h->old_time})

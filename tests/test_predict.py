@@ -390,6 +390,8 @@ def test_closed_loop_predict_then_track(built):
     drift = np.abs(est[-1, :3, 3] - gt[-1, :3, 3]).max()
     travelled = np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1).sum()
     print(dict(ate_mm=ate * 1e3, final_drift_mm=drift * 1e3, travelled_m=travelled))
+    mp.close()          # before the tracker whose stream it borrows
+    odo.close()
     assert travelled > 0.3 and ate < 5e-3 and drift < 1e-2, (ate, drift, travelled)
 
 
