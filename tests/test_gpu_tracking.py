@@ -711,3 +711,33 @@ def test_properties_identity_and_rigid_equivariance(setup):
     assert abs(o1.stats().lastICPCount - o2.stats().lastICPCount) <= 2e-3 * o1.stats().lastICPCount
     o1.close()
     o2.close()
+
+
+def test_jump_guard_returns_the_prior_pose(setup):
+    """RGBDOdometryef.cpp:579-583: when the photometric term is active and the solved translation is more than 0.3 m away from
+    the prior, the prior pose is returned unchanged; ICP-only mode (icpWeight >= 100) has no such guard.  A frame rendered 0.36 m
+    behind its model view, with a distance threshold wide enough for ICP to follow, exercises both branches on both implementations."""
+    i = setup["intr"]
+    scene, poses = setup["scene"], setup["poses"]
+    A = poses[400].copy()
+    B = A.copy()
+    B[:3, 3] = A[:3, 3] - 0.36 * A[:3, 2]          # the camera steps back along its optical axis
+    depth, rgba = scene.render_frame(B)
+    mv, mn, mrgba = scene.render_model(A)
+    fr = dict(depth=depth, rgba=rgba, mv=mv, mn=mn, mrgba=mrgba, model_pose=A.copy(), gt_pose=B.copy())
+    d = to_device(fr)
+    setup["torch"].cuda.synchronize()
+    results = {}
+    for name, kw in (("icp+rgb", dict(icpWeight=10.0)), ("icp_only", dict(icpWeight=100.0))):
+        for impl in ("mine", "ref"):
+            odo = (setup["Odo"] if impl == "mine" else setup["Ref"])(i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], distThresh=0.6)
+            results[name, impl] = run_frame(odo, d, so3=False, first_rgb=d["mrgba"], **kw)
+            odo.close()
+    t_free, R_free = results["icp_only", "mine"]
+    moved = np.linalg.norm(t_free - A[:3, 3])
+    assert moved > 0.3, f"ICP did not follow the 0.36 m step (moved {moved:.3f} m): the guard is not exercised"
+    assert np.abs(t_free - results["icp_only", "ref"][0]).max() < 1e-4 and np.abs(R_free - results["icp_only", "ref"][1]).max() < 1e-4
+    t_ref, R_ref = results["icp+rgb", "ref"]
+    t_mine, R_mine = results["icp+rgb", "mine"]
+    assert np.array_equal(t_ref, A[:3, 3]) and np.array_equal(R_ref, A[:3, :3]), f"reference: the guard was not triggered (moved {np.linalg.norm(t_ref - A[:3, 3]):.3f} m)"
+    assert np.array_equal(t_mine, A[:3, 3]) and np.array_equal(R_mine, A[:3, :3]), f"the guard did not restore the prior pose (moved {np.linalg.norm(t_mine - A[:3, 3]):.3f} m)"
