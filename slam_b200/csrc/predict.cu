@@ -426,6 +426,7 @@ struct slam_predict
     float4 * old_vertex = nullptr, * old_normal = nullptr;
     unsigned short * old_time = nullptr;
     bool timed = false;
+    bool zdirty = false;   // a call failed between the splat and the resolve launch: the z-buffer may hold keys of that call
 };
 
 static int predict_check(slam_predict_t h)
@@ -484,6 +485,7 @@ extern "C" int slam_predict_create(const slam_predict_params * params, slam_pred
 {
     SLAM_ARG_CHECK(params && out);
     SLAM_ARG_CHECK(params->width > 0 && params->height > 0 && params->width <= 8192 && params->height <= 8192);
+    SLAM_ARG_CHECK((size_t)params->width * params->height <= ((size_t)1 << 24));   // a warp's flattened fragment list (32 sprites) is indexed with an int
     SLAM_ARG_CHECK(params->fx != 0.f && params->fy != 0.f);
     int ndev = 0;
     if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -561,6 +563,8 @@ static int run_predict(slam_predict * h, const float * d_surfels, int count, con
     const int n = h->cam.W * h->cam.H;
     const float4 * surfels = reinterpret_cast<const float4 *>(d_surfels);
     SLAM_CUDA_TRY(cudaMemsetAsync(h->frag_counter, 0, 8, h->stream));
+    if(h->zdirty) k_zclear<<<div_up(n, 256), 256, 0, h->stream>>>(h->zbuf, n);
+    h->zdirty = true;   // until the resolve launch below has re-armed the buffer
     SLAM_CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     if(count > 0)
     {
@@ -574,6 +578,7 @@ static int run_predict(slam_predict * h, const float * d_surfels, int count, con
     k_resolve<<<div_up(n, 256), 256, 0, h->stream>>>(surfels, h->cam, h->call, h->zbuf, h->rays, d_raw_depth, reinterpret_cast<const uchar4 *>(d_raw_rgba), o, mode);
     SLAM_CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     SLAM_CUDA_TRY(cudaGetLastError());
+    h->zdirty = false;
     h->timed = true;
     return SLAM_OK;
 }

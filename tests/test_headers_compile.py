@@ -28,24 +28,24 @@ CPP_SOURCE = r"""
 #include <cstdio>
 #include <cuda_runtime_api.h>
 #include "RGBDOdometryef.hpp"
-#include "slam_predict.h"
+#include "ModelPrediction.hpp"
 int main()
 {
     try
     {
         // the reference's constructor arguments (RGBDOdometryef.h:32-36)
-        RGBDOdometryef odom(64, 48, 31.5f, 23.5f, 48.f, -48.f);
+        RGBDOdometryef odom(128, 96, 63.5f, 47.5f, 96.f, -96.f);
         unsigned short * depth = nullptr;
         unsigned char * rgba = nullptr;
         float * verts = nullptr, * norms = nullptr;
-        cudaMalloc((void **)&depth, 64 * 48 * 2);
-        cudaMalloc((void **)&rgba, 64 * 48 * 4);
-        cudaMalloc((void **)&verts, 64 * 48 * 16);
-        cudaMalloc((void **)&norms, 64 * 48 * 16);
-        cudaMemset(depth, 0, 64 * 48 * 2);
-        cudaMemset(rgba, 0, 64 * 48 * 4);
-        cudaMemset(verts, 0, 64 * 48 * 16);
-        cudaMemset(norms, 0, 64 * 48 * 16);
+        cudaMalloc((void **)&depth, 128 * 96 * 2);
+        cudaMalloc((void **)&rgba, 128 * 96 * 4);
+        cudaMalloc((void **)&verts, 128 * 96 * 16);
+        cudaMalloc((void **)&norms, 128 * 96 * 16);
+        cudaMemset(depth, 0, 128 * 96 * 2);
+        cudaMemset(rgba, 0, 128 * 96 * 4);
+        cudaMemset(verts, 0, 128 * 96 * 16);
+        cudaMemset(norms, 0, 128 * 96 * 16);
         const float pose[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
         odom.initFirstRGB(rgba);
         odom.initICPModel(verts, norms, 20.f, pose);
@@ -56,6 +56,21 @@ int main()
         odom.getIncrementalTransformation(trans, rot, false, 10.f, true, false, true);
         // nothing to align: the pose must come back unchanged
         std::printf("tracked %g %g %g count %g\n", trans[0], trans[1], trans[2], odom.lastICPCount);
+        // the producer and the relocaliser with the reference's class and method names: an empty map predicts nothing, the fill-in
+        // passes then take everything from the (empty) raw frame, and a relocaliser without key frames finds nothing
+        slam_b200::IndexMap indexMap(128, 96, 63.5f, 47.5f, 96.f, -96.f);
+        slam_b200::FillIn fillIn(indexMap);
+        indexMap.combinedPredict(pose, std::make_pair((const float *)nullptr, 0), 20.f, 10.f, 1, 1, 200, slam_b200::IndexMap::ACTIVE);
+        fillIn.vertex(indexMap.vertexTex(), depth, false);
+        fillIn.normal(indexMap.normalTex(), depth, false);
+        fillIn.image(indexMap.imageTex(), rgba, false);
+        odom.initICPModel(fillIn.vertexTexture(), fillIn.normalTexture(), 20.f, pose);
+        slam_b200::Ferns ferns(500, 3000, 115.f, 63.5f, 47.5f, 96.f, -96.f, 128, 96, 7u);
+        std::vector<slam_b200::Ferns::SurfaceConstraint> constraints;
+        float est[16];
+        ferns.findFrame(constraints, pose, fillIn.vertexTexture(), fillIn.normalTexture(), fillIn.imageTexture(), 1000, true, est);
+        std::printf("frames %d closest %d constraints %d\n", ferns.numFrames(), ferns.lastClosest, (int)constraints.size());
+        if(ferns.numFrames() != 0 || ferns.lastClosest != -1 || !constraints.empty()) return 4;
         return (std::fabs(trans[0]) < 1e-6f && std::fabs(rot[0] - 1.f) < 1e-6f) ? 0 : 3;
     }
     catch(const std::exception & e)
