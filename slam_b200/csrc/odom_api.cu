@@ -9,6 +9,7 @@
 //   * host-stepped (params.host_loop = 1): the reference's control flow, one reduction
 //     launch + one sync per step, kept for step-by-step parity checks against the reference replay.
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <mutex>
 #include <cstring>
@@ -1283,6 +1284,19 @@ extern "C" int slam_odom_tap(slam_odom_t h, int tap, int level, int seq, void * 
 }
 
 // ------------------------------------------------------------------ per-frame front ends
+// SLAM_ODOM_DEBUG_TIMING=1: host-side split of the per-frame call (enqueue of the preparation launches / of the persistent kernel / wait),
+// printed every 256 frames -- a development aid for the launch-bound part of a frame.
+struct FrameHostTiming
+{
+    double prep = 0, gn = 0, wait = 0;
+    long long n = 0;
+};
+static thread_local FrameHostTiming g_frame_timing;
+static inline double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, const uchar4 * rgba, const float4 * mv, const float4 * mn, const uchar4 * mrgba,
                                   const float * poses16, float depth_cutoff, float model_cutoff, float * trans, float * rot, int rgb_only,
                                   float icp_weight, int pyramid, int fast_odom, int so3, bool defer_wait = false)
@@ -1292,6 +1306,8 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
     {
         // All five inputs are known up front: the current-frame depth branch (pyramid, vertex / normal maps) runs on a
         // second stream next to the model / RGB branch, and the "last" and "next" RGB-D pyramids are built together.
+        static const bool debug_timing = getenv("SLAM_ODOM_DEBUG_TIMING") != nullptr;
+        const double t_in = debug_timing ? now_us() : 0.0;
         if(int rc = set_device(h)) return rc;
         if(h->pending_async)
             if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
@@ -1354,7 +1370,8 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
                 h->launches++;
             }
         }
-        // the depth branch is enqueued after the (longer) model / RGB branch so that the critical path starts first; it only waits for fork_ev
+        // the depth branch is enqueued after the model / RGB branch (it only waits for fork_ev); alternating the two chains' launches
+        // was measured and makes no difference: the six preparation kernels (~45 us of device time) serialise on the GPU either way
         for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
         {
             const LevelGeom & g = h->geom[l];
@@ -1367,6 +1384,23 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         h->have_depth_tmp = true;
         SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         if(defer_wait) return slam_odom_get_incremental_transformation_async(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+        if(debug_timing)
+        {
+            const double t_prep = now_us();
+            int rc2 = slam_odom_get_incremental_transformation_async(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
+            const double t_gn = now_us();
+            if(rc2 == SLAM_OK) rc2 = finish_device_loop(h, trans, rot);
+            const double t_done = now_us();
+            FrameHostTiming & ft = g_frame_timing;
+            ft.prep += t_prep - t_in, ft.gn += t_gn - t_prep, ft.wait += t_done - t_gn;
+            if(++ft.n % 256 == 0)
+            {
+                fprintf(stderr, "slam_odom frame host timing: enqueue prep %.1f us, enqueue persistent kernel %.1f us, wait %.1f us (mean of 256)\n", ft.prep / 256,
+                        ft.gn / 256, ft.wait / 256);
+                ft.prep = ft.gn = ft.wait = 0;
+            }
+            return rc2;
+        }
         return slam_odom_get_incremental_transformation(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
     }
     if(int rc = slam_odom_init_icp_model(h, (const float *)mv, (const float *)mn, model_cutoff, poses16)) return rc;

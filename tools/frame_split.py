@@ -46,3 +46,16 @@ for i in range(n):
     odo.initICP(frames[i % NF]["depth"], DEPTH_CUTOFF)
 torch.cuda.synchronize()
 print(f"one async prep entry point (3 launches, python + C + launches, no wait): {(time.perf_counter() - t0) / n * 1e6:.1f} us")
+# the solve alone on prepared buffers: wall - kernel = launch latency of the cooperative kernel + completion flag + python
+odo.set_profiling(True)
+d0 = frames[0]
+tr, ro = d0["model_pose"][:3, 3].copy(), d0["model_pose"][:3, :3].copy()
+for i in range(20):
+    odo.getIncrementalTransformation(tr.copy(), ro.copy(), False, 10.0, True, False, False)
+odo.get_profile(reset=True)
+t0 = time.perf_counter()
+for i in range(n):
+    odo.getIncrementalTransformation(tr.copy(), ro.copy(), False, 10.0, True, False, False)
+w = (time.perf_counter() - t0) / n * 1e6
+ms, nl = odo.get_profile(reset=True)
+print(f"solve only (no so3): wall {w:.1f} us per call, kernel {ms / nl * 1e3:.1f} us -> {w - ms / nl * 1e3:.1f} us of launch + flag + python")
