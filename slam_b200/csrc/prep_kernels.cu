@@ -52,16 +52,32 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
         return static_cast<unsigned short>(static_cast<int>(sum / wall));
     }
 
-    for(int yi = y_mi; yi < y_ma; ++yi)
-        for(int xi = x_mi; xi < x_ma; ++xi)
-        {
-            const int val = src[(2 * y + yi) * scols + 2 * x + xi];
-            if(abs(val - center) < 3 * sigma_color)
+    // border: the clipped window with every load issued first (the sums are exact, see above, so the order is free); the border
+    // threads used to walk their taps one dependent round trip at a time and set the duration of the whole launch
+    {
+        (void)weights;
+        int val[5][5];
+        bool in[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
             {
-                sum += val * weights[abs(xi)] * weights[abs(yi)];
-                wall += weights[abs(xi)] * weights[abs(yi)];
+                const int yi = r - 2, xi = c - 2;
+                in[r][c] = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
+                val[r][c] = in[r][c] ? (int)src[(2 * y + yi) * scols + 2 * x + xi] : 0;
             }
-        }
+        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};   // weights[abs(xi)], xi = c - 2
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(in[r][c] && abs(val[r][c] - center) < 3 * sigma_color)
+                {
+                    sum += val[r][c] * w5[c] * w5[r];
+                    wall += w5[c] * w5[r];
+                }
+    }
     return static_cast<unsigned short>(static_cast<int>(sum / wall));
 }
 
@@ -88,6 +104,14 @@ __device__ __forceinline__ bool vertex_from_depth(unsigned short d, int u, int v
 // 5x5 {1,4,6,4,1}^2 pyramid tap loop shared by the float-depth and u8-intensity versions
 // (utils.cu:332-363 and 470-500): window [max(0,2x-2), min(2x+3, cols-1)), weight index
 // (ty-cy-1)*5+(tx-cx-1), integer `count`.
+// the same table as a product of two {1,4,6,4,1} entries picked without a memory lookup (a, b in [0, 4])
+__device__ __forceinline__ float gauss5_weight_rc(int a, int b)
+{
+    const float wa = (a == 0 || a == 4) ? 1.f : (a == 2 ? 6.f : 4.f);
+    const float wb = (b == 0 || b == 4) ? 1.f : (b == 2 ? 6.f : 4.f);
+    return wa * wb;
+}
+
 __device__ __forceinline__ float gauss5_weight(int idx)
 {
     const float k[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
@@ -125,17 +149,28 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
                 }
         return (float)(sum / (float)count);
     }
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
-        {
-            const float s = src[cy * scols + cx];
-            if(!isnan(s))
-            {
-                const float w = gauss5_weight((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum = __fmaf_rn(s, w, sum);
-                count += w;
-            }
-        }
+    // border: the clipped window of the reference's loop (rows [cy, ty), columns [cx0, tx), at most 5 x 5), same taps in the same
+    // order with the same misaligned weights -- but every load is issued before the first is consumed: the border threads
+    // used to walk their taps one dependent L2 round trip at a time and set the duration of the whole launch
+    {
+        const int cx0 = max(0, 2 * x - D / 2);
+        const int nr = ty - cy, nc = tx - cx0;
+        float v[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? src[(cy + r) * scols + (cx0 + c)] : SLAM_QNAN;
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(r < nr && c < nc && !isnan(v[r][c]))
+                {
+                    const float w = gauss5_weight_rc(nr - 1 - r, nc - 1 - c);   // index (ty-cy-1)*5 + (tx-cx-1)
+                    sum = __fmaf_rn(v[r][c], w, sum);
+                    count += (int)w;
+                }
+    }
     return (float)(sum / (float)count);
 }
 
@@ -169,17 +204,26 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
                 }
         return (unsigned char)((float)isum / (float)count);
     }
-    for(; cy < ty; ++cy)
-        for(int cx = max(0, 2 * x - D / 2); cx < tx; ++cx)
-        {
-            const unsigned char s = src[cy * scols + cx];
-            if(s > 0)
-            {
-                const float w = gauss5_weight((ty - cy - 1) * 5 + (tx - cx - 1));
-                sum += s * w;
-                count += w;
-            }
-        }
+    // border: as in the float version, all loads first; the sums are small integers, exact in fp32 in any order
+    {
+        const int cx0 = max(0, 2 * x - D / 2);
+        const int nr = ty - cy, nc = tx - cx0;
+        int v[5][5];
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? (int)src[(cy + r) * scols + (cx0 + c)] : 0;
+#pragma unroll
+        for(int r = 0; r < 5; r++)
+#pragma unroll
+            for(int c = 0; c < 5; c++)
+                if(v[r][c] > 0)
+                {
+                    const float w = gauss5_weight_rc(nr - 1 - r, nc - 1 - c);
+                    sum += (float)v[r][c] * w;
+                    count += (int)w;
+                }
+    }
     return (unsigned char)(sum / (float)count);
 }
 
