@@ -431,22 +431,27 @@ __global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a0)
             a.t = make_float3(__ldg(q + 9), __ldg(q + 10), __ldg(q + 11));
         }
     }
-    // thread -> 4x4 block; consecutive threads walk along x
+    // Four consecutive lanes own one 4x4 pixel block (the unit that folds into one level-2 pixel), one 2x2 quarter each: quarter
+    // q = lane & 3 sits at (2 (q & 1), 2 (q >> 1)) inside the block; consecutive blocks walk along x.  A lane loads and stores its
+    // four level-0 pixels, folds them into its level-1 pixel, and the four level-1 pixels of a block meet through shuffles for the
+    // level-2 pixel (same operands in the same order as one thread per 4x4 block, which this replaces: 4x the threads in flight).
     const int bcols = div_up(a.cols, 4), brows = div_up(a.rows, 4);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if(b >= bcols * brows) return;
-    const int bx = b % bcols, by = b / bcols;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = tid >> 2, q = tid & 3;
+    const bool live = b < bcols * brows;       // lanes past the end stay for the shuffles and touch no memory
+    const int bx = live ? b % bcols : 0, by = live ? b / bcols : 0;
+    const int qx = q & 1, qy = q >> 1;
 
-    float3 v0[4][4], n0[4][4];
+    float3 v0[2][2], n0[2][2];
     const int plane0 = a.rows * a.cols;
 #pragma unroll
-    for(int j = 0; j < 4; j++)
+    for(int j = 0; j < 2; j++)
 #pragma unroll
-        for(int i = 0; i < 4; i++)
+        for(int i = 0; i < 2; i++)
         {
-            const int x = bx * 4 + i, y = by * 4 + j;
+            const int x = bx * 4 + 2 * qx + i, y = by * 4 + 2 * qy + j;
             float3 v = make_float3(SLAM_QNAN, SLAM_QNAN, SLAM_QNAN), n = v;
-            if(x < a.cols && y < a.rows)
+            if(live && x < a.cols && y < a.rows)
             {
                 const float4 vs = __ldg(a.vsrc + y * a.cols + x);
                 const float4 ns = __ldg(a.nsrc + y * a.cols + x);
@@ -481,24 +486,27 @@ __global__ void __launch_bounds__(128) k_model_maps(const ModelMapsArgs a0)
     if(a.levels < 2) return;
 
     const int rows1 = a.rows / 2, cols1 = a.cols / 2, plane1 = rows1 * cols1;
-    float3 v1[2][2], n1[2][2];
-#pragma unroll
-    for(int j = 0; j < 2; j++)
-#pragma unroll
-        for(int i = 0; i < 2; i++)
-        {
-            v1[j][i] = resize4<false>(v0[2 * j][2 * i], v0[2 * j][2 * i + 1], v0[2 * j + 1][2 * i], v0[2 * j + 1][2 * i + 1]);
-            n1[j][i] = resize4<true>(n0[2 * j][2 * i], n0[2 * j][2 * i + 1], n0[2 * j + 1][2 * i], n0[2 * j + 1][2 * i + 1]);
-            const int x = bx * 2 + i, y = by * 2 + j;
-            if(x < cols1 && y < rows1) store_map_pixel(a.vdst[1], a.ndst[1], plane1, y * cols1 + x, v1[j][i], n1[j][i], a.transform, a.R, a.t);
-        }
+    const float3 v1 = resize4<false>(v0[0][0], v0[0][1], v0[1][0], v0[1][1]);
+    const float3 n1 = resize4<true>(n0[0][0], n0[0][1], n0[1][0], n0[1][1]);
+    {
+        const int x = bx * 2 + qx, y = by * 2 + qy;
+        if(live && x < cols1 && y < rows1) store_map_pixel(a.vdst[1], a.ndst[1], plane1, y * cols1 + x, v1, n1, a.transform, a.R, a.t);
+    }
     if(a.levels < 3) return;
 
     const int rows2 = rows1 / 2, cols2 = cols1 / 2, plane2 = rows2 * cols2;
-    if(bx < cols2 && by < rows2)
+    float3 qv[4], qn[4];   // the block's level-1 pixels in the order (0,0) (0,1) (1,0) (1,1) = quarters 0..3
+    const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+    for(int k = 0; k < 4; k++)
     {
-        const float3 v2 = resize4<false>(v1[0][0], v1[0][1], v1[1][0], v1[1][1]);
-        const float3 n2 = resize4<true>(n1[0][0], n1[0][1], n1[1][0], n1[1][1]);
+        qv[k] = make_float3(__shfl_sync(0xffffffffu, v1.x, base + k), __shfl_sync(0xffffffffu, v1.y, base + k), __shfl_sync(0xffffffffu, v1.z, base + k));
+        qn[k] = make_float3(__shfl_sync(0xffffffffu, n1.x, base + k), __shfl_sync(0xffffffffu, n1.y, base + k), __shfl_sync(0xffffffffu, n1.z, base + k));
+    }
+    if(live && q == 0 && bx < cols2 && by < rows2)
+    {
+        const float3 v2 = resize4<false>(qv[0], qv[1], qv[2], qv[3]);
+        const float3 n2 = resize4<true>(qn[0], qn[1], qn[2], qn[3]);
         store_map_pixel(a.vdst[2], a.ndst[2], plane2, by * cols2 + bx, v2, n2, a.transform, a.R, a.t);
         if(a.vcam2) store_map_pixel(a.vcam2, a.ncam2, plane2, by * cols2 + bx, v2, n2, false, a.R, a.t);
     }
@@ -991,7 +999,7 @@ int launch_depth_level(const unsigned short * depth, int rows, int cols, float f
 int launch_model_maps(const ModelMapsArgs & a, cudaStream_t s, int nseq = 1)
 {
     const int nblk = div_up(a.cols, 4) * div_up(a.rows, 4);
-    k_model_maps<<<dim3(div_up(nblk, 128), nseq), 128, 0, s>>>(a);
+    k_model_maps<<<dim3(div_up(nblk * 4, 128), nseq), 128, 0, s>>>(a);   // four lanes per 4x4 block
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
