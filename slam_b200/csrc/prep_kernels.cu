@@ -27,7 +27,6 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
 
     float sum = 0;
     float wall = 0;
-    const float weights[] = {0.375f, 0.25f, 0.0625f};
 
     if(x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3)
     {
@@ -55,7 +54,6 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
     // border: the clipped window with every load issued first (the sums are exact, see above, so the order is free); the border
     // threads used to walk their taps one dependent round trip at a time and set the duration of the whole launch
     {
-        (void)weights;
         int val[5][5];
         bool in[5][5];
 #pragma unroll
@@ -67,7 +65,7 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
                 in[r][c] = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
                 val[r][c] = in[r][c] ? (int)src[(2 * y + yi) * scols + 2 * x + xi] : 0;
             }
-        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};   // weights[abs(xi)], xi = c - 2
+        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};   // the reference's weights[abs(xi)] = {0.375, 0.25, 0.0625}, xi = c - 2
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
@@ -110,12 +108,6 @@ __device__ __forceinline__ float gauss5_weight_rc(int a, int b)
     const float wa = (a == 0 || a == 4) ? 1.f : (a == 2 ? 6.f : 4.f);
     const float wb = (b == 0 || b == 4) ? 1.f : (b == 2 ? 6.f : 4.f);
     return wa * wb;
-}
-
-__device__ __forceinline__ float gauss5_weight(int idx)
-{
-    const float k[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
-    return k[idx];
 }
 
 __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int srows, int scols, int x, int y)

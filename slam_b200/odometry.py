@@ -278,15 +278,27 @@ class RGBDOdometry:
         fr.depth_cutoff, fr.model_depth_cutoff = depth_cutoff, model_depth_cutoff
         return fr
 
-    def _track(self, fn, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
-        # one conversion per argument: np.array(copy) + cached ctypes pointers keep the per-frame host cost of the mirror small
-        t = np.array(trans, dtype=np.float32).reshape(-1)
-        r = np.array(rot, dtype=np.float32).reshape(-1)
-        rc = fn(self._h, C.byref(frame), t.ctypes.data_as(_FP), r.ctypes.data_as(_FP), int(bool(rgbOnly)), float(icpWeight), int(bool(pyramid)),
-                int(bool(fastOdom)), int(bool(so3)))
+    def _io_buffers(self):
+        # per-handle in-out buffers with their ctypes pointers made once: the per-frame host cost of the mirror stays a few microseconds
+        buf = getattr(self, "_io", None)
+        if buf is None:
+            t = np.zeros(3 * self.batch, np.float32)
+            r = np.zeros(9 * self.batch, np.float32)
+            buf = self._io = (t, r, t.ctypes.data_as(_FP), r.ctypes.data_as(_FP))
+        return buf
+
+    def _track(self, fn, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3, next_frame=None):
+        t, r, tp, rp = self._io_buffers()
+        t[:] = np.asarray(trans, dtype=np.float32).reshape(-1)
+        r[:] = np.asarray(rot, dtype=np.float32).reshape(-1)
+        flags = (1 if rgbOnly else 0, float(icpWeight), 1 if pyramid else 0, 1 if fastOdom else 0, 1 if so3 else 0)
+        if next_frame is None:
+            rc = fn(self._h, C.byref(frame), tp, rp, *flags)
+        else:
+            rc = fn(self._h, C.byref(frame), C.byref(next_frame), tp, rp, *flags)
         if rc != 0:
             _check(self.lib, rc)
-        return t.reshape(np.shape(trans)), r.reshape(np.shape(rot))
+        return t.reshape(np.shape(trans)).copy(), r.reshape(np.shape(rot)).copy()
 
     def track_device(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True):
         return self._track(self.lib.slam_odom_track_device, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
@@ -294,11 +306,7 @@ class RGBDOdometry:
     def track_host(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True, next_frame=None):
         if next_frame is None:
             return self._track(self.lib.slam_odom_track_host, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
-        t = np.ascontiguousarray(trans, dtype=np.float32).reshape(-1).copy()
-        r = np.ascontiguousarray(rot, dtype=np.float32).reshape(-1).copy()
-        _check(self.lib, self.lib.slam_odom_track_host_next(self._h, C.byref(frame), C.byref(next_frame), _fptr(t), _fptr(r), int(bool(rgbOnly)), float(icpWeight),
-                                                            int(bool(pyramid)), int(bool(fastOdom)), int(bool(so3))))
-        return t.reshape(np.shape(trans)), r.reshape(np.shape(rot))
+        return self._track(self.lib.slam_odom_track_host_next, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3, next_frame=next_frame)
 
     def prefetch_host(self, frame):
         _check(self.lib, self.lib.slam_odom_prefetch_host(self._h, C.byref(frame)))
