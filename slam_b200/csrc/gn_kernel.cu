@@ -1,226 +1,46 @@
-// Device-resident Gauss-Newton loop of the tracker: ONE persistent, cooperatively
-// launched kernel runs the SO3 pre-alignment and the coarse-to-fine ICP+RGB iterations of
-// RGBDOdometryef::getIncrementalTransformation (src/odom/RGBDOdometryef.cpp:267-595),
-// including the 3x3 / 6x6 solves and the pose updates that the reference does on the host
-// between ~40 kernel launches, ~25 cudaDeviceSynchronize and ~20 cudaMalloc/cudaFree pairs
-// per frame.
+// Device-resident Gauss-Newton loop of the tracker: ONE persistent, cooperatively launched kernel runs the SO3
+// pre-alignment and the coarse-to-fine ICP+RGB iterations of RGBDOdometryef::getIncrementalTransformation
+// (src/odom/RGBDOdometryef.cpp:267-595), including the 3x3 / 6x6 solves and the pose updates that the reference does on
+// the host between ~40 kernel launches, ~25 cudaDeviceSynchronize and ~20 cudaMalloc/cudaFree pairs per frame.
 //
-// Layout of the computation
-//   * the CTAs of the grid are split into groups of G CTAs; a group owns one sequence
-//     (batch == 1: one group of all 148 CTAs; batch > 1: independent groups, so
-//     independent sequences progress concurrently with no inter-group traffic);
-//   * every thread owns a fixed set of pixels per level ("slots": k = gtid + m * gthreads),
-//     so per-pixel state that does not depend on the pose (RGB candidate flag, depth,
-//     intensity, gradients) is loaded ONCE per level into registers, and the photometric
-//     correspondences found in phase A stay in registers for phase B;
-//   * loads are issued for all of a thread's slots before any is consumed (the working set
-//     lives in the 126 MB L2, so what matters is round trips, not bytes);
-//   * a step is "map" (accumulate the 29/11 products in registers) + "publish" (transposed
-//     warp reduction -> shared memory -> one 64-float partial row per CTA in global memory)
-//     + a group barrier (release/acquire counter) + "fold" (every CTA re-reads the G partial
-//     rows in a fixed order, so all CTAs hold bit-identical sums);
-//   * warp 0 of EVERY CTA then solves the normal equations redundantly in fp64
-//     (small_math.hpp): the 6x6 LDL^T on one lane, everything around it (combining the
-//     systems, resultRt update, K R K^-1, K t, current pose) spread over the lanes in
-//     shared-memory stages.  No host round trip, no second launch, no broadcast step;
-//   * partial rows are double-buffered by step parity, which makes one barrier per
-//     reduction sufficient.
+// A frame is a chain of ~30 reductions, each followed by a solve whose result the next map needs: what bounds it is the
+// latency of that chain, not bytes (the 45 MB working set of a 640x480 frame sits in the 126 MB L2).  Layout of the computation:
+//   * the CTAs of the grid are split into groups of G CTAs; a group owns one sequence (batch == 1: one group of all 148
+//     CTAs; batch > 1: independent groups, no inter-group traffic);
+//   * STAGING (once per frame and level): a CTA owns every P-th 32-pixel segment of a level and keeps the pose-independent
+//     operands of its pixels in shared memory for the whole frame -- current vertex + normal for ICP (reduce.cu:282-283), and
+//     for RGB the outcome of the pose-independent half of the association (reduce.cu:780-807: window test, gradient
+//     threshold, finite depth) with its operands.  Pixels that cannot take part are dropped while staging (ballot + prefix
+//     sum -> dense lists), so the iterations never spend a lane on a dead pixel and the per-CTA work is balanced;
+//   * an ICP+RGB iteration is: RGB association (list -> gathers -> count) | post the count | ICP products (list -> gathers
+//     -> 29 sums) | block reduction + post | read the global count (its trip through L2 overlapped the ICP map) -> sigma |
+//     RGB products from the correspondences kept in shared memory | block reduction + post | read all sums | solve;
+//   * INTER-CTA ALL-REDUCE: fixed-point words in L2 that carry their own arrival count (gn_kernel.cuh): one atomic add per word
+//     and CTA, the readers poll the words; no fence, no fold, deterministic sums;
+//   * warp 0 of EVERY CTA then solves the normal equations redundantly (gn_fast_math.cuh), so the next parameters are in
+//     every CTA's shared memory without a broadcast;
+//   * small levels (and the SO3 pre-alignment, whose two 160x120 images are staged in shared memory) run on the first P CTAs
+//     only: fewer arrivals per reduction; the other CTAs just follow the sums.
+// Levels whose lists do not fit shared memory (large images, small groups) stream their operands from L2 per iteration.
 // Per-pixel arithmetic is pixel_ops.cuh, shared with the single-launch operator kernels.
 #include <cfloat>
 #include <cstring>
+#include <cstdlib>
 #include "gn_kernel.cuh"
 #include "gn_scalar.cuh"
+#include "gn_fast_math.cuh"
 
 namespace slam {
 
-constexpr int kIcpChunk = 3;    // ICP gathers in flight per thread (register budget)
+// Unroll factors are kept small on purpose: the per-iteration code of the whole CTA has to stay inside the 32 KB instruction
+// cache (ncu: 18 % of the instruction-cache requests missed and every phase started with an instruction-fetch stall when it did not).
+constexpr int kIcpChunk = 2;      // ICP entries in flight per thread
+constexpr int kRgbChunk = 3;      // RGB entries in flight per thread
+constexpr int kMaxStageSlots = 16;   // 32-pixel segments a warp stages per level at most (resident levels)
+constexpr int kSpinCap = 1 << 21; // polls before a reader gives up (~1 s)
+constexpr double kFracScale = 281474976710656.0;   // 2^48
 
-// ctr points at the 64-bit barrier word of the group; the arrival counter is its high half.
-__device__ __forceinline__ void group_barrier(unsigned long long * ctr, unsigned & target, unsigned G)
-{
-    __syncthreads();
-    if(G > 1 && threadIdx.x == 0)
-    {
-        unsigned * hi = reinterpret_cast<unsigned *>(ctr) + 1;
-        target += G;
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(hi), "r"(1u) : "memory");
-        unsigned v;
-        do
-        {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(hi) : "memory");
-        } while((int)(v - target) < 0);
-    }
-    __syncthreads();
-}
-
-// Barrier + all-reduce of one small unsigned per CTA in the same round trip: thread 0 adds `mine` to the low half of the
-// barrier word (relaxed) before it arrives on the high half (release), and polls the whole word: the value that shows the
-// last arrival also holds every CTA's contribution (a later contribution needs another barrier in between).  The low
-// half is a running sum modulo 2^32; `running` carries the previous total.  Returns the sum over the group in sh_out
-// (thread 0 writes it before the closing __syncthreads()).
-__device__ __forceinline__ void group_barrier_sum(unsigned long long * ctr, unsigned & target, unsigned G, unsigned mine, unsigned & running, int * sh_out)
-{
-    __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        unsigned * lo = reinterpret_cast<unsigned *>(ctr);
-        target += G;
-        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(lo), "r"(mine) : "memory");
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(lo + 1), "r"(1u) : "memory");
-        unsigned long long v;
-        do
-        {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
-        } while((int)((unsigned)(v >> 32) - target) < 0);
-        const unsigned now = (unsigned)v;
-        *sh_out = (int)(now - running);
-        running = now;
-    }
-    __syncthreads();
-}
-
-// Block sum of up to 32 per-thread floats (v[NV..31] must be 0) -> dst[0..31] (global partial row
-// of this CTA).  Transposed warp reduction, then 32 threads add the per-warp rows.
-// The caller must reach a __syncthreads() (e.g. group_barrier) before sh.red is reused.
-// With count_cols, slots 29 / 30 / 31 carry exact small integers as floats (RGB correspondence count, low
-// 12 bits and high bits of the squared-residual sum); they are recombined into the two int32 columns
-// 29 (count) and 30 (sigma) of the partial row.
-// Returns (thread 0, with count_cols) the CTA's contribution to the mid-iteration all-reduce: count | (sigma != 0) << 24.
-__device__ __forceinline__ unsigned cta_publish32(float (&v)[32], GnShared & sh, float * dst, const bool count_cols = false)
-{
-    unsigned word = 0;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const float s = warp_reduce_scatter32(v);
-    sh.red[wid * 32 + lane] = s;
-    __syncthreads();
-    if(threadIdx.x < 32)
-    {
-        float total = 0.f;
-#pragma unroll 16
-        for(int w = 0; w < nw; w++) total += sh.red[w * 32 + threadIdx.x];
-        if(count_cols)
-        {
-            const float hi = __shfl_sync(0xffffffffu, total, 31);
-            if(threadIdx.x == 29) total = __int_as_float((int)total);
-            if(threadIdx.x == 30) total = __int_as_float((int)total + ((int)hi << 12));
-            const unsigned cnt = (unsigned)__float_as_int(__shfl_sync(0xffffffffu, total, 29));
-            const unsigned sig = (unsigned)__float_as_int(__shfl_sync(0xffffffffu, total, 30));
-            word = cnt + (sig != 0u ? (1u << 24) : 0u);
-        }
-        dst[threadIdx.x] = total;
-    }
-    return word;
-}
-
-// Same for two per-thread ints (count, sigma) -> dst[0..1].
-__device__ __forceinline__ void cta_publish_int2(int c0, int c1, GnShared & sh, int * dst)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    c0 = warp_sum(c0);
-    c1 = warp_sum(c1);
-    int * red = reinterpret_cast<int *>(sh.red);
-    if(lane == 0)
-    {
-        red[wid * 2] = c0;
-        red[wid * 2 + 1] = c1;
-    }
-    __syncthreads();
-    if(threadIdx.x < 2)
-    {
-        int t = 0;
-        for(int w = 0; w < nw; w++) t += red[w * 2 + threadIdx.x];
-        dst[threadIdx.x] = t;
-    }
-    __syncthreads();
-}
-
-// Fold the G partial rows (64 columns each) of this group into sh.total, in a fixed order (so
-// every CTA of the group gets bit-identical sums).  All of a thread's loads are issued before the
-// first use: one L2 round trip for the whole fold.  Columns 29 and 30 hold the integer count /
-// sigma of the RGB residual (bit patterns).
-__device__ __forceinline__ void fold_partials(GnShared & sh, const float * rows, int G)
-{
-    constexpr int kVecPerRow = kGnPartialStride / 4;                       // 16 float4 per row
-    constexpr int kMaxPasses = (kGnMaxCtas * kVecPerRow) / kGnThreads;     // 8
-    const int nvec = G * kVecPerRow;
-    const int c4 = threadIdx.x % kVecPerRow;    // which float4 column
-    const int r0 = threadIdx.x / kVecPerRow;    // first row of this thread; stride 32 rows
-    float4 v[kMaxPasses];
-#pragma unroll
-    for(int m = 0; m < kMaxPasses; m++)
-    {
-        const int q = threadIdx.x + m * kGnThreads;
-        v[m] = (q < nvec) ? __ldcg(reinterpret_cast<const float4 *>(rows) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float4 acc = v[0];
-    const bool has_int = (c4 == 7);   // columns 28..31 -> .y = count, .z = sigma
-#pragma unroll
-    for(int m = 1; m < kMaxPasses; m++)
-    {
-        acc.x += v[m].x;
-        acc.w += v[m].w;
-        if(has_int)
-        {
-            acc.y = __int_as_float(__float_as_int(acc.y) + __float_as_int(v[m].y));
-            acc.z = __int_as_float(__float_as_int(acc.z) + __float_as_int(v[m].z));
-        }
-        else
-        {
-            acc.y += v[m].y;
-            acc.z += v[m].z;
-        }
-    }
-    reinterpret_cast<float4 *>(sh.red)[r0 * kVecPerRow + c4] = acc;
-    __syncthreads();
-    if(threadIdx.x < kGnPartialStride)
-    {
-        const bool is_int = (threadIdx.x == 29 || threadIdx.x == 30);
-        float ft = 0.f;
-        int it = 0;
-#pragma unroll 8
-        for(int k = 0; k < kGnThreads / kVecPerRow; k++)
-        {
-            const float x = sh.red[k * kGnPartialStride + threadIdx.x];
-            if(is_int)
-                it += __float_as_int(x);
-            else
-                ft += x;
-        }
-        sh.total[threadIdx.x] = is_int ? __int_as_float(it) : ft;
-    }
-    __syncthreads();
-}
-
-// count / sigma of the whole image right after the phase-A barrier (warp 0 only): all loads in flight at once.
-__device__ __forceinline__ void fold_count_sigma(GnShared & sh, const float * rows, int G)
-{
-    constexpr int kMax = kGnMaxCtas / 32;
-    int c0 = 0, c1 = 0;
-    float a[kMax], b[kMax];
-#pragma unroll
-    for(int j = 0; j < kMax; j++)
-    {
-        const int r = (int)threadIdx.x + 32 * j;
-        a[j] = (r < G) ? __ldcg(rows + r * kGnPartialStride + 29) : 0.f;
-        b[j] = (r < G) ? __ldcg(rows + r * kGnPartialStride + 30) : 0.f;
-    }
-#pragma unroll
-    for(int j = 0; j < kMax; j++)
-    {
-        c0 += __float_as_int(a[j]);
-        c1 += __float_as_int(b[j]);
-    }
-    c0 = warp_sum(c0);
-    c1 = warp_sum(c1);
-    if(threadIdx.x == 0)
-    {
-        sh.total[29] = __int_as_float(c0);
-        sh.total[30] = __int_as_float(c1);
-    }
-}
-
-// The buffers of one pyramid level of one sequence.  Read field by field from the kernel parameter (one sequence:
-// constant-bank loads, no local copy of the block) or from the per-sequence array in global memory.
+// The buffers of one pyramid level of one sequence.
 struct LevelPtrs
 {
     const float * vcurr, * ncurr, * vprev, * nprev, * lastDepth, * nextDepth;
@@ -228,6 +48,107 @@ struct LevelPtrs
     const short * dIdx, * dIdy;
     Corres * corres;
 };
+
+struct GnWork
+{
+    // the running level: buffers and this CTA's lists.  Kept in shared memory and re-read by every phase, so that none of it
+    // occupies registers across the phases of an iteration (the map loops need them all)
+    LevelPtrs P;
+    int lv_n_icp, lv_n_rgb;
+    int n_icp[SLAM_MAX_LEVELS], n_rgb[SLAM_MAX_LEVELS];   // list lengths of this CTA
+    int scan_cnt[2][kMaxStageSlots * kGnWarps];   // staging: survivors per (segment slot, warp), then their list offsets
+    int cnt[2];                    // RGB correspondence count / squared-residual sum of this CTA (shared-memory atomics)
+    unsigned long long mid;        // global correspondence count word
+    long long sigma;               // global squared-residual sum (rgbOnly: read at the mid point)
+    int timeouts;
+    unsigned ph[12];               // cycles per phase (leading CTA, thread 0)
+};
+
+// ------------------------------------------------------------------ fixed-point all-reduce
+__device__ __forceinline__ void red_u64(unsigned long long * p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_relaxed(const unsigned long long * p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long * ring_word(unsigned long long * ring, unsigned step, int w)
+{
+    return ring + ((size_t)(step & (kRingSlots - 1)) * kRingWords + w) * kWordStride;
+}
+// One CTA's fp32 partial sum of column c: integer part and fraction (both exact) go to the two words of the column.
+__device__ __forceinline__ void post_float(unsigned long long * ring, unsigned step, int wbase, int c, float v)
+{
+    const float vi = rintf(v);
+    const float vf = v - vi;
+    const long long qi = __float2ll_rn(vi);
+    const long long qf = __double2ll_rn((double)vf * kFracScale);
+    red_u64(ring_word(ring, step, wbase + 2 * c), ((unsigned long long)qi << 8) + 1ull);
+    red_u64(ring_word(ring, step, wbase + 2 * c + 1), ((unsigned long long)qf << 8) + 1ull);
+}
+__device__ __forceinline__ void post_int(unsigned long long * ring, unsigned step, int w, long long v)
+{
+    red_u64(ring_word(ring, step, w), ((unsigned long long)v << 8) + 1ull);
+}
+// Wait until `want` CTAs have contributed to the word; returns the (signed) sum.
+__device__ __forceinline__ long long poll_word(unsigned long long * ring, unsigned step, int w, unsigned want, GnWork & wk)
+{
+    const unsigned long long * p = ring_word(ring, step, w);
+    unsigned long long v;
+    int spin = 0;
+    do
+    {
+        v = ld_u64_relaxed(p);
+    } while(((unsigned)v & 0xffu) != want && ++spin < kSpinCap);
+    if(spin >= kSpinCap) wk.timeouts = 1;
+    return (long long)v >> 8;
+}
+__device__ __forceinline__ void spin_cycles(int cycles)
+{
+    if(cycles > 0)
+    {
+        const long long t = clock64();
+        while(clock64() - t < cycles) {}
+    }
+}
+
+// Block sum of up to 32 per-thread floats (v[ncols..31] must be 0), posted to the ncols columns starting at word wbase.
+// The caller must reach a __syncthreads() before sh.red is reused.
+__device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, unsigned long long * ring, unsigned step, int wbase, int ncols)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float s = warp_reduce_scatter32(v);
+    sh.red[wid * 32 + lane] = s;
+    __syncthreads();
+    if(wid == 0)
+    {
+        float total = 0.f;
+#pragma unroll
+        for(int w = 0; w < kGnWarps; w++) total += sh.red[w * 32 + lane];
+        if(lane < ncols) post_float(ring, step, wbase, lane, total);
+    }
+}
+
+// Threads 0..127: read the ncols columns at word wbase (two words each) into dst[0..ncols-1] (floats).  t = index of this
+// thread within the reader set of the block of words, t < 2 * ncols active.  Whole warps must call (shuffle inside).
+__device__ __forceinline__ void read_columns(unsigned long long * ring, unsigned step, int wbase, int ncols, int t, unsigned want, float * dst, GnWork & wk)
+{
+    const bool active = t >= 0 && t < 2 * ncols;
+    double d = 0.0;
+    if(active)
+    {
+        const long long v = poll_word(ring, step, wbase + t, want, wk);
+        d = (t & 1) ? (double)v * (1.0 / kFracScale) : (double)v;
+    }
+    const double o = __shfl_xor_sync(0xffffffffu, d, 1);
+    if(active && !(t & 1)) dst[t >> 1] = (float)(d + o);
+}
+
+// Read field by field from the kernel parameter (one sequence: constant-bank loads, no local copy of the block) or from the
+// per-sequence array in global memory.
 #define GN_LEVEL_FIELDS(S) \
     p.vcurr = (S).vcurr[lvl]; p.ncurr = (S).ncurr[lvl]; p.vprev = (S).vprev[lvl]; p.nprev = (S).nprev[lvl]; \
     p.lastDepth = (S).lastDepth[lvl]; p.nextDepth = (S).nextDepth[lvl]; p.lastImage = (S).lastImage[lvl]; \
@@ -247,45 +168,37 @@ __device__ __forceinline__ LevelPtrs level_ptrs(const bool one, const GnSeqIn & 
     return p;
 }
 
-// Pose-independent half of the photometric association (reduce.cu:780-807) for NS slots of a thread at once, with every
-// load of every slot issued before the first use (ONE round trip to L2 per batch instead of a chain of early-exit
-// branches per pixel): the clipped 4x4 all-nonzero window of nextImage, the gradient pair (from dIdx/dIdy, or derived
-// from the same window with the arithmetic of utils.cu:582-606 when no derivative images were made), nextDepth.
-template <int C0, int NS>
-__device__ __forceinline__ void candidate_batch(const ResidualArgs & a, const bool derive, const int gtid, const int gthreads, const int nslots, const int plane,
-                                                unsigned & cand, float (&c_d1)[kSlotChunk], float (&c_img)[kSlotChunk], short (&c_gx)[kSlotChunk],
-                                                short (&c_gy)[kSlotChunk])
+// Pose-independent half of the photometric association (reduce.cu:780-807) for NS pixels of a thread at once, with every
+// load of every pixel issued before the first use: the clipped 4x4 all-nonzero window of nextImage, the gradient pair (from
+// dIdx/dIdy, or derived from the same window with the arithmetic of utils.cu:582-606 when no derivative images were made),
+// nextDepth.  cand[s] = the pixel passes; d1 / gxy (gx | gy << 16) / img are its operands.
+template <int NS>
+__device__ __forceinline__ void rgb_candidate_state(const ResidualArgs & a, const bool derive, const int (&k)[NS], const bool (&live)[NS], const int (&px)[NS],
+                                                    const int (&py)[NS], bool (&cand)[NS], float (&d1o)[NS], unsigned (&gxy)[NS], unsigned (&img)[NS])
 {
     unsigned char w[NS][16];
     float d1[NS];
     short gxl[NS], gyl[NS];
-    int px[NS], py[NS];
-    bool live[NS];
 #pragma unroll
     for(int s = 0; s < NS; s++)
     {
-        const int c = C0 + s;
-        const int k = gtid + c * gthreads;
-        live[s] = (c < nslots) && (k < plane);
-        const int kk = live[s] ? k : 0;
-        py[s] = kk / a.cols;
-        px[s] = kk - py[s] * a.cols;
+        const int kk = live[s] ? k[s] : 0;
+        const int x = live[s] ? px[s] : 0, y = live[s] ? py[s] : 0;
 #pragma unroll
         for(int r = 0; r < 4; r++)
 #pragma unroll
             for(int q = 0; q < 4; q++)
             {
-                const int u = min(max(py[s] - 2 + r, 0), a.rows - 1), v = min(max(px[s] - 2 + q, 0), a.cols - 1);
-                w[s][r * 4 + q] = __ldg(a.nextImage + u * a.cols + v);
+                const int u = min(max(y - 2 + r, 0), a.rows - 1), v = min(max(x - 2 + q, 0), a.cols - 1);
+                w[s][r * 4 + q] = live[s] ? __ldg(a.nextImage + u * a.cols + v) : (unsigned char)0;
             }
-        d1[s] = __ldg(a.nextDepth + kk);
-        gxl[s] = derive ? (short)0 : __ldg(a.dIdx + kk);
-        gyl[s] = derive ? (short)0 : __ldg(a.dIdy + kk);
+        d1[s] = live[s] ? __ldg(a.nextDepth + kk) : 0.f;
+        gxl[s] = (derive || !live[s]) ? (short)0 : __ldg(a.dIdx + kk);
+        gyl[s] = (derive || !live[s]) ? (short)0 : __ldg(a.dIdy + kk);
     }
 #pragma unroll
     for(int s = 0; s < NS; s++)
     {
-        const int c = C0 + s;
         const int x = px[s], y = py[s];
         bool ok = live[s] && (x < a.cols - 5 && y < a.rows - 1);
         // window taps the reference's clipped loops never visit (rows / columns below 0) do not vote
@@ -322,47 +235,189 @@ __device__ __forceinline__ void candidate_batch(const ResidualArgs & a, const bo
         const int valx = gx, valy = gy;
         const float mTwo = (valx * valx) + (valy * valy);
         ok = ok && (mTwo >= a.minScale) && !isnan(d1[s]);
-        if(ok)
-        {
-            cand |= 1u << c;
-            c_d1[c] = d1[s];
-            c_img[c] = static_cast<float>(w[s][2 * 4 + 2]);   // the pixel itself
-            c_gx[c] = gx;
-            c_gy[c] = gy;
-        }
+        cand[s] = ok;
+        d1o[s] = d1[s];
+        gxy[s] = ((unsigned)(unsigned short)gx) | (((unsigned)(unsigned short)gy) << 16);
+        img[s] = w[s][2 * 4 + 2];   // the pixel itself
     }
 }
 
+// Stage one resident level of this CTA: lists of ICP and RGB entries in shared memory (see the header comment).
+// Two passes over the CTA's segments with the same (rolled) code: the first counts the surviving pixels per (segment, warp),
+// a block-wide prefix sum turns the counts into list positions, the second pass loads again (L1 / L2 hot) and scatters.
+// Rolled on purpose: the kernel is bound by instruction fetch, and this code runs once per level.
+__device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, const bool rgb, const int lvl, const LevelPtrs & P, const int rank, GnWork & wk, char * dyn)
+{
+    const LevelPlan pl = L.plan[lvl];
+    const LevelGeom g = L.geom[lvl];
+    const int plane = g.rows * g.cols;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float * icp_list = reinterpret_cast<float *>(dyn + pl.off_icp);
+    float * rgb_d1 = reinterpret_cast<float *>(dyn + pl.off_rgb);
+    unsigned * rgb_gxy = reinterpret_cast<unsigned *>(rgb_d1 + pl.cap);
+    unsigned * rgb_xyi = rgb_gxy + pl.cap;
+    ResidualArgs ra;
+    ra.minScale = L.min_scale[lvl];
+    ra.dIdx = P.dIdx; ra.dIdy = P.dIdy;
+    ra.nextDepth = P.nextDepth;
+    ra.nextImage = P.nextImage;
+    ra.cols = g.cols; ra.rows = g.rows;
+    const int nslots = (pl.segs_per_cta + kGnWarps - 1) / kGnWarps;   // <= kMaxStageSlots (gn_make_plan)
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for(int pass = 0; pass < 2; pass++)
+    {
+#pragma unroll 1
+        for(int m = 0; m < nslots; m++)
+        {
+            const int j = m * kGnWarps + wid;        // this warp's j-th segment of the CTA
+            const int seg = j * pl.P + rank;
+            const int k1[1] = {seg * 32 + lane};
+            const bool l1[1] = {j < pl.segs_per_cta && seg < pl.nseg && k1[0] < plane};
+            const int kk = l1[0] ? k1[0] : 0;
+            const int y1[1] = {kk / g.cols};
+            const int x1[1] = {kk - y1[0] * g.cols};
+            float v[6];
+            bool fi = false;
+            if(icp)
+            {
+                v[0] = l1[0] ? __ldg(P.vcurr + kk) : SLAM_QNAN;
+                v[3] = l1[0] ? __ldg(P.ncurr + kk) : SLAM_QNAN;
+                if(pass == 1)
+                {
+                    v[1] = l1[0] ? __ldg(P.vcurr + plane + kk) : 0.f;
+                    v[2] = l1[0] ? __ldg(P.vcurr + 2 * plane + kk) : 0.f;
+                    v[4] = l1[0] ? __ldg(P.ncurr + plane + kk) : 0.f;
+                    v[5] = l1[0] ? __ldg(P.ncurr + 2 * plane + kk) : 0.f;
+                }
+                fi = !isnan(v[0]) && !isnan(v[3]);
+            }
+            bool c1[1] = {false};
+            float d1[1] = {0.f};
+            unsigned g1[1] = {0u}, i1[1] = {0u};
+            if(rgb)
+            {
+                rgb_candidate_state<1>(ra, L.derive_gradients, k1, l1, x1, y1, c1, d1, g1, i1);
+                // the reference writes a DataTerm for every pixel (reduce.cu:838): pixels that never become entries get their zero once
+                if(L.full_corres && pass == 1 && l1[0] && !c1[0]) reinterpret_cast<int4 *>(P.corres)[kk] = make_int4(0, 0, 0, 0);
+            }
+            const unsigned bi = __ballot_sync(0xffffffffu, fi);
+            const unsigned br = __ballot_sync(0xffffffffu, c1[0]);
+            if(pass == 0)
+            {
+                if(lane == 0)
+                {
+                    wk.scan_cnt[0][m * kGnWarps + wid] = __popc(bi);
+                    wk.scan_cnt[1][m * kGnWarps + wid] = __popc(br);
+                }
+            }
+            else
+            {
+                if(fi)
+                {
+                    const int pos = wk.scan_cnt[0][m * kGnWarps + wid] + __popc(bi & lt);
+#pragma unroll
+                    for(int q = 0; q < 6; q++) icp_list[q * pl.cap + pos] = v[q];
+                }
+                if(c1[0])
+                {
+                    const int pos = wk.scan_cnt[1][m * kGnWarps + wid] + __popc(br & lt);
+                    rgb_d1[pos] = d1[0];
+                    rgb_gxy[pos] = g1[0];
+                    rgb_xyi[pos] = (unsigned)x1[0] | ((unsigned)y1[0] << 11) | (i1[0] << 22);
+                }
+            }
+        }
+        if(pass == 0)
+        {
+            __syncthreads();
+            if(wid < 2)
+            {
+                // exclusive prefix of the counts in (slot, warp) order, in place; warp 0: ICP, warp 1: RGB
+                constexpr int kPer = kMaxStageSlots * kGnWarps / 32;
+                const int n = nslots * kGnWarps;
+                int c[kPer], sum = 0;
+#pragma unroll
+                for(int q = 0; q < kPer; q++)
+                {
+                    const int idx = lane * kPer + q;
+                    c[q] = idx < n ? wk.scan_cnt[wid][idx] : 0;
+                    sum += c[q];
+                }
+                int incl = sum;
+#pragma unroll
+                for(int o = 1; o < 32; o <<= 1)
+                {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if(lane >= o) incl += up;
+                }
+                int run = incl - sum;
+#pragma unroll
+                for(int q = 0; q < kPer; q++)
+                {
+                    const int idx = lane * kPer + q;
+                    if(idx < n) wk.scan_cnt[wid][idx] = run;
+                    run += c[q];
+                }
+                if(lane == 31)
+                {
+                    if(wid == 0) wk.n_icp[lvl] = run;
+                    else wk.n_rgb[lvl] = run;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ the kernel
+// ICP / RGB / RGB_ONLY: the mode of the call (RGBDOdometryef.cpp:275-276), compile-time so that each variant carries only its
+// own phases.  GEN = false is the product's common case and the one tuned for instruction footprint: every level resident,
+// no step trace; GEN = true adds the streamed levels, the step trace / time stamps and the full DataTerm image.
+// PH: per-phase cycle accounting of the leading CTA (slam_odom_get_phase_cycles).
+template <bool ICP, bool RGB, bool RGB_ONLY, bool GEN, bool PH>
 __global__ void __launch_bounds__(kGnThreads, 1)
-k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, float * partials, GnResult * results, slam_step_record * trace,
+k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, unsigned long long * rings, GnResult * results, slam_step_record * trace,
                 int * trace_count, const int G, const int groups, GnResult * host_results, unsigned * host_flags, const unsigned host_seqno)
 {
     __shared__ GnShared sh;
+    __shared__ GnWork wk;
+    extern __shared__ __align__(16) char dyn[];
 
     const int group = blockIdx.x / G;
     const int rank = blockIdx.x - group * G;
     if(group >= groups) return;
 
-    unsigned long long * bar = &ctl->barrier[group];
-    unsigned sum_running = ctl->sum_base[group];   // thread 0's copy is the one that is used
-    // the counter is never reset: every launch starts from the value the previous launch ended with, published in
-    // ctl->base by the group leader (stable for the whole launch: it is rewritten only at the very end)
-    unsigned target = ctl->base[group];
-    unsigned step = 0;
-    // partial rows of this group: [parity][rank][64]
-    float * gpart = partials + (size_t)group * 2 * G * kGnPartialStride;
+    unsigned long long * ring = rings + (size_t)group * (kRingBytes / 8);
+    // the ring position is never reset: every launch continues where the previous one stopped (ctl->step, written by the
+    // group leader at the very end of a launch)
+    unsigned step = ctl->step[group];
 
     const long long t_start = clock64();
-#define GN_STAMP(rec, idx) do { if(rec) (rec)->t_cycles[idx] = (unsigned)(clock64() - t_start); } while(0)
-    const int gtid = rank * blockDim.x + threadIdx.x;
-    const int gthreads = G * blockDim.x;
+#define GN_STAMP(rec, idx) do { if(GEN && rec) (rec)->t_cycles[idx] = (unsigned)(clock64() - t_start); } while(0)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool leader = (rank == 0 && threadIdx.x == 0);
     const bool warp0 = threadIdx.x < 32;
+    const bool keeper = (rank == 0 && wid == kGnWarps - 1);   // clears the ring slot of step + 2 (nothing on the chain waits for this warp)
+    if(threadIdx.x == 0)
+    {
+        wk.cnt[0] = wk.cnt[1] = 0;
+        wk.timeouts = 0;
+    }
+    long long ph_t = t_start;
+    if(PH && threadIdx.x < 12) wk.ph[threadIdx.x] = 0u;
+#define GN_PHASE(idx) do { if(PH && leader) { const long long now_ = clock64(); wk.ph[idx] += (unsigned)(now_ - ph_t); ph_t = now_; } } while(0)
+
+    // Start of every reduction step: the word set two steps ahead is cleared.  Every CTA has read the sums of step - 2 (it has
+    // posted to step - 1 since, and this CTA saw those posts), so nobody reads that set any more; the fence that orders the
+    // clearing before this CTA's own final post of the step follows in GN_STEP_FENCE().
+#define GN_STEP_BEGIN() do { if(keeper) { unsigned long long * z = ring_word(ring, step + 2, 0); for(int c = lane; c < kRingWords; c += 32) z[(size_t)c * kWordStride] = 0ull; } } while(0)
+#define GN_STEP_FENCE() do { if(keeper) __threadfence(); } while(0)
 
     for(int seq = group; seq < L.batch; seq += groups)
     {
-        slam_step_record * tr = (L.trace && leader) ? trace + (size_t)seq * kGnMaxTrace : nullptr;
+        slam_step_record * tr = (GEN && L.trace && leader) ? trace + (size_t)seq * kGnMaxTrace : nullptr;
         int ntr = 0;
 
         if(threadIdx.x == 0)
@@ -386,62 +441,113 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         }
         __syncthreads();
 
+        // ------------------------------------------------ staging: every resident level, and the SO3 images
+#pragma unroll 1
+        for(int lvl = L.levels - 1; lvl >= 0; lvl--)
+        {
+            if(L.iterations[lvl] > 0 && L.plan[lvl].resident && rank < L.plan[lvl].P)
+                stage_level(L, ICP, RGB, lvl, level_ptrs(L.batch == 1, seq0, seqs, seq, lvl), rank, wk, dyn);
+        }
+        if(L.so3 && L.so3_resident && rank < L.so3_P)
+        {
+            const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
+            const int N = L.geom[2].rows * L.geom[2].cols;
+            unsigned char * s_last = reinterpret_cast<unsigned char *>(dyn + L.off_so3);
+            unsigned char * s_next = s_last + ((N + 15) & ~15);
+            if((N & 15) == 0)
+            {
+#pragma unroll 1
+                for(int q = threadIdx.x; q < N / 16; q += kGnThreads)
+                {
+                    reinterpret_cast<uint4 *>(s_last)[q] = __ldg(reinterpret_cast<const uint4 *>(P2.lastNextImage) + q);
+                    reinterpret_cast<uint4 *>(s_next)[q] = __ldg(reinterpret_cast<const uint4 *>(P2.nextImage) + q);
+                }
+            }
+            else
+            {
+#pragma unroll 1
+                for(int q = threadIdx.x; q < N; q += kGnThreads)
+                {
+                    s_last[q] = __ldg(P2.lastNextImage + q);
+                    s_next[q] = __ldg(P2.nextImage + q);
+                }
+            }
+            __syncthreads();
+        }
+        GN_PHASE(0);
+
         // ------------------------------------------------ SO3 pre-alignment, level 2
         if(L.so3)
         {
             const LevelGeom g = L.geom[2];
             const int N = g.rows * g.cols;
-            const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
+            const int Pn = L.so3_P;
             if(threadIdx.x == 0)
             {
                 level_begin(sh, g);
                 so3_prepare(sh);
+                wk.P = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
             }
             __syncthreads();
+#pragma unroll 1
             for(int it = 0; it < 10; it++)
             {
-                So3Args a;
-                a.lastImage = P2.lastNextImage;
-                a.nextImage = P2.nextImage;
-                a.imageBasis = mat3_from(sh.so3H);
-                a.kinv = mat3_from(sh.so3Kinv);
-                a.krlr = mat3_from(sh.so3KR);
-                a.cols = g.cols;
-                a.rows = g.rows;
-
-                float acc[32];
-#pragma unroll
-                for(int k = 0; k < 32; k++) acc[k] = 0.f;
-                for(int k = gtid; k < N; k += gthreads)
+                GN_STEP_BEGIN();
+                if(rank < Pn)
                 {
-                    const int y = k / g.cols;
-                    const int x = k - y * g.cols;
-                    float row[4];
-                    const bool found = so3_pixel(a, x, y, row);
-                    float a11[11];
-#pragma unroll
-                    for(int q = 0; q < 11; q++) a11[q] = acc[q];
-                    accumulate_so3(a11, row, found);
-#pragma unroll
-                    for(int q = 0; q < 11; q++) acc[q] = a11[q];
-                }
-                float * myrow = gpart + ((step & 1) * G + rank) * kGnPartialStride;
-                cta_publish32(acc, sh, myrow);
-                group_barrier(bar, target, G);
-                fold_partials(sh, gpart + (step & 1) * G * kGnPartialStride, G);
-                step++;
+                    So3Args a;
+                    if(L.so3_resident)
+                    {
+                        a.lastImage = reinterpret_cast<const unsigned char *>(dyn + L.off_so3);
+                        a.nextImage = a.lastImage + ((N + 15) & ~15);
+                    }
+                    else
+                    {
+                        a.lastImage = wk.P.lastNextImage;
+                        a.nextImage = wk.P.nextImage;
+                    }
+                    a.imageBasis = mat3_from(sh.so3H);
+                    a.kinv = mat3_from(sh.so3Kinv);
+                    a.krlr = mat3_from(sh.so3KR);
+                    a.cols = g.cols;
+                    a.rows = g.rows;
 
+                    float acc[32];
+#pragma unroll
+                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
+#pragma unroll 1
+                    for(int k = rank * kGnThreads + threadIdx.x; k < N; k += Pn * kGnThreads)
+                    {
+                        const int y = k / g.cols;
+                        const int x = k - y * g.cols;
+                        float row[4];
+                        const bool found = so3_pixel(a, x, y, row);
+                        float a11[11];
+#pragma unroll
+                        for(int q = 0; q < 11; q++) a11[q] = acc[q];
+                        accumulate_so3(a11, row, found);
+#pragma unroll
+                        for(int q = 0; q < 11; q++) acc[q] = a11[q];
+                    }
+                    GN_STEP_FENCE();
+                    cta_reduce_post(acc, sh, ring, step, kWSo3, 11);
+                }
                 if(warp0)
                 {
-                    slam_step_record * rec = (threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
-                    if(rec) memset(rec, 0, sizeof(*rec));
-                    warp_so3_update(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R in shared memory
-                    if(rec) ntr++;
+                    spin_cycles(L.poll_delay);
+                    read_columns(ring, step, kWSo3, 11, threadIdx.x, (unsigned)Pn, sh.total, wk);
+                    __syncwarp();
+                    slam_step_record * rec = (GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
+                    if(GEN && rec) memset(rec, 0, sizeof(*rec));
+                    warp_so3_update_fast(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R in shared memory
+                    if(GEN && rec) ntr++;
                 }
+                step++;
                 __syncthreads();
                 if(sh.stop) break;
             }
         }
+        GN_PHASE(1);
 
         if(threadIdx.x == 0)
         {
@@ -453,52 +559,34 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         __syncthreads();
 
         // ------------------------------------------------ coarse-to-fine ICP + RGB
+#pragma unroll 1
         for(int lvl = L.levels - 1; lvl >= 0; lvl--)
         {
-            const LevelGeom g = L.geom[lvl];
-            const int plane = g.rows * g.cols;
-            const int nslots = (plane + gthreads - 1) / gthreads;
-            // all of this thread's pixels fit one register-resident chunk (always true for one 640x480 sequence on a full GPU)
-            const bool single = nslots <= kSlotChunk;
-            const LevelPtrs P = level_ptrs(L.batch == 1, seq0, seqs, seq, lvl);
+            if(L.iterations[lvl] <= 0) continue;
+            const bool resident = !GEN || L.plan[lvl].resident != 0;
+            const int Pn = L.plan[lvl].P;
+            const bool part = rank < Pn;
             if(warp0)
             {
                 if(threadIdx.x == 0)
                 {
                     sh.res.lastRGBError = FLT_MAX;
-                    level_begin(sh, g);
+                    level_begin(sh, L.geom[lvl]);
+                    wk.P = level_ptrs(L.batch == 1, seq0, seqs, seq, lvl);
+                    wk.lv_n_icp = resident ? wk.n_icp[lvl] : 0;
+                    wk.lv_n_rgb = resident ? wk.n_rgb[lvl] : 0;
                 }
                 __syncwarp();
-                warp_prepare(sh, false);   // krk / kt of the first iteration of this level (Rcurr/tcurr carry over)
-            }
-
-            // ---- per-level, pose-independent pixel state (registers): RGB candidate test (reduce.cu:780-807) and its operands
-            unsigned cand = 0;              // bit c: slot c is an RGB candidate
-            float c_d1[kSlotChunk];         // nextDepth
-            float c_img[kSlotChunk];        // nextImage as float
-            short c_gx[kSlotChunk], c_gy[kSlotChunk];
-#pragma unroll
-            for(int c = 0; c < kSlotChunk; c++)
-            {
-                c_d1[c] = 0.f; c_img[c] = 0.f; c_gx[c] = 0; c_gy[c] = 0;
-            }
-            if(L.rgb && single)
-            {
-                ResidualArgs a;
-                a.minScale = L.min_scale[lvl];
-                a.dIdx = P.dIdx; a.dIdy = P.dIdy;
-                a.nextDepth = P.nextDepth;
-                a.nextImage = P.nextImage;
-                a.cols = g.cols; a.rows = g.rows;
-                candidate_batch<0, 3>(a, L.derive_gradients, gtid, gthreads, nslots, plane, cand, c_d1, c_img, c_gx, c_gy);
-                if(nslots > 3) candidate_batch<3, kSlotChunk - 3>(a, L.derive_gradients, gtid, gthreads, nslots, plane, cand, c_d1, c_img, c_gx, c_gy);
+                warp_prepare_fast(sh, false);   // krk / kt of the first iteration of this level (Rcurr/tcurr carry over)
             }
             __syncthreads();
 
+#pragma unroll 1
             for(int j = 0; j < L.iterations[lvl]; j++)
             {
+                GN_STEP_BEGIN();
                 slam_step_record * rec = nullptr;
-                if(threadIdx.x == 0 && tr && ntr < kGnMaxTrace)
+                if(GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace)
                 {
                     rec = &tr[ntr];
                     memset(rec, 0, sizeof(*rec));
@@ -519,313 +607,374 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     GN_STAMP(rec, 0);
                     GN_STAMP(rec, 1);
                 }
+                GN_PHASE(2);
 
-                float * rowsA = gpart + (step & 1) * G * kGnPartialStride;
-                float * myrow = rowsA + rank * kGnPartialStride;
-
-                // phase A -> B state of this thread's slots (registers, single-chunk case)
-                unsigned valid_mask = 0;
-                int r_zxy[kSlotChunk];      // (zy << 16) | zx : pixel in the last image
-                float r_diff[kSlotChunk];   // next - last intensity
-                float r_d0[kSlotChunk];     // lastDepth at that pixel
-#pragma unroll
-                for(int c = 0; c < kSlotChunk; c++)
+                // ---------------- RGB association (reduce.cu:809-841): correspondences + their count
+                if(RGB && part)
                 {
-                    r_zxy[c] = 0; r_diff[c] = 0.f; r_d0[c] = 0.f;
-                }
-
-                unsigned mid_word = 0;
-                float sigma_now = 0.f;
-                // ---------------- phase A: ICP products + RGB association
-                {
-                    float acc[32];
-#pragma unroll
-                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
-                    if(L.icp)
+                    const LevelGeom g = L.geom[lvl];
+                    const int cap = L.plan[lvl].cap;
+                    ResidualArgs a;
+                    a.minScale = L.min_scale[lvl];
+                    a.dIdx = wk.P.dIdx; a.dIdy = wk.P.dIdy;
+                    a.lastDepth = wk.P.lastDepth; a.nextDepth = wk.P.nextDepth;
+                    a.lastImage = wk.P.lastImage; a.nextImage = wk.P.nextImage;
+                    a.maxDepthDelta = L.max_depth_delta;
+                    a.kt = make_float3(sh.kt[0], sh.kt[1], sh.kt[2]);
+                    a.krkinv = mat3_from(sh.krk);
+                    a.cols = g.cols; a.rows = g.rows;
+                    int cnt0 = 0, cnt1 = 0;
+                    if(resident)
                     {
-                        IcpArgs a;
-                        a.Rcurr = mat3_from(sh.Rcurr);
-                        a.tcurr = make_float3(sh.tcurr[0], sh.tcurr[1], sh.tcurr[2]);
-                        a.Rprev_inv = mat3_from(sh.Rprev_inv);
-                        a.tprev = make_float3(sh.tprev[0], sh.tprev[1], sh.tprev[2]);
-                        a.fx = g.fx; a.fy = g.fy; a.cx = g.cx; a.cy = g.cy;
-                        a.distThres = L.dist_thresh;
-                        a.angleThres = L.angle_thresh;
-                        a.cols = g.cols;
-                        a.rows = g.rows;
-                        a.vcurr = P.vcurr; a.ncurr = P.ncurr; a.vprev = P.vprev; a.nprev = P.nprev;
-                        for(int m0 = 0; m0 < nslots; m0 += kIcpChunk)
+                        const int n_rgb = wk.lv_n_rgb;
+                        const float * rgb_d1 = reinterpret_cast<const float *>(dyn + L.plan[lvl].off_rgb);
+                        const unsigned * rgb_xyi = reinterpret_cast<const unsigned *>(rgb_d1 + 2 * cap);
+                        int * st_zxy = reinterpret_cast<int *>(dyn + L.off_state);   // (zy << 16) | zx of the correspondence, -1: none
+                        float * st_diff = reinterpret_cast<float *>(st_zxy + cap);
+                        float * st_d0 = st_diff + cap;
+#pragma unroll 1
+                        for(int e0 = threadIdx.x; e0 < n_rgb; e0 += kRgbChunk * kGnThreads)
                         {
-                            float3 vg[kIcpChunk], nc[kIcpChunk], vp[kIcpChunk], np[kIcpChunk];
-                            int o[kIcpChunk];
-                            bool ok[kIcpChunk];
-                            // 1) current vertex + normal of every slot of the chunk (coalesced across the warp)
+                            int o0[kRgbChunk], zxy[kRgbChunk];
+                            float td1[kRgbChunk], d0[kRgbChunk];
+                            unsigned xyi[kRgbChunk];
+                            unsigned char lst[kRgbChunk];
+                            bool inb[kRgbChunk];
+                            // 1) warp every entry, 2) issue the gathers, 3) gates
 #pragma unroll
-                            for(int c = 0; c < kIcpChunk; c++)
+                            for(int c = 0; c < kRgbChunk; c++)
                             {
-                                const int k = gtid + (m0 + c) * gthreads;
-                                ok[c] = (m0 + c < nslots) && (k < plane);
-                                const int kk = ok[c] ? k : 0;
-                                vg[c] = make_float3(__ldg(a.vcurr + kk), __ldg(a.vcurr + plane + kk), __ldg(a.vcurr + 2 * plane + kk));
-                                nc[c] = make_float3(__ldg(a.ncurr + kk), __ldg(a.ncurr + plane + kk), __ldg(a.ncurr + 2 * plane + kk));
-                            }
-                            // 2) project all, 3) issue all gathers
-#pragma unroll
-                            for(int c = 0; c < kIcpChunk; c++)
-                            {
-                                float3 g3;
-                                const bool inb = icp_project(a, vg[c], g3, o[c]);
-                                vg[c] = g3;
-                                ok[c] = ok[c] && inb;
-                                if(!ok[c]) o[c] = 0;
+                                const int e = e0 + c * kGnThreads;
+                                const bool live = e < n_rgb;
+                                const int ee = live ? e : e0;
+                                xyi[c] = rgb_xyi[ee];
+                                int u0, v0;
+                                inb[c] = rgb_project(a, (int)(xyi[c] & 2047u), (int)((xyi[c] >> 11) & 2047u), rgb_d1[ee], u0, v0, td1[c]) && live;
+                                o0[c] = inb[c] ? v0 * g.cols + u0 : 0;
+                                zxy[c] = (v0 << 16) | u0;
                             }
 #pragma unroll
-                            for(int c = 0; c < kIcpChunk; c++)
+                            for(int c = 0; c < kRgbChunk; c++)
                             {
-                                vp[c] = make_float3(__ldg(a.vprev + o[c]), __ldg(a.vprev + plane + o[c]), __ldg(a.vprev + 2 * plane + o[c]));
-                                np[c] = make_float3(__ldg(a.nprev + o[c]), __ldg(a.nprev + plane + o[c]), __ldg(a.nprev + 2 * plane + o[c]));
+                                d0[c] = inb[c] ? __ldg(a.lastDepth + o0[c]) : 0.f;
+                                lst[c] = inb[c] ? __ldg(a.lastImage + o0[c]) : (unsigned char)0;
                             }
-                            // 4) gates, rows, products
 #pragma unroll
-                            for(int c = 0; c < kIcpChunk; c++)
+                            for(int c = 0; c < kRgbChunk; c++)
                             {
-                                float row[7];
-                                const bool found = icp_finish(a, vg[c], nc[c], vp[c], np[c], row) && ok[c];
-                                if(found)
+                                const int e = e0 + c * kGnThreads;
+                                if(e < n_rgb)
                                 {
-                                    float a29[29];
-#pragma unroll
-                                    for(int q = 0; q < 29; q++) a29[q] = acc[q];
-                                    accumulate_se3(a29, row, true);
-#pragma unroll
-                                    for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                                    const bool valid = inb[c] && rgb_accept(a, td1[c], d0[c], lst[c]);
+                                    const float diff = __fsub_rn(static_cast<float>(xyi[c] >> 22), static_cast<float>(lst[c]));
+                                    if(valid)
+                                    {
+                                        cnt0 += 1;
+                                        cnt1 += (int)(diff * diff);
+                                    }
+                                    st_zxy[e] = valid ? zxy[c] : -1;
+                                    st_diff[e] = diff;
+                                    st_d0[e] = d0[c];
+                                    if(GEN && L.full_corres)   // the reference writes a DataTerm for every pixel (reduce.cu:838): only when a test taps it
+                                    {
+                                        const int x = (int)(xyi[c] & 2047u), y = (int)((xyi[c] >> 11) & 2047u);
+                                        Corres cc;
+                                        cc.zx = valid ? (short)(zxy[c] & 0xffff) : 0;
+                                        cc.zy = valid ? (short)(zxy[c] >> 16) : 0;
+                                        cc.ox = valid ? (short)x : 0;
+                                        cc.oy = valid ? (short)y : 0;
+                                        cc.diff = valid ? diff : 0.f;
+                                        cc.valid = valid ? 1 : 0;
+                                        reinterpret_cast<int4 *>(wk.P.corres)[y * g.cols + x] = *reinterpret_cast<const int4 *>(&cc);
+                                    }
                                 }
                             }
                         }
                     }
-                    int cnt0 = 0, cnt1 = 0;
-                    if(L.rgb)
+                    else if(GEN)
                     {
-                        ResidualArgs a;
-                        a.minScale = L.min_scale[lvl];
-                        a.dIdx = P.dIdx; a.dIdy = P.dIdy;
-                        a.lastDepth = P.lastDepth; a.nextDepth = P.nextDepth;
-                        a.lastImage = P.lastImage; a.nextImage = P.nextImage;
-                        a.maxDepthDelta = L.max_depth_delta;
-                        a.kt = make_float3(sh.kt[0], sh.kt[1], sh.kt[2]);
-                        a.krkinv = mat3_from(sh.krk);
-                        a.cols = g.cols; a.rows = g.rows;
-                        Corres * cimg = P.corres;
-                        if(single)
+                        // streamed level: correspondences go through memory (corresImg, as in the reference)
+                        const int plane = g.rows * g.cols;
+                        Corres * cimg = wk.P.corres;
+#pragma unroll 1
+                        for(int k = rank * kGnThreads + threadIdx.x; k < plane; k += G * kGnThreads)
                         {
-                            int o0[kSlotChunk];
-                            float td1[kSlotChunk];
-                            unsigned inb = 0;
-                            // 1) warp every candidate, 2) issue the gathers, 3) gates
-#pragma unroll
-                            for(int c = 0; c < kSlotChunk; c++)
+                            const int i = k / g.cols;
+                            const int j0 = k - i * g.cols;
+                            Corres c;
+                            c.zx = c.zy = c.ox = c.oy = 0;
+                            c.diff = 0.f;
+                            c.valid = 0;
+                            if(rgb_candidate(a, j0, i) && rgb_associate(a, j0, i, c))
                             {
-                                o0[c] = 0;
-                                td1[c] = 0.f;
-                                if((cand >> c) & 1u)
+                                cnt0 += 1;
+                                cnt1 += (int)(c.diff * c.diff);
+                            }
+                            reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
+                        }
+                    }
+                    const int w0 = __reduce_add_sync(0xffffffffu, cnt0);
+                    const int w1 = __reduce_add_sync(0xffffffffu, cnt1);
+                    if(lane == 0 && (w0 | w1))
+                    {
+                        atomicAdd(&wk.cnt[0], w0);
+                        atomicAdd(&wk.cnt[1], w1);
+                    }
+                    __syncthreads();
+                    if(threadIdx.x == 0)
+                    {
+                        const int c0 = wk.cnt[0], c1 = wk.cnt[1];
+                        wk.cnt[0] = wk.cnt[1] = 0;
+                        post_int(ring, step, kWMid, (long long)c0 + (c1 != 0 ? (1ll << 32) : 0ll));
+                        post_int(ring, step, kWSigma, (long long)c1);
+                    }
+                }
+                GN_PHASE(3);
+
+                // Two map + block-reduction passes share ONE copy of the reduction code: pass 0 = ICP products (reduce.cu:282-416;
+                // the count's trip through L2 overlaps this map), pass 1 = RGB Jacobian products (reduce.cu:494-624).
+                bool stop_now = false;
+#pragma unroll 1
+                for(int pass = ICP ? 0 : 1; pass < (RGB ? 2 : 1); pass++)
+                {
+                    float acc[32];
+#pragma unroll
+                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
+                    if(ICP && pass == 0)
+                    {
+                        if(part)
+                        {
+                            const LevelGeom g = L.geom[lvl];
+                            const int plane = g.rows * g.cols;
+                            const int cap = L.plan[lvl].cap;
+                            IcpArgs a;
+                            a.Rcurr = mat3_from(sh.Rcurr);
+                            a.tcurr = make_float3(sh.tcurr[0], sh.tcurr[1], sh.tcurr[2]);
+                            a.Rprev_inv = mat3_from(sh.Rprev_inv);
+                            a.tprev = make_float3(sh.tprev[0], sh.tprev[1], sh.tprev[2]);
+                            a.fx = g.fx; a.fy = g.fy; a.cx = g.cx; a.cy = g.cy;
+                            a.distThres = L.dist_thresh;
+                            a.angleThres = L.angle_thresh;
+                            a.cols = g.cols;
+                            a.rows = g.rows;
+                            a.vcurr = wk.P.vcurr; a.ncurr = wk.P.ncurr; a.vprev = wk.P.vprev; a.nprev = wk.P.nprev;
+                            const float * icp_list = reinterpret_cast<const float *>(dyn + L.plan[lvl].off_icp);
+                            const int n_items = resident ? wk.lv_n_icp : plane;
+                            const int first = resident ? (int)threadIdx.x : rank * kGnThreads + (int)threadIdx.x;
+                            const int stride = resident ? kGnThreads : G * kGnThreads;
+#pragma unroll 1
+                            for(int e0 = first; e0 < n_items; e0 += kIcpChunk * stride)
+                            {
+                                float3 vg[kIcpChunk], nc[kIcpChunk], vp[kIcpChunk], np[kIcpChunk];
+                                int o[kIcpChunk];
+                                bool ok[kIcpChunk];
+                                // 1) current vertex + normal of every entry of the chunk, 2) project all, 3) issue all gathers, 4) gates, rows, products
+#pragma unroll
+                                for(int c = 0; c < kIcpChunk; c++)
                                 {
-                                    const int k = gtid + c * gthreads;
-                                    const int i = k / g.cols;
-                                    int u0, v0;
-                                    if(rgb_project(a, k - i * g.cols, i, c_d1[c], u0, v0, td1[c]))
+                                    const int e = e0 + c * stride;
+                                    ok[c] = e < n_items;
+                                    const int ee = ok[c] ? e : e0;
+                                    float3 v;
+                                    if(resident)
                                     {
-                                        inb |= 1u << c;
-                                        o0[c] = v0 * g.cols + u0;
-                                        r_zxy[c] = (v0 << 16) | u0;
+                                        v = make_float3(icp_list[ee], icp_list[cap + ee], icp_list[2 * cap + ee]);
+                                        nc[c] = make_float3(icp_list[3 * cap + ee], icp_list[4 * cap + ee], icp_list[5 * cap + ee]);
+                                    }
+                                    else
+                                    {
+                                        v = make_float3(__ldg(a.vcurr + ee), __ldg(a.vcurr + plane + ee), __ldg(a.vcurr + 2 * plane + ee));
+                                        nc[c] = make_float3(__ldg(a.ncurr + ee), __ldg(a.ncurr + plane + ee), __ldg(a.ncurr + 2 * plane + ee));
+                                    }
+                                    const bool inb = icp_project(a, v, vg[c], o[c]);
+                                    ok[c] = ok[c] && inb;
+                                    if(!ok[c]) o[c] = 0;
+                                }
+#pragma unroll
+                                for(int c = 0; c < kIcpChunk; c++)
+                                {
+                                    vp[c] = make_float3(__ldg(a.vprev + o[c]), __ldg(a.vprev + plane + o[c]), __ldg(a.vprev + 2 * plane + o[c]));
+                                    np[c] = make_float3(__ldg(a.nprev + o[c]), __ldg(a.nprev + plane + o[c]), __ldg(a.nprev + 2 * plane + o[c]));
+                                }
+#pragma unroll
+                                for(int c = 0; c < kIcpChunk; c++)
+                                {
+                                    float row[7];
+                                    const bool found = icp_finish(a, vg[c], nc[c], vp[c], np[c], row) && ok[c];
+                                    if(found)
+                                    {
+                                        float a29[29];
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                        accumulate_se3(a29, row, true);
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) acc[q] = a29[q];
                                     }
                                 }
                             }
-                            unsigned char lst[kSlotChunk];
-#pragma unroll
-                            for(int c = 0; c < kSlotChunk; c++)
+                        }
+                        GN_STAMP(rec, 2);
+                        GN_PHASE(4);
+                    }
+                    else
+                    {
+                        // ---------------- the global correspondence count: every CTA (rgbOnly decides the early exit on it)
+                        if(threadIdx.x == 0)
+                        {
+                            wk.mid = (unsigned long long)poll_word(ring, step, kWMid, (unsigned)Pn, wk);
+                            if(RGB_ONLY) wk.sigma = poll_word(ring, step, kWSigma, (unsigned)Pn, wk);
+                        }
+                        __syncthreads();
+                        GN_STAMP(rec, 3);
+                        GN_PHASE(5);
+                        float sigma_now = 0.f;
+                        if(RGB_ONLY)
+                        {
+                            // count / sigma of the whole image -> rgbError decides the early exit (every CTA, identically)
+                            if(threadIdx.x == 0)
                             {
-                                r_d0[c] = __ldg(a.lastDepth + o0[c]);
-                                lst[c] = __ldg(a.lastImage + o0[c]);
+                                sh.total[29] = __int_as_float((int)(wk.mid & 0xffffffffull));
+                                sh.total[30] = __int_as_float((int)wk.sigma);
+                                gn_sigma(sh, true, rec);
                             }
-#pragma unroll
-                            for(int c = 0; c < kSlotChunk; c++)
+                            __syncthreads();
+                            if(sh.stop)
                             {
-                                if(((inb >> c) & 1u) && rgb_accept(a, td1[c], r_d0[c], lst[c]))
-                                {
-                                    valid_mask |= 1u << c;
-                                    r_diff[c] = __fsub_rn(c_img[c], static_cast<float>(lst[c]));
-                                    cnt0 += 1;
-                                    cnt1 += (int)(r_diff[c] * r_diff[c]);
-                                }
+                                stop_now = true;   // rgbOnly && rgbError > lastRGBError, RGBDOdometryef.cpp:460-463
+                                break;
                             }
-                            if(L.full_corres)   // the reference writes a DataTerm for every pixel (reduce.cu:838): only when a test taps it
-                            {
-#pragma unroll
-                                for(int c = 0; c < kSlotChunk; c++)
-                                {
-                                    const int k = gtid + c * gthreads;
-                                    if(c < nslots && k < plane)
-                                    {
-                                        Corres cc;
-                                        const bool v = (valid_mask >> c) & 1u;
-                                        const int i = k / g.cols;
-                                        cc.zx = v ? (short)(r_zxy[c] & 0xffff) : 0;
-                                        cc.zy = v ? (short)(r_zxy[c] >> 16) : 0;
-                                        cc.ox = v ? (short)(k - i * g.cols) : 0;
-                                        cc.oy = v ? (short)i : 0;
-                                        cc.diff = v ? r_diff[c] : 0.f;
-                                        cc.valid = v ? 1 : 0;
-                                        reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&cc);
-                                    }
-                                }
-                            }
+                            sigma_now = sh.sigmaVal;
                         }
                         else
                         {
-                            // general case (several sequences share the GPU, or a large image): correspondences go through memory
-                            for(int m = 0; m < nslots; m++)
+                            // sigmaVal = sqrt(count) needs nothing else (RGBDOdometryef.cpp:457-471; the squared-residual sum is a statistic)
+                            const int rgbSize = (int)(wk.mid & 0xffffffffull);
+                            const int sel = (rgbSize != 0 && (wk.mid >> 32) == 0ull) ? 1 : rgbSize;
+                            sigma_now = __fsqrt_rn((float)sel);
+                            if(GEN && rec) rec->sigma_in = sigma_now;
+                        }
+                        GN_STAMP(rec, 4);
+                        if(part)
+                        {
+                            const LevelGeom g = L.geom[lvl];
+                            const int cap = L.plan[lvl].cap;
+                            RgbStepArgs a;
+                            a.sigma = sigma_now;
+                            a.fx = g.fx; a.fy = g.fy;
+                            a.sobelScale = L.sobel_scale;
+                            a.cols = g.cols; a.rows = g.rows;
+                            a.dIdx = wk.P.dIdx; a.dIdy = wk.P.dIdy;
+                            a.lastDepth = wk.P.lastDepth;
+                            a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
+                            a.cloud = nullptr;
+                            if(resident)
                             {
-                                const int k = gtid + m * gthreads;
-                                if(k >= plane) break;
-                                const int i = k / g.cols;
-                                const int j0 = k - i * g.cols;
-                                Corres c;
-                                c.zx = c.zy = c.ox = c.oy = 0;
-                                c.diff = 0.f;
-                                c.valid = 0;
-                                if(rgb_candidate(a, j0, i) && rgb_associate(a, j0, i, c))
+                                const int n_rgb = wk.lv_n_rgb;
+                                const unsigned * rgb_gxy = reinterpret_cast<const unsigned *>(dyn + L.plan[lvl].off_rgb) + cap;
+                                const int * st_zxy = reinterpret_cast<const int *>(dyn + L.off_state);
+                                const float * st_diff = reinterpret_cast<const float *>(st_zxy + cap);
+                                const float * st_d0 = st_diff + cap;
+#pragma unroll 1
+                                for(int e = threadIdx.x; e < n_rgb; e += kGnThreads)
                                 {
-                                    cnt0 += 1;
-                                    cnt1 += (int)(c.diff * c.diff);
+                                    const int zxy = st_zxy[e];
+                                    if(zxy >= 0)
+                                    {
+                                        const unsigned gq = rgb_gxy[e];
+                                        float row[7];
+                                        rgb_row_regs(a, zxy & 0xffff, zxy >> 16, st_d0[e], (short)(gq & 0xffffu), (short)(gq >> 16), st_diff[e], row);
+                                        float a29[29];
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                        accumulate_se3(a29, row, true);
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                                    }
                                 }
-                                reinterpret_cast<int4 *>(cimg)[k] = *reinterpret_cast<const int4 *>(&c);
+                            }
+                            else if(GEN)
+                            {
+                                const Corres * cimg = wk.P.corres;
+                                const int plane = g.rows * g.cols;
+#pragma unroll 1
+                                for(int k = rank * kGnThreads + threadIdx.x; k < plane; k += G * kGnThreads)
+                                {
+                                    const int4 raw = *(reinterpret_cast<const int4 *>(cimg) + k);   // written by this very thread above
+                                    const Corres c = *reinterpret_cast<const Corres *>(&raw);
+                                    if(c.valid & 0xff)
+                                    {
+                                        float row[7];
+                                        rgb_row(a, c, row);
+                                        float a29[29];
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) a29[q] = acc[q];
+                                        accumulate_se3(a29, row, true);
+#pragma unroll
+                                        for(int q = 0; q < 29; q++) acc[q] = a29[q];
+                                    }
+                                }
                             }
                         }
+                        GN_STAMP(rec, 5);
                     }
-                    GN_STAMP(rec, 2);
-                    // per-thread counts are tiny: carried through the float reduction exactly (block sums < 2^24)
-                    acc[29] = (float)cnt0;
-                    acc[30] = (float)(cnt1 & 0xfff);
-                    acc[31] = (float)(cnt1 >> 12);
-                    mid_word = cta_publish32(acc, sh, myrow, L.rgb);
+                    if(part)
+                    {
+                        if(pass == (RGB ? 1 : 0)) GN_STEP_FENCE();   // before this CTA's last post of the step
+                        cta_reduce_post(acc, sh, ring, step, pass ? kWRgb : kWIcp, 29);
+                    }
+                    if(pass == 1) GN_PHASE(6);
                 }
-
-                if(L.rgb)
+                if(RGB_ONLY && stop_now)
                 {
-                    if(L.rgb_only)
-                    {
-                        group_barrier(bar, target, G);
-                        GN_STAMP(rec, 3);
-                        // count / sigma of the whole image -> rgbError decides the early exit (every CTA, identically)
-                        if(warp0)
-                        {
-                            fold_count_sigma(sh, rowsA, G);
-                            if(threadIdx.x == 0) gn_sigma(sh, true, rec);
-                        }
-                        __syncthreads();
-                    }
-                    else
-                    {
-                        // the barrier itself sums the correspondence counts: sigmaVal = sqrt(count) needs nothing else
-                        // (RGBDOdometryef.cpp:457-471; the squared-residual sum is a statistic, folded after phase B)
-                        group_barrier_sum(bar, target, G, mid_word, sum_running, &sh.mid_sum);
-                        GN_STAMP(rec, 3);
-                        const int word = sh.mid_sum;
-                        const int rgbSize = word & 0xffffff;
-                        const int sel = (rgbSize != 0 && (word >> 24) == 0) ? 1 : rgbSize;
-                        sigma_now = __fsqrt_rn((float)sel);
-                        if(rec) rec->sigma_in = sigma_now;
-                    }
-                    GN_STAMP(rec, 4);
-                    if(L.rgb_only && sh.stop)
-                    {
-                        step++;
-                        break;   // rgbOnly && rgbError > lastRGBError, RGBDOdometryef.cpp:460-463
-                    }
-
-                    // ---------------- phase B: RGB Jacobian products
-                    float acc[32];
-#pragma unroll
-                    for(int k = 0; k < 32; k++) acc[k] = 0.f;
-                    RgbStepArgs a;
-                    a.sigma = L.rgb_only ? sh.sigmaVal : sigma_now;
-                    a.fx = g.fx; a.fy = g.fy;
-                    a.sobelScale = L.sobel_scale;
-                    a.cols = g.cols; a.rows = g.rows;
-                    a.dIdx = P.dIdx; a.dIdy = P.dIdy;
-                    a.lastDepth = P.lastDepth;
-                    a.invFx = 1.0f / g.fx; a.invFy = 1.0f / g.fy; a.cx = g.cx; a.cy = g.cy;
-                    a.cloud = nullptr;
-                    if(single)
-                    {
-#pragma unroll
-                        for(int c = 0; c < kSlotChunk; c++)
-                            if((valid_mask >> c) & 1u)
-                            {
-                                float row[7];
-                                rgb_row_regs(a, r_zxy[c] & 0xffff, r_zxy[c] >> 16, r_d0[c], c_gx[c], c_gy[c], r_diff[c], row);
-                                float a29[29];
-#pragma unroll
-                                for(int q = 0; q < 29; q++) a29[q] = acc[q];
-                                accumulate_se3(a29, row, true);
-#pragma unroll
-                                for(int q = 0; q < 29; q++) acc[q] = a29[q];
-                            }
-                    }
-                    else
-                    {
-                        const Corres * cimg = P.corres;
-                        for(int m = 0; m < nslots; m++)
-                        {
-                            const int k = gtid + m * gthreads;
-                            if(k >= plane) break;
-                            const int4 raw = *(reinterpret_cast<const int4 *>(cimg) + k);   // written by this very thread in phase A
-                            const Corres c = *reinterpret_cast<const Corres *>(&raw);
-                            if(c.valid & 0xff)
-                            {
-                                float row[7];
-                                rgb_row(a, c, row);
-                                float a29[29];
-#pragma unroll
-                                for(int q = 0; q < 29; q++) a29[q] = acc[q];
-                                accumulate_se3(a29, row, true);
-#pragma unroll
-                                for(int q = 0; q < 29; q++) acc[q] = a29[q];
-                            }
-                        }
-                    }
-                    GN_STAMP(rec, 5);
-                    cta_publish32(acc, sh, myrow + 32);
+                    step++;
+                    break;
                 }
-                group_barrier(bar, target, G);
-                fold_partials(sh, rowsA, G);
+
+                // ---------------- all sums of the step: warps 0..3 read the words, warp 0 solves
+                if(threadIdx.x < 128)
+                {
+                    spin_cycles(L.poll_delay);
+                    const int t = (int)threadIdx.x;
+                    if(ICP && RGB)
+                    {
+                        const int kind = t >= 58 ? 1 : 0;
+                        read_columns(ring, step, kind ? kWRgb : kWIcp, 29, t - 58 * kind, (unsigned)Pn, sh.total + 32 * kind, wk);
+                    }
+                    else
+                        read_columns(ring, step, ICP ? kWIcp : kWRgb, 29, t, (unsigned)Pn, sh.total + (ICP ? 0 : 32), wk);
+                    if(RGB && !RGB_ONLY && t == 127)
+                    {
+                        const long long sg = poll_word(ring, step, kWSigma, (unsigned)Pn, wk);
+                        const int rgbSize = (int)(wk.mid & 0xffffffffull);
+                        sh.total[29] = __int_as_float(rgbSize);
+                        sh.total[30] = __int_as_float((int)sg);
+                        // what gn_sigma records at the mid-iteration point, from the integer columns
+                        sh.rgb_sigma_last = (int)sg;
+                        sh.rgb_count_last = rgbSize;
+                        sh.res.lastRGBCount = (float)rgbSize;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    GN_STAMP(rec, 6);
+                    GN_PHASE(7);
+                    if(GEN && rec && RGB && !RGB_ONLY)
+                    {
+                        rec->rgb_count = __float_as_int(sh.total[29]);
+                        rec->rgb_sigma = __float_as_int(sh.total[30]);
+                    }
+                    if(warp0) warp_update_fast(sh, ICP, RGB, L.icp_weight, rec, t_start);
+                    GN_STAMP(rec, 7);
+                    GN_PHASE(8);
+                    if(GEN && rec) ntr++;
+                }
                 step++;
-                GN_STAMP(rec, 6);
-                if(L.rgb && !L.rgb_only && threadIdx.x == 32)
-                {
-                    // what gn_sigma records at the mid-iteration point, from the folded integer columns
-                    const int rgbSize = __float_as_int(sh.total[29]), sigma = __float_as_int(sh.total[30]);
-                    sh.rgb_sigma_last = sigma;
-                    sh.rgb_count_last = rgbSize;
-                    sh.res.lastRGBCount = (float)rgbSize;
-                }
-                if(rec && L.rgb && !L.rgb_only)
-                {
-                    rec->rgb_count = __float_as_int(sh.total[29]);
-                    rec->rgb_sigma = __float_as_int(sh.total[30]);
-                }
-
-                if(warp0)
-                    warp_update(sh, L.icp, L.rgb, L.icp_weight, rec, t_start);
-                else if(threadIdx.x < 64)
-                    warp_stats(sh, L.icp, L.rgb, L.icp_weight);   // lastA / lastb / ICP error: off the solving warp
-                GN_STAMP(rec, 7);
-                if(rec) ntr++;
                 __syncthreads();
+                GN_PHASE(9);
             }
         }
 
-        if(threadIdx.x == 0) seq_end(sh, L.rgb, L.rgb_only, leader ? &results[seq] : nullptr);
+        if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
+        __syncthreads();
+        if(threadIdx.x == 0) seq_end(sh, RGB, RGB_ONLY, leader ? &results[seq] : nullptr);
         if(rank == 0 && host_results && warp0)   // `leader` is thread 0 of the group's first CTA: all of its warp 0 copies
         {
             // The result block also goes straight to mapped host memory, followed by a per-sequence flag the host polls: the caller
@@ -838,39 +987,66 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             __syncwarp();
             if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + seq) = host_seqno;
         }
-        if(leader && L.trace) trace_count[seq] = ntr;
+        if(GEN && leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();
     }
-    if(leader)
+    GN_PHASE(10);
+    if(PH && blockIdx.x == 0 && threadIdx.x < 12)
     {
-        ctl->base[group] = target;   // every CTA of the group ends with the same target
-        ctl->sum_base[group] = sum_running;
+        __syncwarp();
+        atomicAdd(&ctl->phase_cycles[threadIdx.x], (unsigned long long)wk.ph[threadIdx.x]);
+        if(threadIdx.x == 0) atomicAdd(&ctl->phase_cycles[12], 1ull);
     }
+    if(leader) ctl->step[group] = step;   // every CTA of the group ends with the same count
+    if(threadIdx.x == 0 && wk.timeouts) atomicAdd(&ctl->timeouts, 1u);
 }
 
-// ------------------------------------------------------------------ host side
-size_t gn_state_bytes(int batch)
+// the kernel variant of a launch
+typedef void (*GnKernel)(const GnLaunch, GnCtl *, const GnSeqIn *, const GnSeqIn, unsigned long long *, GnResult *, slam_step_record *, int *, const int, const int,
+                         GnResult *, unsigned *, const unsigned);
+static GnKernel gn_pick_kernel(const GnLaunch & L, bool general, bool phases)
 {
+    if(general || phases)
+    {
+        // the general variants always account the phases (they are not the tuned path)
+        if(L.rgb_only) return general ? k_gn_persistent<false, true, true, true, true> : k_gn_persistent<false, true, true, false, true>;
+        if(L.icp && L.rgb) return general ? k_gn_persistent<true, true, false, true, true> : k_gn_persistent<true, true, false, false, true>;
+        return general ? k_gn_persistent<true, false, false, true, true> : k_gn_persistent<true, false, false, false, true>;
+    }
+    if(L.rgb_only) return k_gn_persistent<false, true, true, false, false>;
+    if(L.icp && L.rgb) return k_gn_persistent<true, true, false, false, false>;
+    return k_gn_persistent<true, false, false, false, false>;
+}
+static const GnKernel kAllGnKernels[] = {
+    k_gn_persistent<false, true, true, true, true>,   k_gn_persistent<true, true, false, true, true>,   k_gn_persistent<true, false, false, true, true>,
+    k_gn_persistent<false, true, true, false, true>,  k_gn_persistent<true, true, false, false, true>,  k_gn_persistent<true, false, false, false, true>,
+    k_gn_persistent<false, true, true, false, false>, k_gn_persistent<true, true, false, false, false>, k_gn_persistent<true, false, false, false, false>,
+};
+// ------------------------------------------------------------------ host side
+size_t gn_state_bytes(int batch, int num_sms)
+{
+    const int groups = batch >= num_sms ? num_sms : batch;
     size_t b = 0;
     b += (sizeof(GnCtl) + 255) / 256 * 256;
     b += (sizeof(GnSeqIn) * batch + 255) / 256 * 256;
-    b += (size_t)kGnMaxCtas * 2 * kGnPartialStride * 4;
+    b += kRingBytes * groups;
     b += (sizeof(GnResult) * batch + 255) / 256 * 256;
     b += (sizeof(slam_step_record) * kGnMaxTrace * batch + 255) / 256 * 256;
     b += ((size_t)4 * batch + 255) / 256 * 256;
     return b;
 }
 
-void gn_bind_state(GnDevice & d, char * base, int batch)
+void gn_bind_state(GnDevice & d, char * base, int batch, int num_sms)
 {
+    const int groups = batch >= num_sms ? num_sms : batch;
     d.batch = batch;
     char * p = base;
     d.ctl = (GnCtl *)p;
     p += (sizeof(GnCtl) + 255) / 256 * 256;
     d.seq_in = (GnSeqIn *)p;
     p += (sizeof(GnSeqIn) * batch + 255) / 256 * 256;
-    d.partials = (float *)p;
-    p += (size_t)kGnMaxCtas * 2 * kGnPartialStride * 4;
+    d.ring = (unsigned long long *)p;
+    p += kRingBytes * groups;
     d.results = (GnResult *)p;
     p += (sizeof(GnResult) * batch + 255) / 256 * 256;
     d.trace = (slam_step_record *)p;
@@ -904,24 +1080,112 @@ void gn_release(GnDevice & d)
     d.h_stage = nullptr;
 }
 
+static int gn_init_device(GnDevice & d)
+{
+    if(d.h_stage) return SLAM_OK;
+    SLAM_CUDA_TRY(cudaMallocHost((void **)&d.h_stage, d.stage_bytes));
+    int dev = 0;
+    SLAM_CUDA_TRY(cudaGetDevice(&dev));
+    SLAM_CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    int coop = 0;
+    SLAM_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if(!coop)
+    {
+        set_last_error("device does not support cooperative launch");
+        return SLAM_ERR_UNSUPPORTED;
+    }
+    if(d.num_sms > kGnMaxCtas) d.num_sms = kGnMaxCtas;
+    int optin = 0;
+    SLAM_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    size_t static_smem = 0;
+    for(GnKernel k : kAllGnKernels)
+    {
+        cudaFuncAttributes fa;
+        SLAM_CUDA_TRY(cudaFuncGetAttributes(&fa, (const void *)k));
+        if(fa.sharedSizeBytes > static_smem) static_smem = fa.sharedSizeBytes;
+    }
+    d.smem_limit = optin - (int)static_smem - 1024;
+    if(d.smem_limit < 0) d.smem_limit = 0;
+    for(GnKernel k : kAllGnKernels) SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_limit));
+    d.phases = getenv("SLAM_GN_PHASES") != nullptr;
+    const char * pd = getenv("SLAM_GN_POLL_DELAY");
+    d.poll_delay = pd ? atoi(pd) : 300;
+    return SLAM_OK;
+}
+
+bool gn_make_plan(GnDevice & d, GnLaunch & L)
+{
+    if(gn_init_device(d) != SLAM_OK) d.smem_limit = 0;
+    const int G = gn_group_size(d.num_sms, L.batch);
+    static const bool no_resident = getenv("SLAM_GN_STREAMED") != nullptr;   // development aid: force the streamed path
+    int off = 0;
+    auto take = [&](int bytes) {
+        const int o = off;
+        off = (off + bytes + 15) & ~15;
+        return o;
+    };
+    // candidates in order of benefit: level 0 carries most iterations and pixels
+    int cap_state = 0;
+    bool all_rgb_resident = true;
+    for(int l = 0; l < L.levels; l++)
+    {
+        LevelPlan & pl = L.plan[l];
+        const int plane = L.geom[l].rows * L.geom[l].cols;
+        pl.nseg = (plane + 31) / 32;
+        pl.P = G;
+        pl.segs_per_cta = 0;
+        pl.cap = 0;
+        pl.off_icp = pl.off_rgb = 0;
+        pl.resident = 0;
+        if(L.iterations[l] <= 0) continue;
+        int P = (pl.nseg + kGnWarps - 1) / kGnWarps;
+        if(P > G) P = G;
+        const int segs = (pl.nseg + P - 1) / P;
+        const int nslots = (segs + kGnWarps - 1) / kGnWarps;
+        const int cap = nslots * kGnThreads;
+        const int need = (L.icp ? 24 * cap : 0) + (L.rgb ? 12 * cap : 0);
+        const int state_now = L.rgb ? 12 * (cap > cap_state ? cap : cap_state) : 0;
+        const int state_before = L.rgb ? 12 * cap_state : 0;
+        const bool fits = !no_resident && nslots <= kMaxStageSlots && L.geom[l].cols <= 2048 && L.geom[l].rows <= 2048 && off + need + 64 + (state_now - state_before) + state_before <= d.smem_limit;
+        if(fits)
+        {
+            pl.resident = 1;
+            pl.P = P;
+            pl.segs_per_cta = segs;
+            pl.cap = cap;
+            if(L.icp) pl.off_icp = take(24 * cap);
+            if(L.rgb) pl.off_rgb = take(12 * cap);
+            if(cap > cap_state) cap_state = cap;
+        }
+        else if(L.rgb)
+            all_rgb_resident = false;
+    }
+    L.off_state = L.rgb ? take(12 * cap_state) : 0;
+    L.so3_resident = 0;
+    L.so3_P = G;
+    L.off_so3 = 0;
+    if(L.so3 && L.levels >= 3)
+    {
+        const int N = L.geom[2].rows * L.geom[2].cols;
+        int P = (N + kGnThreads - 1) / kGnThreads;
+        if(P > G) P = G;
+        L.so3_P = P;
+        const int bytes = 2 * ((N + 15) & ~15);
+        if(!no_resident && off + bytes <= d.smem_limit)
+        {
+            L.so3_resident = 1;
+            L.off_so3 = take(bytes);
+        }
+    }
+    L.dyn_bytes = off;
+    L.poll_delay = d.poll_delay;
+    return all_rgb_resident;
+}
+
 // Fill the pinned staging image of the per-sequence input blocks (pointers + prior pose).
 int gn_stage_inputs(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnSeqIn ** out)
 {
-    if(!d.h_stage)
-    {
-        SLAM_CUDA_TRY(cudaMallocHost((void **)&d.h_stage, d.stage_bytes));
-        int dev = 0;
-        SLAM_CUDA_TRY(cudaGetDevice(&dev));
-        SLAM_CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
-        int coop = 0;
-        SLAM_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        if(!coop)
-        {
-            set_last_error("device does not support cooperative launch");
-            return SLAM_ERR_UNSUPPORTED;
-        }
-        if(d.num_sms > kGnMaxCtas) d.num_sms = kGnMaxCtas;
-    }
+    if(int rc = gn_init_device(d)) return rc;
     GnSeqIn * in = reinterpret_cast<GnSeqIn *>(d.h_stage);
     memset(in, 0, sizeof(GnSeqIn) * L.batch);
     for(int b = 0; b < L.batch; b++)
@@ -958,14 +1222,14 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     GnLaunch Lc = L;
     GnCtl * ctl = d.ctl;
     const GnSeqIn * seq_in = d.seq_in;
-    float * partials = d.partials;
+    unsigned long long * ring = d.ring;
     GnResult * results = d.results;
     slam_step_record * trace = d.trace;
     int * trace_count = d.trace_count;
     GnSeqIn seq0 = in[0];
     // h_flags != nullptr: h_results / h_flags are mapped pinned memory the kernel writes itself (device view == host pointer under UVA)
     GnResult * host_results = h_flags ? h_results : nullptr;
-    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &partials, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno};
+    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(d.profiling)
     {
@@ -975,7 +1239,11 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         SLAM_CUDA_TRY(cudaEventCreate(&e1));
         SLAM_CUDA_TRY(cudaEventRecord(e0, stream));
     }
-    SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_gn_persistent, dim3(G * groups), dim3(kGnThreads), args, 0, stream));
+    // the tuned variant needs every level (and the SO3 images) resident and no step trace
+    bool general = L.trace || L.full_corres || (L.so3 && !L.so3_resident);
+    for(int l = 0; l < L.levels; l++) general = general || (L.iterations[l] > 0 && !L.plan[l].resident);
+    const GnKernel kernel = gn_pick_kernel(L, general, d.phases);
+    SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
     if(d.profiling)
     {
         SLAM_CUDA_TRY(cudaEventRecord(e1, stream));

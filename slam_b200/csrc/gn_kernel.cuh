@@ -6,10 +6,25 @@
 namespace slam {
 
 constexpr int kGnThreads = 512;
-constexpr int kGnMaxCtas = 256;        // >= SM count of any target part (B200: 148)
-constexpr int kGnPartialStride = 64;   // floats per CTA per buffer: [0..31] phase A, [32..63] phase B
+constexpr int kGnWarps = kGnThreads / 32;
+constexpr int kGnMaxCtas = 255;        // >= SM count of any target part (B200: 148); the arrival count of a reduction word has 8 bits
 constexpr int kGnMaxTrace = 64;        // step records kept per sequence
-constexpr int kSlotChunk = 5;          // pixels per thread and level that stay register-resident (640x480 on 148 CTAs: 5)
+
+// ---- the inter-CTA all-reduce: fixed-point words in L2 -------------------------------------------------------------------
+// Every reduced column is carried by two 64-bit words (integer part | fraction * 2^48 of each CTA's fp32 partial sum), each
+// with the number of CTAs that have contributed in its low 8 bits: ONE relaxed atomic add per word publishes the data and
+// the arrival together, and the readers poll the words themselves (one trip through L2 instead of store + fence + arrival +
+// poll + fold; integer addition makes the sums independent of the arrival order, i.e. deterministic).  A ring of four word
+// sets is used round-robin by consecutive steps; the set of step s + 2 is cleared during the final wait of step s.
+constexpr int kRingSlots = 4;
+constexpr int kWIcp = 0;               // 29 columns x 2 words: JtJJtrSE3 of icpStep
+constexpr int kWRgb = 58;              // 29 columns x 2 words: JtJJtrSE3 of rgbStep
+constexpr int kWSo3 = 116;             // 11 columns x 2 words: JtJJtrSO3
+constexpr int kWMid = 138;             // RGB correspondence count (+ 2^32 per CTA whose squared-residual sum is non-zero)
+constexpr int kWSigma = 139;           // squared-residual sum of the RGB association (int)
+constexpr int kRingWords = 140;
+constexpr int kWordStride = 32;        // in 64-bit units: the words are 256 B apart (different L2 slices)
+constexpr size_t kRingBytes = (size_t)kRingSlots * kRingWords * kWordStride * 8;
 
 // CTAs per sequence group for a batch on a device with num_sms SMs (must match gn_enqueue).
 inline int gn_group_size(int num_sms, int batch) { return batch >= num_sms ? 1 : num_sms / batch; }
@@ -37,11 +52,25 @@ struct GnSeqIn
 
 struct GnCtl
 {
-    // one 64-bit word per CTA group, never reset: high half = arrival counter, low half = running sum of what the
-    // arriving CTAs contribute at the mid-iteration barrier (RGB correspondence count, see group_barrier_sum)
-    unsigned long long barrier[kGnMaxCtas];
-    unsigned base[kGnMaxCtas];      // arrival counter at the end of the previous launch (written by the group leader)
-    unsigned sum_base[kGnMaxCtas];  // running sum at the end of the previous launch
+    unsigned step[kGnMaxCtas + 1];   // per CTA group: reduction steps done so far (position in the ring), carried across launches
+    unsigned timeouts;               // polls that gave up (a lost arrival would otherwise hang the GPU): non-zero = results invalid
+    unsigned long long phase_cycles[16];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
+};
+
+// How one pyramid level is mapped onto the CTAs of a group.  Resident levels keep the pose-independent operands of their
+// pixels in shared memory for the whole frame: the CTA owns every P-th 32-pixel segment of the image, and the pixels that can
+// take part at all (valid current vertex + normal for ICP; the pose-independent half of the RGB association for RGB) are
+// compacted into dense lists, so no lane idles on a dead pixel.  Non-resident levels (image too large for shared memory) stream
+// their operands from L2 every iteration.
+struct LevelPlan
+{
+    int resident;        // operands staged in shared memory
+    int P;               // CTAs of the group that take part (small levels: fewer CTAs, fewer arrivals)
+    int nseg;            // 32-pixel segments of the level
+    int segs_per_cta;    // segments a participating CTA owns at most
+    int cap;             // capacity of the CTA's lists (entries)
+    int off_icp;         // byte offsets into the dynamic shared memory: ICP list, 6 float planes of cap entries
+    int off_rgb;         // RGB list: nextDepth (float), gradients (2 x s16), x | y << 11 | intensity << 22 (u32), cap entries each
 };
 
 struct GnLaunch
@@ -50,11 +79,18 @@ struct GnLaunch
     LevelGeom geom[SLAM_MAX_LEVELS];
     int iterations[SLAM_MAX_LEVELS];
     bool icp, rgb, rgb_only, so3, trace, full_corres;
-    bool derive_gradients;   // no derivative images were made: single-chunk groups derive them from nextImage in registers
+    bool derive_gradients;   // no derivative images were made: resident levels derive them from nextImage while staging
     float icp_weight;
     float dist_thresh, angle_thresh;
     float sobel_scale, max_depth_delta;
     float min_scale[SLAM_MAX_LEVELS];
+    // shared-memory plan (gn_make_plan)
+    LevelPlan plan[SLAM_MAX_LEVELS];
+    int off_state;           // phase A -> phase B state of the RGB entries (3 words per entry), shared by all levels
+    int so3_resident, so3_P; // SO3 pre-alignment: both level-2 images in shared memory; participating CTAs
+    int off_so3;
+    int dyn_bytes;
+    int poll_delay;          // cycles between posting a contribution and the first poll
 };
 
 struct GnDevice
@@ -62,15 +98,18 @@ struct GnDevice
     // device
     GnCtl * ctl = nullptr;
     GnSeqIn * seq_in = nullptr;
-    float * partials = nullptr;
+    unsigned long long * ring = nullptr;   // [groups][kRingSlots][kRingWords] words, kWordStride apart
     GnResult * results = nullptr;
     slam_step_record * trace = nullptr;
     int * trace_count = nullptr;
     // host
-    char * h_stage = nullptr;       // pinned image of [GnCtl | GnSeqIn x batch]
+    char * h_stage = nullptr;       // pinned image of [GnSeqIn x batch]
     size_t stage_bytes = 0;
     int batch = 0;
     int num_sms = 0;
+    int smem_limit = 0;             // dynamic shared memory the persistent kernel may use
+    int poll_delay = 0;
+    bool phases = false;            // SLAM_GN_PHASES: launch the variants with per-phase cycle accounting
     bool so3_swapped = false;
     // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)
     bool profiling = false;
@@ -81,9 +120,12 @@ struct GnDevice
 
 int gn_fold_profile(GnDevice & d);
 
-size_t gn_state_bytes(int batch);
-void gn_bind_state(GnDevice & d, char * base, int batch);
+size_t gn_state_bytes(int batch, int num_sms);
+void gn_bind_state(GnDevice & d, char * base, int batch, int num_sms);
 int gn_stage_inputs(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnSeqIn ** out);
+// Fill the shared-memory plan of a launch (L.geom / levels / icp / rgb / so3 set): which levels are resident, list capacities,
+// offsets.  Returns true when every RGB level is resident (no derivative images needed from memory).
+bool gn_make_plan(GnDevice & d, GnLaunch & L);
 // h_flags != nullptr: zero-copy completion -- the kernel writes h_results (mapped pinned memory) itself and then stores seqno into
 // h_flags[seq]; otherwise the results follow with a D2H copy on `stream`.
 int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const float * trans, const float * rot, GnResult * h_results,

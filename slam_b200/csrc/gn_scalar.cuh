@@ -8,6 +8,8 @@
 
 namespace slam {
 
+constexpr int kGnPartialStride = 64;   // floats of the folded sums: [0..31] ICP / SO3, [32..63] RGB
+
 struct GnShared
 {
     // parameters of the running iteration (warp 0 writes, everyone reads after a sync)
@@ -22,6 +24,7 @@ struct GnShared
     double K[9], Kinv[9];   // intrinsics of the running level (and of level 2 during SO3)
     double A[36], b[6], x[6], Rinc[9], newRt[12], Mi[9], KR[9], tinv[3];
     double aug[2][42];      // ping-pong buffers of the 6x7 Gauss-Jordan elimination
+    double Ab[28];          // combined system of the running step (27 entries, upper-triangle order of the 6x7 augmented system)
     int solve_ok;
     int stop_level, so3_done;   // batched streaming engine only: level whose iterations were cut short (rgbOnly), SO3 loop finished
     int rgb_sigma_last, rgb_count_last;   // operands of lastRGBError (computed once, at the end)

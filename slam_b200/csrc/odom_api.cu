@@ -696,7 +696,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     ArenaPlan plan;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
     const size_t pose_off = plan.take(sizeof(float) * 12 * h->batch);
-    const size_t gn_off = plan.take(gn_state_bytes(h->batch));
+    const size_t gn_off = plan.take(gn_state_bytes(h->batch, h->num_sms));
     const size_t be_off = h->batch >= kBatchEngineMin ? plan.take(batch_state_bytes(h->batch, h->geom, h->levels)) : 0;
     h->arena_bytes = plan.off;
     SLAM_CUDA_TRY(cudaMalloc((void **)&h->arena, h->arena_bytes));
@@ -707,7 +707,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     h->seq_stride = h->batch > 1 ? (size_t)((char *)h->seq[1].depth[0] - (char *)h->seq[0].depth[0]) : 0;
     h->d_poses12 = (float *)(h->arena + pose_off);
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_poses12, sizeof(float) * 12 * h->batch));
-    gn_bind_state(h->gn, h->arena + gn_off, h->batch);
+    gn_bind_state(h->gn, h->arena + gn_off, h->batch, h->num_sms);
     if(h->batch >= kBatchEngineMin)
     {
         batch_bind_state(h->be, h->arena + be_off, h->batch, h->geom, h->levels, h->gn.seq_in, h->gn.results);
@@ -856,13 +856,22 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
         return SLAM_ERR_UNSUPPORTED;
     }
-    // Derivative images are only materialised when something reads them from memory: a test tap / trace, or groups
-    // whose per-thread pixel sets do not fit the register-resident chunk.  Otherwise the persistent kernel derives
-    // the two gradients of its own pixels from nextImage (same arithmetic, bit-identical).
     const bool streaming = h->batch >= kBatchEngineMin && h->trace_level < 2;   // many sequences: lock-step streaming launches
-    const int G = gn_group_size(h->num_sms, h->batch);
-    const int nslots0 = (h->geom[0].rows * h->geom[0].cols + G * kGnThreads - 1) / (G * kGnThreads);
-    const bool derive = rgb && !h->trace_on && !streaming && nslots0 <= kSlotChunk;
+    GnLaunch L = {};
+    L.levels = h->levels;
+    L.batch = h->batch;
+    for(int l = 0; l < h->levels; l++) L.geom[l] = h->geom[l];
+    default_iterations(h, pyramid, fast_odom, L.iterations);
+    L.icp = icp;
+    L.rgb = rgb;
+    L.rgb_only = rgb_only != 0;
+    L.so3 = so3 != 0;
+    // shared-memory plan of the persistent kernel: which levels keep their operands resident
+    const bool all_resident = streaming ? false : gn_make_plan(h->gn, L);
+    // Derivative images are only materialised when something reads them from memory: a test tap / trace, or a level that
+    // streams its operands.  Otherwise the persistent kernel derives the two gradients of its own pixels from nextImage
+    // while staging them (same arithmetic, bit-identical).
+    const bool derive = rgb && !h->trace_on && !streaming && all_resident;
     h->be.cand_ready = false;
     if(rgb && !derive)
     {
@@ -895,16 +904,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         h->launches++;
     }
 
-    GnLaunch L = {};
     L.derive_gradients = derive;
-    L.levels = h->levels;
-    L.batch = h->batch;
-    for(int l = 0; l < h->levels; l++) L.geom[l] = h->geom[l];
-    default_iterations(h, pyramid, fast_odom, L.iterations);
-    L.icp = icp;
-    L.rgb = rgb;
-    L.rgb_only = rgb_only != 0;
-    L.so3 = so3 != 0;
     L.icp_weight = icp_weight;
     L.dist_thresh = h->p.dist_thresh;
     L.angle_thresh = h->p.angle_thresh;
@@ -1174,6 +1174,17 @@ extern "C" int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long 
         h->gn.kernel_ms = 0.0;
         h->gn.kernel_launches = 0;
     }
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long * out16, int reset)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(out16);
+    if(int rc = set_device(h)) return rc;
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    SLAM_CUDA_TRY(cudaMemcpy(out16, h->gn.ctl->phase_cycles, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+    if(reset) SLAM_CUDA_TRY(cudaMemset(h->gn.ctl->phase_cycles, 0, sizeof(unsigned long long) * 16));
     return SLAM_OK;
 }
 

@@ -126,6 +126,7 @@ def load_library():
     lib.slam_odom_score_poses.argtypes = [vp, i, i, i, fp, fp, fp, fp, fp, fp]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
+    lib.slam_odom_get_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
     lib.slam_odom_stream.argtypes = [vp]
     lib.slam_odom_stream.restype = vp
     lib.slam_op_workspace_bytes.restype = C.c_size_t
@@ -347,6 +348,14 @@ class RGBDOdometry:
         ms, n = C.c_double(0), C.c_longlong(0)
         _check(self.lib, self.lib.slam_odom_get_profile(self._h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
+
+    PHASES = ("staging", "so3", "step set-up", "rgb assoc", "icp map+reduce", "count wait", "rgb products+reduce", "sums wait", "solve", "end barrier", "tail")
+
+    def get_phase_cycles(self, reset=False):
+        """-> ({phase: SM cycles of the persistent kernel's leading CTA}, launches) accumulated since the last reset."""
+        out = (C.c_ulonglong * 16)()
+        _check(self.lib, self.lib.slam_odom_get_phase_cycles(self._h, out, int(reset)))
+        return {name: int(out[k]) for k, name in enumerate(self.PHASES)}, int(out[12])
 
     @property
     def stream(self) -> int:

@@ -482,8 +482,11 @@ def test_batch_equals_single_sequences(setup):
     ob.initICP(depth, 3.0)
     ob.initRGB(rgba)
     tb, rb = ob.getIncrementalTransformation(poses[:, :3, 3].copy(), poses[:, :3, :3].copy(), False, 10.0, True, False, False)
+    # A sequence of a batch runs on a third of the CTAs with streamed operands, a single sequence on all of them with
+    # resident lists: the fp32 partial sums differ (free by contract), which after 19 steps is a few ulp of the pose
+    # (translations of ~3 m: 1 ulp = 2.4e-7).  The bar is half of the north-star's per-step 1e-5.
     for b in range(B):
-        assert np.abs(tb[b] - singles[b][0]).max() < 1e-6 and np.abs(rb[b] - singles[b][1]).max() < 1e-6, f"sequence {b}"
+        assert np.abs(tb[b] - singles[b][0]).max() < 5e-6 and np.abs(rb[b] - singles[b][1]).max() < 5e-6, f"sequence {b}"
     ob.close()
 
 

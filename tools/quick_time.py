@@ -35,6 +35,12 @@ def bench(name, odo, n=200, **kw):
         odo.set_profiling(False)
         if nl:
             extra = f"  gn kernel {ms / nl * 1e3:8.1f} us/launch"
+        odo.get_phase_cycles(reset=True)
+        for i in range(50):
+            run_frame(odo, frames[i % NF], **kw)
+        ph, nl = odo.get_phase_cycles(reset=True)
+        if nl:
+            extra += "\n      cycles/frame: " + ", ".join(f"{k} {v / nl:.0f}" for k, v in ph.items()) + f"  (sum {sum(ph.values()) / nl:.0f})"
     print(f"{name:40s} {dt*1e6:9.1f} us/frame  {1/dt:9.1f} fps{extra}", flush=True)
 
 import os
