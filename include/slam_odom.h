@@ -211,9 +211,11 @@ long long slam_odom_launch_count(slam_odom_t h);
 int slam_odom_set_profiling(slam_odom_t h, int enable);
 int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_kernel_launches, int reset);
 /* SM cycles the leading CTA of the persistent kernel spent per phase, summed over the launches since the handle was created
- * (or since the last reset): [0] staging, [1] SO3 loop, [2] step set-up, [3] RGB association + count post, [4] ICP products +
- * block reduction + post, [5] wait for the global count, [6] RGB products + block reduction + post, [7] wait for all sums,
- * [8] solve, [9] end-of-step barrier, [10] tail, [12] launches.  Synchronises the handle's stream. */
+ * (or since the last reset): [0] staging, [1] rest of the SO3 loop, [2] step set-up, [3] RGB association + count post, [4] ICP
+ * products, [5] their block reduction + post + wait for the global count, [6] RGB products + block reduction + post, [7] wait for
+ * all sums, [8] solve, [9] end-of-step barrier, [10] tail, [11] SO3 map, [12] SO3 block reduction + post, [13] SO3 wait for the
+ * sums, [14] SO3 update, [15] launches.  Only the variants launched with SLAM_GN_PHASES=1 (or the step trace) count.
+ * Synchronises the handle's stream. */
 int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long out16[16], int reset);
 /* The stream the handle runs on (cudaStream_t), e.g. to record the caller's own events on it. */
 void * slam_odom_stream(slam_odom_t h);

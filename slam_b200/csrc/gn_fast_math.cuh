@@ -7,7 +7,7 @@
 //   * the 6x6 system is eliminated WITHOUT divisions on the chain (fraction-free Gauss-Jordan on a power-of-two
 //     prescaled system: rows are multiplied by the pivot instead of the pivot row being divided; the six divisions that
 //     remain are independent and happen once, at the end);
-//   * the rotation increment uses the series of sin(t)/t and (1 - cos t)/t^2 in t^2 (|increment| <= 0.5 rad, far above any
+//   * the rotation increment uses the series of sin(t)/t and (1 - cos t)/t^2 in t^2 (|increment| <= 0.1 rad, far above any
 //     Gauss-Newton step of a tracked frame; larger angles take the textbook route), no square root, no division;
 //   * the products with K and K^-1 use their zero pattern;
 //   * everything is FMA-contracted.
@@ -106,20 +106,14 @@ __device__ __forceinline__ void rodrigues_fast(const double wx, const double wy,
 {
     const double xx = wx * wx, yy = wy * wy, zz = wz * wz;
     const double t2 = xx + yy + zz;
-    if(t2 > 0.25)   // uniform; never on a tracked frame
+    if(t2 > 0.01)   // uniform; 0.1 rad per Gauss-Newton step never happens on a tracked frame
     {
         rodrigues_textbook(wx, wy, wz, R);
         return;
     }
-    // series in t2, 10 terms: truncation below 1e-25 for t2 <= 0.25
-    double A = -1.0 / 121645100408832000.0;    // -1/19!
-    double B = -1.0 / 2432902008176640000.0;   // -1/20!
-    A = __fma_rn(A, t2, 1.0 / 355687428096000.0);      // 1/17!
-    B = __fma_rn(B, t2, 1.0 / 6402373705728000.0);     // 1/18!
-    A = __fma_rn(A, t2, -1.0 / 1307674368000.0);       // -1/15!
-    B = __fma_rn(B, t2, -1.0 / 20922789888000.0);      // -1/16!
-    A = __fma_rn(A, t2, 1.0 / 6227020800.0);           // 1/13!
-    B = __fma_rn(B, t2, 1.0 / 87178291200.0);          // 1/14!
+    // series in t2, 7 terms: truncation below 1e-25 for t2 <= 0.01
+    double A = 1.0 / 6227020800.0;            // 1/13!
+    double B = 1.0 / 87178291200.0;           // 1/14!
     A = __fma_rn(A, t2, -1.0 / 39916800.0);            // -1/11!
     B = __fma_rn(B, t2, -1.0 / 479001600.0);           // -1/12!
     A = __fma_rn(A, t2, 1.0 / 362880.0);               // 1/9!
@@ -268,83 +262,171 @@ __device__ __forceinline__ int se3_index(const int i, const int j)
 // RGBDOdometryef.cpp:509-575 on warp 0: combine the two systems (lastA = A_rgb + w^2 A_icp, lastb = b_rgb + w b_icp), solve,
 // update resultRt, derive the next iteration's parameters.  icp sums = total[0..28], rgb sums = total[32..60].
 // The combined entries stay in sh.Ab (27 doubles, upper triangle order): lastA / lastb of the step for the statistics.
+//
+// One warp runs this between two reductions while the other fifteen wait, and it runs it from the instruction caches' slow
+// side: straight-line code of a single warp is fetched at ~3 cycles per instruction from the 32 KB L1.5 and ~6.5 from L2
+// (tools/micro/icache.cu), so what counts is the NUMBER of instructions.  Everything after the elimination is therefore laid
+// out across the lanes (one output entry per lane, operands through shared memory) in three stages instead of being evaluated
+// redundantly by all lanes: ~5x fewer instructions than the all-lanes form, at the price of three shared-memory round trips.
 __device__ __forceinline__ void warp_update_fast(GnShared & sh, const bool icp, const bool rgb, const float icpWeight, slam_step_record * rec, const long long t_start)
 {
     const int lane = threadIdx.x & 31;
     const int j = lane < 7 ? lane : 6;
 #define GN_FSTAMP(idx) do { if(rec) rec->t_solve[idx] = (unsigned)(clock64() - t_start); } while(0)
-    // ---- entry `lane` of the combined system
+    // ---- entry `lane` of the combined system -> 6x7 matrix (row stride 8) in shared memory, both triangles
     if(lane < 27)
     {
+        int i = 0, rem = lane;
+        while(rem >= 7 - i)
+        {
+            rem -= 7 - i;
+            i++;
+        }
+        const int jj = i + rem;
         const float vi = sh.total[lane];
         const float vr = sh.total[32 + lane];
-        // which column: entries 6, 12, 17, 21, 24, 26 are the b column (weight w), the rest A (weight w^2)
-        const bool is_b = (lane == 6 || lane == 12 || lane == 17 || lane == 21 || lane == 24 || lane == 26);
         const double w = icpWeight;
-        const double ww = is_b ? w : w * w;
-        sh.Ab[lane] = (icp && rgb) ? smath::add((double)vr, smath::mul(ww, (double)vi)) : (icp ? (double)vi : (double)vr);
+        const double ww = (jj == 6) ? w : w * w;
+        const double v = (icp && rgb) ? smath::add((double)vr, smath::mul(ww, (double)vi)) : (icp ? (double)vi : (double)vr);
+        sh.Ab[lane] = v;
+        sh.Wsys[i * 8 + jj] = v;
+        if(jj < 6) sh.Wsys[jj * 8 + i] = v;
     }
     __syncwarp();
     double c[6];
 #pragma unroll
-    for(int i = 0; i < 6; i++) c[i] = sh.Ab[se3_index(i, j)];
+    for(int i = 0; i < 6; i++) c[i] = sh.Wsys[i * 8 + j];
+    // largest diagonal entry, to 2^-20: positive doubles order like their high words (a negative or NaN entry makes the
+    // maximum absurd and the test below fail, which is the right outcome)
+    const unsigned dhi = __reduce_max_sync(0xffffffffu, lane < 6 ? (unsigned)__double2hiint(sh.Wsys[lane * 9]) : 0u);
+    bool ok = dhi > 0u && dhi < 0x7ff00000u;
+    const double floor_d = __hiloint2double((int)dhi, 0) * 1e-9;
     GN_FSTAMP(0);
-    double x[6];
-    const bool ok = warp_solve6_fraction_free(c, x);
+    // ---- fraction-free Gauss-Jordan (see warp_solve6_fraction_free): rows rotate, the pivot row is always c[0]
+    double prod = 1.0;
+#pragma unroll 1
+    for(int k = 0; k < 6; k++)
+    {
+        double colk[6];
+#pragma unroll
+        for(int i = 0; i < 6; i++) colk[i] = shfl_d(c[i], k);
+        const double p = colk[0];
+        ok = ok && (p > floor_d * prod);
+        const double sk = __hiloint2double(0x7fe00000 - (__double2hiint(p) & 0x7ff00000), 0);
+        const double ps = p * sk;
+        const double s2 = (j < k) ? 0.0 : c[0] * sk;
+        const double keep = c[0];
+#pragma unroll
+        for(int i = 0; i < 5; i++) c[i] = __fma_rn(c[i + 1], ps, -(colk[i + 1] * s2));
+        c[5] = keep;
+        prod *= ps;
+    }
+    // ---- x_i = b_i / a_ii: the columns go back to shared memory, lane i < 6 divides
+    if(lane < 7)
+    {
+#pragma unroll
+        for(int i = 0; i < 6; i++) sh.Wsys[i * 8 + lane] = c[i];
+    }
+    __syncwarp();
+    if(lane < 6)
+    {
+        const double d = sh.Wsys[lane * 9], b = sh.Wsys[lane * 8 + 6];
+        const double r = rcp_newton(d);
+        const double q0 = b * r;
+        sh.x[lane] = __fma_rn(__fma_rn(-d, q0, b), r, q0);   // one residual correction: within an ulp of the quotient
+    }
+    __syncwarp();
     GN_FSTAMP(1);
     if(!ok)   // uniform: every lane saw the same pivots
     {
-        __syncwarp();
         if(lane == 0) solve_fallback(sh, icp, rgb, icpWeight);
         __syncwarp();
-#pragma unroll
-        for(int i = 0; i < 6; i++) x[i] = sh.x[i];
     }
-    // ---- incremental rotation of the step (odom/utils.h:16-52)
-    double Rinc[9];
-    rodrigues_fast(x[3], x[4], x[5], Rinc);
-    GN_FSTAMP(2);
-    // ---- resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), rows 0..2
-    // (resultRt and the intrinsics are fetched only now: held across the elimination they would starve it of registers)
-    double Rt[12], Mo[9];
-#pragma unroll
-    for(int q = 0; q < 12; q++) Rt[q] = sh.resultRt[q];
-#pragma unroll
-    for(int q = 0; q < 9; q++) Mo[q] = sh.Mi[q];
-    double M[12];
-#pragma unroll
-    for(int i = 0; i < 3; i++)
-#pragma unroll
-        for(int q = 0; q < 4; q++)
+    // ---- incremental rotation of the step (odom/utils.h:16-52), every lane; lane 0 publishes it
+    {
+        double Rinc[9];
+        rodrigues_fast(sh.x[3], sh.x[4], sh.x[5], Rinc);
+        if(lane == 0)
         {
-            double s = __fma_rn(Rinc[i * 3 + 2], Rt[2 * 4 + q], __fma_rn(Rinc[i * 3 + 1], Rt[1 * 4 + q], Rinc[i * 3 + 0] * Rt[0 * 4 + q]));
-            if(q == 3) s += x[i];
-            M[i * 4 + q] = s;
+#pragma unroll
+            for(int q = 0; q < 9; q++) sh.Rinc[q] = Rinc[q];
         }
-    // inverse of the new linear part: (Rinc R)^-1 = R^-1 Rinc^T (Rinc is a rotation to the last bit; resultRt.inverse(),
-    // RGBDOdometryef.cpp:422, without a determinant and a division on the chain)
-    double Mi[9];
-#pragma unroll
-    for(int i = 0; i < 3; i++)
-#pragma unroll
-        for(int q = 0; q < 3; q++)
-            Mi[i * 3 + q] = __fma_rn(Mo[i * 3 + 2], Rinc[q * 3 + 2], __fma_rn(Mo[i * 3 + 1], Rinc[q * 3 + 1], Mo[i * 3 + 0] * Rinc[q * 3 + 0]));
+    }
+    __syncwarp();
+    GN_FSTAMP(2);
+    // ---- stage 1.  lanes 0..11: resultRt <- [Rinc | x[0:3]; 0 0 0 1] * resultRt (odom/utils.h:54-68), entry (i, q) of rows 0..2;
+    //      lanes 12..20: inverse of the new linear part, (Rinc R)^-1 = R^-1 Rinc^T (Rinc is a rotation to the last bit;
+    //      resultRt.inverse(), RGBDOdometryef.cpp:422, without a determinant and a division on the chain)
+    if(lane < 21)
+    {
+        const bool isM = lane < 12;
+        const int r = isM ? lane : lane - 12;
+        const int i = isM ? (r >> 2) : r / 3;
+        const int q = isM ? (r & 3) : r - 3 * i;
+        const double * pa = isM ? &sh.Rinc[i * 3] : &sh.Mi[i * 3];
+        const double * pb = isM ? &sh.resultRt[q] : &sh.Rinc[q * 3];
+        const int sb = isM ? 4 : 1;
+        double s = __fma_rn(pa[2], pb[2 * sb], __fma_rn(pa[1], pb[sb], pa[0] * pb[0]));
+        if(isM && q == 3) s += sh.x[i];
+        sh.Wm[lane] = s;
+    }
+    __syncwarp();
+    GN_FSTAMP(3);
+    // ---- stage 2.  lanes 0..2: t' = -M^-1 t; 3..11: K M^-1; 12..14: translation of float(resultRt)^-1; 15..23: Rcurr
+    //      (odom/utils.h:70-73 + RGBDOdometryef.cpp:563-575 in fp32, the expressions of smath::compose_current_pose);
+    //      every lane < 21 also files its stage-1 entry in its permanent place
     if(lane < 12)
     {
-        double v = M[0];
-#pragma unroll
-        for(int q = 1; q < 12; q++) v = (lane == q) ? M[q] : v;
-        sh.resultRt[lane] = v;
+        const double mine = sh.Wm[lane];
+        const int i = lane < 3 ? lane : (lane - 3) / 3;
+        const int q = lane < 3 ? 0 : (lane - 3) - 3 * i;
+        const double * pa = lane < 3 ? &sh.Wm[12 + 3 * i] : &sh.K[i * 3];
+        const double * pb = lane < 3 ? &sh.Wm[3] : &sh.Wm[12 + q];
+        const int sb = lane < 3 ? 4 : 3;
+        const double s = __fma_rn(pa[2], pb[2 * sb], __fma_rn(pa[1], pb[sb], pa[0] * pb[0]));
+        sh.Wk[lane] = lane < 3 ? -s : s;
+        sh.resultRt[lane] = mine;
     }
-    else if(lane < 18)
+    else if(lane < 24)
     {
-        double v = x[0];
-#pragma unroll
-        for(int q = 1; q < 6; q++) v = (lane - 12 == q) ? x[q] : v;
-        sh.x[lane - 12] = v;
+        if(lane < 21) sh.Mi[lane - 12] = sh.Wm[lane];
+        const int r = lane < 15 ? lane - 12 : lane - 15;
+        const int i = lane < 15 ? r : r / 3;
+        const int q = lane < 15 ? 0 : r - 3 * i;
+        if(lane < 15)
+        {
+            // tinv[i] = -(Rinv[i][:] . to), Rinv = Ro^T, Ro/to = float(resultRt)
+            const float a0 = (float)sh.Wm[0 * 4 + i], a1 = (float)sh.Wm[1 * 4 + i], a2 = (float)sh.Wm[2 * 4 + i];
+            sh.Wf[i] = -smath::dot3(a0, (float)sh.Wm[3], a1, (float)sh.Wm[7], a2, (float)sh.Wm[11]);
+        }
+        else
+        {
+            // Rcurr = Rprev * Rinv
+            sh.Rcurr[r] = smath::dot3(sh.Rprev[i * 3 + 0], (float)sh.Wm[q * 4 + 0], sh.Rprev[i * 3 + 1], (float)sh.Wm[q * 4 + 1], sh.Rprev[i * 3 + 2], (float)sh.Wm[q * 4 + 2]);
+        }
     }
-    GN_FSTAMP(3);
-    prepare_tail(sh, k_params(sh), M, Mi, true);
+    __syncwarp();
+    // ---- stage 3.  lanes 0..8: krk = float(K M^-1 K^-1); 9..11: kt = float(K t') (RGBDOdometryef.cpp:422-432); 12..14: tcurr
+    if(lane < 12)
+    {
+        const int i = lane < 9 ? lane / 3 : lane - 9;
+        const int q = lane < 9 ? lane - 3 * i : 0;
+        const double * pa = lane < 9 ? &sh.Wk[3 + i * 3] : &sh.K[i * 3];
+        const double * pb = lane < 9 ? &sh.Kinv[q] : &sh.Wk[0];
+        const int sb = lane < 9 ? 3 : 1;
+        const float s = (float)__fma_rn(pa[2], pb[2 * sb], __fma_rn(pa[1], pb[sb], pa[0] * pb[0]));
+        if(lane < 9)
+            sh.krk[lane] = s;
+        else
+            sh.kt[lane - 9] = s;
+    }
+    else if(lane < 15)
+    {
+        const int i = lane - 12;
+        // tcurr = Rprev * tinv + tprev
+        sh.tcurr[i] = smath::add(smath::dot3(sh.Rprev[i * 3 + 0], sh.Wf[0], sh.Rprev[i * 3 + 1], sh.Wf[1], sh.Rprev[i * 3 + 2], sh.Wf[2]), sh.tprev[i]);
+    }
+    __syncwarp();
     GN_FSTAMP(4);
     if(lane == 0)
     {

@@ -34,8 +34,8 @@ namespace slam {
 
 // Unroll factors are kept small on purpose: the per-iteration code of the whole CTA has to stay inside the 32 KB instruction
 // cache (ncu: 18 % of the instruction-cache requests missed and every phase started with an instruction-fetch stall when it did not).
-constexpr int kIcpChunk = 2;      // ICP entries in flight per thread
-constexpr int kRgbChunk = 3;      // RGB entries in flight per thread
+constexpr int kIcpChunk = 1;      // ICP entries in flight per thread
+constexpr int kRgbChunk = 1;      // RGB entries in flight per thread
 constexpr int kMaxStageSlots = 16;   // 32-pixel segments a warp stages per level at most (resident levels)
 constexpr int kSpinCap = 1 << 21; // polls before a reader gives up (~1 s)
 constexpr double kFracScale = 281474976710656.0;   // 2^48
@@ -61,7 +61,8 @@ struct GnWork
     unsigned long long mid;        // global correspondence count word
     long long sigma;               // global squared-residual sum (rgbOnly: read at the mid point)
     int timeouts;
-    unsigned ph[12];               // cycles per phase (leading CTA, thread 0)
+    unsigned ph[16];               // cycles per phase (leading CTA, thread 0)
+    unsigned long long base[kRingSlots * kRingWords];   // value of every reduction word when this CTA last consumed it
 };
 
 // ------------------------------------------------------------------ fixed-point all-reduce
@@ -93,18 +94,35 @@ __device__ __forceinline__ void post_int(unsigned long long * ring, unsigned ste
 {
     red_u64(ring_word(ring, step, w), ((unsigned long long)v << 8) + 1ull);
 }
-// Wait until `want` CTAs have contributed to the word; returns the (signed) sum.
+// The words are never cleared: every CTA remembers the value a word had when it last consumed it (wk.base, loaded from memory
+// at kernel start) and takes differences -- of the 8-bit arrival count modulo 256, of the 56-bit sum modulo 2^56.  Every CTA
+// consumes every word that is posted in a step, so the bases stay in step without any fence or clearing pass on the chain.
+__device__ __forceinline__ bool word_complete(const unsigned long long v, const unsigned long long base, const unsigned want)
+{
+    return (((unsigned)v - (unsigned)base) & 0xffu) == want;
+}
+__device__ __forceinline__ long long word_consume(const unsigned long long v, unsigned long long & base, const unsigned want)
+{
+    // the arrivals are added to the same 64-bit word: when the 8-bit count wraps, its carry lands in the sum's lowest bit
+    const long long carry = (long long)((((unsigned)base & 0xffu) + want) >> 8);
+    const long long d = ((long long)((v & ~0xffull) - (base & ~0xffull)) >> 8) - carry;
+    base = v;
+    return d;
+}
+// Wait until `want` CTAs have contributed to the word; returns the (signed) sum of their contributions.
 __device__ __forceinline__ long long poll_word(unsigned long long * ring, unsigned step, int w, unsigned want, GnWork & wk)
 {
     const unsigned long long * p = ring_word(ring, step, w);
+    unsigned long long & base = wk.base[(step & (kRingSlots - 1)) * kRingWords + w];
+    const unsigned long long b = base;
     unsigned long long v;
     int spin = 0;
     do
     {
         v = ld_u64_relaxed(p);
-    } while(((unsigned)v & 0xffu) != want && ++spin < kSpinCap);
+    } while(!word_complete(v, b, want) && ++spin < kSpinCap);
     if(spin >= kSpinCap) wk.timeouts = 1;
-    return (long long)v >> 8;
+    return word_consume(v, base, want);
 }
 __device__ __forceinline__ void spin_cycles(int cycles)
 {
@@ -134,14 +152,21 @@ __device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, u
 
 // Threads 0..127: read the ncols columns at word wbase (two words each) into dst[0..ncols-1] (floats).  t = index of this
 // thread within the reader set of the block of words, t < 2 * ncols active.  Whole warps must call (shuffle inside).
-__device__ __forceinline__ void read_columns(unsigned long long * ring, unsigned step, int wbase, int ncols, int t, unsigned want, float * dst, GnWork & wk)
+// extra_word >= 0: this thread (not one of the column readers) reads that single integer word in the same polling loop (so that
+// its trip through L2 overlaps the others') and gets the sum back in *extra_out.
+__device__ __forceinline__ void read_columns(unsigned long long * ring, unsigned step, int wbase, int ncols, int t, unsigned want, float * dst, GnWork & wk,
+                                             const int extra_word = -1, long long * extra_out = nullptr)
 {
     const bool active = t >= 0 && t < 2 * ncols;
+    const bool extra = !active && extra_word >= 0;
     double d = 0.0;
-    if(active)
+    if(active || extra)
     {
-        const long long v = poll_word(ring, step, wbase + t, want, wk);
-        d = (t & 1) ? (double)v * (1.0 / kFracScale) : (double)v;
+        const long long v = poll_word(ring, step, extra ? extra_word : wbase + t, want, wk);
+        if(extra)
+            *extra_out = v;
+        else
+            d = (t & 1) ? (double)v * (1.0 / kFracScale) : (double)v;
     }
     const double o = __shfl_xor_sync(0xffffffffu, d, 1);
     if(active && !(t & 1)) dst[t >> 1] = (float)(d + o);
@@ -243,8 +268,9 @@ __device__ __forceinline__ void rgb_candidate_state(const ResidualArgs & a, cons
 }
 
 // Stage one resident level of this CTA: lists of ICP and RGB entries in shared memory (see the header comment).
-// Two passes over the CTA's segments with the same (rolled) code: the first counts the surviving pixels per (segment, warp),
-// a block-wide prefix sum turns the counts into list positions, the second pass loads again (L1 / L2 hot) and scatters.
+// Pass 1 loads the operands of every pixel of the CTA's segments ONCE (one round trip to L2 per segment slot), stores them at
+// their uncompacted position and counts the survivors per (slot, warp); a block-wide prefix sum turns the counts into list
+// positions; pass 2 compacts the lists in place, shared memory only (entries only move towards the front, slot by slot).
 // Rolled on purpose: the kernel is bound by instruction fetch, and this code runs once per level.
 __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, const bool rgb, const int lvl, const LevelPtrs & P, const int rank, GnWork & wk, char * dyn)
 {
@@ -256,116 +282,143 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
     float * rgb_d1 = reinterpret_cast<float *>(dyn + pl.off_rgb);
     unsigned * rgb_gxy = reinterpret_cast<unsigned *>(rgb_d1 + pl.cap);
     unsigned * rgb_xyi = rgb_gxy + pl.cap;
-    ResidualArgs ra;
-    ra.minScale = L.min_scale[lvl];
-    ra.dIdx = P.dIdx; ra.dIdy = P.dIdy;
-    ra.nextDepth = P.nextDepth;
-    ra.nextImage = P.nextImage;
-    ra.cols = g.cols; ra.rows = g.rows;
-    const int nslots = (pl.segs_per_cta + kGnWarps - 1) / kGnWarps;   // <= kMaxStageSlots (gn_make_plan)
+    const int nslots = (pl.segs_per_cta + kGnWarps - 1) / kGnWarps;   // <= kMaxStageSlots (gn_make_plan); cap = segs_per_cta * 32
     const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-    for(int pass = 0; pass < 2; pass++)
     {
+        ResidualArgs ra;
+        ra.minScale = L.min_scale[lvl];
+        ra.dIdx = P.dIdx; ra.dIdy = P.dIdy;
+        ra.nextDepth = P.nextDepth;
+        ra.nextImage = P.nextImage;
+        ra.cols = g.cols; ra.rows = g.rows;
 #pragma unroll 1
         for(int m = 0; m < nslots; m++)
         {
             const int j = m * kGnWarps + wid;        // this warp's j-th segment of the CTA
             const int seg = j * pl.P + rank;
+            const int u = m * kGnThreads + (int)threadIdx.x;
             const int k1[1] = {seg * 32 + lane};
             const bool l1[1] = {j < pl.segs_per_cta && seg < pl.nseg && k1[0] < plane};
             const int kk = l1[0] ? k1[0] : 0;
             const int y1[1] = {kk / g.cols};
             const int x1[1] = {kk - y1[0] * g.cols};
-            float v[6];
             bool fi = false;
             if(icp)
             {
-                v[0] = l1[0] ? __ldg(P.vcurr + kk) : SLAM_QNAN;
-                v[3] = l1[0] ? __ldg(P.ncurr + kk) : SLAM_QNAN;
-                if(pass == 1)
+                float v[6];
+#pragma unroll
+                for(int q = 0; q < 3; q++)
                 {
-                    v[1] = l1[0] ? __ldg(P.vcurr + plane + kk) : 0.f;
-                    v[2] = l1[0] ? __ldg(P.vcurr + 2 * plane + kk) : 0.f;
-                    v[4] = l1[0] ? __ldg(P.ncurr + plane + kk) : 0.f;
-                    v[5] = l1[0] ? __ldg(P.ncurr + 2 * plane + kk) : 0.f;
+                    v[q] = l1[0] ? __ldg(P.vcurr + q * plane + kk) : SLAM_QNAN;
+                    v[3 + q] = l1[0] ? __ldg(P.ncurr + q * plane + kk) : SLAM_QNAN;
                 }
                 fi = !isnan(v[0]) && !isnan(v[3]);
+                if(j < pl.segs_per_cta)
+                {
+#pragma unroll
+                    for(int q = 0; q < 6; q++) icp_list[q * pl.cap + u] = v[q];
+                }
             }
             bool c1[1] = {false};
-            float d1[1] = {0.f};
-            unsigned g1[1] = {0u}, i1[1] = {0u};
             if(rgb)
             {
+                float d1[1];
+                unsigned g1[1], i1[1];
                 rgb_candidate_state<1>(ra, L.derive_gradients, k1, l1, x1, y1, c1, d1, g1, i1);
                 // the reference writes a DataTerm for every pixel (reduce.cu:838): pixels that never become entries get their zero once
-                if(L.full_corres && pass == 1 && l1[0] && !c1[0]) reinterpret_cast<int4 *>(P.corres)[kk] = make_int4(0, 0, 0, 0);
+                if(L.full_corres && l1[0] && !c1[0]) reinterpret_cast<int4 *>(P.corres)[kk] = make_int4(0, 0, 0, 0);
+                if(j < pl.segs_per_cta)
+                {
+                    rgb_d1[u] = d1[0];
+                    rgb_gxy[u] = g1[0];
+                    // a candidate's own intensity is non-zero (it is part of the window test): intensity 0 marks "not a candidate"
+                    rgb_xyi[u] = c1[0] ? ((unsigned)x1[0] | ((unsigned)y1[0] << 11) | (i1[0] << 22)) : 0u;
+                }
             }
             const unsigned bi = __ballot_sync(0xffffffffu, fi);
             const unsigned br = __ballot_sync(0xffffffffu, c1[0]);
-            if(pass == 0)
+            if(lane == 0)
             {
-                if(lane == 0)
-                {
-                    wk.scan_cnt[0][m * kGnWarps + wid] = __popc(bi);
-                    wk.scan_cnt[1][m * kGnWarps + wid] = __popc(br);
-                }
-            }
-            else
-            {
-                if(fi)
-                {
-                    const int pos = wk.scan_cnt[0][m * kGnWarps + wid] + __popc(bi & lt);
-#pragma unroll
-                    for(int q = 0; q < 6; q++) icp_list[q * pl.cap + pos] = v[q];
-                }
-                if(c1[0])
-                {
-                    const int pos = wk.scan_cnt[1][m * kGnWarps + wid] + __popc(br & lt);
-                    rgb_d1[pos] = d1[0];
-                    rgb_gxy[pos] = g1[0];
-                    rgb_xyi[pos] = (unsigned)x1[0] | ((unsigned)y1[0] << 11) | (i1[0] << 22);
-                }
+                wk.scan_cnt[0][m * kGnWarps + wid] = __popc(bi);
+                wk.scan_cnt[1][m * kGnWarps + wid] = __popc(br);
             }
         }
-        if(pass == 0)
+    }
+    __syncthreads();
+    if(wid < 2)
+    {
+        // exclusive prefix of the counts in (slot, warp) order, in place; warp 0: ICP, warp 1: RGB
+        constexpr int kPer = kMaxStageSlots * kGnWarps / 32;
+        const int n = nslots * kGnWarps;
+        int c[kPer], sum = 0;
+#pragma unroll
+        for(int q = 0; q < kPer; q++)
         {
-            __syncthreads();
-            if(wid < 2)
-            {
-                // exclusive prefix of the counts in (slot, warp) order, in place; warp 0: ICP, warp 1: RGB
-                constexpr int kPer = kMaxStageSlots * kGnWarps / 32;
-                const int n = nslots * kGnWarps;
-                int c[kPer], sum = 0;
+            const int idx = lane * kPer + q;
+            c[q] = idx < n ? wk.scan_cnt[wid][idx] : 0;
+            sum += c[q];
+        }
+        int incl = sum;
 #pragma unroll
-                for(int q = 0; q < kPer; q++)
-                {
-                    const int idx = lane * kPer + q;
-                    c[q] = idx < n ? wk.scan_cnt[wid][idx] : 0;
-                    sum += c[q];
-                }
-                int incl = sum;
+        for(int o = 1; o < 32; o <<= 1)
+        {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if(lane >= o) incl += up;
+        }
+        int run = incl - sum;
 #pragma unroll
-                for(int o = 1; o < 32; o <<= 1)
-                {
-                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if(lane >= o) incl += up;
-                }
-                int run = incl - sum;
+        for(int q = 0; q < kPer; q++)
+        {
+            const int idx = lane * kPer + q;
+            if(idx < n) wk.scan_cnt[wid][idx] = run;
+            run += c[q];
+        }
+        if(lane == 31)
+        {
+            if(wid == 0) wk.n_icp[lvl] = run;
+            else wk.n_rgb[lvl] = run;
+        }
+    }
+    __syncthreads();
+    // in-place compaction: slot m's entries are read, then (after a barrier) written at their final positions, which lie at or
+    // before their old ones and behind everything earlier slots wrote; later slots' entries are not touched
+#pragma unroll 1
+    for(int m = 0; m < nslots; m++)
+    {
+        const int u = m * kGnThreads + (int)threadIdx.x;
+        const bool exists = m * kGnWarps + wid < pl.segs_per_cta;
+        float v[6];
+        float d1 = 0.f;
+        unsigned gq = 0u, xyi = 0u;
+        bool fi = false;
+        if(icp && exists)
+        {
 #pragma unroll
-                for(int q = 0; q < kPer; q++)
-                {
-                    const int idx = lane * kPer + q;
-                    if(idx < n) wk.scan_cnt[wid][idx] = run;
-                    run += c[q];
-                }
-                if(lane == 31)
-                {
-                    if(wid == 0) wk.n_icp[lvl] = run;
-                    else wk.n_rgb[lvl] = run;
-                }
-            }
-            __syncthreads();
+            for(int q = 0; q < 6; q++) v[q] = icp_list[q * pl.cap + u];
+            fi = !isnan(v[0]) && !isnan(v[3]);
+        }
+        if(rgb && exists)
+        {
+            d1 = rgb_d1[u];
+            gq = rgb_gxy[u];
+            xyi = rgb_xyi[u];
+        }
+        const bool fr = rgb && (xyi >> 22) != 0u;
+        const unsigned bi = __ballot_sync(0xffffffffu, fi);
+        const unsigned br = __ballot_sync(0xffffffffu, fr);
+        __syncthreads();
+        if(fi)
+        {
+            const int pos = wk.scan_cnt[0][m * kGnWarps + wid] + __popc(bi & lt);
+#pragma unroll
+            for(int q = 0; q < 6; q++) icp_list[q * pl.cap + pos] = v[q];
+        }
+        if(fr)
+        {
+            const int pos = wk.scan_cnt[1][m * kGnWarps + wid] + __popc(br & lt);
+            rgb_d1[pos] = d1;
+            rgb_gxy[pos] = gq;
+            rgb_xyi[pos] = xyi;
         }
     }
     __syncthreads();
@@ -379,7 +432,8 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
 template <bool ICP, bool RGB, bool RGB_ONLY, bool GEN, bool PH>
 __global__ void __launch_bounds__(kGnThreads, 1)
 k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, unsigned long long * rings, GnResult * results, slam_step_record * trace,
-                int * trace_count, const int G, const int groups, GnResult * host_results, unsigned * host_flags, const unsigned host_seqno)
+                int * trace_count, const int G, const int groups, GnResult * host_results, unsigned * host_flags, const unsigned host_seqno,
+                const unsigned long long gate_target)
 {
     __shared__ GnShared sh;
     __shared__ GnWork wk;
@@ -390,30 +444,31 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     if(group >= groups) return;
 
     unsigned long long * ring = rings + (size_t)group * (kRingBytes / 8);
-    // the ring position is never reset: every launch continues where the previous one stopped (ctl->step, written by the
-    // group leader at the very end of a launch)
-    unsigned step = ctl->step[group];
+    unsigned step = 0;   // reduction steps done so far: position in the ring of word sets
 
     const long long t_start = clock64();
 #define GN_STAMP(rec, idx) do { if(GEN && rec) (rec)->t_cycles[idx] = (unsigned)(clock64() - t_start); } while(0)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool leader = (rank == 0 && threadIdx.x == 0);
     const bool warp0 = threadIdx.x < 32;
-    const bool keeper = (rank == 0 && wid == kGnWarps - 1);   // clears the ring slot of step + 2 (nothing on the chain waits for this warp)
     if(threadIdx.x == 0)
     {
         wk.cnt[0] = wk.cnt[1] = 0;
         wk.timeouts = 0;
     }
     long long ph_t = t_start;
-    if(PH && threadIdx.x < 12) wk.ph[threadIdx.x] = 0u;
+    if(PH && threadIdx.x < 16) wk.ph[threadIdx.x] = 0u;
 #define GN_PHASE(idx) do { if(PH && leader) { const long long now_ = clock64(); wk.ph[idx] += (unsigned)(now_ - ph_t); ph_t = now_; } } while(0)
 
-    // Start of every reduction step: the word set two steps ahead is cleared.  Every CTA has read the sums of step - 2 (it has
-    // posted to step - 1 since, and this CTA saw those posts), so nobody reads that set any more; the fence that orders the
-    // clearing before this CTA's own final post of the step follows in GN_STEP_FENCE().
-#define GN_STEP_BEGIN() do { if(keeper) { unsigned long long * z = ring_word(ring, step + 2, 0); for(int c = lane; c < kRingWords; c += 32) z[(size_t)c * kWordStride] = 0ull; } } while(0)
-#define GN_STEP_FENCE() do { if(keeper) __threadfence(); } while(0)
+    // the reduction words as the previous launch left them (nobody posts before every CTA of the group has passed its first
+    // wait, and that needs this CTA's own post)
+    for(int w = threadIdx.x; w < kRingSlots * kRingWords; w += kGnThreads) wk.base[w] = ld_u64_relaxed(ring + (size_t)w * kWordStride);
+    __syncthreads();
+    // ... which has to hold for a CTA that starts late as well: every CTA checks in once its bases are loaded, and nobody posts
+    // before all have (the check is made after the staging, when it has long been true)
+    if(threadIdx.x == 0) red_u64(&ctl->arrived[group], 1ull);
+    bool gate_open = false;
+#define GN_GATE() do { if(!gate_open) { if(threadIdx.x == 0) { int spin_ = 0; while(ld_u64_relaxed(&ctl->arrived[group]) < gate_target && ++spin_ < kSpinCap) {} if(spin_ >= kSpinCap) wk.timeouts = 1; } __syncthreads(); gate_open = true; } } while(0)
 
     for(int seq = group; seq < L.batch; seq += groups)
     {
@@ -474,6 +529,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             }
             __syncthreads();
         }
+        GN_GATE();
         GN_PHASE(0);
 
         // ------------------------------------------------ SO3 pre-alignment, level 2
@@ -492,7 +548,6 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 #pragma unroll 1
             for(int it = 0; it < 10; it++)
             {
-                GN_STEP_BEGIN();
                 if(rank < Pn)
                 {
                     So3Args a;
@@ -529,18 +584,21 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 #pragma unroll
                         for(int q = 0; q < 11; q++) acc[q] = a11[q];
                     }
-                    GN_STEP_FENCE();
+                    GN_PHASE(11);
                     cta_reduce_post(acc, sh, ring, step, kWSo3, 11);
                 }
+                GN_PHASE(12);
                 if(warp0)
                 {
                     spin_cycles(L.poll_delay);
                     read_columns(ring, step, kWSo3, 11, threadIdx.x, (unsigned)Pn, sh.total, wk);
                     __syncwarp();
+                    GN_PHASE(13);
                     slam_step_record * rec = (GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
                     if(GEN && rec) memset(rec, 0, sizeof(*rec));
                     warp_so3_update_fast(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R in shared memory
                     if(GEN && rec) ntr++;
+                    GN_PHASE(14);
                 }
                 step++;
                 __syncthreads();
@@ -584,7 +642,6 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 #pragma unroll 1
             for(int j = 0; j < L.iterations[lvl]; j++)
             {
-                GN_STEP_BEGIN();
                 slam_step_record * rec = nullptr;
                 if(GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace)
                 {
@@ -734,6 +791,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 // Two map + block-reduction passes share ONE copy of the reduction code: pass 0 = ICP products (reduce.cu:282-416;
                 // the count's trip through L2 overlaps this map), pass 1 = RGB Jacobian products (reduce.cu:494-624).
                 bool stop_now = false;
+                unsigned long long mid_peek = 0ull;
 #pragma unroll 1
                 for(int pass = ICP ? 0 : 1; pass < (RGB ? 2 : 1); pass++)
                 {
@@ -821,7 +879,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         // ---------------- the global correspondence count: every CTA (rgbOnly decides the early exit on it)
                         if(threadIdx.x == 0)
                         {
-                            wk.mid = (unsigned long long)poll_word(ring, step, kWMid, (unsigned)Pn, wk);
+                            unsigned long long & mbase = wk.base[(step & (kRingSlots - 1)) * kRingWords + kWMid];
+                            if(ICP && word_complete(mid_peek, mbase, (unsigned)Pn))
+                                wk.mid = (unsigned long long)word_consume(mid_peek, mbase, (unsigned)Pn);
+                            else
+                                wk.mid = (unsigned long long)poll_word(ring, step, kWMid, (unsigned)Pn, wk);
                             if(RGB_ONLY) wk.sigma = poll_word(ring, step, kWSigma, (unsigned)Pn, wk);
                         }
                         __syncthreads();
@@ -917,9 +979,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         }
                         GN_STAMP(rec, 5);
                     }
+                    // the count word is fetched while the block reduction runs: by now every CTA has posted to it long ago,
+                    // so the value is normally complete when the reduction is done and nobody waits for this trip through L2
+                    if(ICP && RGB && pass == 0 && threadIdx.x == 0) mid_peek = ld_u64_relaxed(ring_word(ring, step, kWMid));
                     if(part)
                     {
-                        if(pass == (RGB ? 1 : 0)) GN_STEP_FENCE();   // before this CTA's last post of the step
                         cta_reduce_post(acc, sh, ring, step, pass ? kWRgb : kWIcp, 29);
                     }
                     if(pass == 1) GN_PHASE(6);
@@ -935,16 +999,17 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 {
                     spin_cycles(L.poll_delay);
                     const int t = (int)threadIdx.x;
+                    long long sg = 0;
+                    const int sigma_word = (RGB && !RGB_ONLY && t == 127) ? kWSigma : -1;   // thread 127 is never a column reader
                     if(ICP && RGB)
                     {
                         const int kind = t >= 58 ? 1 : 0;
-                        read_columns(ring, step, kind ? kWRgb : kWIcp, 29, t - 58 * kind, (unsigned)Pn, sh.total + 32 * kind, wk);
+                        read_columns(ring, step, kind ? kWRgb : kWIcp, 29, t - 58 * kind, (unsigned)Pn, sh.total + 32 * kind, wk, sigma_word, &sg);
                     }
                     else
-                        read_columns(ring, step, ICP ? kWIcp : kWRgb, 29, t, (unsigned)Pn, sh.total + (ICP ? 0 : 32), wk);
+                        read_columns(ring, step, ICP ? kWIcp : kWRgb, 29, t, (unsigned)Pn, sh.total + (ICP ? 0 : 32), wk, sigma_word, &sg);
                     if(RGB && !RGB_ONLY && t == 127)
                     {
-                        const long long sg = poll_word(ring, step, kWSigma, (unsigned)Pn, wk);
                         const int rgbSize = (int)(wk.mid & 0xffffffffull);
                         sh.total[29] = __int_as_float(rgbSize);
                         sh.total[30] = __int_as_float((int)sg);
@@ -991,19 +1056,18 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         __syncthreads();
     }
     GN_PHASE(10);
-    if(PH && blockIdx.x == 0 && threadIdx.x < 12)
+    if(PH && blockIdx.x == 0 && threadIdx.x < 15)
     {
         __syncwarp();
         atomicAdd(&ctl->phase_cycles[threadIdx.x], (unsigned long long)wk.ph[threadIdx.x]);
-        if(threadIdx.x == 0) atomicAdd(&ctl->phase_cycles[12], 1ull);
+        if(threadIdx.x == 0) atomicAdd(&ctl->phase_cycles[15], 1ull);
     }
-    if(leader) ctl->step[group] = step;   // every CTA of the group ends with the same count
     if(threadIdx.x == 0 && wk.timeouts) atomicAdd(&ctl->timeouts, 1u);
 }
 
 // the kernel variant of a launch
 typedef void (*GnKernel)(const GnLaunch, GnCtl *, const GnSeqIn *, const GnSeqIn, unsigned long long *, GnResult *, slam_step_record *, int *, const int, const int,
-                         GnResult *, unsigned *, const unsigned);
+                         GnResult *, unsigned *, const unsigned, const unsigned long long);
 static GnKernel gn_pick_kernel(const GnLaunch & L, bool general, bool phases)
 {
     if(general || phases)
@@ -1109,7 +1173,7 @@ static int gn_init_device(GnDevice & d)
     for(GnKernel k : kAllGnKernels) SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_limit));
     d.phases = getenv("SLAM_GN_PHASES") != nullptr;
     const char * pd = getenv("SLAM_GN_POLL_DELAY");
-    d.poll_delay = pd ? atoi(pd) : 300;
+    d.poll_delay = pd ? atoi(pd) : 600;
     return SLAM_OK;
 }
 
@@ -1142,7 +1206,7 @@ bool gn_make_plan(GnDevice & d, GnLaunch & L)
         if(P > G) P = G;
         const int segs = (pl.nseg + P - 1) / P;
         const int nslots = (segs + kGnWarps - 1) / kGnWarps;
-        const int cap = nslots * kGnThreads;
+        const int cap = segs * 32;   // list capacity: every pixel of the CTA's segments
         const int need = (L.icp ? 24 * cap : 0) + (L.rgb ? 12 * cap : 0);
         const int state_now = L.rgb ? 12 * (cap > cap_state ? cap : cap_state) : 0;
         const int state_before = L.rgb ? 12 * cap_state : 0;
@@ -1229,7 +1293,10 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     GnSeqIn seq0 = in[0];
     // h_flags != nullptr: h_results / h_flags are mapped pinned memory the kernel writes itself (device view == host pointer under UVA)
     GnResult * host_results = h_flags ? h_results : nullptr;
-    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno};
+    // every launch raises the check-in counter of each group by G (GN_GATE)
+    d.launch_no++;
+    unsigned long long gate_target = d.launch_no * (unsigned long long)G;
+    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno, &gate_target};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(d.profiling)
     {
@@ -1243,6 +1310,13 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     bool general = L.trace || L.full_corres || (L.so3 && !L.so3_resident);
     for(int l = 0; l < L.levels; l++) general = general || (L.iterations[l] > 0 && !L.plan[l].resident);
     const GnKernel kernel = gn_pick_kernel(L, general, d.phases);
+    static const bool debug = getenv("SLAM_ODOM_DEBUG") != nullptr;
+    if(debug && d.launch_no < 3)
+    {
+        fprintf(stderr, "gn_enqueue: general %d phases %d dyn %d of %d, so3 resident %d P %d, levels:", (int)general, (int)d.phases, L.dyn_bytes, d.smem_limit, L.so3_resident, L.so3_P);
+        for(int l = 0; l < L.levels; l++) fprintf(stderr, " [%d: it %d res %d P %d cap %d]", l, L.iterations[l], L.plan[l].resident, L.plan[l].P, L.plan[l].cap);
+        fprintf(stderr, "\n");
+    }
     SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
     if(d.profiling)
     {

@@ -15,7 +15,8 @@ constexpr int kGnMaxTrace = 64;        // step records kept per sequence
 // with the number of CTAs that have contributed in its low 8 bits: ONE relaxed atomic add per word publishes the data and
 // the arrival together, and the readers poll the words themselves (one trip through L2 instead of store + fence + arrival +
 // poll + fold; integer addition makes the sums independent of the arrival order, i.e. deterministic).  A ring of four word
-// sets is used round-robin by consecutive steps; the set of step s + 2 is cleared during the final wait of step s.
+// sets is used round-robin by consecutive steps; the words are never cleared -- the readers take differences against the value
+// they consumed last (sums modulo 2^56, counts modulo 256).
 constexpr int kRingSlots = 4;
 constexpr int kWIcp = 0;               // 29 columns x 2 words: JtJJtrSE3 of icpStep
 constexpr int kWRgb = 58;              // 29 columns x 2 words: JtJJtrSE3 of rgbStep
@@ -52,7 +53,7 @@ struct GnSeqIn
 
 struct GnCtl
 {
-    unsigned step[kGnMaxCtas + 1];   // per CTA group: reduction steps done so far (position in the ring), carried across launches
+    unsigned long long arrived[kGnMaxCtas + 1];   // per CTA group: CTAs that have checked in, summed over all launches (GN_GATE)
     unsigned timeouts;               // polls that gave up (a lost arrival would otherwise hang the GPU): non-zero = results invalid
     unsigned long long phase_cycles[16];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
 };
@@ -109,6 +110,7 @@ struct GnDevice
     int num_sms = 0;
     int smem_limit = 0;             // dynamic shared memory the persistent kernel may use
     int poll_delay = 0;
+    unsigned long long launch_no = 0;   // launches so far (the check-in counters grow by G per launch)
     bool phases = false;            // SLAM_GN_PHASES: launch the variants with per-phase cycle accounting
     bool so3_swapped = false;
     // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)

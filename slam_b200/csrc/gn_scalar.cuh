@@ -25,6 +25,11 @@ struct GnShared
     double A[36], b[6], x[6], Rinc[9], newRt[12], Mi[9], KR[9], tinv[3];
     double aug[2][42];      // ping-pong buffers of the 6x7 Gauss-Jordan elimination
     double Ab[28];          // combined system of the running step (27 entries, upper-triangle order of the 6x7 augmented system)
+    // lane-parallel step update (gn_fast_math.cuh): staging areas between its stages
+    double Wsys[48];        // the 6x7 combined system, row stride 8; later the eliminated columns
+    double Wm[24];          // [0..11] affine rows of the new resultRt, [12..20] inverse of its linear part
+    double Wk[12];          // [0..2] -M^-1 t, [3..11] K M^-1
+    float Wf[4];            // float(resultRt)^-1 translation
     int solve_ok;
     int stop_level, so3_done;   // batched streaming engine only: level whose iterations were cut short (rgbOnly), SO3 loop finished
     int rgb_sigma_last, rgb_count_last;   // operands of lastRGBError (computed once, at the end)

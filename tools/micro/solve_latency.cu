@@ -7,7 +7,7 @@
 namespace slam { void set_last_error(const std::string &) {} }
 using namespace slam;
 
-__global__ void k_solve(long long * cycles, int reps, int evict, const float * junk, float * sink, slam_step_record * recs)
+__global__ void __launch_bounds__(512, 1) k_solve(long long * cycles, int reps, int evict, const float * junk, float * sink, slam_step_record * recs)
 {
     __shared__ GnShared sh;
     if(threadIdx.x == 0)
@@ -18,6 +18,8 @@ __global__ void k_solve(long long * cycles, int reps, int evict, const float * j
         level_begin(sh, g);
         for(int k = 0; k < 16; k++) sh.resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
     }
+    __syncthreads();
+    if(threadIdx.x < 32) warp_prepare_fast(sh, true);
     __syncthreads();
     for(int r = 0; r < reps; r++)
     {
@@ -58,7 +60,9 @@ __global__ void k_solve(long long * cycles, int reps, int evict, const float * j
         }
         __syncthreads();
     }
-    if(threadIdx.x == 0) sink[0] = sh.krk[0] + sh.kt[0] + sh.Rcurr[0];
+    if(threadIdx.x < 9) sink[threadIdx.x] = sh.krk[threadIdx.x];
+    if(threadIdx.x < 3) { sink[9 + threadIdx.x] = sh.kt[threadIdx.x]; sink[12 + threadIdx.x] = sh.tcurr[threadIdx.x]; }
+    if(threadIdx.x < 9) sink[15 + threadIdx.x] = sh.Rcurr[threadIdx.x];
 }
 
 int main()
@@ -74,7 +78,8 @@ int main()
     for(int evict : {0, 100000})
     {
         k_solve<<<1, 512>>>(cyc, 12, evict, junk, sink, evict ? recs : nullptr);
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaError_t e = cudaGetLastError();
+        if(e == cudaSuccess) e = cudaDeviceSynchronize();
         if(e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         long long h[12];
         cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -86,6 +91,10 @@ int main()
             slam_step_record hr[12];
             cudaMemcpy(hr, recs, sizeof(hr), cudaMemcpyDeviceToHost);
             const slam_step_record & q = hr[8];
+            float hs[24];
+            cudaMemcpy(hs, sink, sizeof(hs), cudaMemcpyDeviceToHost);
+            printf("after 12 steps: krk %g %g %g | %g %g %g | %g %g %g; kt %g %g %g; tcurr %g %g %g; Rcurr[0..2] %g %g %g\n", hs[0], hs[1], hs[2], hs[3], hs[4], hs[5], hs[6], hs[7], hs[8], hs[9],
+                   hs[10], hs[11], hs[12], hs[13], hs[14], hs[15], hs[16], hs[17]);
             printf("stages of call 8 (cycles since entry): combined %u, eliminated %u, rotation %u, resultRt %u, parameters %u; x = %g %g %g %g %g %g\n", q.t_solve[0], q.t_solve[1], q.t_solve[2],
                    q.t_solve[3], q.t_solve[4], q.x[0], q.x[1], q.x[2], q.x[3], q.x[4], q.x[5]);
         }
