@@ -103,6 +103,8 @@ int slam_odom_get_incremental_transformation(slam_odom_t h, float * trans, float
 /* Asynchronous form for pipelines: enqueue only; the pose is read back by _wait(). */
 int slam_odom_get_incremental_transformation_async(slam_odom_t h, const float * trans, const float * rot, int rgb_only,
                                                    float icp_weight, int pyramid, int fast_odom, int so3);
+/* Collects the pending track.  The init_* entry points collect it themselves when they are called first (a pipelined caller
+ * may prepare frame N + 1 before this call: the image swap of frame N has then already happened); the pose is kept for this call. */
 int slam_odom_wait(slam_odom_t h, float * trans, float * rot);
 
 /* getCovariance()   (:597-600); out[36*batch] row-major */
@@ -135,6 +137,13 @@ int slam_odom_track_host(slam_odom_t h, const slam_frame_host * frame, float * t
  * the host time of staging overlaps the device time of tracking (a pipelined reader loop in one call). */
 int slam_odom_track_host_next(slam_odom_t h, const slam_frame_host * f, const slam_frame_host * next, float * trans, float * rot, int rgb_only,
                               float icp_weight, int pyramid, int fast_odom, int so3);
+/* The reference's own data flow: the sensor frame (depth, rgba) arrives in HOST memory (apps/elastic_fusion_file.cpp:301-340
+ * uploads it every frame), while the model prediction never leaves the device (it is rendered into GL textures,
+ * :366-374) -- here model_vertices4 / model_normals4 / model_rgba are DEVICE pointers and depth / rgba are host pointers
+ * (pinned for full PCIe speed).  1.8 MB cross PCIe per 640x480 frame instead of the 12.9 MB of slam_odom_track_host.
+ * `next` (may be NULL): the following frame, whose depth / rgba copies are issued behind this frame's kernels. */
+int slam_odom_track_sensor(slam_odom_t h, const slam_frame_host * f, const slam_frame_host * next, float * trans, float * rot, int rgb_only,
+                           float icp_weight, int pyramid, int fast_odom, int so3);
 /* Same sequence with all inputs already in device memory (one call per frame). */
 int slam_odom_track_device(slam_odom_t h, const slam_frame_host * frame_dev, float * trans, float * rot, int rgb_only,
                            float icp_weight, int pyramid, int fast_odom, int so3);
@@ -201,6 +210,14 @@ int slam_odom_init_icp_depth_raw(slam_odom_t h, const uint16_t * d_raw_depth, fl
  * the reference's lastICPError is sqrt(residual) / count.  Host output arrays; synchronises the handle's stream. */
 int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
                           const float * rot9n, float * residual_n, float * count_n);
+
+/* The same scoring without leaving the device: the n hypotheses (global indices index_base .. index_base + n - 1) are scored and
+ * the launch folds (lastICPError bits << 32 | global index) of each into *d_best_key (device memory, uint64) with atomicMin;
+ * lastICPError = sqrt(residual) / inliers in float32, +inf below min_inliers (the guard of lc/Ferns.cpp:275-279).  The caller sets
+ * *d_best_key to UINT64_MAX (or INT64_MAX) beforehand and, with the hypotheses sharded over several GPUs, min-all-reduces that one
+ * word (ncclMin): smallest error wins, ties go to the smaller index, whatever the number of GPUs.  Only enqueues (handle's stream). */
+int slam_odom_score_poses_best(slam_odom_t h, int seq, int level, int n, int index_base, float min_inliers, const float * prev_trans3,
+                               const float * prev_rot9, const float * trans3n, const float * rot9n, unsigned long long * d_best_key);
 
 /* Kernel-launch counter (for bench.py's gpu_launches). */
 long long slam_odom_launch_count(slam_odom_t h);

@@ -12,7 +12,7 @@
 //   * the products with K and K^-1 use their zero pattern;
 //   * everything is FMA-contracted.
 // The textbook forms (small_math.hpp: LDL^T / Gauss-Jordan with divisions, libm sin / cos, generic 3x3 products) remain the
-// ones the host-stepped loop and the replay oracle run; the two agree to ~1e-15 relative (tests compare them per step).
+// ones the host-stepped loop and the reference replay run; the two agree to ~1e-15 relative (tests compare them per step).
 #pragma once
 #include "gn_scalar.cuh"
 

@@ -39,6 +39,7 @@ struct StagingSlot
     float pose[16 * 1];
     std::vector<float> poses;
     const void * tag_depth = nullptr;   // host pointer this slot was prefetched from
+    unsigned long long generation = 0;  // staging order (the older slot is the one a stale prefetch is dropped from)
     cudaEvent_t ready = nullptr;
     bool pending = false;
     float depth_cutoff = 0, model_depth_cutoff = 0;
@@ -65,6 +66,8 @@ struct slam_odom
     unsigned short * filtered_depth = nullptr;   // [batch][H][W] output of the depth pre-filter (allocated on first use)
     char * score_ws = nullptr;        // pose-hypothesis scoring: poses | partials | tickets | results (grown on demand)
     size_t score_ws_bytes = 0;
+    float * h_score_poses = nullptr;  // pinned staging of the hypotheses
+    int score_ws_n = -1, score_ws_plane = -1;   // layout the workspace was last cleared for
     float * d_poses12 = nullptr;      // [batch][12] model poses (R row-major | t) of the batched preparation launches
     float * h_poses12 = nullptr;      // pinned staging of the same
 
@@ -79,15 +82,19 @@ struct slam_odom
     float * h_sums = nullptr;         // pinned scratch for the host-stepped loop [96]
 
     std::vector<slam_odom_stats> stats;
+    std::vector<float> last_pose;     // [batch][12]: rot9 | trans3 of the last collected track (slam_odom_wait after an implicit collection)
     std::vector<std::vector<slam_step_record>> trace;
     bool trace_on = false;
     int trace_level = 0;
     bool have_depth_tmp = false;
     bool pending_async = false;
     bool last_icp = false, last_rgb = false, last_so3 = false;
+    bool deriv_src_swapped = false;   // the frame the stale derivative images would belong to sits in lastNextImage (swap after an SO3 call)
+    bool deriv_stale = true;          // dIdx / dIdy do not belong to the current nextImage pyramid (the persistent kernel derived its own gradients)
     long long launches = 0;
 
     StagingSlot slot[2];
+    unsigned long long stage_generation = 0;
     int next_slot = 0;
     bool staging_ready = false;
 
@@ -314,6 +321,7 @@ int enqueue_derivatives(slam_odom * h, int b)
     int rc = launch_derivatives_simple(h->levels, s.nextImage, s.dIdx, s.dIdy, rows, cols, h->stream);
     if(rc) return rc;
     h->launches++;
+    if(b == h->batch - 1) h->deriv_stale = false;
     return SLAM_OK;
 }
 
@@ -637,26 +645,24 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
 
 }   // namespace
 
+static int finish_device_loop(slam_odom_t h, float * trans, float * rot);
+// The bookkeeping of an asynchronous track (the lastNextImage <-> nextImage swap of RGBDOdometryef.cpp:585-591, the statistics)
+// happens when it is collected.  Every entry point that writes one of those buffers collects a pending track first, so a
+// pipelined caller may prepare frame N + 1 before slam_odom_wait() without landing its images in the pre-swap buffers.
+static int flush_pending(slam_odom_t h)
+{
+    if(h->pending_async) return finish_device_loop(h, nullptr, nullptr);
+    return SLAM_OK;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" const char * slam_odom_version(void) { return "slam_b200 0.1 (sm_100a)"; }
 extern "C" const char * slam_odom_last_error(void) { return g_last_error.c_str(); }
 
-extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * out)
-{
-    SLAM_ARG_CHECK(params && out);
-    SLAM_ARG_CHECK(params->width > 0 && params->height > 0);
-    SLAM_ARG_CHECK(params->num_levels >= 0 && params->num_levels <= SLAM_MAX_LEVELS);
-    int ndev = 0;
-    SLAM_CUDA_TRY(cudaGetDeviceCount(&ndev));
-    if(ndev == 0)
-    {
-        set_last_error("no CUDA device: libslam_odom has no CPU fallback");
-        return SLAM_ERR_CUDA;
-    }
-    SLAM_ARG_CHECK(params->device >= 0 && params->device < ndev);
-    SLAM_CUDA_TRY(cudaSetDevice(params->device));
+extern "C" int slam_odom_destroy(slam_odom_t h);
 
-    slam_odom * h = new slam_odom();
+static int create_body(slam_odom * h, const slam_odom_params * params)
+{
     h->p = *params;
     if(h->p.dist_thresh == 0) h->p.dist_thresh = 0.10f;
     if(h->p.angle_thresh == 0) h->p.angle_thresh = sinf(20.f * 3.14159254f / 180.f);
@@ -673,7 +679,6 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
         h->geom[l].cy = params->cy / div;
         if(h->geom[l].rows < 2 || h->geom[l].cols < 2)
         {
-            delete h;
             set_last_error("image too small for the requested pyramid");
             return SLAM_ERR_ARG;
         }
@@ -729,6 +734,7 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_sums, 128 * 4));
 
     h->stats.resize(h->batch);
+    h->last_pose.assign((size_t)12 * h->batch, 0.f);
     h->trace.resize(h->batch);
     for(auto & st : h->stats)
     {
@@ -737,6 +743,34 @@ extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * o
         st.lastICPCount = st.lastRGBCount = st.lastSO3Count = (float)(params->width * params->height);
     }
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_create(const slam_odom_params * params, slam_odom_t * out)
+{
+    SLAM_ARG_CHECK(params && out);
+    SLAM_ARG_CHECK(params->width > 0 && params->height > 0);
+    SLAM_ARG_CHECK(params->num_levels >= 0 && params->num_levels <= SLAM_MAX_LEVELS);
+    int ndev = 0;
+    SLAM_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if(ndev == 0)
+    {
+        set_last_error("no CUDA device: libslam_odom has no CPU fallback");
+        return SLAM_ERR_CUDA;
+    }
+    SLAM_ARG_CHECK(params->device >= 0 && params->device < ndev);
+    SLAM_CUDA_TRY(cudaSetDevice(params->device));
+
+    slam_odom * h = new slam_odom();
+    // any failure past this point releases whatever was created so far (streams, events, arena, pinned blocks)
+    const int rc = create_body(h, params);
+    if(rc != SLAM_OK)
+    {
+        const std::string keep = g_last_error;
+        slam_odom_destroy(h);
+        g_last_error = keep;
+        return rc;
+    }
     *out = h;
     return SLAM_OK;
 }
@@ -767,6 +801,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->h_sums) cudaFreeHost(h->h_sums);
     if(h->h_poses12) cudaFreeHost(h->h_poses12);
     if(h->score_ws) cudaFree(h->score_ws);
+    if(h->h_score_poses) cudaFreeHost(h->h_score_poses);
     if(h->filtered_depth) cudaFree(h->filtered_depth);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -783,6 +818,7 @@ extern "C" int slam_odom_init_icp_depth(slam_odom_t h, const uint16_t * d_depth,
     if(int rc = check_handle(h)) return rc;
     SLAM_ARG_CHECK(d_depth);
     if(int rc = set_device(h)) return rc;
+    if(int rc = flush_pending(h)) return rc;
     const size_t row = pitch_bytes ? pitch_bytes : (size_t)h->geom[0].cols * 2;
     for(int b = 0; b < h->batch; b++)
         if(int rc = enqueue_init_icp_depth(h, b, (const uint16_t *)((const char *)d_depth + (size_t)b * row * h->geom[0].rows), pitch_bytes, depth_cutoff))
@@ -795,6 +831,7 @@ extern "C" int slam_odom_init_icp_maps(slam_odom_t h, const float * d_vertices4,
     if(int rc = check_handle(h)) return rc;
     SLAM_ARG_CHECK(d_vertices4 && d_normals4);
     if(int rc = set_device(h)) return rc;
+    if(int rc = flush_pending(h)) return rc;
     const size_t n4 = (size_t)h->geom[0].rows * h->geom[0].cols * 4;
     for(int b = 0; b < h->batch; b++)
         if(int rc = enqueue_model_maps(h, b, d_vertices4 + b * n4, d_normals4 + b * n4, false, nullptr)) return rc;
@@ -808,6 +845,7 @@ extern "C" int slam_odom_init_icp_model(slam_odom_t h, const float * d_vertices4
     if(int rc = check_handle(h)) return rc;
     SLAM_ARG_CHECK(d_vertices4 && d_normals4 && model_pose16);
     if(int rc = set_device(h)) return rc;
+    if(int rc = flush_pending(h)) return rc;
     const size_t n4 = (size_t)h->geom[0].rows * h->geom[0].cols * 4;
     for(int b = 0; b < h->batch; b++)
         if(int rc = enqueue_model_maps(h, b, d_vertices4 + b * n4, d_normals4 + b * n4, true, model_pose16 + 16 * b)) return rc;
@@ -820,6 +858,7 @@ static int init_rgb_common(slam_odom_t h, const uint8_t * d_rgba, int which)
     if(int rc = check_handle(h)) return rc;
     SLAM_ARG_CHECK(d_rgba);
     if(int rc = set_device(h)) return rc;
+    if(int rc = flush_pending(h)) return rc;
     if(which != 2 && !h->have_depth_tmp)
     {
         // RGBDOdometryef.cpp:239,245: populateRGBDData reads vmaps_tmp written by initICPModel / initICP(maps)
@@ -832,7 +871,11 @@ static int init_rgb_common(slam_odom_t h, const uint8_t * d_rgba, int which)
         SeqBuffers & s = h->seq[b];
         int rc;
         if(which == 0)
+        {
+            h->deriv_stale = true;
+            h->deriv_src_swapped = false;
             rc = enqueue_populate_rgbd(h, b, d_rgba + b * n4, s.nextDepth, s.nextImage);
+        }
         else if(which == 1)
             rc = enqueue_populate_rgbd(h, b, d_rgba + b * n4, s.lastDepth, s.lastImage);
         else
@@ -873,6 +916,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     // while staging them (same arithmetic, bit-identical).
     const bool derive = rgb && !h->trace_on && !streaming && all_resident;
     h->be.cand_ready = false;
+    h->deriv_stale = !(rgb && !derive);
     if(rgb && !derive)
     {
         int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
@@ -1015,8 +1059,13 @@ static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
         st.gn_iterations = r.gn_iterations;
         if(trans) memcpy(trans + 3 * b, r.tcurr, 12);
         if(rot) memcpy(rot + 9 * b, r.Rcurr, 36);
+        memcpy(&h->last_pose[12 * b], r.Rcurr, 36);
+        memcpy(&h->last_pose[12 * b + 9], r.tcurr, 12);
         if(h->gn.so3_swapped)
+        {
             for(int l = 0; l < h->levels; l++) std::swap(h->seq[b].lastNextImage[l], h->seq[b].nextImage[l]);
+            h->deriv_src_swapped = true;
+        }
     }
     h->gn.so3_swapped = false;
     return SLAM_OK;
@@ -1042,6 +1091,16 @@ extern "C" int slam_odom_wait(slam_odom_t h, float * trans, float * rot)
 {
     if(int rc = check_handle(h)) return rc;
     if(int rc = set_device(h)) return rc;
+    if(!h->pending_async)
+    {
+        // already collected (an init_* call for the next frame came first): hand out the pose that was kept
+        for(int b = 0; b < h->batch; b++)
+        {
+            if(rot) memcpy(rot + 9 * b, &h->last_pose[12 * b], 36);
+            if(trans) memcpy(trans + 3 * b, &h->last_pose[12 * b + 9], 12);
+        }
+        return SLAM_OK;
+    }
     return finish_device_loop(h, trans, rot);
 }
 
@@ -1095,13 +1154,10 @@ extern "C" int slam_odom_init_icp_depth_raw(slam_odom_t h, const uint16_t * d_ra
     return slam_odom_init_icp_depth(h, h->filtered_depth, 0, depth_cutoff);
 }
 
-extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
-                                     const float * rot9n, float * residual_n, float * count_n)
+// Common part of the two scoring entry points: upload the poses, launch.  best_key (device pointer, may be null): see k_score_poses.
+static int enqueue_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
+                               const float * rot9n, float ** out2_dev, unsigned long long * d_best_key, int index_base, float min_inliers)
 {
-    if(int rc = check_handle(h)) return rc;
-    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && level >= 0 && level < h->levels && n > 0 && n <= 65535);
-    SLAM_ARG_CHECK(prev_trans3 && prev_rot9 && trans3n && rot9n && residual_n && count_n);
-    if(int rc = set_device(h)) return rc;
     if(h->pending_async)
         if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
     const LevelGeom & g = h->geom[level];
@@ -1112,20 +1168,32 @@ extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, c
     {
         SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
         if(h->score_ws) cudaFree(h->score_ws);
+        if(h->h_score_poses) cudaFreeHost(h->h_score_poses);
         h->score_ws = nullptr;
+        h->h_score_poses = nullptr;
         h->score_ws_bytes = 0;
         SLAM_CUDA_TRY(cudaMalloc((void **)&h->score_ws, need));
+        SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_score_poses, pose_bytes));
         h->score_ws_bytes = need;
+        h->score_ws_n = -1;
     }
-    // the layout of the workspace depends on n: tickets must start at zero
-    SLAM_CUDA_TRY(cudaMemsetAsync(h->score_ws, 0, need, h->stream));
-    std::vector<float> poses((size_t)n * 12);
+    // the layout of the workspace depends on n (the tickets must start at zero; the kernel leaves them at zero)
+    if(h->score_ws_n != n || h->score_ws_plane != plane)
+    {
+        SLAM_CUDA_TRY(cudaMemsetAsync(h->score_ws, 0, need, h->stream));
+        h->score_ws_n = n;
+        h->score_ws_plane = plane;
+    }
+    // the pinned staging block is reused: the previous upload must have been consumed
+    SLAM_CUDA_TRY(cudaEventSynchronize(h->compute_done));
+    float * poses = h->h_score_poses;
     for(int i = 0; i < n; i++)
     {
         memcpy(&poses[(size_t)i * 12], rot9n + (size_t)i * 9, 9 * sizeof(float));
         memcpy(&poses[(size_t)i * 12 + 9], trans3n + (size_t)i * 3, 3 * sizeof(float));
     }
-    SLAM_CUDA_TRY(cudaMemcpyAsync(h->score_ws, poses.data(), (size_t)n * 12 * 4, cudaMemcpyHostToDevice, h->stream));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(h->score_ws, poses, (size_t)n * 12 * 4, cudaMemcpyHostToDevice, h->stream));
+    SLAM_CUDA_TRY(cudaEventRecord(h->compute_done, h->stream));
     SeqBuffers & s = h->seq[seq];
     float Rprev_inv[9];
     smath::mat3_inverse(prev_rot9, Rprev_inv);
@@ -1139,9 +1207,21 @@ extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, c
     a.angleThres = h->p.angle_thresh;
     a.cols = g.cols; a.rows = g.rows;
     a.vcurr = s.vcurr[level]; a.ncurr = s.ncurr[level]; a.vprev = s.vprev[level]; a.nprev = s.nprev[level];
-    float * out2 = nullptr;
-    if(int rc = launch_score_poses(a, reinterpret_cast<const float *>(h->score_ws), n, h->score_ws + pose_bytes, &out2, h->stream)) return rc;
+    if(int rc = launch_score_poses(a, reinterpret_cast<const float *>(h->score_ws), n, h->score_ws + pose_bytes, out2_dev, h->stream, d_best_key, index_base, min_inliers))
+        return rc;
     h->launches++;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float * prev_trans3, const float * prev_rot9, const float * trans3n,
+                                     const float * rot9n, float * residual_n, float * count_n)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && level >= 0 && level < h->levels && n > 0 && n <= 65535);
+    SLAM_ARG_CHECK(prev_trans3 && prev_rot9 && trans3n && rot9n && residual_n && count_n);
+    if(int rc = set_device(h)) return rc;
+    float * out2 = nullptr;
+    if(int rc = enqueue_score_poses(h, seq, level, n, prev_trans3, prev_rot9, trans3n, rot9n, &out2, nullptr, 0, 1.f)) return rc;
     std::vector<float> out((size_t)n * 2);
     SLAM_CUDA_TRY(cudaMemcpyAsync(out.data(), out2, (size_t)n * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1151,6 +1231,17 @@ extern "C" int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, c
         count_n[i] = out[2 * i + 1];
     }
     return SLAM_OK;
+}
+
+extern "C" int slam_odom_score_poses_best(slam_odom_t h, int seq, int level, int n, int index_base, float min_inliers, const float * prev_trans3,
+                                          const float * prev_rot9, const float * trans3n, const float * rot9n, unsigned long long * d_best_key)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && level >= 0 && level < h->levels && n > 0 && n <= 65535 && index_base >= 0);
+    SLAM_ARG_CHECK(prev_trans3 && prev_rot9 && trans3n && rot9n && d_best_key);
+    if(int rc = set_device(h)) return rc;
+    float * out2 = nullptr;
+    return enqueue_score_poses(h, seq, level, n, prev_trans3, prev_rot9, trans3n, rot9n, &out2, d_best_key, index_base, min_inliers);
 }
 
 extern "C" long long slam_odom_launch_count(slam_odom_t h) { return h ? h->launches : 0; }
@@ -1263,8 +1354,25 @@ extern "C" int slam_odom_tap(slam_odom_t h, int tap, int level, int seq, void * 
         case SLAM_TAP_LAST_IMAGE: src = s.lastImage[level]; break;
         case SLAM_TAP_NEXT_IMAGE: src = s.nextImage[level]; break;
         case SLAM_TAP_LASTNEXT_IMAGE: src = s.lastNextImage[level]; break;
-        case SLAM_TAP_DIDX: src = s.dIdx[level]; break;
-        case SLAM_TAP_DIDY: src = s.dIdy[level]; break;
+        case SLAM_TAP_DIDX:
+        case SLAM_TAP_DIDY:
+            if(h->deriv_stale)
+            {
+                // the last track derived its gradients in registers: produce the images now (computeDerivativeImages, utils.cu:579-638)
+                int rows[SLAM_MAX_LEVELS], cols[SLAM_MAX_LEVELS];
+                for(int l = 0; l < h->levels; l++)
+                {
+                    rows[l] = h->geom[l].rows;
+                    cols[l] = h->geom[l].cols;
+                }
+                SeqBuffers & s0 = h->seq[0];
+                if(int rc = launch_derivatives_simple(h->levels, h->deriv_src_swapped ? s0.lastNextImage : s0.nextImage, s0.dIdx, s0.dIdy, rows, cols, h->stream, h->batch, h->seq_stride))
+                    return rc;
+                h->launches++;
+                h->deriv_stale = false;
+            }
+            src = tap == SLAM_TAP_DIDX ? (const void *)s.dIdx[level] : (const void *)s.dIdy[level];
+            break;
         case SLAM_TAP_CORRES: src = s.corres[level]; break;
         case SLAM_TAP_CLOUD:
         {
@@ -1322,6 +1430,7 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         if(int rc = set_device(h)) return rc;
         if(h->pending_async)
             if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+        h->deriv_src_swapped = false;
         SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
         SLAM_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->fork_ev, 0));
         const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
@@ -1469,6 +1578,20 @@ static int stage_frame(slam_odom_t h, StagingSlot & sl, const slam_frame_host * 
     sl.depth_cutoff = f->depth_cutoff;
     sl.model_depth_cutoff = f->model_depth_cutoff;
     sl.tag_depth = f->depth;
+    sl.generation = ++h->stage_generation;
+    SLAM_CUDA_TRY(cudaEventRecord(sl.ready, cs));
+    sl.pending = true;
+    return SLAM_OK;
+}
+
+// depth + rgba only (slam_odom_track_sensor): the model prediction stays where the caller rendered it
+static int stage_sensor(slam_odom_t h, StagingSlot & sl, const slam_frame_host * f, cudaStream_t cs)
+{
+    const size_t n = (size_t)h->geom[0].rows * h->geom[0].cols * h->batch;
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.depth, f->depth, n * 2, cudaMemcpyHostToDevice, cs));
+    SLAM_CUDA_TRY(cudaMemcpyAsync(sl.rgba, f->rgba, n * 4, cudaMemcpyHostToDevice, cs));
+    sl.tag_depth = f->depth;
+    sl.generation = ++h->stage_generation;
     SLAM_CUDA_TRY(cudaEventRecord(sl.ready, cs));
     sl.pending = true;
     return SLAM_OK;
@@ -1519,7 +1642,7 @@ extern "C" int slam_odom_track_host(slam_odom_t h, const slam_frame_host * f, fl
         sl = free_slot(h);
         if(!sl)
         {
-            sl = &h->slot[0];   // drop a stale prefetch
+            sl = h->slot[0].generation <= h->slot[1].generation ? &h->slot[0] : &h->slot[1];   // drop the older stale prefetch
             SLAM_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
         }
         if(int rc = stage_frame(h, *sl, f, h->copy_stream)) return rc;
@@ -1544,7 +1667,7 @@ extern "C" int slam_odom_track_host_next(slam_odom_t h, const slam_frame_host * 
         sl = free_slot(h);
         if(!sl)
         {
-            sl = &h->slot[0];   // drop a stale prefetch
+            sl = h->slot[0].generation <= h->slot[1].generation ? &h->slot[0] : &h->slot[1];   // drop the older stale prefetch
             SLAM_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
         }
         if(int rc = stage_frame(h, *sl, f, h->copy_stream)) return rc;
@@ -1560,6 +1683,45 @@ extern "C" int slam_odom_track_host_next(slam_odom_t h, const slam_frame_host * 
         for(auto & cand : h->slot)
             if(&cand != sl && !cand.pending) other = &cand;
         if(other) rc = stage_frame(h, *other, next, h->copy_stream);   // the slot still in use by this frame's kernels is left alone
+    }
+    if(h->pending_async)
+    {
+        const int rc2 = finish_device_loop(h, trans, rot);
+        if(!rc) rc = rc2;
+    }
+    sl->pending = false;
+    return rc;
+}
+
+extern "C" int slam_odom_track_sensor(slam_odom_t h, const slam_frame_host * f, const slam_frame_host * next, float * trans, float * rot, int rgb_only,
+                                      float icp_weight, int pyramid, int fast_odom, int so3)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(f && f->depth && f->rgba && f->model_vertices4 && f->model_normals4 && f->model_rgba && f->model_pose16 && trans && rot);
+    if(int rc = set_device(h)) return rc;
+    if(int rc = ensure_staging(h)) return rc;
+    StagingSlot * sl = find_staged(h, f->depth);
+    if(!sl)
+    {
+        sl = free_slot(h);
+        if(!sl)
+        {
+            sl = h->slot[0].generation <= h->slot[1].generation ? &h->slot[0] : &h->slot[1];   // drop the older stale prefetch
+            SLAM_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+        }
+        if(int rc = stage_sensor(h, *sl, f, h->copy_stream)) return rc;
+    }
+    SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, sl->ready, 0));
+    // enqueue this frame's work, and only then spend host time on the next frame's copies: they overlap the kernels
+    int rc = track_from_device_ptrs(h, sl->depth, sl->rgba, (const float4 *)f->model_vertices4, (const float4 *)f->model_normals4, (const uchar4 *)f->model_rgba,
+                                    f->model_pose16, f->depth_cutoff, f->model_depth_cutoff, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3, true);
+    if(rc) return rc;
+    if(next && next->depth && next->rgba && !find_staged(h, next->depth))
+    {
+        StagingSlot * other = nullptr;
+        for(auto & cand : h->slot)
+            if(&cand != sl && !cand.pending) other = &cand;
+        if(other) rc = stage_sensor(h, *other, next, h->copy_stream);   // the slot still in use by this frame's kernels is left alone
     }
     if(h->pending_async)
     {

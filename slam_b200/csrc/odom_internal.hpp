@@ -69,7 +69,8 @@ int launch_rgb_residual(const ResidualArgs & a, Corres * corres, void * workspac
 int launch_rgb_step(const RgbStepArgs & a, const Corres * corres, void * workspace, float * out29, cudaStream_t s);
 int launch_so3_step(const So3Args & a, void * workspace, float * out11, cudaStream_t s);
 size_t score_workspace_bytes(int n, int plane);
-int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * workspace /* zero-initialised once */, float ** out2_dev, cudaStream_t s);
+int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * workspace /* zero-initialised once */, float ** out2_dev, cudaStream_t s,
+                       unsigned long long * best_key = nullptr, int index_base = 0, float min_inliers = 1.f);
 
 // helpers exported by prep_kernels.cu that need the full argument structs
 int launch_model_maps_simple(const float4 * vsrc, const float4 * nsrc, int rows, int cols, int levels, float * const * vdst, float * const * ndst,

@@ -154,8 +154,13 @@ int launch_icp_step(const IcpArgs & a, void * workspace, float * out29, cudaStre
 // grid = (pixel blocks, hypotheses); the maps are shared by all hypotheses and stay in L2.  Per-hypothesis last-ticket fold
 // in block order: deterministic.
 constexpr int kScoreStride = 2;
+// best_key != nullptr: the block that folds a hypothesis also turns its two sums into the reference's acceptance statistic
+// lastICPError = sqrt(residual) / inliers (RGBDOdometryef.cpp:509; +inf below min_inliers, the guard of lc/Ferns.cpp:275-279) and
+// folds (error bits << 32 | global hypothesis index) into *best_key with a 64-bit atomicMin: non-negative floats order like their
+// bit patterns, so the smallest key is the smallest error, ties to the smaller index -- on one GPU and, after a min-all-reduce of
+// that one word, on any number of them.
 __global__ void __launch_bounds__(kReduceThreads) k_score_poses(const IcpArgs a0, const float * __restrict__ poses12, float * partials, unsigned * tickets,
-                                                                float * out2)
+                                                                float * out2, unsigned long long * best_key, const int index_base, const float min_inliers)
 {
     __shared__ float s_red[2][kReduceThreads / 32];
     __shared__ int s_last;
@@ -198,11 +203,22 @@ __global__ void __launch_bounds__(kReduceThreads) k_score_poses(const IcpArgs a0
     __syncthreads();
     if(!s_last) return;
     __threadfence();
-    if(threadIdx.x < 2)
+    if(threadIdx.x < 32)
     {
         float t = 0.f;
-        for(int b = 0; b < (int)gridDim.x; b++) t += __ldcg(rows + b * kScoreStride + threadIdx.x);
-        out2[hyp * 2 + threadIdx.x] = t;
+        if(threadIdx.x < 2)
+        {
+            for(int b = 0; b < (int)gridDim.x; b++) t += __ldcg(rows + b * kScoreStride + threadIdx.x);
+            out2[hyp * 2 + threadIdx.x] = t;
+        }
+        const float cnt = __shfl_sync(0xffffffffu, t, 1);
+        if(best_key && threadIdx.x == 0)
+        {
+            float err = __fdiv_rn(__fsqrt_rn(t), cnt);   // float32 sqrt and divide, correctly rounded: what numpy computes from the same sums
+            if(!(cnt >= min_inliers) || isnan(err)) err = __int_as_float(0x7f800000);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(err) << 32) | (unsigned long long)(unsigned)(index_base + hyp);
+            atomicMin(best_key, key);
+        }
     }
     if(threadIdx.x == 0) tickets[hyp] = 0u;
 }
@@ -211,14 +227,15 @@ int score_blocks(int plane) { int g = div_up(plane, kReduceThreads * 4); return 
 
 size_t score_workspace_bytes(int n, int plane) { return (size_t)n * score_blocks(plane) * kScoreStride * 4 + (size_t)n * 4 + (size_t)n * 8 + 256; }
 
-int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * workspace, float ** out2_dev, cudaStream_t s)
+int launch_score_poses(const IcpArgs & a, const float * poses12, int n, void * workspace, float ** out2_dev, cudaStream_t s, unsigned long long * best_key,
+                       int index_base, float min_inliers)
 {
     const int plane = a.rows * a.cols;
     const int nb = score_blocks(plane);
     float * partials = reinterpret_cast<float *>(workspace);
     unsigned * tickets = reinterpret_cast<unsigned *>(partials + (size_t)n * nb * kScoreStride);
     float * out2 = reinterpret_cast<float *>(tickets + n);
-    k_score_poses<<<dim3(nb, n), kReduceThreads, 0, s>>>(a, poses12, partials, tickets, out2);
+    k_score_poses<<<dim3(nb, n), kReduceThreads, 0, s>>>(a, poses12, partials, tickets, out2, best_key, index_base, min_inliers);
     SLAM_CUDA_TRY(cudaGetLastError());
     *out2_dev = out2;
     return SLAM_OK;

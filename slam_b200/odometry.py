@@ -114,6 +114,7 @@ def load_library():
     lib.slam_odom_track_host.argtypes = [vp, C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
     lib.slam_odom_track_device.argtypes = [vp, C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
     lib.slam_odom_track_host_next.argtypes = [vp, C.POINTER(FrameHost), C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
+    lib.slam_odom_track_sensor.argtypes = [vp, C.POINTER(FrameHost), C.POINTER(FrameHost), fp, fp, i, f, i, i, i]
     lib.slam_odom_tap_bytes.argtypes = [vp, i, i]
     lib.slam_odom_tap_bytes.restype = C.c_size_t
     lib.slam_odom_tap.argtypes = [vp, i, i, i, vp, C.c_size_t]
@@ -124,6 +125,7 @@ def load_library():
     lib.slam_odom_init_icp_depth_raw.argtypes = [vp, vp, f, f]
     lib.slam_op_depth_bilateral.argtypes = [vp, i, i, f, vp, i, vp]
     lib.slam_odom_score_poses.argtypes = [vp, i, i, i, fp, fp, fp, fp, fp, fp]
+    lib.slam_odom_score_poses_best.argtypes = [vp, i, i, i, i, f, fp, fp, fp, fp, vp]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
     lib.slam_odom_get_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
@@ -240,6 +242,20 @@ class RGBDOdometry:
             rot[...] = r
         return t, r
 
+    def getIncrementalTransformationAsync(self, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3):
+        """Enqueue only (device-resident loop); collect with wait().  A pipelined caller may prepare the next frame in between."""
+        t = np.ascontiguousarray(trans, dtype=np.float32).reshape(-1).copy()
+        r = np.ascontiguousarray(rot, dtype=np.float32).reshape(-1).copy()
+        _check(self.lib, self.lib.slam_odom_get_incremental_transformation_async(self._h, _fptr(t), _fptr(r), int(bool(rgbOnly)), float(icpWeight),
+                                                                                  int(bool(pyramid)), int(bool(fastOdom)), int(bool(so3))))
+
+    def wait(self):
+        """-> (trans, rot) of the pending asynchronous track."""
+        t = np.zeros(3 * self.batch, np.float32)
+        r = np.zeros(9 * self.batch, np.float32)
+        _check(self.lib, self.lib.slam_odom_wait(self._h, _fptr(t), _fptr(r)))
+        return (t, r.reshape(3, 3)) if self.batch == 1 else (t.reshape(self.batch, 3), r.reshape(self.batch, 3, 3))
+
     def getCovariance(self):
         out = np.zeros(36 * self.batch, dtype=np.float64)
         _check(self.lib, self.lib.slam_odom_get_covariance(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
@@ -309,6 +325,17 @@ class RGBDOdometry:
             return self._track(self.lib.slam_odom_track_host, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3)
         return self._track(self.lib.slam_odom_track_host_next, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3, next_frame=next_frame)
 
+    def track_sensor(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True, next_frame=None):
+        """The reference's data flow: frame.depth / frame.rgba in (pinned) host memory, the model prediction in device memory."""
+        t, r, tp, rp = self._io_buffers()
+        t[:] = np.asarray(trans, dtype=np.float32).reshape(-1)
+        r[:] = np.asarray(rot, dtype=np.float32).reshape(-1)
+        rc = self.lib.slam_odom_track_sensor(self._h, C.byref(frame), C.byref(next_frame) if next_frame is not None else None, tp, rp, 1 if rgbOnly else 0,
+                                             float(icpWeight), 1 if pyramid else 0, 1 if fastOdom else 0, 1 if so3 else 0)
+        if rc != 0:
+            _check(self.lib, rc)
+        return t.reshape(np.shape(trans)).copy(), r.reshape(np.shape(rot)).copy()
+
     def prefetch_host(self, frame):
         _check(self.lib, self.lib.slam_odom_prefetch_host(self._h, C.byref(frame)))
 
@@ -339,6 +366,18 @@ class RGBDOdometry:
         cnt = np.zeros(len(t), np.float32)
         _check(self.lib, self.lib.slam_odom_score_poses(self._h, int(seq), int(level), len(t), _fptr(pt), _fptr(pr), _fptr(t), _fptr(r), _fptr(res), _fptr(cnt)))
         return res, cnt
+
+    def score_poses_best(self, level, prev_pose, trans_n, rot_n, key_tensor, index_base=0, min_inliers=1.0, seq=0):
+        """Enqueue the scoring of n hypotheses (global indices index_base ..) and fold the packed key of the best one into
+        key_tensor (one int64 / uint64 element in device memory, preset to its maximum) with a 64-bit atomicMin.  No read-back."""
+        prev = np.ascontiguousarray(prev_pose, dtype=np.float32)
+        pt = np.ascontiguousarray(prev[:3, 3]).copy()
+        pr = np.ascontiguousarray(prev[:3, :3]).reshape(-1).copy()
+        t = np.ascontiguousarray(trans_n, dtype=np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(rot_n, dtype=np.float32).reshape(-1, 9)
+        assert len(t) == len(r) and len(t) > 0
+        _check(self.lib, self.lib.slam_odom_score_poses_best(self._h, seq, int(level), len(t), int(index_base), float(min_inliers), _fptr(pt), _fptr(pr),
+                                                             _fptr(t), _fptr(r), _addr(key_tensor)))
 
     def set_profiling(self, on=True):
         _check(self.lib, self.lib.slam_odom_set_profiling(self._h, int(on)))

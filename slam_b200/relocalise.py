@@ -6,6 +6,11 @@ The score of a hypothesis is the reference's acceptance statistic lastICPError =
 (RGBDOdometryef.cpp:505-507), +inf when fewer than `min_inliers` pixels associate (lc/Ferns.cpp:262 rejects on the same
 two numbers).  Non-negative IEEE-754 floats order like their bit patterns, so the integer minimum of the keys is the
 minimum error, ties broken by the smaller index: the result does not depend on the number of ranks.
+
+Two forms: score_sharded() reads the per-hypothesis sums back and packs the keys on the host (parity tests look at every
+hypothesis); score_sharded_device() is the product path -- the scoring launch itself folds its block's best key into one device
+word (atomicMin, slam_odom_score_poses_best), that word is min-all-reduced in place by NCCL, and only the winning key (8 bytes)
+ever reaches the host.  broadcast_frame() replicates rank 0's frame (depth + the two predicted maps) once per frame.
 """
 from __future__ import annotations
 
@@ -66,3 +71,66 @@ def score_sharded(odo, level, prev_pose, trans_n, rot_n, rank=0, world=1, min_in
     keys = pack_keys(err, np.arange(lo, hi))
     e, i = unpack_key(best_key(keys, group, device))
     return i, e, err
+
+
+INT64_MAX = np.iinfo(np.int64).max
+
+
+def perturbed_hypotheses(gt_pose, n, sigma_t=0.05, sigma_r_deg=3.0, seed=0xBEEF):
+    """SURVEY 8(d) configs[4]: n hypotheses = gt_pose o random SE3 perturbation (translation sigma 5 cm, rotation sigma 3 deg about a
+    random axis), hypothesis 0 unperturbed.  -> (trans[n,3], rot[n,3,3]) float32; identical on every rank for the same seed."""
+    rng = np.random.default_rng(seed)
+    gt = np.asarray(gt_pose, np.float64)
+    T = np.empty((n, 3), np.float32)
+    R = np.empty((n, 3, 3), np.float32)
+    for i in range(n):
+        if i == 0:
+            dR, dt = np.eye(3), np.zeros(3)
+        else:
+            w = rng.normal(scale=np.deg2rad(sigma_r_deg), size=3)
+            th = np.linalg.norm(w)
+            k = w / th if th > 0 else np.array([1.0, 0, 0])
+            K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+            dR = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+            dt = rng.normal(scale=sigma_t, size=3)
+        R[i] = (gt[:3, :3] @ dR).astype(np.float32)
+        T[i] = (gt[:3, 3] + gt[:3, :3] @ dt).astype(np.float32)
+    return T, R
+
+
+def broadcast_frame(tensors, src=0, group=None):
+    """Replicate the frame of rank `src` (device tensors: depth, predicted vertices / normals, ...) on every rank, in place."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+
+
+def score_sharded_device(odo, level, prev_pose, trans_n, rot_n, key_tensor, rank=0, world=1, min_inliers=1.0, group=None, stream=None):
+    """Product path: this rank's block of hypotheses is scored on its GPU, the launch leaves the block's best packed key in
+    key_tensor (one int64 on the device), one NCCL min-all-reduce of that word picks the winner of all ranks.  Nothing but the
+    final 8 bytes is read back.  stream: torch stream wrapping the handle's CUDA stream (the collective is ordered behind the
+    scoring launch on it).  -> (best global index, its error)."""
+    import torch
+    import torch.distributed as dist
+    trans_n = np.asarray(trans_n, np.float32).reshape(-1, 3)
+    rot_n = np.asarray(rot_n, np.float32).reshape(-1, 3, 3)
+    lo, hi = shard_range(len(trans_n), rank, world)
+    ctx = torch.cuda.stream(stream) if stream is not None else _null_context()
+    with ctx:
+        key_tensor.fill_(INT64_MAX)
+        if hi > lo:
+            odo.score_poses_best(level, prev_pose, trans_n[lo:hi], rot_n[lo:hi], key_tensor, index_base=lo, min_inliers=min_inliers)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(key_tensor, op=dist.ReduceOp.MIN, group=group)
+        key = int(key_tensor.item())
+    e, i = unpack_key(key)
+    return i, e
+
+
+class _null_context:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

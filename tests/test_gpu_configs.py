@@ -202,3 +202,102 @@ def test_pose_hypothesis_scores_match_reference_icp_step(built, ref_lib, icl_seq
         res2, cnt2 = odo.score_poses(level, model, T, R)
         assert np.array_equal(res, res2) and np.array_equal(cnt, cnt2)
     odo.close()
+
+
+def test_device_side_best_key_equals_host_packing_for_any_sharding(built, icl_sequence):
+    """slam_odom_score_poses_best (product path of configs[4]): the scoring launch folds the packed key of its block's best
+    hypothesis into one device word.  Whatever the number of blocks the 256 hypotheses are cut into (1, 2, 4, 8 "ranks",
+    emulated one after the other on this GPU with the min taken over their words), the winner is the one the host-side packing
+    of all per-hypothesis sums picks: same index, same float32 error bits."""
+    import torch
+    from slam_b200 import RGBDOdometry
+    from slam_b200.relocalise import INT64_MAX, icp_error, pack_keys, perturbed_hypotheses, shard_range, unpack_key
+    scene, intr, poses = icl_sequence
+    fr = frame_pair(scene, poses, 640)
+    d = to_device(fr)
+    torch.cuda.synchronize()
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+    odo.initICPModel(d["mv"], d["mn"], MODEL_CUTOFF, d["model_pose"])
+    odo.initICP(d["depth"], DEPTH_CUTOFF)
+    model = fr["model_pose"].astype(np.float32)
+    N = 256
+    T, R = perturbed_hypotheses(fr["gt_pose"], N)     # SURVEY 8(d): sigma_t 5 cm, sigma_r 3 deg, seed 0xBEEF, hypothesis 0 = gt
+    assert np.allclose(T[0], fr["gt_pose"][:3, 3], atol=1e-7) and np.allclose(R[0], fr["gt_pose"][:3, :3], atol=1e-7)
+    stream = torch.cuda.ExternalStream(odo.stream)
+    for level in (0, 2):
+        min_inl = 1400 >> (2 * level)
+        res, cnt = odo.score_poses(level, model, T, R)
+        keys = pack_keys(icp_error(res, cnt, min_inl), np.arange(N))
+        want = unpack_key(int(keys.min()))
+        for world in (1, 2, 4, 8):
+            words = []
+            for rank in range(world):
+                lo, hi = shard_range(N, rank, world)
+                key = torch.full((1,), INT64_MAX, dtype=torch.int64, device="cuda:0")
+                with torch.cuda.stream(stream):
+                    odo.score_poses_best(level, model, T[lo:hi], R[lo:hi], key, index_base=lo, min_inliers=min_inl)
+                    words.append(int(key.item()))
+            got = unpack_key(min(words))
+            assert got[1] == want[1] and np.float32(got[0]).view(np.uint32) == np.float32(want[0]).view(np.uint32), f"level {level}, {world} blocks: {got} vs {want}"
+        assert want[1] == 0, f"level {level}: hypothesis {want[1]} beats the true pose"
+    # a guard nobody passes leaves the word at +inf | smallest index
+    key = torch.full((1,), INT64_MAX, dtype=torch.int64, device="cuda:0")
+    with torch.cuda.stream(stream):
+        odo.score_poses_best(0, model, T[:4], R[:4], key, index_base=10, min_inliers=1e9)
+        e, i = unpack_key(int(key.item()))
+    assert np.isinf(e) and i == 10
+    odo.close()
+
+
+def _nccl_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from slam_b200 import RGBDOdometry
+    from slam_b200.relocalise import INT64_MAX, broadcast_frame, perturbed_hypotheses, score_sharded, score_sharded_device
+    from tests.support import make_scene
+    scene, intr = make_scene(640, 480)
+    poses = scene.trajectory(1000)
+    # every rank renders a DIFFERENT frame; rank 0's is the one that counts
+    fr = frame_pair(scene, poses, 300 + 37 * rank)
+    dev = f"cuda:{rank}"
+    d = to_device(fr, dev)
+    meta = torch.from_numpy(np.concatenate([fr["model_pose"].reshape(-1), fr["gt_pose"].reshape(-1)]).astype(np.float64)).to(dev)
+    broadcast_frame([d["depth"], d["mv"], d["mn"], meta])
+    meta = meta.cpu().numpy()
+    model, gt = meta[:16].reshape(4, 4).astype(np.float32), meta[16:].reshape(4, 4)
+    odo = RGBDOdometry(intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"], device=rank)
+    odo.initICPModel(d["mv"], d["mn"], MODEL_CUTOFF, model)
+    odo.initICP(d["depth"], DEPTH_CUTOFF)
+    T, R = perturbed_hypotheses(gt, 256)
+    key = torch.full((1,), INT64_MAX, dtype=torch.int64, device=dev)
+    stream = torch.cuda.ExternalStream(odo.stream, device=dev)
+    res = {}
+    for level in (0, 2):
+        best, err = score_sharded_device(odo, level, model, T, R, key, rank, world, min_inliers=1400 >> (2 * level), stream=stream)
+        alone = score_sharded(odo, level, model, T, R, 0, 1, min_inliers=1400 >> (2 * level))
+        res[level] = (best, float(np.float32(err)), alone[0], float(np.float32(alone[1])))
+    out[rank] = res
+    odo.close()
+    dist.destroy_process_group()
+
+
+def test_hypotheses_sharded_over_two_gpus_with_nccl(built):
+    """configs[4] on hardware: two ranks, two GPUs, rank 0's frame broadcast with NCCL, 128 hypotheses scored per rank, ONE
+    min-all-reduce of a device word; every rank must name the winner a single GPU names when it scores all 256 alone."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, 29611, out), nprocs=2, join=True)
+    assert len(out) == 2
+    for level in (0, 2):
+        b0, e0, a0, ae0 = out[0][level]
+        b1, e1, a1, ae1 = out[1][level]
+        assert (b0, e0) == (b1, e1) == (a0, ae0) == (a1, ae1), f"level {level}: {out[0][level]} vs {out[1][level]}"

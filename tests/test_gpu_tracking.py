@@ -670,6 +670,77 @@ def test_host_buffer_entry_points_equal_device_entry_point(setup):
         o.close()
 
 
+def test_sensor_entry_point_equals_device_entry_point(setup):
+    """slam_odom_track_sensor (the reference's data flow: depth + RGBA from pinned host memory, model prediction in device
+    memory, the next sensor frame's copies issued behind this frame's kernels) == slam_odom_track_device, bit for bit."""
+    t = setup["torch"]
+    scene, poses = setup["scene"], setup["poses"]
+    i = setup["intr"]
+    ks = (500, 501, 502, 503)
+    frames = [frame_pair(scene, poses, k) for k in ks]
+    first = scene.render_frame(poses[ks[0] - 1])[1]
+    mk = lambda: setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    dev, sen = mk(), mk()
+    pin = lambda a: t.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).pin_memory()
+    hfr = [{k: pin(f[k]) for k in ("depth", "rgba")} for f in frames]
+    dfr = [to_device(f) for f in frames]
+    t.cuda.synchronize()
+    for o in (dev, sen):
+        o.initFirstRGB(t.from_numpy(first).to("cuda:0"))
+    sframes = [sen.make_frame(h["depth"], h["rgba"], d["mv"], d["mn"], d["mrgba"], f["model_pose"], 3.0, 20.0) for h, d, f in zip(hfr, dfr, frames)]
+    for n, f in enumerate(frames):
+        P = f["model_pose"]
+        prior = (P[:3, 3].copy(), P[:3, :3].copy())
+        d = dfr[n]
+        want = dev.track_device(dev.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, 3.0, 20.0), *prior)
+        got = sen.track_sensor(sframes[n], *prior, next_frame=sframes[n + 1] if n + 1 < len(frames) and n % 2 == 0 else None)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), f"frame {n}"
+    for o in (dev, sen):
+        o.close()
+
+
+def test_preparing_the_next_frame_before_wait_keeps_the_image_swap(setup):
+    """A pipelined caller enqueues frame N (so3 = 1), prepares frame N + 1 and only then collects frame N.  The
+    lastNextImage <-> nextImage swap of RGBDOdometryef.cpp:585-591 belongs to frame N and must have happened before frame
+    N + 1's initRGB writes nextImage: the poses must equal the strictly sequential call order."""
+    t = setup["torch"]
+    scene, poses = setup["scene"], setup["poses"]
+    i = setup["intr"]
+    ks = (300, 301, 302)
+    frames = [to_device(frame_pair(scene, poses, k)) for k in ks]
+    first = t.from_numpy(scene.render_frame(poses[ks[0] - 1])[1]).to("cuda:0")
+    t.cuda.synchronize()
+    mk = lambda: setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+
+    def prepare(o, d):
+        o.initICPModel(d["mv"], d["mn"], 20.0, d["model_pose"])
+        o.initRGBModel(d["mrgba"])
+        o.initICP(d["depth"], 3.0)
+        o.initRGB(d["rgba"])
+
+    seq = mk()
+    seq.initFirstRGB(first)
+    want = []
+    for d in frames:
+        prepare(seq, d)
+        P = d["model_pose"]
+        want.append(seq.getIncrementalTransformation(P[:3, 3].copy(), P[:3, :3].copy(), False, 10.0, True, False, True))
+    pipe = mk()
+    pipe.initFirstRGB(first)
+    got = []
+    prepare(pipe, frames[0])
+    for n, d in enumerate(frames):
+        P = d["model_pose"]
+        pipe.getIncrementalTransformationAsync(P[:3, 3].copy(), P[:3, :3].copy(), False, 10.0, True, False, True)
+        if n + 1 < len(frames):
+            prepare(pipe, frames[n + 1])     # before the wait: the entry points collect the pending track themselves
+        got.append(pipe.wait())              # ... and wait() still hands out its pose
+    for n in range(len(frames)):
+        assert np.array_equal(got[n][0], want[n][0]) and np.array_equal(got[n][1], want[n][1]), f"frame {n}"
+    seq.close()
+    pipe.close()
+
+
 def test_properties_identity_and_rigid_equivariance(setup):
     """Size-independent properties of the whole tracker at the full 640x480 size:
       * identity: a frame tracked against the model predicted at the frame's own pose stays where it is;

@@ -176,3 +176,20 @@ def test_two_rank_relocalisation_min_allreduce_gloo(built, tmp_path):
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["best"] == res["want"] == 41 and res["err"] == res["want_err"]
     assert res["local"] == 128      # rank 0 scored its half of the 257 hypotheses
+
+
+def test_perturbed_hypotheses_are_reproducible_and_start_with_the_ground_truth():
+    """SURVEY 8(d) configs[4]: the hypothesis set is a pure function of (pose, n, seed) -- every rank builds the same one."""
+    from slam_b200.relocalise import perturbed_hypotheses
+    gt = np.eye(4)
+    gt[:3, 3] = [1.0, -0.5, 2.0]
+    T1, R1 = perturbed_hypotheses(gt, 64)
+    T2, R2 = perturbed_hypotheses(gt, 64)
+    assert np.array_equal(T1, T2) and np.array_equal(R1, R2)
+    assert np.array_equal(T1[0], gt[:3, 3].astype(np.float32)) and np.array_equal(R1[0], np.eye(3, dtype=np.float32))
+    d = np.linalg.norm(T1[1:] - T1[0], axis=1)
+    assert 0.04 < d.mean() < 0.13          # sigma 5 cm per axis
+    ang = np.degrees(np.arccos(np.clip((np.trace(R1[1:], axis1=1, axis2=2) - 1) / 2, -1, 1)))
+    assert 2.0 < ang.mean() < 8.0          # sigma 3 deg per axis
+    for r in R1:
+        assert np.allclose(r @ r.T, np.eye(3), atol=1e-6)
