@@ -35,6 +35,9 @@ def load():
     lib.ref_odom_create.restype = vp
     lib.ref_odom_create.argtypes = [i, i, f, f, f, f, f, f]
     lib.ref_odom_destroy.argtypes = [vp]
+    lib.ref_odom_create_levels.restype = vp
+    lib.ref_odom_create_levels.argtypes = [i, i, f, f, f, f, f, f, i]
+    lib.ref_odom_set_iterations4.argtypes = [vp, i, i, i, i]
     lib.ref_odom_set_iterations.argtypes = [vp, i, i, i]
     lib.ref_odom_init_icp_depth.argtypes = [vp, vp, f]
     lib.ref_odom_init_icp_maps.argtypes = [vp, vp, vp, f]
@@ -77,12 +80,22 @@ def _addr(x) -> int:
 class RefOdometry:
     """The reference tracker (its own kernels) behind the same Python surface as slam_b200.RGBDOdometry."""
 
-    def __init__(self, width, height, cx, cy, fx, fy, distThresh=0.0, angleThresh=0.0, iterations=None):
+    def __init__(self, width, height, cx, cy, fx, fy, distThresh=0.0, angleThresh=0.0, iterations=None, num_levels=3):
+        """num_levels = 4: the replay loops over four levels (the class itself hard-codes three, RGBDOdometryef.h:104; every
+        wrapper it calls is level-agnostic, odom/utils.cuh:62-175)."""
         self.lib = load()
         self.width, self.height = width, height
-        self._h = C.c_void_p(self.lib.ref_odom_create(width, height, cx, cy, fx, fy, distThresh, angleThresh))
+        if num_levels == 3:
+            self._h = C.c_void_p(self.lib.ref_odom_create(width, height, cx, cy, fx, fy, distThresh, angleThresh))
+        else:
+            self._h = C.c_void_p(self.lib.ref_odom_create_levels(width, height, cx, cy, fx, fy, distThresh, angleThresh, int(num_levels)))
+            assert self._h, "reference replay: unsupported level count"
         if iterations:
-            self.lib.ref_odom_set_iterations(self._h, *[int(v) for v in iterations[:3]])
+            it = [int(v) for v in iterations] + [0] * 4
+            if num_levels == 3:
+                self.lib.ref_odom_set_iterations(self._h, *it[:3])
+            else:
+                self.lib.ref_odom_set_iterations4(self._h, *it[:4])
 
     def close(self):
         if getattr(self, "_h", None):

@@ -36,7 +36,10 @@ namespace {
 struct RefOdom
 {
     // ---- members of RGBDOdometryef (RGBDOdometryef.h:72-131) ----
-    static const int NUM_PYRS = 3;
+    // the class hard-codes NUM_PYRS = 3 (RGBDOdometryef.h:104); every wrapper it calls is level-agnostic (odom/utils.cuh:62-175), so the
+    // replay takes the level count at run time (BASELINE configs[2]: four levels, iterations 10/5/4/4)
+    static const int MAX_PYRS = 4;
+    int NUM_PYRS = 3;
     std::vector<DeviceArray2D<unsigned short>> depth_tmp;
     DeviceArray<float> vmaps_tmp, nmaps_tmp;
     std::vector<DeviceArray2D<float>> vmaps_g_prev_, nmaps_g_prev_, vmaps_curr_, nmaps_curr_;
@@ -46,11 +49,11 @@ struct RefOdom
     DeviceArray<JtJJtrSO3> sumDataSO3, outDataSO3;
     int sobelSize;
     float sobelScale, maxDepthDeltaRGB, maxDepthRGB;
-    DeviceArray2D<float> lastDepth[NUM_PYRS], nextDepth[NUM_PYRS];
-    DeviceArray2D<unsigned char> lastImage[NUM_PYRS], nextImage[NUM_PYRS], lastNextImage[NUM_PYRS];
-    DeviceArray2D<short> nextdIdx[NUM_PYRS], nextdIdy[NUM_PYRS];
-    DeviceArray2D<DataTerm> corresImg[NUM_PYRS];
-    DeviceArray2D<float3> pointClouds[NUM_PYRS];
+    DeviceArray2D<float> lastDepth[MAX_PYRS], nextDepth[MAX_PYRS];
+    DeviceArray2D<unsigned char> lastImage[MAX_PYRS], nextImage[MAX_PYRS], lastNextImage[MAX_PYRS];
+    DeviceArray2D<short> nextdIdx[MAX_PYRS], nextdIdy[MAX_PYRS];
+    DeviceArray2D<DataTerm> corresImg[MAX_PYRS];
+    DeviceArray2D<float3> pointClouds[MAX_PYRS];
     std::vector<int> iterations;
     std::vector<float> minimumGradientMagnitudes;
     float distThres_, angleThres_;
@@ -64,8 +67,8 @@ struct RefOdom
     int user_iterations[4] = {0, 0, 0, 0};
 
     // RGBDOdometryef.cpp:21-111
-    RefOdom(int w, int h, float cx, float cy, float fx, float fy, float distThresh, float angleThresh)
-     : sobelSize(3), sobelScale(1.0 / pow(2.0, 3)), maxDepthDeltaRGB(0.07), maxDepthRGB(6.0), distThres_(distThresh), angleThres_(angleThresh),
+    RefOdom(int w, int h, float cx, float cy, float fx, float fy, float distThresh, float angleThresh, int levels = 3)
+     : NUM_PYRS(levels), sobelSize(3), sobelScale(1.0 / pow(2.0, 3)), maxDepthDeltaRGB(0.07), maxDepthRGB(6.0), distThres_(distThresh), angleThres_(angleThresh),
        width(w), height(h)
     {
         lastICPError = 0; lastICPCount = w * h; lastRGBError = 0; lastRGBCount = w * h; lastSO3Error = 0; lastSO3Count = w * h;
@@ -104,6 +107,7 @@ struct RefOdom
         minimumGradientMagnitudes[0] = 5;
         minimumGradientMagnitudes[1] = 3;
         minimumGradientMagnitudes[2] = 1;
+        if(NUM_PYRS > 3) minimumGradientMagnitudes[3] = 1;
     }
 
     // RGBDOdometryef.cpp:118-142
@@ -280,7 +284,8 @@ struct RefOdom
         iterations[0] = fastOdom ? 3 : 10;
         iterations[1] = pyramid ? 5 : 0;
         iterations[2] = pyramid ? 4 : 0;
-        if(user_iterations[0] || user_iterations[1] || user_iterations[2])
+        if(NUM_PYRS > 3) iterations[3] = pyramid ? 4 : 0;
+        if(user_iterations[0] || user_iterations[1] || user_iterations[2] || user_iterations[3])
             for(int i = 0; i < NUM_PYRS; i++) iterations[i] = user_iterations[i];
 
         float Rprev_inv[9];
@@ -440,7 +445,19 @@ void * ref_odom_create(int width, int height, float cx, float cy, float fx, floa
     if(angleThresh == 0) angleThresh = sinf(20.f * 3.14159254f / 180.f);
     return new RefOdom(width, height, cx, cy, fx, fy, distThresh, angleThresh);
 }
+void * ref_odom_create_levels(int width, int height, float cx, float cy, float fx, float fy, float distThresh, float angleThresh, int levels)
+{
+    if(levels < 3 || levels > RefOdom::MAX_PYRS) return nullptr;
+    if(distThresh == 0) distThresh = 0.10f;
+    if(angleThresh == 0) angleThresh = sinf(20.f * 3.14159254f / 180.f);
+    return new RefOdom(width, height, cx, cy, fx, fy, distThresh, angleThresh, levels);
+}
 void ref_odom_destroy(void * h) { delete (RefOdom *)h; }
+void ref_odom_set_iterations4(void * h, int i0, int i1, int i2, int i3)
+{
+    RefOdom * r = (RefOdom *)h;
+    r->user_iterations[0] = i0; r->user_iterations[1] = i1; r->user_iterations[2] = i2; r->user_iterations[3] = i3;
+}
 void ref_odom_set_iterations(void * h, int i0, int i1, int i2)
 {
     RefOdom * r = (RefOdom *)h;

@@ -322,6 +322,7 @@ __device__ __forceinline__ void warp_update_fast(GnShared & sh, const bool icp, 
         prod *= ps;
     }
     // ---- x_i = b_i / a_ii: the columns go back to shared memory, lane i < 6 divides
+    __syncwarp();   // every lane has read its column of Wsys
     if(lane < 7)
     {
 #pragma unroll

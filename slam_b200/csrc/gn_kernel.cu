@@ -61,6 +61,7 @@ struct GnWork
     unsigned long long mid;        // global correspondence count word
     long long sigma;               // global squared-residual sum (rgbOnly: read at the mid point)
     int timeouts;
+    int so3_stop[2];               // outcome of the SO3 iteration, by iteration parity (read by every warp after the barrier while warp 0 may already be in the next one)
     unsigned ph[16];               // cycles per phase (leading CTA, thread 0)
     unsigned long long base[kRingSlots * kRingWords];   // value of every reduction word when this CTA last consumed it
 };
@@ -597,12 +598,13 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     slam_step_record * rec = (GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
                     if(GEN && rec) memset(rec, 0, sizeof(*rec));
                     warp_so3_update_fast(sh, it, rec);   // also leaves the next iteration's H, K^-1, K R in shared memory
+                    if(threadIdx.x == 0) wk.so3_stop[it & 1] = sh.stop;
                     if(GEN && rec) ntr++;
                     GN_PHASE(14);
                 }
                 step++;
                 __syncthreads();
-                if(sh.stop) break;
+                if(wk.so3_stop[it & 1]) break;
             }
         }
         GN_PHASE(1);

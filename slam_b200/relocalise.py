@@ -69,7 +69,8 @@ def score_sharded(odo, level, prev_pose, trans_n, rot_n, rank=0, world=1, min_in
     else:
         err = np.zeros(0, np.float32)
     keys = pack_keys(err, np.arange(lo, hi))
-    e, i = unpack_key(best_key(keys, group, device))
+    # world == 1: this rank scores everything alone, whatever process group may exist (the single-GPU check of a sharded run)
+    e, i = unpack_key(int(keys.min()) if world == 1 else best_key(keys, group, device))
     return i, e, err
 
 
@@ -102,8 +103,10 @@ def broadcast_frame(tensors, src=0, group=None):
     """Replicate the frame of rank `src` (device tensors: depth, predicted vertices / normals, ...) on every rank, in place."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        import torch
         for t in tensors:
-            dist.broadcast(t, src=src, group=group)
+            # NCCL has no 16-bit integer type: the u16 depth image travels as the bytes it is
+            dist.broadcast(t.view(torch.uint8) if t.dtype in (torch.int16, torch.uint16) else t, src=src, group=group)
 
 
 def score_sharded_device(odo, level, prev_pose, trans_n, rot_n, key_tensor, rank=0, world=1, min_inliers=1.0, group=None, stream=None):

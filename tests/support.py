@@ -110,6 +110,24 @@ def se3_sums_rel_err(mine29, ref29, noise_floor=True):
     return float(np.max(err))
 
 
+def se3_jtj_literal_rel_err(mine29, ref29):
+    """Literal element-wise relative error |mine - ref| / |ref| of the 21 JtJ terms and the residual (index 27) -- the
+    north-star's "1e-4 relative" read word for word.  These sums do not cancel; the 6 Jtr terms do (near convergence they are
+    sums of ~1e5 signed terms of either sign) and are judged by se3_sums_rel_err instead."""
+    m = np.asarray(mine29, dtype=np.float64)
+    r = np.asarray(ref29, dtype=np.float64)
+    worst, k = 0.0, 0
+    for i in range(7):
+        for j in range(i, 7):
+            if j < 6 or i == 6:
+                if r[k] != 0.0:
+                    worst = max(worst, abs(m[k] - r[k]) / abs(r[k]))
+                else:
+                    worst = max(worst, abs(m[k]))
+            k += 1
+    return worst
+
+
 def so3_sums_rel_err(mine11, ref11):
     m = np.asarray(mine11, dtype=np.float64)
     r = np.asarray(ref11, dtype=np.float64)

@@ -1,10 +1,14 @@
 """BASELINE.json configs[2]: 1280x720 RealSense-shaped depth, 4-level pyramid, ICP-only tracking with 10/5/4/4 iterations.
 
-The reference is compiled for three levels (NUM_PYRS, RGBDOdometryef.h:75), so parity is pinned in two steps:
+The reference class is compiled for three levels (NUM_PYRS, RGBDOdometryef.h:104) but every wrapper it calls is level-agnostic
+(odom/utils.cuh:62-175), so the replay (oracle/ref_harness.cu) takes the level count at run time:
   * at 1280x720 with three levels the whole tracker is compared with the reference replay (prepared maps bit-exact, pose);
-  * the fourth level's buffers are compared with the reference's own per-level operators (pyrDown, createVMap,
-    createNMap, resizeVMap / resizeNMap, tranformMaps) applied once more, and the 4-level device-resident loop is compared
-    with the host-stepped loop (which launches the operator kernels the other tests pin) and with the ground truth.
+  * with FOUR levels and 10/5/4/4 iterations the Gauss-Newton chain is compared with the 4-level reference replay step by step
+    (same bars as the 3-level tests: first step exact, sums, increments and poses within 1e-5) and every level's prepared maps
+    bit for bit;
+  * the fourth level's buffers are also compared with the reference's own per-level operators (pyrDown, createVMap,
+    createNMap, resizeVMap / resizeNMap, tranformMaps) applied once more, and the 4-level device-resident loop with the
+    host-stepped loop and the ground truth.
 """
 import ctypes as C
 
@@ -133,6 +137,34 @@ def test_720p_four_levels(hd):
     assert np.array_equal(tf, td) and np.array_equal(rf, rd)
     for o in (host, devo, fast):
         o.close()
+
+
+def test_720p_four_levels_match_the_four_level_reference_replay(hd):
+    """configs[2] against the reference itself: the replay harness run with four levels and 10/5/4/4 iterations."""
+    from slam_b200 import Tap
+    from tests.test_gpu_tracking import compare_traces
+    i = hd["intr"]
+    kw = dict(so3=False, rgbOnly=False, icpWeight=100.0, pyramid=True, fastOdom=False)
+    ref = hd["Ref"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], iterations=ITER4, num_levels=4)
+    ref.set_trace(True)
+    tr, rr = run_frame(ref, hd["d"], **kw)
+    ref_trace = ref.get_trace()
+    assert [r["level"] for r in ref_trace] == [3] * 4 + [2] * 4 + [1] * 5 + [0] * 10
+    for which in ("host loop", "device loop"):
+        mine = hd["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], num_levels=4, iterations=ITER4, host_loop=(which == "host loop"))
+        mine.set_trace(True)
+        tm, rm = run_frame(mine, hd["d"], **kw)
+        for level in range(4):
+            for tap in (Tap.VMAP_CURR, Tap.NMAP_CURR, Tap.VMAP_PREV, Tap.NMAP_PREV):
+                nan_diff, val_diff = planar_map_mismatch(mine.tap(tap, level), ref.tap(tap, level))
+                assert nan_diff == 0 and val_diff == 0, f"{which}: tap {tap} level {level}: nan {nan_diff} values {val_diff}"
+            assert np.array_equal(mine.tap(Tap.DEPTH_U16, level), ref.tap(Tap.DEPTH_U16, level)), f"{which}: depth pyramid level {level}"
+        compare_traces(mine.get_trace(), ref_trace, f"720p 4-level {which}")
+        assert np.abs(tm - tr).max() < 1e-5 and np.abs(rm - rr).max() < 1e-5, f"{which}: pose differs from the 4-level reference replay"
+        sm, sr = mine.stats(), ref.stats()
+        assert abs(sm.lastICPCount - sr.lastICPCount) <= max(8, 2e-3 * sr.lastICPCount)
+        mine.close()
+    ref.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@
 import numpy as np
 import pytest
 
-from tests.support import (frame_pair, planar_map_mismatch, run_frame, se3_sums_rel_err, so3_sums_rel_err, to_device)
+from tests.support import (frame_pair, planar_map_mismatch, run_frame, se3_jtj_literal_rel_err, se3_sums_rel_err, so3_sums_rel_err, to_device)
 
 pytestmark = pytest.mark.gpu
 
@@ -288,9 +288,11 @@ def test_teacher_forced_steps_match_reference(setup):
         m29, c2, r29 = out29.cpu().numpy()[:29], out2.cpu().numpy(), rgb29.cpu().numpy()[:29]
         assert m29[28] == rec["icp"][28], f"{tag}: icp inliers {m29[28]} vs {rec['icp'][28]}"
         assert se3_sums_rel_err(m29, rec["icp"]) < SUM_TOL, f"{tag}: icp sums {se3_sums_rel_err(m29, rec['icp'])}"
+        assert se3_jtj_literal_rel_err(m29, rec["icp"]) < SUM_TOL, f"{tag}: icp JtJ element-wise {se3_jtj_literal_rel_err(m29, rec['icp'])}"
         assert c2[0] == rec["rgb_count"] and c2[1] == rec["rgb_sigma"], f"{tag}: rgb count/sigma {c2} vs {rec['rgb_count']},{rec['rgb_sigma']}"
         assert r29[28] == rec["rgb"][28], tag
         assert se3_sums_rel_err(r29, rec["rgb"]) < SUM_TOL, f"{tag}: rgb sums {se3_sums_rel_err(r29, rec['rgb'])}"
+        assert se3_jtj_literal_rel_err(r29, rec["rgb"]) < SUM_TOL, f"{tag}: rgb JtJ element-wise {se3_jtj_literal_rel_err(r29, rec['rgb'])}"
         n_exact += 1
     assert n_exact == 19
     mine.close()
