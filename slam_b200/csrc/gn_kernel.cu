@@ -268,6 +268,66 @@ __device__ __forceinline__ void rgb_candidate_state(const ResidualArgs & a, cons
     }
 }
 
+// The same test for one 32-pixel segment that lies in one image row and starts at a multiple of 32 columns (every level of a
+// 640x480 or 1280x720 pyramid): ten lanes fetch the row strip [x0 - 4, x0 + 36) of each of the four window rows as aligned 32-bit
+// words, every lane cuts its own four taps (columns x - 2 .. x + 1) out of two neighbouring words with two shuffles and a funnel
+// shift, and "all sixteen taps non-zero" becomes four zero-byte tests.  Four loads per segment row instead of sixteen byte loads
+// per pixel.  Taps outside the image are filled with 0xff: the reference's clipped loops never visit them, so they do not vote.
+__device__ __forceinline__ void rgb_candidate_segment(const ResidualArgs & a, const bool derive, const bool live /* warp-uniform */, const int x0, const int y,
+                                                      const int k, bool & cand, float & d1o, unsigned & gxy, unsigned & img)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = x0 + lane;
+    unsigned w[4];
+    const int wpr = a.cols >> 2;                 // words per image row
+    const int wi = (x0 >> 2) - 1 + lane;         // lanes 0..9: word of the strip
+    const int b = lane + 2;                      // byte offset of this lane's first tap inside the strip
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+    {
+        const int yy = y - 2 + r;
+        unsigned strip = 0xffffffffu;
+        if(live && lane < 10 && yy >= 0 && yy < a.rows && wi >= 0 && wi < wpr) strip = __ldg(reinterpret_cast<const unsigned *>(a.nextImage + (size_t)yy * a.cols) + wi);
+        const unsigned lo = __shfl_sync(0xffffffffu, strip, b >> 2);
+        const unsigned hi = __shfl_sync(0xffffffffu, strip, (b >> 2) + 1);
+        w[r] = __funnelshift_r(lo, hi, 8 * (b & 3));
+    }
+    const float d1 = live ? __ldg(a.nextDepth + k) : 0.f;
+    short gx = (derive || !live) ? (short)0 : __ldg(a.dIdx + k);
+    short gy = (derive || !live) ? (short)0 : __ldg(a.dIdy + k);
+    bool ok = live && (x < a.cols - 5 && y < a.rows - 1);
+#pragma unroll
+    for(int r = 0; r < 4; r++) ok = ok && (((w[r] - 0x01010101u) & ~w[r] & 0x80808080u) == 0u);
+    if(derive)
+    {
+        if(x >= 1 && y >= 1 && x < a.cols - 1 && y < a.rows - 1)
+        {
+            // interior: the nine taps are window entries (r + 1, q + 1), accumulated in the reference's order
+            const float fgx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+            const float fgy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+            float dxVal = 0, dyVal = 0;
+#pragma unroll
+            for(int t = 0; t < 9; t++)
+            {
+                const float v = (float)((w[t / 3 + 1] >> (8 * (t % 3 + 1))) & 0xffu);
+                dxVal = __fmaf_rn(v, fgx[8 - t], dxVal);
+                dyVal = __fmaf_rn(v, fgy[8 - t], dyVal);
+            }
+            gx = (short)dxVal;
+            gy = (short)dyVal;
+        }
+        else if(ok)
+            derivative_pixel(a.nextImage, a.rows, a.cols, x, y, gx, gy);   // image border: the clipped loop itself
+    }
+    const int valx = gx, valy = gy;
+    const float mTwo = (valx * valx) + (valy * valy);
+    ok = ok && (mTwo >= a.minScale) && !isnan(d1);
+    cand = ok;
+    d1o = d1;
+    gxy = ((unsigned)(unsigned short)gx) | (((unsigned)(unsigned short)gy) << 16);
+    img = (w[2] >> 16) & 0xffu;   // the pixel itself
+}
+
 // Stage one resident level of this CTA: lists of ICP and RGB entries in shared memory (see the header comment).
 // Pass 1 loads the operands of every pixel of the CTA's segments ONCE (one round trip to L2 per segment slot), stores them at
 // their uncompacted position and counts the survivors per (slot, warp); a block-wide prefix sum turns the counts into list
@@ -285,6 +345,7 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
     unsigned * rgb_xyi = rgb_gxy + pl.cap;
     const int nslots = (pl.segs_per_cta + kGnWarps - 1) / kGnWarps;   // <= kMaxStageSlots (gn_make_plan); cap = segs_per_cta * 32
     const unsigned lt = (1u << lane) - 1u;
+    const bool aligned = (g.cols & 31) == 0;   // every 32-pixel segment lies in one row and starts at a multiple of 32 columns
     {
         ResidualArgs ra;
         ra.minScale = L.min_scale[lvl];
@@ -325,7 +386,10 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
             {
                 float d1[1];
                 unsigned g1[1], i1[1];
-                rgb_candidate_state<1>(ra, L.derive_gradients, k1, l1, x1, y1, c1, d1, g1, i1);
+                if(aligned)
+                    rgb_candidate_segment(ra, L.derive_gradients, j < pl.segs_per_cta && seg < pl.nseg, x1[0] - lane, y1[0], kk, c1[0], d1[0], g1[0], i1[0]);
+                else
+                    rgb_candidate_state<1>(ra, L.derive_gradients, k1, l1, x1, y1, c1, d1, g1, i1);
                 // the reference writes a DataTerm for every pixel (reduce.cu:838): pixels that never become entries get their zero once
                 if(L.full_corres && l1[0] && !c1[0]) reinterpret_cast<int4 *>(P.corres)[kk] = make_int4(0, 0, 0, 0);
                 if(j < pl.segs_per_cta)
