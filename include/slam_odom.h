@@ -231,9 +231,9 @@ int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_k
  * (or since the last reset): [0] staging, [1] rest of the SO3 loop, [2] step set-up, [3] RGB association + count post, [4] ICP
  * products, [5] their block reduction + post + wait for the global count, [6] RGB products + block reduction + post, [7] wait for
  * all sums, [8] solve, [9] end-of-step barrier, [10] tail, [11] SO3 map, [12] SO3 block reduction + post, [13] SO3 wait for the
- * sums, [14] SO3 update, [15] launches.  Only the variants launched with SLAM_GN_PHASES=1 (or the step trace) count.
+ * sums, [14] SO3 update, [15] launches, [16..19] staging of level 0..3, [20] staging of the SO3 images ([0] then holds only the check-in gate).  Only the variants launched with SLAM_GN_PHASES=1 (or the step trace) count.
  * Synchronises the handle's stream. */
-int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long out16[16], int reset);
+int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long out24[24], int reset);
 /* The stream the handle runs on (cudaStream_t), e.g. to record the caller's own events on it. */
 void * slam_odom_stream(slam_odom_t h);
 

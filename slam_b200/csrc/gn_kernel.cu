@@ -62,7 +62,7 @@ struct GnWork
     long long sigma;               // global squared-residual sum (rgbOnly: read at the mid point)
     int timeouts;
     int so3_stop[2];               // outcome of the SO3 iteration, by iteration parity (read by every warp after the barrier while warp 0 may already be in the next one)
-    unsigned ph[16];               // cycles per phase (leading CTA, thread 0)
+    unsigned ph[24];               // cycles per phase (leading CTA, thread 0)
     unsigned long long base[kRingSlots * kRingWords];   // value of every reduction word when this CTA last consumed it
 };
 
@@ -148,6 +148,25 @@ __device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, u
 #pragma unroll
         for(int w = 0; w < kGnWarps; w++) total += sh.red[w * 32 + lane];
         if(lane < ncols) post_float(ring, step, wbase, lane, total);
+    }
+}
+
+// Block-level half of an ICP + RGB reduction: every warp holds, per lane, its partial sum of ICP column `lane` (s_icp) and of RGB
+// column `lane` (s_rgb), from two warp_reduce_scatter32 calls; one barrier, then warp 0 adds up and posts the ICP columns while
+// warp 1 does the same for the RGB columns.  has_icp / has_rgb: which halves exist (CTA-uniform).
+__device__ __forceinline__ void cta_post_pair(const float s_icp, const float s_rgb, const bool has_icp, const bool has_rgb, GnShared & sh, unsigned long long * ring,
+                                              unsigned step)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    sh.red[wid * 64 + lane] = s_icp;
+    sh.red[wid * 64 + 32 + lane] = s_rgb;
+    __syncthreads();
+    if(wid < 2 && (wid == 0 ? has_icp : has_rgb))
+    {
+        float total = 0.f;
+#pragma unroll
+        for(int w = 0; w < kGnWarps; w++) total += sh.red[w * 64 + wid * 32 + lane];
+        if(lane < 29) post_float(ring, step, wid == 0 ? kWIcp : kWRgb, lane, total);
     }
 }
 
@@ -522,7 +541,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         wk.timeouts = 0;
     }
     long long ph_t = t_start;
-    if(PH && threadIdx.x < 16) wk.ph[threadIdx.x] = 0u;
+    if(PH && threadIdx.x < 24) wk.ph[threadIdx.x] = 0u;
 #define GN_PHASE(idx) do { if(PH && leader) { const long long now_ = clock64(); wk.ph[idx] += (unsigned)(now_ - ph_t); ph_t = now_; } } while(0)
 
     // the reduction words as the previous launch left them (nobody posts before every CTA of the group has passed its first
@@ -567,6 +586,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         {
             if(L.iterations[lvl] > 0 && L.plan[lvl].resident && rank < L.plan[lvl].P)
                 stage_level(L, ICP, RGB, lvl, level_ptrs(L.batch == 1, seq0, seqs, seq, lvl), rank, wk, dyn);
+            GN_PHASE(16 + (lvl < 3 ? lvl : 3));
         }
         if(L.so3 && L.so3_resident && rank < L.so3_P)
         {
@@ -594,6 +614,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             }
             __syncthreads();
         }
+        GN_PHASE(20);
         GN_GATE();
         GN_PHASE(0);
 
@@ -858,6 +879,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 // the count's trip through L2 overlaps this map), pass 1 = RGB Jacobian products (reduce.cu:494-624).
                 bool stop_now = false;
                 unsigned long long mid_peek = 0ull;
+                float s_icp = 0.f;   // this warp's partial sum of ICP column `lane` (kept in a register until the RGB products are in)
 #pragma unroll 1
                 for(int pass = ICP ? 0 : 1; pass < (RGB ? 2 : 1); pass++)
                 {
@@ -1045,12 +1067,17 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         }
                         GN_STAMP(rec, 5);
                     }
-                    // the count word is fetched while the block reduction runs: by now every CTA has posted to it long ago,
-                    // so the value is normally complete when the reduction is done and nobody waits for this trip through L2
+                    // the count word is fetched while the warp reduction runs: by now every CTA has posted to it long ago, so the
+                    // value is normally complete when the reduction is done and nobody waits for this trip through L2
                     if(ICP && RGB && pass == 0 && threadIdx.x == 0) mid_peek = ld_u64_relaxed(ring_word(ring, step, kWMid));
                     if(part)
                     {
-                        cta_reduce_post(acc, sh, ring, step, pass ? kWRgb : kWIcp, 29);
+                        // warp level now (one copy of the code for both passes); block level + post once, after the last pass
+                        const float s = warp_reduce_scatter32(acc);
+                        if(ICP && RGB && pass == 0)
+                            s_icp = s;
+                        else
+                            cta_post_pair((ICP && RGB) ? s_icp : (ICP ? s : 0.f), RGB ? s : 0.f, ICP, RGB, sh, ring, step);
                     }
                     if(pass == 1) GN_PHASE(6);
                 }
@@ -1122,10 +1149,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         __syncthreads();
     }
     GN_PHASE(10);
-    if(PH && blockIdx.x == 0 && threadIdx.x < 15)
+    if(PH && blockIdx.x == 0 && threadIdx.x < 24)
     {
         __syncwarp();
-        atomicAdd(&ctl->phase_cycles[threadIdx.x], (unsigned long long)wk.ph[threadIdx.x]);
+        if(threadIdx.x != 15) atomicAdd(&ctl->phase_cycles[threadIdx.x], (unsigned long long)wk.ph[threadIdx.x]);
         if(threadIdx.x == 0) atomicAdd(&ctl->phase_cycles[15], 1ull);
     }
     if(threadIdx.x == 0 && wk.timeouts) atomicAdd(&ctl->timeouts, 1u);
@@ -1239,7 +1266,7 @@ static int gn_init_device(GnDevice & d)
     for(GnKernel k : kAllGnKernels) SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_limit));
     d.phases = getenv("SLAM_GN_PHASES") != nullptr;
     const char * pd = getenv("SLAM_GN_POLL_DELAY");
-    d.poll_delay = pd ? atoi(pd) : 600;
+    d.poll_delay = pd ? atoi(pd) : 900;
     return SLAM_OK;
 }
 

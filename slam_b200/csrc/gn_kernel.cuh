@@ -55,7 +55,7 @@ struct GnCtl
 {
     unsigned long long arrived[kGnMaxCtas + 1];   // per CTA group: CTAs that have checked in, summed over all launches (GN_GATE)
     unsigned timeouts;               // polls that gave up (a lost arrival would otherwise hang the GPU): non-zero = results invalid
-    unsigned long long phase_cycles[16];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
+    unsigned long long phase_cycles[24];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
 };
 
 // How one pyramid level is mapped onto the CTAs of a group.  Resident levels keep the pose-independent operands of their

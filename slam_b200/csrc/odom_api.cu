@@ -1268,14 +1268,14 @@ extern "C" int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long 
     return SLAM_OK;
 }
 
-extern "C" int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long * out16, int reset)
+extern "C" int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long * out24, int reset)
 {
     if(int rc = check_handle(h)) return rc;
-    SLAM_ARG_CHECK(out16);
+    SLAM_ARG_CHECK(out24);
     if(int rc = set_device(h)) return rc;
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    SLAM_CUDA_TRY(cudaMemcpy(out16, h->gn.ctl->phase_cycles, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
-    if(reset) SLAM_CUDA_TRY(cudaMemset(h->gn.ctl->phase_cycles, 0, sizeof(unsigned long long) * 16));
+    SLAM_CUDA_TRY(cudaMemcpy(out24, h->gn.ctl->phase_cycles, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost));
+    if(reset) SLAM_CUDA_TRY(cudaMemset(h->gn.ctl->phase_cycles, 0, sizeof(unsigned long long) * 24));
     return SLAM_OK;
 }
 

@@ -389,13 +389,13 @@ class RGBDOdometry:
         return ms.value, n.value
 
     PHASES = ("staging", "so3 rest", "step set-up", "rgb assoc", "icp map", "icp reduce + count wait", "rgb products+reduce", "sums wait", "solve", "end barrier", "tail",
-              "so3 map", "so3 reduce+post", "so3 wait", "so3 update")
+              "so3 map", "so3 reduce+post", "so3 wait", "so3 update", "launches", "stage L0", "stage L1", "stage L2", "stage L3", "stage so3 images")
 
     def get_phase_cycles(self, reset=False):
         """-> ({phase: SM cycles of the persistent kernel's leading CTA}, launches) accumulated since the last reset."""
-        out = (C.c_ulonglong * 16)()
+        out = (C.c_ulonglong * 24)()
         _check(self.lib, self.lib.slam_odom_get_phase_cycles(self._h, out, int(reset)))
-        return {name: int(out[k]) for k, name in enumerate(self.PHASES)}, int(out[15])
+        return {name: int(out[k]) for k, name in enumerate(self.PHASES) if k != 15}, int(out[15])
 
     @property
     def stream(self) -> int:
