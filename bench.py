@@ -727,6 +727,46 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
     return out
 
 
+def pin_rank_to_cores(local_rank: int, world: int) -> str:
+    """One process per GPU: give every rank its own slice of the host cores, so that the per-frame host work of N ranks (launch
+    calls, the result poll, the clock sampler) does not migrate or pile up on the same cores.  The slice starts on the NUMA node of
+    the rank's GPU when sysfs tells which one that is."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cores) < 2 * world:
+            return f"{len(cores)} cores, not pinned"
+        node_cores = None
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+            if bus is not None:
+                base = Path("/sys/bus/pci/devices")
+                for d in base.iterdir():
+                    if d.name.lower().endswith(f"{bus:02x}:00.0"):
+                        node = int((d / "numa_node").read_text())
+                        if node >= 0:
+                            txt = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+                            node_cores = []
+                            for part in txt.split(","):
+                                a, _, b = part.partition("-")
+                                node_cores += list(range(int(a), int(b or a) + 1))
+                            node_cores = [c for c in node_cores if c in cores]
+                        break
+        except Exception:
+            node_cores = None
+        per = len(cores) // world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        if node_cores and len(node_cores) >= per:
+            # ranks whose GPUs share a node split that node's cores among them
+            share = max(1, len(node_cores) // max(1, world))
+            k = (local_rank * share) % max(1, len(node_cores) - share + 1)
+            mine = node_cores[k:k + max(share, 2)]
+        os.sched_setaffinity(0, set(mine))
+        return f"cores {mine[0]}-{mine[-1]} ({len(mine)})"
+    except Exception as e:   # pragma: no cover
+        return f"not pinned ({e})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -746,6 +786,7 @@ def main():
             args.steps = 200   # bounded sample: ~0.15 s per frame on 8 cores
         run_reference_arm(args, rank, world)
         return
+    log(f"[rank {rank}] host cores: {pin_rank_to_cores(local_rank, world)}")
     if world == 1 and args.gpus > 1:
         log(f"--gpus {args.gpus} without torchrun: running a single rank (launch with torch.distributed.run for N > 1)")
     run_ours(args, rank, local_rank, world)

@@ -1130,20 +1130,51 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             }
         }
 
-        if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
-        __syncthreads();
-        if(threadIdx.x == 0) seq_end(sh, RGB, RGB_ONLY, leader ? &results[seq] : nullptr);
-        if(rank == 0 && host_results && warp0)   // `leader` is thread 0 of the group's first CTA: all of its warp 0 copies
+        // ---- the pose goes out first: the caller is released ~4 us before the statistics are complete
+        if(threadIdx.x == 0)
         {
-            // The result block also goes straight to mapped host memory, followed by a per-sequence flag the host polls: the caller
-            // has its pose ~1 us after the last solve instead of after kernel retirement + a D2H copy + a stream synchronisation.
+            if(RGB)   // RGBDOdometryef.cpp:579-583 (seq_end repeats this test on the result, harmlessly)
+            {
+                const float dx = smath::sub(sh.tcurr[0], sh.tprev[0]), dy = smath::sub(sh.tcurr[1], sh.tprev[1]), dz = smath::sub(sh.tcurr[2], sh.tprev[2]);
+                const float n = __fsqrt_rn(smath::add(smath::add(smath::mul(dx, dx), smath::mul(dy, dy)), smath::mul(dz, dz)));
+                if((double)n > 0.3)
+                {
+                    for(int k = 0; k < 9; k++) sh.Rcurr[k] = sh.Rprev[k];
+                    for(int k = 0; k < 3; k++) sh.tcurr[k] = sh.tprev[k];
+                }
+            }
+            for(int k = 0; k < 9; k++) sh.res.Rcurr[k] = sh.Rcurr[k];
+            for(int k = 0; k < 3; k++) sh.res.tcurr[k] = sh.tcurr[k];
+        }
+        if(rank == 0 && host_results && warp0)
+        {
+            // The result block goes straight to mapped host memory, followed by a per-sequence flag the host polls: the caller has
+            // its pose ~1 us after the last solve instead of after kernel retirement + a D2H copy + a stream synchronisation.
             __syncwarp();
             const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
             uint2 * dst = reinterpret_cast<uint2 *>(host_results + seq);
-            for(int k = threadIdx.x; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
+            if(threadIdx.x < 6) dst[threadIdx.x] = src[threadIdx.x];   // Rcurr[9] | tcurr[3]
             __threadfence_system();
             __syncwarp();
             if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + seq) = host_seqno;
+        }
+        if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            if(wk.timeouts) sh.res.gn_iterations = -1;   // an inter-CTA wait gave up: the host turns this into an error
+            seq_end(sh, RGB, RGB_ONLY, leader ? &results[seq] : nullptr);
+        }
+        if(rank == 0 && host_results && warp0)   // `leader` is thread 0 of the group's first CTA: all of its warp 0 copies
+        {
+            // ... then the statistics (lastA, lastb, errors, counts) and a second flag (host_flags[batch + seq])
+            __syncwarp();
+            const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
+            uint2 * dst = reinterpret_cast<uint2 *>(host_results + seq);
+            for(int k = threadIdx.x + 6; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
+            __threadfence_system();
+            __syncwarp();
+            if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + L.batch + seq) = host_seqno;
         }
         if(GEN && leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();

@@ -75,7 +75,8 @@ struct slam_odom
     GnDevice gn;                      // device pointers of the persistent kernel's state
     BatchDevice be;                   // batched streaming engine (batch >= kBatchEngineMin)
     GnResult * h_results = nullptr;   // pinned, mapped [batch]
-    unsigned * h_flags = nullptr;     // pinned, mapped [batch]: completion sequence numbers written by the persistent kernel
+    unsigned * h_flags = nullptr;     // pinned, mapped [2][batch]: sequence numbers written by the persistent kernel: [0] pose out, [1] statistics out
+    bool stats_lazy = false;          // the statistics of the last track are still to be taken from h_results (second flag)
     unsigned zc_seqno = 0;            // sequence number of the launch in flight
     bool zero_copy = false;           // results + completion flag written by the kernel itself (single-launch loop only)
     bool zc_pending = false;
@@ -646,6 +647,7 @@ int host_loop_one(slam_odom * h, int b, float * trans, float * rot, bool rgbOnly
 }   // namespace
 
 static int finish_device_loop(slam_odom_t h, float * trans, float * rot);
+static int resolve_stats(slam_odom_t h);
 // The bookkeeping of an asynchronous track (the lastNextImage <-> nextImage swap of RGBDOdometryef.cpp:585-591, the statistics)
 // happens when it is collected.  Every entry point that writes one of those buffers collects a pending track first, so a
 // pipelined caller may prepare frame N + 1 before slam_odom_wait() without landing its images in the pre-swap buffers.
@@ -720,8 +722,8 @@ static int create_body(slam_odom * h, const slam_odom_params * params)
     }
 
     SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_results, sizeof(GnResult) * h->batch, cudaHostAllocMapped));
-    SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_flags, sizeof(unsigned) * h->batch, cudaHostAllocMapped));
-    memset(h->h_flags, 0, sizeof(unsigned) * h->batch);
+    SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_flags, sizeof(unsigned) * 2 * h->batch, cudaHostAllocMapped));
+    memset(h->h_flags, 0, sizeof(unsigned) * 2 * h->batch);
     {
         // zero-copy completion needs the device view of the pinned block to be the host pointer (unified addressing)
         void * dv = nullptr;
@@ -973,6 +975,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     else
     {
         const bool zc = h->zero_copy && !h->trace_on;
+        if(int rc2 = resolve_stats(h)) return rc2;   // the launch reuses the mapped result block
         if(zc) h->zc_seqno++;
         rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream, zc ? h->h_flags : nullptr, h->zc_seqno);
         h->zc_pending = zc && rc == SLAM_OK;
@@ -988,9 +991,9 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
 
 // Wait for the completion flags the persistent kernel writes into mapped host memory after its last solve.  The stream is polled
 // now and then so that a failed launch surfaces as an error instead of a hang.
-static int wait_zero_copy(slam_odom_t h)
+static int wait_zero_copy(slam_odom_t h, int which = 0)
 {
-    volatile unsigned * flags = h->h_flags;
+    volatile unsigned * flags = h->h_flags + (size_t)which * h->batch;
     for(unsigned spins = 1;; spins++)
     {
         bool all = true;
@@ -1023,20 +1026,18 @@ static int wait_zero_copy(slam_odom_t h)
     return SLAM_OK;
 }
 
-static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
+// The statistics of a zero-copy track reach the host a few microseconds after its pose (second flag): taken when somebody
+// asks for them, or before the next launch reuses the result block.
+static int copy_stats(slam_odom_t h)
 {
-    if(h->pending_async && h->zc_pending)
-    {
-        h->zc_pending = false;
-        if(int rc = wait_zero_copy(h)) return rc;
-    }
-    else
-        SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if(!h->pending_async) return SLAM_OK;
-    h->pending_async = false;
     for(int b = 0; b < h->batch; b++)
     {
         const GnResult & r = h->h_results[b];
+        if(r.gn_iterations < 0)
+        {
+            set_last_error("persistent kernel: a wait between thread blocks timed out; the results of this track are invalid");
+            return SLAM_ERR_CUDA;
+        }
         slam_odom_stats & st = h->stats[b];
         if(h->last_icp)
         {
@@ -1057,6 +1058,38 @@ static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
         memcpy(st.lastb, r.lastb, sizeof(st.lastb));
         st.so3_iterations = r.so3_iterations;
         st.gn_iterations = r.gn_iterations;
+    }
+    return SLAM_OK;
+}
+
+static int resolve_stats(slam_odom_t h)
+{
+    if(!h->stats_lazy) return SLAM_OK;
+    h->stats_lazy = false;
+    if(int rc = wait_zero_copy(h, 1)) return rc;
+    return copy_stats(h);
+}
+
+static int finish_device_loop(slam_odom_t h, float * trans, float * rot)
+{
+    bool lazy = false;
+    if(h->pending_async && h->zc_pending)
+    {
+        h->zc_pending = false;
+        if(int rc = wait_zero_copy(h, 0)) return rc;   // the pose is out; the statistics follow (resolve_stats)
+        lazy = true;
+    }
+    else
+        SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if(!h->pending_async) return SLAM_OK;
+    h->pending_async = false;
+    if(lazy)
+        h->stats_lazy = true;
+    else if(int rc = copy_stats(h))
+        return rc;
+    for(int b = 0; b < h->batch; b++)
+    {
+        const GnResult & r = h->h_results[b];
         if(trans) memcpy(trans + 3 * b, r.tcurr, 12);
         if(rot) memcpy(rot + 9 * b, r.Rcurr, 36);
         memcpy(&h->last_pose[12 * b], r.Rcurr, 36);
@@ -1128,6 +1161,7 @@ extern "C" int slam_odom_get_covariance(slam_odom_t h, double * out36)
     SLAM_ARG_CHECK(out36);
     if(h->pending_async)
         if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    if(int rc = resolve_stats(h)) return rc;
     for(int b = 0; b < h->batch; b++) smath::lu_inverse<double, 6>(h->stats[b].lastA, out36 + 36 * b);   // RGBDOdometryef.cpp:597-600
     return SLAM_OK;
 }
@@ -1138,6 +1172,7 @@ extern "C" int slam_odom_get_stats(slam_odom_t h, slam_odom_stats * stats)
     SLAM_ARG_CHECK(stats);
     if(h->pending_async)
         if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
+    if(int rc = resolve_stats(h)) return rc;
     for(int b = 0; b < h->batch; b++) stats[b] = h->stats[b];
     return SLAM_OK;
 }
