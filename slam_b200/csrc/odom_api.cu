@@ -73,7 +73,8 @@ struct slam_odom
 
     // device-resident loop
     GnDevice gn;                      // device pointers of the persistent kernel's state
-    BatchDevice be;                   // batched streaming engine (batch >= kBatchEngineMin)
+    BatchDevice be;                   // batched streaming engine (batch >= be_min)
+    int be_min = kBatchEngineMin;     // SLAM_BATCH_ENGINE_MIN overrides (development aid)
     GnResult * h_results = nullptr;   // pinned, mapped [batch]
     unsigned * h_flags = nullptr;     // pinned, mapped [2][batch]: sequence numbers written by the persistent kernel: [0] pose out, [1] statistics out
     bool stats_lazy = false;          // the statistics of the last track are still to be taken from h_results (second flag)
@@ -700,11 +701,12 @@ static int create_body(slam_odom * h, const slam_odom_params * params)
     SLAM_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, params->device));
     if(h->num_sms > kGnMaxCtas) h->num_sms = kGnMaxCtas;
 
+    if(const char * e = getenv("SLAM_BATCH_ENGINE_MIN")) h->be_min = std::max(2, atoi(e));
     ArenaPlan plan;
     for(int b = 0; b < h->batch; b++) layout_sequence(h, plan, nullptr);
     const size_t pose_off = plan.take(sizeof(float) * 12 * h->batch);
     const size_t gn_off = plan.take(gn_state_bytes(h->batch, h->num_sms));
-    const size_t be_off = h->batch >= kBatchEngineMin ? plan.take(batch_state_bytes(h->batch, h->geom, h->levels)) : 0;
+    const size_t be_off = h->batch >= h->be_min ? plan.take(batch_state_bytes(h->batch, h->geom, h->levels)) : 0;
     h->arena_bytes = plan.off;
     SLAM_CUDA_TRY(cudaMalloc((void **)&h->arena, h->arena_bytes));
     SLAM_CUDA_TRY(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -715,7 +717,7 @@ static int create_body(slam_odom * h, const slam_odom_params * params)
     h->d_poses12 = (float *)(h->arena + pose_off);
     SLAM_CUDA_TRY(cudaMallocHost((void **)&h->h_poses12, sizeof(float) * 12 * h->batch));
     gn_bind_state(h->gn, h->arena + gn_off, h->batch, h->num_sms);
-    if(h->batch >= kBatchEngineMin)
+    if(h->batch >= h->be_min)
     {
         batch_bind_state(h->be, h->arena + be_off, h->batch, h->geom, h->levels, h->gn.seq_in, h->gn.results);
         h->be.num_sms = h->num_sms;
@@ -789,7 +791,7 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
         if(sl.depth) cudaFree(sl.depth);
         if(sl.ready) cudaEventDestroy(sl.ready);
     }
-    if(h->batch >= kBatchEngineMin)
+    if(h->batch >= h->be_min)
     {
         batch_report();
         for(auto st : h->be.side) cudaStreamSynchronize(st);
@@ -901,7 +903,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
         return SLAM_ERR_UNSUPPORTED;
     }
-    const bool streaming = h->batch >= kBatchEngineMin && h->trace_level < 2;   // many sequences: lock-step streaming launches
+    const bool streaming = h->batch >= h->be_min && h->trace_level < 2;   // many sequences: lock-step streaming launches
     GnLaunch L = {};
     L.levels = h->levels;
     L.batch = h->batch;
@@ -1466,14 +1468,21 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         if(h->pending_async)
             if(int rc = finish_device_loop(h, nullptr, nullptr)) return rc;
         h->deriv_src_swapped = false;
-        SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
-        SLAM_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->fork_ev, 0));
         const size_t n0 = (size_t)h->geom[0].rows * h->geom[0].cols;
         // every launch covers all sequences of the batch (gridDim.y), see prep_kernels.cu: seq_shift
         const int B = h->batch;
         const size_t S = h->seq_stride;
         SeqBuffers & s = h->seq[0];
         int rc = SLAM_OK;
+        // Three-level pyramids of a size that tiles evenly: the whole preparation is ONE launch (k_prepare_frame: shared-memory
+        // tiles with halos, every level from the one above inside the block).  SLAM_ODOM_UNFUSED_PREP=1 keeps the per-level launches.
+        static const bool unfused = getenv("SLAM_ODOM_UNFUSED_PREP") != nullptr;
+        const bool one_launch = !unfused && h->levels == 3 && h->geom[0].rows % 4 == 0 && h->geom[0].cols % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 3) == 0;
+        if(!one_launch)
+        {
+            SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));
+            SLAM_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->fork_ev, 0));
+        }
         for(int b = 0; b < B; b++)
         {
             const float * q = poses16 + 16 * b;
@@ -1486,6 +1495,54 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         }
         // one sequence: the pose travels in the kernel parameters (no copy in front of the first launch of the chain)
         if(B > 1) SLAM_CUDA_TRY(cudaMemcpyAsync(h->d_poses12, h->h_poses12, sizeof(float) * 12 * B, cudaMemcpyHostToDevice, h->stream));
+        if(one_launch)
+        {
+            PrepFrameArgs a = {};
+            a.rows = h->geom[0].rows;
+            a.cols = h->geom[0].cols;
+            a.vsrc = mv;
+            a.nsrc = mn;
+            a.model_rgba = mrgba;
+            a.rgba = rgba;
+            a.depth_tmp = s.depth_tmp;
+            a.depth_cut = h->maxDepthRGB;
+            a.depth = depth;
+            a.depthCutoff = depth_cutoff;
+            for(int l = 0; l < 3; l++)
+            {
+                a.vprev[l] = s.vprev[l];
+                a.nprev[l] = s.nprev[l];
+                a.lastDepth[l] = s.lastDepth[l];
+                a.nextDepth[l] = s.nextDepth[l];
+                a.lastImage[l] = s.lastImage[l];
+                a.nextImage[l] = s.nextImage[l];
+                a.depth_l[l] = s.depth[l];
+                a.vcurr[l] = s.vcurr[l];
+                a.ncurr[l] = s.ncurr[l];
+                a.fx_inv[l] = 1.f / h->geom[l].fx;
+                a.fy_inv[l] = 1.f / h->geom[l].fy;
+                a.cx[l] = h->geom[l].cx;
+                a.cy[l] = h->geom[l].cy;
+            }
+            if(B == 1)
+            {
+                const float * q = h->h_poses12;
+                a.R.r0 = make_float3(q[0], q[1], q[2]);
+                a.R.r1 = make_float3(q[3], q[4], q[5]);
+                a.R.r2 = make_float3(q[6], q[7], q[8]);
+                a.t = make_float3(q[9], q[10], q[11]);
+            }
+            else
+                a.poses12 = h->d_poses12;
+            a.map_in_stride = n0 * 16;
+            a.rgba_stride = n0 * 4;
+            a.depth_in_stride = n0 * 2;
+            a.arena_stride = S;
+            if(int rc2 = launch_prepare_frame(a, h->stream, B)) return rc2;
+            h->launches++;
+            h->have_depth_tmp = true;
+        }
+        else
         {
             Mat3 R0 = {};
             float3 t0 = make_float3(0, 0, 0);
@@ -1527,17 +1584,20 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         }
         // the depth branch is enqueued after the model / RGB branch (it only waits for fork_ev); alternating the two chains' launches
         // was measured and makes no difference: the six preparation kernels (~45 us of device time) serialise on the GPU either way
-        for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
+        if(!one_launch)
         {
-            const LevelGeom & g = h->geom[l];
-            rc = launch_depth_level(l == 0 ? depth : s.depth[l], g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, depth_cutoff, s.vcurr[l], s.ncurr[l],
-                                    l + 1 < h->levels ? s.depth[l + 1] : nullptr, h->aux_stream, B, l == 0 ? n0 * 2 : S, S);
-            h->launches++;
+            for(int l = 0; l < h->levels && rc == SLAM_OK; l++)
+            {
+                const LevelGeom & g = h->geom[l];
+                rc = launch_depth_level(l == 0 ? depth : s.depth[l], g.rows, g.cols, g.fx, g.fy, g.cx, g.cy, depth_cutoff, s.vcurr[l], s.ncurr[l],
+                                        l + 1 < h->levels ? s.depth[l + 1] : nullptr, h->aux_stream, B, l == 0 ? n0 * 2 : S, S);
+                h->launches++;
+            }
+            if(rc) return rc;
+            SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
+            h->have_depth_tmp = true;
+            SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         }
-        if(rc) return rc;
-        SLAM_CUDA_TRY(cudaEventRecord(h->join_ev, h->aux_stream));
-        h->have_depth_tmp = true;
-        SLAM_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->join_ev, 0));
         if(defer_wait) return slam_odom_get_incremental_transformation_async(h, trans, rot, rgb_only, icp_weight, pyramid, fast_odom, so3);
         if(debug_timing)
         {

@@ -51,6 +51,39 @@ struct GnResult
 };
 
 // launchers implemented in prep_kernels.cu / reduce_kernels.cu
+// Arguments of the one-launch frame preparation (three-level pyramids), see k_prepare_frame in prep_kernels.cu.
+struct PrepFrameArgs
+{
+    int rows, cols;
+    int tiles_x, tiles, model_blocks;
+    // model + RGB-D role
+    const float4 * vsrc;
+    const float4 * nsrc;
+    const uchar4 * model_rgba;
+    const uchar4 * rgba;
+    float * vprev[3];
+    float * nprev[3];
+    float * depth_tmp;
+    float * lastDepth[3];
+    float * nextDepth[3];
+    unsigned char * lastImage[3];
+    unsigned char * nextImage[3];
+    Mat3 R;
+    float3 t;
+    const float * poses12;   // batched: per-sequence [R | t]
+    float depth_cut;
+    // sensor depth role
+    const unsigned short * depth;
+    unsigned short * depth_l[3];   // [1], [2]: the coarser depth levels (outputs)
+    float * vcurr[3];
+    float * ncurr[3];
+    float fx_inv[3], fy_inv[3], cx[3], cy[3];
+    float depthCutoff;
+    // batched launch (gridDim.y sequences): byte strides of the caller's input stacks and of the arena buffers
+    size_t map_in_stride, rgba_stride, depth_in_stride, arena_stride;
+};
+int launch_prepare_frame(PrepFrameArgs & a, cudaStream_t s, int nseq);
+
 struct ModelMapsArgs;
 struct DerivArgs;
 int launch_depth_level(const unsigned short * depth, int rows, int cols, float fx, float fy, float cx, float cy, float depthCutoff, float * vmap,

@@ -13,12 +13,30 @@
 namespace slam {
 
 // ------------------------------------------------------------------ per-pixel pieces
+// The window operators read their source through an accessor: a dense image in global memory, or a tile (core + halo) of it that a
+// block has staged in shared memory -- same taps, same order, same arithmetic.
+template <class T>
+struct ImageSrc
+{
+    const T * p;
+    int cols;
+    __device__ __forceinline__ T at(int r, int c) const { return p[r * cols + c]; }
+};
+template <class T, int PITCH>
+struct TileSrc
+{
+    const T * p;          // element (0, 0) of the IMAGE as seen through the tile: tile base - (r0 * PITCH + c0)
+    __device__ __forceinline__ TileSrc(const T * tile, int r0, int c0) : p(tile - (r0 * PITCH + c0)) {}
+    __device__ __forceinline__ T at(int r, int c) const { return p[r * PITCH + c]; }
+};
+
 // utils.cu:57-94  pyrDownGaussKernel (u16 depth, bilateral-gated 5x5, sigma_color = 30)
-__device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned short * src, int srows, int scols, int x, int y)
+template <class Src>
+__device__ __forceinline__ unsigned short pyr_down_u16_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
     const float sigma_color = 30;
-    const int center = src[(2 * y) * scols + 2 * x];
+    const int center = src.at(2 * y, 2 * x);
 
     const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
     const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
@@ -32,12 +50,11 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
     {
         // interior: the full 5x5 window; all 25 loads are issued before the first use.  Every product and partial sum
         // is exact in fp32 (16-bit values x multiples of 1/256), so only the final quotient rounds, as in the reference.
-        const unsigned short * p = src + (2 * y - 2) * scols + (2 * x - 2);
         int val[5][5];
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
-            for(int c = 0; c < 5; c++) val[r][c] = p[r * scols + c];
+            for(int c = 0; c < 5; c++) val[r][c] = src.at(2 * y - 2 + r, 2 * x - 2 + c);
         const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
 #pragma unroll
         for(int r = 0; r < 5; r++)
@@ -63,7 +80,7 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
             {
                 const int yi = r - 2, xi = c - 2;
                 in[r][c] = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
-                val[r][c] = in[r][c] ? (int)src[(2 * y + yi) * scols + 2 * x + xi] : 0;
+                val[r][c] = in[r][c] ? (int)src.at(2 * y + yi, 2 * x + xi) : 0;
             }
         const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};   // the reference's weights[abs(xi)] = {0.375, 0.25, 0.0625}, xi = c - 2
 #pragma unroll
@@ -77,6 +94,11 @@ __device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned shor
                 }
     }
     return static_cast<unsigned short>(static_cast<int>(sum / wall));
+}
+
+__device__ __forceinline__ unsigned short pyr_down_u16_pixel(const unsigned short * src, int srows, int scols, int x, int y)
+{
+    return pyr_down_u16_at(ImageSrc<unsigned short>{src, scols}, srows, scols, x, y);
 }
 
 // utils.cu:109-133 computeVmapKernel.  Returns false (vertex invalid) or the vertex.
@@ -110,7 +132,8 @@ __device__ __forceinline__ float gauss5_weight_rc(int a, int b)
     return wa * wb;
 }
 
-__device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int srows, int scols, int x, int y)
+template <class Src>
+__device__ __forceinline__ float pyr_down_gauss_f_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1);
@@ -122,12 +145,11 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
     {
         // interior: full window, weight index (4-r)*5 + (4-c) = the symmetric {1,4,6,4,1}^2 table; loads first,
         // then the reference's accumulation order (rows outer, columns inner), one FMA per finite tap.
-        const float * p = src + (2 * y - 2) * scols + (2 * x - 2);
         float v[5][5];
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
-            for(int c = 0; c < 5; c++) v[r][c] = p[r * scols + c];
+            for(int c = 0; c < 5; c++) v[r][c] = src.at(2 * y - 2 + r, 2 * x - 2 + c);
         const float w5[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
 #pragma unroll
         for(int r = 0; r < 5; r++)
@@ -151,7 +173,7 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
-            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? src[(cy + r) * scols + (cx0 + c)] : SLAM_QNAN;
+            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? src.at(cy + r, cx0 + c) : SLAM_QNAN;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
@@ -166,7 +188,13 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
     return (float)(sum / (float)count);
 }
 
-__device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned char * src, int srows, int scols, int x, int y)
+__device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int srows, int scols, int x, int y)
+{
+    return pyr_down_gauss_f_at(ImageSrc<float>{src, scols}, srows, scols, x, y);
+}
+
+template <class Src>
+__device__ __forceinline__ unsigned char pyr_down_gauss_u8_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
     const int tx = min(2 * x - D / 2 + D, scols - 1);
@@ -177,12 +205,11 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
     if(x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)
     {
         // interior: full window; integer arithmetic is exact here (<= 255 * 256), only the quotient rounds
-        const unsigned char * p = src + (2 * y - 2) * scols + (2 * x - 2);
         int v[5][5];
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
-            for(int c = 0; c < 5; c++) v[r][c] = p[r * scols + c];
+            for(int c = 0; c < 5; c++) v[r][c] = src.at(2 * y - 2 + r, 2 * x - 2 + c);
         const int w5[5] = {1, 4, 6, 4, 1};
         int isum = 0;
 #pragma unroll
@@ -204,7 +231,7 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
-            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? (int)src[(cy + r) * scols + (cx0 + c)] : 0;
+            for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? (int)src.at(cy + r, cx0 + c) : 0;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
@@ -217,6 +244,11 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned 
                 }
     }
     return (unsigned char)(sum / (float)count);
+}
+
+__device__ __forceinline__ unsigned char pyr_down_gauss_u8_pixel(const unsigned char * src, int srows, int scols, int x, int y)
+{
+    return pyr_down_gauss_u8_at(ImageSrc<unsigned char>{src, scols}, srows, scols, x, y);
 }
 
 // utils.cu:550-563 bgr2IntensityKernel (c0,c1,c2 = first three bytes of the RGBA8 texel)
@@ -238,6 +270,44 @@ __device__ __forceinline__ T * seq_shift(T * p, size_t stride_bytes)
     return p ? (T *)((const char *)p + (size_t)blockIdx.y * stride_bytes) : p;
 }
 
+// createVMap + createNMap (utils.cu:109-188) of one pixel, depth read through an accessor
+template <class Src>
+__device__ __forceinline__ void vertex_normal_pixel(const Src & depth, int u, int v, int rows, int cols, float fx_inv, float fy_inv, float cx, float cy,
+                                                    float depthCutoff, float * __restrict__ vmap, float * __restrict__ nmap)
+{
+    const int plane = rows * cols;
+    const int o = v * cols + u;
+
+    float3 v00;
+    const bool ok00 = vertex_from_depth(depth.at(v, u), u, v, fx_inv, fy_inv, cx, cy, depthCutoff, v00);
+    if(ok00)
+    {
+        vmap[o] = v00.x;
+        vmap[o + plane] = v00.y;
+        vmap[o + 2 * plane] = v00.z;
+    }
+    else
+        vmap[o] = SLAM_QNAN;   // y,z planes keep stale data, as in the reference
+
+    if(u == cols - 1 || v == rows - 1)
+    {
+        nmap[o] = SLAM_QNAN;
+        return;
+    }
+    float3 v01, v10;
+    const bool ok01 = vertex_from_depth(depth.at(v, u + 1), u + 1, v, fx_inv, fy_inv, cx, cy, depthCutoff, v01);
+    const bool ok10 = vertex_from_depth(depth.at(v + 1, u), u, v + 1, fx_inv, fy_inv, cx, cy, depthCutoff, v10);
+    if(ok00 && ok01 && ok10)
+    {
+        const float3 r = unit3(cross3(v01 - v00, v10 - v00));
+        nmap[o] = r.x;
+        nmap[o + plane] = r.y;
+        nmap[o + 2 * plane] = r.z;
+    }
+    else
+        nmap[o] = SLAM_QNAN;
+}
+
 // ------------------------------------------------------------------ fused depth level
 // One launch per pyramid level l of the CURRENT frame:
 //   blocks [0, nb_map)  : depth_l -> vmap_l, nmap_l  (createVMap + createNMap, utils.cu:109-188)
@@ -256,37 +326,7 @@ __global__ void __launch_bounds__(256) k_depth_level(const unsigned short * __re
         const int bx = blockIdx.x % nb_map_x, by = blockIdx.x / nb_map_x;
         const int u = bx * 32 + tx, v = by * 8 + ty;
         if(u >= cols || v >= rows) return;
-        const int plane = rows * cols;
-        const int o = v * cols + u;
-
-        float3 v00;
-        const bool ok00 = vertex_from_depth(depth[o], u, v, fx_inv, fy_inv, cx, cy, depthCutoff, v00);
-        if(ok00)
-        {
-            vmap[o] = v00.x;
-            vmap[o + plane] = v00.y;
-            vmap[o + 2 * plane] = v00.z;
-        }
-        else
-            vmap[o] = SLAM_QNAN;   // y,z planes keep stale data, as in the reference
-
-        if(u == cols - 1 || v == rows - 1)
-        {
-            nmap[o] = SLAM_QNAN;
-            return;
-        }
-        float3 v01, v10;
-        const bool ok01 = vertex_from_depth(depth[o + 1], u + 1, v, fx_inv, fy_inv, cx, cy, depthCutoff, v01);
-        const bool ok10 = vertex_from_depth(depth[o + cols], u, v + 1, fx_inv, fy_inv, cx, cy, depthCutoff, v10);
-        if(ok00 && ok01 && ok10)
-        {
-            const float3 r = unit3(cross3(v01 - v00, v10 - v00));
-            nmap[o] = r.x;
-            nmap[o + plane] = r.y;
-            nmap[o + 2 * plane] = r.z;
-        }
-        else
-            nmap[o] = SLAM_QNAN;
+        vertex_normal_pixel(ImageSrc<unsigned short>{depth, cols}, u, v, rows, cols, fx_inv, fy_inv, cx, cy, depthCutoff, vmap, nmap);
     }
     else
     {
@@ -601,6 +641,349 @@ __global__ void __launch_bounds__(256) k_rgbd_down_dual(const float * __restrict
     ddstNext[y * dcols + x] = d;
     idstLast[y * dcols + x] = pyr_down_gauss_u8_pixel(isrcLast, srows, scols, x, y);
     idstNext[y * dcols + x] = pyr_down_gauss_u8_pixel(isrcNext, srows, scols, x, y);
+}
+
+// ------------------------------------------------------------------ the preparation of a whole frame in ONE launch
+// Three-level pyramids (the reference's NUM_PYRS).  Every block owns a tile of 64 x 32 level-0 pixels = 32 x 16 of level 1 = 16 x 8 of
+// level 2 and produces every output of its tile on all three levels: the level-0 inputs of the tile PLUS the halo that the 5x5
+// windows of the coarser levels reach are staged in shared memory once, the level-1 tile (with its own halo) is computed from
+// that into shared memory, and level 2 from level 1 -- no level waits for another launch.  The halo pixels of levels 0 / 1 are
+// computed redundantly by neighbouring blocks with the same operands in the same order, so every output is bit-identical to the
+// per-level launches above (which stay for four-level pyramids, odd sizes and the operator-level entry points).
+//   blocks [0, tiles)         model + RGB-D role: k_model_maps + 2 x k_rgbd_down_dual
+//   blocks [tiles, 2 tiles)   sensor depth role:  3 x k_depth_level
+// window operators on tiles: same code as on images (the accessor is a template parameter)
+#define tile_pyr_down_f pyr_down_gauss_f_at
+#define tile_pyr_down_u8 pyr_down_gauss_u8_at
+#define tile_pyr_down_u16 pyr_down_u16_at
+#define tile_vertex_normal vertex_normal_pixel
+
+constexpr int kTileW = 64, kTileH = 32, kPrepThreads = 512;
+// model role: level-0 tile = core + 6 before / + 2 after (x: 64 + 9 = 73, y: 32 + 9 = 41); level-1 tile = core + 2 before / + 1 after
+constexpr int kM0W = 73, kM0H = 41, kM0P8 = 76, kM1W = 35, kM1H = 19, kM1P8 = 36;
+// depth role: the normals reach one pixel further on every level: level 0 77 x 45, level 1 37 x 21, level 2 17 x 9
+constexpr int kD0W = 77, kD0H = 45, kD0P = 78, kD1W = 37, kD1H = 21, kD1P = 38, kD2W = 17, kD2H = 9, kD2P = 18;
+
+template <class T>
+__device__ __forceinline__ T * shifted(T * p, size_t bytes) { return (T *)((const char *)p + bytes); }
+
+__global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFrameArgs a0)
+{
+    __shared__ __align__(16) unsigned char smem[kM0W * kM0H * 4 + 2 * kM0P8 * kM0H + kM1W * kM1H * 4 + 2 * kM1P8 * kM1H];
+    static_assert(sizeof(smem) >= (kD0P * kD0H + kD1P * kD1H + kD2P * kD2H) * 2, "the depth role's tiles alias the model role's");
+    const int t = threadIdx.x;
+    // batched launch: byte offsets of this sequence (zero for a single sequence)
+    const size_t sh_map = (size_t)blockIdx.y * a0.map_in_stride, sh_rgba = (size_t)blockIdx.y * a0.rgba_stride, sh_depth = (size_t)blockIdx.y * a0.depth_in_stride,
+                 sh_arena = (size_t)blockIdx.y * a0.arena_stride;
+    const int rows = a0.rows, cols = a0.cols;
+    const int rows1 = rows / 2, cols1 = cols / 2, rows2 = rows1 / 2, cols2 = cols1 / 2;
+    if((int)blockIdx.x < a0.model_blocks)
+    {
+        // ------------------------------------------------ model maps + both RGB-D pyramids
+        const int tbx = blockIdx.x % a0.tiles_x, tby = blockIdx.x / a0.tiles_x;
+        const float4 * vsrc = shifted(a0.vsrc, sh_map);
+        const float4 * nsrc = shifted(a0.nsrc, sh_map);
+        const uchar4 * model_rgba = shifted(a0.model_rgba, sh_rgba);
+        const uchar4 * rgba = shifted(a0.rgba, sh_rgba);
+        Mat3 R = a0.R;
+        float3 tr = a0.t;
+        if(a0.poses12)
+        {
+            const float * q = a0.poses12 + 12 * blockIdx.y;
+            R.r0 = make_float3(__ldg(q + 0), __ldg(q + 1), __ldg(q + 2));
+            R.r1 = make_float3(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5));
+            R.r2 = make_float3(__ldg(q + 6), __ldg(q + 7), __ldg(q + 8));
+            tr = make_float3(__ldg(q + 9), __ldg(q + 10), __ldg(q + 11));
+        }
+        float * d0 = reinterpret_cast<float *>(smem);
+        unsigned char * li0 = smem + kM0W * kM0H * 4;
+        unsigned char * ni0 = li0 + kM0P8 * kM0H;
+        float * d1 = reinterpret_cast<float *>(ni0 + kM0P8 * kM0H);
+        unsigned char * li1 = reinterpret_cast<unsigned char *>(d1 + kM1W * kM1H);
+        unsigned char * ni1 = li1 + kM1P8 * kM1H;
+        const int X0 = tbx * kTileW, Y0 = tby * kTileH;   // core origin, level 0
+        const int c0 = X0 - 6, r0 = Y0 - 6;               // tile origin, level 0
+        const int X1 = X0 / 2, Y1 = Y0 / 2, c1o = X1 - 2, r1o = Y1 - 2;
+
+        // halo of level 0: depth (z of the model vertex after the maxDepthRGB cut) and the two intensities, shared memory only.  The
+        // 945 halo pixels (6 rows above, 3 below, 6 columns left, 3 right of the core) are enumerated densely, four per thread, and
+        // every load of the block -- halo and core -- is issued before the first is consumed (the inputs come from DRAM).
+        constexpr int kHaloTop = 6 * kM0W, kHaloBottom = 3 * kM0W, kHaloSides = kTileH * 9, kHalo = kHaloTop + kHaloBottom + kHaloSides;
+        constexpr int kHaloPer = (kHalo + kPrepThreads - 1) / kPrepThreads;
+        float hz[kHaloPer];
+        uchar4 hl[kHaloPer], hn[kHaloPer];
+        int hs[kHaloPer];   // position in the tile, -1: nothing
+#pragma unroll
+        for(int k = 0; k < kHaloPer; k++)
+        {
+            const int hidx = t + k * kPrepThreads;
+            int r, c;
+            if(hidx < kHaloTop)
+            {
+                r = hidx / kM0W;
+                c = hidx - r * kM0W;
+            }
+            else if(hidx < kHaloTop + kHaloBottom)
+            {
+                r = (hidx - kHaloTop) / kM0W;
+                c = (hidx - kHaloTop) - r * kM0W;
+                r += 6 + kTileH;
+            }
+            else
+            {
+                const int q = hidx - kHaloTop - kHaloBottom;
+                r = q / 9;
+                c = q - r * 9;
+                r += 6;
+                c = c < 6 ? c : c + kTileW;
+            }
+            const int gx = c0 + c, gy = r0 + r;
+            const bool inb = hidx < kHalo && gx >= 0 && gx < cols && gy >= 0 && gy < rows;   // outside: never read, the windows are clipped to the image
+            hs[k] = inb ? r * kM0W + c : -1;
+            const int o = inb ? gy * cols + gx : 0;
+            hz[k] = inb ? __ldg(reinterpret_cast<const float *>(vsrc + o) + 2) : 0.f;
+            hl[k] = inb ? __ldg(model_rgba + o) : make_uchar4(0, 0, 0, 0);
+            hn[k] = inb ? __ldg(rgba + o) : make_uchar4(0, 0, 0, 0);
+        }
+        // core of level 0 + the model maps of all three levels: four consecutive lanes own one 4x4 pixel block, one 2x2 quarter
+        // each (k_model_maps): 128 blocks per tile, 512 lanes
+        float * vdst[3], * ndst[3];
+#pragma unroll
+        for(int l = 0; l < 3; l++)
+        {
+            vdst[l] = shifted(a0.vprev[l], sh_arena);
+            ndst[l] = shifted(a0.nprev[l], sh_arena);
+        }
+        float * depth_tmp = shifted(a0.depth_tmp, sh_arena);
+        float * lastDepth0 = shifted(a0.lastDepth[0], sh_arena);
+        float * nextDepth0 = shifted(a0.nextDepth[0], sh_arena);
+        unsigned char * lastImage0 = shifted(a0.lastImage[0], sh_arena);
+        unsigned char * nextImage0 = shifted(a0.nextImage[0], sh_arena);
+        const int bcols = cols / 4, brows = rows / 4;   // the host takes this path only when both are multiples of 4
+        const int plane0 = rows * cols, plane1 = rows1 * cols1, plane2 = rows2 * cols2;
+        // the core: the loads are issued before the halo is consumed
+        static_assert(kPrepThreads == (kTileW / 4) * (kTileH / 4) * 4, "one pass: four lanes per 4x4 block of the tile");
+        {
+            const int b = t >> 2, q = t & 3;
+            const int bx = tbx * (kTileW / 4) + (b & 15), by = tby * (kTileH / 4) + (b >> 4);
+            float4 cvs[4], cns[4];
+            uchar4 cml[4], cmn[4];
+            {
+                const bool lv = bx < bcols && by < brows;
+#pragma unroll
+                for(int k = 0; k < 4; k++)
+                {
+                    const int x = bx * 4 + 2 * (q & 1) + (k & 1), y = by * 4 + 2 * (q >> 1) + (k >> 1);
+                    const int o = lv ? y * cols + x : 0;
+                    cvs[k] = lv ? __ldg(vsrc + o) : make_float4(0, 0, 0, 0);
+                    cns[k] = lv ? __ldg(nsrc + o) : make_float4(0, 0, 0, 0);
+                    cml[k] = lv ? __ldg(model_rgba + o) : make_uchar4(0, 0, 0, 0);
+                    cmn[k] = lv ? __ldg(rgba + o) : make_uchar4(0, 0, 0, 0);
+                }
+            }
+            {
+#pragma unroll
+                for(int k = 0; k < kHaloPer; k++)
+                    if(hs[k] >= 0)
+                    {
+                        const int r = hs[k] / kM0W, c = hs[k] - r * kM0W;
+                        d0[hs[k]] = depth_from_vertex_z(hz[k], a0.depth_cut);
+                        li0[r * kM0P8 + c] = intensity_pixel(hl[k]);
+                        ni0[r * kM0P8 + c] = intensity_pixel(hn[k]);
+                    }
+            }
+            const bool live = bx < bcols && by < brows;   // lanes outside the image stay for the shuffles and touch no memory
+            const int qx = q & 1, qy = q >> 1;
+            float3 v0[2][2], n0[2][2];
+#pragma unroll
+            for(int j = 0; j < 2; j++)
+#pragma unroll
+                for(int i = 0; i < 2; i++)
+                {
+                    const int x = bx * 4 + 2 * qx + i, y = by * 4 + 2 * qy + j;
+                    float3 v = make_float3(SLAM_QNAN, SLAM_QNAN, SLAM_QNAN), n = v;
+                    if(live)
+                    {
+                        const int o = y * cols + x;
+                        const float4 vs = cvs[j * 2 + i];
+                        const float4 ns = cns[j * 2 + i];
+                        if(!(vs.z == 0))   // copyMapsKernel: validity of BOTH maps keyed on the vertex z
+                        {
+                            v = make_float3(vs.x, vs.y, vs.z);
+                            n = make_float3(ns.x, ns.y, ns.z);
+                        }
+                        const float dz = depth_from_vertex_z(vs.z, a0.depth_cut);
+                        const unsigned char li = intensity_pixel(cml[j * 2 + i]);
+                        const unsigned char ni = intensity_pixel(cmn[j * 2 + i]);
+                        depth_tmp[o] = dz;
+                        lastDepth0[o] = dz;
+                        nextDepth0[o] = dz;
+                        lastImage0[o] = li;
+                        nextImage0[o] = ni;
+                        const int sr = y - r0, sc = x - c0;
+                        d0[sr * kM0W + sc] = dz;
+                        li0[sr * kM0P8 + sc] = li;
+                        ni0[sr * kM0P8 + sc] = ni;
+                        store_map_pixel(vdst[0], ndst[0], plane0, o, v, n, true, R, tr);   // level-0 copyMaps + tranformMaps
+                    }
+                    v0[j][i] = v;
+                    n0[j][i] = n;
+                }
+            const float3 v1 = resize4<false>(v0[0][0], v0[0][1], v0[1][0], v0[1][1]);
+            const float3 n1 = resize4<true>(n0[0][0], n0[0][1], n0[1][0], n0[1][1]);
+            if(live) store_map_pixel(vdst[1], ndst[1], plane1, (by * 2 + qy) * cols1 + bx * 2 + qx, v1, n1, true, R, tr);
+            float3 qv[4], qn[4];   // the block's level-1 pixels in the order (0,0) (0,1) (1,0) (1,1) = quarters 0..3
+            const int base = (t & 31) & ~3;
+#pragma unroll
+            for(int k = 0; k < 4; k++)
+            {
+                qv[k] = make_float3(__shfl_sync(0xffffffffu, v1.x, base + k), __shfl_sync(0xffffffffu, v1.y, base + k), __shfl_sync(0xffffffffu, v1.z, base + k));
+                qn[k] = make_float3(__shfl_sync(0xffffffffu, n1.x, base + k), __shfl_sync(0xffffffffu, n1.y, base + k), __shfl_sync(0xffffffffu, n1.z, base + k));
+            }
+            if(live && q == 0)
+            {
+                const float3 v2 = resize4<false>(qv[0], qv[1], qv[2], qv[3]);
+                const float3 n2 = resize4<true>(qn[0], qn[1], qn[2], qn[3]);
+                store_map_pixel(vdst[2], ndst[2], plane2, by * cols2 + bx, v2, n2, true, R, tr);
+            }
+        }
+        __syncthreads();
+        // level 1 of the RGB-D pyramids (core + halo) from the level-0 tile
+        {
+            float * ddstLast = shifted(a0.lastDepth[1], sh_arena);
+            float * ddstNext = shifted(a0.nextDepth[1], sh_arena);
+            unsigned char * idstLast = shifted(a0.lastImage[1], sh_arena);
+            unsigned char * idstNext = shifted(a0.nextImage[1], sh_arena);
+            const TileSrc<float, kM0W> sd(d0, r0, c0);
+            const TileSrc<unsigned char, kM0P8> sl(li0, r0, c0), sn(ni0, r0, c0);
+            for(int idx = t; idx < kM1W * kM1H; idx += kPrepThreads)
+            {
+                const int r = idx / kM1W, c = idx - r * kM1W;
+                const int x = c1o + c, y = r1o + r;
+                if(x < 0 || x >= cols1 || y < 0 || y >= rows1) continue;
+                const float d = tile_pyr_down_f(sd, rows, cols, x, y);
+                const unsigned char l = tile_pyr_down_u8(sl, rows, cols, x, y);
+                const unsigned char n = tile_pyr_down_u8(sn, rows, cols, x, y);
+                d1[r * kM1W + c] = d;
+                li1[r * kM1P8 + c] = l;
+                ni1[r * kM1P8 + c] = n;
+                if(r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2)
+                {
+                    const int o = y * cols1 + x;
+                    ddstLast[o] = d;
+                    ddstNext[o] = d;
+                    idstLast[o] = l;
+                    idstNext[o] = n;
+                }
+            }
+        }
+        __syncthreads();
+        // level 2 from the level-1 tile
+        if(t < (kTileW / 4) * (kTileH / 4))
+        {
+            const int x = X0 / 4 + (t & 15), y = Y0 / 4 + (t >> 4);
+            if(x < cols2 && y < rows2)
+            {
+                const TileSrc<float, kM1W> sd(d1, r1o, c1o);
+                const TileSrc<unsigned char, kM1P8> sl(li1, r1o, c1o), sn(ni1, r1o, c1o);
+                const float d = tile_pyr_down_f(sd, rows1, cols1, x, y);
+                const int o = y * cols2 + x;
+                shifted(a0.lastDepth[2], sh_arena)[o] = d;
+                shifted(a0.nextDepth[2], sh_arena)[o] = d;
+                shifted(a0.lastImage[2], sh_arena)[o] = tile_pyr_down_u8(sl, rows1, cols1, x, y);
+                shifted(a0.nextImage[2], sh_arena)[o] = tile_pyr_down_u8(sn, rows1, cols1, x, y);
+            }
+        }
+    }
+    else
+    {
+        // ------------------------------------------------ the current frame's depth: pyramid + vertex / normal maps
+        const int tile = blockIdx.x - a0.model_blocks;
+        const int tbx = tile % a0.tiles_x, tby = tile / a0.tiles_x;
+        const unsigned short * depth = shifted(a0.depth, sh_depth);
+        unsigned short * z0 = reinterpret_cast<unsigned short *>(smem);
+        unsigned short * z1 = z0 + kD0P * kD0H;
+        unsigned short * z2 = z1 + kD1P * kD1H;
+        const int X0 = tbx * kTileW, Y0 = tby * kTileH;
+        const int c0 = X0 - 6, r0 = Y0 - 6;
+        const int X1 = X0 / 2, Y1 = Y0 / 2, c1o = X1 - 2, r1o = Y1 - 2;
+        const int X2 = X0 / 4, Y2 = Y0 / 4;
+        {
+            // the tile as 32-bit words (it starts at an even column and the image has an even number of columns), every load of the
+            // thread in flight before the first store
+            constexpr int kWordsPerRow = kD0P / 2, kWords = kWordsPerRow * kD0H, kPer = (kWords + kPrepThreads - 1) / kPrepThreads;
+            unsigned w[kPer];
+            int ws[kPer];
+#pragma unroll
+            for(int k = 0; k < kPer; k++)
+            {
+                const int idx = t + k * kPrepThreads;
+                const int r = idx / kWordsPerRow, c = 2 * (idx - r * kWordsPerRow);
+                const int gx = c0 + c, gy = r0 + r;
+                const bool inb = idx < kWords && gx >= 0 && gx + 1 < cols + 1 && gx < cols && gy >= 0 && gy < rows;
+                ws[k] = inb ? r * kWordsPerRow + (c >> 1) : -1;
+                w[k] = inb ? __ldg(reinterpret_cast<const unsigned *>(depth + gy * cols + gx)) : 0u;
+            }
+#pragma unroll
+            for(int k = 0; k < kPer; k++)
+                if(ws[k] >= 0) reinterpret_cast<unsigned *>(z0)[ws[k]] = w[k];
+        }
+        __syncthreads();
+        {
+            const TileSrc<unsigned short, kD0P> s0(z0, r0, c0);
+            float * vmap = shifted(a0.vcurr[0], sh_arena);
+            float * nmap = shifted(a0.ncurr[0], sh_arena);
+#pragma unroll 1
+            for(int idx = t; idx < kTileW * kTileH; idx += kPrepThreads)
+            {
+                const int u = X0 + (idx & (kTileW - 1)), v = Y0 + idx / kTileW;
+                if(u < cols && v < rows) tile_vertex_normal(s0, u, v, rows, cols, a0.fx_inv[0], a0.fy_inv[0], a0.cx[0], a0.cy[0], a0.depthCutoff, vmap, nmap);
+            }
+            unsigned short * dst1 = shifted(a0.depth_l[1], sh_arena);
+            for(int idx = t; idx < kD1W * kD1H; idx += kPrepThreads)
+            {
+                const int r = idx / kD1W, c = idx - r * kD1W;
+                const int x = c1o + c, y = r1o + r;
+                if(x < 0 || x >= cols1 || y < 0 || y >= rows1) continue;
+                const unsigned short d = tile_pyr_down_u16(s0, rows, cols, x, y);
+                z1[r * kD1P + c] = d;
+                if(r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2) dst1[y * cols1 + x] = d;
+            }
+        }
+        __syncthreads();
+        {
+            const TileSrc<unsigned short, kD1P> s1(z1, r1o, c1o);
+            float * vmap = shifted(a0.vcurr[1], sh_arena);
+            float * nmap = shifted(a0.ncurr[1], sh_arena);
+#pragma unroll 1
+            for(int idx = t; idx < (kTileW / 2) * (kTileH / 2); idx += kPrepThreads)
+            {
+                const int u = X1 + (idx & (kTileW / 2 - 1)), v = Y1 + idx / (kTileW / 2);
+                if(u < cols1 && v < rows1) tile_vertex_normal(s1, u, v, rows1, cols1, a0.fx_inv[1], a0.fy_inv[1], a0.cx[1], a0.cy[1], a0.depthCutoff, vmap, nmap);
+            }
+            unsigned short * dst2 = shifted(a0.depth_l[2], sh_arena);
+            if(t < kD2W * kD2H)
+            {
+                const int r = t / kD2W, c = t - r * kD2W;
+                const int x = X2 + c, y = Y2 + r;
+                if(x < cols2 && y < rows2)
+                {
+                    const unsigned short d = tile_pyr_down_u16(s1, rows1, cols1, x, y);
+                    z2[r * kD2P + c] = d;
+                    if(r < kTileH / 4 && c < kTileW / 4) dst2[y * cols2 + x] = d;
+                }
+            }
+        }
+        __syncthreads();
+        if(t < (kTileW / 4) * (kTileH / 4))
+        {
+            const TileSrc<unsigned short, kD2P> s2(z2, Y2, X2);
+            const int u = X2 + (t & 15), v = Y2 + (t >> 4);
+            if(u < cols2 && v < rows2)
+                tile_vertex_normal(s2, u, v, rows2, cols2, a0.fx_inv[2], a0.fy_inv[2], a0.cx[2], a0.cy[2], a0.depthCutoff, shifted(a0.vcurr[2], sh_arena),
+                                    shifted(a0.ncurr[2], sh_arena));
+        }
+    }
 }
 
 // ------------------------------------------------------------------ image derivatives
@@ -984,6 +1367,20 @@ int launch_depth_level(const unsigned short * depth, int rows, int cols, float f
     const int nb_down = next_depth ? tiles_32x8(rows / 2, cols / 2) : 0;
     k_depth_level<<<dim3(nb_map + nb_down, nseq), 256, 0, s>>>(depth, rows, cols, 1.f / fx, 1.f / fy, cx, cy, depthCutoff, vmap, nmap, next_depth, nb_map_x, nb_map,
                                                                in_stride, out_stride);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    return SLAM_OK;
+}
+
+int launch_prepare_frame(PrepFrameArgs & a, cudaStream_t s, int nseq)
+{
+    a.tiles_x = div_up(a.cols, kTileW);
+    a.tiles = a.tiles_x * div_up(a.rows, kTileH);
+    a.model_blocks = a.tiles;
+    int blocks = 2 * a.tiles;
+    static const char * only = getenv("SLAM_PREP_ONLY_ROLE");   // development aid (timing of one role; the results are incomplete)
+    if(only && only[0] == 'm') blocks = a.tiles;
+    if(only && only[0] == 'd') a.model_blocks = 0, blocks = a.tiles;
+    k_prepare_frame<<<dim3(blocks, nseq), kPrepThreads, 0, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }

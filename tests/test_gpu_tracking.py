@@ -11,7 +11,7 @@
 import numpy as np
 import pytest
 
-from tests.support import (frame_pair, planar_map_mismatch, run_frame, se3_jtj_literal_rel_err, se3_sums_rel_err, so3_sums_rel_err, to_device)
+from tests.support import (bits_equal_where, frame_pair, planar_map_mismatch, run_frame, se3_jtj_literal_rel_err, se3_sums_rel_err, so3_sums_rel_err, to_device)
 
 pytestmark = pytest.mark.gpu
 
@@ -460,6 +460,59 @@ def test_frame_call_equals_separate_calls(setup):
             if key[0] in (Tap.VMAP_CURR, Tap.NMAP_PREV):
                 ok = np.broadcast_to(~np.isnan(b[0]), b.shape)   # validity lives in the x plane
             assert np.array_equal(a[ok], b[ok]), f"tap {key} differs"
+
+
+@pytest.mark.parametrize("size", [(640, 480), (320, 240), (200, 152)])
+def test_one_launch_preparation_equals_separate_calls(setup, size):
+    """The frame-level entry point prepares a three-level frame in ONE launch (k_prepare_frame: shared-memory tiles with halos,
+    every pyramid level computed from the one above inside the block).  Every buffer it leaves behind must equal, bit for bit,
+    what the five reference-shaped calls (per-level launches, bit-exact against the reference in
+    test_prepared_buffers_bit_exact) leave -- also for sizes whose last tiles are partial."""
+    from slam_b200 import Tap
+    from tests.support import make_scene
+    w, h = size
+    scene, i = make_scene(w, h)
+    poses = scene.trajectory(40)
+    frames = [to_device(frame_pair(scene, poses, k)) for k in (30, 31)]
+    first = setup["torch"].from_numpy(scene.render_frame(poses[29])[1]).to("cuda:0")
+    setup["torch"].cuda.synchronize()
+    float_taps = (Tap.LAST_DEPTH, Tap.NEXT_DEPTH)
+    map_taps = (Tap.VMAP_CURR, Tap.NMAP_CURR, Tap.VMAP_PREV, Tap.NMAP_PREV)
+    int_taps = (Tap.DEPTH_U16, Tap.LAST_IMAGE, Tap.NEXT_IMAGE, Tap.LASTNEXT_IMAGE)
+    got = {}
+    for which in ("separate", "track_device"):
+        o = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+        o.initFirstRGB(first)
+        out = None
+        for d in frames:
+            pose = d["model_pose"]
+            if which == "separate":
+                out = run_frame(o, d, so3=True)
+            else:
+                out = o.track_device(o.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], pose, 3.0, 20.0), pose[:3, 3].copy(), pose[:3, :3].copy())
+        got[which] = (out, {(tap, l): o.tap(tap, l) for tap in float_taps + map_taps + int_taps for l in range(3)})
+        o.close()
+    a_out, a = got["track_device"]
+    b_out, b = got["separate"]
+    bad = []
+    for key in a:
+        tap, level = key
+        if tap == Tap.DEPTH_U16 and level == 0:
+            continue   # level 0 is the caller's own buffer in the frame-level call
+        if tap in int_taps:
+            if not np.array_equal(a[key], b[key]):
+                bad.append(f"tap {tap} level {level}: {(a[key] != b[key]).sum()} differ")
+        elif tap in float_taps:
+            if not np.array_equal(np.isnan(a[key]), np.isnan(b[key])):
+                bad.append(f"tap {tap} level {level}: NaN pattern")
+            elif not bits_equal_where(a[key], b[key], ~np.isnan(b[key])):
+                bad.append(f"tap {tap} level {level}: values")
+        else:
+            nan_diff, val_diff = planar_map_mismatch(a[key], b[key])
+            if nan_diff or val_diff:
+                bad.append(f"tap {tap} level {level}: nan {nan_diff} values {val_diff}")
+    assert not bad, "; ".join(bad)
+    assert np.array_equal(a_out[0], b_out[0]) and np.array_equal(a_out[1], b_out[1])
 
 
 def test_batch_equals_single_sequences(setup):

@@ -1,52 +1,47 @@
-"""Throughput of the tracker for batches of independent sequences on one GPU (development aid)."""
-import os, sys, time
+"""Development aid: frames/s of a batched handle at a given batch size (which engine runs is decided by the library;
+SLAM_BATCH_ENGINE_MIN=<n> moves the threshold).  usage: python tools/batch_time.py B [steps]"""
+import sys
+import time
 from pathlib import Path
+
 import numpy as np
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
-from slam_b200 import RGBDOdometry
-from tests.support import make_scene, frame_pair
 
-scene, intr = make_scene(640, 480)
-poses = scene.trajectory(1000)
-NF = 8
-frames = [frame_pair(scene, poses, 100 + 90 * i) for i in range(NF)]
-first = scene.render_frame(poses[99])[1]
-args = (intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from slam_b200 import RGBDOdometry          # noqa: E402
+from slam_b200.synth import Scene   # noqa: E402
 
-def stack(key, B, off):
-    arrs = [frames[(off + b) % NF][key] for b in range(B)]
-    a = np.stack([(x.view(np.int16) if x.dtype == np.uint16 else x) for x in arrs])
-    return torch.from_numpy(a).to("cuda:0")
-
-for B in [int(x) for x in (sys.argv[1:] or ["1", "2", "4", "8", "16", "32", "64"])]:
-    odo = RGBDOdometry(*args, batch=B)
-    sets = []
-    for off in range(2):
-        d = {k: stack(k, B, off) for k in ("depth", "rgba", "mv", "mn", "mrgba")}
-        P = np.stack([frames[(off + b) % NF]["model_pose"] for b in range(B)])
-        fr = odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, 3.0, 20.0)
-        sets.append((d, P, fr))
-    firstB = torch.from_numpy(np.stack([first] * B)).to("cuda:0")
-    torch.cuda.synchronize()
-    odo.initFirstRGB(firstB)
-    def step(i):
-        d, P, fr = sets[i % 2]
-        m = os.environ.get('SLAM_MODE', 'full')
-        kw = dict(icpWeight=100.0, so3=False) if m == 'icp' else dict(rgbOnly=True, so3=False) if m == 'rgb' else {}
-        return odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy(), **kw)
-    for i in range(4):
-        out = step(i)
-    torch.cuda.synchronize()
-    n = max(4, 64 // B)
-    odo.set_profiling(True); odo.get_profile(reset=True)
-    t0 = time.perf_counter()
-    for i in range(n):
-        out = step(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    ms, nl = odo.get_profile(reset=True)
-    gt = np.stack([frames[((n - 1) % 2 + b) % NF]["gt_pose"][:3, 3] for b in range(B)])
-    err = np.linalg.norm(out[0].reshape(B, 3) - gt, axis=1).max() * 1e3
-    print(f"batch {B:3d}: {n * B / dt:9.1f} frames/s   {dt / n * 1e3:8.3f} ms per batched step   gn kernel {ms / max(nl,1):8.3f} ms  max err {err:.2f} mm", flush=True)
-    odo.close()
+W, H = 640, 480
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+scene = Scene(width=W, height=H, fx=481.20, fy=-480.0, cx=319.5, cy=239.5)
+poses = scene.trajectory(12, seed=7)
+frames = []
+for k in range(1, 12):
+    depth, rgba = scene.render_frame(poses[k])
+    mv, mn, mrgba = scene.render_model(poses[k - 1])
+    frames.append(dict(depth=depth.view(np.int16), rgba=rgba, mv=mv, mn=mn, mrgba=mrgba, model_pose=poses[k - 1], gt=poses[k]))
+first = torch.from_numpy(scene.render_frame(poses[0])[1]).cuda()
+nf = len(frames)
+keys = ("depth", "rgba", "mv", "mn", "mrgba")
+odo = RGBDOdometry(W, H, 319.5, 239.5, 481.20, -480.0, device=0, batch=B)
+odo.initFirstRGB(torch.stack([first] * B))
+sets = []
+for off in (0, 1):
+    d = {k: torch.stack([torch.from_numpy(frames[(off + 3 * b) % nf][k]).cuda() for b in range(B)]) for k in keys}
+    P = np.stack([frames[(off + 3 * b) % nf]["model_pose"] for b in range(B)])
+    G = np.stack([frames[(off + 3 * b) % nf]["gt"][:3, 3] for b in range(B)])
+    sets.append((P, odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, 3.0, 20.0), G, d))
+torch.cuda.synchronize()
+for i in range(3):
+    P, fr, G, _ = sets[i % 2]
+    out = odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for i in range(steps):
+    P, fr, G, _ = sets[(3 + i) % 2]
+    out = odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+err = float(np.linalg.norm(out[0].reshape(B, 3) - G, axis=1).max() * 1e3)
+print(f"batch {B:3d}: {dt / steps * 1e3:8.3f} ms/step  {B * steps / dt:9.1f} frames/s  worst error {err:.3f} mm  launches/step {odo.launch_count() / (steps + 3):.1f}")
