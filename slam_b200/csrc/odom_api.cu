@@ -1477,7 +1477,9 @@ static int track_from_device_ptrs(slam_odom_t h, const unsigned short * depth, c
         // Three-level pyramids of a size that tiles evenly: the whole preparation is ONE launch (k_prepare_frame: shared-memory
         // tiles with halos, every level from the one above inside the block).  SLAM_ODOM_UNFUSED_PREP=1 keeps the per-level launches.
         static const bool unfused = getenv("SLAM_ODOM_UNFUSED_PREP") != nullptr;
-        const bool one_launch = !unfused && h->levels == 3 && h->geom[0].rows % 4 == 0 && h->geom[0].cols % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 3) == 0;
+        const uintptr_t align_all = reinterpret_cast<uintptr_t>(mv) | reinterpret_cast<uintptr_t>(mn) | reinterpret_cast<uintptr_t>(mrgba) | reinterpret_cast<uintptr_t>(rgba);
+        const bool one_launch = !unfused && h->levels == 3 && h->geom[0].rows % 4 == 0 && h->geom[0].cols % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 3) == 0 &&
+                                (align_all & 15) == 0;   // 16-byte cp.async chunks, 32-bit depth words
         if(!one_launch)
         {
             SLAM_CUDA_TRY(cudaEventRecord(h->fork_ev, h->stream));

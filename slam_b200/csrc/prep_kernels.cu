@@ -658,12 +658,20 @@ __global__ void __launch_bounds__(256) k_rgbd_down_dual(const float * __restrict
 #define tile_pyr_down_u16 pyr_down_u16_at
 #define tile_vertex_normal vertex_normal_pixel
 
-constexpr int kTileW = 64, kTileH = 32, kPrepThreads = 512;
-// model role: level-0 tile = core + 6 before / + 2 after (x: 64 + 9 = 73, y: 32 + 9 = 41); level-1 tile = core + 2 before / + 1 after
-constexpr int kM0W = 73, kM0H = 41, kM0P8 = 76, kM1W = 35, kM1H = 19, kM1P8 = 36;
-// depth role: the normals reach one pixel further on every level: level 0 77 x 45, level 1 37 x 21, level 2 17 x 9
-constexpr int kD0W = 77, kD0H = 45, kD0P = 78, kD1W = 37, kD1H = 21, kD1P = 38, kD2W = 17, kD2H = 9, kD2P = 18;
+// Tile = 64 x 36 level-0 pixels: a 640 x 480 frame is 10 x 14 = 140 tiles, at most one block of each role per SM of a 148-SM part
+// (with 64 x 32 tiles = 150 blocks two SMs carried two of the heavy model blocks and the launch took 1.6x the average SM's time).
+constexpr int kTileW = 64, kTileH = 36, kPrepThreads = (kTileW / 4) * (kTileH / 4) * 4;   // four lanes per 4x4 block: 576 threads
+// model role: level-0 tile = core + 6 before / + 2 after (the 5x5 windows of level 1, which itself needs + 2 before / + 1 after for level 2)
+constexpr int kM0W = kTileW + 9, kM0H = kTileH + 9, kM0P8 = (kM0W + 3) & ~3, kM1W = kTileW / 2 + 3, kM1H = kTileH / 2 + 3, kM1P8 = (kM1W + 3) & ~3;
+// depth role: the normals reach one pixel further on every level
+constexpr int kD0W = kTileW + 13, kD0H = kTileH + 13, kD0P = (kD0W + 1) & ~1, kD1W = kTileW / 2 + 5, kD1H = kTileH / 2 + 5, kD1P = (kD1W + 1) & ~1,
+              kD2W = kTileW / 4 + 1, kD2H = kTileH / 4 + 1, kD2P = (kD2W + 1) & ~1;
+static_assert(kTileW / 4 == 16, "the lane -> 4x4 block mapping below assumes 16 blocks per tile row");
 
+__device__ __forceinline__ void cp_async16_prep(void * smem, const void * gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 template <class T>
 __device__ __forceinline__ T * shifted(T * p, size_t bytes) { return (T *)((const char *)p + bytes); }
 
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
         // halo of level 0: depth (z of the model vertex after the maxDepthRGB cut) and the two intensities, shared memory only.  The
         // 945 halo pixels (6 rows above, 3 below, 6 columns left, 3 right of the core) are enumerated densely, four per thread, and
         // every load of the block -- halo and core -- is issued before the first is consumed (the inputs come from DRAM).
-        constexpr int kHaloTop = 6 * kM0W, kHaloBottom = 3 * kM0W, kHaloSides = kTileH * 9, kHalo = kHaloTop + kHaloBottom + kHaloSides;
+        constexpr int kHaloTop = 6 * kM0W, kHaloBottom = 3 * kM0W, kHaloSides = kTileH * 9, kHalo = kHaloTop + kHaloBottom + kHaloSides;   // 6 + 3 rows, 6 + 3 columns
         constexpr int kHaloPer = (kHalo + kPrepThreads - 1) / kPrepThreads;
         float hz[kHaloPer];
         uchar4 hl[kHaloPer], hn[kHaloPer];
@@ -761,25 +769,46 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
         unsigned char * nextImage0 = shifted(a0.nextImage[0], sh_arena);
         const int bcols = cols / 4, brows = rows / 4;   // the host takes this path only when both are multiples of 4
         const int plane0 = rows * cols, plane1 = rows1 * cols1, plane2 = rows2 * cols2;
-        // the core: the loads are issued before the halo is consumed
-        static_assert(kPrepThreads == (kTileW / 4) * (kTileH / 4) * 4, "one pass: four lanes per 4x4 block of the tile");
+        // the core's inputs (model vertex texels, both RGBA images: 24 B per pixel) go to shared memory by cp.async: all of them in flight
+        // at once with no register held for them, next to the halo loads above and the normal texels below (registers)
+        extern __shared__ __align__(16) unsigned char prep_dyn[];
+        float4 * s_v = reinterpret_cast<float4 *>(prep_dyn);
+        uchar4 * s_m = reinterpret_cast<uchar4 *>(s_v + kTileW * kTileH);
+        uchar4 * s_c = s_m + kTileW * kTileH;
+        {
+            const bool full_w = X0 + kTileW <= cols;
+            // 16-byte chunks: one texel of a float4 map, four texels of an RGBA8 image
+            for(int ch = t; ch < kTileW * kTileH; ch += kPrepThreads)
+            {
+                const int ry = ch / kTileW, rx = ch - ry * kTileW;
+                if(Y0 + ry < rows && X0 + rx < cols)
+                {
+                    const int o = (Y0 + ry) * cols + X0 + rx;
+                    cp_async16_prep(s_v + ch, vsrc + o);
+                }
+            }
+            for(int ch = t; ch < kTileW * kTileH / 4; ch += kPrepThreads)
+            {
+                const int ry = ch / (kTileW / 4), rx = 4 * (ch - ry * (kTileW / 4));
+                if(Y0 + ry < rows && (full_w || X0 + rx + 3 < cols))   // cols is a multiple of 4: a chunk is inside or outside as a whole
+                {
+                    const int o = (Y0 + ry) * cols + X0 + rx;
+                    cp_async16_prep(s_m + ry * kTileW + rx, model_rgba + o);
+                    cp_async16_prep(s_c + ry * kTileW + rx, rgba + o);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         {
             const int b = t >> 2, q = t & 3;
             const int bx = tbx * (kTileW / 4) + (b & 15), by = tby * (kTileH / 4) + (b >> 4);
-            float4 cvs[4], cns[4];
-            uchar4 cml[4], cmn[4];
+            float4 cns[4];
+#pragma unroll
+            for(int k = 0; k < 4; k++)
             {
                 const bool lv = bx < bcols && by < brows;
-#pragma unroll
-                for(int k = 0; k < 4; k++)
-                {
-                    const int x = bx * 4 + 2 * (q & 1) + (k & 1), y = by * 4 + 2 * (q >> 1) + (k >> 1);
-                    const int o = lv ? y * cols + x : 0;
-                    cvs[k] = lv ? __ldg(vsrc + o) : make_float4(0, 0, 0, 0);
-                    cns[k] = lv ? __ldg(nsrc + o) : make_float4(0, 0, 0, 0);
-                    cml[k] = lv ? __ldg(model_rgba + o) : make_uchar4(0, 0, 0, 0);
-                    cmn[k] = lv ? __ldg(rgba + o) : make_uchar4(0, 0, 0, 0);
-                }
+                const int x = bx * 4 + 2 * (q & 1) + (k & 1), y = by * 4 + 2 * (q >> 1) + (k >> 1);
+                cns[k] = lv ? __ldg(nsrc + y * cols + x) : make_float4(0, 0, 0, 0);
             }
             {
 #pragma unroll
@@ -792,6 +821,8 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                         ni0[r * kM0P8 + c] = intensity_pixel(hn[k]);
                     }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
             const bool live = bx < bcols && by < brows;   // lanes outside the image stay for the shuffles and touch no memory
             const int qx = q & 1, qy = q >> 1;
             float3 v0[2][2], n0[2][2];
@@ -805,7 +836,8 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                     if(live)
                     {
                         const int o = y * cols + x;
-                        const float4 vs = cvs[j * 2 + i];
+                        const int so = (y - Y0) * kTileW + (x - X0);
+                        const float4 vs = s_v[so];
                         const float4 ns = cns[j * 2 + i];
                         if(!(vs.z == 0))   // copyMapsKernel: validity of BOTH maps keyed on the vertex z
                         {
@@ -813,8 +845,8 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                             n = make_float3(ns.x, ns.y, ns.z);
                         }
                         const float dz = depth_from_vertex_z(vs.z, a0.depth_cut);
-                        const unsigned char li = intensity_pixel(cml[j * 2 + i]);
-                        const unsigned char ni = intensity_pixel(cmn[j * 2 + i]);
+                        const unsigned char li = intensity_pixel(s_m[so]);
+                        const unsigned char ni = intensity_pixel(s_c[so]);
                         depth_tmp[o] = dz;
                         lastDepth0[o] = dz;
                         nextDepth0[o] = dz;
@@ -848,50 +880,59 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
             }
         }
         __syncthreads();
-        // level 1 of the RGB-D pyramids (core + halo) from the level-0 tile
+        // level 1 of the RGB-D pyramids (core + halo) from the level-0 tile.  The work items are (image, pixel) pairs -- depth, then the
+        // model's intensity, then the frame's -- so that every warp of the block has the same share (a warp works on one image).
         {
-            float * ddstLast = shifted(a0.lastDepth[1], sh_arena);
-            float * ddstNext = shifted(a0.nextDepth[1], sh_arena);
-            unsigned char * idstLast = shifted(a0.lastImage[1], sh_arena);
-            unsigned char * idstNext = shifted(a0.nextImage[1], sh_arena);
             const TileSrc<float, kM0W> sd(d0, r0, c0);
             const TileSrc<unsigned char, kM0P8> sl(li0, r0, c0), sn(ni0, r0, c0);
-            for(int idx = t; idx < kM1W * kM1H; idx += kPrepThreads)
+            constexpr int kPx = kM1W * kM1H, kPxPad = (kPx + 31) & ~31;   // padded: an image starts at a warp boundary
+            for(int item = t; item < 3 * kPxPad; item += kPrepThreads)
             {
+                const int img = item / kPxPad, idx = item - img * kPxPad;
+                if(idx >= kPx) continue;
                 const int r = idx / kM1W, c = idx - r * kM1W;
                 const int x = c1o + c, y = r1o + r;
                 if(x < 0 || x >= cols1 || y < 0 || y >= rows1) continue;
-                const float d = tile_pyr_down_f(sd, rows, cols, x, y);
-                const unsigned char l = tile_pyr_down_u8(sl, rows, cols, x, y);
-                const unsigned char n = tile_pyr_down_u8(sn, rows, cols, x, y);
-                d1[r * kM1W + c] = d;
-                li1[r * kM1P8 + c] = l;
-                ni1[r * kM1P8 + c] = n;
-                if(r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2)
+                const bool core = r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2;
+                const int o = y * cols1 + x;
+                if(img == 0)
                 {
-                    const int o = y * cols1 + x;
-                    ddstLast[o] = d;
-                    ddstNext[o] = d;
-                    idstLast[o] = l;
-                    idstNext[o] = n;
+                    const float d = tile_pyr_down_f(sd, rows, cols, x, y);
+                    d1[r * kM1W + c] = d;
+                    if(core)
+                    {
+                        shifted(a0.lastDepth[1], sh_arena)[o] = d;
+                        shifted(a0.nextDepth[1], sh_arena)[o] = d;
+                    }
+                }
+                else
+                {
+                    const unsigned char v = tile_pyr_down_u8(img == 1 ? sl : sn, rows, cols, x, y);
+                    (img == 1 ? li1 : ni1)[r * kM1P8 + c] = v;
+                    if(core) shifted(img == 1 ? a0.lastImage[1] : a0.nextImage[1], sh_arena)[o] = v;
                 }
             }
         }
         __syncthreads();
-        // level 2 from the level-1 tile
-        if(t < (kTileW / 4) * (kTileH / 4))
+        // level 2 from the level-1 tile: one (image, pixel) item per thread
+        constexpr int kPx2 = (kTileW / 4) * (kTileH / 4);
+        static_assert(3 * kPx2 <= kPrepThreads, "one item per thread");
+        if(t < 3 * kPx2)
         {
-            const int x = X0 / 4 + (t & 15), y = Y0 / 4 + (t >> 4);
+            const int img = t / kPx2, k = t - img * kPx2;
+            const int x = X0 / 4 + (k & 15), y = Y0 / 4 + (k >> 4);
             if(x < cols2 && y < rows2)
             {
-                const TileSrc<float, kM1W> sd(d1, r1o, c1o);
-                const TileSrc<unsigned char, kM1P8> sl(li1, r1o, c1o), sn(ni1, r1o, c1o);
-                const float d = tile_pyr_down_f(sd, rows1, cols1, x, y);
                 const int o = y * cols2 + x;
-                shifted(a0.lastDepth[2], sh_arena)[o] = d;
-                shifted(a0.nextDepth[2], sh_arena)[o] = d;
-                shifted(a0.lastImage[2], sh_arena)[o] = tile_pyr_down_u8(sl, rows1, cols1, x, y);
-                shifted(a0.nextImage[2], sh_arena)[o] = tile_pyr_down_u8(sn, rows1, cols1, x, y);
+                if(img == 0)
+                {
+                    const float d = tile_pyr_down_f(TileSrc<float, kM1W>(d1, r1o, c1o), rows1, cols1, x, y);
+                    shifted(a0.lastDepth[2], sh_arena)[o] = d;
+                    shifted(a0.nextDepth[2], sh_arena)[o] = d;
+                }
+                else
+                    shifted(img == 1 ? a0.lastImage[2] : a0.nextImage[2], sh_arena)[o] =
+                        tile_pyr_down_u8(TileSrc<unsigned char, kM1P8>(img == 1 ? li1 : ni1, r1o, c1o), rows1, cols1, x, y);
             }
         }
     }
@@ -1380,7 +1421,14 @@ int launch_prepare_frame(PrepFrameArgs & a, cudaStream_t s, int nseq)
     static const char * only = getenv("SLAM_PREP_ONLY_ROLE");   // development aid (timing of one role; the results are incomplete)
     if(only && only[0] == 'm') blocks = a.tiles;
     if(only && only[0] == 'd') a.model_blocks = 0, blocks = a.tiles;
-    k_prepare_frame<<<dim3(blocks, nseq), kPrepThreads, 0, s>>>(a);
+    constexpr int kDyn = kTileW * kTileH * 24;   // the model role's input tile (float4 vertex, two RGBA8 texels per pixel)
+    static bool attr_set = false;
+    if(!attr_set)
+    {
+        SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k_prepare_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, kDyn));
+        attr_set = true;
+    }
+    k_prepare_frame<<<dim3(blocks, nseq), kPrepThreads, kDyn, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
     return SLAM_OK;
 }
