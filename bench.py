@@ -212,7 +212,7 @@ def run_reference_arm(args, rank, world):
 def workload_config(n_gpus):
     return {"workload": "configs[1]: ICP+RGB+SO3 frame-to-model odometry, synthetic ICL-NUIM-shaped 640x480 sequence, 3-level pyramid, 10/5/4 iterations, "
                         "icpWeight 10, open-loop inputs", "frames_distinct": N_FRAMES_DISTINCT, "sequences": n_gpus,
-            "l2_policy": f"inputs larger than L2: {N_FRAMES_DISTINCT} distinct frames x {BYTES_PER_FRAME_IN / 1e6:.1f} MB cycled", "parallelism": f"1 sequence per GPU x {n_gpus}"}
+            "l2_policy": f"inputs larger than L2: {N_FRAMES_DISTINCT} distinct frames x {BYTES_PER_FRAME_IN / 1e6:.1f} MB cycled", "parallelism": f"1 sequence per GPU x {n_gpus} (every rank tracks its own copy of the same sequence)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -228,7 +228,10 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     t_gen = time.perf_counter()
-    frames, first_rgba = make_frames(rank, N_FRAMES_DISTINCT)
+    # Every rank tracks its own copy of the SAME synthetic sequence: weak scaling wants identical work per GPU, and the time of a
+    # frame depends on its content (SO3 iterations until convergence, valid pixels) -- with a different trajectory per rank the
+    # max-over-ranks time measured the slowest trajectory (+17 us per frame on rank 1 of 2), not the system.
+    frames, first_rgba = make_frames(0, N_FRAMES_DISTINCT)
     log(f"[rank {rank}] generated {len(frames)} synthetic frames in {time.perf_counter() - t_gen:.1f}s")
 
     # ---- device-resident copies of all inputs
@@ -294,6 +297,7 @@ def run_ours(args, rank, local_rank, world):
     w1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop(w0, w1)
+    log(f"[rank {rank}] value loop: {dev_ms / args.steps * 1e3:.1f} us per step on this rank")
     gn_ms, gn_launches = odo.get_profile(reset=True)
     odo.set_profiling(False)
     launches = odo.launch_count() - launches0
@@ -455,7 +459,7 @@ def run_batched(args, rank, local_rank, world, dframes, hframes, dfirst, frames,
         G = np.stack([frames[(off + 5 * b) % nf]["gt_pose"][:3, 3] for b in range(B)])
         sets.append((d, P, odo.make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P, DEPTH_CUTOFF, MODEL_CUTOFF), G))
     torch.cuda.synchronize()
-    steps = max(4, min(40, args.steps // 16))
+    steps = max(16, min(40, args.steps // 16))   # at least 16 batched steps whatever --steps says
     warm = 3
 
     def step(i):
