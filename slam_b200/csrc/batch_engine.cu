@@ -682,6 +682,15 @@ kb_phase_a_staged(const GnLaunch L, const GnSeqIn * seqs, char * states, size_t 
                     d1[0] = dd.x; d1[1] = dd.y;
                 }
             }
+            // a pair of pixels whose current vertex or normal is NaN can never associate (reduce.cu:282-283), and dead pixels come in
+            // regions (beyond the depth cut-off, holes): when no lane of the warp has a live pixel or a candidate in this half trip,
+            // the projection, the gathers and the products are skipped as a whole
+            {
+                bool live = false;
+                if(kIcp && inside) live = (!isnan(vx[0]) && !isnan(nx[0])) || (!isnan(vx[1]) && !isnan(nx[1]));
+                if(kRgb) live = live || cm != 0u;
+                if(!__any_sync(0xffffffffu, live)) continue;
+            }
             float3 vg[PX], vp[PX], np[PX];
             int o[PX];
             bool ok[PX];
