@@ -547,7 +547,7 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
     # ---- configs[4]: ONE frame (rank 0's) for all ranks, hypotheses of SURVEY 8(d) (gt o SE3 noise, 5 cm / 3 deg, seed 0xBEEF,
     #      hypothesis 0 unperturbed), score = lastICPError with the inliers >= 1400 guard of lc/Ferns.cpp:275-279 (scaled by the level's
     #      pixel count), sharded over the ranks, winner by one NCCL min-all-reduce of the device-side packed key
-    from slam_b200.relocalise import broadcast_frame, perturbed_hypotheses, score_sharded_device
+    from slam_b200.relocalise import broadcast_frame, connect_peers, perturbed_hypotheses, score_sharded_device, score_sharded_peers
     d = dframes[3]
     fr = frames[3]
     bufs = [d["depth"], d["mv"], d["mn"]]
@@ -562,24 +562,36 @@ def run_other_configs(args, rank, local_rank, world, odo, dframes, frames, barri
     T, R = perturbed_hypotheses(gt, n_hyp)
     key = torch.full((1,), np.iinfo(np.int64).max, dtype=torch.int64, device=dev)
     ostream = torch.cuda.ExternalStream(odo.stream, device=dev)
+    # N > 1: the minimum over the ranks is taken over NVLink peer memory when the ranks can map each other's memory (CUDA IPC), with
+    # the NCCL min-all-reduce of the device word timed next to it
+    peers = world > 1 and connect_peers(odo, rank, world)
     for level in (0, 2):
         min_inl = 1400 >> (2 * level)
-        for _ in range(3):
-            best, err = score_sharded_device(odo, level, model, T, R, key, rank, world, min_inliers=min_inl, stream=ostream)
-        barrier()
-        t0 = time.perf_counter()
-        reps = 20
-        for _ in range(reps):
-            best, err = score_sharded_device(odo, level, model, T, R, key, rank, world, min_inliers=min_inl, stream=ostream)
-        barrier()
-        ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / reps
+
+        def timed(fn, reps=20):
+            for _ in range(3):
+                res = fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = fn()
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) * 1e3) / reps, res
+
+        nccl_ms, (best, err) = timed(lambda: score_sharded_device(odo, level, model, T, R, key, rank, world, min_inliers=min_inl, stream=ostream))
+        ms = nccl_ms
+        if peers:
+            ms, (pbest, perr) = timed(lambda: score_sharded_peers(odo, level, model, T, R, rank, world, min_inliers=min_inl))
+            assert (pbest, np.float32(perr)) == (best, np.float32(err)), f"configs[4] level {level}: peer-memory winner {pbest} / {perr} != NCCL winner {best} / {err}"
         # the winner must not depend on the sharding: every rank scores all hypotheses alone (untimed) and compares
         full_best, full_err, _ = score_sharded(odo, level, model, T, R, 0, 1, min_inliers=min_inl)
         assert (full_best, np.float32(full_err)) == (best, np.float32(err)), f"configs[4] level {level}: sharded winner {best} / {err} != single-GPU winner {full_best} / {full_err}"
         out[f"configs[4] level {level}"] = {"hypotheses": n_hyp, "per_gpu": n_hyp // world, "ms_per_frame": ms, "hypotheses_per_s": n_hyp / (ms * 1e-3),
                                             "best_index": best, "best_error": err, "min_inliers": min_inl, "winner_equals_single_gpu": True,
                                             "perturbation": "sigma_t 5 cm, sigma_r 3 deg, seed 0xBEEF, hypothesis 0 = ground truth",
-                                            "collective": "1 NCCL min-all-reduce of one device int64" if world > 1 else "none"}
+                                            "collective": ("none" if world == 1 else "minimum over NVLink peer memory: one 16-byte store per peer + poll, in the launch behind the "
+                                                           "scoring launch" if peers else "1 NCCL min-all-reduce of one device int64"),
+                                            "nccl_ms_per_frame": nccl_ms if world > 1 else None}
     # ---- the depth pre-filter in front of initICP (13x13 bilateral, compute-bound: 169 exp per pixel)
     if world == 1:
         from slam_b200.odometry import load_library

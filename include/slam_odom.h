@@ -219,6 +219,19 @@ int slam_odom_score_poses(slam_odom_t h, int seq, int level, int n, const float 
 int slam_odom_score_poses_best(slam_odom_t h, int seq, int level, int n, int index_base, float min_inliers, const float * prev_trans3,
                                const float * prev_rot9, const float * trans3n, const float * rot9n, unsigned long long * d_best_key);
 
+/* The sharded form of that decision over NVLink peer memory, one process per GPU on one node (no counterpart in the reference, which
+ * scores one candidate at a time, lc/Ferns.cpp:253-279).  Set-up, once: every rank calls slam_odom_peer_export (64 opaque bytes: the CUDA
+ * IPC handle of its slot array), the ranks exchange the handles by any means (bench.py: torch.distributed.all_gather_object) and call
+ * slam_odom_peer_connect with all `world` handles in rank order (world <= 16).  Per frame every rank calls
+ * slam_odom_score_poses_best_peers with ITS block of the hypotheses (n may be 0): the block is scored as by slam_odom_score_poses_best,
+ * a one-warp launch writes the rank's key into its slot on every peer and takes the minimum over the slots the peers wrote here, and
+ * the call returns the winning key of ALL ranks in *best_key (host memory): (lastICPError bits << 32 | global index), INT64_MAX if no
+ * hypothesis on any rank was acceptable.  Collective: every connected rank has to make the call for every frame. */
+int slam_odom_peer_export(slam_odom_t h, void * handle64);
+int slam_odom_peer_connect(slam_odom_t h, int rank, int world, const void * handles64);
+int slam_odom_score_poses_best_peers(slam_odom_t h, int seq, int level, int n, int index_base, float min_inliers, const float * prev_trans3,
+                                     const float * prev_rot9, const float * trans3n, const float * rot9n, unsigned long long * best_key);
+
 /* Kernel-launch counter (for bench.py's gpu_launches). */
 long long slam_odom_launch_count(slam_odom_t h);
 /* CUDA-event timing of the Gauss-Newton reduction kernels on the handle's stream: enable, run, then read the

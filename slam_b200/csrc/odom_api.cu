@@ -45,6 +45,67 @@ struct StagingSlot
     float depth_cutoff = 0, model_depth_cutoff = 0;
 };
 
+// ---- cross-GPU minimum over peer memory (NVLink / NVSwitch), for the sharded hypothesis scoring
+// Every rank owns an array of slots, one per rank and frame parity, in its own HBM; the arrays are exchanged as CUDA IPC handles
+// once.  Per frame ONE warp per rank writes (key, frame number) into its slot on every peer -- the frame number with release
+// semantics at system scope, after the key -- and then polls its own array until every peer's frame number has arrived: an
+// all-gather of 16 bytes per peer and a min, in the launch that follows the scoring launch, with no collective library and no host
+// round trip in between.  Two parities: a rank may already publish frame s + 1 while a slow peer still reads frame s (it cannot get
+// to s + 2 without that peer's s + 1).
+constexpr int kMaxPeers = 16;
+struct PeerSlot
+{
+    unsigned long long key, seq;
+};
+struct PeerPtrs
+{
+    PeerSlot * p[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(32) k_peer_min(const PeerPtrs peers, const int me, const int world, const unsigned long long * my_key, const unsigned long long seq,
+                                                 PeerSlot * local, unsigned long long * result)
+{
+    const int r = threadIdx.x;
+    unsigned long long k = ~0ull;
+    bool gave_up = false;
+    if(r < world)
+    {
+        const unsigned long long mine = *my_key;   // left by the scoring launch in front of this one
+        PeerSlot * dst = peers.p[r] + (seq & 1ull) * kMaxPeers + me;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&dst->key), "l"(mine) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->seq), "l"(seq) : "memory");
+        const PeerSlot * src = local + (seq & 1ull) * kMaxPeers + r;
+        unsigned long long got = 0ull, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for(;;)
+        {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&src->seq) : "memory");
+            if(got == seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if(t1 - t0 > 10000000000ull)   // 10 s: a peer that never publishes must not hang this GPU
+            {
+                gave_up = true;
+                break;
+            }
+        }
+        if(!gave_up) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(k) : "l"(&src->key) : "memory");
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+        k = other < k ? other : k;
+    }
+    const unsigned lost = __ballot_sync(0xffffffffu, gave_up);
+    if(r == 0)
+    {
+        result[0] = k;
+        result[2] = (unsigned long long)__popc(lost);
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(result + 1) = seq;
+    }
+}
+
 struct slam_odom
 {
     slam_odom_params p;
@@ -67,6 +128,14 @@ struct slam_odom
     char * score_ws = nullptr;        // pose-hypothesis scoring: poses | partials | tickets | results (grown on demand)
     size_t score_ws_bytes = 0;
     float * h_score_poses = nullptr;  // pinned staging of the hypotheses
+    // hypothesis scoring across GPUs over peer memory (slam_odom_peer_export / _connect / _score_poses_best_peers)
+    PeerSlot * peer_local = nullptr;              // [2][kMaxPeers] slots the other ranks write into (IPC-exported allocation)
+    PeerSlot * peer_ptr[kMaxPeers] = {};          // rank r's slot array as mapped into this process (own rank: peer_local)
+    int peer_rank = -1, peer_world = 0;
+    unsigned long long peer_seq = 0;
+    unsigned long long * d_peer_key = nullptr;    // this rank's best key of the frame being scored
+    unsigned long long * h_peer_result = nullptr; // mapped pinned: [0] winner key, [1] sequence number, [2] polls that gave up, [3] INT64_MAX (source of the reset copy)
+    unsigned long long * d_peer_result = nullptr;
     int score_ws_n = -1, score_ws_plane = -1;   // layout the workspace was last cleared for
     float * d_poses12 = nullptr;      // [batch][12] model poses (R row-major | t) of the batched preparation launches
     float * h_poses12 = nullptr;      // pinned staging of the same
@@ -806,6 +875,11 @@ extern "C" int slam_odom_destroy(slam_odom_t h)
     if(h->h_poses12) cudaFreeHost(h->h_poses12);
     if(h->score_ws) cudaFree(h->score_ws);
     if(h->h_score_poses) cudaFreeHost(h->h_score_poses);
+    for(int r = 0; r < h->peer_world; r++)
+        if(r != h->peer_rank && h->peer_ptr[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
+    if(h->peer_local) cudaFree(h->peer_local);
+    if(h->d_peer_key) cudaFree(h->d_peer_key);
+    if(h->h_peer_result) cudaFreeHost(h->h_peer_result);
     if(h->filtered_depth) cudaFree(h->filtered_depth);
     if(h->compute_done) cudaEventDestroy(h->compute_done);
     if(h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1279,6 +1353,122 @@ extern "C" int slam_odom_score_poses_best(slam_odom_t h, int seq, int level, int
     if(int rc = set_device(h)) return rc;
     float * out2 = nullptr;
     return enqueue_score_poses(h, seq, level, n, prev_trans3, prev_rot9, trans3n, rot9n, &out2, d_best_key, index_base, min_inliers);
+}
+
+extern "C" int slam_odom_peer_export(slam_odom_t h, void * handle64)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(handle64);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI passes the handle as 64 opaque bytes");
+    if(int rc = set_device(h)) return rc;
+    if(!h->peer_local)
+    {
+        SLAM_CUDA_TRY(cudaMalloc((void **)&h->peer_local, sizeof(PeerSlot) * 2 * kMaxPeers));
+        SLAM_CUDA_TRY(cudaMemset(h->peer_local, 0, sizeof(PeerSlot) * 2 * kMaxPeers));
+        SLAM_CUDA_TRY(cudaMalloc((void **)&h->d_peer_key, 8));
+        SLAM_CUDA_TRY(cudaHostAlloc((void **)&h->h_peer_result, 4 * 8, cudaHostAllocMapped));
+        memset(h->h_peer_result, 0, 4 * 8);
+        h->h_peer_result[3] = 0x7fffffffffffffffull;
+        SLAM_CUDA_TRY(cudaHostGetDevicePointer((void **)&h->d_peer_result, h->h_peer_result, 0));
+    }
+    cudaIpcMemHandle_t hd;
+    SLAM_CUDA_TRY(cudaIpcGetMemHandle(&hd, h->peer_local));
+    memcpy(handle64, &hd, 64);
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_peer_connect(slam_odom_t h, int rank, int world, const void * handles64)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(handles64 && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world);
+    if(!h->peer_local)
+    {
+        set_last_error("slam_odom_peer_connect: call slam_odom_peer_export first");
+        return SLAM_ERR_ORDER;
+    }
+    if(h->peer_world)
+    {
+        set_last_error("slam_odom_peer_connect: already connected");
+        return SLAM_ERR_ORDER;
+    }
+    if(int rc = set_device(h)) return rc;
+    for(int r = 0; r < world; r++)
+    {
+        if(r == rank)
+        {
+            h->peer_ptr[r] = h->peer_local;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char *)handles64 + 64 * r, 64);
+        void * p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+        if(e != cudaSuccess)
+        {
+            for(int q = 0; q < r; q++)
+                if(q != rank && h->peer_ptr[q]) cudaIpcCloseMemHandle(h->peer_ptr[q]);
+            for(int q = 0; q < kMaxPeers; q++) h->peer_ptr[q] = nullptr;
+            set_last_error(std::string("slam_odom_peer_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            return SLAM_ERR_CUDA;
+        }
+        h->peer_ptr[r] = (PeerSlot *)p;
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_score_poses_best_peers(slam_odom_t h, int seq, int level, int n, int index_base, float min_inliers, const float * prev_trans3,
+                                                const float * prev_rot9, const float * trans3n, const float * rot9n, unsigned long long * best_key)
+{
+    if(int rc = check_handle(h)) return rc;
+    SLAM_ARG_CHECK(seq >= 0 && seq < h->batch && level >= 0 && level < h->levels && n >= 0 && n <= 65535 && index_base >= 0 && best_key);
+    SLAM_ARG_CHECK(n == 0 || (prev_trans3 && prev_rot9 && trans3n && rot9n));
+    if(!h->peer_world)
+    {
+        set_last_error("slam_odom_score_poses_best_peers: not connected (slam_odom_peer_export / _connect)");
+        return SLAM_ERR_ORDER;
+    }
+    if(int rc = set_device(h)) return rc;
+    const unsigned long long fno = ++h->peer_seq;
+    // this rank's key starts at INT64_MAX (a rank without hypotheses or without an acceptable one publishes that)
+    SLAM_CUDA_TRY(cudaMemcpyAsync(h->d_peer_key, h->h_peer_result + 3, 8, cudaMemcpyHostToDevice, h->stream));
+    if(n > 0)
+    {
+        float * out2 = nullptr;
+        if(int rc = enqueue_score_poses(h, seq, level, n, prev_trans3, prev_rot9, trans3n, rot9n, &out2, h->d_peer_key, index_base, min_inliers)) return rc;
+    }
+    PeerPtrs pp = {};
+    for(int r = 0; r < h->peer_world; r++) pp.p[r] = h->peer_ptr[r];
+    k_peer_min<<<1, 32, 0, h->stream>>>(pp, h->peer_rank, h->peer_world, h->d_peer_key, fno, h->peer_local, h->d_peer_result);
+    SLAM_CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    volatile unsigned long long * res = h->h_peer_result;
+    for(unsigned spins = 1; res[1] != fno; spins++)
+    {
+        if((spins & 0x3fff) == 0)
+        {
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            if(q == cudaSuccess) break;
+            if(q != cudaErrorNotReady)
+            {
+                set_last_error(std::string("peer minimum: ") + cudaGetErrorString(q));
+                return SLAM_ERR_CUDA;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if(res[1] != fno || res[2] != 0)
+    {
+        set_last_error("peer minimum: a peer did not publish its key in time");
+        return SLAM_ERR_CUDA;
+    }
+    *best_key = res[0];
+    return SLAM_OK;
 }
 
 extern "C" long long slam_odom_launch_count(slam_odom_t h) { return h ? h->launches : 0; }

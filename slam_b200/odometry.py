@@ -126,6 +126,9 @@ def load_library():
     lib.slam_op_depth_bilateral.argtypes = [vp, i, i, f, vp, i, vp]
     lib.slam_odom_score_poses.argtypes = [vp, i, i, i, fp, fp, fp, fp, fp, fp]
     lib.slam_odom_score_poses_best.argtypes = [vp, i, i, i, i, f, fp, fp, fp, fp, vp]
+    lib.slam_odom_peer_export.argtypes = [vp, vp]
+    lib.slam_odom_peer_connect.argtypes = [vp, i, i, vp]
+    lib.slam_odom_score_poses_best_peers.argtypes = [vp, i, i, i, i, f, fp, fp, fp, fp, C.POINTER(C.c_ulonglong)]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
     lib.slam_odom_get_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
@@ -378,6 +381,30 @@ class RGBDOdometry:
         assert len(t) == len(r) and len(t) > 0
         _check(self.lib, self.lib.slam_odom_score_poses_best(self._h, seq, int(level), len(t), int(index_base), float(min_inliers), _fptr(pt), _fptr(pr),
                                                              _fptr(t), _fptr(r), _addr(key_tensor)))
+
+    def peer_export(self) -> bytes:
+        """The CUDA IPC handle (64 bytes) of this handle's slot array for the cross-GPU minimum (see slam_odom.h)."""
+        buf = C.create_string_buffer(64)
+        _check(self.lib, self.lib.slam_odom_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        buf = C.create_string_buffer(handles, len(handles))
+        _check(self.lib, self.lib.slam_odom_peer_connect(self._h, int(rank), int(world), buf))
+
+    def score_poses_best_peers(self, level, prev_pose, trans_n, rot_n, index_base=0, min_inliers=1.0, seq=0) -> int:
+        """Score this rank's block of hypotheses and return the winning packed key of ALL connected ranks (collective call)."""
+        prev = np.ascontiguousarray(prev_pose, dtype=np.float32)
+        pt = np.ascontiguousarray(prev[:3, 3]).copy()
+        pr = np.ascontiguousarray(prev[:3, :3]).reshape(-1).copy()
+        t = np.ascontiguousarray(trans_n, dtype=np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(rot_n, dtype=np.float32).reshape(-1, 9)
+        assert len(t) == len(r)
+        key = C.c_ulonglong(0)
+        _check(self.lib, self.lib.slam_odom_score_poses_best_peers(self._h, seq, int(level), len(t), int(index_base), float(min_inliers), _fptr(pt), _fptr(pr),
+                                                                   _fptr(t) if len(t) else None, _fptr(r) if len(r) else None, C.byref(key)))
+        return int(key.value)
 
     def set_profiling(self, on=True):
         _check(self.lib, self.lib.slam_odom_set_profiling(self._h, int(on)))

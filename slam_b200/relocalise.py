@@ -131,6 +131,43 @@ def score_sharded_device(odo, level, prev_pose, trans_n, rot_n, key_tensor, rank
     return i, e
 
 
+def connect_peers(odo, rank=None, world=None, group=None) -> bool:
+    """Exchange the CUDA IPC handles of the ranks' slot arrays (once per handle) so that score_sharded_peers can take the minimum
+    over NVLink peer memory.  Returns False (and leaves the handle unconnected) when the processes cannot map each other's memory --
+    the caller then stays on score_sharded_device (NCCL)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    mine = odo.peer_export()
+    handles = [None] * world
+    if world > 1:
+        dist.all_gather_object(handles, mine, group=group)
+    else:
+        handles[0] = mine
+    ok = True
+    try:
+        odo.peer_connect(rank, world, b"".join(handles))
+    except Exception:
+        ok = False
+    if world > 1:   # all or none
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        ok = all(flags)
+    return ok
+
+
+def score_sharded_peers(odo, level, prev_pose, trans_n, rot_n, rank=0, world=1, min_inliers=1.0):
+    """Product path on one NVLink node: this rank's block of hypotheses is scored, one warp writes the block's best packed key into
+    every peer's memory and takes the minimum of what the peers wrote here (slam_odom_score_poses_best_peers) -- no collective
+    library, no host round trip between scoring and reduction.  Collective: every rank calls it.  -> (best global index, its error)."""
+    trans_n = np.asarray(trans_n, np.float32).reshape(-1, 3)
+    rot_n = np.asarray(rot_n, np.float32).reshape(-1, 3, 3)
+    lo, hi = shard_range(len(trans_n), rank, world)
+    key = odo.score_poses_best_peers(level, prev_pose, trans_n[lo:hi], rot_n[lo:hi], index_base=lo, min_inliers=min_inliers)
+    e, i = unpack_key(key)
+    return i, e
+
+
 class _null_context:
     def __enter__(self):
         return self

@@ -290,7 +290,7 @@ def _nccl_worker(rank, world, port, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     from slam_b200 import RGBDOdometry
-    from slam_b200.relocalise import INT64_MAX, broadcast_frame, perturbed_hypotheses, score_sharded, score_sharded_device
+    from slam_b200.relocalise import INT64_MAX, broadcast_frame, connect_peers, perturbed_hypotheses, score_sharded, score_sharded_device, score_sharded_peers
     from tests.support import make_scene
     scene, intr = make_scene(640, 480)
     poses = scene.trajectory(1000)
@@ -309,10 +309,19 @@ def _nccl_worker(rank, world, port, out):
     key = torch.full((1,), INT64_MAX, dtype=torch.int64, device=dev)
     stream = torch.cuda.ExternalStream(odo.stream, device=dev)
     res = {}
+    peers = connect_peers(odo, rank, world)
     for level in (0, 2):
         best, err = score_sharded_device(odo, level, model, T, R, key, rank, world, min_inliers=1400 >> (2 * level), stream=stream)
         alone = score_sharded(odo, level, model, T, R, 0, 1, min_inliers=1400 >> (2 * level))
         res[level] = (best, float(np.float32(err)), alone[0], float(np.float32(alone[1])))
+        if peers:
+            # the same decision over NVLink peer memory (three frames in a row: both slot parities and their reuse), and a frame
+            # in which no hypothesis is acceptable anywhere (every rank publishes INT64_MAX)
+            for _ in range(3):
+                pb, pe = score_sharded_peers(odo, level, model, T, R, rank, world, min_inliers=1400 >> (2 * level))
+                assert (pb, float(np.float32(pe))) == res[level][:2], f"rank {rank} level {level}: peers {pb} / {pe} != NCCL {res[level][:2]}"
+            assert odo.score_poses_best_peers(level, model, T[:0], R[:0]) == INT64_MAX   # collective: both ranks call it
+    res["peers"] = peers
     out[rank] = res
     odo.close()
     dist.destroy_process_group()
@@ -329,6 +338,7 @@ def test_hypotheses_sharded_over_two_gpus_with_nccl(built):
     out = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, 29611, out), nprocs=2, join=True)
     assert len(out) == 2
+    assert out[0]["peers"] == out[1]["peers"]
     for level in (0, 2):
         b0, e0, a0, ae0 = out[0][level]
         b1, e1, a1, ae1 = out[1][level]
