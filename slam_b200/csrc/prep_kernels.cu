@@ -55,16 +55,23 @@ __device__ __forceinline__ unsigned short pyr_down_u16_at(const Src & src, int s
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++) val[r][c] = src.at(2 * y - 2 + r, 2 * x - 2 + c);
-        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+        // The reference accumulates val * w[c] * w[r] and w[c] * w[r] in fp32 with w = {1, 4, 6, 4, 1} / 16: every term and every
+        // partial sum is a multiple of 1/256 below 2^16, hence exact -- so the same two sums are taken in integers (one IMAD and one
+        // IADD per tap instead of a conversion, two multiplies and two adds) and scaled by 1/256 exactly; the quotient, the only
+        // rounding, gets the identical operands.
+        const int w5i[5] = {1, 4, 6, 4, 1};
+        int isum = 0, iwall = 0;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++)
-                if(abs(val[r][c] - center) < 3 * sigma_color)
+                if(abs(val[r][c] - center) < 90)   // 3 * sigma_color
                 {
-                    sum += val[r][c] * w5[c] * w5[r];
-                    wall += w5[c] * w5[r];
+                    isum += val[r][c] * (w5i[c] * w5i[r]);
+                    iwall += w5i[c] * w5i[r];
                 }
+        sum = (float)isum * 0.00390625f;
+        wall = (float)iwall * 0.00390625f;
         return static_cast<unsigned short>(static_cast<int>(sum / wall));
     }
 
