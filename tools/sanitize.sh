@@ -15,4 +15,7 @@ for tool in memcheck racecheck synccheck; do
     run batched_engine_8seq $tool python tools/sanitize_driver.py batch8
     run predict_splat_resolve $tool python -m pytest tests/test_predict.py -q -m gpu -x -k "combined_predict_is_bit_exact"
     run fern_search $tool python -m pytest tests/test_ferns.py -q -m gpu -x -k "encode_search_and_database"
+    # the one-launch frame preparation (shared-memory tiles, cp.async staging), alone: the tracker behind it is covered above
+    run prepare_frame_1seq $tool --kernel-name kns=k_prepare_frame python tools/sanitize_driver.py frame1
+    run prepare_frame_8seq $tool --kernel-name kns=k_prepare_frame python tools/sanitize_driver.py frame8
 done

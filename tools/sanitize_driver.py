@@ -1,5 +1,6 @@
 """Small workloads for compute-sanitizer (racecheck / synccheck / memcheck); see profiles/r02_sanitizer_*.log.
-usage: sanitize_driver.py gn1 | gn3 | batch8   (the prediction / fern kernels are run through their own tests, see tools/sanitize.sh)"""
+usage: sanitize_driver.py gn1 | gn3 | batch8 | frame1 | frame8   (the prediction / fern kernels are run through their own tests, see tools/sanitize.sh)
+frame1 / frame8: the frame-level entry point (k_prepare_frame: the whole preparation in one tiled launch, then the tracker) for one / eight sequences."""
 import sys
 from pathlib import Path
 import numpy as np
@@ -11,9 +12,9 @@ mode = sys.argv[1]
 scene, intr = make_scene(640, 480)
 poses = scene.trajectory(1000)
 args = (intr["width"], intr["height"], intr["cx"], intr["cy"], intr["fx"], intr["fy"])
-if mode in ("gn1", "gn3", "batch8"):
+if mode in ("gn1", "gn3", "batch8", "frame1", "frame8"):
     from slam_b200 import RGBDOdometry
-    B = {"gn1": 1, "gn3": 3, "batch8": 8}[mode]
+    B = {"gn1": 1, "gn3": 3, "batch8": 8, "frame1": 1, "frame8": 8}[mode]
     ks = [150 + 40 * b for b in range(B)]
     frames = [frame_pair(scene, poses, k) for k in ks]
     first = np.stack([scene.render_frame(poses[k - 1])[1] for k in ks])
@@ -23,6 +24,10 @@ if mode in ("gn1", "gn3", "batch8"):
     odo = RGBDOdometry(*args, batch=B)
     odo.initFirstRGB(torch.from_numpy(first).to("cuda:0"))
     for rep in range(2):
+        if mode.startswith("frame"):
+            fr = odo.make_frame(depth, rgba, mv, mn, mrgba, P if B > 1 else P[0], 3.0, 20.0)
+            t, r = odo.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+            continue
         odo.initICPModel(mv, mn, 20.0, P)
         odo.initRGBModel(mrgba)
         odo.initICP(depth, 3.0)
