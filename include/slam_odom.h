@@ -244,9 +244,16 @@ int slam_odom_get_profile(slam_odom_t h, double * gn_kernel_ms, long long * gn_k
  * (or since the last reset): [0] staging, [1] rest of the SO3 loop, [2] step set-up, [3] RGB association + count post, [4] ICP
  * products, [5] their block reduction + post + wait for the global count, [6] RGB products + block reduction + post, [7] wait for
  * all sums, [8] solve, [9] end-of-step barrier, [10] tail, [11] SO3 map, [12] SO3 block reduction + post, [13] SO3 wait for the
- * sums, [14] SO3 update, [15] launches, [16..19] staging of level 0..3, [20] staging of the SO3 images ([0] then holds only the check-in gate).  Only the variants launched with SLAM_GN_PHASES=1 (or the step trace) count.
+ * sums, [14] SO3 update, [15] launches, [16..19] staging of level 0..3, [20] staging of the SO3 images ([0] then holds only the check-in gate), [21] split launch: wait for the cluster's hand-off.  Only the variants launched with SLAM_GN_PHASES=1 (or the step trace) count.
  * Synchronises the handle's stream. */
 int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long out24[24], int reset);
+/* Launch shape of the device-resident loop for one sequence (getIncrementalTransformation, RGBDOdometryef.cpp:267-595).  enable = 1
+ * (the default; SLAM_GN_SPLIT=0 in the environment turns it off for the process): the SO3 pre-alignment runs on one thread-block
+ * cluster of 16 SMs (all-reduce through distributed shared memory) next to a second kernel on the other SMs, which stages the pyramid
+ * levels meanwhile, takes the rotation over and runs the ICP+RGB iterations; 0: one cooperative launch for the whole frame.  Calls that
+ * do not qualify (no SO3 step, several sequences, rgb_only, step trace, levels that do not fit shared memory) always use one launch.
+ * Returns the previous setting through *previous (may be NULL). */
+int slam_odom_set_split_launch(slam_odom_t h, int enable, int * previous);
 /* The stream the handle runs on (cudaStream_t), e.g. to record the caller's own events on it. */
 void * slam_odom_stream(slam_odom_t h);
 

@@ -134,9 +134,40 @@ __device__ __forceinline__ void spin_cycles(int cycles)
     }
 }
 
+// ------------------------------------------------------------------ all-reduce inside one thread-block cluster (split launch)
+// Every CTA stores its partial row into the ClArea of every peer (distributed shared memory), all threads of the cluster pass one
+// barrier.cluster (release / acquire), every CTA folds the rows in rank order: one trip through the SM-to-SM network instead of
+// one through L2 (~1.3 k against ~2.5 k cycles, profiles/r02_micro_sync_latency.log), deterministic.
+__device__ __forceinline__ unsigned cl_map(const void * p, const unsigned rank)
+{
+    unsigned a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void cl_st_f32(const unsigned a, const float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void cl_st_v2(const unsigned a, const int x, const int y) { asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// lane `col` of one warp: this CTA's total of a column goes to every peer
+__device__ __forceinline__ void cl_post_col(ClArea * cl, const int par, const int rank, const int csize, const int col, const float total)
+{
+#pragma unroll 4
+    for(int r = 0; r < csize; r++) cl_st_f32(cl_map(&cl->rows[par][rank][col], (unsigned)r), total);
+}
+// after the barrier: the sum of column `col` over the first `want` CTAs
+__device__ __forceinline__ float cl_fold_col(const ClArea * cl, const int par, const int want, const int col)
+{
+    double s = 0.0;
+#pragma unroll 4
+    for(int r = 0; r < want; r++) s += (double)cl->rows[par][r][col];
+    return (float)s;
+}
+
 // Block sum of up to 32 per-thread floats (v[ncols..31] must be 0), posted to the ncols columns starting at word wbase.
 // The caller must reach a __syncthreads() before sh.red is reused.
-__device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, unsigned long long * ring, unsigned step, int wbase, int ncols)
+template <bool CL>
+__device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, unsigned long long * ring, unsigned step, int wbase, int ncols, ClArea * cl, const int rank,
+                                                const int csize)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float s = warp_reduce_scatter32(v);
@@ -147,15 +178,22 @@ __device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, u
         float total = 0.f;
 #pragma unroll
         for(int w = 0; w < kGnWarps; w++) total += sh.red[w * 32 + lane];
-        if(lane < ncols) post_float(ring, step, wbase, lane, total);
+        if(lane < ncols)
+        {
+            if(CL)
+                cl_post_col(cl, (int)(step & 1u), rank, csize, lane, total);
+            else
+                post_float(ring, step, wbase, lane, total);
+        }
     }
 }
 
 // Block-level half of an ICP + RGB reduction: every warp holds, per lane, its partial sum of ICP column `lane` (s_icp) and of RGB
 // column `lane` (s_rgb), from two warp_reduce_scatter32 calls; one barrier, then warp 0 adds up and posts the ICP columns while
 // warp 1 does the same for the RGB columns.  has_icp / has_rgb: which halves exist (CTA-uniform).
+template <bool CL>
 __device__ __forceinline__ void cta_post_pair(const float s_icp, const float s_rgb, const bool has_icp, const bool has_rgb, GnShared & sh, unsigned long long * ring,
-                                              unsigned step)
+                                              unsigned step, ClArea * cl, const int rank, const int csize)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     sh.red[wid * 64 + lane] = s_icp;
@@ -166,7 +204,13 @@ __device__ __forceinline__ void cta_post_pair(const float s_icp, const float s_r
         float total = 0.f;
 #pragma unroll
         for(int w = 0; w < kGnWarps; w++) total += sh.red[w * 64 + wid * 32 + lane];
-        if(lane < 29) post_float(ring, step, wid == 0 ? kWIcp : kWRgb, lane, total);
+        if(lane < 29)
+        {
+            if(CL)
+                cl_post_col(cl, (int)(step & 1u), rank, csize, wid * 32 + lane, total);
+            else
+                post_float(ring, step, wid == 0 ? kWIcp : kWRgb, lane, total);
+        }
     }
 }
 
@@ -513,19 +557,28 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
 // own phases.  GEN = false is the product's common case and the one tuned for instruction footprint: every level resident,
 // no step trace; GEN = true adds the streamed levels, the step trace / time stamps and the full DataTerm image.
 // PH: per-phase cycle accounting of the leading CTA (slam_odom_get_phase_cycles).
-template <bool ICP, bool RGB, bool RGB_ONLY, bool GEN, bool PH>
+// ROLE: 0 = the whole frame in one cooperative launch.  Split launch (one sequence, every level resident): 1 = the SO3 pre-alignment
+// and the coarse levels on ONE thread-block cluster (grid = cluster = G CTAs, all-reduce through distributed shared memory), which
+// hands the running state to 2 = the fine levels on the other SMs; that kernel is released (programmatic dependent launch) as soon
+// as the cluster is resident, stages its levels next to the cluster's iterations and then waits for the hand-off.
+template <bool ICP, bool RGB, bool RGB_ONLY, bool GEN, bool PH, int ROLE>
 __global__ void __launch_bounds__(kGnThreads, 1)
 k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeqIn seq0, unsigned long long * rings, GnResult * results, slam_step_record * trace,
                 int * trace_count, const int G, const int groups, GnResult * host_results, unsigned * host_flags, const unsigned host_seqno,
-                const unsigned long long gate_target)
+                const unsigned long long gate_target, const unsigned long long handoff_seq)
 {
     __shared__ GnShared sh;
     __shared__ GnWork wk;
     extern __shared__ __align__(16) char dyn[];
+    constexpr bool CL = ROLE == 1;
+    // the fine-level kernel may start as soon as every CTA of the cluster is resident (it does not wait for this grid's memory:
+    // what it needs from here arrives through GnCtl::handoff)
+    if(CL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int group = blockIdx.x / G;
-    const int rank = blockIdx.x - group * G;
+    const int rank = blockIdx.x - group * G;   // CL: grid = one cluster, so this is %cluster_ctarank
     if(group >= groups) return;
+    ClArea * cl = reinterpret_cast<ClArea *>(dyn + L.off_cl);
 
     unsigned long long * ring = rings + (size_t)group * (kRingBytes / 8);
     unsigned step = 0;   // reduction steps done so far: position in the ring of word sets
@@ -542,16 +595,29 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     }
     long long ph_t = t_start;
     if(PH && threadIdx.x < 24) wk.ph[threadIdx.x] = 0u;
+    unsigned long long gt_start = 0ull;
+    if(PH && ROLE != 0 && leader)
+    {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
+        if(CL) *reinterpret_cast<volatile unsigned long long *>(&ctl->dbg_t[0]) = gt_start;
+    }
 #define GN_PHASE(idx) do { if(PH && leader) { const long long now_ = clock64(); wk.ph[idx] += (unsigned)(now_ - ph_t); ph_t = now_; } } while(0)
 
     // the reduction words as the previous launch left them (nobody posts before every CTA of the group has passed its first
     // wait, and that needs this CTA's own post)
-    for(int w = threadIdx.x; w < kRingSlots * kRingWords; w += kGnThreads) wk.base[w] = ld_u64_relaxed(ring + (size_t)w * kWordStride);
+    if(!CL)
+        for(int w = threadIdx.x; w < kRingSlots * kRingWords; w += kGnThreads) wk.base[w] = ld_u64_relaxed(ring + (size_t)w * kWordStride);
     __syncthreads();
     // ... which has to hold for a CTA that starts late as well: every CTA checks in once its bases are loaded, and nobody posts
     // before all have (the check is made after the staging, when it has long been true)
-    if(threadIdx.x == 0) red_u64(&ctl->arrived[group], 1ull);
-    bool gate_open = false;
+    if(!CL && threadIdx.x == 0) red_u64(&ctl->arrived[group], 1ull);
+    bool gate_open = CL;   // the cluster does not use the reduction words
+    if(CL)
+    {
+        // nobody stores into a peer's shared memory before that peer is running
+        cl_arrive();
+        cl_wait();
+    }
 #define GN_GATE() do { if(!gate_open) { if(threadIdx.x == 0) { int spin_ = 0; while(ld_u64_relaxed(&ctl->arrived[group]) < gate_target && ++spin_ < kSpinCap) {} if(spin_ >= kSpinCap) wk.timeouts = 1; } __syncthreads(); gate_open = true; } } while(0)
 
     for(int seq = group; seq < L.batch; seq += groups)
@@ -671,13 +737,25 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         for(int q = 0; q < 11; q++) acc[q] = a11[q];
                     }
                     GN_PHASE(11);
-                    cta_reduce_post(acc, sh, ring, step, kWSo3, 11);
+                    cta_reduce_post<CL>(acc, sh, ring, step, kWSo3, 11, cl, rank, G);
+                }
+                if(CL)
+                {
+                    cl_arrive();
+                    cl_wait();
                 }
                 GN_PHASE(12);
                 if(warp0)
                 {
-                    spin_cycles(L.poll_delay);
-                    read_columns(ring, step, kWSo3, 11, threadIdx.x, (unsigned)Pn, sh.total, wk);
+                    if(CL)
+                    {
+                        if(lane < 11) sh.total[lane] = cl_fold_col(cl, (int)(step & 1u), Pn, lane);
+                    }
+                    else
+                    {
+                        spin_cycles(L.poll_delay);
+                        read_columns(ring, step, kWSo3, 11, threadIdx.x, (unsigned)Pn, sh.total, wk);
+                    }
                     __syncwarp();
                     GN_PHASE(13);
                     slam_step_record * rec = (GEN && threadIdx.x == 0 && tr && ntr < kGnMaxTrace) ? &tr[ntr] : nullptr;
@@ -694,7 +772,38 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         }
         GN_PHASE(1);
 
-        if(threadIdx.x == 0)
+        if(ROLE == 2)
+        {
+            // the running state after the cluster's levels (GnCtl::handoff, published with the number of this launch pair)
+            if(warp0)
+            {
+                if(lane == 0)
+                {
+                    int spin = 0;
+                    unsigned long long v;
+                    do
+                    {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&ctl->handoff_seq) : "memory");
+                    } while(v != handoff_seq && ++spin < kSpinCap);
+                    if(spin >= kSpinCap) wk.timeouts = 1;
+                }
+                __syncwarp();
+                const GnHandoff * ho = &ctl->handoff;
+                const uint2 * src = reinterpret_cast<const uint2 *>(&ho->res);
+                uint2 * dst = reinterpret_cast<uint2 *>(&sh.res);
+                for(int k = lane; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = __ldcg(src + k);
+                if(lane < 16) sh.resultRt[lane] = __ldcg(&ho->resultRt[lane]);
+                if(lane < 9) sh.Rcurr[lane] = __ldcg(&ho->Rcurr[lane]);
+                if(lane < 3) sh.tcurr[lane] = __ldcg(&ho->tcurr[lane]);
+                if(lane == 0)
+                {
+                    sh.rgb_sigma_last = __ldcg(&ho->rgb_sigma_last);
+                    sh.rgb_count_last = __ldcg(&ho->rgb_count_last);
+                    if(__ldcg(&ho->timeouts)) wk.timeouts = 1;
+                }
+            }
+        }
+        else if(threadIdx.x == 0)
         {
             for(int k = 0; k < 16; k++) sh.resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
             if(L.so3)
@@ -702,6 +811,16 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     for(int y = 0; y < 3; y++) sh.resultRt[x * 4 + y] = sh.resultR[x * 3 + y];
         }
         __syncthreads();
+        GN_PHASE(21);
+        if(PH && ROLE == 2 && leader)
+        {
+            // nanoseconds since the cluster kernel started: when this kernel started, when the hand-off arrived
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            const unsigned long long a0 = *reinterpret_cast<volatile unsigned long long *>(&ctl->dbg_t[0]);
+            wk.ph[22] = (unsigned)(gt_start - a0);
+            wk.ph[23] = (unsigned)(now - a0);
+        }
 
         // ------------------------------------------------ coarse-to-fine ICP + RGB
 #pragma unroll 1
@@ -869,10 +988,18 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     {
                         const int c0 = wk.cnt[0], c1 = wk.cnt[1];
                         wk.cnt[0] = wk.cnt[1] = 0;
-                        post_int(ring, step, kWMid, (long long)c0 + (c1 != 0 ? (1ll << 32) : 0ll));
-                        post_int(ring, step, kWSigma, (long long)c1);
+                        if(CL)
+                        {
+                            for(int r = 0; r < G; r++) cl_st_v2(cl_map(&cl->mid[step & 1u][rank], (unsigned)r), c0, c1);
+                        }
+                        else
+                        {
+                            post_int(ring, step, kWMid, (long long)c0 + (c1 != 0 ? (1ll << 32) : 0ll));
+                            post_int(ring, step, kWSigma, (long long)c1);
+                        }
                     }
                 }
+                if(CL && RGB) cl_arrive();   // the counts travel while the ICP products are formed
                 GN_PHASE(3);
 
                 // Two map + block-reduction passes share ONE copy of the reduction code: pass 0 = ICP products (reduce.cu:282-416;
@@ -965,7 +1092,23 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     else
                     {
                         // ---------------- the global correspondence count: every CTA (rgbOnly decides the early exit on it)
-                        if(threadIdx.x == 0)
+                        if(CL)
+                        {
+                            cl_wait();
+                            if(threadIdx.x == 0)
+                            {
+                                long long c0 = 0, c1 = 0;
+                                for(int r = 0; r < Pn; r++)
+                                {
+                                    const int2 m = cl->mid[step & 1u][r];
+                                    c0 += m.x;
+                                    c1 += m.y;
+                                }
+                                wk.mid = (unsigned long long)c0 + (c1 != 0 ? (1ull << 32) : 0ull);
+                                wk.sigma = c1;
+                            }
+                        }
+                        else if(threadIdx.x == 0)
                         {
                             unsigned long long & mbase = wk.base[(step & (kRingSlots - 1)) * kRingWords + kWMid];
                             if(ICP && word_complete(mid_peek, mbase, (unsigned)Pn))
@@ -1069,7 +1212,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     }
                     // the count word is fetched while the warp reduction runs: by now every CTA has posted to it long ago, so the
                     // value is normally complete when the reduction is done and nobody waits for this trip through L2
-                    if(ICP && RGB && pass == 0 && threadIdx.x == 0) mid_peek = ld_u64_relaxed(ring_word(ring, step, kWMid));
+                    if(!CL && ICP && RGB && pass == 0 && threadIdx.x == 0) mid_peek = ld_u64_relaxed(ring_word(ring, step, kWMid));
                     if(part)
                     {
                         // warp level now (one copy of the code for both passes); block level + post once, after the last pass
@@ -1077,7 +1220,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                         if(ICP && RGB && pass == 0)
                             s_icp = s;
                         else
-                            cta_post_pair((ICP && RGB) ? s_icp : (ICP ? s : 0.f), RGB ? s : 0.f, ICP, RGB, sh, ring, step);
+                            cta_post_pair<CL>((ICP && RGB) ? s_icp : (ICP ? s : 0.f), RGB ? s : 0.f, ICP, RGB, sh, ring, step, cl, rank, G);
                     }
                     if(pass == 1) GN_PHASE(6);
                 }
@@ -1088,19 +1231,32 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 }
 
                 // ---------------- all sums of the step: warps 0..3 read the words, warp 0 solves
+                if(CL)
+                {
+                    cl_arrive();
+                    cl_wait();
+                }
                 if(threadIdx.x < 128)
                 {
-                    spin_cycles(L.poll_delay);
                     const int t = (int)threadIdx.x;
                     long long sg = 0;
                     const int sigma_word = (RGB && !RGB_ONLY && t == 127) ? kWSigma : -1;   // thread 127 is never a column reader
-                    if(ICP && RGB)
+                    if(CL)
                     {
-                        const int kind = t >= 58 ? 1 : 0;
-                        read_columns(ring, step, kind ? kWRgb : kWIcp, 29, t - 58 * kind, (unsigned)Pn, sh.total + 32 * kind, wk, sigma_word, &sg);
+                        if(t < 64 && (t & 31) < 29 && (t < 32 ? ICP : RGB)) sh.total[t] = cl_fold_col(cl, (int)(step & 1u), Pn, t);
+                        sg = wk.sigma;
                     }
                     else
-                        read_columns(ring, step, ICP ? kWIcp : kWRgb, 29, t, (unsigned)Pn, sh.total + (ICP ? 0 : 32), wk, sigma_word, &sg);
+                    {
+                        spin_cycles(L.poll_delay);
+                        if(ICP && RGB)
+                        {
+                            const int kind = t >= 58 ? 1 : 0;
+                            read_columns(ring, step, kind ? kWRgb : kWIcp, 29, t - 58 * kind, (unsigned)Pn, sh.total + 32 * kind, wk, sigma_word, &sg);
+                        }
+                        else
+                            read_columns(ring, step, ICP ? kWIcp : kWRgb, 29, t, (unsigned)Pn, sh.total + (ICP ? 0 : 32), wk, sigma_word, &sg);
+                    }
                     if(RGB && !RGB_ONLY && t == 127)
                     {
                         const int rgbSize = (int)(wk.mid & 0xffffffffull);
@@ -1128,6 +1284,31 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 __syncthreads();
                 GN_PHASE(9);
             }
+        }
+
+        if(CL)
+        {
+            // ---- hand the running state to the fine-level kernel
+            if(rank == 0 && warp0)
+            {
+                GnHandoff * ho = &ctl->handoff;
+                const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
+                uint2 * dst = reinterpret_cast<uint2 *>(&ho->res);
+                for(int k = lane; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
+                if(lane < 16) ho->resultRt[lane] = sh.resultRt[lane];
+                if(lane < 9) ho->Rcurr[lane] = sh.Rcurr[lane];
+                if(lane < 3) ho->tcurr[lane] = sh.tcurr[lane];
+                if(lane == 0)
+                {
+                    ho->rgb_sigma_last = sh.rgb_sigma_last;
+                    ho->rgb_count_last = sh.rgb_count_last;
+                    ho->timeouts = wk.timeouts;
+                }
+                __threadfence();
+                __syncwarp();
+                if(lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ctl->handoff_seq), "l"(handoff_seq) : "memory");
+            }
+            break;   // one sequence
         }
 
         // ---- the pose goes out first: the caller is released ~4 us before the statistics are complete
@@ -1180,35 +1361,54 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         __syncthreads();
     }
     GN_PHASE(10);
-    if(PH && blockIdx.x == 0 && threadIdx.x < 24)
+    if(PH && blockIdx.x == 0 && threadIdx.x < 24 && (L.ph_role == 0 || L.ph_role == ROLE || ROLE == 0))
     {
         __syncwarp();
         if(threadIdx.x != 15) atomicAdd(&ctl->phase_cycles[threadIdx.x], (unsigned long long)wk.ph[threadIdx.x]);
-        if(threadIdx.x == 0) atomicAdd(&ctl->phase_cycles[15], 1ull);
+        if(threadIdx.x == 0 && !CL) atomicAdd(&ctl->phase_cycles[15], 1ull);   // launches (a split pair counts once)
     }
     if(threadIdx.x == 0 && wk.timeouts) atomicAdd(&ctl->timeouts, 1u);
 }
 
 // the kernel variant of a launch
 typedef void (*GnKernel)(const GnLaunch, GnCtl *, const GnSeqIn *, const GnSeqIn, unsigned long long *, GnResult *, slam_step_record *, int *, const int, const int,
-                         GnResult *, unsigned *, const unsigned, const unsigned long long);
+                         GnResult *, unsigned *, const unsigned, const unsigned long long, const unsigned long long);
 static GnKernel gn_pick_kernel(const GnLaunch & L, bool general, bool phases)
 {
     if(general || phases)
     {
         // the general variants always account the phases (they are not the tuned path)
-        if(L.rgb_only) return general ? k_gn_persistent<false, true, true, true, true> : k_gn_persistent<false, true, true, false, true>;
-        if(L.icp && L.rgb) return general ? k_gn_persistent<true, true, false, true, true> : k_gn_persistent<true, true, false, false, true>;
-        return general ? k_gn_persistent<true, false, false, true, true> : k_gn_persistent<true, false, false, false, true>;
+        if(L.rgb_only) return general ? k_gn_persistent<false, true, true, true, true, 0> : k_gn_persistent<false, true, true, false, true, 0>;
+        if(L.icp && L.rgb) return general ? k_gn_persistent<true, true, false, true, true, 0> : k_gn_persistent<true, true, false, false, true, 0>;
+        return general ? k_gn_persistent<true, false, false, true, true, 0> : k_gn_persistent<true, false, false, false, true, 0>;
     }
-    if(L.rgb_only) return k_gn_persistent<false, true, true, false, false>;
-    if(L.icp && L.rgb) return k_gn_persistent<true, true, false, false, false>;
-    return k_gn_persistent<true, false, false, false, false>;
+    if(L.rgb_only) return k_gn_persistent<false, true, true, false, false, 0>;
+    if(L.icp && L.rgb) return k_gn_persistent<true, true, false, false, false, 0>;
+    return k_gn_persistent<true, false, false, false, false, 0>;
+}
+// the pair of a split launch: role 1 = cluster (coarse levels), role 2 = fine levels
+static GnKernel gn_pick_split_kernel(const GnLaunch & L, bool phases, int role)
+{
+    if(L.icp && L.rgb)
+    {
+        if(role == 1) return phases ? k_gn_persistent<true, true, false, false, true, 1> : k_gn_persistent<true, true, false, false, false, 1>;
+        return phases ? k_gn_persistent<true, true, false, false, true, 2> : k_gn_persistent<true, true, false, false, false, 2>;
+    }
+    if(role == 1) return phases ? k_gn_persistent<true, false, false, false, true, 1> : k_gn_persistent<true, false, false, false, false, 1>;
+    return phases ? k_gn_persistent<true, false, false, false, true, 2> : k_gn_persistent<true, false, false, false, false, 2>;
 }
 static const GnKernel kAllGnKernels[] = {
-    k_gn_persistent<false, true, true, true, true>,   k_gn_persistent<true, true, false, true, true>,   k_gn_persistent<true, false, false, true, true>,
-    k_gn_persistent<false, true, true, false, true>,  k_gn_persistent<true, true, false, false, true>,  k_gn_persistent<true, false, false, false, true>,
-    k_gn_persistent<false, true, true, false, false>, k_gn_persistent<true, true, false, false, false>, k_gn_persistent<true, false, false, false, false>,
+    k_gn_persistent<false, true, true, true, true, 0>,   k_gn_persistent<true, true, false, true, true, 0>,   k_gn_persistent<true, false, false, true, true, 0>,
+    k_gn_persistent<false, true, true, false, true, 0>,  k_gn_persistent<true, true, false, false, true, 0>,  k_gn_persistent<true, false, false, false, true, 0>,
+    k_gn_persistent<false, true, true, false, false, 0>, k_gn_persistent<true, true, false, false, false, 0>, k_gn_persistent<true, false, false, false, false, 0>,
+    k_gn_persistent<true, true, false, false, true, 1>,  k_gn_persistent<true, true, false, false, false, 1>, k_gn_persistent<true, false, false, false, true, 1>,
+    k_gn_persistent<true, false, false, false, false, 1>,
+    k_gn_persistent<true, true, false, false, true, 2>,  k_gn_persistent<true, true, false, false, false, 2>, k_gn_persistent<true, false, false, false, true, 2>,
+    k_gn_persistent<true, false, false, false, false, 2>,
+};
+static const GnKernel kClusterGnKernels[] = {
+    k_gn_persistent<true, true, false, false, true, 1>,  k_gn_persistent<true, true, false, false, false, 1>, k_gn_persistent<true, false, false, false, true, 1>,
+    k_gn_persistent<true, false, false, false, false, 1>,
 };
 // ------------------------------------------------------------------ host side
 size_t gn_state_bytes(int batch, int num_sms)
@@ -1295,16 +1495,32 @@ static int gn_init_device(GnDevice & d)
     d.smem_limit = optin - (int)static_smem - 1024;
     if(d.smem_limit < 0) d.smem_limit = 0;
     for(GnKernel k : kAllGnKernels) SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_limit));
+    const char * sp = getenv("SLAM_GN_SPLIT");
+    d.split = sp ? atoi(sp) : 1;
+    if(d.split)
+        for(GnKernel k : kClusterGnKernels)
+            if(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+            {
+                cudaGetLastError();
+                d.split = 0;
+            }
     d.phases = getenv("SLAM_GN_PHASES") != nullptr;
     const char * pd = getenv("SLAM_GN_POLL_DELAY");
     d.poll_delay = pd ? atoi(pd) : 900;
     return SLAM_OK;
 }
 
+static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool cluster);
+int gn_configure(GnDevice & d) { return gn_init_device(d); }
+
 bool gn_make_plan(GnDevice & d, GnLaunch & L)
 {
     if(gn_init_device(d) != SLAM_OK) d.smem_limit = 0;
-    const int G = gn_group_size(d.num_sms, L.batch);
+    return gn_make_plan_for(d, L, gn_group_size(d.num_sms, L.batch), false);
+}
+
+static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool cluster)
+{
     static const bool no_resident = getenv("SLAM_GN_STREAMED") != nullptr;   // development aid: force the streamed path
     int off = 0;
     auto take = [&](int bytes) {
@@ -1365,9 +1581,66 @@ bool gn_make_plan(GnDevice & d, GnLaunch & L)
             L.off_so3 = take(bytes);
         }
     }
+    L.off_cl = 0;
+    if(cluster)
+    {
+        L.off_cl = take((int)sizeof(ClArea));
+        if(off > d.smem_limit) all_rgb_resident = false;   // (never with the levels a cluster takes)
+    }
     L.dyn_bytes = off;
     L.poll_delay = d.poll_delay;
+    {
+        const char * ph = getenv("SLAM_GN_PHASES");
+        L.ph_role = ph ? atoi(ph) - 1 : 0;
+        if(L.ph_role < 0 || L.ph_role > 2) L.ph_role = 0;
+    }
     return all_rgb_resident;
+}
+
+// Split launch: which levels the cluster takes (the coarse ones, from the top down to the first level that is too large) and the
+// two shared-memory plans.  Returns false when the launch does not qualify (then the whole frame runs in one launch).
+static bool gn_make_split(GnDevice & d, const GnLaunch & L, GnLaunch & La, GnLaunch & Lb)
+{
+    if(d.split != 1 || d.split_broken || L.batch != 1 || L.rgb_only || !L.icp || L.trace || L.full_corres) return false;
+    if(d.num_sms < kClusterCtas + 32) return false;
+    // Which levels go with the SO3 pre-alignment onto the cluster: by default none.  Measured (tools/iter_cost.py): an ICP+RGB iteration
+    // of the 160x120 level costs 6.8 us on the 16 CTAs of a cluster against 5.2 us on 38 CTAs with the reduction words in L2 (the
+    // map phases grow by more than the shorter all-reduce saves), an SO3 iteration 3.4 against 4.0 us.  SLAM_GN_SPLIT_LEVELS=1 moves
+    // every level of at most kClusterMaxPixels pixels as well (development aid).
+    static const bool coarse_too = getenv("SLAM_GN_SPLIT_LEVELS") && atoi(getenv("SLAM_GN_SPLIT_LEVELS")) > 0;
+    int first_fine = L.levels - 1;   // levels [0, first_fine] stay with the fine kernel
+    if(coarse_too)
+        while(first_fine >= 0 && L.geom[first_fine].rows * L.geom[first_fine].cols <= kClusterMaxPixels) first_fine--;
+    if(first_fine < 0) return false;                     // nothing for the fine kernel
+    if(first_fine == L.levels - 1 && !L.so3) return false;   // nothing for the cluster
+    if(L.so3 && first_fine >= 2 && first_fine != L.levels - 1) return false;   // a cluster that takes levels takes level 2 (SO3 runs there)
+    int it_a = 0, it_b = 0;
+    La = L;
+    Lb = L;
+    for(int l = 0; l < L.levels; l++)
+    {
+        if(l <= first_fine)
+        {
+            La.iterations[l] = 0;
+            it_b += L.iterations[l];
+        }
+        else
+        {
+            Lb.iterations[l] = 0;
+            it_a += L.iterations[l];
+        }
+    }
+    if((it_a <= 0 && !L.so3) || it_b <= 0) return false;
+    Lb.so3 = false;
+    gn_make_plan_for(d, La, kClusterCtas, true);
+    gn_make_plan_for(d, Lb, d.num_sms - kClusterCtas, false);
+    for(int l = 0; l < L.levels; l++)
+    {
+        if(La.iterations[l] > 0 && !La.plan[l].resident) return false;
+        if(Lb.iterations[l] > 0 && !Lb.plan[l].resident) return false;
+    }
+    if(La.so3 && !La.so3_resident) return false;
+    return true;
 }
 
 // Fill the pinned staging image of the per-sequence input blocks (pointers + prior pose).
@@ -1417,10 +1690,22 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     GnSeqIn seq0 = in[0];
     // h_flags != nullptr: h_results / h_flags are mapped pinned memory the kernel writes itself (device view == host pointer under UVA)
     GnResult * host_results = h_flags ? h_results : nullptr;
-    // every launch raises the check-in counter of each group by G (GN_GATE)
     d.launch_no++;
-    unsigned long long gate_target = d.launch_no * (unsigned long long)G;
-    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno, &gate_target};
+    unsigned long long handoff_seq = d.launch_no;
+    // the tuned variant needs every level (and the SO3 images) resident and no step trace
+    bool general = L.trace || L.full_corres || (L.so3 && !L.so3_resident);
+    for(int l = 0; l < L.levels; l++) general = general || (L.iterations[l] > 0 && !L.plan[l].resident);
+    GnLaunch La, Lb;
+    const bool split = !general && gn_make_split(d, L, La, Lb);
+    if(split)
+    {
+        G = d.num_sms - kClusterCtas;
+        Lc = Lb;
+    }
+    // every launch raises the check-in counter of each group by G (GN_GATE)
+    d.gate_total += (unsigned long long)G;
+    unsigned long long gate_target = d.gate_total;
+    void * args[] = {&Lc, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &G, &groups, &host_results, &h_flags, &seqno, &gate_target, &handoff_seq};
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if(d.profiling)
     {
@@ -1430,10 +1715,7 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         SLAM_CUDA_TRY(cudaEventCreate(&e1));
         SLAM_CUDA_TRY(cudaEventRecord(e0, stream));
     }
-    // the tuned variant needs every level (and the SO3 images) resident and no step trace
-    bool general = L.trace || L.full_corres || (L.so3 && !L.so3_resident);
-    for(int l = 0; l < L.levels; l++) general = general || (L.iterations[l] > 0 && !L.plan[l].resident);
-    const GnKernel kernel = gn_pick_kernel(L, general, d.phases);
+    const GnKernel kernel = split ? gn_pick_split_kernel(L, d.phases, 2) : gn_pick_kernel(L, general, d.phases);
     static const bool debug = getenv("SLAM_ODOM_DEBUG") != nullptr;
     if(debug && d.launch_no < 3)
     {
@@ -1441,7 +1723,67 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         for(int l = 0; l < L.levels; l++) fprintf(stderr, " [%d: it %d res %d P %d cap %d]", l, L.iterations[l], L.plan[l].resident, L.plan[l].P, L.plan[l].cap);
         fprintf(stderr, "\n");
     }
-    SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
+    d.last_launches = 1;
+    if(split)
+    {
+        d.last_launches = 2;
+        // 1) the cluster: SO3 pre-alignment + coarse levels, one cluster of kClusterCtas CTAs
+        int Ga = kClusterCtas, groups_a = 1;
+        void * args_a[] = {&La, &ctl, &seq_in, &seq0, &ring, &results, &trace, &trace_count, &Ga, &groups_a, &host_results, &h_flags, &seqno, &gate_target, &handoff_seq};
+        cudaLaunchConfig_t ca = {};
+        ca.gridDim = dim3(kClusterCtas);
+        ca.blockDim = dim3(kGnThreads);
+        ca.dynamicSmemBytes = (size_t)La.dyn_bytes;
+        ca.stream = stream;
+        cudaLaunchAttribute aa[1];
+        aa[0].id = cudaLaunchAttributeClusterDimension;
+        aa[0].val.clusterDim.x = kClusterCtas;
+        aa[0].val.clusterDim.y = 1;
+        aa[0].val.clusterDim.z = 1;
+        ca.attrs = aa;
+        ca.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelExC(&ca, (const void *)gn_pick_split_kernel(L, d.phases, 1), args_a);
+        if(e == cudaSuccess)
+        {
+            // 2) the fine levels on the other SMs: released as soon as every CTA of the cluster has started (programmatic dependent
+            //    launch), so that it can never take the SMs the cluster needs; not cooperative -- its CTAs are co-resident because
+            //    the grid is the number of SMs the cluster leaves (if they are not, the late ones start when the cluster retires)
+            cudaLaunchConfig_t cb = {};
+            cb.gridDim = dim3(G);
+            cb.blockDim = dim3(kGnThreads);
+            cb.dynamicSmemBytes = (size_t)Lb.dyn_bytes;
+            cb.stream = stream;
+            cudaLaunchAttribute ab[1];
+            ab[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            ab[0].val.programmaticStreamSerializationAllowed = 1;
+            cb.attrs = ab;
+            cb.numAttrs = 1;
+            e = cudaLaunchKernelExC(&cb, (const void *)kernel, args);
+            if(e != cudaSuccess)
+            {
+                // the cluster is already in the stream: its partner follows as an ordinary launch (it finds the hand-off waiting)
+                cudaGetLastError();
+                d.split_broken = 1;
+                cb.numAttrs = 0;
+                SLAM_CUDA_TRY(cudaLaunchKernelExC(&cb, (const void *)kernel, args));
+            }
+        }
+        else
+        {
+            // no cluster on this device / in this context: one launch for the whole frame, from now on
+            cudaGetLastError();
+            d.split_broken = 1;
+            d.last_launches = 1;
+            d.gate_total -= (unsigned long long)G;
+            G = gn_group_size(d.num_sms, L.batch);
+            d.gate_total += (unsigned long long)G;
+            gate_target = d.gate_total;
+            Lc = L;
+            SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)gn_pick_kernel(L, general, d.phases), dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
+        }
+    }
+    else
+        SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
     if(d.profiling)
     {
         SLAM_CUDA_TRY(cudaEventRecord(e1, stream));

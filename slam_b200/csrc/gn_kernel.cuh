@@ -51,11 +51,36 @@ struct GnSeqIn
     float tprev[3];
 };
 
+// What the coarse-level kernel (one thread-block cluster: SO3 pre-alignment + the small pyramid levels) hands to the fine-level
+// kernel that runs next to it (split launch, gn_kernel.cu): the state that carries over from one level to the next.
+struct GnHandoff
+{
+    GnResult res;
+    double resultRt[16];
+    float Rcurr[9], tcurr[3];
+    int rgb_sigma_last, rgb_count_last;
+    int timeouts, pad;
+};
+
 struct GnCtl
 {
     unsigned long long arrived[kGnMaxCtas + 1];   // per CTA group: CTAs that have checked in, summed over all launches (GN_GATE)
     unsigned timeouts;               // polls that gave up (a lost arrival would otherwise hang the GPU): non-zero = results invalid
     unsigned long long phase_cycles[24];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
+    // split launch: written by the leading CTA of the cluster, then handoff_seq = number of the launch (release); polled by the fine-level kernel
+    alignas(16) GnHandoff handoff;
+    unsigned long long handoff_seq;
+    unsigned long long dbg_t[4];     // phase accounting only: [0] = %globaltimer at the start of the cluster kernel
+};
+
+// Split launch: the cluster that runs the SO3 pre-alignment and the coarse levels.  Its all-reduce goes through distributed shared
+// memory (every CTA stores its partial row into every peer, one barrier.cluster, every CTA folds the rows in rank order).
+constexpr int kClusterCtas = 16;       // non-portable cluster size (needs cudaFuncAttributeNonPortableClusterSizeAllowed)
+constexpr int kClusterMaxPixels = 24576;   // levels up to this many pixels run on the cluster
+struct ClArea
+{
+    float rows[2][kClusterCtas][64];   // [parity][rank of the writer][column]: [0..31] ICP / SO3, [32..63] RGB
+    int2 mid[2][kClusterCtas];         // RGB correspondence count, squared-residual sum of every CTA
 };
 
 // How one pyramid level is mapped onto the CTAs of a group.  Resident levels keep the pose-independent operands of their
@@ -90,8 +115,10 @@ struct GnLaunch
     int off_state;           // phase A -> phase B state of the RGB entries (3 words per entry), shared by all levels
     int so3_resident, so3_P; // SO3 pre-alignment: both level-2 images in shared memory; participating CTAs
     int off_so3;
+    int off_cl;              // split launch, cluster kernel: the ClArea
     int dyn_bytes;
     int poll_delay;          // cycles between posting a contribution and the first poll
+    int ph_role;             // phase accounting: 0 = both kernels of a split launch add their cycles, 1 / 2 = only that role
 };
 
 struct GnDevice
@@ -110,7 +137,11 @@ struct GnDevice
     int num_sms = 0;
     int smem_limit = 0;             // dynamic shared memory the persistent kernel may use
     int poll_delay = 0;
-    unsigned long long launch_no = 0;   // launches so far (the check-in counters grow by G per launch)
+    unsigned long long launch_no = 0;   // launches so far
+    unsigned long long gate_total = 0;  // check-ins every group's counter has seen so far (grows by the group size of each launch)
+    int split = -1;                 // SLAM_GN_SPLIT: 1 = cluster + fine-level launch pair where it applies (default), 0 = one launch
+    int last_launches = 1;          // kernels the last gn_enqueue put into the stream (2 for a split launch)
+    int split_broken = 0;           // the device refused the cluster / programmatic launch once: stay with one launch
     bool phases = false;            // SLAM_GN_PHASES: launch the variants with per-phase cycle accounting
     bool so3_swapped = false;
     // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)
@@ -121,6 +152,8 @@ struct GnDevice
 };
 
 int gn_fold_profile(GnDevice & d);
+// One-time device set-up of the persistent kernel (attributes, limits, environment switches); idempotent.
+int gn_configure(GnDevice & d);
 
 size_t gn_state_bytes(int batch, int num_sms);
 void gn_bind_state(GnDevice & d, char * base, int batch, int num_sms);

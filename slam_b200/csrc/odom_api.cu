@@ -1055,7 +1055,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         if(zc) h->zc_seqno++;
         rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream, zc ? h->h_flags : nullptr, h->zc_seqno);
         h->zc_pending = zc && rc == SLAM_OK;
-        h->launches++;
+        h->launches += h->gn.last_launches;
     }
     if(rc) return rc;
     h->pending_async = true;
@@ -1503,6 +1503,16 @@ extern "C" int slam_odom_get_phase_cycles(slam_odom_t h, unsigned long long * ou
     SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
     SLAM_CUDA_TRY(cudaMemcpy(out24, h->gn.ctl->phase_cycles, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost));
     if(reset) SLAM_CUDA_TRY(cudaMemset(h->gn.ctl->phase_cycles, 0, sizeof(unsigned long long) * 24));
+    return SLAM_OK;
+}
+
+extern "C" int slam_odom_set_split_launch(slam_odom_t h, int enable, int * previous)
+{
+    if(int rc = check_handle(h)) return rc;
+    if(int rc = set_device(h)) return rc;
+    if(int rc = gn_configure(h->gn)) return rc;
+    if(previous) *previous = h->gn.split;
+    h->gn.split = enable ? 1 : 0;
     return SLAM_OK;
 }
 

@@ -81,6 +81,7 @@ struct PrepFrameArgs
     float depthCutoff;
     // batched launch (gridDim.y sequences): byte strides of the caller's input stacks and of the arena buffers
     size_t map_in_stride, rgba_stride, depth_in_stride, arena_stride;
+    unsigned long long * dbg;   // development aid (SLAM_PREP_DEBUG): per block {start, end (%globaltimer), SM}
 };
 int launch_prepare_frame(PrepFrameArgs & a, cudaStream_t s, int nseq);
 

@@ -8,6 +8,8 @@
 // launch; depth+intensity pyramids side by side), dense row-major buffers instead of
 // pitched ones, and no per-call cudaMalloc/cudaMemcpy/cudaDeviceSynchronize.
 // The un-fused operator entry points (slam_op_*) are kept for operator-level parity.
+#include <vector>
+#include <cstdio>
 #include "odom_internal.hpp"
 
 namespace slam {
@@ -31,7 +33,18 @@ struct TileSrc
 };
 
 // utils.cu:57-94  pyrDownGaussKernel (u16 depth, bilateral-gated 5x5, sigma_color = 30)
-template <class Src>
+// MODE (all three 5x5 window operators below): 0 = the pixel decides (interior / clipped window), 1 = the caller guarantees an interior
+// pixel, 2 = the caller guarantees a border pixel.  The tiled frame preparation sorts its pixels by window_interior() first, so that
+// no warp runs both paths for the sake of the one border pixel in each of its rows.
+__device__ __forceinline__ bool window_interior_u16(int srows, int scols, int x, int y)
+{
+    return 2 * x - 2 >= 0 && 2 * y - 2 >= 0 && 2 * x + 3 <= scols && 2 * y + 3 <= srows;
+}
+__device__ __forceinline__ bool window_interior_gauss(int srows, int scols, int x, int y)
+{
+    return x >= 1 && y >= 1 && 2 * x + 3 <= scols - 1 && 2 * y + 3 <= srows - 1;
+}
+template <int MODE = 0, class Src>
 __device__ __forceinline__ unsigned short pyr_down_u16_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
@@ -46,7 +59,7 @@ __device__ __forceinline__ unsigned short pyr_down_u16_at(const Src & src, int s
     float sum = 0;
     float wall = 0;
 
-    if(x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3)
+    if(MODE != 2 && (MODE == 1 || (x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3)))
     {
         // interior: the full 5x5 window; all 25 loads are issued before the first use.  Every product and partial sum
         // is exact in fp32 (16-bit values x multiples of 1/256), so only the final quotient rounds, as in the reference.
@@ -77,28 +90,32 @@ __device__ __forceinline__ unsigned short pyr_down_u16_at(const Src & src, int s
 
     // border: the clipped window with every load issued first (the sums are exact, see above, so the order is free); the border
     // threads used to walk their taps one dependent round trip at a time and set the duration of the whole launch
+    // The sums are exact for any subset of the taps (see above): the same integer form, a tap outside the clipped window gets a value
+    // that fails the colour gate (the code is cold -- a handful of warps per frame run it -- so its length is its cost).
     {
         int val[5][5];
-        bool in[5][5];
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++)
             {
                 const int yi = r - 2, xi = c - 2;
-                in[r][c] = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
-                val[r][c] = in[r][c] ? (int)src.at(2 * y + yi, 2 * x + xi) : 0;
+                const bool in = yi >= y_mi && yi < y_ma && xi >= x_mi && xi < x_ma;
+                val[r][c] = in ? (int)src.at(2 * y + yi, 2 * x + xi) : (1 << 20);
             }
-        const float w5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};   // the reference's weights[abs(xi)] = {0.375, 0.25, 0.0625}, xi = c - 2
+        const int w5i[5] = {1, 4, 6, 4, 1};   // the reference's weights[abs(xi)] = {0.375, 0.25, 0.0625}, xi = c - 2, times 16
+        int isum = 0, iwall = 0;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++)
-                if(in[r][c] && abs(val[r][c] - center) < 3 * sigma_color)
+                if(abs(val[r][c] - center) < 90)   // 3 * sigma_color
                 {
-                    sum += val[r][c] * w5[c] * w5[r];
-                    wall += w5[c] * w5[r];
+                    isum += val[r][c] * (w5i[c] * w5i[r]);
+                    iwall += w5i[c] * w5i[r];
                 }
+        sum = (float)isum * 0.00390625f;
+        wall = (float)iwall * 0.00390625f;
     }
     return static_cast<unsigned short>(static_cast<int>(sum / wall));
 }
@@ -139,7 +156,7 @@ __device__ __forceinline__ float gauss5_weight_rc(int a, int b)
     return wa * wb;
 }
 
-template <class Src>
+template <int MODE = 0, class Src>
 __device__ __forceinline__ float pyr_down_gauss_f_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
@@ -148,7 +165,7 @@ __device__ __forceinline__ float pyr_down_gauss_f_at(const Src & src, int srows,
     int cy = max(0, 2 * y - D / 2);
     float sum = 0;
     int count = 0;
-    if(x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)
+    if(MODE != 2 && (MODE == 1 || (x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)))
     {
         // interior: full window, weight index (4-r)*5 + (4-c) = the symmetric {1,4,6,4,1}^2 table; loads first,
         // then the reference's accumulation order (rows outer, columns inner), one FMA per finite tap.
@@ -181,16 +198,28 @@ __device__ __forceinline__ float pyr_down_gauss_f_at(const Src & src, int srows,
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? src.at(cy + r, cx0 + c) : SLAM_QNAN;
+        // weight of tap (r, c) = table entry (nr - 1 - r, nc - 1 - c), i.e. index (ty-cy-1)*5 + (tx-cx-1): one factor per row and per
+        // column, formed once (the products of {1, 4, 6} are exact, and so is the count as a float sum of them)
+        float wr[5], wc[5];
+#pragma unroll
+        for(int k = 0; k < 5; k++)
+        {
+            const int a = nr - 1 - k, b = nc - 1 - k;
+            wr[k] = (a == 0 || a == 4) ? 1.f : (a == 2 ? 6.f : 4.f);
+            wc[k] = (b == 0 || b == 4) ? 1.f : (b == 2 ? 6.f : 4.f);
+        }
+        float countf = 0.f;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++)
-                if(r < nr && c < nc && !isnan(v[r][c]))
+                if(!isnan(v[r][c]))   // taps outside the clipped window were given NaN
                 {
-                    const float w = gauss5_weight_rc(nr - 1 - r, nc - 1 - c);   // index (ty-cy-1)*5 + (tx-cx-1)
+                    const float w = wr[r] * wc[c];
                     sum = __fmaf_rn(v[r][c], w, sum);
-                    count += (int)w;
+                    countf += w;
                 }
+        return (float)(sum / countf);
     }
     return (float)(sum / (float)count);
 }
@@ -200,7 +229,7 @@ __device__ __forceinline__ float pyr_down_gauss_f_pixel(const float * src, int s
     return pyr_down_gauss_f_at(ImageSrc<float>{src, scols}, srows, scols, x, y);
 }
 
-template <class Src>
+template <int MODE = 0, class Src>
 __device__ __forceinline__ unsigned char pyr_down_gauss_u8_at(const Src & src, int srows, int scols, int x, int y)
 {
     const int D = 5;
@@ -209,7 +238,7 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_at(const Src & src, i
     int cy = max(0, 2 * y - D / 2);
     float sum = 0;
     int count = 0;
-    if(x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)
+    if(MODE != 2 && (MODE == 1 || (x >= 1 && y >= 1 && tx == 2 * x + 3 && ty == 2 * y + 3)))
     {
         // interior: full window; integer arithmetic is exact here (<= 255 * 256), only the quotient rounds
         int v[5][5];
@@ -239,16 +268,26 @@ __device__ __forceinline__ unsigned char pyr_down_gauss_u8_at(const Src & src, i
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++) v[r][c] = (r < nr && c < nc) ? (int)src.at(cy + r, cx0 + c) : 0;
+        // one weight factor per row and per column (see the float version); all sums are integers below 2^16, exact either way
+        int wr[5], wc[5];
+#pragma unroll
+        for(int k = 0; k < 5; k++)
+        {
+            const int a = nr - 1 - k, b = nc - 1 - k;
+            wr[k] = (a == 0 || a == 4) ? 1 : (a == 2 ? 6 : 4);
+            wc[k] = (b == 0 || b == 4) ? 1 : (b == 2 ? 6 : 4);
+        }
+        int isum = 0;
 #pragma unroll
         for(int r = 0; r < 5; r++)
 #pragma unroll
             for(int c = 0; c < 5; c++)
                 if(v[r][c] > 0)
                 {
-                    const float w = gauss5_weight_rc(nr - 1 - r, nc - 1 - c);
-                    sum += (float)v[r][c] * w;
-                    count += (int)w;
+                    isum += v[r][c] * (wr[r] * wc[c]);
+                    count += wr[r] * wc[c];
                 }
+        return (unsigned char)((float)isum / (float)count);
     }
     return (unsigned char)(sum / (float)count);
 }
@@ -663,6 +702,7 @@ __global__ void __launch_bounds__(256) k_rgbd_down_dual(const float * __restrict
 #define tile_pyr_down_f pyr_down_gauss_f_at
 #define tile_pyr_down_u8 pyr_down_gauss_u8_at
 #define tile_pyr_down_u16 pyr_down_u16_at
+constexpr int kBorderListMax = 512;   // border pixels of one pass of one tile (3 images x (row + column of the level-1 tile) at most)
 #define tile_vertex_normal vertex_normal_pixel
 
 // Tile = 64 x 36 level-0 pixels: a 640 x 480 frame is 10 x 14 = 140 tiles, at most one block of each role per SM of a 148-SM part
@@ -686,7 +726,15 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
 {
     __shared__ __align__(16) unsigned char smem[kM0W * kM0H * 4 + 2 * kM0P8 * kM0H + kM1W * kM1H * 4 + 2 * kM1P8 * kM1H];
     static_assert(sizeof(smem) >= (kD0P * kD0H + kD1P * kD1H + kD2P * kD2H) * 2, "the depth role's tiles alias the model role's");
+    // Pixels whose 5x5 window is clipped by the image border (one column of a left / right tile, one row of a top / bottom tile) are
+    // set aside by the pass that meets them and handled afterwards by a few dense warps: a warp that runs the interior AND the clipped
+    // path for one border lane per row made the left / right tiles 1.7x as expensive as the others, and they set the launch's duration.
+    __shared__ int border_n[2];
+    __shared__ unsigned short border_list[2][kBorderListMax];
     const int t = threadIdx.x;
+    if(t < 2) border_n[t] = 0;
+    unsigned long long dbg_t0 = 0ull;
+    if(a0.dbg && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     // batched launch: byte offsets of this sequence (zero for a single sequence)
     const size_t sh_map = (size_t)blockIdx.y * a0.map_in_stride, sh_rgba = (size_t)blockIdx.y * a0.rgba_stride, sh_depth = (size_t)blockIdx.y * a0.depth_in_stride,
                  sh_arena = (size_t)blockIdx.y * a0.arena_stride;
@@ -900,11 +948,16 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                 const int r = idx / kM1W, c = idx - r * kM1W;
                 const int x = c1o + c, y = r1o + r;
                 if(x < 0 || x >= cols1 || y < 0 || y >= rows1) continue;
+                if(!window_interior_gauss(rows, cols, x, y))
+                {
+                    border_list[0][atomicAdd(&border_n[0], 1)] = (unsigned short)(img * kPx + idx);
+                    continue;
+                }
                 const bool core = r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2;
                 const int o = y * cols1 + x;
                 if(img == 0)
                 {
-                    const float d = tile_pyr_down_f(sd, rows, cols, x, y);
+                    const float d = tile_pyr_down_f<1>(sd, rows, cols, x, y);
                     d1[r * kM1W + c] = d;
                     if(core)
                     {
@@ -914,7 +967,35 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                 }
                 else
                 {
-                    const unsigned char v = tile_pyr_down_u8(img == 1 ? sl : sn, rows, cols, x, y);
+                    const unsigned char v = tile_pyr_down_u8<1>(img == 1 ? sl : sn, rows, cols, x, y);
+                    (img == 1 ? li1 : ni1)[r * kM1P8 + c] = v;
+                    if(core) shifted(img == 1 ? a0.lastImage[1] : a0.nextImage[1], sh_arena)[o] = v;
+                }
+            }
+            __syncthreads();
+            // the border pixels of the pass (none in most tiles)
+            const int nb = border_n[0];
+            for(int k = t; k < nb; k += kPrepThreads)
+            {
+                const int item = border_list[0][k];
+                const int img = item / kPx, idx = item - img * kPx;
+                const int r = idx / kM1W, c = idx - r * kM1W;
+                const int x = c1o + c, y = r1o + r;
+                const bool core = r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2;
+                const int o = y * cols1 + x;
+                if(img == 0)
+                {
+                    const float d = tile_pyr_down_f<2>(sd, rows, cols, x, y);
+                    d1[r * kM1W + c] = d;
+                    if(core)
+                    {
+                        shifted(a0.lastDepth[1], sh_arena)[o] = d;
+                        shifted(a0.nextDepth[1], sh_arena)[o] = d;
+                    }
+                }
+                else
+                {
+                    const unsigned char v = tile_pyr_down_u8<2>(img == 1 ? sl : sn, rows, cols, x, y);
                     (img == 1 ? li1 : ni1)[r * kM1P8 + c] = v;
                     if(core) shifted(img == 1 ? a0.lastImage[1] : a0.nextImage[1], sh_arena)[o] = v;
                 }
@@ -931,16 +1012,35 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
             if(x < cols2 && y < rows2)
             {
                 const int o = y * cols2 + x;
-                if(img == 0)
+                if(!window_interior_gauss(rows1, cols1, x, y))
+                    border_list[1][atomicAdd(&border_n[1], 1)] = (unsigned short)t;
+                else if(img == 0)
                 {
-                    const float d = tile_pyr_down_f(TileSrc<float, kM1W>(d1, r1o, c1o), rows1, cols1, x, y);
+                    const float d = tile_pyr_down_f<1>(TileSrc<float, kM1W>(d1, r1o, c1o), rows1, cols1, x, y);
                     shifted(a0.lastDepth[2], sh_arena)[o] = d;
                     shifted(a0.nextDepth[2], sh_arena)[o] = d;
                 }
                 else
                     shifted(img == 1 ? a0.lastImage[2] : a0.nextImage[2], sh_arena)[o] =
-                        tile_pyr_down_u8(TileSrc<unsigned char, kM1P8>(img == 1 ? li1 : ni1, r1o, c1o), rows1, cols1, x, y);
+                        tile_pyr_down_u8<1>(TileSrc<unsigned char, kM1P8>(img == 1 ? li1 : ni1, r1o, c1o), rows1, cols1, x, y);
             }
+        }
+        __syncthreads();
+        if(t < border_n[1])
+        {
+            const int item = border_list[1][t];
+            const int img = item / kPx2, k = item - img * kPx2;
+            const int x = X0 / 4 + (k & 15), y = Y0 / 4 + (k >> 4);
+            const int o = y * cols2 + x;
+            if(img == 0)
+            {
+                const float d = tile_pyr_down_f<2>(TileSrc<float, kM1W>(d1, r1o, c1o), rows1, cols1, x, y);
+                shifted(a0.lastDepth[2], sh_arena)[o] = d;
+                shifted(a0.nextDepth[2], sh_arena)[o] = d;
+            }
+            else
+                shifted(img == 1 ? a0.lastImage[2] : a0.nextImage[2], sh_arena)[o] =
+                    tile_pyr_down_u8<2>(TileSrc<unsigned char, kM1P8>(img == 1 ? li1 : ni1, r1o, c1o), rows1, cols1, x, y);
         }
     }
     else
@@ -993,7 +1093,23 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                 const int r = idx / kD1W, c = idx - r * kD1W;
                 const int x = c1o + c, y = r1o + r;
                 if(x < 0 || x >= cols1 || y < 0 || y >= rows1) continue;
-                const unsigned short d = tile_pyr_down_u16(s0, rows, cols, x, y);
+                if(!window_interior_u16(rows, cols, x, y))
+                {
+                    border_list[0][atomicAdd(&border_n[0], 1)] = (unsigned short)idx;
+                    continue;
+                }
+                const unsigned short d = tile_pyr_down_u16<1>(s0, rows, cols, x, y);
+                z1[r * kD1P + c] = d;
+                if(r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2) dst1[y * cols1 + x] = d;
+            }
+            __syncthreads();
+            const int nb = border_n[0];
+            for(int k = t; k < nb; k += kPrepThreads)
+            {
+                const int idx = border_list[0][k];
+                const int r = idx / kD1W, c = idx - r * kD1W;
+                const int x = c1o + c, y = r1o + r;
+                const unsigned short d = tile_pyr_down_u16<2>(s0, rows, cols, x, y);
                 z1[r * kD1P + c] = d;
                 if(r >= 2 && r < 2 + kTileH / 2 && c >= 2 && c < 2 + kTileW / 2) dst1[y * cols1 + x] = d;
             }
@@ -1016,10 +1132,25 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
                 const int x = X2 + c, y = Y2 + r;
                 if(x < cols2 && y < rows2)
                 {
-                    const unsigned short d = tile_pyr_down_u16(s1, rows1, cols1, x, y);
-                    z2[r * kD2P + c] = d;
-                    if(r < kTileH / 4 && c < kTileW / 4) dst2[y * cols2 + x] = d;
+                    if(!window_interior_u16(rows1, cols1, x, y))
+                        border_list[1][atomicAdd(&border_n[1], 1)] = (unsigned short)t;
+                    else
+                    {
+                        const unsigned short d = tile_pyr_down_u16<1>(s1, rows1, cols1, x, y);
+                        z2[r * kD2P + c] = d;
+                        if(r < kTileH / 4 && c < kTileW / 4) dst2[y * cols2 + x] = d;
+                    }
                 }
+            }
+            __syncthreads();
+            if(t < border_n[1])
+            {
+                const int q = border_list[1][t];
+                const int r = q / kD2W, c = q - r * kD2W;
+                const int x = X2 + c, y = Y2 + r;
+                const unsigned short d = tile_pyr_down_u16<2>(s1, rows1, cols1, x, y);
+                z2[r * kD2P + c] = d;
+                if(r < kTileH / 4 && c < kTileW / 4) dst2[y * cols2 + x] = d;
             }
         }
         __syncthreads();
@@ -1030,6 +1161,20 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
             if(u < cols2 && v < rows2)
                 tile_vertex_normal(s2, u, v, rows2, cols2, a0.fx_inv[2], a0.fy_inv[2], a0.cx[2], a0.cy[2], a0.depthCutoff, shifted(a0.vcurr[2], sh_arena),
                                     shifted(a0.ncurr[2], sh_arena));
+        }
+    }
+    if(a0.dbg)
+    {
+        __syncthreads();
+        if(t == 0)
+        {
+            unsigned long long t1;
+            unsigned sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            a0.dbg[3 * blockIdx.x + 0] = dbg_t0;
+            a0.dbg[3 * blockIdx.x + 1] = t1;
+            a0.dbg[3 * blockIdx.x + 2] = sm;
         }
     }
 }
@@ -1435,8 +1580,29 @@ int launch_prepare_frame(PrepFrameArgs & a, cudaStream_t s, int nseq)
         SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k_prepare_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, kDyn));
         attr_set = true;
     }
+    static const bool debug = getenv("SLAM_PREP_DEBUG") != nullptr;
+    static unsigned long long * dbg = nullptr;
+    static int dbg_calls = 0;
+    a.dbg = nullptr;
+    if(debug && nseq == 1)
+    {
+        if(!dbg) SLAM_CUDA_TRY(cudaMalloc((void **)&dbg, sizeof(unsigned long long) * 3 * 1024));
+        a.dbg = dbg;
+    }
     k_prepare_frame<<<dim3(blocks, nseq), kPrepThreads, kDyn, s>>>(a);
     SLAM_CUDA_TRY(cudaGetLastError());
+    if(a.dbg && ++dbg_calls == 40)
+    {
+        // per block: start and duration in ns relative to the first block, SM
+        std::vector<unsigned long long> hbuf(3 * blocks);
+        SLAM_CUDA_TRY(cudaStreamSynchronize(s));
+        SLAM_CUDA_TRY(cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * 3 * blocks, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for(int b = 0; b < blocks; b++) t0 = hbuf[3 * b] < t0 ? hbuf[3 * b] : t0;
+        for(int b = 0; b < blocks; b++)
+            fprintf(stderr, "prep block %3d role %c tile %3d sm %3d start %6llu dur %6llu\n", b, b < a.model_blocks ? 'm' : 'd', b < a.model_blocks ? b : b - a.model_blocks,
+                    (int)hbuf[3 * b + 2], hbuf[3 * b] - t0, hbuf[3 * b + 1] - hbuf[3 * b]);
+    }
     return SLAM_OK;
 }
 

@@ -130,6 +130,7 @@ def load_library():
     lib.slam_odom_peer_connect.argtypes = [vp, i, i, vp]
     lib.slam_odom_score_poses_best_peers.argtypes = [vp, i, i, i, i, f, fp, fp, fp, fp, C.POINTER(C.c_ulonglong)]
     lib.slam_odom_set_profiling.argtypes = [vp, i]
+    lib.slam_odom_set_split_launch.argtypes = [vp, i, C.POINTER(C.c_int)]
     lib.slam_odom_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), i]
     lib.slam_odom_get_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
     lib.slam_odom_stream.argtypes = [vp]
@@ -406,6 +407,12 @@ class RGBDOdometry:
                                                                    _fptr(t) if len(t) else None, _fptr(r) if len(r) else None, C.byref(key)))
         return int(key.value)
 
+    def set_split_launch(self, on=True) -> bool:
+        """Cluster (SO3 pre-alignment) + fine-level kernel pair instead of one cooperative launch per frame; returns the previous setting."""
+        prev = C.c_int(0)
+        _check(self.lib, self.lib.slam_odom_set_split_launch(self._h, int(on), C.byref(prev)))
+        return bool(prev.value)
+
     def set_profiling(self, on=True):
         _check(self.lib, self.lib.slam_odom_set_profiling(self._h, int(on)))
 
@@ -416,7 +423,7 @@ class RGBDOdometry:
         return ms.value, n.value
 
     PHASES = ("staging", "so3 rest", "step set-up", "rgb assoc", "icp map", "icp reduce + count wait", "rgb products+reduce", "sums wait", "solve", "end barrier", "tail",
-              "so3 map", "so3 reduce+post", "so3 wait", "so3 update", "launches", "stage L0", "stage L1", "stage L2", "stage L3", "stage so3 images")
+              "so3 map", "so3 reduce+post", "so3 wait", "so3 update", "launches", "stage L0", "stage L1", "stage L2", "stage L3", "stage so3 images", "hand-off wait", "ns: fine kernel start", "ns: hand-off seen")
 
     def get_phase_cycles(self, reset=False):
         """-> ({phase: SM cycles of the persistent kernel's leading CTA}, launches) accumulated since the last reset."""

@@ -870,3 +870,40 @@ def test_jump_guard_returns_the_prior_pose(setup):
     t_mine, R_mine = results["icp+rgb", "mine"]
     assert np.array_equal(t_ref, A[:3, 3]) and np.array_equal(R_ref, A[:3, :3]), f"reference: the guard was not triggered (moved {np.linalg.norm(t_ref - A[:3, 3]):.3f} m)"
     assert np.array_equal(t_mine, A[:3, 3]) and np.array_equal(R_mine, A[:3, :3]), f"the guard did not restore the prior pose (moved {np.linalg.norm(t_mine - A[:3, 3]):.3f} m)"
+
+
+def test_split_launch_equals_single_launch_and_reference(setup):
+    """The cluster + fine-level kernel pair (SO3 pre-alignment on one thread-block cluster through distributed shared memory, hand-off
+    of the rotation to the kernel that runs the pyramid levels) against the one-launch form of the same loop and the reference's own
+    kernels (RGBDOdometryef.cpp:267-595), on consecutive frames so that the lastNextImage / nextImage swap after every SO3 call is
+    exercised by both.  The launch counter proves which form ran."""
+    split, ref = new_pair(setup)
+    single, _ = new_pair(setup)
+    assert split.set_split_launch(True) in (True, False)
+    single.set_split_launch(False)
+    fr0, d0 = device_frame(setup, 299)
+    first = d0["rgba"]
+    for n, k in enumerate(range(300, 306)):
+        fr, d = device_frame(setup, k)
+        l0s, l01 = split.launch_count(), single.launch_count()
+        ts, rs = run_frame(split, d, first_rgb=first if n == 0 else None, so3=True)
+        t1, r1 = run_frame(single, d, first_rgb=first if n == 0 else None, so3=True)
+        tr, rr = run_frame(ref, d, first_rgb=first if n == 0 else None, so3=True)
+        assert split.launch_count() - l0s == single.launch_count() - l01 + 1, "the split form is one launch more per frame"
+        assert np.abs(ts - t1).max() < POSE_TOL and np.abs(rs - r1).max() < POSE_TOL, (k, ts, t1)
+        assert np.abs(ts - tr).max() < POSE_TOL and np.abs(rs - rr).max() < POSE_TOL, (k, ts, tr)
+        ss, s1 = split.stats(), single.stats()
+        assert ss.gn_iterations == s1.gn_iterations == 19
+        assert ss.so3_iterations == s1.so3_iterations and ss.so3_iterations >= 1
+        assert close_count(ss.lastICPCount, s1.lastICPCount) and close_count(ss.lastRGBCount, s1.lastRGBCount)
+        assert abs(ss.lastSO3Error - s1.lastSO3Error) <= 1e-4 * max(1.0, abs(s1.lastSO3Error))
+        assert ss.lastSO3Count == s1.lastSO3Count
+    # calls that do not qualify keep the one-launch form: no SO3 step, ICP only
+    fr, d = device_frame(setup, 306)
+    l0 = split.launch_count()
+    ta, ra = run_frame(split, d, so3=False, icpWeight=100.0)
+    l1 = split.launch_count()
+    tb, rb = run_frame(single, d, so3=False, icpWeight=100.0)
+    assert np.abs(ta - tb).max() == 0 and np.abs(ra - rb).max() == 0, "same kernel, same bits"
+    for o in (split, single, ref):
+        o.close()
