@@ -552,6 +552,37 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
     __syncthreads();
 }
 
+// End of a sequence: the jump guard and lastRGBError (seq_end), then the result block of the sequence in DEVICE memory.  Only the
+// fields this call computes are written -- the reference's lastICPError / lastRGBError / lastSO3Error are members that keep their
+// value across calls which do not run that term -- so the block always holds the current statistics and the host fetches it when
+// somebody asks (slam_odom_get_stats / _get_covariance), not once per frame.  Lane 0.
+static __device__ __noinline__ void seq_end_merge(GnShared & sh, const bool icp, const bool rgb, const bool rgb_only, const bool so3, GnResult * out)
+{
+    seq_end(sh, rgb, rgb_only, nullptr);
+    if(!out) return;
+    for(int k = 0; k < 9; k++) out->Rcurr[k] = sh.Rcurr[k];
+    for(int k = 0; k < 3; k++) out->tcurr[k] = sh.tcurr[k];
+    if(icp)
+    {
+        out->lastICPError = sh.res.lastICPError;
+        out->lastICPCount = sh.res.lastICPCount;
+    }
+    if(rgb)
+    {
+        out->lastRGBError = sh.res.lastRGBError;
+        out->lastRGBCount = sh.res.lastRGBCount;
+    }
+    if(so3)
+    {
+        out->lastSO3Error = sh.res.lastSO3Error;
+        out->lastSO3Count = sh.res.lastSO3Count;
+    }
+    for(int k = 0; k < 36; k++) out->lastA[k] = sh.res.lastA[k];
+    for(int k = 0; k < 6; k++) out->lastb[k] = sh.res.lastb[k];
+    out->so3_iterations = sh.res.so3_iterations;
+    out->gn_iterations = sh.res.gn_iterations;
+}
+
 // ------------------------------------------------------------------ the kernel
 // ICP / RGB / RGB_ONLY: the mode of the call (RGBDOdometryef.cpp:275-276), compile-time so that each variant carries only its
 // own phases.  GEN = false is the product's common case and the one tuned for instruction footprint: every level resident,
@@ -1337,25 +1368,20 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             if(threadIdx.x < 6) dst[threadIdx.x] = src[threadIdx.x];   // Rcurr[9] | tcurr[3]
             __threadfence_system();
             __syncwarp();
-            if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + seq) = host_seqno;
+            // an inter-CTA wait that gave up poisons the flag: the host reports an error instead of this pose
+            if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + seq) = wk.timeouts ? (host_seqno | 0x80000000u) : host_seqno;
         }
-        if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
-        __syncthreads();
-        if(threadIdx.x == 0)
+        // ... the statistics (lastA, lastb, errors, counts) stay in device memory (results[seq]); the host fetches them on demand: no
+        // second trip to host memory at the end of the kernel
+        if(rank == 0)
         {
-            if(wk.timeouts) sh.res.gn_iterations = -1;   // an inter-CTA wait gave up: the host turns this into an error
-            seq_end(sh, RGB, RGB_ONLY, leader ? &results[seq] : nullptr);
-        }
-        if(rank == 0 && host_results && warp0)   // `leader` is thread 0 of the group's first CTA: all of its warp 0 copies
-        {
-            // ... then the statistics (lastA, lastb, errors, counts) and a second flag (host_flags[batch + seq])
-            __syncwarp();
-            const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
-            uint2 * dst = reinterpret_cast<uint2 *>(host_results + seq);
-            for(int k = threadIdx.x + 6; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
-            __threadfence_system();
-            __syncwarp();
-            if(threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(host_flags + L.batch + seq) = host_seqno;
+            if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
+            __syncthreads();
+            if(threadIdx.x == 0)
+            {
+                if(wk.timeouts) sh.res.gn_iterations = -1;   // the host turns this into an error
+                seq_end_merge(sh, ICP, RGB, RGB_ONLY, L.so3 || ROLE == 2, &results[seq]);
+            }
         }
         if(GEN && leader && L.trace) trace_count[seq] = ntr;
         __syncthreads();

@@ -160,6 +160,7 @@ struct slam_odom
     bool have_depth_tmp = false;
     bool pending_async = false;
     bool last_icp = false, last_rgb = false, last_so3 = false;
+    bool pend_icp = false, pend_rgb = false, pend_so3 = false;   // terms computed by the launches whose statistics have not been merged into `stats` yet
     bool deriv_src_swapped = false;   // the frame the stale derivative images would belong to sits in lastNextImage (swap after an SO3 call)
     bool deriv_stale = true;          // dIdx / dIdy do not belong to the current nextImage pyramid (the persistent kernel derived its own gradients)
     long long launches = 0;
@@ -1038,6 +1039,7 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     int rc;
     if(streaming)
     {
+        if(int rc2 = resolve_stats(h)) return rc2;   // (statistics of an earlier zero-copy launch: the D2H copy below replaces h_results)
         GnSeqIn * in = nullptr;
         rc = gn_stage_inputs(h->gn, L, h->seq.data(), trans, rot, &in);
         if(rc) return rc;
@@ -1051,8 +1053,15 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     else
     {
         const bool zc = h->zero_copy && !h->trace_on;
-        if(int rc2 = resolve_stats(h)) return rc2;   // the launch reuses the mapped result block
-        if(zc) h->zc_seqno++;
+        // zero-copy launches leave their statistics in the device-side result block, which merges from launch to launch (only the terms
+        // a call computes are written): nothing to collect per frame.  A launch whose results follow by a D2H copy replaces h_results.
+        if(!zc)
+            if(int rc2 = resolve_stats(h)) return rc2;
+        if(zc)
+        {
+            h->zc_seqno = (h->zc_seqno + 1) & 0x7fffffffu;   // bit 31 of the completion flag marks a failed launch
+            if(!h->zc_seqno) h->zc_seqno = 1;
+        }
         rc = gn_enqueue(h->gn, L, h->seq.data(), trans, rot, h->h_results, h->stream, zc ? h->h_flags : nullptr, h->zc_seqno);
         h->zc_pending = zc && rc == SLAM_OK;
         h->launches += h->gn.last_launches;
@@ -1062,6 +1071,9 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     h->last_icp = icp;
     h->last_rgb = rgb;
     h->last_so3 = so3 != 0;
+    h->pend_icp = h->pend_icp || icp;
+    h->pend_rgb = h->pend_rgb || rgb;
+    h->pend_so3 = h->pend_so3 || so3 != 0;
     return SLAM_OK;
 }
 
@@ -1083,7 +1095,9 @@ static int wait_zero_copy(slam_odom_t h, int which = 0)
                 for(int b = 0; b < h->batch; b++)
                     if(flags[b] != h->zc_seqno)
                     {
-                        set_last_error("persistent kernel finished without publishing its results");
+                        set_last_error(flags[b] == (h->zc_seqno | 0x80000000u)
+                                           ? "persistent kernel: a wait between thread blocks timed out; the results of this track are invalid"
+                                           : "persistent kernel finished without publishing its results");
                         return SLAM_ERR_CUDA;
                     }
                 break;
@@ -1115,17 +1129,17 @@ static int copy_stats(slam_odom_t h)
             return SLAM_ERR_CUDA;
         }
         slam_odom_stats & st = h->stats[b];
-        if(h->last_icp)
+        if(h->pend_icp)
         {
             st.lastICPError = r.lastICPError;
             st.lastICPCount = r.lastICPCount;
         }
-        if(h->last_rgb)
+        if(h->pend_rgb)
         {
             st.lastRGBError = r.lastRGBError;
             st.lastRGBCount = r.lastRGBCount;
         }
-        if(h->last_so3)
+        if(h->pend_so3)
         {
             st.lastSO3Error = r.lastSO3Error;
             st.lastSO3Count = r.lastSO3Count;
@@ -1135,6 +1149,7 @@ static int copy_stats(slam_odom_t h)
         st.so3_iterations = r.so3_iterations;
         st.gn_iterations = r.gn_iterations;
     }
+    h->pend_icp = h->pend_rgb = h->pend_so3 = false;
     return SLAM_OK;
 }
 
@@ -1142,7 +1157,9 @@ static int resolve_stats(slam_odom_t h)
 {
     if(!h->stats_lazy) return SLAM_OK;
     h->stats_lazy = false;
-    if(int rc = wait_zero_copy(h, 1)) return rc;
+    // the persistent kernel keeps the result blocks in device memory: wait for its last instructions, fetch them
+    SLAM_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    SLAM_CUDA_TRY(cudaMemcpy(h->h_results, h->gn.results, sizeof(GnResult) * h->batch, cudaMemcpyDeviceToHost));
     return copy_stats(h);
 }
 

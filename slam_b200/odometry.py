@@ -306,12 +306,22 @@ class RGBDOdometry:
             t = np.zeros(3 * self.batch, np.float32)
             r = np.zeros(9 * self.batch, np.float32)
             buf = self._io = (t, r, t.ctypes.data_as(_FP), r.ctypes.data_as(_FP))
+            self._r33 = r.reshape(3, 3) if self.batch == 1 else None
         return buf
+
+    def _pose_in(self, t, r, trans, rot):
+        # the common single-sequence call: (3,) and (3, 3) float32 arrays go straight into the call buffers
+        if self._r33 is not None and type(trans) is np.ndarray and type(rot) is np.ndarray and trans.shape == (3,) and rot.shape == (3, 3):
+            t[:] = trans
+            self._r33[:] = rot
+            return True
+        t[:] = np.asarray(trans, dtype=np.float32).reshape(-1)
+        r[:] = np.asarray(rot, dtype=np.float32).reshape(-1)
+        return False
 
     def _track(self, fn, frame, trans, rot, rgbOnly, icpWeight, pyramid, fastOdom, so3, next_frame=None):
         t, r, tp, rp = self._io_buffers()
-        t[:] = np.asarray(trans, dtype=np.float32).reshape(-1)
-        r[:] = np.asarray(rot, dtype=np.float32).reshape(-1)
+        fast = self._pose_in(t, r, trans, rot)
         flags = (1 if rgbOnly else 0, float(icpWeight), 1 if pyramid else 0, 1 if fastOdom else 0, 1 if so3 else 0)
         if next_frame is None:
             rc = fn(self._h, C.byref(frame), tp, rp, *flags)
@@ -319,6 +329,8 @@ class RGBDOdometry:
             rc = fn(self._h, C.byref(frame), C.byref(next_frame), tp, rp, *flags)
         if rc != 0:
             _check(self.lib, rc)
+        if fast:
+            return t.copy(), self._r33.copy()
         return t.reshape(np.shape(trans)).copy(), r.reshape(np.shape(rot)).copy()
 
     def track_device(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True):
@@ -332,12 +344,13 @@ class RGBDOdometry:
     def track_sensor(self, frame, trans, rot, rgbOnly=False, icpWeight=10.0, pyramid=True, fastOdom=False, so3=True, next_frame=None):
         """The reference's data flow: frame.depth / frame.rgba in (pinned) host memory, the model prediction in device memory."""
         t, r, tp, rp = self._io_buffers()
-        t[:] = np.asarray(trans, dtype=np.float32).reshape(-1)
-        r[:] = np.asarray(rot, dtype=np.float32).reshape(-1)
+        fast = self._pose_in(t, r, trans, rot)
         rc = self.lib.slam_odom_track_sensor(self._h, C.byref(frame), C.byref(next_frame) if next_frame is not None else None, tp, rp, 1 if rgbOnly else 0,
                                              float(icpWeight), 1 if pyramid else 0, 1 if fastOdom else 0, 1 if so3 else 0)
         if rc != 0:
             _check(self.lib, rc)
+        if fast:
+            return t.copy(), self._r33.copy()
         return t.reshape(np.shape(trans)).copy(), r.reshape(np.shape(rot)).copy()
 
     def prefetch_host(self, frame):
