@@ -421,8 +421,10 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "k_gn_persistent", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "us_per_launch": gn_us, "launches": int(gn_launches),
                          "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": (gn_ms / dev_ms) if dev_ms else None,
-                         "note": "one launch = all SO3 + 19 ICP/RGB iterations of a frame; the 45 MB working set stays in the 126 MB L2, so DRAM traffic is far "
-                                 "below the algorithmic bytes and the kernel is latency-bound (grid barriers + fp64 solves), not bandwidth-bound"},
+                         "launch_shape": "split: SO3 on one 16-CTA cluster + fine-level kernel on the other SMs, timed as one bracket" if launches == 3 * args.steps else "one cooperative launch",
+                         "note": "one bracket = all SO3 + 19 ICP/RGB iterations of a frame (split launch: the cluster kernel and the fine-level kernel that runs "
+                                 "next to it); the 45 MB working set stays in the 126 MB L2, so DRAM traffic is far below the algorithmic bytes and the path "
+                                 "is latency-bound (a chain of 23-29 dependent reductions + fp64 solves), not bandwidth-bound"},
             "batched": batched,
             "other_configs": extras,
             "cpu_baseline": cpu,
