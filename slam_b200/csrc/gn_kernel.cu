@@ -604,7 +604,13 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     constexpr bool CL = ROLE == 1;
     // the fine-level kernel may start as soon as every CTA of the cluster is resident (it does not wait for this grid's memory:
     // what it needs from here arrives through GnCtl::handoff)
-    if(CL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // The cluster itself is launched as a programmatic dependent of the kernel in front of it (the frame preparation releases its
+    // dependents when it starts): its CTAs take their SMs as that grid drains and wait here for its completion and memory.
+    if(CL)
+    {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     const int group = blockIdx.x / G;
     const int rank = blockIdx.x - group * G;   // CL: grid = one cluster, so this is %cluster_ctarank
@@ -1761,13 +1767,16 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         ca.blockDim = dim3(kGnThreads);
         ca.dynamicSmemBytes = (size_t)La.dyn_bytes;
         ca.stream = stream;
-        cudaLaunchAttribute aa[1];
+        cudaLaunchAttribute aa[2];
         aa[0].id = cudaLaunchAttributeClusterDimension;
         aa[0].val.clusterDim.x = kClusterCtas;
         aa[0].val.clusterDim.y = 1;
         aa[0].val.clusterDim.z = 1;
+        aa[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        aa[1].val.programmaticStreamSerializationAllowed = 1;
         ca.attrs = aa;
-        ca.numAttrs = 1;
+        static const bool chain = !(getenv("SLAM_GN_PDL_CHAIN") && atoi(getenv("SLAM_GN_PDL_CHAIN")) == 0);
+        ca.numAttrs = chain ? 2 : 1;
         cudaError_t e = cudaLaunchKernelExC(&ca, (const void *)gn_pick_split_kernel(L, d.phases, 1), args_a);
         if(e == cudaSuccess)
         {

@@ -733,6 +733,9 @@ __global__ void __launch_bounds__(kPrepThreads, 2) k_prepare_frame(const PrepFra
     __shared__ unsigned short border_list[2][kBorderListMax];
     const int t = threadIdx.x;
     if(t < 2) border_n[t] = 0;
+    // the kernel behind this one (the SO3 cluster of the split Gauss-Newton launch) may take its SMs while this grid drains; it waits
+    // for this grid's completion itself (griddepcontrol.wait) before it reads anything
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     unsigned long long dbg_t0 = 0ull;
     if(a0.dbg && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     // batched launch: byte offsets of this sequence (zero for a single sequence)

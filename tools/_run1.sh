@@ -1,6 +1,11 @@
-mkdir -p gpurun_out/prof
-# 1) launch list of the bench command itself (cold, serialised)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/prof/launches.csv python bench.py --steps 20 --warmup 3 --no-baselines --no-batched > gpurun_out/prof/launches_bench.log 2>&1
-# 2) full captures: one frame's three kernels (prepare, cluster, fine levels) after warm-up
-ncu --set full --import-source on --clock-control none -k regex:"k_prepare_frame|k_gn_persistent" -s 30 -c 3 -o gpurun_out/prof/r02_split python bench.py --steps 10 --warmup 3 --no-baselines --no-batched > gpurun_out/prof/full_bench.log 2>&1
-ls -la gpurun_out/prof
+mkdir -p gpurun_out
+for chain in 1 0 1 0; do
+(SLAM_GN_PDL_CHAIN=$chain timeout 600 python bench.py --steps 500 --warmup 20 --no-baselines --no-batched) > gpurun_out/t11_bench_$chain.json 2> gpurun_out/t11_bench_$chain.err
+python - gpurun_out/t11_bench_$chain.json <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["roofline"]["us_per_launch"], d["check"])
+PY
+done
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/t11_gputests.log 2>&1
+tail -5 gpurun_out/t11_gputests.log | head -2
