@@ -820,12 +820,12 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                     unsigned long long v;
                     do
                     {
-                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&ctl->handoff_seq) : "memory");
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(&ctl->handoff_seq[seq]) : "memory");
                     } while(v != handoff_seq && ++spin < kSpinCap);
                     if(spin >= kSpinCap) wk.timeouts = 1;
                 }
                 __syncwarp();
-                const GnHandoff * ho = &ctl->handoff;
+                const GnHandoff * ho = &ctl->handoff[seq];
                 const uint2 * src = reinterpret_cast<const uint2 *>(&ho->res);
                 uint2 * dst = reinterpret_cast<uint2 *>(&sh.res);
                 for(int k = lane; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = __ldcg(src + k);
@@ -1328,7 +1328,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             // ---- hand the running state to the fine-level kernel
             if(rank == 0 && warp0)
             {
-                GnHandoff * ho = &ctl->handoff;
+                GnHandoff * ho = &ctl->handoff[seq];
                 const uint2 * src = reinterpret_cast<const uint2 *>(&sh.res);
                 uint2 * dst = reinterpret_cast<uint2 *>(&ho->res);
                 for(int k = lane; k < (int)(sizeof(GnResult) / sizeof(uint2)); k += 32) dst[k] = src[k];
@@ -1343,9 +1343,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
                 }
                 __threadfence();
                 __syncwarp();
-                if(lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ctl->handoff_seq), "l"(handoff_seq) : "memory");
+                if(lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&ctl->handoff_seq[seq]), "l"(handoff_seq) : "memory");
             }
-            break;   // one sequence
+            __syncthreads();   // the next sequence re-initialises the state the hand-off was copied from
+            continue;
         }
 
         // ---- the pose goes out first: the caller is released ~4 us before the statistics are complete
@@ -1529,6 +1530,7 @@ static int gn_init_device(GnDevice & d)
     for(GnKernel k : kAllGnKernels) SLAM_CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_limit));
     const char * sp = getenv("SLAM_GN_SPLIT");
     d.split = sp ? atoi(sp) : 1;
+    if(const char * sm = getenv("SLAM_GN_SEQ_MAX")) d.seq_max = atoi(sm);
     if(d.split)
         for(GnKernel k : kClusterGnKernels)
             if(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
@@ -1543,7 +1545,15 @@ static int gn_init_device(GnDevice & d)
 }
 
 static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool cluster);
+static bool gn_make_split(GnDevice & d, const GnLaunch & L, GnLaunch & La, GnLaunch & Lb);
 int gn_configure(GnDevice & d) { return gn_init_device(d); }
+
+bool gn_split_applies(GnDevice & d, const GnLaunch & L)
+{
+    if(gn_init_device(d) != SLAM_OK) return false;
+    GnLaunch La, Lb;
+    return !L.trace && !L.full_corres && gn_make_split(d, L, La, Lb);
+}
 
 bool gn_make_plan(GnDevice & d, GnLaunch & L)
 {
@@ -1633,7 +1643,7 @@ static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool
 // two shared-memory plans.  Returns false when the launch does not qualify (then the whole frame runs in one launch).
 static bool gn_make_split(GnDevice & d, const GnLaunch & L, GnLaunch & La, GnLaunch & Lb)
 {
-    if(d.split != 1 || d.split_broken || L.batch != 1 || L.rgb_only || !L.icp || L.trace || L.full_corres) return false;
+    if(d.split != 1 || d.split_broken || L.batch > kSplitMaxSeqs || (L.batch > 1 && (L.batch < 3 || L.batch > d.seq_max)) || L.rgb_only || !L.icp || L.trace || L.full_corres) return false;
     if(d.num_sms < kClusterCtas + 32) return false;
     // Which levels go with the SO3 pre-alignment onto the cluster: by default none.  Measured (tools/iter_cost.py): an ICP+RGB iteration
     // of the 160x120 level costs 6.8 us on the 16 CTAs of a cluster against 5.2 us on 38 CTAs with the reduction words in L2 (the
@@ -1727,11 +1737,16 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     // the tuned variant needs every level (and the SO3 images) resident and no step trace
     bool general = L.trace || L.full_corres || (L.so3 && !L.so3_resident);
     for(int l = 0; l < L.levels; l++) general = general || (L.iterations[l] > 0 && !L.plan[l].resident);
+    // the split pair has its own shared-memory plans (132 CTAs for ALL sequences of a small batch, where the one-launch form would give
+    // every sequence a fraction of the CTAs and stream its fine levels)
     GnLaunch La, Lb;
-    const bool split = !general && gn_make_split(d, L, La, Lb);
+    const bool split = !L.trace && !L.full_corres && gn_make_split(d, L, La, Lb);
     if(split)
     {
+        // one group for the whole batch: the pair works through the sequences one after the other (the cluster runs ahead with the
+        // SO3 pre-alignments, the fine-level kernel finds every hand-off waiting but the first)
         G = d.num_sms - kClusterCtas;
+        groups = 1;
         Lc = Lb;
     }
     // every launch raises the check-in counter of each group by G (GN_GATE)
@@ -1808,9 +1823,16 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
             // no cluster on this device / in this context: one launch for the whole frame, from now on
             cudaGetLastError();
             d.split_broken = 1;
+            if(general && L.derive_gradients)
+            {
+                // (the caller planned for resident levels and made no derivative images; its next call plans without the pair)
+                set_last_error("the cluster launch of the split Gauss-Newton pair failed; call again");
+                return SLAM_ERR_CUDA;
+            }
             d.last_launches = 1;
             d.gate_total -= (unsigned long long)G;
             G = gn_group_size(d.num_sms, L.batch);
+            groups = L.batch >= d.num_sms ? d.num_sms : L.batch;
             d.gate_total += (unsigned long long)G;
             gate_target = d.gate_total;
             Lc = L;

@@ -53,6 +53,7 @@ struct GnSeqIn
 
 // What the coarse-level kernel (one thread-block cluster: SO3 pre-alignment + the small pyramid levels) hands to the fine-level
 // kernel that runs next to it (split launch, gn_kernel.cu): the state that carries over from one level to the next.
+constexpr int kSplitMaxSeqs = 16;      // sequences one split launch pair works through, one after the other
 struct GnHandoff
 {
     GnResult res;
@@ -67,9 +68,10 @@ struct GnCtl
     unsigned long long arrived[kGnMaxCtas + 1];   // per CTA group: CTAs that have checked in, summed over all launches (GN_GATE)
     unsigned timeouts;               // polls that gave up (a lost arrival would otherwise hang the GPU): non-zero = results invalid
     unsigned long long phase_cycles[24];   // SM cycles the leading CTA spent per phase, accumulated over launches (slam_odom_get_phase_cycles)
-    // split launch: written by the leading CTA of the cluster, then handoff_seq = number of the launch (release); polled by the fine-level kernel
-    alignas(16) GnHandoff handoff;
-    unsigned long long handoff_seq;
+    // split launch, per sequence: written by the leading CTA of the cluster, then handoff_seq = number of the launch (release); polled
+    // by the fine-level kernel
+    alignas(16) GnHandoff handoff[kSplitMaxSeqs];
+    unsigned long long handoff_seq[kSplitMaxSeqs];
     unsigned long long dbg_t[4];     // phase accounting only: [0] = %globaltimer at the start of the cluster kernel
 };
 
@@ -141,6 +143,9 @@ struct GnDevice
     unsigned long long gate_total = 0;  // check-ins every group's counter has seen so far (grows by the group size of each launch)
     int split = -1;                 // SLAM_GN_SPLIT: 1 = cluster + fine-level launch pair where it applies (default), 0 = one launch
     int last_launches = 1;          // kernels the last gn_enqueue put into the stream (2 for a split launch)
+    int seq_max = 8;                // SLAM_GN_SEQ_MAX: batches of 3 .. seq_max sequences run as ONE split launch pair, sequence after sequence
+                                    // (measured, frames/s at 2 / 3 / 4 / 8 / 12 / 16 sequences: pair 5430 / 5460 / 5470 / 5640 / 5720 / 5740, against 5710 / 3730
+                                    // for concurrent CTA groups at 2 / 3 and 4040 / 5100 / 6450 / 7170 for the streaming engine at 4 / 8 / 12 / 16)
     int split_broken = 0;           // the device refused the cluster / programmatic launch once: stay with one launch
     bool phases = false;            // SLAM_GN_PHASES: launch the variants with per-phase cycle accounting
     bool so3_swapped = false;
@@ -154,6 +159,8 @@ struct GnDevice
 int gn_fold_profile(GnDevice & d);
 // One-time device set-up of the persistent kernel (attributes, limits, environment switches); idempotent.
 int gn_configure(GnDevice & d);
+// Would this launch (levels / geom / iterations / batch / mode / trace flags set) run as the split pair?
+bool gn_split_applies(GnDevice & d, const GnLaunch & L);
 
 size_t gn_state_bytes(int batch, int num_sms);
 void gn_bind_state(GnDevice & d, char * base, int batch, int num_sms);

@@ -978,7 +978,12 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
         set_last_error("so3 pre-alignment needs pyramid level 2 (num_levels >= 3)");
         return SLAM_ERR_UNSUPPORTED;
     }
-    const bool streaming = h->batch >= h->be_min && h->trace_level < 2;   // many sequences: lock-step streaming launches
+    // A few sequences with the SO3 step: ONE split launch pair works through them one after the other (gn_kernel.cu) -- at 8
+    // sequences per GPU that beats both the streaming engine (too few sequences to fill its ~140 launches) and concurrent CTA groups.
+    gn_configure(h->gn);
+    const bool seq_split = h->batch >= 3 && h->batch <= h->gn.seq_max && h->batch <= kSplitMaxSeqs && so3 && icp && !rgb_only && !h->trace_on &&
+                           h->gn.split == 1 && !h->gn.split_broken;
+    const bool streaming = h->batch >= h->be_min && h->trace_level < 2 && !seq_split;   // many sequences: lock-step streaming launches
     GnLaunch L = {};
     L.levels = h->levels;
     L.batch = h->batch;
@@ -989,7 +994,9 @@ static int enqueue_device_loop(slam_odom_t h, const float * trans, const float *
     L.rgb_only = rgb_only != 0;
     L.so3 = so3 != 0;
     // shared-memory plan of the persistent kernel: which levels keep their operands resident
-    const bool all_resident = streaming ? false : gn_make_plan(h->gn, L);
+    L.trace = h->trace_on;
+    L.full_corres = h->trace_level >= 2;
+    const bool all_resident = streaming ? false : (gn_make_plan(h->gn, L) || gn_split_applies(h->gn, L));
     // Derivative images are only materialised when something reads them from memory: a test tap / trace, or a level that
     // streams its operands.  Otherwise the persistent kernel derives the two gradients of its own pixels from nextImage
     // while staging them (same arithmetic, bit-identical).

@@ -907,3 +907,43 @@ def test_split_launch_equals_single_launch_and_reference(setup):
     assert np.abs(ta - tb).max() == 0 and np.abs(ra - rb).max() == 0, "same kernel, same bits"
     for o in (split, single, ref):
         o.close()
+
+
+@pytest.mark.parametrize("B", [3, 8])
+def test_sequential_split_batch_equals_single_sequences(setup, B):
+    """A few sequences with the SO3 step run as ONE split launch pair that works through them one after the other (the cluster kernel runs
+    ahead with the SO3 pre-alignments, the fine-level kernel takes every hand-off over): the same kernels on the same CTAs with the same
+    shared-memory plan as a single sequence, so every sequence of the batch must come out with the bits of its single-sequence run --
+    over two consecutive frames, so that the per-sequence lastNextImage / nextImage swap is exercised too.  B = 8 is above the
+    streaming engine's threshold: the launch counter proves that the pair ran (3 launches per frame)."""
+    i = setup["intr"]
+    t = setup["torch"]
+    ks = [150 + 90 * b for b in range(B)]
+    stack = lambda frames, key: t.from_numpy(np.stack([(f[key].view(np.int16) if f[key].dtype == np.uint16 else f[key]) for f in frames])).to("cuda:0")
+    first = np.stack([setup["scene"].render_frame(setup["poses"][k - 1])[1] for k in ks])
+    ob = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"], batch=B)
+    ob.initFirstRGB(t.from_numpy(first).to("cuda:0"))
+    singles = []
+    for b in range(B):
+        o = setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+        o.initFirstRGB(t.from_numpy(first[b]).to("cuda:0"))
+        singles.append(o)
+    for step in range(2):
+        frames = [frame_pair(setup["scene"], setup["poses"], k + step) for k in ks]
+        depth, rgba, mv, mn, mrgba = (stack(frames, k) for k in ("depth", "rgba", "mv", "mn", "mrgba"))
+        P = np.stack([f["model_pose"] for f in frames])
+        fr = ob.make_frame(depth, rgba, mv, mn, mrgba, P, 3.0, 20.0)
+        l0 = ob.launch_count()
+        tb, rb = ob.track_device(fr, P[:, :3, 3].copy(), P[:, :3, :3].copy())
+        assert ob.launch_count() - l0 == 3, "frame preparation + cluster kernel + fine-level kernel"
+        for b in range(B):
+            d = to_device(frames[b])
+            f1 = singles[b].make_frame(d["depth"], d["rgba"], d["mv"], d["mn"], d["mrgba"], P[b], 3.0, 20.0)
+            t1, r1 = singles[b].track_device(f1, P[b][:3, 3].copy(), P[b][:3, :3].copy())
+            assert np.abs(tb[b] - t1).max() == 0 and np.abs(rb[b] - r1).max() == 0, f"frame {step}, sequence {b}: {tb[b]} vs {t1}"
+            sb, s1 = ob.stats(b), singles[b].stats()
+            assert (sb.so3_iterations, sb.gn_iterations, sb.lastICPCount, sb.lastRGBCount) == (s1.so3_iterations, s1.gn_iterations, s1.lastICPCount, s1.lastRGBCount)
+            err_mm = float(np.linalg.norm(tb[b] - frames[b]["gt_pose"][:3, 3]) * 1e3)
+            assert err_mm < 5.0, f"sequence {b} lost track ({err_mm:.2f} mm)"
+    for o in singles + [ob]:
+        o.close()
