@@ -276,13 +276,9 @@ __device__ __forceinline__ void warp_update_fast(GnShared & sh, const bool icp, 
     // ---- entry `lane` of the combined system -> 6x7 matrix (row stride 8) in shared memory, both triangles
     if(lane < 27)
     {
-        int i = 0, rem = lane;
-        while(rem >= 7 - i)
-        {
-            rem -= 7 - i;
-            i++;
-        }
-        const int jj = i + rem;
+        // row i of the upper triangle that entry `lane` belongs to (rows start at 0, 7, 13, 18, 22, 25), branch-free
+        const int i = (lane >= 7) + (lane >= 13) + (lane >= 18) + (lane >= 22) + (lane >= 25);
+        const int jj = lane - (7 * i - (i * (i - 1)) / 2) + i;
         const float vi = sh.total[lane];
         const float vr = sh.total[32 + lane];
         const double w = icpWeight;
@@ -454,13 +450,8 @@ __device__ __forceinline__ void warp_stats_fast(GnShared & sh, const bool icp)
     const int lane = threadIdx.x & 31;
     if(lane < 27)
     {
-        int i = 0, rem = lane;
-        while(rem >= 7 - i)
-        {
-            rem -= 7 - i;
-            i++;
-        }
-        const int j = i + rem;
+        const int i = (lane >= 7) + (lane >= 13) + (lane >= 18) + (lane >= 22) + (lane >= 25);
+        const int j = lane - (7 * i - (i * (i - 1)) / 2) + i;
         const double v = sh.Ab[lane];
         if(j == 6)
             sh.res.lastb[i] = v;

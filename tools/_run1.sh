@@ -1,8 +1,10 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests -m gpu -x -q -k "sequential_split or split_launch or batch_equals") > gpurun_out/t12_tests.log 2>&1
-tail -15 gpurun_out/t12_tests.log
-for B in 2 3 4 8 12 16; do
-  timeout 120 python tools/batch_time.py $B 40 2>&1 | tail -1
-  SLAM_GN_SEQ_MAX=16 timeout 120 python tools/batch_time.py $B 40 2>&1 | tail -1 | sed 's/^/   seq_max 16: /'
-  SLAM_GN_SEQ_MAX=1 timeout 120 python tools/batch_time.py $B 40 2>&1 | tail -1 | sed 's/^/   seq_max  1: /'
-done
+(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/t15_gputests.log 2>&1
+tail -5 gpurun_out/t15_gputests.log | head -2
+(timeout 600 python bench.py) > gpurun_out/t15_bench.json 2> gpurun_out/t15_bench.err
+python - gpurun_out/t15_bench.json <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e_all_host"]["value"], d["roofline"]["us_per_launch"], d["roofline"]["frac"], d["roofline"]["share_of_step"], d["gpu_launches"], d["batched"]["value"], d["batched"]["roofline"]["frac"], d["cpu_baseline"]["value"], d.get("ref_cuda"))
+for k,v in d["other_configs"].items(): print(k, {a:b for a,b in v.items() if isinstance(b,(int,float))})
+PY
