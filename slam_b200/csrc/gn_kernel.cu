@@ -583,6 +583,17 @@ static __device__ __noinline__ void seq_end_merge(GnShared & sh, const bool icp,
     out->gn_iterations = sh.res.gn_iterations;
 }
 
+// The intrinsics of a level and their inverse, prepared by the host (same routine, same bits as level_begin of gn_scalar.cuh).  Lanes 0..8 of warp 0.
+__device__ __forceinline__ void level_begin_from(GnShared & sh, const GnLaunch & L, const int lvl)
+{
+    const int lane = threadIdx.x & 31;
+    if(lane < 9)
+    {
+        sh.K[lane] = L.K[lvl][lane];
+        sh.Kinv[lane] = L.Kinv[lvl][lane];
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // ICP / RGB / RGB_ONLY: the mode of the call (RGBDOdometryef.cpp:275-276), compile-time so that each variant carries only its
 // own phases.  GEN = false is the product's common case and the one tuned for instruction footprint: every level resident,
@@ -727,11 +738,15 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const LevelGeom g = L.geom[2];
             const int N = g.rows * g.cols;
             const int Pn = L.so3_P;
-            if(threadIdx.x == 0)
+            if(warp0)
             {
-                level_begin(sh, g);
-                so3_prepare(sh);
-                wk.P = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
+                level_begin_from(sh, L, 2);
+                __syncwarp();
+                if(threadIdx.x == 0)
+                {
+                    so3_prepare(sh);
+                    wk.P = level_ptrs(L.batch == 1, seq0, seqs, seq, 2);
+                }
             }
             __syncthreads();
 #pragma unroll 1
@@ -869,10 +884,10 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const bool part = rank < Pn;
             if(warp0)
             {
+                level_begin_from(sh, L, lvl);
                 if(threadIdx.x == 0)
                 {
                     sh.res.lastRGBError = FLT_MAX;
-                    level_begin(sh, L.geom[lvl]);
                     wk.P = level_ptrs(L.batch == 1, seq0, seqs, seq, lvl);
                     wk.lv_n_icp = resident ? wk.n_icp[lvl] : 0;
                     wk.lv_n_rgb = resident ? wk.n_rgb[lvl] : 0;
@@ -1365,6 +1380,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             for(int k = 0; k < 9; k++) sh.res.Rcurr[k] = sh.Rcurr[k];
             for(int k = 0; k < 3; k++) sh.res.tcurr[k] = sh.tcurr[k];
         }
+        if(rank == 0) __syncthreads();   // the guarded pose is final: warp 0 sends it out while warp 1 does the statistics
         if(rank == 0 && host_results && warp0)
         {
             // The result block goes straight to mapped host memory, followed by a per-sequence flag the host polls: the caller has
@@ -1380,11 +1396,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         }
         // ... the statistics (lastA, lastb, errors, counts) stay in device memory (results[seq]); the host fetches them on demand: no
         // second trip to host memory at the end of the kernel
-        if(rank == 0)
+        if(rank == 0 && wid == 1)
         {
-            if(warp0 && sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
-            __syncthreads();
-            if(threadIdx.x == 0)
+            if(sh.res.gn_iterations > 0) warp_stats_fast(sh, ICP);   // lastA / lastb / ICP error of the last step
+            __syncwarp();
+            if(lane == 0)
             {
                 if(wk.timeouts) sh.res.gn_iterations = -1;   // the host turns this into an error
                 seq_end_merge(sh, ICP, RGB, RGB_ONLY, L.so3 || ROLE == 2, &results[seq]);
@@ -1622,6 +1638,13 @@ static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool
             L.so3_resident = 1;
             L.off_so3 = take(bytes);
         }
+    }
+    for(int l = 0; l < L.levels; l++)
+    {
+        double K[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        K[0] = L.geom[l].fx; K[4] = L.geom[l].fy; K[2] = L.geom[l].cx; K[5] = L.geom[l].cy; K[8] = 1;   // k_matrix_d
+        smath::mat3_inverse(K, L.Kinv[l]);
+        for(int k = 0; k < 9; k++) L.K[l][k] = K[k];
     }
     L.off_cl = 0;
     if(cluster)

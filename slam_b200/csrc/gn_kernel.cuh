@@ -120,6 +120,8 @@ struct GnLaunch
     int off_cl;              // split launch, cluster kernel: the ClArea
     int dyn_bytes;
     int poll_delay;          // cycles between posting a contribution and the first poll
+    double K[SLAM_MAX_LEVELS][9], Kinv[SLAM_MAX_LEVELS][9];   // intrinsics of every level and their inverse (gn_make_plan; the kernels used to
+                                                              // form them with one thread at every level change, on the chain)
     int ph_role;             // phase accounting: 0 = both kernels of a split launch add their cycles, 1 / 2 = only that role
 };
 
