@@ -1,11 +1,6 @@
-mkdir -p gpurun_out
-(time timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/t16_gputests.log 2>&1
-tail -5 gpurun_out/t16_gputests.log | head -2
-for i in 1 2; do
-(timeout 600 python bench.py --steps 1000 --warmup 20 --no-baselines --no-batched) > gpurun_out/t16_bench.json 2> gpurun_out/t16_bench.err
-python - gpurun_out/t16_bench.json <<'PY'
+for pd in 500 700 900 1100 1300; do
+SLAM_GN_POLL_DELAY=$pd timeout 300 python bench.py --steps 400 --warmup 20 --no-baselines --no-batched 2>/dev/null | python -c "
 import json,sys
-d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["us_per_launch"], d["roofline"]["frac"], d["gpu_launches"])
-PY
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('poll delay $pd:', round(d['value'],1), round(d['roofline']['us_per_launch'],2), round(d['e2e']['value'],1))"
 done
