@@ -361,7 +361,10 @@ __device__ __forceinline__ void rgb_candidate_segment(const ResidualArgs & a, co
     bool ok = live && (x < a.cols - 5 && y < a.rows - 1);
 #pragma unroll
     for(int r = 0; r < 4; r++) ok = ok && (((w[r] - 0x01010101u) & ~w[r] & 0x80808080u) == 0u);
-    if(derive)
+    ok = ok && !isnan(d1);
+    // the gradient is only needed where the other tests passed; pixels without depth come in regions (beyond the cut-off, holes), so
+    // whole segments skip it
+    if(derive && __any_sync(0xffffffffu, ok))
     {
         if(x >= 1 && y >= 1 && x < a.cols - 1 && y < a.rows - 1)
         {
@@ -384,7 +387,7 @@ __device__ __forceinline__ void rgb_candidate_segment(const ResidualArgs & a, co
     }
     const int valx = gx, valy = gy;
     const float mTwo = (valx * valx) + (valy * valy);
-    ok = ok && (mTwo >= a.minScale) && !isnan(d1);
+    ok = ok && (mTwo >= a.minScale);
     cand = ok;
     d1o = d1;
     gxy = ((unsigned)(unsigned short)gx) | (((unsigned)(unsigned short)gy) << 16);
@@ -409,6 +412,36 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
     const int nslots = (pl.segs_per_cta + kGnWarps - 1) / kGnWarps;   // <= kMaxStageSlots (gn_make_plan); cap = segs_per_cta * 32
     const unsigned lt = (1u << lane) - 1u;
     const bool aligned = (g.cols & 31) == 0;   // every 32-pixel segment lies in one row and starts at a multiple of 32 columns
+    // The ICP operands are plain copies (global -> their uncompacted place in the list): cp.async puts every one of them in flight up
+    // front, with no register and no wait in the segment loop below, whose round trips to L2 they used to share; what the loop needs
+    // from them (does the pixel survive?) is read back from shared memory afterwards.
+    if(icp)
+    {
+#pragma unroll 1
+        for(int m = 0; m < nslots; m++)
+        {
+            const int j = m * kGnWarps + wid;
+            if(j >= pl.segs_per_cta) break;
+            const int seg = j * pl.P + rank;
+            const int u = m * kGnThreads + (int)threadIdx.x;
+            const int k1 = seg * 32 + lane;
+            if(seg < pl.nseg && k1 < plane)
+            {
+#pragma unroll
+                for(int q = 0; q < 3; q++)
+                {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(icp_list + q * pl.cap + u)), "l"(P.vcurr + q * plane + k1) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(icp_list + (3 + q) * pl.cap + u)), "l"(P.ncurr + q * plane + k1) : "memory");
+                }
+            }
+            else
+            {
+#pragma unroll
+                for(int q = 0; q < 6; q++) icp_list[q * pl.cap + u] = SLAM_QNAN;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     {
         ResidualArgs ra;
         ra.minScale = L.min_scale[lvl];
@@ -427,23 +460,6 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
             const int kk = l1[0] ? k1[0] : 0;
             const int y1[1] = {kk / g.cols};
             const int x1[1] = {kk - y1[0] * g.cols};
-            bool fi = false;
-            if(icp)
-            {
-                float v[6];
-#pragma unroll
-                for(int q = 0; q < 3; q++)
-                {
-                    v[q] = l1[0] ? __ldg(P.vcurr + q * plane + kk) : SLAM_QNAN;
-                    v[3 + q] = l1[0] ? __ldg(P.ncurr + q * plane + kk) : SLAM_QNAN;
-                }
-                fi = !isnan(v[0]) && !isnan(v[3]);
-                if(j < pl.segs_per_cta)
-                {
-#pragma unroll
-                    for(int q = 0; q < 6; q++) icp_list[q * pl.cap + u] = v[q];
-                }
-            }
             bool c1[1] = {false};
             if(rgb)
             {
@@ -463,14 +479,27 @@ __device__ __forceinline__ void stage_level(const GnLaunch & L, const bool icp, 
                     rgb_xyi[u] = c1[0] ? ((unsigned)x1[0] | ((unsigned)y1[0] << 11) | (i1[0] << 22)) : 0u;
                 }
             }
-            const unsigned bi = __ballot_sync(0xffffffffu, fi);
             const unsigned br = __ballot_sync(0xffffffffu, c1[0]);
-            if(lane == 0)
-            {
-                wk.scan_cnt[0][m * kGnWarps + wid] = __popc(bi);
-                wk.scan_cnt[1][m * kGnWarps + wid] = __popc(br);
-            }
+            if(lane == 0) wk.scan_cnt[1][m * kGnWarps + wid] = __popc(br);
         }
+    }
+    if(icp)
+    {
+        // the copies have landed: survivors per (slot, warp) from the staged vertex / normal x planes
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll 1
+        for(int m = 0; m < nslots; m++)
+        {
+            const int u = m * kGnThreads + (int)threadIdx.x;
+            const bool exists = m * kGnWarps + wid < pl.segs_per_cta;
+            const bool fi = exists && !isnan(icp_list[u]) && !isnan(icp_list[3 * pl.cap + u]);
+            const unsigned bi = __ballot_sync(0xffffffffu, fi);
+            if(lane == 0) wk.scan_cnt[0][m * kGnWarps + wid] = __popc(bi);
+        }
+    }
+    else if(lane == 0)
+    {
+        for(int m = 0; m < nslots; m++) wk.scan_cnt[0][m * kGnWarps + wid] = 0;
     }
     __syncthreads();
     if(wid < 2)
