@@ -1684,9 +1684,12 @@ static bool gn_make_plan_for(GnDevice & d, GnLaunch & L, const int G, const bool
     L.dyn_bytes = off;
     L.poll_delay = d.poll_delay;
     {
-        const char * ph = getenv("SLAM_GN_PHASES");
-        L.ph_role = ph ? atoi(ph) - 1 : 0;
-        if(L.ph_role < 0 || L.ph_role > 2) L.ph_role = 0;
+        static const int ph_role = [] {
+            const char * ph = getenv("SLAM_GN_PHASES");
+            const int r = ph ? atoi(ph) - 1 : 0;
+            return (r < 0 || r > 2) ? 0 : r;
+        }();
+        L.ph_role = ph_role;
     }
     return all_rgb_resident;
 }
