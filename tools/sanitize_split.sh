@@ -13,6 +13,8 @@ run() { # name tool command...
 for tool in memcheck racecheck synccheck; do
     run gn_split_pair_batch1 $tool python tools/sanitize_driver.py gn1
     run gn_split_pair_frame_call $tool --kernel-name kns=k_gn_persistent python tools/sanitize_driver.py frame1
+    # eight sequences through ONE pair, one after the other (per-sequence hand-over blocks, restaged lists)
+    run gn_split_pair_8seq $tool --kernel-name kns=k_gn_persistent python tools/sanitize_driver.py frame8
     run prepare_frame_border_lists_1seq $tool --kernel-name kns=k_prepare_frame python tools/sanitize_driver.py frame1
     run prepare_frame_border_lists_8seq $tool --kernel-name kns=k_prepare_frame python tools/sanitize_driver.py frame8
 done
