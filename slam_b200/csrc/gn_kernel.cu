@@ -26,6 +26,8 @@
 #include <cfloat>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <mutex>
 #include "gn_kernel.cuh"
 #include "gn_scalar.cuh"
 #include "gn_fast_math.cuh"
@@ -1538,8 +1540,36 @@ int gn_fold_profile(GnDevice & d)
     return SLAM_OK;
 }
 
+// The fine-level kernel of a split pair is not a cooperative launch (a cooperative launch cannot be a programmatic dependent): its
+// CTAs are placed one by one.  Two pairs of two HANDLES in flight on one GPU could therefore each hold a part of the SMs and wait
+// for the other's (the waits are bounded, so that would end in two errors, not in a hang -- but it must not happen).  When more
+// than one handle lives on a device, every pair is ordered behind the previous pair of any other handle with an event; a single
+// handle (the normal case: several sequences belong in ONE batched handle) pays nothing.
+struct PairGate
+{
+    std::mutex m;
+    std::atomic<int> handles{0};
+    cudaEvent_t last = nullptr;
+    const GnDevice * owner = nullptr;
+};
+static PairGate g_pair_gate[64];
+
 void gn_release(GnDevice & d)
 {
+    if(d.gate_member && d.device >= 0 && d.device < 64)
+    {
+        PairGate & g = g_pair_gate[d.device];
+        std::lock_guard<std::mutex> lock(g.m);
+        g.handles--;
+        if(g.owner == &d)
+        {
+            g.owner = nullptr;
+            g.last = nullptr;
+        }
+        d.gate_member = false;
+    }
+    if(d.pair_done) cudaEventDestroy(d.pair_done);
+    d.pair_done = nullptr;
     for(auto e : d.ev) cudaEventDestroy(e);
     d.ev.clear();
     if(d.h_stage) cudaFreeHost(d.h_stage);
@@ -1552,6 +1582,12 @@ static int gn_init_device(GnDevice & d)
     SLAM_CUDA_TRY(cudaMallocHost((void **)&d.h_stage, d.stage_bytes));
     int dev = 0;
     SLAM_CUDA_TRY(cudaGetDevice(&dev));
+    d.device = dev;
+    if(!d.gate_member && dev >= 0 && dev < 64)
+    {
+        g_pair_gate[dev].handles++;
+        d.gate_member = true;
+    }
     SLAM_CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
     int coop = 0;
     SLAM_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1826,6 +1862,15 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
         fprintf(stderr, "\n");
     }
     d.last_launches = 1;
+    // several handles on this device: pairs of different handles run one after the other (see PairGate)
+    static const bool gate_off = getenv("SLAM_GN_PAIR_GATE") && atoi(getenv("SLAM_GN_PAIR_GATE")) == 0;   // development aid
+    PairGate * gate = (split && !gate_off && d.device >= 0 && d.device < 64 && g_pair_gate[d.device].handles.load() > 1) ? &g_pair_gate[d.device] : nullptr;
+    std::unique_lock<std::mutex> gate_lock;
+    if(gate)
+    {
+        gate_lock = std::unique_lock<std::mutex>(gate->m);
+        if(gate->last && gate->owner != &d) SLAM_CUDA_TRY(cudaStreamWaitEvent(stream, gate->last, 0));
+    }
     if(split)
     {
         d.last_launches = 2;
@@ -1896,6 +1941,13 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     }
     else
         SLAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kernel, dim3(G * groups), dim3(kGnThreads), args, (size_t)L.dyn_bytes, stream));
+    if(gate)
+    {
+        if(!d.pair_done) SLAM_CUDA_TRY(cudaEventCreateWithFlags(&d.pair_done, cudaEventDisableTiming));
+        SLAM_CUDA_TRY(cudaEventRecord(d.pair_done, stream));
+        gate->last = d.pair_done;
+        gate->owner = &d;
+    }
     if(d.profiling)
     {
         SLAM_CUDA_TRY(cudaEventRecord(e1, stream));

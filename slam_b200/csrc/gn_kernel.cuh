@@ -151,6 +151,9 @@ struct GnDevice
     int split_broken = 0;           // the device refused the cluster / programmatic launch once: stay with one launch
     bool phases = false;            // SLAM_GN_PHASES: launch the variants with per-phase cycle accounting
     bool so3_swapped = false;
+    int device = -1;                // CUDA device of the handle (pair gate below)
+    bool gate_member = false;
+    cudaEvent_t pair_done = nullptr;   // recorded behind every split launch pair when several handles share the device
     // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // start/stop pairs of launches not yet folded into the totals

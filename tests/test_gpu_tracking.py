@@ -947,3 +947,51 @@ def test_sequential_split_batch_equals_single_sequences(setup, B):
             assert err_mm < 5.0, f"sequence {b} lost track ({err_mm:.2f} mm)"
     for o in singles + [ob]:
         o.close()
+
+
+def test_two_handles_with_pairs_in_flight_on_one_gpu(setup):
+    """Two handles on one GPU enqueue their split launch pairs back to back (asynchronous form) before either is collected.  The
+    fine-level kernel of a pair is not a cooperative launch, so two pairs in flight could each hold a part of the SMs; the library
+    orders pairs of different handles behind each other with an event (gn_kernel.cu: PairGate).  Every pose must equal the one a
+    single handle produces alone, over several frames, and no wait may time out."""
+    t = setup["torch"]
+    scene, poses = setup["scene"], setup["poses"]
+    i = setup["intr"]
+    mk = lambda: setup["Odo"](i["width"], i["height"], i["cx"], i["cy"], i["fx"], i["fy"])
+    seqs = [(300, 301, 302, 303), (620, 621, 622, 623)]
+    frames = [[to_device(frame_pair(scene, poses, k)) for k in ks] for ks in seqs]
+    firsts = [t.from_numpy(scene.render_frame(poses[ks[0] - 1])[1]).to("cuda:0") for ks in seqs]
+    t.cuda.synchronize()
+
+    def prepare(o, d):
+        o.initICPModel(d["mv"], d["mn"], 20.0, d["model_pose"])
+        o.initRGBModel(d["mrgba"])
+        o.initICP(d["depth"], 3.0)
+        o.initRGB(d["rgba"])
+
+    want = []
+    for s in range(2):
+        o = mk()
+        o.initFirstRGB(firsts[s])
+        res = []
+        for d in frames[s]:
+            prepare(o, d)
+            P = d["model_pose"]
+            res.append(o.getIncrementalTransformation(P[:3, 3].copy(), P[:3, :3].copy(), False, 10.0, True, False, True))
+        want.append(res)
+        o.close()
+    a, b = mk(), mk()
+    a.initFirstRGB(firsts[0])
+    b.initFirstRGB(firsts[1])
+    for n in range(len(frames[0])):
+        for o, s in ((a, 0), (b, 1)):
+            d = frames[s][n]
+            prepare(o, d)
+            P = d["model_pose"]
+            o.getIncrementalTransformationAsync(P[:3, 3].copy(), P[:3, :3].copy(), False, 10.0, True, False, True)
+        got = (a.wait(), b.wait())
+        for s in range(2):
+            assert np.array_equal(got[s][0], want[s][n][0]) and np.array_equal(got[s][1], want[s][n][1]), f"handle {s}, frame {n}"
+    assert a.stats().gn_iterations == 19 and b.stats().gn_iterations == 19
+    a.close()
+    b.close()
