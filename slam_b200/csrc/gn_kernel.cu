@@ -691,11 +691,29 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     // before all have (the check is made after the staging, when it has long been true)
     if(!CL && threadIdx.x == 0) red_u64(&ctl->arrived[group], 1ull);
     bool gate_open = CL;   // the cluster does not use the reduction words
-    if(CL)
+    // nobody stores into a peer's shared memory before that peer is running: every CTA arrives here, and waits for the others only
+    // right before the first all-reduce (by then they have long arrived)
+    bool cl_start_pending = CL;
+    if(CL) cl_arrive();
+    // (iii) the SO3 images of the first sequence go on their way before anything else (cp.async, collected where they are needed)
+    bool so3_images_hoisted = false;
+    if(CL && L.so3 && L.so3_resident && rank < L.so3_P)
     {
-        // nobody stores into a peer's shared memory before that peer is running
-        cl_arrive();
-        cl_wait();
+        const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, group, 2);
+        const int N = L.geom[2].rows * L.geom[2].cols;
+        if((N & 15) == 0)
+        {
+            unsigned char * s_last = reinterpret_cast<unsigned char *>(dyn + L.off_so3);
+            unsigned char * s_next = s_last + ((N + 15) & ~15);
+#pragma unroll 1
+            for(int q = threadIdx.x; q < N / 16; q += kGnThreads)
+            {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_last + 16 * q)), "l"(P2.lastNextImage + 16 * q) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_next + 16 * q)), "l"(P2.nextImage + 16 * q) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            so3_images_hoisted = true;
+        }
     }
 #define GN_GATE() do { if(!gate_open) { if(threadIdx.x == 0) { int spin_ = 0; while(ld_u64_relaxed(&ctl->arrived[group]) < gate_target && ++spin_ < kSpinCap) {} if(spin_ >= kSpinCap) wk.timeouts = 1; } __syncthreads(); gate_open = true; } } while(0)
 
@@ -721,7 +739,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
 #pragma unroll
                 for(int k = 0; k < 3; k++) tp[k] = seqs[seq].tprev[k];
             }
-            seq_begin_pose(sh, Rp, tp);
+            seq_begin_pose<false>(sh, Rp, tp);
+        }
+        else if(wid == 1)
+        {
+            for(int k = lane; k < (int)(sizeof(GnResult) / sizeof(int)); k += 32) reinterpret_cast<int *>(&sh.res)[k] = 0;
         }
         __syncthreads();
 
@@ -739,7 +761,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const int N = L.geom[2].rows * L.geom[2].cols;
             unsigned char * s_last = reinterpret_cast<unsigned char *>(dyn + L.off_so3);
             unsigned char * s_next = s_last + ((N + 15) & ~15);
-            if((N & 15) == 0)
+            if(so3_images_hoisted && seq == group)
+            {
+                asm volatile("cp.async.wait_all;" ::: "memory");   // issued at the start of the kernel
+            }
+            else if((N & 15) == 0)
             {
 #pragma unroll 1
                 for(int q = threadIdx.x; q < N / 16; q += kGnThreads)
@@ -761,6 +787,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
         }
         GN_PHASE(20);
         GN_GATE();
+        if(CL && cl_start_pending)
+        {
+            cl_wait();
+            cl_start_pending = false;
+        }
         GN_PHASE(0);
 
         // ------------------------------------------------ SO3 pre-alignment, level 2

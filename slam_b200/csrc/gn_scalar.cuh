@@ -533,6 +533,8 @@ __device__ __forceinline__ void gn_sigma(GnShared & sh, const bool rgb_only, sla
 }
 
 // lane 0.  The prior pose arrives by value (registers): the persistent kernel reads it from its parameter block.
+// CLEAR_RES = false: the caller clears sh.res itself (the persistent kernel does it with another warp meanwhile).
+template <bool CLEAR_RES = true>
 __device__ __forceinline__ void seq_begin_pose(GnShared & sh, const float (&Rp)[9], const float (&tp)[3])
 {
 #pragma unroll
@@ -547,7 +549,7 @@ __device__ __forceinline__ void seq_begin_pose(GnShared & sh, const float (&Rp)[
     }
     sh.lastError = FLT_MAX / 2;
     sh.lastCount = FLT_MAX / 2;
-    memset(&sh.res, 0, sizeof(sh.res));
+    if(CLEAR_RES) memset(&sh.res, 0, sizeof(sh.res));
     sh.stop = 0;
     sh.rgb_sigma_last = 0;
     sh.rgb_count_last = -1;
