@@ -283,6 +283,9 @@ def run_ours(args, rank, local_rank, world):
     odo.set_profiling(True)
     odo.get_profile(reset=True)
     launches0 = odo.launch_count()
+    import gc
+    gc.collect()
+    gc.disable()      # no collector pause inside the timed regions (a 20-step region lasts 3.5 ms)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
@@ -311,8 +314,10 @@ def run_ours(args, rank, local_rank, world):
 
     # ================= e2e: host buffers through the C ABI =================
     def time_e2e(track, frames_):
+        # the warm-up steps run the same pipeline as the timed ones (the next frame's H2D copies are issued behind this frame's kernels),
+        # so the first timed step finds its inputs prefetched like every later one
         for i in range(args.warmup):
-            track(frames_[i % nf], *priors[i % nf])
+            track(frames_[i % nf], *priors[i % nf], next_frame=frames_[(i + 1) % nf])
         barrier()
         t0 = time.perf_counter()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -335,6 +340,7 @@ def run_ours(args, rank, local_rank, world):
     # pessimistic line: the 11 MB model prediction travels over PCIe as well (slam_odom_track_host)
     e2e_all_ms = time_e2e(odo.track_host, host_frames)
     e2e_all_value = world * args.steps / (e2e_all_ms / 1e3)
+    gc.enable()
 
     # ================= roofline of the dominant kernel =================
     peak, peak_src = measured_peak()
