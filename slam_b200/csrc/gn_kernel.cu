@@ -1564,8 +1564,13 @@ int gn_fold_profile(GnDevice & d)
         SLAM_CUDA_TRY(cudaEventElapsedTime(&ms, d.ev[i], d.ev[i + 1]));
         d.kernel_ms += ms;
         d.kernel_launches++;
-        cudaEventDestroy(d.ev[i]);
-        cudaEventDestroy(d.ev[i + 1]);
+        for(cudaEvent_t e : {d.ev[i], d.ev[i + 1]})
+        {
+            if(d.ev_pool.size() < 8192)
+                d.ev_pool.push_back(e);
+            else
+                cudaEventDestroy(e);   // (the batched engine brings its own events)
+        }
     }
     d.ev.clear();
     return SLAM_OK;
@@ -1603,6 +1608,8 @@ void gn_release(GnDevice & d)
     d.pair_done = nullptr;
     for(auto e : d.ev) cudaEventDestroy(e);
     d.ev.clear();
+    for(auto e : d.ev_pool) cudaEventDestroy(e);
+    d.ev_pool.clear();
     if(d.h_stage) cudaFreeHost(d.h_stage);
     d.h_stage = nullptr;
 }
@@ -1880,8 +1887,16 @@ int gn_enqueue(GnDevice & d, const GnLaunch & L, const SeqBuffers * seqs, const 
     {
         if(d.ev.size() >= 4096)
             if(int rc = gn_fold_profile(d)) return rc;
-        SLAM_CUDA_TRY(cudaEventCreate(&e0));
-        SLAM_CUDA_TRY(cudaEventCreate(&e1));
+        for(cudaEvent_t * e : {&e0, &e1})
+        {
+            if(d.ev_pool.empty())
+                SLAM_CUDA_TRY(cudaEventCreate(e));
+            else
+            {
+                *e = d.ev_pool.back();
+                d.ev_pool.pop_back();
+            }
+        }
         SLAM_CUDA_TRY(cudaEventRecord(e0, stream));
     }
     const GnKernel kernel = split ? gn_pick_split_kernel(L, d.phases, 2) : gn_pick_kernel(L, general, d.phases);

@@ -157,6 +157,7 @@ struct GnDevice
     // optional CUDA-event timing of the persistent kernel (bench.py's roofline numerator)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // start/stop pairs of launches not yet folded into the totals
+    std::vector<cudaEvent_t> ev_pool; // folded events, reused (creating two events per frame showed up as host hiccups in short timed regions)
     double kernel_ms = 0.0;
     long long kernel_launches = 0;
 };
