@@ -167,13 +167,46 @@ __device__ __forceinline__ float cl_fold_col(const ClArea * cl, const int par, c
 
 // Block sum of up to 32 per-thread floats (v[ncols..31] must be 0), posted to the ncols columns starting at word wbase.
 // The caller must reach a __syncthreads() before sh.red is reused.
+// Reduce-scatter of 16 values per lane (v[16..31] unused): lanes 2c and 2c + 1 end with the warp-wide sum of value c.  16 shuffles
+// instead of the 31 of the 32-wide form; fixed pattern.
+template <int W>
+__device__ __forceinline__ void warp_rs16_step(float (&v)[32], const int lane)
+{
+    const bool upper = (lane & (2 * W)) != 0;
+#pragma unroll
+    for(int i = 0; i < W; i++)
+    {
+        const float send = upper ? v[i] : v[i + W];
+        const float keep = upper ? v[i + W] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * W);
+    }
+}
+__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[32])
+{
+    const int lane = threadIdx.x & 31;
+    warp_rs16_step<8>(v, lane);   // lanes with bit 4 keep values 8..15
+    warp_rs16_step<4>(v, lane);
+    warp_rs16_step<2>(v, lane);
+    warp_rs16_step<1>(v, lane);   // value index = lane >> 1
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <bool CL>
 __device__ __forceinline__ void cta_reduce_post(float (&v)[32], GnShared & sh, unsigned long long * ring, unsigned step, int wbase, int ncols, ClArea * cl, const int rank,
                                                 const int csize)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const float s = warp_reduce_scatter32(v);
-    sh.red[wid * 32 + lane] = s;
+    if(CL)
+    {
+        // (the cluster kernel only reduces the 11 SO3 columns here)
+        const float s = warp_reduce_scatter16(v);
+        if((lane & 1) == 0) sh.red[wid * 32 + (lane >> 1)] = s;
+    }
+    else
+    {
+        const float s = warp_reduce_scatter32(v);
+        sh.red[wid * 32 + lane] = s;
+    }
     __syncthreads();
     if(wid == 0)
     {
