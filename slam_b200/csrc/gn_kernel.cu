@@ -732,7 +732,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     bool so3_images_hoisted = false;
     if(CL && L.so3 && L.so3_resident && rank < L.so3_P)
     {
-        const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, group, 2);
+        const LevelPtrs P2 = level_ptrs(L.batch == 1, seq0, seqs, (ROLE != 0 && L.batch > 1) ? L.batch - 1 : group, 2);
         const int N = L.geom[2].rows * L.geom[2].cols;
         if((N & 15) == 0)
         {
@@ -750,7 +750,11 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
     }
 #define GN_GATE() do { if(!gate_open) { if(threadIdx.x == 0) { int spin_ = 0; while(ld_u64_relaxed(&ctl->arrived[group]) < gate_target && ++spin_ < kSpinCap) {} if(spin_ >= kSpinCap) wk.timeouts = 1; } __syncthreads(); gate_open = true; } } while(0)
 
-    for(int seq = group; seq < L.batch; seq += groups)
+    // A split pair that works through several sequences takes them LAST FIRST: the batched preparation in front of it wrote the
+    // sequences in ascending order, so the last ones are what is still in L2 (8 x 45 MB do not fit)
+    const int seq_first = (ROLE != 0 && L.batch > 1) ? L.batch - 1 : group;
+    const int seq_step = (ROLE != 0 && L.batch > 1) ? -1 : groups;
+    for(int seq = seq_first; seq >= 0 && seq < L.batch; seq += seq_step)
     {
         slam_step_record * tr = (GEN && L.trace && leader) ? trace + (size_t)seq * kGnMaxTrace : nullptr;
         int ntr = 0;
@@ -794,7 +798,7 @@ k_gn_persistent(const GnLaunch L, GnCtl * ctl, const GnSeqIn * seqs, const GnSeq
             const int N = L.geom[2].rows * L.geom[2].cols;
             unsigned char * s_last = reinterpret_cast<unsigned char *>(dyn + L.off_so3);
             unsigned char * s_next = s_last + ((N + 15) & ~15);
-            if(so3_images_hoisted && seq == group)
+            if(so3_images_hoisted && seq == seq_first)
             {
                 asm volatile("cp.async.wait_all;" ::: "memory");   // issued at the start of the kernel
             }
